@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""Headline benchmark: fusion forward throughput in HR MPix/s (BASELINE.json metric).
+
+Workload (config.workload = "C3"): BASELINE.json configs[2] -- full-res DIV2K-shape inference,
+510x339 LR -> 2040x1356 HR fusion forward over synthetic cached expert outputs + features,
+random-init weights.  One "step" = one image per GPU (images are independent units: weak
+scaling, no data-path collective -- SURVEY §8e).  configs[1] (training step) needs the backward
+kernels, which are not built yet; configs[0] is the CPU-runnable parity case.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+
+* value : whole-job HR MPix/s with the inputs resident in HBM (CUDA events, barrier + sync on both
+          sides, max over ranks).  The 553 MB of inputs per step exceed the 126 MB L2.
+* e2e   : same metric through forward_with_precomputed with pinned HOST buffers: every step
+          copies the inputs host->device and the SR image device->host inside the timed region.
+* roofline : the dominant kernel (3x3 128->128 refinement conv), algorithmic FLOPs per launch /
+          mean CUDA-event duration of those launches inside the timed region, against the
+          measured bf16 tensor peak of MEASURED_PEAKS.json.
+* cpu_baseline : the oracle (CPU port of the reference forward) on the host cores, rank 0, N=1.
+* --impl reference : the reference's CPU implementation of the path = the oracle port (the
+          reference is pure Python and does not travel to the GPU box), all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LR_H, LR_W = 339, 510                       # config 3
+FLOP_PER_HR_PIXEL = 1_774_222                # SURVEY §8d, whole forward
+HOT_LAYER_FLOP_PER_HR_PIXEL = 2 * 9 * 128 * 128   # one 3x3 128->128 conv
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1371.0), d.get("hbm_gbs", 6555.2), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_throughput(H, W, steps, warmup, threads):
+    """HR MPix/s of the CPU oracle (port of the reference forward) on a LR HxW image."""
+    import torch
+    import isr_b200
+    from oracle import fusion_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    m = isr_b200.CompleteEnhancedFusionSR(None).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    lr, imgs, fts, _ = O.synthetic_inputs(1, H, W)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.run_pipeline(sd, lr, imgs, fts)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return 16 * H * W / t / 1e6, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    h, w = 96, 128                                              # bounded sample of the C3 workload
+    v, t = cpu_oracle_throughput(h, w, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": "fusion_forward_hr_mpix_per_s", "value": v, "unit": "HR MPix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3 fusion forward (BASELINE configs[2]), CPU sample", "lr": [h, w], "hr": [4 * h, 4 * w],
+                   "batch_per_step": 1},
+        "cpu_baseline": {"value": v, "unit": "HR MPix/s", "cores": threads, "kind": "port",
+                         "sample": f"each step = one fp32 oracle forward on a {h}x{w} LR crop-sized synthetic image "
+                                   f"({16 * h * w / 1e6:.3f} HR MPix; the metric is linear in pixels)"},
+        "e2e": {"value": v, "unit": "HR MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("FFSR_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--lr", type=int, nargs=2, default=[LR_H, LR_W], help="LR size (parity/debug runs only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import isr_b200
+    from oracle import fusion_oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the fusion path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    H, W = args.lr
+    B = 1
+
+    torch.manual_seed(0)
+    m = isr_b200.CompleteEnhancedFusionSR(None).eval().to(dev)
+    m.precision = args.precision
+    # images are independent units: rank r takes images r, r+world, ... (seeded per image)
+    lr, imgs, fts, _ = O.synthetic_inputs(B, H, W, seed=1234 + rank)
+    host = {"lr": lr.pin_memory(), "imgs": {k: v.pin_memory() for k, v in imgs.items()},
+            "fts": {k: v.pin_memory() for k, v in fts.items()}}
+    lrd = lr.to(dev)
+    imd = {k: v.to(dev) for k, v in imgs.items()}
+    ftd = {k: v.to(dev) for k, v in fts.items()}
+    h2d = lr.numel() * 4 + sum(v.numel() * 4 for v in imgs.values()) + sum(v.numel() * 4 for v in fts.values())
+    d2h = B * 3 * 16 * H * W * 4
+    mpix_step = B * 16 * H * W / 1e6
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    for _ in range(warmup):
+        sr = m.forward_with_precomputed(lrd, imd, ftd)
+    eng = m._engine
+    hot = [f"rf.{i}" for i in eng._refine_idx[1:-1]]
+    eng.timed_layers = {n: [] for n in hot}
+
+    # ---- timed region: inputs resident in HBM ---------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sr = m.forward_with_precomputed(lrd, imd, ftd)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    launches = eng.launches * args.steps
+    hot_ms = [a.elapsed_time(b) for evs in eng.timed_layers.values() for a, b in evs]
+    eng.timed_layers = None
+
+    # ---- e2e: pinned host buffers, H2D + D2H inside the timed region -----------------------
+    out_host = torch.empty(B, 3, 4 * H, 4 * W).pin_memory()
+
+    def e2e_step():
+        l = host["lr"].to(dev, non_blocking=True)
+        im = {k: v.to(dev, non_blocking=True) for k, v in host["imgs"].items()}
+        ft = {k: v.to(dev, non_blocking=True) for k, v in host["fts"].items()}
+        out_host.copy_(m.forward_with_precomputed(l, im, ft), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+    if rank == 0:
+        tensor_peak, hbm_peak, peak_src = _peaks()
+        hot_flop = HOT_LAYER_FLOP_PER_HR_PIXEL * B * 16 * H * W
+        hot_mean_ms = sum(hot_ms) / max(len(hot_ms), 1)
+        achieved = hot_flop / (hot_mean_ms * 1e-3) / 1e12 if hot_ms else None
+        line = {
+            "metric": "fusion_forward_hr_mpix_per_s", "value": world * mpix_step * args.steps / (ms * 1e-3),
+            "unit": "HR MPix/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "C3 fusion forward (BASELINE configs[2]): 510x339 LR -> 2040x1356 HR, cached "
+                                   "4-expert outputs + features, random-init weights, eval",
+                       "lr": [H, W], "hr": [4 * H, 4 * W], "batch_per_gpu_per_step": B, "precision": args.precision,
+                       "partition": "independent images round-robin over ranks, no collective",
+                       "l2": "per-step inputs (553 MB) and activations exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": world * mpix_step * args.steps / (ms_e2e * 1e-3), "unit": "HR MPix/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                         "frac": (achieved / tensor_peak) if achieved else None, "traffic": None,
+                         "kernel": "3x3 128->128 refinement conv (refine.2/4/6/8), "
+                                   + ("k_conv_ffma<64,3> fp32 CUDA-core path" if args.precision == "fp32" else "tcgen05 implicit GEMM"),
+                         "launch_ms": hot_mean_ms, "launches_timed": len(hot_ms), "flop_per_launch": hot_flop,
+                         "peak_source": peak_src,
+                         "whole_forward_tflops": FLOP_PER_HR_PIXEL * B * 16 * H * W / (ms / args.steps * 1e-3) / 1e12},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            ch, cw = (H, W) if threads >= 16 else (H // 2, W // 2)
+            v, t = cpu_oracle_throughput(ch, cw, 1, 0, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "HR MPix/s", "cores": threads, "kind": "port",
+                                    "sample": f"one fp32 oracle forward, LR {ch}x{cw} ({16 * ch * cw / 1e6:.3f} HR MPix), "
+                                              f"{t:.1f} s on {threads} threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,101 @@
+"""ctypes binding of ``libffsr_b200.so`` (C ABI declared in ``include/ffsr_b200.h``).
+
+Loading never falls back: a missing library raises ``FusionLibraryError`` with the build
+command.  ``check(rc)`` turns a non-zero return code into ``RuntimeError`` carrying
+``ffsr_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libffsr_b200.so")
+
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
+EPI_PLAIN, EPI_RESIDUAL, EPI_LKAGATE = 0, 1, 2
+DT_F32, DT_BF16 = 0, 1
+
+
+class FusionLibraryError(RuntimeError):
+    pass
+
+
+class ConvParams(C.Structure):
+    _fields_ = [
+        ("inp", C.c_void_p),
+        ("in_sN", C.c_longlong), ("in_sY", C.c_longlong), ("in_sX", C.c_longlong), ("in_sC", C.c_longlong),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int), ("ksize", C.c_int),
+        ("w", C.c_void_p), ("bias", C.c_void_p), ("groups", C.c_int),
+        ("out", C.c_void_p),
+        ("out_sN", C.c_longlong), ("out_sY", C.c_longlong), ("out_sX", C.c_longlong),
+        ("act", C.c_int), ("epi", C.c_int),
+        ("r1", C.c_void_p), ("r1_sN", C.c_longlong), ("r1_sY", C.c_longlong), ("r1_sX", C.c_longlong),
+        ("r2", C.c_void_p), ("r2_sN", C.c_longlong), ("r2_sY", C.c_longlong), ("r2_sX", C.c_longlong),
+        ("sa", C.c_float), ("sa_ptr", C.c_void_p),
+        ("sb", C.c_float), ("sb_ptr", C.c_void_p),
+        ("ch_k", C.c_void_p), ("ch_d", C.c_void_p),
+        ("in_dtype", C.c_int), ("out_dtype", C.c_int),
+    ]
+
+
+_P, _I, _L, _LL, _SZ = C.c_void_p, C.c_int, C.c_long, C.c_longlong, C.c_size_t
+
+# name -> (restype, argtypes); the authoritative list of exported symbols (tests check it
+# against include/ffsr_b200.h)
+PROTOTYPES = {
+    "ffsr_last_error": (C.c_char_p, []),
+    "ffsr_version": (C.c_char_p, []),
+    "ffsr_device_check": (_I, []),
+    "ffsr_dct_bands": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ffsr_dwt_sub_size": (_I, [_I, _I, C.POINTER(_I), C.POINTER(_I)]),
+    "ffsr_dwt_bands": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ffsr_fft_twiddles": (_I, [_I, _P, _P]),
+    "ffsr_fft_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ffsr_fft_bands": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _SZ, _P, _P]),
+    "ffsr_crossband_attention": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
+    "ffsr_crossband_out": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "ffsr_lka_depthwise": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ffsr_layernorm": (_I, [_P, _L, _I, _P, _P, _P, _I, _P]),
+    "ffsr_token_attention": (_I, [_P, _I, _I, _L, _I, _P, _I, _P]),
+    "ffsr_gate_finalize": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "ffsr_conv2d": (_I, [C.POINTER(ConvParams), _P]),
+    "ffsr_conv_params_size": (_SZ, []),
+    "ffsr_modulate_hr": (_I, [C.POINTER(_P), _P, _P, _P, _I, _I, _I, _I, _P, _P, _LL, _I, _P]),
+    "ffsr_expert_downsample": (_I, [_P, _I, _I, _I, _P, _LL, _P, _LL, _I, _P]),
+    "ffsr_resize_nhwc": (_I, [_P, _I, _I, _I, _I, _LL, _P, _I, _I, _LL, _I, _P]),
+    "ffsr_spatial_gate": (_I, [_P, _L, _I, _P, _P, _P, _P, _P, _I, _P]),
+    "ffsr_blend_hr": (_I, [_P, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _LL, _P, _LL, _P]),
+    "ffsr_blur_pool": (_I, [_P, _LL, _I, _I, _I, _P, _P, _LL, _P]),
+    "ffsr_laplacian_sub": (_I, [_P, _LL, _P, _LL, _I, _I, _I, _P, _LL, _P]),
+    "ffsr_edge_attn_upsample": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _LL, _I, _P]),
+    "ffsr_final_combine": (_I, [_P, _LL, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the kernel library (once) and attach prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FusionLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C image-super-resolution_b200/csrc`). There is no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError here == symbol not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ffsr_conv_params_size() != C.sizeof(ConvParams):
+        raise FusionLibraryError("ffsr_conv_params layout mismatch between _cabi.py and the built library; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().ffsr_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libffsr_b200 {what} failed (code {rc}): {msg}")

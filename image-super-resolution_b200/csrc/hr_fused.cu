@@ -1,0 +1,550 @@
+// HR-side fused elementwise / resampling kernels (all HBM-bound; one thread per pixel or
+// per pixel x 4-channel group, coalesced planar reads, channels-last vector writes).
+// Each kernel cites the reference op sequence it replaces in include/ffsr_b200.h.
+#include "common.cuh"
+#include "../../include/ffsr_b200.h"
+
+namespace {
+struct Img4 {
+  const float* p[4];
+};
+
+template <typename T>
+__device__ __forceinline__ void store_vec4(T* dst, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store_vec4<float>(float* dst, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store_vec4<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+template <typename T>
+__device__ __forceinline__ float4 load_vec4(const T* src);
+template <>
+__device__ __forceinline__ float4 load_vec4<float>(const float* src) {
+  return *reinterpret_cast<const float4*>(src);
+}
+template <>
+__device__ __forceinline__ float4 load_vec4<__nv_bfloat16>(const __nv_bfloat16* src) {
+  const uint2 u = *reinterpret_cast<const uint2*>(src);
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// Phase 4 tail (modulation heads at HR)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_modulate_hr(Img4 imgs, const float* __restrict__ m32,
+                                                     const float* __restrict__ w2, const float* __restrict__ b2,
+                                                     int B, int H, int W, int clamp01, float* __restrict__ ecol,
+                                                     T* __restrict__ cat3, long long cat3_sX) {
+  __shared__ float sw[4][3][32];
+  __shared__ float sb[4][3];
+  if (m32) {
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) (&sw[0][0][0])[i] = w2[i];
+    if (threadIdx.x < 12) (&sb[0][0])[threadIdx.x] = b2[threadIdx.x];
+  }
+  __syncthreads();
+  const int Hh = 4 * H, Wh = 4 * W;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  if (X >= Wh) return;
+  const long HWh = (long)Hh * Wh;
+  const long pix = (long)Y * Wh + X;
+  const BilinTap ty = bilin_tap(Y, H, Hh), tx = bilin_tap(X, W, Wh);
+  float o[12];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float mod[3] = {0.f, 0.f, 0.f};
+    if (m32) {
+      const float* base = m32 + ((long)(b * 4 + e) * H) * W * 32;
+      const float4* p00 = reinterpret_cast<const float4*>(base + ((long)ty.i0 * W + tx.i0) * 32);
+      const float4* p01 = reinterpret_cast<const float4*>(base + ((long)ty.i0 * W + tx.i1) * 32);
+      const float4* p10 = reinterpret_cast<const float4*>(base + ((long)ty.i1 * W + tx.i0) * 32);
+      const float4* p11 = reinterpret_cast<const float4*>(base + ((long)ty.i1 * W + tx.i1) * 32);
+      mod[0] = sb[e][0]; mod[1] = sb[e][1]; mod[2] = sb[e][2];
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 a = p00[c4], bq = p01[c4], c = p10[c4], d = p11[c4];
+        float g[4];
+        g[0] = gelu_erf(ty.w0 * (tx.w0 * a.x + tx.w1 * bq.x) + ty.w1 * (tx.w0 * c.x + tx.w1 * d.x));
+        g[1] = gelu_erf(ty.w0 * (tx.w0 * a.y + tx.w1 * bq.y) + ty.w1 * (tx.w0 * c.y + tx.w1 * d.y));
+        g[2] = gelu_erf(ty.w0 * (tx.w0 * a.z + tx.w1 * bq.z) + ty.w1 * (tx.w0 * c.z + tx.w1 * d.z));
+        g[3] = gelu_erf(ty.w0 * (tx.w0 * a.w + tx.w1 * bq.w) + ty.w1 * (tx.w0 * c.w + tx.w1 * d.w));
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mod[k] = fmaf(sw[e][k][4 * c4 + i], g[i], mod[k]);
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float v = imgs.p[e][((long)b * 3 + ch) * HWh + pix];
+      if (m32) {
+        v = v * (1.0f + 0.2f * (sigmoid_acc(mod[ch]) - 0.5f));
+        if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+      }
+      o[e * 3 + ch] = v;
+      ecol[((long)(b * 4 + e) * 3 + ch) * HWh + pix] = v;
+    }
+  }
+  if (cat3) {
+    T* dst = cat3 + ((long)b * HWh + pix) * cat3_sX;
+    store_vec4<T>(dst, o[0], o[1], o[2], o[3]);
+    store_vec4<T>(dst + 4, o[4], o[5], o[6], o[7]);
+    store_vec4<T>(dst + 8, o[8], o[9], o[10], o[11]);
+  }
+}
+
+extern "C" int ffsr_modulate_hr(const float* const* imgs, const float* m32, const float* w2, const float* b2, int B,
+                                int H, int W, int clamp01, float* ecol, void* cat3, long long cat3_sX, int cat3_dtype,
+                                cudaStream_t stream) {
+  FFSR_REQUIRE(imgs && imgs[0] && imgs[1] && imgs[2] && imgs[3] && ecol, FFSR_ERR_ARG, "modulate_hr: null pointer");
+  FFSR_REQUIRE(!m32 || (w2 && b2), FFSR_ERR_ARG, "modulate_hr: modulation weights missing");
+  FFSR_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && 4 * H <= 65535, FFSR_ERR_ARG, "modulate_hr: bad shape");
+  const int esz = cat3_dtype == FFSR_DT_BF16 ? 2 : 4;
+  FFSR_REQUIRE(!cat3 || (((uintptr_t)cat3 % 16) == 0 && (cat3_sX * esz) % 16 == 0 && cat3_sX >= 12), FFSR_ERR_ALIGN,
+               "modulate_hr: concat slice must be 16B aligned with a 16B-multiple pixel stride");
+  FFSR_REQUIRE(!m32 || ((uintptr_t)m32 % 16) == 0, FFSR_ERR_ALIGN, "modulate_hr: m32 must be 16B aligned");
+  Img4 im;
+  for (int e = 0; e < 4; ++e) im.p[e] = imgs[e];
+  dim3 grid(ceil_div(4 * W, 128), 4 * H, B);
+  if (cat3_dtype == FFSR_DT_BF16)
+    k_modulate_hr<__nv_bfloat16><<<grid, 128, 0, stream>>>(im, m32, w2, b2, B, H, W, clamp01, ecol, (__nv_bfloat16*)cat3, cat3_sX);
+  else
+    k_modulate_hr<float><<<grid, 128, 0, stream>>>(im, m32, w2, b2, B, H, W, clamp01, ecol, (float*)cat3, cat3_sX);
+  return ffsr_check_launch("modulate_hr");
+}
+
+// ------------------------------------------------------------------------------------------
+// /2 and /4 bilinear (exact 2-tap averages) of the 12-channel expert stack
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_expert_downsample(const float* __restrict__ ecol, int B, int H, int W,
+                                                           T* __restrict__ cat2, long long cat2_sX,
+                                                           T* __restrict__ s1in, long long s1_sX) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  const int Wh = 4 * W;
+  const long HWh = 16L * H * W;
+  float d2[4][12];   // the 2x2 half-res outputs of this LR pixel
+  float d4[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const float* pl = ecol + ((long)b * 12 + k) * HWh + (long)(4 * y) * Wh + 4 * x;
+    const float4 r0 = *reinterpret_cast<const float4*>(pl);
+    const float4 r1 = *reinterpret_cast<const float4*>(pl + Wh);
+    const float4 r2 = *reinterpret_cast<const float4*>(pl + 2 * Wh);
+    const float4 r3 = *reinterpret_cast<const float4*>(pl + 3 * Wh);
+    d2[0][k] = 0.5f * (0.5f * r0.x + 0.5f * r0.y) + 0.5f * (0.5f * r1.x + 0.5f * r1.y);
+    d2[1][k] = 0.5f * (0.5f * r0.z + 0.5f * r0.w) + 0.5f * (0.5f * r1.z + 0.5f * r1.w);
+    d2[2][k] = 0.5f * (0.5f * r2.x + 0.5f * r2.y) + 0.5f * (0.5f * r3.x + 0.5f * r3.y);
+    d2[3][k] = 0.5f * (0.5f * r2.z + 0.5f * r2.w) + 0.5f * (0.5f * r3.z + 0.5f * r3.w);
+    d4[k] = 0.5f * (0.5f * r1.y + 0.5f * r1.z) + 0.5f * (0.5f * r2.y + 0.5f * r2.z);   // centre 2x2
+  }
+  const int W2 = 2 * W;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const long pix = ((long)b * 2 * H + 2 * y + (s >> 1)) * W2 + 2 * x + (s & 1);
+    T* dst = cat2 + pix * cat2_sX;
+    store_vec4<T>(dst, d2[s][0], d2[s][1], d2[s][2], d2[s][3]);
+    store_vec4<T>(dst + 4, d2[s][4], d2[s][5], d2[s][6], d2[s][7]);
+    store_vec4<T>(dst + 8, d2[s][8], d2[s][9], d2[s][10], d2[s][11]);
+  }
+  T* dst = s1in + (((long)b * H + y) * W + x) * s1_sX;
+  store_vec4<T>(dst, d4[0], d4[1], d4[2], d4[3]);
+  store_vec4<T>(dst + 4, d4[4], d4[5], d4[6], d4[7]);
+  store_vec4<T>(dst + 8, d4[8], d4[9], d4[10], d4[11]);
+}
+
+extern "C" int ffsr_expert_downsample(const float* ecol, int B, int Hh, int Wh, void* cat2, long long cat2_sX,
+                                      void* s1in, long long s1_sX, int dtype, cudaStream_t stream) {
+  FFSR_REQUIRE(ecol && cat2 && s1in, FFSR_ERR_ARG, "expert_downsample: null pointer");
+  FFSR_REQUIRE(Hh % 4 == 0 && Wh % 4 == 0 && Hh > 0 && Wh > 0, FFSR_ERR_ARG, "expert_downsample: HR size must be 4x LR");
+  const int esz = dtype == FFSR_DT_BF16 ? 2 : 4;
+  FFSR_REQUIRE(((uintptr_t)cat2 % 16) == 0 && ((uintptr_t)s1in % 16) == 0 && (cat2_sX * esz) % 16 == 0 &&
+                   (s1_sX * esz) % 16 == 0 && ((uintptr_t)ecol % 16) == 0,
+               FFSR_ERR_ALIGN, "expert_downsample: 16B alignment required");
+  const int H = Hh / 4, W = Wh / 4;
+  dim3 grid(ceil_div(W, 128), H, B);
+  if (dtype == FFSR_DT_BF16)
+    k_expert_downsample<__nv_bfloat16><<<grid, 128, 0, stream>>>(ecol, B, H, W, (__nv_bfloat16*)cat2, cat2_sX, (__nv_bfloat16*)s1in, s1_sX);
+  else
+    k_expert_downsample<float><<<grid, 128, 0, stream>>>(ecol, B, H, W, (float*)cat2, cat2_sX, (float*)s1in, s1_sX);
+  return ffsr_check_launch("expert_downsample");
+}
+
+// ------------------------------------------------------------------------------------------
+// generic bilinear resize of a channels-last tensor into a channel slice
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_resize_nhwc(const T* __restrict__ src, int h, int w, int C4, long long src_sX,
+                                                     T* __restrict__ dst, int H, int W, long long dst_sX, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % C4);
+  const long pix = i / C4;
+  const int X = (int)(pix % W), Y = (int)((pix / W) % H);
+  const long n = pix / ((long)W * H);
+  const BilinTap ty = bilin_tap(Y, h, H), tx = bilin_tap(X, w, W);
+  const T* base = src + n * h * w * src_sX + 4 * c4;
+  const float4 a = load_vec4<T>(base + ((long)ty.i0 * w + tx.i0) * src_sX);
+  const float4 b = load_vec4<T>(base + ((long)ty.i0 * w + tx.i1) * src_sX);
+  const float4 c = load_vec4<T>(base + ((long)ty.i1 * w + tx.i0) * src_sX);
+  const float4 d = load_vec4<T>(base + ((long)ty.i1 * w + tx.i1) * src_sX);
+  store_vec4<T>(dst + pix * dst_sX + 4 * c4,
+                ty.w0 * (tx.w0 * a.x + tx.w1 * b.x) + ty.w1 * (tx.w0 * c.x + tx.w1 * d.x),
+                ty.w0 * (tx.w0 * a.y + tx.w1 * b.y) + ty.w1 * (tx.w0 * c.y + tx.w1 * d.y),
+                ty.w0 * (tx.w0 * a.z + tx.w1 * b.z) + ty.w1 * (tx.w0 * c.z + tx.w1 * d.z),
+                ty.w0 * (tx.w0 * a.w + tx.w1 * b.w) + ty.w1 * (tx.w0 * c.w + tx.w1 * d.w));
+}
+
+extern "C" int ffsr_resize_nhwc(const void* src, int N, int h, int w, int C, long long src_sX, void* dst, int H, int W,
+                                long long dst_sX, int dtype, cudaStream_t stream) {
+  FFSR_REQUIRE(src && dst, FFSR_ERR_ARG, "resize_nhwc: null pointer");
+  FFSR_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, FFSR_ERR_ARG, "resize_nhwc: C%%4 != 0 or bad shape");
+  const int esz = dtype == FFSR_DT_BF16 ? 2 : 4;
+  FFSR_REQUIRE(((uintptr_t)src % (4 * esz)) == 0 && ((uintptr_t)dst % (4 * esz)) == 0 && src_sX % 4 == 0 && dst_sX % 4 == 0,
+               FFSR_ERR_ALIGN, "resize_nhwc: vector alignment");
+  const long total = (long)N * H * W * (C / 4);
+  if (dtype == FFSR_DT_BF16)
+    k_resize_nhwc<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, stream>>>((const __nv_bfloat16*)src, h, w, C / 4, src_sX, (__nv_bfloat16*)dst, H, W, dst_sX, total);
+  else
+    k_resize_nhwc<float><<<ceil_div(total, 256), 256, 0, stream>>>((const float*)src, h, w, C / 4, src_sX, (float*)dst, H, W, dst_sX, total);
+  return ffsr_check_launch("resize_nhwc");
+}
+
+// ------------------------------------------------------------------------------------------
+// SpatialGate: y = x * sigmoid(w2 . gelu(W1 x + b1) + b2), one thread per pixel
+// ------------------------------------------------------------------------------------------
+template <typename T, int C>
+__global__ void __launch_bounds__(128) k_spatial_gate(const T* __restrict__ x, long pixels, const float* __restrict__ w1,
+                                                      const float* __restrict__ b1, const float* __restrict__ w2,
+                                                      const float* __restrict__ b2, T* __restrict__ y) {
+  constexpr int HID = C / 4;
+  __shared__ float sw1[HID][C];
+  __shared__ float sb1[HID], sw2[HID];
+  for (int i = threadIdx.x; i < HID * C; i += blockDim.x) (&sw1[0][0])[i] = w1[i];
+  if (threadIdx.x < HID) { sb1[threadIdx.x] = b1[threadIdx.x]; sw2[threadIdx.x] = w2[threadIdx.x]; }
+  __syncthreads();
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pixels) return;
+  float v[C];
+#pragma unroll
+  for (int c = 0; c < C; c += 4) {
+    const float4 t = load_vec4<T>(x + p * C + c);
+    v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
+  }
+  float z = b2[0];
+#pragma unroll 4
+  for (int h = 0; h < HID; ++h) {
+    float a = sb1[h];
+#pragma unroll
+    for (int c = 0; c < C; ++c) a = fmaf(sw1[h][c], v[c], a);
+    z = fmaf(sw2[h], gelu_erf(a), z);
+  }
+  const float g = sigmoid_acc(z);
+#pragma unroll
+  for (int c = 0; c < C; c += 4) store_vec4<T>(y + p * C + c, v[c] * g, v[c + 1] * g, v[c + 2] * g, v[c + 3] * g);
+}
+
+extern "C" int ffsr_spatial_gate(const void* x, long pixels, int C, const float* w1, const float* b1, const float* w2,
+                                 const float* b2, void* y, int dtype, cudaStream_t stream) {
+  FFSR_REQUIRE(x && y && w1 && b1 && w2 && b2, FFSR_ERR_ARG, "spatial_gate: null pointer");
+  FFSR_REQUIRE(C == 64 || C == 32, FFSR_ERR_ARG, "spatial_gate: C must be 32 or 64");
+  FFSR_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0, FFSR_ERR_ALIGN, "spatial_gate: 16B alignment");
+  const int grid = ceil_div(pixels, 128);
+  if (dtype == FFSR_DT_BF16) {
+    if (C == 64) k_spatial_gate<__nv_bfloat16, 64><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)x, pixels, w1, b1, w2, b2, (__nv_bfloat16*)y);
+    else k_spatial_gate<__nv_bfloat16, 32><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)x, pixels, w1, b1, w2, b2, (__nv_bfloat16*)y);
+  } else {
+    if (C == 64) k_spatial_gate<float, 64><<<grid, 128, 0, stream>>>((const float*)x, pixels, w1, b1, w2, b2, (float*)y);
+    else k_spatial_gate<float, 32><<<grid, 128, 0, stream>>>((const float*)x, pixels, w1, b1, w2, b2, (float*)y);
+  }
+  return ffsr_check_launch("spatial_gate");
+}
+
+// ------------------------------------------------------------------------------------------
+// Phase 5b/5c/6 blend at HR
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bilin_plane(const float* __restrict__ pl, int W, const BilinTap& ty, const BilinTap& tx) {
+  const float top = tx.w0 * pl[(long)ty.i0 * W + tx.i0] + tx.w1 * pl[(long)ty.i0 * W + tx.i1];
+  const float bot = tx.w0 * pl[(long)ty.i1 * W + tx.i0] + tx.w1 * pl[(long)ty.i1 * W + tx.i1];
+  return ty.w0 * top + ty.w1 * bot;
+}
+
+__global__ void __launch_bounds__(128) k_blend_hr(const float* __restrict__ hier, long long hier_sX,
+                                                  const float* __restrict__ ecol, const float* __restrict__ routing,
+                                                  const float* __restrict__ gates, const float* __restrict__ diff,
+                                                  const float* __restrict__ fw0_w, const float* __restrict__ fw0_b,
+                                                  const float* __restrict__ fw2_w, const float* __restrict__ fw2_b,
+                                                  int B, int H, int W, float* __restrict__ fused_before,
+                                                  float* __restrict__ fused_nhwc, long long fused_sX,
+                                                  __nv_bfloat16* __restrict__ fused_lp, long long fused_lp_sX) {
+  __shared__ float s0w[16][3], s0b[16], s2w[4][16], s2b[4];
+  if (threadIdx.x < 48) (&s0w[0][0])[threadIdx.x] = fw0_w[threadIdx.x];
+  if (threadIdx.x < 16) s0b[threadIdx.x] = fw0_b[threadIdx.x];
+  if (threadIdx.x < 64) (&s2w[0][0])[threadIdx.x] = fw2_w[threadIdx.x];
+  if (threadIdx.x < 4) s2b[threadIdx.x] = fw2_b[threadIdx.x];
+  __syncthreads();
+  const int Hh = 4 * H, Wh = 4 * W;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  if (X >= Wh) return;
+  const long HW = (long)H * W, HWh = (long)Hh * Wh, pix = (long)Y * Wh + X;
+  const BilinTap ty = bilin_tap(Y, H, Hh), tx = bilin_tap(X, W, Wh);
+
+  // 5b: frequency-guided softmax weights from routing_lr upsampled x4
+  float r[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) r[c] = bilin_plane(routing + ((long)b * 3 + c) * HW, W, ty, tx);
+  float lg[4] = {s2b[0], s2b[1], s2b[2], s2b[3]};
+#pragma unroll
+  for (int h = 0; h < 16; ++h) {
+    const float a = gelu_erf(fmaf(s0w[h][2], r[2], fmaf(s0w[h][1], r[1], fmaf(s0w[h][0], r[0], s0b[h]))));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) lg[e] = fmaf(s2w[e][h], a, lg[e]);
+  }
+  const float mx = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
+  float fw[4], den = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { fw[e] = expf(lg[e] - mx); den += fw[e]; }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) fw[e] /= den;
+
+  // 6: gates / difficulty upsampled x4
+  float g[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) g[e] = bilin_plane(gates + ((long)b * 4 + e) * HW, W, ty, tx);
+  const float gsum = (((g[0] + g[1]) + g[2]) + g[3]) + 1e-8f;
+  const float bw = 0.3f + 0.4f * bilin_plane(diff + (long)b * HW, W, ty, tx);
+
+  const float* hp = hier + ((long)b * HWh + pix) * hier_sX;
+  float out[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float freq = 0.f, dyn = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v = ecol[((long)(b * 4 + e) * 3 + c) * HWh + pix];
+      freq += v * fw[e];
+      dyn += v * g[e];
+    }
+    const float f0 = hp[c] * 0.7f + freq * 0.3f;
+    if (fused_before) fused_before[((long)b * 3 + c) * HWh + pix] = f0;
+    out[c] = (1.0f - bw) * f0 + bw * (dyn / gsum);
+  }
+  float* fo = fused_nhwc + ((long)b * HWh + pix) * fused_sX;
+  fo[0] = out[0]; fo[1] = out[1]; fo[2] = out[2];
+  if (fused_sX > 3) fo[3] = 0.f;
+  if (fused_lp) {
+    __nv_bfloat16* lp = fused_lp + ((long)b * HWh + pix) * fused_lp_sX;
+    store_vec4<__nv_bfloat16>(lp, out[0], out[1], out[2], 0.f);
+    for (int c = 4; c + 4 <= (int)fused_lp_sX; c += 4) store_vec4<__nv_bfloat16>(lp + c, 0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+extern "C" int ffsr_blend_hr(const float* hier, long long hier_sX, const float* ecol, const float* routing,
+                             const float* gates, const float* diff, const float* fw0_w, const float* fw0_b,
+                             const float* fw2_w, const float* fw2_b, int B, int H, int W, float* fused_before,
+                             float* fused_nhwc, long long fused_sX, void* fused_lp, long long fused_lp_sX,
+                             cudaStream_t stream) {
+  FFSR_REQUIRE(hier && ecol && routing && gates && diff && fw0_w && fw0_b && fw2_w && fw2_b && fused_nhwc, FFSR_ERR_ARG,
+               "blend_hr: null pointer");
+  FFSR_REQUIRE(B > 0 && B <= 65535 && 4 * H <= 65535 && fused_sX >= 3, FFSR_ERR_ARG, "blend_hr: bad shape");
+  FFSR_REQUIRE(!fused_lp || (((uintptr_t)fused_lp % 8) == 0 && fused_lp_sX % 4 == 0 && fused_lp_sX >= 4), FFSR_ERR_ALIGN,
+               "blend_hr: low-precision copy alignment");
+  dim3 grid(ceil_div(4 * W, 128), 4 * H, B);
+  k_blend_hr<<<grid, 128, 0, stream>>>(hier, hier_sX, ecol, routing, gates, diff, fw0_w, fw0_b, fw2_w, fw2_b, B, H, W,
+                                       fused_before, fused_nhwc, fused_sX, (__nv_bfloat16*)fused_lp, fused_lp_sX);
+  return ffsr_check_launch("blend_hr");
+}
+
+// ------------------------------------------------------------------------------------------
+// Laplacian pyramid: down = avg_pool2(gauss5x5(x));  lap = x - bilinear(down)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_blur_pool(const float* __restrict__ x, long long x_sX, int H, int W,
+                                                   const float* __restrict__ gauss25, float* __restrict__ down,
+                                                   long long down_sX) {
+  __shared__ float sg[25];
+  if (threadIdx.x < 25) sg[threadIdx.x] = gauss25[threadIdx.x];
+  __syncthreads();
+  const int H2 = H / 2, W2 = W / 2;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y, n = blockIdx.z;
+  if (j >= W2) return;
+  const float* img = x + (long)n * H * W * x_sX;
+  float win[6][6][3];
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 6; ++bb) {
+      const int yy = 2 * i + a - 2, xx = 2 * j + bb - 2;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const float* p = img + ((long)yy * W + xx) * x_sX;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) win[a][bb][c] = ok ? p[c] : 0.f;
+    }
+  float* o = down + (((long)n * H2 + i) * W2 + j) * down_sX;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float bl[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        float acc = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 5; ++dx) acc = fmaf(sg[dy * 5 + dx], win[a + dy][bb + dx][c], acc);
+        bl[a][bb] = acc;
+      }
+    o[c] = (((bl[0][0] + bl[0][1]) + bl[1][0]) + bl[1][1]) * 0.25f;
+  }
+  if (down_sX > 3) o[3] = 0.f;
+}
+
+extern "C" int ffsr_blur_pool(const float* x, long long x_sX, int N, int H, int W, const float* gauss25, float* down,
+                              long long down_sX, cudaStream_t stream) {
+  FFSR_REQUIRE(x && gauss25 && down, FFSR_ERR_ARG, "blur_pool: null pointer");
+  FFSR_REQUIRE(N > 0 && H >= 2 && W >= 2 && x_sX >= 3 && down_sX >= 3, FFSR_ERR_ARG, "blur_pool: bad shape");
+  dim3 grid(ceil_div(W / 2, 128), H / 2, N);
+  k_blur_pool<<<grid, 128, 0, stream>>>(x, x_sX, H, W, gauss25, down, down_sX);
+  return ffsr_check_launch("blur_pool");
+}
+
+__global__ void __launch_bounds__(128) k_laplacian_sub(const float* __restrict__ x, long long x_sX,
+                                                       const float* __restrict__ down, long long down_sX, int H, int W,
+                                                       float* __restrict__ lap, long long lap_sX) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y, n = blockIdx.z;
+  if (X >= W) return;
+  const int h = H / 2, w = W / 2;
+  const BilinTap ty = bilin_tap(Y, h, H), tx = bilin_tap(X, w, W);
+  const float* d = down + (long)n * h * w * down_sX;
+  const float* a = d + ((long)ty.i0 * w + tx.i0) * down_sX;
+  const float* b = d + ((long)ty.i0 * w + tx.i1) * down_sX;
+  const float* c = d + ((long)ty.i1 * w + tx.i0) * down_sX;
+  const float* e = d + ((long)ty.i1 * w + tx.i1) * down_sX;
+  const long pix = ((long)n * H + Y) * W + X;
+  const float* xp = x + pix * x_sX;
+  float* o = lap + pix * lap_sX;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch)
+    o[ch] = xp[ch] - (ty.w0 * (tx.w0 * a[ch] + tx.w1 * b[ch]) + ty.w1 * (tx.w0 * c[ch] + tx.w1 * e[ch]));
+  if (lap_sX > 3) o[3] = 0.f;
+}
+
+extern "C" int ffsr_laplacian_sub(const float* x, long long x_sX, const float* down, long long down_sX, int N, int H,
+                                  int W, float* lap, long long lap_sX, cudaStream_t stream) {
+  FFSR_REQUIRE(x && down && lap, FFSR_ERR_ARG, "laplacian_sub: null pointer");
+  FFSR_REQUIRE(N > 0 && H >= 2 && W >= 2, FFSR_ERR_ARG, "laplacian_sub: bad shape");
+  dim3 grid(ceil_div(W, 128), H, N);
+  k_laplacian_sub<<<grid, 128, 0, stream>>>(x, x_sX, down, down_sX, H, W, lap, lap_sX);
+  return ffsr_check_launch("laplacian_sub");
+}
+
+// ------------------------------------------------------------------------------------------
+// refiner tail: (o * attn), bilinear to HxW if needed, times softmax(level_weights)[level]
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_edge_attn_up(const float* __restrict__ o, const float* __restrict__ attn, int h,
+                                                      int w, int C4, const float* __restrict__ level_w, int level,
+                                                      T* __restrict__ dst, int H, int W, long long dst_sX, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float l0 = level_w[0], l1 = level_w[1], l2 = level_w[2];
+  const float m = fmaxf(l0, fmaxf(l1, l2));
+  const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
+  const float lw = (level == 0 ? e0 : (level == 1 ? e1 : e2)) / ((e0 + e1) + e2);
+  const int c4 = (int)(i % C4);
+  const long pix = i / C4;
+  const int X = (int)(pix % W), Y = (int)((pix / W) % H);
+  const long n = pix / ((long)W * H);
+  const int C = 4 * C4;
+  const float* ob = o + n * h * w * C + 4 * c4;
+  const float* ab = attn + n * h * w;
+  float4 r;
+  if (h == H && w == W) {
+    const long q = (long)Y * w + X;
+    const float4 v = *reinterpret_cast<const float4*>(ob + q * C);
+    const float a = ab[q];
+    r = make_float4(v.x * a, v.y * a, v.z * a, v.w * a);
+  } else {
+    const BilinTap ty = bilin_tap(Y, h, H), tx = bilin_tap(X, w, W);
+    const long q00 = (long)ty.i0 * w + tx.i0, q01 = (long)ty.i0 * w + tx.i1;
+    const long q10 = (long)ty.i1 * w + tx.i0, q11 = (long)ty.i1 * w + tx.i1;
+    const float4 v00 = *reinterpret_cast<const float4*>(ob + q00 * C), v01 = *reinterpret_cast<const float4*>(ob + q01 * C);
+    const float4 v10 = *reinterpret_cast<const float4*>(ob + q10 * C), v11 = *reinterpret_cast<const float4*>(ob + q11 * C);
+    const float a00 = ab[q00], a01 = ab[q01], a10 = ab[q10], a11 = ab[q11];
+    r.x = ty.w0 * (tx.w0 * (v00.x * a00) + tx.w1 * (v01.x * a01)) + ty.w1 * (tx.w0 * (v10.x * a10) + tx.w1 * (v11.x * a11));
+    r.y = ty.w0 * (tx.w0 * (v00.y * a00) + tx.w1 * (v01.y * a01)) + ty.w1 * (tx.w0 * (v10.y * a10) + tx.w1 * (v11.y * a11));
+    r.z = ty.w0 * (tx.w0 * (v00.z * a00) + tx.w1 * (v01.z * a01)) + ty.w1 * (tx.w0 * (v10.z * a10) + tx.w1 * (v11.z * a11));
+    r.w = ty.w0 * (tx.w0 * (v00.w * a00) + tx.w1 * (v01.w * a01)) + ty.w1 * (tx.w0 * (v10.w * a10) + tx.w1 * (v11.w * a11));
+  }
+  store_vec4<T>(dst + pix * dst_sX + 4 * c4, r.x * lw, r.y * lw, r.z * lw, r.w * lw);
+}
+
+extern "C" int ffsr_edge_attn_upsample(const float* o, const float* attn, int N, int h, int w, int C,
+                                       const float* level_w, int level, void* dst, int H, int W, long long dst_sX,
+                                       int dtype, cudaStream_t stream) {
+  FFSR_REQUIRE(o && attn && level_w && dst, FFSR_ERR_ARG, "edge_attn_upsample: null pointer");
+  FFSR_REQUIRE(C % 4 == 0 && level >= 0 && level < 3, FFSR_ERR_ARG, "edge_attn_upsample: bad C/level");
+  const int esz = dtype == FFSR_DT_BF16 ? 2 : 4;
+  FFSR_REQUIRE(((uintptr_t)o % 16) == 0 && ((uintptr_t)dst % (4 * esz)) == 0 && dst_sX % 4 == 0, FFSR_ERR_ALIGN,
+               "edge_attn_upsample: alignment");
+  const long total = (long)N * H * W * (C / 4);
+  if (dtype == FFSR_DT_BF16)
+    k_edge_attn_up<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, stream>>>(o, attn, h, w, C / 4, level_w, level, (__nv_bfloat16*)dst, H, W, dst_sX, total);
+  else
+    k_edge_attn_up<float><<<ceil_div(total, 256), 256, 0, stream>>>(o, attn, h, w, C / 4, level_w, level, (float*)dst, H, W, dst_sX, total);
+  return ffsr_check_launch("edge_attn_upsample");
+}
+
+// ------------------------------------------------------------------------------------------
+// final: clamp(x + gate*strength*edge, 0, 1) + residual_scale * bilinear_x4(lr)  [clamp in eval]
+// xe: channels-last, x in channels 0..2, edge map in 3..5; out: [B][3][4H][4W] planar
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_final_combine(const float* __restrict__ xe, long long xe_sX,
+                                                       const float* __restrict__ gate, const float* __restrict__ strength,
+                                                       const float* __restrict__ lr, const float* __restrict__ rs,
+                                                       int H, int W, int clamp01, float* __restrict__ out) {
+  const int Hh = 4 * H, Wh = 4 * W;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  if (X >= Wh) return;
+  const long HW = (long)H * W, HWh = (long)Hh * Wh, pix = (long)Y * Wh + X;
+  const BilinTap ty = bilin_tap(Y, H, Hh), tx = bilin_tap(X, W, Wh);
+  const float* p = xe + ((long)b * HWh + pix) * xe_sX;
+  const float gs = gate[(long)b * HWh + pix] * strength[0];
+  const float scale = rs[0];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = p[c] + gs * p[3 + c];
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    v += scale * bilin_plane(lr + ((long)b * 3 + c) * HW, W, ty, tx);
+    if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+    out[((long)b * 3 + c) * HWh + pix] = v;
+  }
+}
+
+extern "C" int ffsr_final_combine(const float* xe, long long xe_sX, const float* gate, const float* strength,
+                                  const float* lr, const float* residual_scale, int B, int H, int W, int clamp01,
+                                  float* out, cudaStream_t stream) {
+  FFSR_REQUIRE(xe && gate && strength && lr && residual_scale && out, FFSR_ERR_ARG, "final_combine: null pointer");
+  FFSR_REQUIRE(B > 0 && B <= 65535 && 4 * H <= 65535 && xe_sX >= 6, FFSR_ERR_ARG, "final_combine: bad shape");
+  dim3 grid(ceil_div(4 * W, 128), 4 * H, B);
+  k_final_combine<<<grid, 128, 0, stream>>>(xe, xe_sX, gate, strength, lr, residual_scale, H, W, clamp01, out);
+  return ffsr_check_launch("final_combine");
+}

@@ -1,0 +1,135 @@
+// LKA depthwise chain on channels-last tensors [N][H][W][C]:
+//   n  = BN1(x) inside the image, 0 outside      (LKABlock.forward, large_kernel_attention.py:146)
+//   t1 = dw5x5(n)    zero pad 2                   (LargeKernelAttention.forward :98)
+//   t2 = dw1x21(t1)  zero pad 10 along W          (:99)
+//   t3 = dw21x1(t2)  zero pad 10 along H          (:100)
+// Every conv zero-pads ITS OWN input, so intermediates are zero outside the image
+// (three separately padded convs != one 25x25 conv at the borders; SURVEY §7 hard part 5).
+// HBM/L1-bound: each thread owns one channel and a short run of outputs along the conv
+// axis, keeps the sliding window in registers, and warps read 32 consecutive channels.
+#include "common.cuh"
+
+namespace {
+constexpr int R5 = 4;    // outputs per thread along W for the 5x5
+constexpr int R21 = 8;   // outputs per thread along the conv axis for the 21-tap passes
+}
+
+// BN is folded to y = x*k + d (eval: running stats; train: batch stats computed upstream).
+__global__ void __launch_bounds__(256) k_lka_dw5(const float* __restrict__ x, int H, int W, int C,
+                                                 const float* __restrict__ bn_k, const float* __restrict__ bn_d,
+                                                 const float* __restrict__ w5, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int runs = (W + R5 - 1) / R5;
+  const int idx = blockIdx.y * blockDim.y + threadIdx.y;      // over H * runs
+  const int y = idx / runs, x0 = (idx % runs) * R5;
+  const int n = blockIdx.z;
+  if (c >= C || y >= H) return;
+  float w[25];
+#pragma unroll
+  for (int i = 0; i < 25; ++i) w[i] = w5[c * 25 + i];
+  const float k = bn_k[c], d = bn_d[c];
+  float acc[R5];
+#pragma unroll
+  for (int r = 0; r < R5; ++r) acc[r] = 0.f;
+  const float* img = x + (long)n * H * W * C;
+#pragma unroll
+  for (int dy = 0; dy < 5; ++dy) {
+    const int yy = y + dy - 2;
+    if (yy < 0 || yy >= H) continue;
+    float v[R5 + 4];
+#pragma unroll
+    for (int i = 0; i < R5 + 4; ++i) {
+      const int xx = x0 + i - 2;
+      v[i] = (xx >= 0 && xx < W) ? fmaf(img[((long)yy * W + xx) * C + c], k, d) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < R5; ++r)
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx) acc[r] = fmaf(w[dy * 5 + dx], v[r + dx], acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < R5; ++r)
+    if (x0 + r < W) out[(((long)n * H + y) * W + x0 + r) * C + c] = acc[r];
+}
+
+// AXIS = 0: taps along W (1x21); AXIS = 1: taps along H (21x1)
+template <int AXIS>
+__global__ void __launch_bounds__(256) k_lka_dw21(const float* __restrict__ in, int H, int W, int C,
+                                                  const float* __restrict__ w21, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.z;
+  int y, x;
+  if (AXIS == 0) {
+    const int runs = (W + R21 - 1) / R21;
+    const int idx = blockIdx.y * blockDim.y + threadIdx.y;    // over H * runs
+    y = idx / runs;
+    x = (idx % runs) * R21;
+    if (y >= H) return;
+  } else {
+    const int runs = (H + R21 - 1) / R21;
+    const int idx = blockIdx.y * blockDim.y + threadIdx.y;    // over runs * W
+    y = (idx / W) * R21;
+    x = idx % W;
+    if (idx >= runs * W) return;
+  }
+  if (c >= C) return;
+  float w[21];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) w[i] = w21[c * 21 + i];
+  const float* img = in + (long)n * H * W * C;
+  float v[R21 + 20];
+#pragma unroll
+  for (int i = 0; i < R21 + 20; ++i) {
+    if (AXIS == 0) {
+      const int xx = x + i - 10;
+      v[i] = (xx >= 0 && xx < W) ? img[((long)y * W + xx) * C + c] : 0.f;
+    } else {
+      const int yy = y + i - 10;
+      v[i] = (yy >= 0 && yy < H) ? img[((long)yy * W + x) * C + c] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R21; ++r) {
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 21; ++t) acc = fmaf(w[t], v[r + t], acc);
+    if (AXIS == 0) {
+      if (x + r < W) out[(((long)n * H + y) * W + x + r) * C + c] = acc;
+    } else {
+      if (y + r < H) out[(((long)n * H + y + r) * W + x) * C + c] = acc;
+    }
+  }
+}
+
+// x: [N][H][W][C] -> out: [N][H][W][C]; tmp1/tmp2: same-size scratch (tmp2 may alias out? no: distinct)
+extern "C" int ffsr_lka_depthwise(const float* x, int N, int H, int W, int C, const float* bn_k, const float* bn_d,
+                                  const float* w5, const float* wh, const float* wv, float* tmp1, float* tmp2,
+                                  float* out, cudaStream_t stream) {
+  FFSR_REQUIRE(x && bn_k && bn_d && w5 && wh && wv && tmp1 && tmp2 && out, FFSR_ERR_ARG, "lka_depthwise: null pointer");
+  FFSR_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 32 == 0, FFSR_ERR_ARG, "lka_depthwise: C must be a multiple of 32");
+  FFSR_REQUIRE(N <= 65535 && (long)H * W / 4 < 65535L * 4, FFSR_ERR_ARG, "lka_depthwise: grid too large");
+  const int cx = C < 64 ? C : 64;
+  const int ty = 256 / cx;
+  {
+    dim3 block(cx, ty);
+    dim3 grid(C / cx, ceil_div((long)H * ceil_div(W, R5), ty), N);
+    k_lka_dw5<<<grid, block, 0, stream>>>(x, H, W, C, bn_k, bn_d, w5, tmp1);
+    int rc = ffsr_check_launch("lka_dw5");
+    if (rc) return rc;
+  }
+  {
+    dim3 block(cx, ty);
+    const long items = (long)H * ceil_div(W, R21);
+    dim3 grid(C / cx, ceil_div(items, ty), N);
+    k_lka_dw21<0><<<grid, block, 0, stream>>>(tmp1, H, W, C, wh, tmp2);
+    int rc = ffsr_check_launch("lka_dw21_h");
+    if (rc) return rc;
+  }
+  {
+    dim3 block(cx, ty);
+    const long items = (long)ceil_div(H, R21) * W;
+    dim3 grid(C / cx, ceil_div(items, ty), N);
+    k_lka_dw21<1><<<grid, block, 0, stream>>>(tmp2, H, W, C, wv, out);
+    return ffsr_check_launch("lka_dw21_v");
+  }
+}

@@ -1,0 +1,375 @@
+// LR-side per-pixel token kernels:
+//   * Phase 3 cross-band attention over the 9 sub-band tokens of each LR pixel
+//     (EnhancedCrossBandWithLKA.forward, src/models/large_kernel_attention.py:207-233)
+//   * Phase 3 tail: out_proj + band residual + routing_lr (:240-241, enhanced_fusion_v2.py:713)
+//   * LayerNorm rows and the 4-token x 8-head attention core used by Phase 4 (:389-392)
+//   * Phase 6 gate normalisation (DynamicExpertSelector.forward, enhanced_fusion_v2.py:462-465)
+// All fp32: routing_lr feeds the expert-selection indices that must be bit-exact.
+#include "common.cuh"
+
+namespace {
+constexpr int CB_DIM = 64, CB_BANDS = 9, CB_HEADS = 4, CB_HD = 16;
+constexpr int CB_PX = 8;                       // LR pixels per tile
+constexpr int CB_TOK = CB_PX * CB_BANDS;       // 72 tokens per tile
+constexpr int CB_THREADS = 192;                // one thread per packed in_proj row
+constexpr int CB_QKV_LD = 3 * CB_DIM + 4;      // +4 floats: keeps rows 16B aligned, breaks bank stride
+
+struct CBSmem {
+  float in[CB_PX][28];                 // 27 band/channel values per pixel
+  float n[CB_TOK][CB_DIM];             // LayerNorm'ed tokens; later the attention context
+  float qkv[CB_TOK][CB_QKV_LD];
+  float wo[CB_DIM][CB_DIM];            // out_proj weight transposed: wo[c][o]
+  float pw[CB_DIM][4];                 // band_proj weight [o][3] + bias in slot 3
+  float lnw[CB_DIM], lnb[CB_DIM], ob[CB_DIM];
+};
+}  // namespace
+
+__global__ void __launch_bounds__(CB_THREADS, 2) k_crossband_attn(
+    const float* __restrict__ raw9, int B, int HW,
+    const float* __restrict__ proj_w, const float* __restrict__ proj_b,
+    const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+    const float* __restrict__ in_w, const float* __restrict__ in_b,
+    const float* __restrict__ out_w, const float* __restrict__ out_b,
+    int nq, float* __restrict__ tok_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CBSmem& s = *reinterpret_cast<CBSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // --- per-block constants -------------------------------------------------------------
+  for (int i = tid; i < CB_DIM * CB_DIM; i += CB_THREADS) {
+    const int o = i / CB_DIM, c = i % CB_DIM;
+    s.wo[c][o] = out_w[i];
+  }
+  if (tid < CB_DIM) {
+    s.pw[tid][0] = proj_w[tid * 3 + 0];
+    s.pw[tid][1] = proj_w[tid * 3 + 1];
+    s.pw[tid][2] = proj_w[tid * 3 + 2];
+    s.pw[tid][3] = proj_b[tid];
+    s.lnw[tid] = ln_w[tid];
+    s.lnb[tid] = ln_b[tid];
+    s.ob[tid] = out_b[tid];
+  }
+  float wrow[CB_DIM];                  // this thread's in_proj row (q|k|v output channel tid)
+#pragma unroll
+  for (int c = 0; c < CB_DIM; c += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(in_w + (long)tid * CB_DIM + c);
+    wrow[c] = v.x; wrow[c + 1] = v.y; wrow[c + 2] = v.z; wrow[c + 3] = v.w;
+  }
+  const float brow = in_b[tid];
+  __syncthreads();
+
+  const int tiles_per_img = (HW + CB_PX - 1) / CB_PX;
+  const int total_tiles = B * tiles_per_img;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img;
+    const int p0 = (tile % tiles_per_img) * CB_PX;
+
+    // A. gather the 27 inputs of each pixel
+    for (int i = tid; i < CB_PX * 27; i += CB_THREADS) {
+      const int px = i / 27, r = i % 27;
+      const int p = p0 + px;
+      s.in[px][r] = (p < HW) ? raw9[((long)b * 27 + r) * HW + p] : 0.f;
+    }
+    __syncthreads();
+
+    // B. band_proj (1x1, 3->64) + LayerNorm(64): one warp per token, 2 channels per lane
+    for (int tk = warp; tk < CB_TOK; tk += CB_THREADS / 32) {
+      const int px = tk / CB_BANDS, band = tk % CB_BANDS;
+      const float x0 = s.in[px][band * 3], x1 = s.in[px][band * 3 + 1], x2 = s.in[px][band * 3 + 2];
+      const int c0 = lane, c1 = lane + 32;
+      const float v0 = fmaf(s.pw[c0][2], x2, fmaf(s.pw[c0][1], x1, fmaf(s.pw[c0][0], x0, s.pw[c0][3])));
+      const float v1 = fmaf(s.pw[c1][2], x2, fmaf(s.pw[c1][1], x1, fmaf(s.pw[c1][0], x0, s.pw[c1][3])));
+      float sum = v0 + v1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * (1.0f / CB_DIM);
+      const float d0 = v0 - mean, d1 = v1 - mean;
+      float sq = d0 * d0 + d1 * d1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * (1.0f / CB_DIM) + 1e-5f);
+      s.n[tk][c0] = d0 * rstd * s.lnw[c0] + s.lnb[c0];
+      s.n[tk][c1] = d1 * rstd * s.lnw[c1] + s.lnb[c1];
+    }
+    __syncthreads();
+
+    // C. packed in_proj: thread `tid` owns output channel tid of [q|k|v]
+    for (int tk = 0; tk < CB_TOK; ++tk) {
+      float acc = brow;
+      const float4* nrow = reinterpret_cast<const float4*>(&s.n[tk][0]);
+#pragma unroll
+      for (int c4 = 0; c4 < CB_DIM / 4; ++c4) {
+        const float4 v = nrow[c4];
+        acc = fmaf(v.x, wrow[4 * c4], acc);
+        acc = fmaf(v.y, wrow[4 * c4 + 1], acc);
+        acc = fmaf(v.z, wrow[4 * c4 + 2], acc);
+        acc = fmaf(v.w, wrow[4 * c4 + 3], acc);
+      }
+      s.qkv[tk][tid] = acc;
+    }
+    __syncthreads();
+
+    // D. softmax(q k^T / 4) v per (pixel, head, query band); context overwrites s.n
+    for (int it = tid; it < CB_PX * CB_HEADS * nq; it += CB_THREADS) {
+      const int qt = it % nq, h = (it / nq) % CB_HEADS, px = it / (nq * CB_HEADS);
+      const float* q = &s.qkv[px * CB_BANDS + qt][h * CB_HD];
+      float sc[CB_BANDS];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < CB_BANDS; ++j) {
+        const float* k = &s.qkv[px * CB_BANDS + j][CB_DIM + h * CB_HD];
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < CB_HD; ++d) a = fmaf(q[d], k[d], a);
+        sc[j] = a * 0.25f;
+        mx = fmaxf(mx, sc[j]);
+      }
+      float den = 0.f;
+#pragma unroll
+      for (int j = 0; j < CB_BANDS; ++j) {
+        sc[j] = expf(sc[j] - mx);
+        den += sc[j];
+      }
+      const float inv = 1.0f / den;
+      float ctx[CB_HD];
+#pragma unroll
+      for (int d = 0; d < CB_HD; ++d) ctx[d] = 0.f;
+#pragma unroll
+      for (int j = 0; j < CB_BANDS; ++j) {
+        const float* v = &s.qkv[px * CB_BANDS + j][2 * CB_DIM + h * CB_HD];
+        const float pj = sc[j] * inv;
+#pragma unroll
+        for (int d = 0; d < CB_HD; ++d) ctx[d] = fmaf(pj, v[d], ctx[d]);
+      }
+#pragma unroll
+      for (int d = 0; d < CB_HD; ++d) s.n[px * CB_BANDS + qt][h * CB_HD + d] = ctx[d];
+    }
+    __syncthreads();
+
+    // E. out_proj + residual with the (pre-LayerNorm) projected token; NHWC store
+    {
+      const int o = tid & 63, g = tid >> 6;
+      for (int ti = g; ti < CB_PX * nq; ti += 3) {
+        const int px = ti / nq, qt = ti % nq;
+        const int p = p0 + px;
+        const float* crow = &s.n[px * CB_BANDS + qt][0];
+        float acc = s.ob[o];
+#pragma unroll 16
+        for (int c = 0; c < CB_DIM; ++c) acc = fmaf(crow[c], s.wo[c][o], acc);
+        const float x0 = s.in[px][qt * 3], x1 = s.in[px][qt * 3 + 1], x2 = s.in[px][qt * 3 + 2];
+        const float res = fmaf(s.pw[o][2], x2, fmaf(s.pw[o][1], x1, fmaf(s.pw[o][0], x0, s.pw[o][3])));
+        if (p < HW) tok_out[(((long)b * nq + qt) * HW + p) * CB_DIM + o] = acc + res;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" int ffsr_crossband_attention(const float* raw9, int B, int H, int W, const float* proj_w,
+                                        const float* proj_b, const float* ln_w, const float* ln_b,
+                                        const float* in_w, const float* in_b, const float* out_w,
+                                        const float* out_b, int nq, float* tok_out, int num_sms,
+                                        cudaStream_t stream) {
+  FFSR_REQUIRE(raw9 && proj_w && proj_b && ln_w && ln_b && in_w && in_b && out_w && out_b && tok_out, FFSR_ERR_ARG,
+               "crossband_attention: null pointer");
+  FFSR_REQUIRE(B > 0 && H > 0 && W > 0 && nq >= 1 && nq <= CB_BANDS, FFSR_ERR_ARG, "crossband_attention: bad shape");
+  FFSR_REQUIRE(((uintptr_t)in_w % 16) == 0, FFSR_ERR_ALIGN, "crossband_attention: in_proj_weight must be 16B aligned");
+  const int HW = H * W;
+  const int tiles = B * ((HW + CB_PX - 1) / CB_PX);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_crossband_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CBSmem));
+    attr_set = true;
+  }
+  const int grid = tiles < 2 * num_sms ? tiles : 2 * num_sms;
+  k_crossband_attn<<<grid, CB_THREADS, sizeof(CBSmem), stream>>>(raw9, B, HW, proj_w, proj_b, ln_w, ln_b, in_w, in_b,
+                                                                 out_w, out_b, nq, tok_out);
+  return ffsr_check_launch("crossband_attention");
+}
+
+// ------------------------------------------------------------------------------------
+// Phase 3 tail: enhanced band = out_proj(x) + raw band; routing_lr = sum of bands 0..2.
+// x: [B][nq][H][W][64] (after the LKA block); enh9/raw9: [B][9][3][H][W]; routing: [B][3][H][W]
+// ------------------------------------------------------------------------------------
+__global__ void k_cb_out(const float* __restrict__ x, const float* __restrict__ raw9, int B, int HW, int nq,
+                         const float* __restrict__ w, const float* __restrict__ bias,
+                         float* __restrict__ enh9, float* __restrict__ routing) {
+  __shared__ float sw[3][CB_DIM];
+  __shared__ float sb[3];
+  for (int i = threadIdx.x; i < 3 * CB_DIM; i += blockDim.x) sw[i / CB_DIM][i % CB_DIM] = w[i];
+  if (threadIdx.x < 3) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long gp = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gp >= (long)B * HW) return;
+  const int b = (int)(gp / HW), p = (int)(gp % HW);
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+  for (int band = 0; band < nq; ++band) {
+    const float4* row = reinterpret_cast<const float4*>(x + (((long)b * nq + band) * HW + p) * CB_DIM);
+    float a0 = sb[0], a1 = sb[1], a2 = sb[2];
+#pragma unroll
+    for (int c4 = 0; c4 < CB_DIM / 4; ++c4) {
+      const float4 v = row[c4];
+      a0 = fmaf(v.x, sw[0][4 * c4], a0); a0 = fmaf(v.y, sw[0][4 * c4 + 1], a0);
+      a0 = fmaf(v.z, sw[0][4 * c4 + 2], a0); a0 = fmaf(v.w, sw[0][4 * c4 + 3], a0);
+      a1 = fmaf(v.x, sw[1][4 * c4], a1); a1 = fmaf(v.y, sw[1][4 * c4 + 1], a1);
+      a1 = fmaf(v.z, sw[1][4 * c4 + 2], a1); a1 = fmaf(v.w, sw[1][4 * c4 + 3], a1);
+      a2 = fmaf(v.x, sw[2][4 * c4], a2); a2 = fmaf(v.y, sw[2][4 * c4 + 1], a2);
+      a2 = fmaf(v.z, sw[2][4 * c4 + 2], a2); a2 = fmaf(v.w, sw[2][4 * c4 + 3], a2);
+    }
+    const long o = ((long)b * 9 + band) * 3 * HW + p;
+    a0 += raw9[o]; a1 += raw9[o + HW]; a2 += raw9[o + 2 * (long)HW];
+    enh9[o] = a0; enh9[o + HW] = a1; enh9[o + 2 * (long)HW] = a2;
+    if (band == 0) { r0 = a0; r1 = a1; r2 = a2; }
+    else if (band < 3) { r0 += a0; r1 += a1; r2 += a2; }
+  }
+  const long ro = (long)b * 3 * HW + p;
+  routing[ro] = r0; routing[ro + HW] = r1; routing[ro + 2 * (long)HW] = r2;
+}
+
+extern "C" int ffsr_crossband_out(const float* x, const float* raw9, int B, int H, int W, int nq, const float* w,
+                                  const float* bias, float* enh9, float* routing, cudaStream_t stream) {
+  FFSR_REQUIRE(x && raw9 && w && bias && enh9 && routing, FFSR_ERR_ARG, "crossband_out: null pointer");
+  FFSR_REQUIRE(nq >= 3 && nq <= 9, FFSR_ERR_ARG, "crossband_out: nq must be in [3,9]");
+  FFSR_REQUIRE(((uintptr_t)x % 16) == 0, FFSR_ERR_ALIGN, "crossband_out: x must be 16B aligned");
+  const long n = (long)B * H * W;
+  k_cb_out<<<ceil_div(n, 128), 128, 0, stream>>>(x, raw9, B, H * W, nq, w, bias, enh9, routing);
+  return ffsr_check_launch("crossband_out");
+}
+
+// ------------------------------------------------------------------------------------
+// LayerNorm over the last dim (E in {64,128,256}): one warp per row.
+// ------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void k_layernorm_rows(const float* __restrict__ x, long rows, int E, const float* __restrict__ w,
+                                 const float* __restrict__ b, TO* __restrict__ y) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * E;
+  float v[8];
+  const int per = E / 32;   // 2, 4 or 8
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < per) { v[i] = xr[lane + 32 * i]; sum += v[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)E;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < per) { v[i] -= mean; sq += v[i] * v[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)E + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < per) {
+      const int c = lane + 32 * i;
+      y[row * E + c] = from_f32<TO>(v[i] * rstd * w[c] + b[c]);
+    }
+}
+
+extern "C" int ffsr_layernorm(const float* x, long rows, int E, const float* w, const float* b, void* y,
+                              int out_bf16, cudaStream_t stream) {
+  FFSR_REQUIRE(x && w && b && y, FFSR_ERR_ARG, "layernorm: null pointer");
+  FFSR_REQUIRE(E % 32 == 0 && E >= 32 && E <= 256, FFSR_ERR_ARG, "layernorm: E must be a multiple of 32 in [32,256]");
+  const int wpb = 8;
+  if (out_bf16)
+    k_layernorm_rows<__nv_bfloat16><<<ceil_div(rows, wpb), wpb * 32, 0, stream>>>(x, rows, E, w, b, (__nv_bfloat16*)y);
+  else
+    k_layernorm_rows<float><<<ceil_div(rows, wpb), wpb * 32, 0, stream>>>(x, rows, E, w, b, (float*)y);
+  return ffsr_check_launch("layernorm");
+}
+
+// ------------------------------------------------------------------------------------
+// Token attention core (Phase 4): softmax(q k^T / 4) v over the T tokens of each LR pixel.
+// Token-major ("expert-major") layout: qkv[B][T][HW][3E] -> ctx[B][T][HW][E], head_dim 16.
+// One thread per (b, pixel, query token, head); heads vary fastest so a warp reads
+// contiguous 64-byte head slices.
+// ------------------------------------------------------------------------------------
+template <typename TI, typename TO, int T>
+__global__ void k_token_attention(const TI* __restrict__ qkv, int B, long HW, int E, TO* __restrict__ ctx) {
+  const int heads = E / 16;
+  const long it = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= (long)B * HW * T * heads) return;
+  const int h = (int)(it % heads);
+  long rest = it / heads;
+  const int qt = (int)(rest % T);
+  rest /= T;
+  const long p = rest % HW;
+  const int b = (int)(rest / HW);
+  const long tstride = HW * 3 * E;                       // between tokens of one pixel
+  const TI* base = qkv + ((long)b * T * HW + p) * 3 * E + h * 16;
+  float q[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) q[d] = to_f32<TI>(base[qt * tstride + d]);
+  float sc[T];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    const TI* k = base + j * tstride + E;
+    float a = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) a = fmaf(q[d], to_f32<TI>(k[d]), a);
+    sc[j] = a * 0.25f;
+    mx = fmaxf(mx, sc[j]);
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int j = 0; j < T; ++j) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
+  const float inv = 1.0f / den;
+  float o[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    const TI* v = base + j * tstride + 2 * E;
+    const float pj = sc[j] * inv;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] = fmaf(pj, to_f32<TI>(v[d]), o[d]);
+  }
+  TO* dst = ctx + (((long)b * T + qt) * HW + p) * E + h * 16;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) dst[d] = from_f32<TO>(o[d]);
+}
+
+extern "C" int ffsr_token_attention(const void* qkv, int B, int T, long HW, int E, void* ctx, int is_bf16,
+                                    cudaStream_t stream) {
+  FFSR_REQUIRE(qkv && ctx, FFSR_ERR_ARG, "token_attention: null pointer");
+  FFSR_REQUIRE(T == 4 && E % 16 == 0 && B > 0 && HW > 0, FFSR_ERR_ARG, "token_attention: built for T=4 tokens, E%%16==0");
+  const long n = (long)B * HW * T * (E / 16);
+  if (is_bf16)
+    k_token_attention<__nv_bfloat16, __nv_bfloat16, 4><<<ceil_div(n, 128), 128, 0, stream>>>(
+        (const __nv_bfloat16*)qkv, B, HW, E, (__nv_bfloat16*)ctx);
+  else
+    k_token_attention<float, float, 4><<<ceil_div(n, 128), 128, 0, stream>>>((const float*)qkv, B, HW, E, (float*)ctx);
+  return ffsr_check_launch("token_attention");
+}
+
+// ------------------------------------------------------------------------------------
+// Phase 6: gates = sigmoid(T*(raw - (0.7 - 0.5 d))) / max(sum + 1e-8, 0.3)
+// raw: [B][H][W][4] (NHWC), diff: [B][1][H][W]; gates out: [B][4][H][W] planar.
+// ------------------------------------------------------------------------------------
+__global__ void k_gate_finalize(const float* __restrict__ raw, const float* __restrict__ diff, int B, int HW,
+                                const float* __restrict__ temperature, float* __restrict__ gates) {
+  const long gp = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gp >= (long)B * HW) return;
+  const int b = (int)(gp / HW), p = (int)(gp % HW);
+  const float4 r = *reinterpret_cast<const float4*>(raw + gp * 4);
+  const float thr = 0.7f - 0.5f * diff[gp];
+  const float T = temperature[0];
+  float g0 = sigmoid_acc(T * (r.x - thr)), g1 = sigmoid_acc(T * (r.y - thr));
+  float g2 = sigmoid_acc(T * (r.z - thr)), g3 = sigmoid_acc(T * (r.w - thr));
+  const float s = fmaxf(((g0 + g1) + g2) + g3 + 1e-8f, 0.3f);
+  float* o = gates + (long)b * 4 * HW + p;
+  o[0] = g0 / s; o[HW] = g1 / s; o[2 * (long)HW] = g2 / s; o[3 * (long)HW] = g3 / s;
+}
+
+extern "C" int ffsr_gate_finalize(const float* raw, const float* diff, int B, int H, int W,
+                                  const float* temperature, float* gates, cudaStream_t stream) {
+  FFSR_REQUIRE(raw && diff && temperature && gates, FFSR_ERR_ARG, "gate_finalize: null pointer");
+  const long n = (long)B * H * W;
+  k_gate_finalize<<<ceil_div(n, 256), 256, 0, stream>>>(raw, diff, B, H * W, temperature, gates);
+  return ffsr_check_launch("gate_finalize");
+}

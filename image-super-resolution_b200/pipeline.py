@@ -1,0 +1,520 @@
+"""Host-side orchestration of the sm_100a kernels for one fusion forward (eval mode).
+
+``FusionEngine.forward`` is what ``CompleteEnhancedFusionSR._run_pipeline`` runs: it
+enqueues ~110 kernel launches of ``libffsr_b200.so`` on the current CUDA stream.  PyTorch
+is used for device memory (caching allocator / persistent workspaces), streams and the tiny
+host-side weight re-packing (BN folding, [taps][Cin][Cout] packing), nothing else.
+
+Phase map (reference file:line in include/ffsr_b200.h):
+  P2  dct/dwt/fft bands      -> raw9 [B][9][3][H][W]
+  P3  cross-band attention   -> tokens [B][nq][H][W][64] -> LKA block -> enhanced bands, routing_lr
+  P6  selector convs on routing_lr -> gates, difficulty           (fp32 always)
+  P4  align -> LN -> MHA -> FFN -> LKA(128) -> mod-head layer 0 at LR -> HR modulation
+  P5  hierarchical conv pyramid; P5b/P6 blend; P7a refine; P7b Laplacian edge; residual
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _cabi as K
+
+EXPERT_ORDER = ("drct", "grl", "nafnet", "mamba")
+_BN_EPS = 1e-5
+
+
+class _View:
+    """Strided channels-last (or NCHW) view handed to ffsr_conv2d."""
+    __slots__ = ("ptr", "sN", "sY", "sX", "sC", "t")
+
+    def __init__(self, ptr, sN, sY, sX, sC, t):
+        self.ptr, self.sN, self.sY, self.sX, self.sC, self.t = ptr, sN, sY, sX, sC, t
+
+
+def nhwc(t: torch.Tensor, c_off: int = 0) -> _View:
+    """t: [N,H,W,Cs] contiguous; view starting at channel c_off."""
+    N, H, W, Cs = t.shape
+    return _View(t.data_ptr() + c_off * t.element_size(), H * W * Cs, W * Cs, Cs, 1, t)
+
+
+def nchw(t: torch.Tensor) -> _View:
+    N, Cc, H, W = t.shape
+    return _View(t.data_ptr(), Cc * H * W, W, 1, H * W, t)
+
+
+def _pack_conv(w: torch.Tensor) -> torch.Tensor:
+    """[Cout,Cin,kh,kw] -> [kh*kw][Cin][Cout] fp32 contiguous."""
+    co, ci, kh, kw = w.shape
+    return w.detach().float().permute(2, 3, 1, 0).reshape(kh * kw, ci, co).contiguous()
+
+
+def _pack_linear(w: torch.Tensor) -> torch.Tensor:
+    """[out,in] -> [1][in][out]."""
+    return w.detach().float().t().contiguous().unsqueeze(0)
+
+
+class FusionEngine:
+    def __init__(self, model):
+        self.m = model
+        self.lib = K.load()
+        self._wkey = None
+        self._w: Dict[str, torch.Tensor] = {}
+        self._ws: Dict[Tuple, torch.Tensor] = {}
+        self._tw: Dict[Tuple, torch.Tensor] = {}
+        self._checked_dev = None
+        self.launches = 0          # kernels enqueued by the last forward (bench reports it)
+        # optional per-launch CUDA-event timing of named conv layers (bench.py roofline):
+        # {weight name: [(start_event, end_event), ...]}
+        self.timed_layers = None
+
+    # ------------------------------------------------------------------ weights
+    def _state_key(self, dev):
+        m = self.m
+        return (str(dev), m.training) + tuple(p._version for p in m.parameters()) + \
+            tuple(b._version for b in m.buffers())
+
+    def _bn_fold(self, bn):
+        k = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + _BN_EPS)
+        d = bn.bias.detach().float() - bn.running_mean.detach().float() * k
+        return k.contiguous(), d.contiguous()
+
+    def _prep_lka(self, key, blk):
+        w = self._w
+        C_ = blk.norm1.weight.shape[0]
+        w[key + ".k1"], w[key + ".d1"] = self._bn_fold(blk.norm1)
+        w[key + ".w5"] = blk.lka.local_conv.weight.detach().float().reshape(C_, 25).contiguous()
+        w[key + ".wh"] = blk.lka.h_conv.weight.detach().float().reshape(C_, 21).contiguous()
+        w[key + ".wv"] = blk.lka.v_conv.weight.detach().float().reshape(C_, 21).contiguous()
+        kb, db = self._bn_fold(blk.lka.bn)                      # BN after the 1x1: fold into it
+        pw = blk.lka.pw_conv.weight.detach().float().reshape(C_, C_)      # [co][ci]
+        w[key + ".pw"] = (pw * kb[:, None]).t().contiguous().unsqueeze(0)
+        w[key + ".pwb"] = db
+        k2, d2 = self._bn_fold(blk.norm2)                        # BN before ffn.0: fold into it
+        f0 = blk.ffn[0].weight.detach().float().reshape(-1, C_)           # [2C][C]
+        w[key + ".f0"] = (f0 * k2[None, :]).t().contiguous().unsqueeze(0)
+        w[key + ".f0b"] = (blk.ffn[0].bias.detach().float() + f0 @ d2).contiguous()
+        w[key + ".f2"] = _pack_conv(blk.ffn[2].weight)
+        w[key + ".f2b"] = blk.ffn[2].bias.detach().float().contiguous()
+
+    def _prepare(self, dev):
+        key = self._state_key(dev)
+        if key == self._wkey:
+            return
+        m, w = self.m, {}
+        self._w = w
+
+        def conv(name, mod, bias=True):
+            w[name] = _pack_conv(mod.weight)
+            if bias and mod.bias is not None:
+                w[name + ".b"] = mod.bias.detach().float().contiguous()
+
+        with torch.no_grad():
+            self._prep_lka("cb.lka", m.cross_band.lka_block)
+            self._prep_lka("co.lka", m.collaborative.lka_global)
+            cb = m.cross_band
+            w["cb.proj_w"] = cb.band_proj.weight.detach().float().reshape(64, 3).contiguous()
+            w["cb.out_w"] = cb.out_proj.weight.detach().float().reshape(3, 64).contiguous()
+            co = m.collaborative
+            for n in EXPERT_ORDER:
+                conv("co.align." + n, co.align_layers[n])
+            w["co.qkv"] = _pack_linear(co.cross_attn.in_proj_weight)
+            w["co.qkv.b"] = co.cross_attn.in_proj_bias.detach().float().contiguous()
+            w["co.out"] = _pack_linear(co.cross_attn.out_proj.weight)
+            w["co.out.b"] = co.cross_attn.out_proj.bias.detach().float().contiguous()
+            w["co.f0"] = _pack_linear(co.ffn[0].weight)
+            w["co.f0.b"] = co.ffn[0].bias.detach().float().contiguous()
+            w["co.f2"] = _pack_linear(co.ffn[2].weight)
+            w["co.f2.b"] = co.ffn[2].bias.detach().float().contiguous()
+            w["co.m0"] = torch.stack([_pack_conv(co.modulation[i][0].weight) for i in range(4)]).contiguous()
+            w["co.m0b"] = torch.stack([co.modulation[i][0].bias.detach().float() for i in range(4)]).contiguous()
+            w["co.m2"] = torch.stack([co.modulation[i][2].weight.detach().float().reshape(3, 32) for i in range(4)]).contiguous()
+            w["co.m2b"] = torch.stack([co.modulation[i][2].bias.detach().float() for i in range(4)]).contiguous()
+            mr = m.multi_res
+            for s in ("stage1", "stage2", "stage3"):
+                conv(f"mr.{s}.c0", getattr(mr, s + "_conv")[0])
+                conv(f"mr.{s}.c2", getattr(mr, s + "_conv")[2])
+                g = getattr(mr, s + "_gate").gate
+                w[f"mr.{s}.g0"] = g[0].weight.detach().float().reshape(g[0].weight.shape[0], -1).contiguous()
+                w[f"mr.{s}.g2"] = g[2].weight.detach().float().reshape(-1).contiguous()
+                r = getattr(mr, s + "_res").block
+                conv(f"mr.{s}.r0", r[0], bias=False)
+                conv(f"mr.{s}.r2", r[2], bias=False)
+            conv("mr.rgb0", mr.to_rgb[0])
+            conv("mr.rgb2", mr.to_rgb[2])
+            w["fw0"] = m.freq_weight_conv[0].weight.detach().float().reshape(16, 3).contiguous()
+            w["fw2"] = m.freq_weight_conv[2].weight.detach().float().reshape(4, 16).contiguous()
+            ds = m.dynamic_selector
+            for i in (0, 2, 4):
+                conv(f"ds.d{i}", ds.difficulty_net[i])
+                conv(f"ds.g{i}", ds.gate_net[i])
+            self._refine_idx = [i for i, l in enumerate(m.refine) if isinstance(l, torch.nn.Conv2d)]
+            for i in self._refine_idx:
+                conv(f"rf.{i}", m.refine[i])
+            ee = m.edge_enhance
+            for lv in range(3):
+                r = ee.edge_refiners[lv]
+                conv(f"ee.{lv}.c1", r.conv1)
+                conv(f"ee.{lv}.c2", r.conv2)
+                conv(f"ee.{lv}.c3", r.conv3)
+                conv(f"ee.{lv}.proj", r.proj)
+                conv(f"ee.{lv}.a0", r.attn.attn[0])
+                conv(f"ee.{lv}.a2", r.attn.attn[2])
+            conv("ee.f0", ee.fusion[0])
+            conv("ee.f2", ee.fusion[2])
+            conv("ee.g0", ee.edge_gate[0])
+            conv("ee.g2", ee.edge_gate[2])
+            w["ee.gauss"] = ee.gaussian.kernel.detach().float()[0, 0].reshape(25).contiguous()
+        self._wkey = key
+
+    # ---------------------------------------------------------------- utilities
+    @staticmethod
+    def _get_stream(dev):
+        return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    @staticmethod
+    def _sm_count(dev):
+        return torch.cuda.get_device_properties(dev).multi_processor_count
+
+    def _buf(self, name, shape, dev, dtype=torch.float32, zero=False, fresh=False):
+        """Persistent workspace keyed by (name, shape): allocated once, reused across calls
+        (padding channels are zeroed once and never written)."""
+        if fresh:
+            return torch.zeros(shape, device=dev, dtype=dtype) if zero else torch.empty(shape, device=dev, dtype=dtype)
+        key = (name, tuple(shape), str(dev), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.zeros(shape, device=dev, dtype=dtype)
+            self._ws[key] = t
+        return t
+
+    def _call(self, fn, *args):
+        rc = fn(*args)
+        self.launches += 1
+        if rc != 0:
+            K.check(rc, fn.__name__)
+
+    def conv(self, x: _View, N, H, W, Cin, wname, Cout, ks, out: _View, act=K.ACT_NONE, epi=K.EPI_PLAIN,
+             bias=True, r1: Optional[_View] = None, r2: Optional[_View] = None, sa=1.0, sa_ptr=None, sb=1.0,
+             sb_ptr=None, ch_k=None, ch_d=None, groups=1, bias_name=None):
+        w = self._w[wname]
+        assert w.shape[-3:] == (ks * ks, Cin, Cout) or w.numel() == groups * ks * ks * Cin * Cout, \
+            (wname, tuple(w.shape), ks, Cin, Cout)
+        b = self._w.get(bias_name or (wname + ".b")) if bias else None
+        p = K.ConvParams()
+        p.inp, p.in_sN, p.in_sY, p.in_sX, p.in_sC = x.ptr, x.sN, x.sY, x.sX, x.sC
+        p.N, p.H, p.W, p.Cin, p.Cout, p.ksize = N, H, W, Cin, Cout, ks
+        p.w = w.data_ptr()
+        p.bias = b.data_ptr() if b is not None else None
+        p.groups = groups
+        p.out, p.out_sN, p.out_sY, p.out_sX = out.ptr, out.sN, out.sY, out.sX
+        p.act, p.epi = act, epi
+        if r1 is not None:
+            p.r1, p.r1_sN, p.r1_sY, p.r1_sX = r1.ptr, r1.sN, r1.sY, r1.sX
+        if r2 is not None:
+            p.r2, p.r2_sN, p.r2_sY, p.r2_sX = r2.ptr, r2.sN, r2.sY, r2.sX
+        p.sa, p.sb = sa, sb
+        p.sa_ptr = sa_ptr.data_ptr() if sa_ptr is not None else None
+        p.sb_ptr = sb_ptr.data_ptr() if sb_ptr is not None else None
+        p.ch_k = ch_k.data_ptr() if ch_k is not None else None
+        p.ch_d = ch_d.data_ptr() if ch_d is not None else None
+        p.in_dtype = K.DT_BF16 if x.t.dtype == torch.bfloat16 else K.DT_F32
+        p.out_dtype = K.DT_BF16 if out.t.dtype == torch.bfloat16 else K.DT_F32
+        ev = self.timed_layers.get(wname) if self.timed_layers is not None else None
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream())
+            self._call(self.lib.ffsr_conv2d, C.byref(p), self._stream)
+            e1.record(torch.cuda.current_stream())
+            ev.append((e0, e1))
+            return
+        self._call(self.lib.ffsr_conv2d, C.byref(p), self._stream)
+
+    def _lka_block(self, key, blk, x: torch.Tensor, name: str) -> torch.Tensor:
+        """x: [N,H,W,C] fp32 -> LKABlock(x) (large_kernel_attention.py:143-149), eval-mode BN folded."""
+        N, H, W, Cc = x.shape
+        dev, w = x.device, self._w
+        t1 = self._buf(name + ".t1", x.shape, dev)
+        t2 = self._buf(name + ".t2", x.shape, dev)
+        a = self._buf(name + ".a", x.shape, dev)
+        self._call(self.lib.ffsr_lka_depthwise, x.data_ptr(), N, H, W, Cc, w[key + ".k1"].data_ptr(),
+                   w[key + ".d1"].data_ptr(), w[key + ".w5"].data_ptr(), w[key + ".wh"].data_ptr(),
+                   w[key + ".wv"].data_ptr(), t1.data_ptr(), t2.data_ptr(), a.data_ptr(), self._stream)
+        self.launches += 2
+        x1 = t1   # t1 is free again after the depthwise chain
+        self.conv(nhwc(a), N, H, W, Cc, key + ".pw", Cc, 1, nhwc(x1), epi=K.EPI_LKAGATE, bias_name=key + ".pwb",
+                  r1=nhwc(x), sa_ptr=blk.scale1, ch_k=w[key + ".k1"], ch_d=w[key + ".d1"])
+        hdn = self._buf(name + ".h", (N, H, W, 2 * Cc), dev)
+        self.conv(nhwc(x1), N, H, W, Cc, key + ".f0", 2 * Cc, 1, nhwc(hdn), act=K.ACT_GELU, bias_name=key + ".f0b")
+        x2 = t2
+        self.conv(nhwc(hdn), N, H, W, 2 * Cc, key + ".f2", Cc, 1, nhwc(x2), epi=K.EPI_RESIDUAL, bias_name=key + ".f2b",
+                  r1=nhwc(x1), sa_ptr=blk.scale2)
+        return x2
+
+    def _twiddles(self, n, dev):
+        key = (n, str(dev))
+        t = self._tw.get(key)
+        if t is None:
+            t = torch.empty(n, 2, device=dev, dtype=torch.float64)
+            self._call(self.lib.ffsr_fft_twiddles, n, t.data_ptr(), self._stream)
+            self._tw[key] = t
+        return t
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, lr: torch.Tensor, img_list: List[torch.Tensor], feats: Dict[str, torch.Tensor],
+                Hh: int, Wh: int, want_inter: bool):
+        m, lib = self.m, self.lib
+        if not lr.is_cuda:
+            raise RuntimeError("CompleteEnhancedFusionSR (sm_100a build) needs CUDA tensors: there is no CPU path")
+        dev = lr.device
+        if self._checked_dev != dev:
+            with torch.cuda.device(dev):
+                K.check(lib.ffsr_device_check(), "device_check")
+            self._checked_dev = dev
+        if len(img_list) != 4:
+            raise ValueError(f"expected the 4 expert outputs drct/grl/nafnet/mamba, got {len(img_list)}")
+        B, Cc, H, W = lr.shape
+        if Cc != 3 or H < 8 or W < 8:
+            raise ValueError("lr_input must be [B,3,H,W] with H,W >= 8 (7-px reflect pad of the db4 DWT)")
+        for t in img_list:
+            if tuple(t.shape) != (B, 3, 4 * H, 4 * W):
+                raise ValueError(f"expert image shape {tuple(t.shape)} != {(B, 3, 4 * H, 4 * W)}")
+        with torch.cuda.device(dev):
+            return self._forward(lr, img_list, feats, B, H, W, want_inter)
+
+    def _forward(self, lr, img_list, feats, B, H, W, want_inter):
+        m, lib, w = self.m, self.lib, None
+        dev = lr.device
+        self._stream = self._get_stream(dev)
+        self._prepare(dev)
+        w = self._w
+        self.launches = 0
+        S = self._stream
+        f32 = torch.float32
+        Hh, Wh = 4 * H, 4 * W
+        lr = lr.detach().to(f32).contiguous()            # fp16 caches are up-cast at the boundary
+        imgs = [t.detach().to(f32).contiguous() for t in img_list]
+        fr = want_inter                                   # intermediates are handed out: use fresh buffers
+
+        # ---------------- Phase 2 ----------------
+        fd = m.freq_decomp
+        raw9 = self._buf("raw9", (B, 9, 3, H, W), dev, fresh=fr)
+        self._call(lib.ffsr_dct_bands, lr.data_ptr(), B, H, W, fd.dct.dct_basis.data_ptr(), fd.dct.dct_basis_t.data_ptr(),
+                   fd.dct.low_mask.data_ptr(), fd.dct.mid_mask.data_ptr(), fd.dct.high_mask.data_ptr(),
+                   fd.dct.band_scale.data_ptr(), raw9.data_ptr(), S)
+        hs, ws_ = C.c_int(), C.c_int()
+        lib.ffsr_dwt_sub_size(H, W, C.byref(hs), C.byref(ws_))
+        sub = self._buf("dwt.sub", (B, 4, 3, hs.value, ws_.value), dev)
+        self._call(lib.ffsr_dwt_bands, lr.data_ptr(), B, H, W, fd.dwt.lo_row.data_ptr(), fd.dwt.hi_row.data_ptr(),
+                   fd.dwt.lo_col.data_ptr(), fd.dwt.hi_col.data_ptr(), fd.dwt.subband_scale.data_ptr(),
+                   sub.data_ptr(), raw9.data_ptr(), S)
+        self.launches += 1
+        fft_bytes = lib.ffsr_fft_workspace_bytes(B, H, W)
+        fws = self._buf("fft.ws", (fft_bytes // 8 + 2,), dev, dtype=torch.float64)
+        ms = fd.fft.freq_mask_logits.shape[-1]
+        self._call(lib.ffsr_fft_bands, lr.data_ptr(), B, H, W, fd.fft.freq_mask_logits.data_ptr(), ms,
+                   fd.fft.temperature.data_ptr(), fd.fft.band_scale.data_ptr(), self._twiddles(H, dev).data_ptr(),
+                   self._twiddles(W, dev).data_ptr(), fws.data_ptr(), fft_bytes, raw9.data_ptr(), S)
+        self.launches += 4
+
+        # ---------------- Phase 3 ----------------
+        cb = m.cross_band
+        nq = 9 if want_inter else 3                       # bands 3..8 feed nothing downstream
+        tok = self._buf("cb.tok", (B * nq, H, W, 64), dev)
+        nsm = self._sm_count(dev)
+        self._call(lib.ffsr_crossband_attention, raw9.data_ptr(), B, H, W, w["cb.proj_w"].data_ptr(),
+                   cb.band_proj.bias.data_ptr(), cb.norm.weight.data_ptr(), cb.norm.bias.data_ptr(),
+                   cb.band_attention.in_proj_weight.data_ptr(), cb.band_attention.in_proj_bias.data_ptr(),
+                   cb.band_attention.out_proj.weight.data_ptr(), cb.band_attention.out_proj.bias.data_ptr(),
+                   nq, tok.data_ptr(), nsm, S)
+        x2 = self._lka_block("cb.lka", cb.lka_block, tok, "cb%d" % nq)
+        enh9 = self._buf("enh9", (B, 9, 3, H, W), dev, fresh=fr)
+        routing = self._buf("routing", (B, 3, H, W), dev, fresh=fr)
+        self._call(lib.ffsr_crossband_out, x2.data_ptr(), raw9.data_ptr(), B, H, W, nq, w["cb.out_w"].data_ptr(),
+                   cb.out_proj.bias.data_ptr(), enh9.data_ptr(), routing.data_ptr(), S)
+
+        # ---------------- Phase 6 (selector nets, fp32) ----------------
+        ds = m.dynamic_selector
+        s_a = self._buf("ds.a", (B, H, W, 32), dev)
+        s_b = self._buf("ds.b", (B, H, W, 32), dev)
+        diff = self._buf("diff", (B, 1, H, W), dev, fresh=fr)
+        graw = self._buf("ds.raw", (B, H, W, 4), dev)
+        gates = self._buf("gates", (B, 4, H, W), dev, fresh=fr)
+        rv = nchw(routing)
+        self.conv(rv, B, H, W, 3, "ds.d0", 32, 3, nhwc(s_a), act=K.ACT_RELU)
+        self.conv(nhwc(s_a), B, H, W, 32, "ds.d2", 32, 3, nhwc(s_b), act=K.ACT_RELU)
+        self.conv(nhwc(s_b), B, H, W, 32, "ds.d4", 1, 3, nhwc(diff.view(B, H, W, 1)), act=K.ACT_SIGMOID)
+        self.conv(rv, B, H, W, 3, "ds.g0", 32, 3, nhwc(s_a), act=K.ACT_RELU)
+        self.conv(nhwc(s_a), B, H, W, 32, "ds.g2", 32, 3, nhwc(s_b), act=K.ACT_RELU)
+        self.conv(nhwc(s_b), B, H, W, 32, "ds.g4", 4, 1, nhwc(graw))
+        self._call(lib.ffsr_gate_finalize, graw.data_ptr(), diff.data_ptr(), B, H, W, ds.temperature.data_ptr(),
+                   gates.data_ptr(), S)
+
+        # ---------------- Phase 4 (LR part) ----------------
+        co = m.collaborative
+        have = [n for n in EXPERT_ORDER if n in feats]
+        m32 = None
+        if have:
+            for n in have:
+                f = feats[n]
+                if f.dim() != 4 or f.shape[0] != B or tuple(f.shape[2:]) != (H, W):
+                    raise NotImplementedError(
+                        f"expert feature '{n}' has shape {tuple(f.shape)}; the sm_100a path needs [B,C,{H},{W}] "
+                        "(features at LR resolution, as CachedSRDataset provides)")
+            tokens = self._buf("co.tok", (B, 4, H, W, 128), dev, zero=True)
+            if len(have) < 4:
+                tokens.zero_()                              # missing expert -> zero token (:378-381)
+            for e, n in enumerate(EXPERT_ORDER):
+                if n not in feats:
+                    continue
+                f = feats[n].detach().to(f32).contiguous()
+                cin_w = co.align_layers[n].weight.shape[1]
+                cin = min(f.shape[1], cin_w)               # truncate / implicit zero-pad (:349-358)
+                wn = "co.align." + n
+                if cin != cin_w:
+                    wn2 = wn + ".c%d" % cin
+                    if wn2 not in w:
+                        w[wn2] = w[wn][:, :cin, :].contiguous()
+                        w[wn2 + ".b"] = w[wn + ".b"]
+                    wn = wn2
+                tv = tokens[:, e]
+                ov = _View(tv.data_ptr(), tokens.stride(0), tokens.stride(2), tokens.stride(3), 1, tokens)
+                self.conv(nchw(f), B, H, W, cin, wn, 128, 1, ov)
+            N4 = B * 4
+            tok4 = tokens.view(N4, H, W, 128)
+            rows = N4 * H * W
+            n1 = self._buf("co.n", (N4, H, W, 128), dev)
+            self._call(lib.ffsr_layernorm, tok4.data_ptr(), rows, 128, co.norm1.weight.data_ptr(),
+                       co.norm1.bias.data_ptr(), n1.data_ptr(), 0, S)
+            qkv = self._buf("co.qkv", (N4, H, W, 384), dev)
+            self.conv(nhwc(n1), N4, H, W, 128, "co.qkv", 384, 1, nhwc(qkv))
+            ctx = self._buf("co.ctx", (N4, H, W, 128), dev)
+            self._call(lib.ffsr_token_attention, qkv.data_ptr(), B, 4, H * W, 128, ctx.data_ptr(), 0, S)
+            t1 = self._buf("co.t1", (N4, H, W, 128), dev)
+            self.conv(nhwc(ctx), N4, H, W, 128, "co.out", 128, 1, nhwc(t1), epi=K.EPI_RESIDUAL, r1=nhwc(tok4))
+            self._call(lib.ffsr_layernorm, t1.data_ptr(), rows, 128, co.norm2.weight.data_ptr(),
+                       co.norm2.bias.data_ptr(), n1.data_ptr(), 0, S)
+            hdn = self._buf("co.h", (N4, H, W, 256), dev)
+            self.conv(nhwc(n1), N4, H, W, 128, "co.f0", 256, 1, nhwc(hdn), act=K.ACT_GELU)
+            t2 = self._buf("co.t2", (N4, H, W, 128), dev)
+            self.conv(nhwc(hdn), N4, H, W, 256, "co.f2", 128, 1, nhwc(t2), epi=K.EPI_RESIDUAL, r1=nhwc(t1))
+            xg = self._lka_block("co.lka", co.lka_global, t2, "co")
+            m32 = self._buf("co.m32", (N4, H, W, 32), dev)
+            self.conv(nhwc(xg), N4, H, W, 128, "co.m0", 32, 1, nhwc(m32), groups=4, bias_name="co.m0b")
+
+        # ---------------- HR: modulation + expert pyramid ----------------
+        ecol = self._buf("ecol", (B, 4, 3, Hh, Wh), dev, fresh=fr)
+        cat3 = self._buf("cat3", (B, Hh, Wh, 80), dev, zero=True)
+        cat2 = self._buf("cat2", (B, 2 * H, 2 * W, 80), dev, zero=True)
+        s1in = self._buf("s1in", (B, H, W, 16), dev, zero=True)
+        ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in imgs])
+        self._call(lib.ffsr_modulate_hr, ptrs, m32.data_ptr() if m32 is not None else None,
+                   w["co.m2"].data_ptr(), w["co.m2b"].data_ptr(), B, H, W, 0 if m.training else 1, ecol.data_ptr(),
+                   cat3.data_ptr() + 64 * 4, 80, K.DT_F32, S)
+        self._call(lib.ffsr_expert_downsample, ecol.data_ptr(), B, Hh, Wh, cat2.data_ptr() + 64 * 4, 80,
+                   s1in.data_ptr(), 16, K.DT_F32, S)
+
+        # ---------------- Phase 5: hierarchical fusion ----------------
+        mr = m.multi_res
+
+        def stage(name, xin: _View, cin, h, wd, c_mid, c_out, r2=None, sb_ptr=None):
+            a = self._buf(name + ".a", (B, h, wd, c_mid), dev)
+            b_ = self._buf(name + ".b", (B, h, wd, c_out), dev)
+            c_ = self._buf(name + ".c", (B, h, wd, c_out), dev)
+            self.conv(xin, B, h, wd, cin, f"mr.{name}.c0", c_mid, 3, nhwc(a), act=K.ACT_GELU)
+            self.conv(nhwc(a), B, h, wd, c_mid, f"mr.{name}.c2", c_out, 3, nhwc(b_), act=K.ACT_GELU)
+            g = getattr(mr, name + "_gate").gate
+            self._call(lib.ffsr_spatial_gate, b_.data_ptr(), B * h * wd, c_out, w[f"mr.{name}.g0"].data_ptr(),
+                       g[0].bias.data_ptr(), w[f"mr.{name}.g2"].data_ptr(), g[2].bias.data_ptr(), b_.data_ptr(),
+                       K.DT_F32, S)
+            d_ = self._buf(name + ".d", (B, h, wd, c_out), dev)
+            self.conv(nhwc(b_), B, h, wd, c_out, f"mr.{name}.r0", c_out, 3, nhwc(d_), act=K.ACT_GELU, bias=False)
+            self.conv(nhwc(d_), B, h, wd, c_out, f"mr.{name}.r2", c_out, 3, nhwc(c_), bias=False, epi=K.EPI_RESIDUAL,
+                      r1=nhwc(b_), sa_ptr=getattr(mr, name + "_res").scale, r2=r2, sb_ptr=sb_ptr)
+            return c_
+
+        f1 = stage("stage1", nhwc(s1in), 12, H, W, 64, 64)
+        self._call(lib.ffsr_resize_nhwc, f1.data_ptr(), B, H, W, 64, 64, cat2.data_ptr(), 2 * H, 2 * W, 80, K.DT_F32, S)
+        f2 = stage("stage2", nhwc(cat2), 76, 2 * H, 2 * W, 64, 64, r2=nhwc(cat2), sb_ptr=mr.residual_weight_1_2)
+        self._call(lib.ffsr_resize_nhwc, f2.data_ptr(), B, 2 * H, 2 * W, 64, 64, cat3.data_ptr(), Hh, Wh, 80, K.DT_F32, S)
+        f3 = stage("stage3", nhwc(cat3), 76, Hh, Wh, 64, 32, r2=nhwc(cat3), sb_ptr=mr.residual_weight_2_3)
+        u16 = self._buf("mr.u16", (B, Hh, Wh, 16), dev)
+        hier = self._buf("mr.hier", (B, Hh, Wh, 4), dev, zero=True)
+        self.conv(nhwc(f3), B, Hh, Wh, 32, "mr.rgb0", 16, 3, nhwc(u16), act=K.ACT_GELU)
+        self.conv(nhwc(u16), B, Hh, Wh, 16, "mr.rgb2", 3, 3, nhwc(hier), act=K.ACT_SIGMOID)
+
+        # ---------------- Phase 5b / 6 blend ----------------
+        fused_before = torch.empty(B, 3, Hh, Wh, device=dev, dtype=f32) if want_inter else None
+        fusedx = self._buf("fusedx", (B, Hh, Wh, 4), dev, zero=True)
+        self._call(lib.ffsr_blend_hr, hier.data_ptr(), 4, ecol.data_ptr(), routing.data_ptr(), gates.data_ptr(),
+                   diff.data_ptr(), w["fw0"].data_ptr(), m.freq_weight_conv[0].bias.data_ptr(), w["fw2"].data_ptr(),
+                   m.freq_weight_conv[2].bias.data_ptr(), B, H, W,
+                   fused_before.data_ptr() if fused_before is not None else None, fusedx.data_ptr(), 4, None, 0, S)
+
+        # ---------------- Phase 7a: refinement ----------------
+        idx = self._refine_idx
+        rc = m.refine[idx[0]].weight.shape[0]
+        ping = self._buf("rf.ping", (B, Hh, Wh, rc), dev)
+        pong = self._buf("rf.pong", (B, Hh, Wh, rc), dev)
+        cat6 = self._buf("cat6", (B, Hh, Wh, 8), dev, zero=True)
+        self.conv(nhwc(fusedx), B, Hh, Wh, 3, f"rf.{idx[0]}", rc, 3, nhwc(ping), act=K.ACT_GELU)
+        cur, nxt = ping, pong
+        for i in idx[1:-1]:
+            self.conv(nhwc(cur), B, Hh, Wh, rc, f"rf.{i}", rc, 3, nhwc(nxt), act=K.ACT_GELU)
+            cur, nxt = nxt, cur
+        self.conv(nhwc(cur), B, Hh, Wh, rc, f"rf.{idx[-1]}", 3, 3, nhwc(cat6), epi=K.EPI_RESIDUAL, r1=nhwc(fusedx), sa=0.1)
+
+        # ---------------- Phase 7b: Laplacian pyramid edge enhancement ----------------
+        ee = m.edge_enhance
+        g25 = w["ee.gauss"].data_ptr()
+        down1 = self._buf("ee.down1", (B, 2 * H, 2 * W, 4), dev, zero=True)
+        down2 = self._buf("ee.down2", (B, H, W, 4), dev, zero=True)
+        lap0 = self._buf("ee.lap0", (B, Hh, Wh, 4), dev, zero=True)
+        lap1 = self._buf("ee.lap1", (B, 2 * H, 2 * W, 4), dev, zero=True)
+        self._call(lib.ffsr_blur_pool, cat6.data_ptr(), 8, B, Hh, Wh, g25, down1.data_ptr(), 4, S)
+        self._call(lib.ffsr_laplacian_sub, cat6.data_ptr(), 8, down1.data_ptr(), 4, B, Hh, Wh, lap0.data_ptr(), 4, S)
+        self._call(lib.ffsr_blur_pool, down1.data_ptr(), 4, B, 2 * H, 2 * W, g25, down2.data_ptr(), 4, S)
+        self._call(lib.ffsr_laplacian_sub, down1.data_ptr(), 4, down2.data_ptr(), 4, B, 2 * H, 2 * W, lap1.data_ptr(), 4, S)
+        cat96 = self._buf("ee.cat96", (B, Hh, Wh, 96), dev)
+        for lv, (lap, h, wd) in enumerate(((lap0, Hh, Wh), (lap1, 2 * H, 2 * W), (down2, H, W))):
+            nm = f"ee{lv}"
+            idt = self._buf(nm + ".idt", (B, h, wd, 32), dev)
+            o1 = self._buf(nm + ".o1", (B, h, wd, 32), dev)
+            o2 = self._buf(nm + ".o2", (B, h, wd, 32), dev)
+            t8 = self._buf(nm + ".t8", (B, h, wd, 8), dev)
+            at = self._buf(nm + ".at", (B, h, wd, 1), dev)
+            self.conv(nhwc(lap), B, h, wd, 3, f"ee.{lv}.proj", 32, 1, nhwc(idt))
+            self.conv(nhwc(lap), B, h, wd, 3, f"ee.{lv}.c1", 32, 3, nhwc(o1), act=K.ACT_GELU)
+            self.conv(nhwc(o1), B, h, wd, 32, f"ee.{lv}.c2", 32, 3, nhwc(o2), act=K.ACT_GELU)
+            self.conv(nhwc(o2), B, h, wd, 32, f"ee.{lv}.c3", 32, 3, nhwc(o1), epi=K.EPI_RESIDUAL, r1=nhwc(idt))
+            self.conv(nhwc(o1), B, h, wd, 32, f"ee.{lv}.a0", 8, 1, nhwc(t8), act=K.ACT_GELU)
+            self.conv(nhwc(t8), B, h, wd, 8, f"ee.{lv}.a2", 1, 3, nhwc(at), act=K.ACT_SIGMOID)
+            self._call(lib.ffsr_edge_attn_upsample, o1.data_ptr(), at.data_ptr(), B, h, wd, 32,
+                       ee.level_weights.data_ptr(), lv, cat96.data_ptr() + 32 * lv * 4, Hh, Wh, 96, K.DT_F32, S)
+        e32 = self._buf("ee.e32", (B, Hh, Wh, 32), dev)
+        self.conv(nhwc(cat96), B, Hh, Wh, 96, "ee.f0", 32, 3, nhwc(e32), act=K.ACT_GELU)
+        self.conv(nhwc(e32), B, Hh, Wh, 32, "ee.f2", 3, 3, nhwc(cat6, 3))
+        g16 = self._buf("ee.g16", (B, Hh, Wh, 16), dev)
+        egate = self._buf("ee.gate", (B, Hh, Wh, 1), dev)
+        self.conv(nhwc(cat6), B, Hh, Wh, 6, "ee.g0", 16, 3, nhwc(g16), act=K.ACT_GELU)
+        self.conv(nhwc(g16), B, Hh, Wh, 16, "ee.g2", 1, 3, nhwc(egate), act=K.ACT_SIGMOID)
+
+        # ---------------- output ----------------
+        out = torch.empty(B, 3, Hh, Wh, device=dev, dtype=f32)
+        self._call(lib.ffsr_final_combine, cat6.data_ptr(), 8, egate.data_ptr(), ee.edge_strength.data_ptr(),
+                   lr.data_ptr(), m.residual_scale.data_ptr(), B, H, W, 0 if m.training else 1, out.data_ptr(), S)
+
+        inter = {}
+        if want_inter:
+            inter["raw_9_bands"] = [raw9[:, i] for i in range(9)]
+            inter["guidance_bands"] = inter["raw_9_bands"][:3]
+            inter["enhanced_9_bands"] = [enh9[:, i] for i in range(9)]
+            inter["routing_lr"] = routing
+            if m32 is not None:
+                inter["collaborative_outputs"] = [ecol[:, e] for e in range(4)]
+            inter["fused_before_dynamic"] = fused_before
+            inter["gates"] = gates
+            inter["difficulty"] = diff
+        return out, inter

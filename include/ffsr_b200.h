@@ -1,0 +1,179 @@
+/* ffsr_b200.h -- C ABI of libffsr_b200.so, the sm_100a kernel library behind the
+ * drop-in CompleteEnhancedFusionSR module (image-super-resolution_b200/fusion.py).
+ *
+ * The reference (Nikhil-AI-Labs/Image-Super-Resolution) is pure Python/PyTorch: it has no
+ * FFI of its own.  The "interface each entry point replaces" is therefore the PyTorch op
+ * sequence at the cited reference file:line (all relative to the reference root); the
+ * binding a maintainer adds is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions:
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator),
+ *    including scratch; kernels never allocate, free or synchronise the host;
+ *  - work is enqueued on the cudaStream_t passed in (never the legacy default stream
+ *    implicitly); entry points are re-entrant across streams;
+ *  - return 0 on success, <0 on error (FFSR_ERR_*); ffsr_last_error() gives the message;
+ *  - sm_100a only: there is no fallback path, ffsr_device_check() fails elsewhere.
+ *  - scalar nn.Parameters (scales, temperatures) are passed as device pointers so that no
+ *    host sync (.item()) is needed.
+ */
+#ifndef FFSR_B200_H
+#define FFSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define FFSR_OK 0
+#define FFSR_ERR_ARG (-1)
+#define FFSR_ERR_ALIGN (-2)
+#define FFSR_ERR_LAUNCH (-3)
+#define FFSR_ERR_DRIVER (-4)
+
+#define FFSR_ACT_NONE 0
+#define FFSR_ACT_GELU 1
+#define FFSR_ACT_RELU 2
+#define FFSR_ACT_SIGMOID 3
+
+#define FFSR_EPI_PLAIN 0    /* out = act(conv + bias)                                        */
+#define FFSR_EPI_RESIDUAL 1 /* out = r1 + sa*act(conv + bias) + sb*r2          (r2 optional) */
+#define FFSR_EPI_LKAGATE 2  /* out = r1 + sa*(r1*ch_k[c] + ch_d[c])*sigmoid(conv + bias)     */
+
+#define FFSR_DT_F32 0
+#define FFSR_DT_BF16 1
+
+const char* ffsr_last_error(void);
+const char* ffsr_version(void);
+/* 0 iff the current device is compute capability 10.x; message otherwise. */
+int ffsr_device_check(void);
+
+/* ---- Phase 2: 9 sub-bands, raw9[B][9][3][H][W] fp32 ------------------------------------
+ * DCTDecomposition.forward      src/models/multi_domain_frequency.py:146-196 */
+int ffsr_dct_bands(const float* lr, int B, int H, int W, const float* basis, const float* basis_t,
+                   const float* m_low, const float* m_mid, const float* m_high, const float* band_scale,
+                   float* raw9, cudaStream_t stream);
+/* DWTDecomposition.forward      src/models/multi_domain_frequency.py:251-299
+ * sub_ws: float[B*12*Hs*Ws] with (Hs,Ws) from ffsr_dwt_sub_size */
+int ffsr_dwt_sub_size(int H, int W, int* Hs, int* Ws);
+int ffsr_dwt_bands(const float* lr, int B, int H, int W, const float* lo_row, const float* hi_row,
+                   const float* lo_col, const float* hi_col, const float* subband_scale, float* sub_ws,
+                   float* raw9, cudaStream_t stream);
+/* FFTDecomposition.forward      src/models/multi_domain_frequency.py:352-385
+ * tw_h / tw_w: double2[H] / double2[W] tables from ffsr_fft_twiddles; ws from ffsr_fft_workspace_bytes */
+int ffsr_fft_twiddles(int n, void* out, cudaStream_t stream);
+size_t ffsr_fft_workspace_bytes(int B, int H, int W);
+int ffsr_fft_bands(const float* lr, int B, int H, int W, const float* logits, int mask_size,
+                   const float* temperature, const float* band_scale, const void* tw_h, const void* tw_w,
+                   void* ws, size_t ws_bytes, float* raw9, cudaStream_t stream);
+
+/* ---- Phase 3: cross-band attention -------------------------------------------------------
+ * EnhancedCrossBandWithLKA.forward steps 1-2  src/models/large_kernel_attention.py:219-233
+ * tok_out[B][nq][H][W][64]: attention output (+residual) of the first nq bands */
+int ffsr_crossband_attention(const float* raw9, int B, int H, int W, const float* proj_w, const float* proj_b,
+                             const float* ln_w, const float* ln_b, const float* in_w, const float* in_b,
+                             const float* out_w, const float* out_b, int nq, float* tok_out, int num_sms,
+                             cudaStream_t stream);
+/* out_proj + band residual (:240-241) and routing_lr = bands 0+1+2 (enhanced_fusion_v2.py:713) */
+int ffsr_crossband_out(const float* x, const float* raw9, int B, int H, int W, int nq, const float* w,
+                       const float* bias, float* enh9, float* routing, cudaStream_t stream);
+
+/* ---- LKA depthwise chain (BN1 affine -> dw5x5 -> dw1x21 -> dw21x1) -----------------------
+ * LargeKernelAttention.forward  src/models/large_kernel_attention.py:98-100; x,out: [N][H][W][C] */
+int ffsr_lka_depthwise(const float* x, int N, int H, int W, int C, const float* bn_k, const float* bn_d,
+                       const float* w5, const float* wh, const float* wv, float* tmp1, float* tmp2, float* out,
+                       cudaStream_t stream);
+
+/* ---- token helpers (Phase 4) -------------------------------------------------------------
+ * nn.LayerNorm rows (large_kernel_attention.py:389,392) and the softmax(QK^T/4)V core of
+ * nn.MultiheadAttention (:390) for T tokens per LR pixel, head_dim 16; token-major layout
+ * qkv[B][T][HW][3E] -> ctx[B][T][HW][E] */
+int ffsr_layernorm(const float* x, long rows, int E, const float* w, const float* b, void* y, int out_bf16,
+                   cudaStream_t stream);
+int ffsr_token_attention(const void* qkv, int B, int T, long HW, int E, void* ctx, int is_bf16, cudaStream_t stream);
+
+/* ---- Phase 6 gate normalisation  src/models/enhanced_fusion_v2.py:462-465 ---------------- */
+int ffsr_gate_finalize(const float* raw, const float* diff, int B, int H, int W, const float* temperature,
+                       float* gates, cudaStream_t stream);
+
+/* ---- generic convolution (1x1 / 3x3, zero pad k/2, stride 1) -----------------------------
+ * Replaces every nn.Conv2d / nn.Linear on the path.  Input element
+ * (n,y,x,c) lives at in + n*in_sN + y*in_sY + x*in_sX + c*in_sC (element strides: NHWC or
+ * NCHW views, channel slices of concat buffers).  Output and residuals are channels-last
+ * (channel stride 1).  Weights are packed [groups][k*k][Cin][Cout] fp32; image n uses weight
+ * set n % groups. */
+typedef struct ffsr_conv_params {
+  const void* in;
+  long long in_sN, in_sY, in_sX, in_sC;
+  int N, H, W, Cin, Cout, ksize;
+  const float* w;
+  const float* bias; /* [groups][Cout] or NULL */
+  int groups;
+  void* out;
+  long long out_sN, out_sY, out_sX;
+  int act; /* FFSR_ACT_* */
+  int epi; /* FFSR_EPI_* */
+  const float* r1;
+  long long r1_sN, r1_sY, r1_sX;
+  const float* r2;
+  long long r2_sN, r2_sY, r2_sX;
+  float sa;
+  const float* sa_ptr; /* effective sa = sa * (sa_ptr ? *sa_ptr : 1) */
+  float sb;
+  const float* sb_ptr;
+  const float* ch_k; /* per-channel affine of FFSR_EPI_LKAGATE */
+  const float* ch_d;
+  int in_dtype, out_dtype; /* FFSR_DT_* */
+} ffsr_conv_params;
+
+int ffsr_conv2d(const ffsr_conv_params* p, cudaStream_t stream);
+/* sizeof(ffsr_conv_params) as compiled into the library (bindings assert their layout against it) */
+size_t ffsr_conv_params_size(void);
+
+/* ---- HR-side fused elementwise kernels ---------------------------------------------------- */
+/* Phase 4 tail: bilinear x4 of the LR modulation features, GELU, 1x1 32->3, sigmoid,
+ * out*(1+0.2*(mod-0.5)), clamp (eval)   src/models/large_kernel_attention.py:410-424
+ * imgs: 4 pointers to [B][3][Hh][Wh]; m32: [B][4][H][W][32] (NULL: Phase 4 skipped, E = imgs);
+ * w2: [4][3][32], b2: [4][3];  ecol: [B][4][3][Hh][Wh] fp32;  cat3: NHWC concat buffer slice */
+int ffsr_modulate_hr(const float* const* imgs, const float* m32, const float* w2, const float* b2, int B, int H,
+                     int W, int clamp01, float* ecol, void* cat3, long long cat3_sX, int cat3_dtype,
+                     cudaStream_t stream);
+/* bilinear /2 and /4 of the expert stack (hierarchical_fusion.py:156-159, 171-174) into the
+ * stage-2 concat buffer slice and the stage-1 input */
+int ffsr_expert_downsample(const float* ecol, int B, int Hh, int Wh, void* cat2, long long cat2_sX, void* s1in,
+                           long long s1_sX, int dtype, cudaStream_t stream);
+/* bilinear resize of a channels-last tensor into a channel slice (hierarchical_fusion.py:166-169,183-186) */
+int ffsr_resize_nhwc(const void* src, int N, int h, int w, int C, long long src_sX, void* dst, int H, int W,
+                     long long dst_sX, int dtype, cudaStream_t stream);
+/* SpatialGate: x * sigmoid(w2 . gelu(W1 x + b1) + b2)   hierarchical_fusion.py:25-43 (in place allowed) */
+int ffsr_spatial_gate(const void* x, long pixels, int C, const float* w1, const float* b1, const float* w2,
+                      const float* b2, void* y, int dtype, cudaStream_t stream);
+/* Phase 5b/5c/6 blend   src/models/enhanced_fusion_v2.py:735-774 */
+int ffsr_blend_hr(const float* hier, long long hier_sX, const float* ecol, const float* routing, const float* gates,
+                  const float* diff, const float* fw0_w, const float* fw0_b, const float* fw2_w, const float* fw2_b,
+                  int B, int H, int W, float* fused_before, float* fused_nhwc, long long fused_sX, void* fused_lp,
+                  long long fused_lp_sX, cudaStream_t stream);
+/* Laplacian pyramid pieces   src/models/edge_enhancement.py:196-220 */
+int ffsr_blur_pool(const float* x, long long x_sX, int N, int H, int W, const float* gauss25, float* down,
+                   long long down_sX, cudaStream_t stream);
+int ffsr_laplacian_sub(const float* x, long long x_sX, const float* down, long long down_sX, int N, int H, int W,
+                       float* lap, long long lap_sX, cudaStream_t stream);
+/* refiner tail: (o * attn) [bilinear to HxW] * softmax(level_weights)[level] -> concat slice
+ * src/models/edge_enhancement.py:118, 243-250 */
+int ffsr_edge_attn_upsample(const float* o, const float* attn, int N, int h, int w, int C, const float* level_w,
+                            int level, void* dst, int H, int W, long long dst_sX, int dtype, cudaStream_t stream);
+/* out = clamp(x + gate*strength*edge, 0, 1) + residual_scale*bilinear_x4(lr) [clamp in eval]
+ * src/models/edge_enhancement.py:259-260, src/models/enhanced_fusion_v2.py:788-795 */
+int ffsr_final_combine(const float* xe, long long xe_sX, const float* gate, const float* strength, const float* lr,
+                       const float* residual_scale, int B, int H, int W, int clamp01, float* out,
+                       cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFSR_B200_H */

@@ -1,0 +1,274 @@
+"""GPU parity tests: the sm_100a path (through the C ABI) against the CPU oracle and the
+reference-generated golden fixtures.  Run on the B200 box: ``pytest tests -m gpu``.
+
+Tolerances (BASELINE.json north_star / SURVEY §8c):
+  fp32 path : max-abs <= 1e-4 on the SR output and on every exposed intermediate
+  indices   : argmax_e gates and (raw > thr) identical to the oracle
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import isr_b200
+from isr_b200 import _cabi as K
+from isr_b200.pipeline import FusionEngine, nhwc, nchw, _pack_conv
+from oracle import fusion_oracle as O
+from oracle.perturb import perturb_state_dict
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _model(perturbed=True, seed=0):
+    torch.manual_seed(seed)
+    m = isr_b200.CompleteEnhancedFusionSR(None)
+    if perturbed:
+        m.load_state_dict(perturb_state_dict(m.state_dict(), seed=7), strict=True)
+    return m.eval()
+
+
+def _to(dev, lr, imgs, fts):
+    return lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, ({k: v.to(dev) for k, v in fts.items()} if fts else None)
+
+
+def _engine(m, dev):
+    eng = FusionEngine(m)
+    eng._stream = eng._get_stream(dev)
+    eng._prepare(dev)
+    return eng
+
+
+# --------------------------------------------------------------------------------------------
+# unit level: generic conv against F.conv2d
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,ks,layout,act,epi", [
+    (3, 32, 3, "nchw", K.ACT_RELU, K.EPI_PLAIN),
+    (3, 128, 3, "nhwc", K.ACT_GELU, K.EPI_PLAIN),
+    (12, 64, 3, "nhwc", K.ACT_GELU, K.EPI_PLAIN),
+    (76, 64, 3, "nhwc", K.ACT_GELU, K.EPI_PLAIN),
+    (64, 64, 3, "nhwc", K.ACT_NONE, K.EPI_RESIDUAL),
+    (128, 128, 3, "nhwc", K.ACT_GELU, K.EPI_PLAIN),
+    (128, 3, 3, "nhwc", K.ACT_NONE, K.EPI_RESIDUAL),
+    (32, 1, 3, "nhwc", K.ACT_SIGMOID, K.EPI_PLAIN),
+    (96, 32, 3, "nhwc", K.ACT_GELU, K.EPI_PLAIN),
+    (180, 128, 1, "nchw", K.ACT_NONE, K.EPI_PLAIN),
+    (128, 384, 1, "nhwc", K.ACT_NONE, K.EPI_PLAIN),
+    (256, 128, 1, "nhwc", K.ACT_NONE, K.EPI_RESIDUAL),
+    (32, 4, 1, "nhwc", K.ACT_NONE, K.EPI_PLAIN),
+    (64, 64, 1, "nhwc", K.ACT_NONE, K.EPI_LKAGATE),
+])
+def test_conv2d_against_torch(cin, cout, ks, layout, act, epi):
+    dev = _cuda()
+    g = torch.Generator().manual_seed(cin * 1000 + cout * 10 + ks)
+    N, H, W = 2, 19, 37                                       # ragged vs the 8x16 tile
+    x = torch.randn(N, cin, H, W, generator=g)
+    wt = torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    r1 = torch.randn(N, cout, H, W, generator=g)
+    r2 = torch.randn(N, cout, H, W, generator=g)
+    chk, chd = torch.randn(cout, generator=g), torch.randn(cout, generator=g)
+    s_ptr = torch.tensor(0.37)
+    ref = F.conv2d(x.double(), wt.double(), b.double(), padding=ks // 2)
+    if epi == K.EPI_LKAGATE:
+        ref = r1.double() + 0.37 * (r1.double() * chk.double()[None, :, None, None] + chd.double()[None, :, None, None]) * torch.sigmoid(ref)
+    else:
+        ref = {K.ACT_NONE: lambda t: t, K.ACT_GELU: F.gelu, K.ACT_RELU: F.relu, K.ACT_SIGMOID: torch.sigmoid}[act](ref)
+        if epi == K.EPI_RESIDUAL:
+            ref = r1.double() + 0.5 * 0.37 * ref + 0.25 * r2.double()
+
+    m = _model(False)
+    eng = FusionEngine(m)
+    eng._stream = eng._get_stream(dev)
+    eng._w = {"t": _pack_conv(wt).to(dev), "t.b": b.to(dev)}
+    xin = x.to(dev).contiguous() if layout == "nchw" else x.permute(0, 2, 3, 1).contiguous().to(dev)
+    out = torch.full((N, H, W, cout + 3), 7.0, device=dev)     # write into a channel slice
+    r1d = r1.permute(0, 2, 3, 1).contiguous().to(dev)
+    r2d = r2.permute(0, 2, 3, 1).contiguous().to(dev)
+    with torch.cuda.device(dev):
+        eng.conv(nchw(xin) if layout == "nchw" else nhwc(xin), N, H, W, cin, "t", cout, ks, nhwc(out, 2),
+                 act=act, epi=epi, r1=nhwc(r1d) if epi else None, r2=nhwc(r2d) if epi == K.EPI_RESIDUAL else None,
+                 sa=0.5 if epi == K.EPI_RESIDUAL else 1.0, sa_ptr=s_ptr.to(dev) if epi else None, sb=0.25,
+                 ch_k=chk.to(dev) if epi == K.EPI_LKAGATE else None, ch_d=chd.to(dev) if epi == K.EPI_LKAGATE else None)
+        torch.cuda.synchronize()
+    got = out[..., 2:2 + cout].permute(0, 3, 1, 2).cpu().double()
+    assert (got - ref).abs().max().item() < 2e-5
+    assert torch.all(out[..., :2] == 7.0) and torch.all(out[..., 2 + cout:] == 7.0), "wrote outside its channel slice"
+
+
+def test_conv2d_rejects_bad_arguments():
+    dev = _cuda()
+    lib = K.load()
+    p = K.ConvParams()
+    p.ksize = 5
+    assert lib.ffsr_conv2d(C.byref(p), None) == -1            # null pointers / bad ksize
+    assert b"conv2d" in lib.ffsr_last_error()
+
+
+# --------------------------------------------------------------------------------------------
+# phase level against the oracle
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W", [(1, 16, 16), (2, 17, 23), (1, 8, 8), (1, 33, 47), (1, 40, 56)])
+def test_phase2_and_phase3_and_gates(B, H, W):
+    dev = _cuda()
+    m = _model(True)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    lr, imgs, fts, _ = O.synthetic_inputs(B, H, W)
+    with torch.no_grad():
+        raw = O.decompose9(sd, lr)
+        enh = O.cross_band(sd, raw)
+        routing = enh[0] + enh[1] + enh[2]
+        gates, diff = O.selector(sd, routing)
+        top1, active = O.derived_indices(sd, routing, gates)
+    m.to(dev)
+    lrd, imd, ftd = _to(dev, lr, imgs, fts)
+    sr, ints = m._run_pipeline(lrd, [imd[k] for k in O.EXPERT_ORDER], ftd, 4 * H, 4 * W, {}, True)
+    names = ["dct_low", "dct_mid", "dct_high", "dwt_LL", "dwt_LH", "dwt_HL", "dwt_HH", "fft_low", "fft_high"]
+    errs = {}
+    for i, n in enumerate(names):
+        errs["raw." + n] = (ints["raw_9_bands"][i].cpu() - raw[i]).abs().max().item()
+        errs["enh." + n] = (ints["enhanced_9_bands"][i].cpu() - enh[i]).abs().max().item()
+    errs["routing"] = (ints["routing_lr"].cpu() - routing).abs().max().item()
+    errs["gates"] = (ints["gates"].cpu() - gates).abs().max().item()
+    errs["difficulty"] = (ints["difficulty"].cpu() - diff).abs().max().item()
+    bad = {k: v for k, v in errs.items() if not v <= 2e-5}
+    assert not bad, f"phase 2/3/6 mismatch: {bad} (all: {errs})"
+    # bit-exact derived indices
+    g_top1 = ints["gates"].cpu().argmax(1)
+    assert torch.equal(g_top1, top1), f"{(g_top1 != top1).sum().item()} top-1 expert flips"
+
+
+@pytest.mark.parametrize("B,H,W,perturbed,feats", [
+    (1, 16, 16, False, True),
+    (1, 17, 23, True, True),
+    (2, 9, 11, True, True),
+    (1, 16, 24, True, False),
+    (1, 64, 64, True, True),
+    (2, 24, 40, True, True),
+])
+def test_full_forward_fp32_against_oracle(B, H, W, perturbed, feats):
+    dev = _cuda()
+    m = _model(perturbed)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    lr, imgs, fts, _ = O.synthetic_inputs(B, H, W, feats=feats)
+    with torch.no_grad():
+        ref, rint = O.run_pipeline(sd, lr, imgs, fts, return_intermediates=True)
+    m.to(dev)
+    lrd, imd, ftd = _to(dev, lr, imgs, fts)
+    sr, ints = m._run_pipeline(lrd, [imd[k] for k in O.EXPERT_ORDER], ftd or {}, 4 * H, 4 * W, {}, True)
+    sr2 = m.forward_with_precomputed(lrd, imd, ftd)
+    errs = {"sr": (sr.cpu() - ref).abs().max().item(),
+            "sr_no_intermediates": (sr2.cpu() - ref).abs().max().item(),
+            "fused_before_dynamic": (ints["fused_before_dynamic"].cpu() - rint["fused_before_dynamic"]).abs().max().item(),
+            "gates": (ints["gates"].cpu() - rint["gates"]).abs().max().item()}
+    if feats:
+        for e in range(4):
+            errs[f"collab{e}"] = (ints["collaborative_outputs"][e].cpu() - rint["collaborative_outputs"][e]).abs().max().item()
+    bad = {k: v for k, v in errs.items() if not v <= FP32_TOL}
+    assert not bad, f"fp32 parity > {FP32_TOL}: {bad} (all: {errs})"
+    assert sr.dtype == torch.float32 and sr.shape == (B, 3, 4 * H, 4 * W) and sr.device.type == "cuda"
+    assert float(sr.min()) >= 0.0 and float(sr.max()) <= 1.0
+    assert torch.equal(ints["gates"].cpu().argmax(1), rint["gates"].argmax(1))
+
+
+@pytest.mark.parametrize("name,perturbed,B,H,W,feats", [
+    ("case_default_16x16", False, 1, 16, 16, True),
+    ("case_perturbed_17x23", True, 1, 17, 23, True),
+    ("case_perturbed_b2_9x11", True, 2, 9, 11, True),
+    ("case_nofeat_16x24", True, 1, 16, 24, False),
+])
+def test_forward_against_reference_golden(golden_dir, name, perturbed, B, H, W, feats):
+    """Directly against tensors the reference itself produced (tests/golden)."""
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    m = _model(perturbed).to(dev)
+    lr, imgs, fts, _ = O.synthetic_inputs(B, H, W, feats=feats)
+    lrd, imd, ftd = _to(dev, lr, imgs, fts)
+    sr = m.forward_with_precomputed(lrd, imd, ftd)
+    assert (sr.cpu() - torch.from_numpy(g["sr"])).abs().max().item() <= FP32_TOL
+    _, ints = m._run_pipeline(lrd, [imd[k] for k in O.EXPERT_ORDER], ftd or {}, 4 * H, 4 * W, {}, True)
+    assert torch.equal(ints["gates"].cpu().argmax(1), torch.from_numpy(g["gates"]).argmax(1))
+    assert (ints["gates"].cpu() - torch.from_numpy(g["gates"])).abs().max().item() <= 2e-5
+
+
+def test_interface_edge_cases():
+    dev = _cuda()
+    m = _model(True).to(dev)
+    lr, imgs, fts, _ = O.synthetic_inputs(1, 16, 16)
+    lrd, imd, ftd = _to(dev, lr, imgs, fts)
+    base = m.forward_with_precomputed(lrd, imd, ftd)
+    # dict order must not matter; fp16 caches are up-cast at the boundary
+    shuffled = {k: imd[k] for k in ["mamba", "nafnet", "drct", "grl"]}
+    assert torch.equal(m.forward_with_precomputed(lrd, shuffled, ftd), base)
+    half = m.forward_with_precomputed(lrd.half(), {k: v.half() for k, v in imd.items()}, {k: v.half() for k, v in ftd.items()})
+    assert (half - base).abs().max().item() < 5e-3
+    # partial feature dict: the missing expert contributes a zero token (large_kernel_attention.py:378-381)
+    part = {k: v for k, v in ftd.items() if k != "grl"}
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.run_pipeline(sd, lr, imgs, {k: v for k, v in fts.items() if k != "grl"})
+    assert (m.forward_with_precomputed(lrd, imd, part).cpu() - ref).abs().max().item() <= FP32_TOL
+    # empty dict == None: Phase 4 skipped
+    assert torch.equal(m.forward_with_precomputed(lrd, imd, {}), m.forward_with_precomputed(lrd, imd, None))
+    with pytest.raises(ValueError):
+        m.forward_with_precomputed(lrd, {k: imd[k] for k in ["drct", "grl"]}, None)
+    with pytest.raises(ValueError):
+        m.forward_with_precomputed(lrd[:, :, :4, :4], imd, None)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.forward_with_precomputed(lrd, imd, ftd)
+    m.eval()
+    # weights edited in place (optimizer / EMA) must be picked up
+    with torch.no_grad():
+        m.residual_scale.add_(0.05)
+        m.refine[0].weight.mul_(1.1)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.run_pipeline(sd, lr, imgs, fts)
+    assert (m.forward_with_precomputed(lrd, imd, ftd).cpu() - ref).abs().max().item() <= FP32_TOL
+
+
+def test_phase2_is_linear_and_bands_recompose_at_full_size():
+    """Size-independent properties at the BASELINE full-res LR size 339x510 (no oracle needed)."""
+    dev = _cuda()
+    m = _model(False).to(dev)             # default init: all band scales are 1
+    eng = _engine(m, dev)
+    H, W = 339, 510
+    g = torch.Generator().manual_seed(5)
+    a, b = torch.rand(1, 3, H, W, generator=g).to(dev), torch.rand(1, 3, H, W, generator=g).to(dev)
+
+    def bands(x):
+        imgs = [torch.zeros(1, 3, 4 * H, 4 * W, device=dev) for _ in range(4)]
+        _, ints = eng.forward(x, imgs, {}, 4 * H, 4 * W, True)
+        return torch.stack(ints["raw_9_bands"], 1)
+
+    ra, rb, rab = bands(a), bands(b), bands(0.25 * a + 0.75 * b)
+    assert (rab - (0.25 * ra + 0.75 * rb)).abs().max().item() < 5e-6            # linearity
+    assert (ra[:, 0] + ra[:, 1] + ra[:, 2] - a).abs().max().item() < 5e-6       # DCT masks partition unity
+    assert (ra[:, 7] + ra[:, 8] - a).abs().max().item() < 5e-6                  # FFT low + high = x
+    # cuFFT cross-check of the dense-DFT path at a non-power-of-two size
+    sd = {k: v for k, v in m.state_dict().items()}
+    ref = torch.stack(O.fft_bands(sd, a), 1)
+    assert (ra[:, 7:9] - ref).abs().max().item() < 5e-6
+
+
+def test_full_resolution_forward_properties():
+    """2040x1356 HR (config 3): batch-consistency and range; the direct oracle comparison at
+    this size lives in bench.py's cpu_baseline leg."""
+    dev = _cuda()
+    m = _model(True).to(dev)
+    lr, imgs, fts, _ = O.synthetic_inputs(1, 339, 510)
+    lrd, imd, ftd = _to(dev, lr, imgs, fts)
+    sr = m.forward_with_precomputed(lrd, imd, ftd)
+    assert sr.shape == (1, 3, 1356, 2040) and torch.isfinite(sr).all()
+    assert float(sr.min()) >= 0 and float(sr.max()) <= 1
+    assert torch.equal(m.forward_with_precomputed(lrd, imd, ftd), sr)           # deterministic, no workspace aliasing

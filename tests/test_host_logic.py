@@ -1,0 +1,99 @@
+"""CPU-only checks of the host side: C-ABI library loads and exports every declared symbol,
+the drop-in module mirrors the reference interface, and the kernel orchestration is
+well-formed (dry run against a recording fake of the library: no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import isr_b200
+from isr_b200 import _cabi
+from isr_b200.pipeline import FusionEngine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _cabi.load()
+    header = open(os.path.join(ROOT, "include", "ffsr_b200.h")).read()
+    declared = set(re.findall(r"\b(ffsr_[a-z0-9_]+)\s*\(", header))
+    declared.discard("ffsr_conv_params")
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/ffsr_b200.h but not exported"
+    assert declared == set(_cabi.PROTOTYPES), declared ^ set(_cabi.PROTOTYPES)
+    assert b"sm_100a" in lib.ffsr_version()
+
+
+def test_conv_params_struct_matches_header_layout():
+    # 64-bit: 5 ptr/ll + 6 int + ... ; the C side is compiled from the same field order, so a
+    # size check catches accidental drift between _cabi.ConvParams and ffsr_conv_params.
+    assert C.sizeof(_cabi.ConvParams) == _cabi.load().ffsr_conv_params_size() == 248
+
+
+def test_module_interface_matches_reference():
+    torch.manual_seed(0)
+    m = isr_b200.CompleteEnhancedFusionSR(None)
+    assert m.cached_mode is True and m.num_experts == 4 and m.upscale == 4
+    assert m.get_trainable_params() == 1_433_217 and m.get_frozen_params() == 0
+    assert all(m.get_improvement_status().values())
+    with pytest.raises(RuntimeError, match="cached mode"):
+        m(torch.rand(1, 3, 16, 16))
+    # no silent CPU fallback: CPU tensors are refused loudly
+    m.eval()
+    imgs = {k: torch.rand(1, 3, 64, 64) for k in isr_b200.EXPERT_ORDER}
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.forward_with_precomputed(torch.rand(1, 3, 16, 16), imgs, None)
+    # strict state_dict round trip with itself and the factory
+    m2 = isr_b200.create_enhanced_fusion(None, {"refine_depth": 6})
+    m2.load_state_dict(m.state_dict(), strict=True)
+    assert "trainable=1,433,217" in repr(m2)
+
+
+class _FakeLib:
+    """Records call names; implements only the two size queries."""
+
+    def __init__(self):
+        self.calls = []
+
+    def ffsr_dwt_sub_size(self, H, W, hs, ws):
+        hs._obj.value = (H + 6) // 2 + 1
+        ws._obj.value = (W + 6) // 2 + 1
+        return 0
+
+    def ffsr_fft_workspace_bytes(self, B, H, W):
+        wf = W // 2 + 1
+        return 2 * B * 3 * H * wf * 16 + (H * wf * 4 + 255) // 256 * 256
+
+    def __getattr__(self, name):
+        def f(*args):
+            self.calls.append(name)
+            return 0
+        f.__name__ = name
+        return f
+
+
+@pytest.mark.parametrize("with_feats,want_inter", [(True, False), (True, True), (False, False)])
+def test_orchestration_dry_run(with_feats, want_inter):
+    torch.manual_seed(0)
+    m = isr_b200.CompleteEnhancedFusionSR(None).eval()
+    eng = FusionEngine(m)
+    eng.lib = _FakeLib()
+    eng._get_stream = lambda dev: C.c_void_p(0)
+    eng._sm_count = lambda dev: 148
+    B, H, W = 2, 12, 20
+    lr = torch.rand(B, 3, H, W)
+    imgs = [torch.rand(B, 3, 4 * H, 4 * W) for _ in range(4)]
+    feats = {k: torch.randn(B, 64 if k == "nafnet" else 180, H, W) for k in isr_b200.EXPERT_ORDER} if with_feats else {}
+    out, inter = eng._forward(lr, imgs, feats, B, H, W, want_inter)
+    assert out.shape == (B, 3, 4 * H, 4 * W)
+    calls = eng.lib.calls
+    assert calls.count("ffsr_conv2d") == (63 if with_feats else 51), calls.count("ffsr_conv2d")
+    assert ("ffsr_token_attention" in calls) == with_feats
+    assert calls[-1] == "ffsr_final_combine"
+    if want_inter:
+        assert set(inter) >= {"raw_9_bands", "enhanced_9_bands", "routing_lr", "collaborative_outputs",
+                              "fused_before_dynamic", "gates", "difficulty"}
+        assert len(inter["raw_9_bands"]) == 9 and inter["gates"].shape == (B, 4, H, W)
