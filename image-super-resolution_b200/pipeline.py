@@ -104,6 +104,13 @@ class FusionEngine:
             return
         m, w = self.m, {}
         self._w = w
+        # contiguous fp32 view of every parameter / buffer handed to the kernels by raw pointer
+        # (e.g. dct_basis_t is registered as a transposed view: its storage is NOT D^T)
+        self._P = {}
+        for n, t in list(m.named_parameters()) + list(m.named_buffers()):
+            if torch.is_floating_point(t):
+                t = t.detach()
+                self._P[n] = t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
         def conv(name, mod, bias=True):
             w[name] = _pack_conv(mod.weight)
@@ -189,6 +196,13 @@ class FusionEngine:
             self._ws[key] = t
         return t
 
+    def workspace(self, name):
+        """Debug/test access to a persistent workspace buffer by name (latest shape)."""
+        hits = [t for k, t in self._ws.items() if k[0] == name]
+        if not hits:
+            raise KeyError(name)
+        return hits[-1]
+
     def _call(self, fn, *args):
         rc = fn(*args)
         self.launches += 1
@@ -231,25 +245,25 @@ class FusionEngine:
             return
         self._call(self.lib.ffsr_conv2d, C.byref(p), self._stream)
 
-    def _lka_block(self, key, blk, x: torch.Tensor, name: str) -> torch.Tensor:
+    def _lka_block(self, key, blk: str, x: torch.Tensor, name: str) -> torch.Tensor:
         """x: [N,H,W,C] fp32 -> LKABlock(x) (large_kernel_attention.py:143-149), eval-mode BN folded."""
         N, H, W, Cc = x.shape
         dev, w = x.device, self._w
-        t1 = self._buf(name + ".t1", x.shape, dev)
-        t2 = self._buf(name + ".t2", x.shape, dev)
-        a = self._buf(name + ".a", x.shape, dev)
+        t1 = self._buf(name + ".lka_t1", x.shape, dev)
+        t2 = self._buf(name + ".lka_t2", x.shape, dev)
+        a = self._buf(name + ".lka_a", x.shape, dev)
         self._call(self.lib.ffsr_lka_depthwise, x.data_ptr(), N, H, W, Cc, w[key + ".k1"].data_ptr(),
                    w[key + ".d1"].data_ptr(), w[key + ".w5"].data_ptr(), w[key + ".wh"].data_ptr(),
                    w[key + ".wv"].data_ptr(), t1.data_ptr(), t2.data_ptr(), a.data_ptr(), self._stream)
         self.launches += 2
         x1 = t1   # t1 is free again after the depthwise chain
         self.conv(nhwc(a), N, H, W, Cc, key + ".pw", Cc, 1, nhwc(x1), epi=K.EPI_LKAGATE, bias_name=key + ".pwb",
-                  r1=nhwc(x), sa_ptr=blk.scale1, ch_k=w[key + ".k1"], ch_d=w[key + ".d1"])
-        hdn = self._buf(name + ".h", (N, H, W, 2 * Cc), dev)
+                  r1=nhwc(x), sa_ptr=self._P[blk + ".scale1"], ch_k=w[key + ".k1"], ch_d=w[key + ".d1"])
+        hdn = self._buf(name + ".lka_h", (N, H, W, 2 * Cc), dev)
         self.conv(nhwc(x1), N, H, W, Cc, key + ".f0", 2 * Cc, 1, nhwc(hdn), act=K.ACT_GELU, bias_name=key + ".f0b")
         x2 = t2
         self.conv(nhwc(hdn), N, H, W, 2 * Cc, key + ".f2", Cc, 1, nhwc(x2), epi=K.EPI_RESIDUAL, bias_name=key + ".f2b",
-                  r1=nhwc(x1), sa_ptr=blk.scale2)
+                  r1=nhwc(x1), sa_ptr=self._P[blk + ".scale2"])
         return x2
 
     def _twiddles(self, n, dev):
@@ -290,6 +304,11 @@ class FusionEngine:
         self._stream = self._get_stream(dev)
         self._prepare(dev)
         w = self._w
+        P = self._P
+
+        def pp(name):
+            return P[name].data_ptr()
+
         self.launches = 0
         S = self._stream
         f32 = torch.float32
@@ -301,21 +320,21 @@ class FusionEngine:
         # ---------------- Phase 2 ----------------
         fd = m.freq_decomp
         raw9 = self._buf("raw9", (B, 9, 3, H, W), dev, fresh=fr)
-        self._call(lib.ffsr_dct_bands, lr.data_ptr(), B, H, W, fd.dct.dct_basis.data_ptr(), fd.dct.dct_basis_t.data_ptr(),
-                   fd.dct.low_mask.data_ptr(), fd.dct.mid_mask.data_ptr(), fd.dct.high_mask.data_ptr(),
-                   fd.dct.band_scale.data_ptr(), raw9.data_ptr(), S)
+        self._call(lib.ffsr_dct_bands, lr.data_ptr(), B, H, W, pp("freq_decomp.dct.dct_basis"), pp("freq_decomp.dct.dct_basis_t"),
+                   pp("freq_decomp.dct.low_mask"), pp("freq_decomp.dct.mid_mask"), pp("freq_decomp.dct.high_mask"),
+                   pp("freq_decomp.dct.band_scale"), raw9.data_ptr(), S)
         hs, ws_ = C.c_int(), C.c_int()
         lib.ffsr_dwt_sub_size(H, W, C.byref(hs), C.byref(ws_))
         sub = self._buf("dwt.sub", (B, 4, 3, hs.value, ws_.value), dev)
-        self._call(lib.ffsr_dwt_bands, lr.data_ptr(), B, H, W, fd.dwt.lo_row.data_ptr(), fd.dwt.hi_row.data_ptr(),
-                   fd.dwt.lo_col.data_ptr(), fd.dwt.hi_col.data_ptr(), fd.dwt.subband_scale.data_ptr(),
+        self._call(lib.ffsr_dwt_bands, lr.data_ptr(), B, H, W, pp("freq_decomp.dwt.lo_row"), pp("freq_decomp.dwt.hi_row"),
+                   pp("freq_decomp.dwt.lo_col"), pp("freq_decomp.dwt.hi_col"), pp("freq_decomp.dwt.subband_scale"),
                    sub.data_ptr(), raw9.data_ptr(), S)
         self.launches += 1
         fft_bytes = lib.ffsr_fft_workspace_bytes(B, H, W)
         fws = self._buf("fft.ws", (fft_bytes // 8 + 2,), dev, dtype=torch.float64)
         ms = fd.fft.freq_mask_logits.shape[-1]
-        self._call(lib.ffsr_fft_bands, lr.data_ptr(), B, H, W, fd.fft.freq_mask_logits.data_ptr(), ms,
-                   fd.fft.temperature.data_ptr(), fd.fft.band_scale.data_ptr(), self._twiddles(H, dev).data_ptr(),
+        self._call(lib.ffsr_fft_bands, lr.data_ptr(), B, H, W, pp("freq_decomp.fft.freq_mask_logits"), ms,
+                   pp("freq_decomp.fft.temperature"), pp("freq_decomp.fft.band_scale"), self._twiddles(H, dev).data_ptr(),
                    self._twiddles(W, dev).data_ptr(), fws.data_ptr(), fft_bytes, raw9.data_ptr(), S)
         self.launches += 4
 
@@ -325,15 +344,15 @@ class FusionEngine:
         tok = self._buf("cb.tok", (B * nq, H, W, 64), dev)
         nsm = self._sm_count(dev)
         self._call(lib.ffsr_crossband_attention, raw9.data_ptr(), B, H, W, w["cb.proj_w"].data_ptr(),
-                   cb.band_proj.bias.data_ptr(), cb.norm.weight.data_ptr(), cb.norm.bias.data_ptr(),
-                   cb.band_attention.in_proj_weight.data_ptr(), cb.band_attention.in_proj_bias.data_ptr(),
-                   cb.band_attention.out_proj.weight.data_ptr(), cb.band_attention.out_proj.bias.data_ptr(),
+                   pp("cross_band.band_proj.bias"), pp("cross_band.norm.weight"), pp("cross_band.norm.bias"),
+                   pp("cross_band.band_attention.in_proj_weight"), pp("cross_band.band_attention.in_proj_bias"),
+                   pp("cross_band.band_attention.out_proj.weight"), pp("cross_band.band_attention.out_proj.bias"),
                    nq, tok.data_ptr(), nsm, S)
-        x2 = self._lka_block("cb.lka", cb.lka_block, tok, "cb%d" % nq)
+        x2 = self._lka_block("cb.lka", "cross_band.lka_block", tok, "cb%d" % nq)
         enh9 = self._buf("enh9", (B, 9, 3, H, W), dev, fresh=fr)
         routing = self._buf("routing", (B, 3, H, W), dev, fresh=fr)
         self._call(lib.ffsr_crossband_out, x2.data_ptr(), raw9.data_ptr(), B, H, W, nq, w["cb.out_w"].data_ptr(),
-                   cb.out_proj.bias.data_ptr(), enh9.data_ptr(), routing.data_ptr(), S)
+                   pp("cross_band.out_proj.bias"), enh9.data_ptr(), routing.data_ptr(), S)
 
         # ---------------- Phase 6 (selector nets, fp32) ----------------
         ds = m.dynamic_selector
@@ -349,7 +368,7 @@ class FusionEngine:
         self.conv(rv, B, H, W, 3, "ds.g0", 32, 3, nhwc(s_a), act=K.ACT_RELU)
         self.conv(nhwc(s_a), B, H, W, 32, "ds.g2", 32, 3, nhwc(s_b), act=K.ACT_RELU)
         self.conv(nhwc(s_b), B, H, W, 32, "ds.g4", 4, 1, nhwc(graw))
-        self._call(lib.ffsr_gate_finalize, graw.data_ptr(), diff.data_ptr(), B, H, W, ds.temperature.data_ptr(),
+        self._call(lib.ffsr_gate_finalize, graw.data_ptr(), diff.data_ptr(), B, H, W, pp("dynamic_selector.temperature"),
                    gates.data_ptr(), S)
 
         # ---------------- Phase 4 (LR part) ----------------
@@ -386,21 +405,21 @@ class FusionEngine:
             tok4 = tokens.view(N4, H, W, 128)
             rows = N4 * H * W
             n1 = self._buf("co.n", (N4, H, W, 128), dev)
-            self._call(lib.ffsr_layernorm, tok4.data_ptr(), rows, 128, co.norm1.weight.data_ptr(),
-                       co.norm1.bias.data_ptr(), n1.data_ptr(), 0, S)
+            self._call(lib.ffsr_layernorm, tok4.data_ptr(), rows, 128, pp("collaborative.norm1.weight"),
+                       pp("collaborative.norm1.bias"), n1.data_ptr(), 0, S)
             qkv = self._buf("co.qkv", (N4, H, W, 384), dev)
             self.conv(nhwc(n1), N4, H, W, 128, "co.qkv", 384, 1, nhwc(qkv))
             ctx = self._buf("co.ctx", (N4, H, W, 128), dev)
             self._call(lib.ffsr_token_attention, qkv.data_ptr(), B, 4, H * W, 128, ctx.data_ptr(), 0, S)
             t1 = self._buf("co.t1", (N4, H, W, 128), dev)
             self.conv(nhwc(ctx), N4, H, W, 128, "co.out", 128, 1, nhwc(t1), epi=K.EPI_RESIDUAL, r1=nhwc(tok4))
-            self._call(lib.ffsr_layernorm, t1.data_ptr(), rows, 128, co.norm2.weight.data_ptr(),
-                       co.norm2.bias.data_ptr(), n1.data_ptr(), 0, S)
+            self._call(lib.ffsr_layernorm, t1.data_ptr(), rows, 128, pp("collaborative.norm2.weight"),
+                       pp("collaborative.norm2.bias"), n1.data_ptr(), 0, S)
             hdn = self._buf("co.h", (N4, H, W, 256), dev)
             self.conv(nhwc(n1), N4, H, W, 128, "co.f0", 256, 1, nhwc(hdn), act=K.ACT_GELU)
             t2 = self._buf("co.t2", (N4, H, W, 128), dev)
             self.conv(nhwc(hdn), N4, H, W, 256, "co.f2", 128, 1, nhwc(t2), epi=K.EPI_RESIDUAL, r1=nhwc(t1))
-            xg = self._lka_block("co.lka", co.lka_global, t2, "co")
+            xg = self._lka_block("co.lka", "collaborative.lka_global", t2, "co")
             m32 = self._buf("co.m32", (N4, H, W, 32), dev)
             self.conv(nhwc(xg), N4, H, W, 128, "co.m0", 32, 1, nhwc(m32), groups=4, bias_name="co.m0b")
 
@@ -427,19 +446,19 @@ class FusionEngine:
             self.conv(nhwc(a), B, h, wd, c_mid, f"mr.{name}.c2", c_out, 3, nhwc(b_), act=K.ACT_GELU)
             g = getattr(mr, name + "_gate").gate
             self._call(lib.ffsr_spatial_gate, b_.data_ptr(), B * h * wd, c_out, w[f"mr.{name}.g0"].data_ptr(),
-                       g[0].bias.data_ptr(), w[f"mr.{name}.g2"].data_ptr(), g[2].bias.data_ptr(), b_.data_ptr(),
+                       pp(f"multi_res.{name}_gate.gate.0.bias"), w[f"mr.{name}.g2"].data_ptr(), pp(f"multi_res.{name}_gate.gate.2.bias"), b_.data_ptr(),
                        K.DT_F32, S)
             d_ = self._buf(name + ".d", (B, h, wd, c_out), dev)
             self.conv(nhwc(b_), B, h, wd, c_out, f"mr.{name}.r0", c_out, 3, nhwc(d_), act=K.ACT_GELU, bias=False)
             self.conv(nhwc(d_), B, h, wd, c_out, f"mr.{name}.r2", c_out, 3, nhwc(c_), bias=False, epi=K.EPI_RESIDUAL,
-                      r1=nhwc(b_), sa_ptr=getattr(mr, name + "_res").scale, r2=r2, sb_ptr=sb_ptr)
+                      r1=nhwc(b_), sa_ptr=P[f"multi_res.{name}_res.scale"], r2=r2, sb_ptr=sb_ptr)
             return c_
 
         f1 = stage("stage1", nhwc(s1in), 12, H, W, 64, 64)
         self._call(lib.ffsr_resize_nhwc, f1.data_ptr(), B, H, W, 64, 64, cat2.data_ptr(), 2 * H, 2 * W, 80, K.DT_F32, S)
-        f2 = stage("stage2", nhwc(cat2), 76, 2 * H, 2 * W, 64, 64, r2=nhwc(cat2), sb_ptr=mr.residual_weight_1_2)
+        f2 = stage("stage2", nhwc(cat2), 76, 2 * H, 2 * W, 64, 64, r2=nhwc(cat2), sb_ptr=P["multi_res.residual_weight_1_2"])
         self._call(lib.ffsr_resize_nhwc, f2.data_ptr(), B, 2 * H, 2 * W, 64, 64, cat3.data_ptr(), Hh, Wh, 80, K.DT_F32, S)
-        f3 = stage("stage3", nhwc(cat3), 76, Hh, Wh, 64, 32, r2=nhwc(cat3), sb_ptr=mr.residual_weight_2_3)
+        f3 = stage("stage3", nhwc(cat3), 76, Hh, Wh, 64, 32, r2=nhwc(cat3), sb_ptr=P["multi_res.residual_weight_2_3"])
         u16 = self._buf("mr.u16", (B, Hh, Wh, 16), dev)
         hier = self._buf("mr.hier", (B, Hh, Wh, 4), dev, zero=True)
         self.conv(nhwc(f3), B, Hh, Wh, 32, "mr.rgb0", 16, 3, nhwc(u16), act=K.ACT_GELU)
@@ -449,8 +468,8 @@ class FusionEngine:
         fused_before = torch.empty(B, 3, Hh, Wh, device=dev, dtype=f32) if want_inter else None
         fusedx = self._buf("fusedx", (B, Hh, Wh, 4), dev, zero=True)
         self._call(lib.ffsr_blend_hr, hier.data_ptr(), 4, ecol.data_ptr(), routing.data_ptr(), gates.data_ptr(),
-                   diff.data_ptr(), w["fw0"].data_ptr(), m.freq_weight_conv[0].bias.data_ptr(), w["fw2"].data_ptr(),
-                   m.freq_weight_conv[2].bias.data_ptr(), B, H, W,
+                   diff.data_ptr(), w["fw0"].data_ptr(), pp("freq_weight_conv.0.bias"), w["fw2"].data_ptr(),
+                   pp("freq_weight_conv.2.bias"), B, H, W,
                    fused_before.data_ptr() if fused_before is not None else None, fusedx.data_ptr(), 4, None, 0, S)
 
         # ---------------- Phase 7a: refinement ----------------
@@ -492,7 +511,7 @@ class FusionEngine:
             self.conv(nhwc(o1), B, h, wd, 32, f"ee.{lv}.a0", 8, 1, nhwc(t8), act=K.ACT_GELU)
             self.conv(nhwc(t8), B, h, wd, 8, f"ee.{lv}.a2", 1, 3, nhwc(at), act=K.ACT_SIGMOID)
             self._call(lib.ffsr_edge_attn_upsample, o1.data_ptr(), at.data_ptr(), B, h, wd, 32,
-                       ee.level_weights.data_ptr(), lv, cat96.data_ptr() + 32 * lv * 4, Hh, Wh, 96, K.DT_F32, S)
+                       pp("edge_enhance.level_weights"), lv, cat96.data_ptr() + 32 * lv * 4, Hh, Wh, 96, K.DT_F32, S)
         e32 = self._buf("ee.e32", (B, Hh, Wh, 32), dev)
         self.conv(nhwc(cat96), B, Hh, Wh, 96, "ee.f0", 32, 3, nhwc(e32), act=K.ACT_GELU)
         self.conv(nhwc(e32), B, Hh, Wh, 32, "ee.f2", 3, 3, nhwc(cat6, 3))
@@ -503,8 +522,8 @@ class FusionEngine:
 
         # ---------------- output ----------------
         out = torch.empty(B, 3, Hh, Wh, device=dev, dtype=f32)
-        self._call(lib.ffsr_final_combine, cat6.data_ptr(), 8, egate.data_ptr(), ee.edge_strength.data_ptr(),
-                   lr.data_ptr(), m.residual_scale.data_ptr(), B, H, W, 0 if m.training else 1, out.data_ptr(), S)
+        self._call(lib.ffsr_final_combine, cat6.data_ptr(), 8, egate.data_ptr(), pp("edge_enhance.edge_strength"),
+                   lr.data_ptr(), pp("residual_scale"), B, H, W, 0 if m.training else 1, out.data_ptr(), S)
 
         inter = {}
         if want_inter:

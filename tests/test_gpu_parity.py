@@ -272,3 +272,99 @@ def test_full_resolution_forward_properties():
     assert sr.shape == (1, 3, 1356, 2040) and torch.isfinite(sr).all()
     assert float(sr.min()) >= 0 and float(sr.max()) <= 1
     assert torch.equal(m.forward_with_precomputed(lrd, imd, ftd), sr)           # deterministic, no workspace aliasing
+
+
+# --------------------------------------------------------------------------------------------
+# finer-grained checks (localise a failure to one kernel)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prefix,key,C_", [("cross_band.lka_block", "cb.lka", 64), ("collaborative.lka_global", "co.lka", 128)])
+@pytest.mark.parametrize("N,H,W", [(2, 13, 29), (1, 40, 9)])
+def test_lka_block_against_oracle(prefix, key, C_, N, H, W):
+    dev = _cuda()
+    m = _model(True)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, C_, H, W, generator=g)
+    with torch.no_grad():
+        ref = O.lka_block(sd, prefix, x)
+    m.to(dev)
+    eng = _engine(m, dev)
+    with torch.cuda.device(dev):
+        y = eng._lka_block(key, prefix, x.permute(0, 2, 3, 1).contiguous().to(dev), "t")
+        torch.cuda.synchronize()
+    # depthwise chain alone first (zero padding of every intermediate at the image border)
+    n = F.batch_norm(x, sd[prefix + ".norm1.running_mean"], sd[prefix + ".norm1.running_var"],
+                     sd[prefix + ".norm1.weight"], sd[prefix + ".norm1.bias"], False, 0.0, 1e-5)
+    a = F.conv2d(n, sd[prefix + ".lka.local_conv.weight"], padding=2, groups=C_)
+    a = F.conv2d(a, sd[prefix + ".lka.h_conv.weight"], padding=(0, 10), groups=C_)
+    a = F.conv2d(a, sd[prefix + ".lka.v_conv.weight"], padding=(10, 0), groups=C_)
+    got_a = eng.workspace("t.lka_a").permute(0, 3, 1, 2).cpu()
+    assert (got_a - a).abs().max().item() < 2e-5, "depthwise chain"
+    assert (y.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() < 2e-5, "LKA block"
+
+
+def test_layernorm_and_token_attention_against_torch():
+    dev = _cuda()
+    lib = K.load()
+    g = torch.Generator().manual_seed(3)
+    B, T, HW, E = 2, 4, 77, 128
+    x = torch.randn(B * T * HW, E, generator=g)
+    wln, bln = torch.randn(E, generator=g), torch.randn(E, generator=g)
+    xd, y = x.to(dev), torch.empty(B * T * HW, E, device=dev)
+    wd, bd = wln.to(dev), bln.to(dev)
+    K.check(lib.ffsr_layernorm(xd.data_ptr(), B * T * HW, E, wd.data_ptr(), bd.data_ptr(), y.data_ptr(), 0, None))
+    torch.cuda.synchronize()
+    assert (y.cpu() - F.layer_norm(x, (E,), wln, bln, 1e-5)).abs().max().item() < 1e-5
+    qkv = torch.randn(B, T, HW, 3 * E, generator=g)
+    ctx = torch.empty(B, T, HW, E, device=dev)
+    qd = qkv.to(dev)
+    K.check(lib.ffsr_token_attention(qd.data_ptr(), B, T, HW, E, ctx.data_ptr(), 0, None))
+    torch.cuda.synchronize()
+    q, k, v = [t.permute(0, 2, 1, 3).reshape(B * HW, T, E // 16, 16).transpose(1, 2) for t in qkv.split(E, dim=-1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 4.0, -1) @ v).transpose(1, 2).reshape(B, HW, T, E).permute(0, 2, 1, 3)
+    assert (ctx.cpu() - ref).abs().max().item() < 1e-5
+
+
+def test_pipeline_internals_against_oracle():
+    """Every stage boundary of one forward, read back from the engine's workspaces."""
+    dev = _cuda()
+    B, H, W = 1, 20, 28
+    m = _model(True)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    lr, imgs, fts, _ = O.synthetic_inputs(B, H, W)
+    il = [imgs[k] for k in O.EXPERT_ORDER]
+    with torch.no_grad():
+        ref, ri = O.run_pipeline(sd, lr, imgs, fts, return_intermediates=True)
+        _, ci = O.collaborative(sd, fts, il, return_internals=True)
+        _, mi = O.multi_res(sd, ri["collaborative_outputs"], return_internals=True)
+        _, ei = O.edge_enhance(sd, ri["refined"], return_internals=True)
+    m.to(dev)
+    lrd, imd, ftd = _to(dev, lr, imgs, fts)
+    sr = m.forward_with_precomputed(lrd, imd, ftd)
+    eng = m._engine
+
+    def cl(t):      # [N,H,W,C] -> [N,C,H,W] on cpu
+        return t.permute(0, 3, 1, 2).cpu()
+
+    errs = {}
+    tok = eng.workspace("co.t2").view(B, 4, H, W, 128).permute(0, 1, 4, 2, 3).cpu()
+    errs["p4.tokens_after_ffn"] = (tok - ci["tokens"]).abs().max().item()
+    lka = eng.workspace("co.lka_t2").view(B, 4, H, W, 128).permute(0, 1, 4, 2, 3).cpu()
+    errs["p4.lka_out"] = (lka - ci["lka_out"]).abs().max().item()
+    ecol = eng.workspace("ecol").cpu()
+    errs["p4.collab"] = max((ecol[:, e] - ri["collaborative_outputs"][e]).abs().max().item() for e in range(4))
+    errs["p5.f1"] = (cl(eng.workspace("stage1.c")) - mi["f1"]).abs().max().item()
+    errs["p5.f2"] = (cl(eng.workspace("stage2.c")) - mi["f2"]).abs().max().item()
+    errs["p5.f3"] = (cl(eng.workspace("stage3.c")) - mi["f3"]).abs().max().item()
+    errs["p5.hier"] = (cl(eng.workspace("mr.hier"))[:, :3] - ri["hierarchical"]).abs().max().item()
+    errs["p6.fused"] = (cl(eng.workspace("fusedx"))[:, :3] - ri["fused_after_dynamic"]).abs().max().item()
+    cat6 = cl(eng.workspace("cat6"))
+    errs["p7.refined"] = (cat6[:, :3] - ri["refined"]).abs().max().item()
+    errs["p7b.lap0"] = (cl(eng.workspace("ee.lap0"))[:, :3] - ei["pyramid"][0]).abs().max().item()
+    errs["p7b.lap1"] = (cl(eng.workspace("ee.lap1"))[:, :3] - ei["pyramid"][1]).abs().max().item()
+    errs["p7b.lap2"] = (cl(eng.workspace("ee.down2"))[:, :3] - ei["pyramid"][2]).abs().max().item()
+    errs["p7b.edge_map"] = (cat6[:, 3:6] - ei["edge_map"]).abs().max().item()
+    errs["p7b.edge_gate"] = (cl(eng.workspace("ee.gate")) - ei["edge_gate"]).abs().max().item()
+    errs["sr"] = (sr.cpu() - ref).abs().max().item()
+    bad = {k: v for k, v in errs.items() if not v <= 5e-5}
+    assert not bad, f"stage mismatch: {bad} (all: {errs})"
