@@ -36,6 +36,7 @@ class ConvParams(C.Structure):
         ("sb", C.c_float), ("sb_ptr", C.c_void_p),
         ("ch_k", C.c_void_p), ("ch_d", C.c_void_p),
         ("in_dtype", C.c_int), ("out_dtype", C.c_int),
+        ("w_dtype", C.c_int), ("r1_dtype", C.c_int), ("r2_dtype", C.c_int),
     ]
 
 

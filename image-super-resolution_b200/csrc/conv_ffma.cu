@@ -12,6 +12,11 @@
 namespace {
 constexpr int TH = 8, TW = 16, PS = 20;
 
+__device__ __forceinline__ float ld_any(const void* base, int dtype, long long off) {
+  return dtype == FFSR_DT_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off])
+                               : reinterpret_cast<const float*>(base)[off];
+}
+
 template <int KS>
 struct ConvGeom {
   static constexpr int HALO = KS / 2;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(256) k_conv_ffma(const ffsr_conv_params p) {
   // ---- epilogue ------------------------------------------------------------------------------
   const float sa = p.sa * (p.sa_ptr ? p.sa_ptr[0] : 1.0f);
   const float sb = p.sb * (p.sb_ptr ? p.sb_ptr[0] : 1.0f);
-  float* __restrict__ out = reinterpret_cast<float*>(p.out) + (long long)n * p.out_sN;
+  const long long out_n = (long long)n * p.out_sN;
   const int y = ty0 + r;
   if (y >= p.H) return;
 #pragma unroll
@@ -118,16 +123,18 @@ __global__ void __launch_bounds__(256) k_conv_ffma(const ffsr_conv_params p) {
       float v = acc[j][k];
       if (p.bias) v += p.bias[(long long)g * p.Cout + oc];
       if (p.epi == FFSR_EPI_LKAGATE) {
-        const float xr = p.r1[(long long)n * p.r1_sN + (long long)y * p.r1_sY + (long long)x * p.r1_sX + oc];
+        const float xr = ld_any(p.r1, p.r1_dtype, (long long)n * p.r1_sN + (long long)y * p.r1_sY + (long long)x * p.r1_sX + oc);
         v = xr + sa * (fmaf(xr, p.ch_k[oc], p.ch_d[oc]) * sigmoid_acc(v));
       } else {
         v = apply_act(v, p.act);
         if (p.epi == FFSR_EPI_RESIDUAL) {
-          v = p.r1[(long long)n * p.r1_sN + (long long)y * p.r1_sY + (long long)x * p.r1_sX + oc] + sa * v;
-          if (p.r2) v += sb * p.r2[(long long)n * p.r2_sN + (long long)y * p.r2_sY + (long long)x * p.r2_sX + oc];
+          v = ld_any(p.r1, p.r1_dtype, (long long)n * p.r1_sN + (long long)y * p.r1_sY + (long long)x * p.r1_sX + oc) + sa * v;
+          if (p.r2) v += sb * ld_any(p.r2, p.r2_dtype, (long long)n * p.r2_sN + (long long)y * p.r2_sY + (long long)x * p.r2_sX + oc);
         }
       }
-      out[(long long)y * p.out_sY + (long long)x * p.out_sX + oc] = v;
+      const long long o = out_n + (long long)y * p.out_sY + (long long)x * p.out_sX + oc;
+      if (p.out_dtype == FFSR_DT_BF16) reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(p.out)[o] = v;
     }
   }
 }
@@ -166,7 +173,8 @@ extern "C" int ffsr_conv2d(const ffsr_conv_params* pp, cudaStream_t stream) {
   FFSR_REQUIRE(p.groups >= 1, FFSR_ERR_ARG, "conv2d: groups must be >= 1");
   FFSR_REQUIRE(p.epi == FFSR_EPI_PLAIN || p.r1, FFSR_ERR_ARG, "conv2d: residual epilogue needs r1");
   FFSR_REQUIRE(p.epi != FFSR_EPI_LKAGATE || (p.ch_k && p.ch_d), FFSR_ERR_ARG, "conv2d: LKA gate needs ch_k/ch_d");
-  if (p.in_dtype == FFSR_DT_BF16 || p.out_dtype == FFSR_DT_BF16) return ffsr_conv2d_tc(pp, stream);
+  if (p.in_dtype == FFSR_DT_BF16) return ffsr_conv2d_tc(pp, stream);       // tcgen05 implicit GEMM
+  FFSR_REQUIRE(p.w_dtype == FFSR_DT_F32, FFSR_ERR_ARG, "conv2d: fp32 input needs fp32-packed weights");
   const bool nchw = (p.in_sX == 1 && p.in_sC != 1);
   if (p.ksize == 3) return nchw ? dispatch_ct<3, true>(p, stream) : dispatch_ct<3, false>(p, stream);
   return nchw ? dispatch_ct<1, true>(p, stream) : dispatch_ct<1, false>(p, stream);

@@ -1,8 +1,424 @@
-// placeholder until the tcgen05 implicit-GEMM kernel lands
+// tcgen05 implicit-GEMM convolution (1x1 / 3x3, zero pad, stride 1), bf16 operands, fp32
+// accumulation in TMEM.  This is the tensor-core path of ffsr_conv2d for the contraction-heavy
+// layers (refinement stack, hierarchical fusion, token GEMMs).
+//
+//   GEMM view : D[pixel, cout] = sum_{tap, cin} A[pixel shifted by tap, cin] * W[tap, cout, cin]
+//   tile      : M = 128 output pixels (8 rows x 16 cols of one image), N = up to 128 cout
+//   A operand : one TMA tiled load per (tap, 64-channel chunk) from the NHWC bf16 activation
+//               tensor with a 4-D tensor map {C, W, H, N}, box {64, 16, 8, 1}, SWIZZLE_128B.
+//               Out-of-image coordinates (the conv halo) and channels >= Cin are zero-filled
+//               by the TMA unit, so padding costs no instructions and no memory traffic.
+//   B operand : weights pre-packed [group*taps][CoutPad][CinPad] bf16 (K-major), 3-D tensor
+//               map, box {64, N, 1}, SWIZZLE_128B.
+//   MMA       : tcgen05.mma.cta_group::1.kind::f16, M=128, N=nblk, K=16, issued by one thread;
+//               accumulators double-buffered in TMEM (2 x 128 columns) so the epilogue of
+//               tile i overlaps the MMAs of tile i+1.
+//   warps     : 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = epilogue
+//               (tcgen05.ld 32x32b -> bias/act/residual -> vector stores).
+// Persistent: grid = min(tiles, #SMs), static round-robin over tiles.
+#include <cuda.h>
 #include "common.cuh"
 #include "../../include/ffsr_b200.h"
-int ffsr_conv2d_tc(const ffsr_conv_params* p, cudaStream_t stream) {
-  (void)p; (void)stream;
-  ffsr_set_error("conv2d: bf16 tensor-core path not built");
-  return FFSR_ERR_ARG;
+
+namespace {
+
+constexpr int TC_TH = 8, TC_TW = 16;           // output pixel tile (M = 128)
+constexpr int TC_STAGES = 6;
+constexpr int TC_A_BYTES = 128 * 128;          // 128 pixels x 64 bf16
+constexpr int TC_B_BYTES = 128 * 128;          // up to 128 cout x 64 bf16
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TcArgs {
+  int N, H, W, Cin, Cout, taps, ks;
+  int nblk;          // UMMA N (multiple of 16, <= 128)
+  int n_nblocks;     // cout blocks
+  int nchunks;       // 64-channel K chunks
+  int ksteps_last;   // K=16 steps issued for the last chunk
+  int groups;
+  int tiles_x, tiles_y;
+  long long total_tiles;
+  void* out;
+  long long out_sN, out_sY, out_sX;
+  int out_bf16;
+  const float* bias;
+  int act, epi;
+  const void* r1;
+  long long r1_sN, r1_sY, r1_sX;
+  int r1_bf16;
+  const void* r2;
+  long long r2_sN, r2_sY, r2_sX;
+  int r2_bf16;
+  float sa, sb;
+  const float* sa_ptr;
+  const float* sb_ptr;
+  const float* ch_k;
+  const float* ch_d;
+};
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major: 1) | SBO>>4 [32,46) = 1024B
+// (8 rows x 128B atom) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float load_res(const void* base, int is_bf16, long long off) {
+  return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off])
+                 : reinterpret_cast<const float*>(base)[off];
+}
+
+// ---------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full = bars;                       // [TC_STAGES]
+  uint64_t* empty = bars + TC_STAGES;          // [TC_STAGES]
+  uint64_t* tfull = bars + 2 * TC_STAGES;      // [2]
+  uint64_t* tempty = bars + 2 * TC_STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int pad = a.ks / 2;
+  const int kiters = a.taps * a.nchunks;
+  const uint32_t stage_tx = TC_A_BYTES + (uint32_t)a.nblk * 128u;
+
+  if (warp == 0) {
+    // ================================ TMA producer ======================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        long long r = t;
+        const int nb = (int)(r % a.n_nblocks); r /= a.n_nblocks;
+        const int tx = (int)(r % a.tiles_x); r /= a.tiles_x;
+        const int ty = (int)(r % a.tiles_y); r /= a.tiles_y;
+        const int n = (int)r;
+        const int g = n % a.groups;
+        for (int tap = 0; tap < a.taps; ++tap) {
+          const int dy = tap / a.ks - pad, dx = tap % a.ks - pad;
+          for (int ch = 0; ch < a.nchunks; ++ch) {
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sa_ = smem + s * TC_STAGE_BYTES;
+            mbar_expect_tx(&full[s], stage_tx);
+            tma_load_4d(sa_, &tmA, &full[s], ch * 64, tx * TC_TW + dx, ty * TC_TH + dy, n);
+            tma_load_3d(sa_ + TC_A_BYTES, &tmB, &full[s], ch * 64, nb * a.nblk, g * a.taps + tap);
+            if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ========================================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.nblk >> 3) << 17) | ((128u >> 4) << 24);
+    int s = 0;
+    uint32_t ph = 0;
+    int as = 0;
+    uint32_t aph = 0;
+    for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      mbar_wait(&tempty[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * 128u;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * TC_STAGE_BYTES);
+          const uint64_t da = make_sw128_desc(a_addr);
+          const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
+          const int ch = it % a.nchunks;
+          const int ksteps = (ch == a.nchunks - 1) ? a.ksteps_last : 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);                       // smem slot reusable once these MMAs retire
+          if (it == kiters - 1) umma_commit(&tfull[as]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) =============================
+    const int wq = warp & 3;                              // TMEM lane quarter this warp may read
+    const int row = wq * 32 + lane;                       // pixel within the tile
+    const int py = row / TC_TW, px = row % TC_TW;
+    const float sa = a.sa * (a.sa_ptr ? a.sa_ptr[0] : 1.0f);
+    const float sb = a.sb * (a.sb_ptr ? a.sb_ptr[0] : 1.0f);
+    int as = 0;
+    uint32_t aph = 0;
+    for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      long long r = t;
+      const int nb = (int)(r % a.n_nblocks); r /= a.n_nblocks;
+      const int tx = (int)(r % a.tiles_x); r /= a.tiles_x;
+      const int ty = (int)(r % a.tiles_y); r /= a.tiles_y;
+      const int n = (int)r;
+      const int g = n % a.groups;
+      const int y = ty * TC_TH + py, x = tx * TC_TW + px;
+      const bool inside = (y < a.H) && (x < a.W);
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 128u;
+      const long long opix = (long long)n * a.out_sN + (long long)y * a.out_sY + (long long)x * a.out_sX;
+      const long long r1pix = (long long)n * a.r1_sN + (long long)y * a.r1_sY + (long long)x * a.r1_sX;
+      const long long r2pix = (long long)n * a.r2_sN + (long long)y * a.r2_sY + (long long)x * a.r2_sX;
+      for (int c0 = 0; c0 < a.nblk; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_wait_ld();
+        if (inside) {
+          const int ocb = nb * a.nblk + c0;
+          float f[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int oc = ocb + k;
+            float val = __uint_as_float(v[k]);
+            if (oc < a.Cout) {
+              if (a.bias) val += __ldg(a.bias + (long long)g * a.Cout + oc);
+              if (a.epi == FFSR_EPI_LKAGATE) {
+                const float xr = load_res(a.r1, a.r1_bf16, r1pix + oc);
+                val = xr + sa * (fmaf(xr, __ldg(a.ch_k + oc), __ldg(a.ch_d + oc)) * sigmoid_acc(val));
+              } else {
+                val = apply_act(val, a.act);
+                if (a.epi == FFSR_EPI_RESIDUAL) {
+                  val = load_res(a.r1, a.r1_bf16, r1pix + oc) + sa * val;
+                  if (a.r2) val += sb * load_res(a.r2, a.r2_bf16, r2pix + oc);
+                }
+              }
+            }
+            f[k] = val;
+          }
+          const bool full16 = (ocb + 16 <= a.Cout);
+          if (a.out_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + opix + ocb;
+            if (full16 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+              uint4 u0, u1;
+              __nv_bfloat162 h;
+              h = __floats2bfloat162_rn(f[0], f[1]);   u0.x = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(f[2], f[3]);   u0.y = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(f[4], f[5]);   u0.z = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(f[6], f[7]);   u0.w = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(f[8], f[9]);   u1.x = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(f[10], f[11]); u1.y = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(f[12], f[13]); u1.z = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(f[14], f[15]); u1.w = *reinterpret_cast<uint32_t*>(&h);
+              reinterpret_cast<uint4*>(o)[0] = u0;
+              reinterpret_cast<uint4*>(o)[1] = u1;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 16; ++k)
+                if (ocb + k < a.Cout) o[k] = __float2bfloat16_rn(f[k]);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(a.out) + opix + ocb;
+            if (full16 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int k = 0; k < 16; k += 4) reinterpret_cast<float4*>(o)[k >> 2] = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 16; ++k)
+                if (ocb + k < a.Cout) o[k] = f[k];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  // ---- teardown: everyone done with TMEM before the allocating warp frees it
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+}  // namespace
+
+int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
+  const ffsr_conv_params& p = *pp;
+  FFSR_REQUIRE(p.in_dtype == FFSR_DT_BF16, FFSR_ERR_ARG, "conv2d(tc): input must be bf16 NHWC (cast upstream)");
+  FFSR_REQUIRE(p.w_dtype == FFSR_DT_BF16, FFSR_ERR_ARG, "conv2d(tc): weights must be packed bf16 [g*taps][CoutPad][CinPad]");
+  FFSR_REQUIRE(p.in_sC == 1, FFSR_ERR_ARG, "conv2d(tc): input must be channels-last");
+  FFSR_REQUIRE(((uintptr_t)p.in % 16) == 0 && (p.in_sX * 2) % 16 == 0 && (p.in_sY * 2) % 16 == 0 && (p.in_sN * 2) % 16 == 0,
+               FFSR_ERR_ALIGN, "conv2d(tc): TMA needs a 16B-aligned base and 16B-multiple strides");
+  EncodeTiledFn enc = get_encode_fn();
+  FFSR_REQUIRE(enc, FFSR_ERR_DRIVER, "conv2d(tc): cuTensorMapEncodeTiled entry point unavailable");
+
+  const int taps = p.ksize * p.ksize;
+  const int cin_pad = (p.Cin + 63) / 64 * 64;
+  const int cout_pad16 = (p.Cout + 15) / 16 * 16;
+  const int nblk = cout_pad16 <= 128 ? cout_pad16 : 128;
+  const int cout_pad = (cout_pad16 + nblk - 1) / nblk * nblk;
+  FFSR_REQUIRE(((uintptr_t)p.w % 16) == 0, FFSR_ERR_ALIGN, "conv2d(tc): weights must be 16B aligned");
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    cuuint64_t strides[3] = {(cuuint64_t)p.in_sX * 2, (cuuint64_t)p.in_sY * 2, (cuuint64_t)p.in_sN * 2};
+    cuuint32_t box[4] = {64, TC_TW, TC_TH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.in), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FFSR_REQUIRE(r == CUDA_SUCCESS, FFSR_ERR_DRIVER, "conv2d(tc): activation tensor map encode failed (CUresult %d)", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)(p.groups * taps)};
+    cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * cout_pad * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)nblk, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<float*>(p.w), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FFSR_REQUIRE(r == CUDA_SUCCESS, FFSR_ERR_DRIVER, "conv2d(tc): weight tensor map encode failed (CUresult %d)", (int)r);
+  }
+
+  TcArgs a;
+  a.N = p.N; a.H = p.H; a.W = p.W; a.Cin = p.Cin; a.Cout = p.Cout; a.taps = taps; a.ks = p.ksize;
+  a.nblk = nblk;
+  a.n_nblocks = cout_pad / nblk;
+  a.nchunks = cin_pad / 64;
+  const int last = p.Cin - (a.nchunks - 1) * 64;
+  a.ksteps_last = (last + 15) / 16;
+  a.groups = p.groups;
+  a.tiles_x = ceil_div(p.W, TC_TW);
+  a.tiles_y = ceil_div(p.H, TC_TH);
+  a.total_tiles = (long long)a.tiles_x * a.tiles_y * p.N * a.n_nblocks;
+  a.out = p.out; a.out_sN = p.out_sN; a.out_sY = p.out_sY; a.out_sX = p.out_sX;
+  a.out_bf16 = p.out_dtype == FFSR_DT_BF16;
+  a.bias = p.bias; a.act = p.act; a.epi = p.epi;
+  a.r1 = p.r1; a.r1_sN = p.r1_sN; a.r1_sY = p.r1_sY; a.r1_sX = p.r1_sX; a.r1_bf16 = p.r1_dtype == FFSR_DT_BF16;
+  a.r2 = p.r2; a.r2_sN = p.r2_sN; a.r2_sY = p.r2_sY; a.r2_sX = p.r2_sX; a.r2_bf16 = p.r2_dtype == FFSR_DT_BF16;
+  a.sa = p.sa; a.sb = p.sb; a.sa_ptr = p.sa_ptr; a.sb_ptr = p.sb_ptr; a.ch_k = p.ch_k; a.ch_d = p.ch_d;
+
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  }
+  const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
+  k_conv_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmB, a);
+  return ffsr_check_launch("conv2d_tc");
 }

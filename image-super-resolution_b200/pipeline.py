@@ -50,6 +50,21 @@ def _pack_conv(w: torch.Tensor) -> torch.Tensor:
     return w.detach().float().permute(2, 3, 1, 0).reshape(kh * kw, ci, co).contiguous()
 
 
+def _pack_tc(w_f32: torch.Tensor) -> torch.Tensor:
+    """fp32 pack [G?][taps][Cin][Cout] -> tcgen05 pack [G*taps][CoutPad][CinPad] bf16 (K-major).
+    CinPad = ceil64(Cin); CoutPad = ceil16(Cout), rounded up to a multiple of 128 when > 128."""
+    if w_f32.dim() == 3:
+        w_f32 = w_f32.unsqueeze(0)
+    G, taps, ci, co = w_f32.shape
+    cip = (ci + 63) // 64 * 64
+    cop = (co + 15) // 16 * 16
+    if cop > 128:
+        cop = (cop + 127) // 128 * 128
+    out = torch.zeros(G * taps, cop, cip, device=w_f32.device, dtype=torch.bfloat16)
+    out[:, :co, :ci] = w_f32.reshape(G * taps, ci, co).transpose(1, 2).to(torch.bfloat16)
+    return out.contiguous()
+
+
 def _pack_linear(w: torch.Tensor) -> torch.Tensor:
     """[out,in] -> [1][in][out]."""
     return w.detach().float().t().contiguous().unsqueeze(0)
@@ -217,6 +232,12 @@ class FusionEngine:
             (wname, tuple(w.shape), ks, Cin, Cout)
         b = self._w.get(bias_name or (wname + ".b")) if bias else None
         p = K.ConvParams()
+        if x.t.dtype == torch.bfloat16:                    # tcgen05 path: K-major bf16 weights, packed lazily
+            wt = self._w.get(wname + ".tc")
+            if wt is None:
+                wt = self._w[wname + ".tc"] = _pack_tc(w)
+            w = wt
+            p.w_dtype = K.DT_BF16
         p.inp, p.in_sN, p.in_sY, p.in_sX, p.in_sC = x.ptr, x.sN, x.sY, x.sX, x.sC
         p.N, p.H, p.W, p.Cin, p.Cout, p.ksize = N, H, W, Cin, Cout, ks
         p.w = w.data_ptr()
@@ -226,8 +247,10 @@ class FusionEngine:
         p.act, p.epi = act, epi
         if r1 is not None:
             p.r1, p.r1_sN, p.r1_sY, p.r1_sX = r1.ptr, r1.sN, r1.sY, r1.sX
+            p.r1_dtype = K.DT_BF16 if r1.t.dtype == torch.bfloat16 else K.DT_F32
         if r2 is not None:
             p.r2, p.r2_sN, p.r2_sY, p.r2_sX = r2.ptr, r2.sN, r2.sY, r2.sX
+            p.r2_dtype = K.DT_BF16 if r2.t.dtype == torch.bfloat16 else K.DT_F32
         p.sa, p.sb = sa, sb
         p.sa_ptr = sa_ptr.data_ptr() if sa_ptr is not None else None
         p.sb_ptr = sb_ptr.data_ptr() if sb_ptr is not None else None

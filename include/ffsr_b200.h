@@ -118,9 +118,9 @@ typedef struct ffsr_conv_params {
   long long out_sN, out_sY, out_sX;
   int act; /* FFSR_ACT_* */
   int epi; /* FFSR_EPI_* */
-  const float* r1;
+  const void* r1;
   long long r1_sN, r1_sY, r1_sX;
-  const float* r2;
+  const void* r2;
   long long r2_sN, r2_sY, r2_sX;
   float sa;
   const float* sa_ptr; /* effective sa = sa * (sa_ptr ? *sa_ptr : 1) */
@@ -129,6 +129,11 @@ typedef struct ffsr_conv_params {
   const float* ch_k; /* per-channel affine of FFSR_EPI_LKAGATE */
   const float* ch_d;
   int in_dtype, out_dtype; /* FFSR_DT_* */
+  int w_dtype;             /* FFSR_DT_F32: w = [groups][k*k][Cin][Cout] fp32 (CUDA-core path);
+                              FFSR_DT_BF16: w = [groups*k*k][CoutPad][CinPad] bf16, K-major (tcgen05 path,
+                              taken iff in_dtype == FFSR_DT_BF16; CinPad = ceil64(Cin), CoutPad = ceil16(Cout)
+                              rounded up to a multiple of 128 when > 128) */
+  int r1_dtype, r2_dtype;  /* FFSR_DT_* of the residual tensors */
 } ffsr_conv_params;
 
 int ffsr_conv2d(const ffsr_conv_params* p, cudaStream_t stream);
