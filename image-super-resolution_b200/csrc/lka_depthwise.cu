@@ -53,9 +53,9 @@ __global__ void __launch_bounds__(256) k_lka_dw5(const float* __restrict__ x, in
 }
 
 // AXIS = 0: taps along W (1x21); AXIS = 1: taps along H (21x1)
-template <int AXIS>
+template <int AXIS, typename TO>
 __global__ void __launch_bounds__(256) k_lka_dw21(const float* __restrict__ in, int H, int W, int C,
-                                                  const float* __restrict__ w21, float* __restrict__ out) {
+                                                  const float* __restrict__ w21, TO* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.z;
   int y, x;
@@ -94,9 +94,9 @@ __global__ void __launch_bounds__(256) k_lka_dw21(const float* __restrict__ in, 
 #pragma unroll
     for (int t = 0; t < 21; ++t) acc = fmaf(w[t], v[r + t], acc);
     if (AXIS == 0) {
-      if (x + r < W) out[(((long)n * H + y) * W + x + r) * C + c] = acc;
+      if (x + r < W) out[(((long)n * H + y) * W + x + r) * C + c] = from_f32<TO>(acc);
     } else {
-      if (y + r < H) out[(((long)n * H + y + r) * W + x) * C + c] = acc;
+      if (y + r < H) out[(((long)n * H + y + r) * W + x) * C + c] = from_f32<TO>(acc);
     }
   }
 }
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) k_lka_dw21(const float* __restrict__ in, 
 // x: [N][H][W][C] -> out: [N][H][W][C]; tmp1/tmp2: same-size scratch (tmp2 may alias out? no: distinct)
 extern "C" int ffsr_lka_depthwise(const float* x, int N, int H, int W, int C, const float* bn_k, const float* bn_d,
                                   const float* w5, const float* wh, const float* wv, float* tmp1, float* tmp2,
-                                  float* out, cudaStream_t stream) {
+                                  void* out, int out_dtype, cudaStream_t stream) {
   FFSR_REQUIRE(x && bn_k && bn_d && w5 && wh && wv && tmp1 && tmp2 && out, FFSR_ERR_ARG, "lka_depthwise: null pointer");
   FFSR_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 32 == 0, FFSR_ERR_ARG, "lka_depthwise: C must be a multiple of 32");
   FFSR_REQUIRE(N <= 65535 && (long)H * W / 4 < 65535L * 4, FFSR_ERR_ARG, "lka_depthwise: grid too large");
@@ -121,7 +121,7 @@ extern "C" int ffsr_lka_depthwise(const float* x, int N, int H, int W, int C, co
     dim3 block(cx, ty);
     const long items = (long)H * ceil_div(W, R21);
     dim3 grid(C / cx, ceil_div(items, ty), N);
-    k_lka_dw21<0><<<grid, block, 0, stream>>>(tmp1, H, W, C, wh, tmp2);
+    k_lka_dw21<0, float><<<grid, block, 0, stream>>>(tmp1, H, W, C, wh, tmp2);
     int rc = ffsr_check_launch("lka_dw21_h");
     if (rc) return rc;
   }
@@ -129,7 +129,10 @@ extern "C" int ffsr_lka_depthwise(const float* x, int N, int H, int W, int C, co
     dim3 block(cx, ty);
     const long items = (long)ceil_div(H, R21) * W;
     dim3 grid(C / cx, ceil_div(items, ty), N);
-    k_lka_dw21<1><<<grid, block, 0, stream>>>(tmp2, H, W, C, wv, out);
+    if (out_dtype == 1)
+      k_lka_dw21<1, __nv_bfloat16><<<grid, block, 0, stream>>>(tmp2, H, W, C, wv, (__nv_bfloat16*)out);
+    else
+      k_lka_dw21<1, float><<<grid, block, 0, stream>>>(tmp2, H, W, C, wv, (float*)out);
     return ffsr_check_launch("lka_dw21_v");
   }
 }

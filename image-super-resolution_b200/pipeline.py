@@ -268,23 +268,26 @@ class FusionEngine:
             return
         self._call(self.lib.ffsr_conv2d, C.byref(p), self._stream)
 
-    def _lka_block(self, key, blk: str, x: torch.Tensor, name: str) -> torch.Tensor:
-        """x: [N,H,W,C] fp32 -> LKABlock(x) (large_kernel_attention.py:143-149), eval-mode BN folded."""
+    def _lka_block(self, key, blk: str, x: torch.Tensor, name: str, lp: bool = False) -> torch.Tensor:
+        """x: [N,H,W,C] fp32 -> LKABlock(x) (large_kernel_attention.py:143-149), eval-mode BN folded.
+        lp: the three 1x1 contractions run on tcgen05 with bf16 activations (output bf16)."""
         N, H, W, Cc = x.shape
         dev, w = x.device, self._w
+        adt = torch.bfloat16 if lp else torch.float32
         t1 = self._buf(name + ".lka_t1", x.shape, dev)
         t2 = self._buf(name + ".lka_t2", x.shape, dev)
-        a = self._buf(name + ".lka_a", x.shape, dev)
+        a = self._buf(name + ".lka_a", x.shape, dev, dtype=adt)
         self._call(self.lib.ffsr_lka_depthwise, x.data_ptr(), N, H, W, Cc, w[key + ".k1"].data_ptr(),
                    w[key + ".d1"].data_ptr(), w[key + ".w5"].data_ptr(), w[key + ".wh"].data_ptr(),
-                   w[key + ".wv"].data_ptr(), t1.data_ptr(), t2.data_ptr(), a.data_ptr(), self._stream)
+                   w[key + ".wv"].data_ptr(), t1.data_ptr(), t2.data_ptr(), a.data_ptr(),
+                   K.DT_BF16 if lp else K.DT_F32, self._stream)
         self.launches += 2
-        x1 = t1   # t1 is free again after the depthwise chain
+        x1 = self._buf(name + ".lka_x1", x.shape, dev, dtype=adt) if lp else t1   # fp32: t1 is free again
         self.conv(nhwc(a), N, H, W, Cc, key + ".pw", Cc, 1, nhwc(x1), epi=K.EPI_LKAGATE, bias_name=key + ".pwb",
                   r1=nhwc(x), sa_ptr=self._P[blk + ".scale1"], ch_k=w[key + ".k1"], ch_d=w[key + ".d1"])
-        hdn = self._buf(name + ".lka_h", (N, H, W, 2 * Cc), dev)
+        hdn = self._buf(name + ".lka_h", (N, H, W, 2 * Cc), dev, dtype=adt)
         self.conv(nhwc(x1), N, H, W, Cc, key + ".f0", 2 * Cc, 1, nhwc(hdn), act=K.ACT_GELU, bias_name=key + ".f0b")
-        x2 = t2
+        x2 = self._buf(name + ".lka_x2", x.shape, dev, dtype=adt) if lp else t2
         self.conv(nhwc(hdn), N, H, W, 2 * Cc, key + ".f2", Cc, 1, nhwc(x2), epi=K.EPI_RESIDUAL, bias_name=key + ".f2b",
                   r1=nhwc(x1), sa_ptr=self._P[blk + ".scale2"])
         return x2
@@ -335,6 +338,12 @@ class FusionEngine:
         self.launches = 0
         S = self._stream
         f32 = torch.float32
+        if m.precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {m.precision!r}")
+        lp = m.precision == "bf16"          # tcgen05 path for phases 4/5/7; phases 2/3/6 stay fp32
+        adt = torch.bfloat16 if lp else f32
+        ADT = K.DT_BF16 if lp else K.DT_F32
+        esz = 2 if lp else 4
         Hh, Wh = 4 * H, 4 * W
         lr = lr.detach().to(f32).contiguous()            # fp16 caches are up-cast at the boundary
         imgs = [t.detach().to(f32).contiguous() for t in img_list]
@@ -427,62 +436,62 @@ class FusionEngine:
             N4 = B * 4
             tok4 = tokens.view(N4, H, W, 128)
             rows = N4 * H * W
-            n1 = self._buf("co.n", (N4, H, W, 128), dev)
+            n1 = self._buf("co.n", (N4, H, W, 128), dev, dtype=adt)
             self._call(lib.ffsr_layernorm, tok4.data_ptr(), rows, 128, pp("collaborative.norm1.weight"),
-                       pp("collaborative.norm1.bias"), n1.data_ptr(), 0, S)
-            qkv = self._buf("co.qkv", (N4, H, W, 384), dev)
+                       pp("collaborative.norm1.bias"), n1.data_ptr(), int(lp), S)
+            qkv = self._buf("co.qkv", (N4, H, W, 384), dev, dtype=adt)
             self.conv(nhwc(n1), N4, H, W, 128, "co.qkv", 384, 1, nhwc(qkv))
-            ctx = self._buf("co.ctx", (N4, H, W, 128), dev)
-            self._call(lib.ffsr_token_attention, qkv.data_ptr(), B, 4, H * W, 128, ctx.data_ptr(), 0, S)
-            t1 = self._buf("co.t1", (N4, H, W, 128), dev)
+            ctx = self._buf("co.ctx", (N4, H, W, 128), dev, dtype=adt)
+            self._call(lib.ffsr_token_attention, qkv.data_ptr(), B, 4, H * W, 128, ctx.data_ptr(), int(lp), S)
+            t1 = self._buf("co.t1", (N4, H, W, 128), dev)          # residual stream stays fp32
             self.conv(nhwc(ctx), N4, H, W, 128, "co.out", 128, 1, nhwc(t1), epi=K.EPI_RESIDUAL, r1=nhwc(tok4))
             self._call(lib.ffsr_layernorm, t1.data_ptr(), rows, 128, pp("collaborative.norm2.weight"),
-                       pp("collaborative.norm2.bias"), n1.data_ptr(), 0, S)
-            hdn = self._buf("co.h", (N4, H, W, 256), dev)
+                       pp("collaborative.norm2.bias"), n1.data_ptr(), int(lp), S)
+            hdn = self._buf("co.h", (N4, H, W, 256), dev, dtype=adt)
             self.conv(nhwc(n1), N4, H, W, 128, "co.f0", 256, 1, nhwc(hdn), act=K.ACT_GELU)
             t2 = self._buf("co.t2", (N4, H, W, 128), dev)
             self.conv(nhwc(hdn), N4, H, W, 256, "co.f2", 128, 1, nhwc(t2), epi=K.EPI_RESIDUAL, r1=nhwc(t1))
-            xg = self._lka_block("co.lka", "collaborative.lka_global", t2, "co")
+            xg = self._lka_block("co.lka", "collaborative.lka_global", t2, "co", lp=lp)
             m32 = self._buf("co.m32", (N4, H, W, 32), dev)
             self.conv(nhwc(xg), N4, H, W, 128, "co.m0", 32, 1, nhwc(m32), groups=4, bias_name="co.m0b")
 
         # ---------------- HR: modulation + expert pyramid ----------------
         ecol = self._buf("ecol", (B, 4, 3, Hh, Wh), dev, fresh=fr)
-        cat3 = self._buf("cat3", (B, Hh, Wh, 80), dev, zero=True)
-        cat2 = self._buf("cat2", (B, 2 * H, 2 * W, 80), dev, zero=True)
-        s1in = self._buf("s1in", (B, H, W, 16), dev, zero=True)
+        cat3 = self._buf("cat3", (B, Hh, Wh, 80), dev, dtype=adt, zero=True)
+        cat2 = self._buf("cat2", (B, 2 * H, 2 * W, 80), dev, dtype=adt, zero=True)
+        s1in = self._buf("s1in", (B, H, W, 16), dev, dtype=adt, zero=True)
         ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in imgs])
         self._call(lib.ffsr_modulate_hr, ptrs, m32.data_ptr() if m32 is not None else None,
                    w["co.m2"].data_ptr(), w["co.m2b"].data_ptr(), B, H, W, 0 if m.training else 1, ecol.data_ptr(),
-                   cat3.data_ptr() + 64 * 4, 80, K.DT_F32, S)
-        self._call(lib.ffsr_expert_downsample, ecol.data_ptr(), B, Hh, Wh, cat2.data_ptr() + 64 * 4, 80,
-                   s1in.data_ptr(), 16, K.DT_F32, S)
+                   cat3.data_ptr() + 64 * esz, 80, ADT, S)
+        self._call(lib.ffsr_expert_downsample, ecol.data_ptr(), B, Hh, Wh, cat2.data_ptr() + 64 * esz, 80,
+                   s1in.data_ptr(), 16, ADT, S)
 
         # ---------------- Phase 5: hierarchical fusion ----------------
         mr = m.multi_res
 
         def stage(name, xin: _View, cin, h, wd, c_mid, c_out, r2=None, sb_ptr=None):
-            a = self._buf(name + ".a", (B, h, wd, c_mid), dev)
-            b_ = self._buf(name + ".b", (B, h, wd, c_out), dev)
-            c_ = self._buf(name + ".c", (B, h, wd, c_out), dev)
+            a = self._buf(name + ".a", (B, h, wd, c_mid), dev, dtype=adt)
+            b_ = self._buf(name + ".b", (B, h, wd, c_out), dev, dtype=adt)
+            c_ = self._buf(name + ".c", (B, h, wd, c_out), dev, dtype=adt)
             self.conv(xin, B, h, wd, cin, f"mr.{name}.c0", c_mid, 3, nhwc(a), act=K.ACT_GELU)
             self.conv(nhwc(a), B, h, wd, c_mid, f"mr.{name}.c2", c_out, 3, nhwc(b_), act=K.ACT_GELU)
             g = getattr(mr, name + "_gate").gate
             self._call(lib.ffsr_spatial_gate, b_.data_ptr(), B * h * wd, c_out, w[f"mr.{name}.g0"].data_ptr(),
                        pp(f"multi_res.{name}_gate.gate.0.bias"), w[f"mr.{name}.g2"].data_ptr(), pp(f"multi_res.{name}_gate.gate.2.bias"), b_.data_ptr(),
-                       K.DT_F32, S)
-            d_ = self._buf(name + ".d", (B, h, wd, c_out), dev)
+                       ADT, S)
+            d_ = self._buf(name + ".d", (B, h, wd, c_out), dev, dtype=adt)
             self.conv(nhwc(b_), B, h, wd, c_out, f"mr.{name}.r0", c_out, 3, nhwc(d_), act=K.ACT_GELU, bias=False)
             self.conv(nhwc(d_), B, h, wd, c_out, f"mr.{name}.r2", c_out, 3, nhwc(c_), bias=False, epi=K.EPI_RESIDUAL,
                       r1=nhwc(b_), sa_ptr=P[f"multi_res.{name}_res.scale"], r2=r2, sb_ptr=sb_ptr)
             return c_
 
         f1 = stage("stage1", nhwc(s1in), 12, H, W, 64, 64)
-        self._call(lib.ffsr_resize_nhwc, f1.data_ptr(), B, H, W, 64, 64, cat2.data_ptr(), 2 * H, 2 * W, 80, K.DT_F32, S)
+        self._call(lib.ffsr_resize_nhwc, f1.data_ptr(), B, H, W, 64, 64, cat2.data_ptr(), 2 * H, 2 * W, 80, ADT, S)
         f2 = stage("stage2", nhwc(cat2), 76, 2 * H, 2 * W, 64, 64, r2=nhwc(cat2), sb_ptr=P["multi_res.residual_weight_1_2"])
-        self._call(lib.ffsr_resize_nhwc, f2.data_ptr(), B, 2 * H, 2 * W, 64, 64, cat3.data_ptr(), Hh, Wh, 80, K.DT_F32, S)
+        self._call(lib.ffsr_resize_nhwc, f2.data_ptr(), B, 2 * H, 2 * W, 64, 64, cat3.data_ptr(), Hh, Wh, 80, ADT, S)
         f3 = stage("stage3", nhwc(cat3), 76, Hh, Wh, 64, 32, r2=nhwc(cat3), sb_ptr=P["multi_res.residual_weight_2_3"])
-        u16 = self._buf("mr.u16", (B, Hh, Wh, 16), dev)
+        u16 = self._buf("mr.u16", (B, Hh, Wh, 16), dev, dtype=adt)
         hier = self._buf("mr.hier", (B, Hh, Wh, 4), dev, zero=True)
         self.conv(nhwc(f3), B, Hh, Wh, 32, "mr.rgb0", 16, 3, nhwc(u16), act=K.ACT_GELU)
         self.conv(nhwc(u16), B, Hh, Wh, 16, "mr.rgb2", 3, 3, nhwc(hier), act=K.ACT_SIGMOID)
@@ -490,18 +499,20 @@ class FusionEngine:
         # ---------------- Phase 5b / 6 blend ----------------
         fused_before = torch.empty(B, 3, Hh, Wh, device=dev, dtype=f32) if want_inter else None
         fusedx = self._buf("fusedx", (B, Hh, Wh, 4), dev, zero=True)
+        fused_lp = self._buf("fused_lp", (B, Hh, Wh, 16), dev, dtype=torch.bfloat16, zero=True) if lp else None
         self._call(lib.ffsr_blend_hr, hier.data_ptr(), 4, ecol.data_ptr(), routing.data_ptr(), gates.data_ptr(),
                    diff.data_ptr(), w["fw0"].data_ptr(), pp("freq_weight_conv.0.bias"), w["fw2"].data_ptr(),
                    pp("freq_weight_conv.2.bias"), B, H, W,
-                   fused_before.data_ptr() if fused_before is not None else None, fusedx.data_ptr(), 4, None, 0, S)
+                   fused_before.data_ptr() if fused_before is not None else None, fusedx.data_ptr(), 4,
+                   fused_lp.data_ptr() if lp else None, 16 if lp else 0, S)
 
         # ---------------- Phase 7a: refinement ----------------
         idx = self._refine_idx
         rc = m.refine[idx[0]].weight.shape[0]
-        ping = self._buf("rf.ping", (B, Hh, Wh, rc), dev)
-        pong = self._buf("rf.pong", (B, Hh, Wh, rc), dev)
+        ping = self._buf("rf.ping", (B, Hh, Wh, rc), dev, dtype=adt)
+        pong = self._buf("rf.pong", (B, Hh, Wh, rc), dev, dtype=adt)
         cat6 = self._buf("cat6", (B, Hh, Wh, 8), dev, zero=True)
-        self.conv(nhwc(fusedx), B, Hh, Wh, 3, f"rf.{idx[0]}", rc, 3, nhwc(ping), act=K.ACT_GELU)
+        self.conv(nhwc(fused_lp if lp else fusedx), B, Hh, Wh, 3, f"rf.{idx[0]}", rc, 3, nhwc(ping), act=K.ACT_GELU)
         cur, nxt = ping, pong
         for i in idx[1:-1]:
             self.conv(nhwc(cur), B, Hh, Wh, rc, f"rf.{i}", rc, 3, nhwc(nxt), act=K.ACT_GELU)
@@ -519,23 +530,24 @@ class FusionEngine:
         self._call(lib.ffsr_laplacian_sub, cat6.data_ptr(), 8, down1.data_ptr(), 4, B, Hh, Wh, lap0.data_ptr(), 4, S)
         self._call(lib.ffsr_blur_pool, down1.data_ptr(), 4, B, 2 * H, 2 * W, g25, down2.data_ptr(), 4, S)
         self._call(lib.ffsr_laplacian_sub, down1.data_ptr(), 4, down2.data_ptr(), 4, B, 2 * H, 2 * W, lap1.data_ptr(), 4, S)
-        cat96 = self._buf("ee.cat96", (B, Hh, Wh, 96), dev)
+        cat96 = self._buf("ee.cat96", (B, Hh, Wh, 96), dev, dtype=adt)
         for lv, (lap, h, wd) in enumerate(((lap0, Hh, Wh), (lap1, 2 * H, 2 * W), (down2, H, W))):
             nm = f"ee{lv}"
             idt = self._buf(nm + ".idt", (B, h, wd, 32), dev)
-            o1 = self._buf(nm + ".o1", (B, h, wd, 32), dev)
-            o2 = self._buf(nm + ".o2", (B, h, wd, 32), dev)
+            o1 = self._buf(nm + ".o1", (B, h, wd, 32), dev, dtype=adt)
+            o2 = self._buf(nm + ".o2", (B, h, wd, 32), dev, dtype=adt)
+            o3 = self._buf(nm + ".o3", (B, h, wd, 32), dev) if lp else o1      # refiner output stays fp32
             t8 = self._buf(nm + ".t8", (B, h, wd, 8), dev)
             at = self._buf(nm + ".at", (B, h, wd, 1), dev)
             self.conv(nhwc(lap), B, h, wd, 3, f"ee.{lv}.proj", 32, 1, nhwc(idt))
             self.conv(nhwc(lap), B, h, wd, 3, f"ee.{lv}.c1", 32, 3, nhwc(o1), act=K.ACT_GELU)
             self.conv(nhwc(o1), B, h, wd, 32, f"ee.{lv}.c2", 32, 3, nhwc(o2), act=K.ACT_GELU)
-            self.conv(nhwc(o2), B, h, wd, 32, f"ee.{lv}.c3", 32, 3, nhwc(o1), epi=K.EPI_RESIDUAL, r1=nhwc(idt))
-            self.conv(nhwc(o1), B, h, wd, 32, f"ee.{lv}.a0", 8, 1, nhwc(t8), act=K.ACT_GELU)
+            self.conv(nhwc(o2), B, h, wd, 32, f"ee.{lv}.c3", 32, 3, nhwc(o3), epi=K.EPI_RESIDUAL, r1=nhwc(idt))
+            self.conv(nhwc(o3), B, h, wd, 32, f"ee.{lv}.a0", 8, 1, nhwc(t8), act=K.ACT_GELU)
             self.conv(nhwc(t8), B, h, wd, 8, f"ee.{lv}.a2", 1, 3, nhwc(at), act=K.ACT_SIGMOID)
-            self._call(lib.ffsr_edge_attn_upsample, o1.data_ptr(), at.data_ptr(), B, h, wd, 32,
-                       pp("edge_enhance.level_weights"), lv, cat96.data_ptr() + 32 * lv * 4, Hh, Wh, 96, K.DT_F32, S)
-        e32 = self._buf("ee.e32", (B, Hh, Wh, 32), dev)
+            self._call(lib.ffsr_edge_attn_upsample, o3.data_ptr(), at.data_ptr(), B, h, wd, 32,
+                       pp("edge_enhance.level_weights"), lv, cat96.data_ptr() + 32 * lv * esz, Hh, Wh, 96, ADT, S)
+        e32 = self._buf("ee.e32", (B, Hh, Wh, 32), dev, dtype=adt)
         self.conv(nhwc(cat96), B, Hh, Wh, 96, "ee.f0", 32, 3, nhwc(e32), act=K.ACT_GELU)
         self.conv(nhwc(e32), B, Hh, Wh, 32, "ee.f2", 3, 3, nhwc(cat6, 3))
         g16 = self._buf("ee.g16", (B, Hh, Wh, 16), dev)

@@ -86,8 +86,8 @@ int ffsr_crossband_out(const float* x, const float* raw9, int B, int H, int W, i
 /* ---- LKA depthwise chain (BN1 affine -> dw5x5 -> dw1x21 -> dw21x1) -----------------------
  * LargeKernelAttention.forward  src/models/large_kernel_attention.py:98-100; x,out: [N][H][W][C] */
 int ffsr_lka_depthwise(const float* x, int N, int H, int W, int C, const float* bn_k, const float* bn_d,
-                       const float* w5, const float* wh, const float* wv, float* tmp1, float* tmp2, float* out,
-                       cudaStream_t stream);
+                       const float* w5, const float* wh, const float* wv, float* tmp1, float* tmp2, void* out,
+                       int out_dtype, cudaStream_t stream);
 
 /* ---- token helpers (Phase 4) -------------------------------------------------------------
  * nn.LayerNorm rows (large_kernel_attention.py:389,392) and the softmax(QK^T/4)V core of

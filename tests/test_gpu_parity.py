@@ -368,3 +368,42 @@ def test_pipeline_internals_against_oracle():
     errs["sr"] = (sr.cpu() - ref).abs().max().item()
     bad = {k: v for k, v in errs.items() if not v <= 5e-5}
     assert not bad, f"stage mismatch: {bad} (all: {errs})"
+
+
+# --------------------------------------------------------------------------------------------
+# bf16 mode: tcgen05 path for phases 4/5/7, fp32 for phases 2/3/6
+# --------------------------------------------------------------------------------------------
+def _psnr(a, b):
+    return float(10.0 * torch.log10(1.0 / ((a.clamp(0, 1) - b) ** 2).mean()))
+
+
+@pytest.mark.parametrize("B,H,W,realistic", [(1, 64, 64, False), (1, 64, 64, True), (2, 40, 56, True), (1, 17, 23, False)])
+def test_bf16_mode_psnr_and_indices(B, H, W, realistic):
+    """north_star: bf16 within 0.01 dB PSNR of the fp32 reference; expert-selection indices bit-exact."""
+    dev = _cuda()
+    m = _model(True)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    lr, imgs, fts, hr = O.synthetic_inputs(B, H, W)
+    if realistic:   # SURVEY §8d realistic variant: experts = clamp(bicubic x4 (lr) + 0.02 randn)
+        g = torch.Generator().manual_seed(77)
+        up = F.interpolate(lr, scale_factor=4, mode="bicubic", align_corners=False)
+        imgs = {k: (up + 0.02 * torch.randn(up.shape, generator=g)).clamp(0, 1) for k in O.EXPERT_ORDER}
+        hr = (up + 0.01 * torch.randn(up.shape, generator=g)).clamp(0, 1)
+    with torch.no_grad():
+        ref, rint = O.run_pipeline(sd, lr, imgs, fts, return_intermediates=True)
+    m.to(dev)
+    m.precision = "bf16"
+    lrd, imd, ftd = _to(dev, lr, imgs, fts)
+    sr, ints = m._run_pipeline(lrd, [imd[k] for k in O.EXPERT_ORDER], ftd, 4 * H, 4 * W, {}, True)
+    sr = sr.cpu()
+    d_psnr = abs(_psnr(sr, hr) - _psnr(ref, hr))
+    maxabs = (sr - ref).abs().max().item()
+    between = _psnr(sr, ref)
+    assert d_psnr <= 0.01, f"|dPSNR| {d_psnr:.4f} dB (PSNR between outputs {between:.1f} dB, max-abs {maxabs:.4f})"
+    assert maxabs < 0.05 and between > 45.0, (maxabs, between)
+    assert torch.equal(ints["gates"].cpu().argmax(1), rint["gates"].argmax(1))
+    assert (ints["gates"].cpu() - rint["gates"]).abs().max().item() <= 2e-5      # phases 2/3/6 are fp32 in both modes
+    # and back: the fp32 path is unaffected by having run bf16 (separate workspaces)
+    m.precision = "fp32"
+    sr32 = m.forward_with_precomputed(lrd, imd, ftd).cpu()
+    assert (sr32 - ref).abs().max().item() <= FP32_TOL

@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_conv_params_struct_matches_header_layout():
     # 64-bit: 5 ptr/ll + 6 int + ... ; the C side is compiled from the same field order, so a
     # size check catches accidental drift between _cabi.ConvParams and ffsr_conv_params.
-    assert C.sizeof(_cabi.ConvParams) == _cabi.load().ffsr_conv_params_size() == 248
+    assert C.sizeof(_cabi.ConvParams) == _cabi.load().ffsr_conv_params_size() == 264
 
 
 def test_module_interface_matches_reference():
@@ -75,10 +75,12 @@ class _FakeLib:
         return f
 
 
-@pytest.mark.parametrize("with_feats,want_inter", [(True, False), (True, True), (False, False)])
-def test_orchestration_dry_run(with_feats, want_inter):
+@pytest.mark.parametrize("with_feats,want_inter,precision", [(True, False, "fp32"), (True, True, "fp32"),
+                                                             (False, False, "fp32"), (True, False, "bf16")])
+def test_orchestration_dry_run(with_feats, want_inter, precision):
     torch.manual_seed(0)
     m = isr_b200.CompleteEnhancedFusionSR(None).eval()
+    m.precision = precision
     eng = FusionEngine(m)
     eng.lib = _FakeLib()
     eng._get_stream = lambda dev: C.c_void_p(0)
