@@ -13,8 +13,11 @@
 //   MMA       : tcgen05.mma.cta_group::1.kind::f16, M=128, N=nblk, K=16, issued by one thread;
 //               accumulators double-buffered in TMEM (2 x 128 columns) so the epilogue of
 //               tile i overlaps the MMAs of tile i+1.
-//   warps     : 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = epilogue
-//               (tcgen05.ld 32x32b -> bias/act/residual -> vector stores).
+//   warps     : 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..17 = epilogue: warp w reads
+//               TMEM lane quarter w%4 (hardware rule) and the 16-column chunks (w-2)/4, +4, ...;
+//               tcgen05.ld 32x32b -> bias/act/residual -> 16-byte vector stores.  16 warps keep
+//               all four SM sub-partitions busy with the GELU math so that the epilogue of a
+//               tile (~2k issue cycles) hides under the MMAs of the next one.
 // Persistent: grid = min(tiles, #SMs), static round-robin over tiles.
 #include <cuda.h>
 #include "common.cuh"
@@ -27,7 +30,8 @@ constexpr int TC_STAGES = 6;
 constexpr int TC_A_BYTES = 128 * 128;          // 128 pixels x 64 bf16
 constexpr int TC_B_BYTES = 128 * 128;          // up to 128 cout x 64 bf16
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 16;              // 4 per TMEM lane quarter: each owns a 16-column slice
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_TMEM_COLS = 256;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
@@ -138,7 +142,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The wait names the loaded registers as in/out operands so that no use of them can be
+// scheduled above it.
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7) on the fast-math units: the operands
+// are bf16 here, so this is far inside the rounding noise and ~2x cheaper than erff().
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+enum { EM_NONE = 0, EM_GELU = 1, EM_RELU = 2, EM_SIGMOID = 3, EM_RESIDUAL = 4, EM_LKAGATE = 5 };
 
 __device__ __forceinline__ float load_res(const void* base, int is_bf16, long long off) {
   return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off])
@@ -163,7 +190,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -235,12 +262,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   } else {
-    // ================================ epilogue (warps 2..5) =============================
+    // ================================ epilogue (warps 2..17) ============================
     const int wq = warp & 3;                              // TMEM lane quarter this warp may read
+    const int cgp = (warp - 2) >> 2;                      // first 16-column chunk of this warp
     const int row = wq * 32 + lane;                       // pixel within the tile
     const int py = row / TC_TW, px = row % TC_TW;
     const float sa = a.sa * (a.sa_ptr ? a.sa_ptr[0] : 1.0f);
     const float sb = a.sb * (a.sb_ptr ? a.sb_ptr[0] : 1.0f);
+    const int mode = a.epi == FFSR_EPI_LKAGATE ? EM_LKAGATE : (a.epi == FFSR_EPI_RESIDUAL ? EM_RESIDUAL : a.act);
     int as = 0;
     uint32_t aph = 0;
     for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
@@ -252,37 +281,64 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int g = n % a.groups;
       const int y = ty * TC_TH + py, x = tx * TC_TW + px;
       const bool inside = (y < a.H) && (x < a.W);
-      mbar_wait(&tfull[as], aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 128u;
       const long long opix = (long long)n * a.out_sN + (long long)y * a.out_sY + (long long)x * a.out_sX;
       const long long r1pix = (long long)n * a.r1_sN + (long long)y * a.r1_sY + (long long)x * a.r1_sX;
       const long long r2pix = (long long)n * a.r2_sN + (long long)y * a.r2_sY + (long long)x * a.r2_sX;
-      for (int c0 = 0; c0 < a.nblk; c0 += 16) {
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 128u;
+      for (int c0 = cgp * 16; c0 < a.nblk; c0 += 64) {
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)c0, v);
-        tmem_wait_ld();
-        if (inside) {
-          const int ocb = nb * a.nblk + c0;
-          float f[16];
+        const int ocb = nb * a.nblk + c0;
+        float f[16];
+        // bias (overlaps the TMEM load latency)
+        if (a.bias) {
+          const float* bp = a.bias + (long long)g * a.Cout + ocb;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int oc = ocb + k;
-            float val = __uint_as_float(v[k]);
-            if (oc < a.Cout) {
-              if (a.bias) val += __ldg(a.bias + (long long)g * a.Cout + oc);
-              if (a.epi == FFSR_EPI_LKAGATE) {
-                const float xr = load_res(a.r1, a.r1_bf16, r1pix + oc);
-                val = xr + sa * (fmaf(xr, __ldg(a.ch_k + oc), __ldg(a.ch_d + oc)) * sigmoid_acc(val));
-              } else {
-                val = apply_act(val, a.act);
-                if (a.epi == FFSR_EPI_RESIDUAL) {
-                  val = load_res(a.r1, a.r1_bf16, r1pix + oc) + sa * val;
-                  if (a.r2) val += sb * load_res(a.r2, a.r2_bf16, r2pix + oc);
+          for (int k = 0; k < 16; ++k) f[k] = (ocb + k < a.Cout) ? __ldg(bp + k) : 0.f;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] = 0.f;
+        }
+        tmem_wait_ld(v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] += __uint_as_float(v[k]);
+        if (inside) {
+          switch (mode) {
+            case EM_GELU:
+#pragma unroll
+              for (int k = 0; k < 16; ++k) f[k] = gelu_fast(f[k]);
+              break;
+            case EM_RELU:
+#pragma unroll
+              for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
+              break;
+            case EM_SIGMOID:
+#pragma unroll
+              for (int k = 0; k < 16; ++k) f[k] = sigmoid_acc(f[k]);
+              break;
+            case EM_RESIDUAL:
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                if (ocb + k < a.Cout) {
+                  float val = load_res(a.r1, a.r1_bf16, r1pix + ocb + k) + sa * apply_act(f[k], a.act);
+                  if (a.r2) val += sb * load_res(a.r2, a.r2_bf16, r2pix + ocb + k);
+                  f[k] = val;
                 }
               }
-            }
-            f[k] = val;
+              break;
+            case EM_LKAGATE:
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                if (ocb + k < a.Cout) {
+                  const float xr = load_res(a.r1, a.r1_bf16, r1pix + ocb + k);
+                  f[k] = xr + sa * (fmaf(xr, __ldg(a.ch_k + ocb + k), __ldg(a.ch_d + ocb + k)) * sigmoid_acc(f[k]));
+                }
+              }
+              break;
+            default:
+              break;
           }
           const bool full16 = (ocb + 16 <= a.Cout);
           if (a.out_bf16) {
