@@ -125,7 +125,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("FFSR_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("FFSR_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--lr", type=int, nargs=2, default=[LR_H, LR_W], help="LR size (parity/debug runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
