@@ -4,12 +4,15 @@
 //
 //   GEMM view : D[pixel, cout] = sum_{tap, cin} A[pixel shifted by tap, cin] * W[tap, cout, cin]
 //   tile      : M = 128 output pixels (8 rows x 16 cols of one image), N = up to 128 cout
-//   A operand : one TMA tiled load per (tap, 64-channel chunk) from the NHWC bf16 activation
-//               tensor with a 4-D tensor map {C, W, H, N}, box {64, 16, 8, 1}, SWIZZLE_128B.
-//               Out-of-image coordinates (the conv halo) and channels >= Cin are zero-filled
-//               by the TMA unit, so padding costs no instructions and no memory traffic.
-//   B operand : weights pre-packed [group*taps][CoutPad][CinPad] bf16 (K-major), 3-D tensor
-//               map, box {64, N, 1}, SWIZZLE_128B.
+//   A operand : per (64-channel chunk, dx) ONE TMA tiled load of a row-haloed copy of the tile
+//               from the NHWC bf16 activation tensor: 4-D tensor map {C, W, H, N}, box
+//               {64, 16, 8+2*pad, 1}, SWIZZLE_128B, at (x0+dx-pad, y0-pad).  An image row of the
+//               box is 16 px x 128 B = two 1024-byte swizzle atoms, so the operand of tap (dy,dx)
+//               is the same copy at byte offset dy*2048: three loads serve nine taps and every
+//               descriptor stays 1024-byte aligned.  Out-of-image coordinates (the conv halo) and
+//               channels >= Cin are zero-filled by the TMA unit: padding costs no instructions.
+//   B operand : weights pre-packed [group][dy][dx][CoutPad][CinPad] bf16 (K-major); one 5-D TMA
+//               load {64, N, 1, ks, 1} brings the ks taps (all dy) of this dx.
 //   MMA       : tcgen05.mma.cta_group::1.kind::f16, M=128, N=nblk, K=16, issued by one thread;
 //               accumulators double-buffered in TMEM (2 x 128 columns) so the epilogue of
 //               tile i overlaps the MMAs of tile i+1.
@@ -26,14 +29,13 @@
 namespace {
 
 constexpr int TC_TH = 8, TC_TW = 16;           // output pixel tile (M = 128)
-constexpr int TC_STAGES = 6;
-constexpr int TC_A_BYTES = 128 * 128;          // 128 pixels x 64 bf16
-constexpr int TC_B_BYTES = 128 * 128;          // up to 128 cout x 64 bf16
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_ROW_BYTES = TC_TW * 128;      // one image row of the tile: 16 px x 64 bf16
+constexpr int TC_SMEM_MAX = 232448;            // 227 KB opt-in limit per CTA
+constexpr int TC_SMEM_HDR = 1024;              // barriers + TMEM slot (after 1024B alignment)
 constexpr int TC_EPI_WARPS = 16;              // 4 per TMEM lane quarter: each owns a 16-column slice
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_TMEM_COLS = 256;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct TcArgs {
   int N, H, W, Cin, Cout, taps, ks;
@@ -41,6 +43,7 @@ struct TcArgs {
   int n_nblocks;     // cout blocks
   int nchunks;       // 64-channel K chunks
   int ksteps_last;   // K=16 steps issued for the last chunk
+  int a_bytes, b_bytes, stage_bytes, nstages;
   int groups;
   int tiles_x, tiles_y;
   long long total_tiles;
@@ -103,6 +106,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
@@ -177,19 +188,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-  uint64_t* full = bars;                       // [TC_STAGES]
-  uint64_t* empty = bars + TC_STAGES;          // [TC_STAGES]
-  uint64_t* tfull = bars + 2 * TC_STAGES;      // [2]
-  uint64_t* tempty = bars + 2 * TC_STAGES + 2; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* full = bars;                           // [TC_MAX_STAGES]
+  uint64_t* empty = bars + TC_MAX_STAGES;          // [TC_MAX_STAGES]
+  uint64_t* tfull = bars + 2 * TC_MAX_STAGES;      // [2]
+  uint64_t* tempty = bars + 2 * TC_MAX_STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
+  uint8_t* stages = smem + TC_SMEM_HDR;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -203,8 +215,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t tmem_base = *tmem_slot;
 
   const int pad = a.ks / 2;
-  const int kiters = a.taps * a.nchunks;
-  const uint32_t stage_tx = TC_A_BYTES + (uint32_t)a.nblk * 128u;
+  const int kiters = a.ks * a.nchunks;               // one pipeline stage per (chunk, dx)
+  const uint32_t stage_tx = (uint32_t)(a.a_bytes + a.b_bytes);
 
   if (warp == 0) {
     // ================================ TMA producer ======================================
@@ -218,15 +230,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int ty = (int)(r % a.tiles_y); r /= a.tiles_y;
         const int n = (int)r;
         const int g = n % a.groups;
-        for (int tap = 0; tap < a.taps; ++tap) {
-          const int dy = tap / a.ks - pad, dx = tap % a.ks - pad;
-          for (int ch = 0; ch < a.nchunks; ++ch) {
+        for (int ch = 0; ch < a.nchunks; ++ch) {
+          for (int dxi = 0; dxi < a.ks; ++dxi) {
             mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* sa_ = smem + s * TC_STAGE_BYTES;
+            uint8_t* sa_ = stages + s * a.stage_bytes;
             mbar_expect_tx(&full[s], stage_tx);
-            tma_load_4d(sa_, &tmA, &full[s], ch * 64, tx * TC_TW + dx, ty * TC_TH + dy, n);
-            tma_load_3d(sa_ + TC_A_BYTES, &tmB, &full[s], ch * 64, nb * a.nblk, g * a.taps + tap);
-            if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+            tma_load_4d(sa_, &tmA, &full[s], ch * 64, tx * TC_TW + dxi - pad, ty * TC_TH - pad, n);
+            tma_load_5d(sa_ + a.a_bytes, &tmB, &full[s], ch * 64, nb * a.nblk, dxi, 0, g);
+            if (++s == a.nstages) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -246,18 +257,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         mbar_wait(&full[s], ph);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + s * TC_STAGE_BYTES);
-          const uint64_t da = make_sw128_desc(a_addr);
-          const uint64_t db = make_sw128_desc(a_addr + TC_A_BYTES);
-          const int ch = it % a.nchunks;
+          const uint32_t a_addr = smem_u32(stages + s * a.stage_bytes);
+          const int ch = it / a.ks;
           const int ksteps = (ch == a.nchunks - 1) ? a.ksteps_last : 4;
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int dyi = 0; dyi < a.ks; ++dyi) {
+            // tap (dyi, dx of this stage): rows dyi..dyi+7 of the haloed copy, dy-th weight slice
+            const uint64_t da = make_sw128_desc(a_addr + (uint32_t)(dyi * TC_ROW_BYTES));
+            const uint64_t db = make_sw128_desc(a_addr + (uint32_t)a.a_bytes + (uint32_t)(dyi * a.nblk * 128));
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || dyi > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(&empty[s]);                       // smem slot reusable once these MMAs retire
           if (it == kiters - 1) umma_commit(&tfull[as]);  // accumulator complete
         }
         __syncwarp();
-        if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+        if (++s == a.nstages) { s = 0; ph ^= 1; }
       }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
@@ -431,7 +445,7 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   {
     cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
     cuuint64_t strides[3] = {(cuuint64_t)p.in_sX * 2, (cuuint64_t)p.in_sY * 2, (cuuint64_t)p.in_sN * 2};
-    cuuint32_t box[4] = {64, TC_TW, TC_TH, 1};
+    cuuint32_t box[4] = {64, TC_TW, (cuuint32_t)(TC_TH + 2 * (p.ksize / 2)), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.in), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -439,11 +453,13 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
     FFSR_REQUIRE(r == CUDA_SUCCESS, FFSR_ERR_DRIVER, "conv2d(tc): activation tensor map encode failed (CUresult %d)", (int)r);
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)(p.groups * taps)};
-    cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * cout_pad * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)nblk, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<float*>(p.w), dims, strides, box, es,
+    // [g][dy][dx][CoutPad][CinPad] viewed as {K, N, dx, dy, g}
+    const cuuint64_t tap_bytes = (cuuint64_t)cin_pad * cout_pad * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)p.ksize, (cuuint64_t)p.ksize, (cuuint64_t)p.groups};
+    cuuint64_t strides[4] = {(cuuint64_t)cin_pad * 2, tap_bytes, tap_bytes * p.ksize, tap_bytes * taps};
+    cuuint32_t box[5] = {64, (cuuint32_t)nblk, 1, (cuuint32_t)p.ksize, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<float*>(p.w), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FFSR_REQUIRE(r == CUDA_SUCCESS, FFSR_ERR_DRIVER, "conv2d(tc): weight tensor map encode failed (CUresult %d)", (int)r);
@@ -456,6 +472,12 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   a.nchunks = cin_pad / 64;
   const int last = p.Cin - (a.nchunks - 1) * 64;
   a.ksteps_last = (last + 15) / 16;
+  a.a_bytes = (TC_TH + 2 * (p.ksize / 2)) * TC_ROW_BYTES;
+  a.b_bytes = p.ksize * nblk * 128;
+  a.stage_bytes = a.a_bytes + a.b_bytes;
+  a.nstages = (TC_SMEM_MAX - 1024 - TC_SMEM_HDR) / a.stage_bytes;
+  if (a.nstages > TC_MAX_STAGES) a.nstages = TC_MAX_STAGES;
+  const int smem_bytes = 1024 + TC_SMEM_HDR + a.nstages * a.stage_bytes;
   a.groups = p.groups;
   a.tiles_x = ceil_div(p.W, TC_TW);
   a.tiles_y = ceil_div(p.H, TC_TH);
@@ -472,9 +494,9 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
   }
   const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
-  k_conv_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmB, a);
+  k_conv_tc<<<grid, TC_THREADS, smem_bytes, stream>>>(tmA, tmB, a);
   return ffsr_check_launch("conv2d_tc");
 }
