@@ -67,9 +67,11 @@ PROTOTYPES = {
     "ffsr_resize_nhwc": (_I, [_P, _I, _I, _I, _I, _LL, _P, _I, _I, _LL, _I, _P]),
     "ffsr_spatial_gate": (_I, [_P, _L, _I, _P, _P, _P, _P, _P, _I, _P]),
     "ffsr_blend_hr": (_I, [_P, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _LL, _P, _LL, _P]),
-    "ffsr_blur_pool": (_I, [_P, _LL, _I, _I, _I, _P, _P, _LL, _P]),
-    "ffsr_laplacian_sub": (_I, [_P, _LL, _P, _LL, _I, _I, _I, _P, _LL, _P]),
-    "ffsr_edge_attn_upsample": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _LL, _I, _P]),
+    "ffsr_blur_pool": (_I, [_P, _LL, _I, _I, _I, _P, _P, _LL, _P, _LL, _P]),
+    "ffsr_laplacian_sub": (_I, [_P, _LL, _P, _LL, _I, _I, _I, _P, _LL, _P, _LL, _P]),
+    "ffsr_edge_attn_upsample": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _LL, _I, _P]),
+    "ffsr_nchw_to_nhwc_bf16": (_I, [_P, _I, _I, _L, _P, _LL, _LL, _P]),
+    "ffsr_cast_f32_to_bf16": (_I, [_P, _P, _L, _P]),
     "ffsr_final_combine": (_I, [_P, _LL, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
 }
 

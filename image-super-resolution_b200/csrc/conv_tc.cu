@@ -35,7 +35,8 @@ constexpr int TC_SMEM_MAX = 232448;            // 227 KB opt-in limit per CTA
 constexpr int TC_SMEM_HDR = 1024;              // barriers + TMEM slot (after 1024B alignment)
 constexpr int TC_EPI_WARPS = 16;              // 4 per TMEM lane quarter: each owns a 16-column slice
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_TMEM_COLS = 512;             // whole TMEM: ring of 512/slot accumulators (1 CTA per SM)
+constexpr int TC_MAX_ACC = 8;
 
 struct TcArgs {
   int N, H, W, Cin, Cout, taps, ks;
@@ -44,6 +45,7 @@ struct TcArgs {
   int nchunks;       // 64-channel K chunks
   int ksteps_last;   // K=16 steps issued for the last chunk
   int a_bytes, b_bytes, stage_bytes, nstages;
+  int acc_slot, nacc; // TMEM columns per accumulator (32/64/128) and ring depth
   int groups;
   int tiles_x, tiles_y;
   long long total_tiles;
@@ -178,6 +180,37 @@ __device__ __forceinline__ float gelu_fast(float x) {
 
 enum { EM_NONE = 0, EM_GELU = 1, EM_RELU = 2, EM_SIGMOID = 3, EM_RESIDUAL = 4, EM_LKAGATE = 5 };
 
+// 16 consecutive residual channels -> fp32 registers; 16-byte vector loads when aligned.
+__device__ __forceinline__ void load_res16(const void* base, int is_bf16, long long off, int nvalid, float (&o)[16]) {
+  if (is_bf16) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + off;
+    if (nvalid == 16 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(p)), u1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+      const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+        o[2 * k] = f2.x; o[2 * k + 1] = f2.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) o[k] = k < nvalid ? __bfloat162float(p[k]) : 0.f;
+    }
+  } else {
+    const float* p = reinterpret_cast<const float*>(base) + off;
+    if (nvalid == 16 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p) + k);
+        o[4 * k] = v.x; o[4 * k + 1] = v.y; o[4 * k + 2] = v.z; o[4 * k + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) o[k] = k < nvalid ? p[k] : 0.f;
+    }
+  }
+}
+
 __device__ __forceinline__ float load_res(const void* base, int is_bf16, long long off) {
   return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off])
                  : reinterpret_cast<const float*>(base)[off];
@@ -191,9 +224,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint64_t* full = bars;                           // [TC_MAX_STAGES]
   uint64_t* empty = bars + TC_MAX_STAGES;          // [TC_MAX_STAGES]
-  uint64_t* tfull = bars + 2 * TC_MAX_STAGES;      // [2]
-  uint64_t* tempty = bars + 2 * TC_MAX_STAGES + 2; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
+  uint64_t* tfull = bars + 2 * TC_MAX_STAGES;                  // [TC_MAX_ACC]
+  uint64_t* tempty = bars + 2 * TC_MAX_STAGES + TC_MAX_ACC;    // [TC_MAX_ACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 2 * TC_MAX_ACC);
   uint8_t* stages = smem + TC_SMEM_HDR;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -202,7 +235,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
+    for (int i = 0; i < TC_MAX_ACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -252,7 +285,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       mbar_wait(&tempty[as], aph ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)as * 128u;
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * a.acc_slot);
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
@@ -273,7 +306,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         __syncwarp();
         if (++s == a.nstages) { s = 0; ph ^= 1; }
       }
-      if (++as == 2) { as = 0; aph ^= 1; }
+      if (++as == a.nacc) { as = 0; aph ^= 1; }
     }
   } else {
     // ================================ epilogue (warps 2..17) ============================
@@ -298,27 +331,37 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const long long opix = (long long)n * a.out_sN + (long long)y * a.out_sY + (long long)x * a.out_sX;
       const long long r1pix = (long long)n * a.r1_sN + (long long)y * a.r1_sY + (long long)x * a.r1_sX;
       const long long r2pix = (long long)n * a.r2_sN + (long long)y * a.r2_sY + (long long)x * a.r2_sX;
-      mbar_wait(&tfull[as], aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 128u;
+      const bool has_r1 = inside && (mode == EM_RESIDUAL || mode == EM_LKAGATE);
+      const bool has_r2 = inside && mode == EM_RESIDUAL && a.r2 != nullptr;
+      bool waited = false;
+      uint32_t taddr = 0;
       for (int c0 = cgp * 16; c0 < a.nblk; c0 += 64) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
         const int ocb = nb * a.nblk + c0;
-        float f[16];
-        // bias (overlaps the TMEM load latency)
-        if (a.bias) {
+        const int nvalid = min(16, a.Cout - ocb);        // may be <= 0 for padded columns
+        float f[16], r1v[16], r2v[16];
+        // operands that do not depend on the accumulator are fetched before waiting for it
+        if (a.bias && nvalid > 0) {
           const float* bp = a.bias + (long long)g * a.Cout + ocb;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) f[k] = (ocb + k < a.Cout) ? __ldg(bp + k) : 0.f;
+          for (int k = 0; k < 16; ++k) f[k] = (k < nvalid) ? __ldg(bp + k) : 0.f;
         } else {
 #pragma unroll
           for (int k = 0; k < 16; ++k) f[k] = 0.f;
         }
+        if (has_r1 && nvalid > 0) load_res16(a.r1, a.r1_bf16, r1pix + ocb, nvalid, r1v);
+        if (has_r2 && nvalid > 0) load_res16(a.r2, a.r2_bf16, r2pix + ocb, nvalid, r2v);
+        if (!waited) {
+          mbar_wait(&tfull[as], aph);
+          tc_fence_after();
+          taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * a.acc_slot);
+          waited = true;
+        }
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
         tmem_wait_ld(v);
 #pragma unroll
         for (int k = 0; k < 16; ++k) f[k] += __uint_as_float(v[k]);
-        if (inside) {
+        if (inside && nvalid > 0) {
           switch (mode) {
             case EM_GELU:
 #pragma unroll
@@ -333,20 +376,22 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               for (int k = 0; k < 16; ++k) f[k] = sigmoid_acc(f[k]);
               break;
             case EM_RESIDUAL:
+              if (a.act != ACT_NONE) {
 #pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                if (ocb + k < a.Cout) {
-                  float val = load_res(a.r1, a.r1_bf16, r1pix + ocb + k) + sa * apply_act(f[k], a.act);
-                  if (a.r2) val += sb * load_res(a.r2, a.r2_bf16, r2pix + ocb + k);
-                  f[k] = val;
-                }
+                for (int k = 0; k < 16; ++k) f[k] = apply_act(f[k], a.act);
+              }
+#pragma unroll
+              for (int k = 0; k < 16; ++k) f[k] = fmaf(sa, f[k], r1v[k]);
+              if (has_r2) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) f[k] = fmaf(sb, r2v[k], f[k]);
               }
               break;
             case EM_LKAGATE:
 #pragma unroll
               for (int k = 0; k < 16; ++k) {
-                if (ocb + k < a.Cout) {
-                  const float xr = load_res(a.r1, a.r1_bf16, r1pix + ocb + k);
+                if (k < nvalid) {
+                  const float xr = r1v[k];
                   f[k] = xr + sa * (fmaf(xr, __ldg(a.ch_k + ocb + k), __ldg(a.ch_d + ocb + k)) * sigmoid_acc(f[k]));
                 }
               }
@@ -388,10 +433,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         }
       }
+      if (!waited) mbar_wait(&tfull[as], aph);          // warps without a column chunk still pace the ring
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
-      if (++as == 2) { as = 0; aph ^= 1; }
+      if (++as == a.nacc) { as = 0; aph ^= 1; }
     }
   }
 
@@ -478,6 +524,9 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   a.nstages = (TC_SMEM_MAX - 1024 - TC_SMEM_HDR) / a.stage_bytes;
   if (a.nstages > TC_MAX_STAGES) a.nstages = TC_MAX_STAGES;
   const int smem_bytes = 1024 + TC_SMEM_HDR + a.nstages * a.stage_bytes;
+  a.acc_slot = nblk <= 32 ? 32 : (nblk <= 64 ? 64 : 128);
+  a.nacc = TC_TMEM_COLS / a.acc_slot;
+  if (a.nacc > TC_MAX_ACC) a.nacc = TC_MAX_ACC;
   a.groups = p.groups;
   a.tiles_x = ceil_div(p.W, TC_TW);
   a.tiles_y = ceil_div(p.H, TC_TH);

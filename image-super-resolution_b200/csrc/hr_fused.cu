@@ -375,7 +375,8 @@ extern "C" int ffsr_blend_hr(const float* hier, long long hier_sX, const float* 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_blur_pool(const float* __restrict__ x, long long x_sX, int H, int W,
                                                    const float* __restrict__ gauss25, float* __restrict__ down,
-                                                   long long down_sX) {
+                                                   long long down_sX, __nv_bfloat16* __restrict__ down_lp,
+                                                   long long down_lp_sX) {
   __shared__ float sg[25];
   if (threadIdx.x < 25) sg[threadIdx.x] = gauss25[threadIdx.x];
   __syncthreads();
@@ -413,20 +414,24 @@ __global__ void __launch_bounds__(128) k_blur_pool(const float* __restrict__ x, 
     o[c] = (((bl[0][0] + bl[0][1]) + bl[1][0]) + bl[1][1]) * 0.25f;
   }
   if (down_sX > 3) o[3] = 0.f;
+  if (down_lp) store_vec4<__nv_bfloat16>(down_lp + (((long)n * H2 + i) * W2 + j) * down_lp_sX, o[0], o[1], o[2], 0.f);
 }
 
 extern "C" int ffsr_blur_pool(const float* x, long long x_sX, int N, int H, int W, const float* gauss25, float* down,
-                              long long down_sX, cudaStream_t stream) {
+                              long long down_sX, void* down_lp, long long down_lp_sX, cudaStream_t stream) {
   FFSR_REQUIRE(x && gauss25 && down, FFSR_ERR_ARG, "blur_pool: null pointer");
   FFSR_REQUIRE(N > 0 && H >= 2 && W >= 2 && x_sX >= 3 && down_sX >= 3, FFSR_ERR_ARG, "blur_pool: bad shape");
   dim3 grid(ceil_div(W / 2, 128), H / 2, N);
-  k_blur_pool<<<grid, 128, 0, stream>>>(x, x_sX, H, W, gauss25, down, down_sX);
+  FFSR_REQUIRE(!down_lp || (((uintptr_t)down_lp % 8) == 0 && down_lp_sX % 4 == 0 && down_lp_sX >= 4), FFSR_ERR_ALIGN,
+               "blur_pool: bf16 copy alignment");
+  k_blur_pool<<<grid, 128, 0, stream>>>(x, x_sX, H, W, gauss25, down, down_sX, (__nv_bfloat16*)down_lp, down_lp_sX);
   return ffsr_check_launch("blur_pool");
 }
 
 __global__ void __launch_bounds__(128) k_laplacian_sub(const float* __restrict__ x, long long x_sX,
                                                        const float* __restrict__ down, long long down_sX, int H, int W,
-                                                       float* __restrict__ lap, long long lap_sX) {
+                                                       float* __restrict__ lap, long long lap_sX,
+                                                       __nv_bfloat16* __restrict__ lap_lp, long long lap_lp_sX) {
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y, n = blockIdx.z;
   if (X >= W) return;
@@ -444,22 +449,26 @@ __global__ void __launch_bounds__(128) k_laplacian_sub(const float* __restrict__
   for (int ch = 0; ch < 3; ++ch)
     o[ch] = xp[ch] - (ty.w0 * (tx.w0 * a[ch] + tx.w1 * b[ch]) + ty.w1 * (tx.w0 * c[ch] + tx.w1 * e[ch]));
   if (lap_sX > 3) o[3] = 0.f;
+  if (lap_lp) store_vec4<__nv_bfloat16>(lap_lp + pix * lap_lp_sX, o[0], o[1], o[2], 0.f);
 }
 
 extern "C" int ffsr_laplacian_sub(const float* x, long long x_sX, const float* down, long long down_sX, int N, int H,
-                                  int W, float* lap, long long lap_sX, cudaStream_t stream) {
+                                  int W, float* lap, long long lap_sX, void* lap_lp, long long lap_lp_sX,
+                                  cudaStream_t stream) {
   FFSR_REQUIRE(x && down && lap, FFSR_ERR_ARG, "laplacian_sub: null pointer");
   FFSR_REQUIRE(N > 0 && H >= 2 && W >= 2, FFSR_ERR_ARG, "laplacian_sub: bad shape");
   dim3 grid(ceil_div(W, 128), H, N);
-  k_laplacian_sub<<<grid, 128, 0, stream>>>(x, x_sX, down, down_sX, H, W, lap, lap_sX);
+  FFSR_REQUIRE(!lap_lp || (((uintptr_t)lap_lp % 8) == 0 && lap_lp_sX % 4 == 0 && lap_lp_sX >= 4), FFSR_ERR_ALIGN,
+               "laplacian_sub: bf16 copy alignment");
+  k_laplacian_sub<<<grid, 128, 0, stream>>>(x, x_sX, down, down_sX, H, W, lap, lap_sX, (__nv_bfloat16*)lap_lp, lap_lp_sX);
   return ffsr_check_launch("laplacian_sub");
 }
 
 // ------------------------------------------------------------------------------------------
 // refiner tail: (o * attn), bilinear to HxW if needed, times softmax(level_weights)[level]
 // ------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) k_edge_attn_up(const float* __restrict__ o, const float* __restrict__ attn, int h,
+template <typename TI, typename T>
+__global__ void __launch_bounds__(256) k_edge_attn_up(const TI* __restrict__ o, const float* __restrict__ attn, int h,
                                                       int w, int C4, const float* __restrict__ level_w, int level,
                                                       T* __restrict__ dst, int H, int W, long long dst_sX, long total) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -473,20 +482,20 @@ __global__ void __launch_bounds__(256) k_edge_attn_up(const float* __restrict__ 
   const int X = (int)(pix % W), Y = (int)((pix / W) % H);
   const long n = pix / ((long)W * H);
   const int C = 4 * C4;
-  const float* ob = o + n * h * w * C + 4 * c4;
+  const TI* ob = o + n * h * w * C + 4 * c4;
   const float* ab = attn + n * h * w;
   float4 r;
   if (h == H && w == W) {
     const long q = (long)Y * w + X;
-    const float4 v = *reinterpret_cast<const float4*>(ob + q * C);
+    const float4 v = load_vec4<TI>(ob + q * C);
     const float a = ab[q];
     r = make_float4(v.x * a, v.y * a, v.z * a, v.w * a);
   } else {
     const BilinTap ty = bilin_tap(Y, h, H), tx = bilin_tap(X, w, W);
     const long q00 = (long)ty.i0 * w + tx.i0, q01 = (long)ty.i0 * w + tx.i1;
     const long q10 = (long)ty.i1 * w + tx.i0, q11 = (long)ty.i1 * w + tx.i1;
-    const float4 v00 = *reinterpret_cast<const float4*>(ob + q00 * C), v01 = *reinterpret_cast<const float4*>(ob + q01 * C);
-    const float4 v10 = *reinterpret_cast<const float4*>(ob + q10 * C), v11 = *reinterpret_cast<const float4*>(ob + q11 * C);
+    const float4 v00 = load_vec4<TI>(ob + q00 * C), v01 = load_vec4<TI>(ob + q01 * C);
+    const float4 v10 = load_vec4<TI>(ob + q10 * C), v11 = load_vec4<TI>(ob + q11 * C);
     const float a00 = ab[q00], a01 = ab[q01], a10 = ab[q10], a11 = ab[q11];
     r.x = ty.w0 * (tx.w0 * (v00.x * a00) + tx.w1 * (v01.x * a01)) + ty.w1 * (tx.w0 * (v10.x * a10) + tx.w1 * (v11.x * a11));
     r.y = ty.w0 * (tx.w0 * (v00.y * a00) + tx.w1 * (v01.y * a01)) + ty.w1 * (tx.w0 * (v10.y * a10) + tx.w1 * (v11.y * a11));
@@ -496,7 +505,7 @@ __global__ void __launch_bounds__(256) k_edge_attn_up(const float* __restrict__ 
   store_vec4<T>(dst + pix * dst_sX + 4 * c4, r.x * lw, r.y * lw, r.z * lw, r.w * lw);
 }
 
-extern "C" int ffsr_edge_attn_upsample(const float* o, const float* attn, int N, int h, int w, int C,
+extern "C" int ffsr_edge_attn_upsample(const void* o, int o_dtype, const float* attn, int N, int h, int w, int C,
                                        const float* level_w, int level, void* dst, int H, int W, long long dst_sX,
                                        int dtype, cudaStream_t stream) {
   FFSR_REQUIRE(o && attn && level_w && dst, FFSR_ERR_ARG, "edge_attn_upsample: null pointer");
@@ -505,10 +514,13 @@ extern "C" int ffsr_edge_attn_upsample(const float* o, const float* attn, int N,
   FFSR_REQUIRE(((uintptr_t)o % 16) == 0 && ((uintptr_t)dst % (4 * esz)) == 0 && dst_sX % 4 == 0, FFSR_ERR_ALIGN,
                "edge_attn_upsample: alignment");
   const long total = (long)N * H * W * (C / 4);
-  if (dtype == FFSR_DT_BF16)
-    k_edge_attn_up<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, stream>>>(o, attn, h, w, C / 4, level_w, level, (__nv_bfloat16*)dst, H, W, dst_sX, total);
+  FFSR_REQUIRE(o_dtype == FFSR_DT_F32 || dtype == FFSR_DT_BF16, FFSR_ERR_ARG, "edge_attn_upsample: bf16 input needs bf16 output");
+  if (o_dtype == FFSR_DT_BF16)
+    k_edge_attn_up<__nv_bfloat16, __nv_bfloat16><<<ceil_div(total, 256), 256, 0, stream>>>((const __nv_bfloat16*)o, attn, h, w, C / 4, level_w, level, (__nv_bfloat16*)dst, H, W, dst_sX, total);
+  else if (dtype == FFSR_DT_BF16)
+    k_edge_attn_up<float, __nv_bfloat16><<<ceil_div(total, 256), 256, 0, stream>>>((const float*)o, attn, h, w, C / 4, level_w, level, (__nv_bfloat16*)dst, H, W, dst_sX, total);
   else
-    k_edge_attn_up<float><<<ceil_div(total, 256), 256, 0, stream>>>(o, attn, h, w, C / 4, level_w, level, (float*)dst, H, W, dst_sX, total);
+    k_edge_attn_up<float, float><<<ceil_div(total, 256), 256, 0, stream>>>((const float*)o, attn, h, w, C / 4, level_w, level, (float*)dst, H, W, dst_sX, total);
   return ffsr_check_launch("edge_attn_upsample");
 }
 
@@ -547,4 +559,57 @@ extern "C" int ffsr_final_combine(const float* xe, long long xe_sX, const float*
   dim3 grid(ceil_div(4 * W, 128), 4 * H, B);
   k_final_combine<<<grid, 128, 0, stream>>>(xe, xe_sX, gate, strength, lr, residual_scale, H, W, clamp01, out);
   return ffsr_check_launch("final_combine");
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 NCHW -> bf16 channels-last slice (expert features -> tcgen05 operand), 32x32 smem transpose
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nchw_to_nhwc_bf16(const float* __restrict__ src, int C, long HW,
+                                                           __nv_bfloat16* __restrict__ dst, long long dst_sN,
+                                                           long long dst_sX) {
+  __shared__ float tile[32][33];
+  const long p0 = (long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32, n = blockIdx.z;
+  const int tx = threadIdx.x, ty = threadIdx.y;           // (32, 8)
+  const float* s = src + (long)n * C * HW;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + ty + 8 * j;
+    const long p = p0 + tx;
+    tile[ty + 8 * j][tx] = (c < C && p < HW) ? s[(long)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  __nv_bfloat16* d = dst + (long long)n * dst_sN;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long p = p0 + ty + 8 * j;
+    const int c = c0 + tx;
+    if (p < HW && c < C) d[p * dst_sX + c] = __float2bfloat16_rn(tile[tx][ty + 8 * j]);
+  }
+}
+
+extern "C" int ffsr_nchw_to_nhwc_bf16(const float* src, int N, int C, long HW, void* dst, long long dst_sN,
+                                      long long dst_sX, cudaStream_t stream) {
+  FFSR_REQUIRE(src && dst && N > 0 && N <= 65535 && C > 0 && HW > 0, FFSR_ERR_ARG, "nchw_to_nhwc_bf16: bad args");
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N);
+  k_nchw_to_nhwc_bf16<<<grid, dim3(32, 8), 0, stream>>>(src, C, HW, (__nv_bfloat16*)dst, dst_sN, dst_sX);
+  return ffsr_check_launch("nchw_to_nhwc_bf16");
+}
+
+__global__ void __launch_bounds__(256) k_cast_bf16(const float4* __restrict__ src, uint2* __restrict__ dst, long n4) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = src[i];
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  dst[i] = u;
+}
+
+extern "C" int ffsr_cast_f32_to_bf16(const float* src, void* dst, long n, cudaStream_t stream) {
+  FFSR_REQUIRE(src && dst && n > 0 && n % 4 == 0, FFSR_ERR_ARG, "cast_f32_to_bf16: n must be a positive multiple of 4");
+  FFSR_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, FFSR_ERR_ALIGN, "cast_f32_to_bf16: alignment");
+  k_cast_bf16<<<ceil_div(n / 4, 256), 256, 0, stream>>>((const float4*)src, (uint2*)dst, n / 4);
+  return ffsr_check_launch("cast_f32_to_bf16");
 }

@@ -141,6 +141,13 @@ class FusionEngine:
             co = m.collaborative
             for n in EXPERT_ORDER:
                 conv("co.align." + n, co.align_layers[n])
+            cin_max = max(co.align_layers[n].weight.shape[1] for n in EXPERT_ORDER)
+            wa = torch.zeros(4, 1, cin_max, co.align_layers["drct"].weight.shape[0], device=dev)
+            for e, n in enumerate(EXPERT_ORDER):
+                pw_ = _pack_conv(co.align_layers[n].weight)
+                wa[e, :, :pw_.shape[1], :] = pw_
+            w["co.align.all"] = wa
+            w["co.align.all.b"] = torch.stack([co.align_layers[n].bias.detach().float() for n in EXPERT_ORDER]).contiguous()
             w["co.qkv"] = _pack_linear(co.cross_attn.in_proj_weight)
             w["co.qkv.b"] = co.cross_attn.in_proj_bias.detach().float().contiguous()
             w["co.out"] = _pack_linear(co.cross_attn.out_proj.weight)
@@ -415,24 +422,38 @@ class FusionEngine:
                         f"expert feature '{n}' has shape {tuple(f.shape)}; the sm_100a path needs [B,C,{H},{W}] "
                         "(features at LR resolution, as CachedSRDataset provides)")
             tokens = self._buf("co.tok", (B, 4, H, W, 128), dev, zero=True)
-            if len(have) < 4:
-                tokens.zero_()                              # missing expert -> zero token (:378-381)
-            for e, n in enumerate(EXPERT_ORDER):
-                if n not in feats:
-                    continue
-                f = feats[n].detach().to(f32).contiguous()
-                cin_w = co.align_layers[n].weight.shape[1]
-                cin = min(f.shape[1], cin_w)               # truncate / implicit zero-pad (:349-358)
-                wn = "co.align." + n
-                if cin != cin_w:
-                    wn2 = wn + ".c%d" % cin
-                    if wn2 not in w:
-                        w[wn2] = w[wn][:, :cin, :].contiguous()
-                        w[wn2 + ".b"] = w[wn + ".b"]
-                    wn = wn2
-                tv = tokens[:, e]
-                ov = _View(tv.data_ptr(), tokens.stride(0), tokens.stride(2), tokens.stride(3), 1, tokens)
-                self.conv(nchw(f), B, H, W, cin, wn, 128, 1, ov)
+            cin_exp = {n: co.align_layers[n].weight.shape[1] for n in EXPERT_ORDER}
+            fast_align = lp and len(have) == 4 and all(feats[n].shape[1] == cin_exp[n] for n in EXPERT_ORDER)
+            if fast_align:
+                # bf16 mode: NCHW fp32 features -> one bf16 channels-last buffer, then ONE grouped tcgen05 1x1 conv
+                cmax = max(cin_exp.values())
+                cs = (cmax + 7) // 8 * 8
+                fbuf = self._buf("co.feat", (B, 4, H, W, cs), dev, dtype=torch.bfloat16, zero=True)
+                for e, n in enumerate(EXPERT_ORDER):
+                    f = feats[n].detach().to(f32).contiguous()
+                    self._call(lib.ffsr_nchw_to_nhwc_bf16, f.data_ptr(), B, cin_exp[n], H * W,
+                               fbuf.data_ptr() + e * H * W * cs * 2, 4 * H * W * cs, cs, S)
+                self.conv(nhwc(fbuf.view(B * 4, H, W, cs)), B * 4, H, W, cmax, "co.align.all", 128, 1,
+                          nhwc(tokens.view(B * 4, H, W, 128)), groups=4)
+            else:
+                if len(have) < 4:
+                    tokens.zero_()                              # missing expert -> zero token (:378-381)
+                for e, n in enumerate(EXPERT_ORDER):
+                    if n not in feats:
+                        continue
+                    f = feats[n].detach().to(f32).contiguous()
+                    cin_w = cin_exp[n]
+                    cin = min(f.shape[1], cin_w)               # truncate / implicit zero-pad (:349-358)
+                    wn = "co.align." + n
+                    if cin != cin_w:
+                        wn2 = wn + ".c%d" % cin
+                        if wn2 not in w:
+                            w[wn2] = w[wn][:, :cin, :].contiguous()
+                            w[wn2 + ".b"] = w[wn + ".b"]
+                        wn = wn2
+                    tv = tokens[:, e]
+                    ov = _View(tv.data_ptr(), tokens.stride(0), tokens.stride(2), tokens.stride(3), 1, tokens)
+                    self.conv(nchw(f), B, H, W, cin, wn, 128, 1, ov)
             N4 = B * 4
             tok4 = tokens.view(N4, H, W, 128)
             rows = N4 * H * W
@@ -526,33 +547,49 @@ class FusionEngine:
         down2 = self._buf("ee.down2", (B, H, W, 4), dev, zero=True)
         lap0 = self._buf("ee.lap0", (B, Hh, Wh, 4), dev, zero=True)
         lap1 = self._buf("ee.lap1", (B, 2 * H, 2 * W, 4), dev, zero=True)
-        self._call(lib.ffsr_blur_pool, cat6.data_ptr(), 8, B, Hh, Wh, g25, down1.data_ptr(), 4, S)
-        self._call(lib.ffsr_laplacian_sub, cat6.data_ptr(), 8, down1.data_ptr(), 4, B, Hh, Wh, lap0.data_ptr(), 4, S)
-        self._call(lib.ffsr_blur_pool, down1.data_ptr(), 4, B, 2 * H, 2 * W, g25, down2.data_ptr(), 4, S)
-        self._call(lib.ffsr_laplacian_sub, down1.data_ptr(), 4, down2.data_ptr(), 4, B, 2 * H, 2 * W, lap1.data_ptr(), 4, S)
+        bf = torch.bfloat16
+        lap0_lp = self._buf("ee.lap0_lp", (B, Hh, Wh, 8), dev, dtype=bf, zero=True) if lp else None
+        lap1_lp = self._buf("ee.lap1_lp", (B, 2 * H, 2 * W, 8), dev, dtype=bf, zero=True) if lp else None
+        down2_lp = self._buf("ee.down2_lp", (B, H, W, 8), dev, dtype=bf, zero=True) if lp else None
+
+        def ptr(t):
+            return t.data_ptr() if t is not None else None
+
+        self._call(lib.ffsr_blur_pool, cat6.data_ptr(), 8, B, Hh, Wh, g25, down1.data_ptr(), 4, None, 0, S)
+        self._call(lib.ffsr_laplacian_sub, cat6.data_ptr(), 8, down1.data_ptr(), 4, B, Hh, Wh, lap0.data_ptr(), 4,
+                   ptr(lap0_lp), 8, S)
+        self._call(lib.ffsr_blur_pool, down1.data_ptr(), 4, B, 2 * H, 2 * W, g25, down2.data_ptr(), 4, ptr(down2_lp), 8, S)
+        self._call(lib.ffsr_laplacian_sub, down1.data_ptr(), 4, down2.data_ptr(), 4, B, 2 * H, 2 * W, lap1.data_ptr(), 4,
+                   ptr(lap1_lp), 8, S)
         cat96 = self._buf("ee.cat96", (B, Hh, Wh, 96), dev, dtype=adt)
-        for lv, (lap, h, wd) in enumerate(((lap0, Hh, Wh), (lap1, 2 * H, 2 * W), (down2, H, W))):
+        levels = ((lap0, lap0_lp, Hh, Wh), (lap1, lap1_lp, 2 * H, 2 * W), (down2, down2_lp, H, W))
+        for lv, (lap, lap_lp, h, wd) in enumerate(levels):
             nm = f"ee{lv}"
+            src = lap_lp if lp else lap                       # bf16 mode: every refiner conv is a tcgen05 launch
             idt = self._buf(nm + ".idt", (B, h, wd, 32), dev)
             o1 = self._buf(nm + ".o1", (B, h, wd, 32), dev, dtype=adt)
             o2 = self._buf(nm + ".o2", (B, h, wd, 32), dev, dtype=adt)
-            o3 = self._buf(nm + ".o3", (B, h, wd, 32), dev) if lp else o1      # refiner output stays fp32
-            t8 = self._buf(nm + ".t8", (B, h, wd, 8), dev)
+            o3 = self._buf(nm + ".o3", (B, h, wd, 32), dev, dtype=adt) if lp else o1
+            t8 = self._buf(nm + ".t8", (B, h, wd, 8), dev, dtype=adt)
             at = self._buf(nm + ".at", (B, h, wd, 1), dev)
-            self.conv(nhwc(lap), B, h, wd, 3, f"ee.{lv}.proj", 32, 1, nhwc(idt))
-            self.conv(nhwc(lap), B, h, wd, 3, f"ee.{lv}.c1", 32, 3, nhwc(o1), act=K.ACT_GELU)
+            self.conv(nhwc(src), B, h, wd, 3, f"ee.{lv}.proj", 32, 1, nhwc(idt))
+            self.conv(nhwc(src), B, h, wd, 3, f"ee.{lv}.c1", 32, 3, nhwc(o1), act=K.ACT_GELU)
             self.conv(nhwc(o1), B, h, wd, 32, f"ee.{lv}.c2", 32, 3, nhwc(o2), act=K.ACT_GELU)
             self.conv(nhwc(o2), B, h, wd, 32, f"ee.{lv}.c3", 32, 3, nhwc(o3), epi=K.EPI_RESIDUAL, r1=nhwc(idt))
             self.conv(nhwc(o3), B, h, wd, 32, f"ee.{lv}.a0", 8, 1, nhwc(t8), act=K.ACT_GELU)
             self.conv(nhwc(t8), B, h, wd, 8, f"ee.{lv}.a2", 1, 3, nhwc(at), act=K.ACT_SIGMOID)
-            self._call(lib.ffsr_edge_attn_upsample, o3.data_ptr(), at.data_ptr(), B, h, wd, 32,
+            self._call(lib.ffsr_edge_attn_upsample, o3.data_ptr(), ADT, at.data_ptr(), B, h, wd, 32,
                        pp("edge_enhance.level_weights"), lv, cat96.data_ptr() + 32 * lv * esz, Hh, Wh, 96, ADT, S)
         e32 = self._buf("ee.e32", (B, Hh, Wh, 32), dev, dtype=adt)
         self.conv(nhwc(cat96), B, Hh, Wh, 96, "ee.f0", 32, 3, nhwc(e32), act=K.ACT_GELU)
         self.conv(nhwc(e32), B, Hh, Wh, 32, "ee.f2", 3, 3, nhwc(cat6, 3))
-        g16 = self._buf("ee.g16", (B, Hh, Wh, 16), dev)
+        g16 = self._buf("ee.g16", (B, Hh, Wh, 16), dev, dtype=adt)
         egate = self._buf("ee.gate", (B, Hh, Wh, 1), dev)
-        self.conv(nhwc(cat6), B, Hh, Wh, 6, "ee.g0", 16, 3, nhwc(g16), act=K.ACT_GELU)
+        gin = cat6
+        if lp:
+            gin = self._buf("cat6_lp", (B, Hh, Wh, 8), dev, dtype=bf, zero=True)
+            self._call(lib.ffsr_cast_f32_to_bf16, cat6.data_ptr(), gin.data_ptr(), cat6.numel(), S)
+        self.conv(nhwc(gin), B, Hh, Wh, 6, "ee.g0", 16, 3, nhwc(g16), act=K.ACT_GELU)
         self.conv(nhwc(g16), B, Hh, Wh, 16, "ee.g2", 1, 3, nhwc(egate), act=K.ACT_SIGMOID)
 
         # ---------------- output ----------------

@@ -164,19 +164,27 @@ int ffsr_blend_hr(const float* hier, long long hier_sX, const float* ecol, const
                   int B, int H, int W, float* fused_before, float* fused_nhwc, long long fused_sX, void* fused_lp,
                   long long fused_lp_sX, cudaStream_t stream);
 /* Laplacian pyramid pieces   src/models/edge_enhancement.py:196-220 */
+/* the optional *_lp outputs are bf16 channels-last copies (tcgen05 operands of the edge refiners) */
 int ffsr_blur_pool(const float* x, long long x_sX, int N, int H, int W, const float* gauss25, float* down,
-                   long long down_sX, cudaStream_t stream);
+                   long long down_sX, void* down_lp, long long down_lp_sX, cudaStream_t stream);
 int ffsr_laplacian_sub(const float* x, long long x_sX, const float* down, long long down_sX, int N, int H, int W,
-                       float* lap, long long lap_sX, cudaStream_t stream);
+                       float* lap, long long lap_sX, void* lap_lp, long long lap_lp_sX, cudaStream_t stream);
 /* refiner tail: (o * attn) [bilinear to HxW] * softmax(level_weights)[level] -> concat slice
  * src/models/edge_enhancement.py:118, 243-250 */
-int ffsr_edge_attn_upsample(const float* o, const float* attn, int N, int h, int w, int C, const float* level_w,
-                            int level, void* dst, int H, int W, long long dst_sX, int dtype, cudaStream_t stream);
+int ffsr_edge_attn_upsample(const void* o, int o_dtype, const float* attn, int N, int h, int w, int C,
+                            const float* level_w, int level, void* dst, int H, int W, long long dst_sX, int dtype,
+                            cudaStream_t stream);
 /* out = clamp(x + gate*strength*edge, 0, 1) + residual_scale*bilinear_x4(lr) [clamp in eval]
  * src/models/edge_enhancement.py:259-260, src/models/enhanced_fusion_v2.py:788-795 */
 int ffsr_final_combine(const float* xe, long long xe_sX, const float* gate, const float* strength, const float* lr,
                        const float* residual_scale, int B, int H, int W, int clamp01, float* out,
                        cudaStream_t stream);
+
+/* layout/precision staging for the tcgen05 path: fp32 NCHW -> bf16 channels-last slice
+ * (expert features, cached_dataset.py layout -> align_layers operand), contiguous fp32 -> bf16 */
+int ffsr_nchw_to_nhwc_bf16(const float* src, int N, int C, long HW, void* dst, long long dst_sN, long long dst_sX,
+                           cudaStream_t stream);
+int ffsr_cast_f32_to_bf16(const float* src, void* dst, long n, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -92,7 +92,8 @@ def test_orchestration_dry_run(with_feats, want_inter, precision):
     out, inter = eng._forward(lr, imgs, feats, B, H, W, want_inter)
     assert out.shape == (B, 3, 4 * H, 4 * W)
     calls = eng.lib.calls
-    assert calls.count("ffsr_conv2d") == (63 if with_feats else 51), calls.count("ffsr_conv2d")
+    expect = (63 if with_feats else 51) - (3 if precision == "bf16" else 0)   # bf16: one grouped align conv
+    assert calls.count("ffsr_conv2d") == expect, calls.count("ffsr_conv2d")
     assert ("ffsr_token_attention" in calls) == with_feats
     assert calls[-1] == "ffsr_final_combine"
     if want_inter:
