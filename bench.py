@@ -169,12 +169,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from isr_b200.dist import max_over_ranks as _mor
+
     def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
+        return _mor(ms, dev)
 
     for _ in range(warmup):
         sr = m.forward_with_precomputed(lrd, imd, ftd)

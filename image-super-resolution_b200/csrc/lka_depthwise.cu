@@ -10,8 +10,8 @@
 #include "common.cuh"
 
 namespace {
-constexpr int R5 = 4;    // outputs per thread along W for the 5x5
-constexpr int R21 = 8;   // outputs per thread along the conv axis for the 21-tap passes
+constexpr int R5 = 4;    // 4x4 output patch per thread for the 5x5 (8x8 input window in registers)
+constexpr int R21 = 16;  // outputs per thread along the conv axis for the 21-tap passes
 }
 
 // BN is folded to y = x*k + d (eval: running stats; train: batch stats computed upstream).
@@ -19,23 +19,25 @@ __global__ void __launch_bounds__(256) k_lka_dw5(const float* __restrict__ x, in
                                                  const float* __restrict__ bn_k, const float* __restrict__ bn_d,
                                                  const float* __restrict__ w5, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int runs = (W + R5 - 1) / R5;
-  const int idx = blockIdx.y * blockDim.y + threadIdx.y;      // over H * runs
-  const int y = idx / runs, x0 = (idx % runs) * R5;
+  const int runs_x = (W + R5 - 1) / R5, runs_y = (H + R5 - 1) / R5;
+  const int idx = blockIdx.y * blockDim.y + threadIdx.y;      // over runs_y * runs_x
+  const int y0 = (idx / runs_x) * R5, x0 = (idx % runs_x) * R5;
   const int n = blockIdx.z;
-  if (c >= C || y >= H) return;
+  if (c >= C || idx >= runs_y * runs_x) return;
   float w[25];
 #pragma unroll
   for (int i = 0; i < 25; ++i) w[i] = w5[c * 25 + i];
   const float k = bn_k[c], d = bn_d[c];
-  float acc[R5];
+  float acc[R5][R5];
 #pragma unroll
-  for (int r = 0; r < R5; ++r) acc[r] = 0.f;
+  for (int a = 0; a < R5; ++a)
+#pragma unroll
+    for (int b = 0; b < R5; ++b) acc[a][b] = 0.f;
   const float* img = x + (long)n * H * W * C;
 #pragma unroll
-  for (int dy = 0; dy < 5; ++dy) {
-    const int yy = y + dy - 2;
-    if (yy < 0 || yy >= H) continue;
+  for (int iy = 0; iy < R5 + 4; ++iy) {
+    const int yy = y0 + iy - 2;
+    if (yy < 0 || yy >= H) continue;                        // zero padding of n = BN1(x)
     float v[R5 + 4];
 #pragma unroll
     for (int i = 0; i < R5 + 4; ++i) {
@@ -43,13 +45,20 @@ __global__ void __launch_bounds__(256) k_lka_dw5(const float* __restrict__ x, in
       v[i] = (xx >= 0 && xx < W) ? fmaf(img[((long)yy * W + xx) * C + c], k, d) : 0.f;
     }
 #pragma unroll
-    for (int r = 0; r < R5; ++r)
+    for (int a = 0; a < R5; ++a) {
+      const int dy = iy - a;                                // tap row that maps input row iy to output row a
+      if (dy < 0 || dy > 4) continue;
 #pragma unroll
-      for (int dx = 0; dx < 5; ++dx) acc[r] = fmaf(w[dy * 5 + dx], v[r + dx], acc[r]);
+      for (int b = 0; b < R5; ++b)
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) acc[a][b] = fmaf(w[dy * 5 + dx], v[b + dx], acc[a][b]);
+    }
   }
 #pragma unroll
-  for (int r = 0; r < R5; ++r)
-    if (x0 + r < W) out[(((long)n * H + y) * W + x0 + r) * C + c] = acc[r];
+  for (int a = 0; a < R5; ++a)
+#pragma unroll
+    for (int b = 0; b < R5; ++b)
+      if (y0 + a < H && x0 + b < W) out[(((long)n * H + y0 + a) * W + x0 + b) * C + c] = acc[a][b];
 }
 
 // AXIS = 0: taps along W (1x21); AXIS = 1: taps along H (21x1)
@@ -112,7 +121,7 @@ extern "C" int ffsr_lka_depthwise(const float* x, int N, int H, int W, int C, co
   const int ty = 256 / cx;
   {
     dim3 block(cx, ty);
-    dim3 grid(C / cx, ceil_div((long)H * ceil_div(W, R5), ty), N);
+    dim3 grid(C / cx, ceil_div((long)ceil_div(H, R5) * ceil_div(W, R5), ty), N);
     k_lka_dw5<<<grid, block, 0, stream>>>(x, H, W, C, bn_k, bn_d, w5, tmp1);
     int rc = ffsr_check_launch("lka_dw5");
     if (rc) return rc;

@@ -288,6 +288,45 @@ extern "C" int ffsr_layernorm(const float* x, long rows, int E, const float* w, 
 // One thread per (b, pixel, query token, head); heads vary fastest so a warp reads
 // contiguous 64-byte head slices.
 // ------------------------------------------------------------------------------------
+template <typename TI>
+__device__ __forceinline__ void load16(const TI* p, float (&o)[16]);
+template <>
+__device__ __forceinline__ void load16<float>(const float* p, float (&o)[16]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 v = reinterpret_cast<const float4*>(p)[k];
+    o[4 * k] = v.x; o[4 * k + 1] = v.y; o[4 * k + 2] = v.z; o[4 * k + 3] = v.w;
+  }
+}
+template <>
+__device__ __forceinline__ void load16<__nv_bfloat16>(const __nv_bfloat16* p, float (&o)[16]) {
+  const uint4 u0 = reinterpret_cast<const uint4*>(p)[0], u1 = reinterpret_cast<const uint4*>(p)[1];
+  const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+    o[2 * k] = f2.x; o[2 * k + 1] = f2.y;
+  }
+}
+template <typename TO>
+__device__ __forceinline__ void store16(TO* p, const float (&o)[16]);
+template <>
+__device__ __forceinline__ void store16<float>(float* p, const float (&o)[16]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) reinterpret_cast<float4*>(p)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+}
+template <>
+__device__ __forceinline__ void store16<__nv_bfloat16>(__nv_bfloat16* p, const float (&o)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+    w[k] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 template <typename TI, typename TO, int T>
 __global__ void k_token_attention(const TI* __restrict__ qkv, int B, long HW, int E, TO* __restrict__ ctx) {
   const int heads = E / 16;
@@ -302,16 +341,16 @@ __global__ void k_token_attention(const TI* __restrict__ qkv, int B, long HW, in
   const long tstride = HW * 3 * E;                       // between tokens of one pixel
   const TI* base = qkv + ((long)b * T * HW + p) * 3 * E + h * 16;
   float q[16];
-#pragma unroll
-  for (int d = 0; d < 16; ++d) q[d] = to_f32<TI>(base[qt * tstride + d]);
+  load16<TI>(base + qt * tstride, q);
   float sc[T];
   float mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < T; ++j) {
-    const TI* k = base + j * tstride + E;
+    float kk[16];
+    load16<TI>(base + j * tstride + E, kk);
     float a = 0.f;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) a = fmaf(q[d], to_f32<TI>(k[d]), a);
+    for (int d = 0; d < 16; ++d) a = fmaf(q[d], kk[d], a);
     sc[j] = a * 0.25f;
     mx = fmaxf(mx, sc[j]);
   }
@@ -324,20 +363,20 @@ __global__ void k_token_attention(const TI* __restrict__ qkv, int B, long HW, in
   for (int d = 0; d < 16; ++d) o[d] = 0.f;
 #pragma unroll
   for (int j = 0; j < T; ++j) {
-    const TI* v = base + j * tstride + 2 * E;
+    float vv[16];
+    load16<TI>(base + j * tstride + 2 * E, vv);
     const float pj = sc[j] * inv;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) o[d] = fmaf(pj, to_f32<TI>(v[d]), o[d]);
+    for (int d = 0; d < 16; ++d) o[d] = fmaf(pj, vv[d], o[d]);
   }
-  TO* dst = ctx + (((long)b * T + qt) * HW + p) * E + h * 16;
-#pragma unroll
-  for (int d = 0; d < 16; ++d) dst[d] = from_f32<TO>(o[d]);
+  store16<TO>(ctx + (((long)b * T + qt) * HW + p) * E + h * 16, o);
 }
 
 extern "C" int ffsr_token_attention(const void* qkv, int B, int T, long HW, int E, void* ctx, int is_bf16,
                                     cudaStream_t stream) {
   FFSR_REQUIRE(qkv && ctx, FFSR_ERR_ARG, "token_attention: null pointer");
   FFSR_REQUIRE(T == 4 && E % 16 == 0 && B > 0 && HW > 0, FFSR_ERR_ARG, "token_attention: built for T=4 tokens, E%%16==0");
+  FFSR_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)ctx % 16) == 0, FFSR_ERR_ALIGN, "token_attention: 16B alignment");
   const long n = (long)B * HW * T * (E / 16);
   if (is_bf16)
     k_token_attention<__nv_bfloat16, __nv_bfloat16, 4><<<ceil_div(n, 128), 128, 0, stream>>>(

@@ -1,0 +1,54 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: round-robin image sharding with no
+data-path collective, max-over-ranks timing, sum of processed units."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n_items, out):
+    sys.path.insert(0, ROOT)
+    import isr_b200  # noqa: F401
+    from isr_b200 import dist as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = D.shard_indices(n_items, rank, world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    t = D.max_over_ranks(10.0 + rank)             # pretend rank r took 10+r ms
+    total = D.sum_over_ranks(float(len(mine)))
+    if rank == 0:
+        out.put((gathered, t, total))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_round_robin_sharding_and_timing_reduction_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_items, world = 101, 2
+    procs = [ctx.Process(target=_worker, args=(r, world, 29641, n_items, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered, t, total = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(i for g in gathered for i in g) == list(range(n_items))     # every image exactly once
+    assert gathered[0] == list(range(0, n_items, 2)) and gathered[1] == list(range(1, n_items, 2))
+    assert abs(len(gathered[0]) - len(gathered[1])) <= 1                      # balanced to one unit
+    assert t == 11.0 and total == float(n_items)
+
+
+def test_shard_edge_cases():
+    sys.path.insert(0, ROOT)
+    import isr_b200  # noqa: F401
+    from isr_b200 import dist as D
+    assert D.shard_indices(0, 0, 4) == []
+    assert D.shard_indices(3, 3, 8) == []                                     # more ranks than images
+    assert D.shard(list("abcde"), 1, 2) == ["b", "d"]
+    assert D.max_over_ranks(3.5) == 3.5                                       # no process group: identity
