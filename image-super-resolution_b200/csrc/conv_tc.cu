@@ -12,7 +12,10 @@
 //               descriptor stays 1024-byte aligned.  Out-of-image coordinates (the conv halo) and
 //               channels >= Cin are zero-filled by the TMA unit: padding costs no instructions.
 //   B operand : weights pre-packed [group][dy][dx][CoutPad][CinPad] bf16 (K-major); one 5-D TMA
-//               load {64, N, 1, ks, 1} brings the ks taps (all dy) of this dx.
+//               load {64, N, 1, ks, 1} brings the ks taps (all dy) of this dx.  When the whole
+//               weight set of a cout block fits beside >= 3 A stages (every layer except
+//               128->128 3x3) it is loaded ONCE per CTA and stays resident: the per-tile TMA
+//               work (the measured limiter: ~4 cycles per 128-byte row per SM) is then A only.
 //   MMA       : tcgen05.mma.cta_group::1.kind::f16, M=128, N=nblk, K=16, issued by one thread;
 //               accumulators double-buffered in TMEM (2 x 128 columns) so the epilogue of
 //               tile i overlaps the MMAs of tile i+1.
@@ -46,6 +49,8 @@ struct TcArgs {
   int ksteps_last;   // K=16 steps issued for the last chunk
   int a_bytes, b_bytes, stage_bytes, nstages;
   int acc_slot, nacc; // TMEM columns per accumulator (32/64/128) and ring depth
+  int b_resident;     // weights of one (group, cout block) stay in smem across tiles
+  int bres_bytes;     // bytes of that resident set (0 when streaming)
   int groups;
   int tiles_x, tiles_y;
   long long total_tiles;
@@ -227,7 +232,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* tfull = bars + 2 * TC_MAX_STAGES;                  // [TC_MAX_ACC]
   uint64_t* tempty = bars + 2 * TC_MAX_STAGES + TC_MAX_ACC;    // [TC_MAX_ACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 2 * TC_MAX_ACC);
-  uint8_t* stages = smem + TC_SMEM_HDR;
+  uint64_t* bfull = bars + 2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1;   // resident-weights barrier
+  uint8_t* bres = smem + TC_SMEM_HDR;                                // resident weights (may be empty)
+  uint8_t* stages = bres + a.bres_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -236,6 +243,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < TC_MAX_ACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
+    mbar_init(bfull, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -249,27 +257,41 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   const int pad = a.ks / 2;
   const int kiters = a.ks * a.nchunks;               // one pipeline stage per (chunk, dx)
-  const uint32_t stage_tx = (uint32_t)(a.a_bytes + a.b_bytes);
+  const uint32_t stage_tx = (uint32_t)(a.a_bytes + (a.b_resident ? 0 : a.b_bytes));
 
   if (warp == 0) {
     // ================================ TMA producer ======================================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      int cur_g = -1, cur_nb = -1, last_s = 0;
+      uint32_t last_ph = 0;
+      bool have_last = false;
       for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
         long long r = t;
-        const int nb = (int)(r % a.n_nblocks); r /= a.n_nblocks;
         const int tx = (int)(r % a.tiles_x); r /= a.tiles_x;
         const int ty = (int)(r % a.tiles_y); r /= a.tiles_y;
-        const int n = (int)r;
+        const int n = (int)(r % a.N); r /= a.N;
+        const int nb = (int)r;                              // cout block varies slowest: resident weights change rarely
         const int g = n % a.groups;
+        if (a.b_resident && (g != cur_g || nb != cur_nb)) {
+          // new weight set: every MMA that reads the old one must have retired first
+          if (have_last) mbar_wait(&empty[last_s], last_ph);
+          mbar_expect_tx(bfull, (uint32_t)a.bres_bytes);
+          for (int ch = 0; ch < a.nchunks; ++ch)
+            for (int dxi = 0; dxi < a.ks; ++dxi)
+              tma_load_5d(bres + (ch * a.ks + dxi) * a.b_bytes, &tmB, bfull, ch * 64, nb * a.nblk, dxi, 0, g);
+          cur_g = g;
+          cur_nb = nb;
+        }
         for (int ch = 0; ch < a.nchunks; ++ch) {
           for (int dxi = 0; dxi < a.ks; ++dxi) {
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sa_ = stages + s * a.stage_bytes;
             mbar_expect_tx(&full[s], stage_tx);
             tma_load_4d(sa_, &tmA, &full[s], ch * 64, tx * TC_TW + dxi - pad, ty * TC_TH - pad, n);
-            tma_load_5d(sa_ + a.a_bytes, &tmB, &full[s], ch * 64, nb * a.nblk, dxi, 0, g);
+            if (!a.b_resident) tma_load_5d(sa_ + a.a_bytes, &tmB, &full[s], ch * 64, nb * a.nblk, dxi, 0, g);
+            last_s = s; last_ph = ph; have_last = true;
             if (++s == a.nstages) { s = 0; ph ^= 1; }
           }
         }
@@ -282,7 +304,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint32_t ph = 0;
     int as = 0;
     uint32_t aph = 0;
+    int cur_g = -1, cur_nb = -1;
+    uint32_t bph = 0;
     for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      if (a.b_resident) {
+        const long long per_nb = (long long)a.tiles_x * a.tiles_y * a.N;
+        const int nb = (int)(t / per_nb);
+        const int g = (int)((t / ((long long)a.tiles_x * a.tiles_y)) % a.N) % a.groups;
+        if (g != cur_g || nb != cur_nb) {
+          mbar_wait(bfull, bph);
+          bph ^= 1;
+          cur_g = g;
+          cur_nb = nb;
+        }
+      }
       mbar_wait(&tempty[as], aph ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * a.acc_slot);
@@ -292,11 +327,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(stages + s * a.stage_bytes);
           const int ch = it / a.ks;
+          // weights: streamed next to the A copy, or the resident slice of this (chunk, dx)
+          const uint32_t b_addr = a.b_resident ? smem_u32(bres + it * a.b_bytes) : a_addr + (uint32_t)a.a_bytes;
           const int ksteps = (ch == a.nchunks - 1) ? a.ksteps_last : 4;
           for (int dyi = 0; dyi < a.ks; ++dyi) {
             // tap (dyi, dx of this stage): rows dyi..dyi+7 of the haloed copy, dy-th weight slice
             const uint64_t da = make_sw128_desc(a_addr + (uint32_t)(dyi * TC_ROW_BYTES));
-            const uint64_t db = make_sw128_desc(a_addr + (uint32_t)a.a_bytes + (uint32_t)(dyi * a.nblk * 128));
+            const uint64_t db = make_sw128_desc(b_addr + (uint32_t)(dyi * a.nblk * 128));
             for (int k = 0; k < ksteps; ++k)
               umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || dyi > 0 || k > 0) ? 1u : 0u);
           }
@@ -321,10 +358,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint32_t aph = 0;
     for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       long long r = t;
-      const int nb = (int)(r % a.n_nblocks); r /= a.n_nblocks;
       const int tx = (int)(r % a.tiles_x); r /= a.tiles_x;
       const int ty = (int)(r % a.tiles_y); r /= a.tiles_y;
-      const int n = (int)r;
+      const int n = (int)(r % a.N); r /= a.N;
+      const int nb = (int)r;
       const int g = n % a.groups;
       const int y = ty * TC_TH + py, x = tx * TC_TW + px;
       const bool inside = (y < a.H) && (x < a.W);
@@ -520,10 +557,14 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   a.ksteps_last = (last + 15) / 16;
   a.a_bytes = (TC_TH + 2 * (p.ksize / 2)) * TC_ROW_BYTES;
   a.b_bytes = p.ksize * nblk * 128;
-  a.stage_bytes = a.a_bytes + a.b_bytes;
-  a.nstages = (TC_SMEM_MAX - 1024 - TC_SMEM_HDR) / a.stage_bytes;
+  const int smem_avail = TC_SMEM_MAX - 1024 - TC_SMEM_HDR;
+  const int b_all = a.nchunks * p.ksize * a.b_bytes;          // all taps, all K chunks of one cout block
+  a.b_resident = (b_all + 3 * a.a_bytes <= smem_avail) ? 1 : 0;
+  a.bres_bytes = a.b_resident ? b_all : 0;
+  a.stage_bytes = a.a_bytes + (a.b_resident ? 0 : a.b_bytes);
+  a.nstages = (smem_avail - a.bres_bytes) / a.stage_bytes;
   if (a.nstages > TC_MAX_STAGES) a.nstages = TC_MAX_STAGES;
-  const int smem_bytes = 1024 + TC_SMEM_HDR + a.nstages * a.stage_bytes;
+  const int smem_bytes = 1024 + TC_SMEM_HDR + a.bres_bytes + a.nstages * a.stage_bytes;
   a.acc_slot = nblk <= 32 ? 32 : (nblk <= 64 ? 64 : 128);
   a.nacc = TC_TMEM_COLS / a.acc_slot;
   if (a.nacc > TC_MAX_ACC) a.nacc = TC_MAX_ACC;
