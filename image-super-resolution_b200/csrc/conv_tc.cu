@@ -78,8 +78,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+// "_e" variants: executed by a whole converged warp, one elected lane acts (see umma_bf16)
+__device__ __forceinline__ void mbar_expect_tx_e(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(bytes)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -103,23 +110,22 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t"
+      "}" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t"
+      "}" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
@@ -129,30 +135,76 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major: 1) | SBO>>4 [32,46) = 1024B
-// (8 rows x 128B atom) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
+// (8 rows x 128B atom) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64);
+// see desc_lo() / TC_DESC_HI below.
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+// Issued by the whole (converged) MMA warp: elect.sync picks one lane inside the asm block, so
+// there is no divergent branch around the tensor-core instruction (a divergent guard makes the
+// compiler wrap every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, and the single
+// issuing thread -- not the tensor pipe -- becomes the limiter).  The two 64-bit shared-memory
+// descriptors are assembled from 32-bit halves in PTX: the high half (SBO, version, swizzle)
+// is a constant, only the 14-bit start address in the low half moves.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                          uint32_t accum) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
       "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(desc_hi)
+      : "memory");
+}
+// Four K=16 steps of one (tap, 64-channel chunk) in ONE asm block: the descriptor increments
+// (+32 B = +2 in 16-byte units) are done in PTX so that the operands cross to the uniform
+// datapath once per block instead of once per MMA.
+__device__ __forceinline__ void umma_bf16_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t accum_first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e, t;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 al, bl;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "add.u32 al, %1, 2;\n\t"
+      "add.u32 bl, %2, 2;\n\t"
+      "mov.b64 da, {al, %5};\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "add.u32 al, %1, 4;\n\t"
+      "add.u32 bl, %2, 4;\n\t"
+      "mov.b64 da, {al, %5};\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "add.u32 al, %1, 6;\n\t"
+      "add.u32 bl, %2, 6;\n\t"
+      "mov.b64 da, {al, %5};\n\t"
+      "mov.b64 db, {bl, %5};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, t;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum_first), "r"(desc_hi)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
 }
+constexpr uint32_t TC_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024B | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -260,8 +312,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t stage_tx = (uint32_t)(a.a_bytes + (a.b_resident ? 0 : a.b_bytes));
 
   if (warp == 0) {
-    // ================================ TMA producer ======================================
-    if (lane == 0) {
+    // ================================ TMA producer (whole warp, converged) ===============
+    {
       int s = 0;
       uint32_t ph = 0;
       int cur_g = -1, cur_nb = -1, last_s = 0;
@@ -277,7 +329,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (a.b_resident && (g != cur_g || nb != cur_nb)) {
           // new weight set: every MMA that reads the old one must have retired first
           if (have_last) mbar_wait(&empty[last_s], last_ph);
-          mbar_expect_tx(bfull, (uint32_t)a.bres_bytes);
+          mbar_expect_tx_e(bfull, (uint32_t)a.bres_bytes);
           for (int ch = 0; ch < a.nchunks; ++ch)
             for (int dxi = 0; dxi < a.ks; ++dxi)
               tma_load_5d(bres + (ch * a.ks + dxi) * a.b_bytes, &tmB, bfull, ch * 64, nb * a.nblk, dxi, 0, g);
@@ -288,7 +340,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int dxi = 0; dxi < a.ks; ++dxi) {
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sa_ = stages + s * a.stage_bytes;
-            mbar_expect_tx(&full[s], stage_tx);
+            mbar_expect_tx_e(&full[s], stage_tx);
             tma_load_4d(sa_, &tmA, &full[s], ch * 64, tx * TC_TW + dxi - pad, ty * TC_TH - pad, n);
             if (!a.b_resident) tma_load_5d(sa_ + a.a_bytes, &tmB, &full[s], ch * 64, nb * a.nblk, dxi, 0, g);
             last_s = s; last_ph = ph; have_last = true;
@@ -324,23 +376,28 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t a_addr = smem_u32(stages + s * a.stage_bytes);
           const int ch = it / a.ks;
           // weights: streamed next to the A copy, or the resident slice of this (chunk, dx)
           const uint32_t b_addr = a.b_resident ? smem_u32(bres + it * a.b_bytes) : a_addr + (uint32_t)a.a_bytes;
           const int ksteps = (ch == a.nchunks - 1) ? a.ksteps_last : 4;
+          uint32_t al = desc_lo(a_addr), bl = desc_lo(b_addr);
+          const uint32_t b_step = (uint32_t)(a.nblk * 128) >> 4;
           for (int dyi = 0; dyi < a.ks; ++dyi) {
             // tap (dyi, dx of this stage): rows dyi..dyi+7 of the haloed copy, dy-th weight slice
-            const uint64_t da = make_sw128_desc(a_addr + (uint32_t)(dyi * TC_ROW_BYTES));
-            const uint64_t db = make_sw128_desc(b_addr + (uint32_t)(dyi * a.nblk * 128));
-            for (int k = 0; k < ksteps; ++k)
-              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || dyi > 0 || k > 0) ? 1u : 0u);
+            const uint32_t acc0 = (it > 0 || dyi > 0) ? 1u : 0u;
+            if (ksteps == 4) {
+              umma_bf16_x4(tmem_d, al, bl, TC_DESC_HI, idesc, acc0);
+            } else {
+              for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, al + 2u * k, bl + 2u * k, TC_DESC_HI, idesc, (acc0 || k > 0) ? 1u : 0u);
+            }
+            al += TC_ROW_BYTES >> 4;
+            bl += b_step;
           }
           umma_commit(&empty[s]);                       // smem slot reusable once these MMAs retire
           if (it == kiters - 1) umma_commit(&tfull[as]);  // accumulator complete
         }
-        __syncwarp();
         if (++s == a.nstages) { s = 0; ph ^= 1; }
       }
       if (++as == a.nacc) { as = 0; aph ^= 1; }
