@@ -203,6 +203,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
       "}" ::"r"(smem_u32(bar))
       : "memory");
 }
+#include "umma_blocks.inc"
 constexpr uint32_t TC_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024B | version 1 | SWIZZLE_128B
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -382,18 +383,24 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           // weights: streamed next to the A copy, or the resident slice of this (chunk, dx)
           const uint32_t b_addr = a.b_resident ? smem_u32(bres + it * a.b_bytes) : a_addr + (uint32_t)a.a_bytes;
           const int ksteps = (ch == a.nchunks - 1) ? a.ksteps_last : 4;
-          uint32_t al = desc_lo(a_addr), bl = desc_lo(b_addr);
+          const uint32_t al = desc_lo(a_addr), bl = desc_lo(b_addr);
           const uint32_t b_step = (uint32_t)(a.nblk * 128) >> 4;
-          for (int dyi = 0; dyi < a.ks; ++dyi) {
-            // tap (dyi, dx of this stage): rows dyi..dyi+7 of the haloed copy, dy-th weight slice
-            const uint32_t acc0 = (it > 0 || dyi > 0) ? 1u : 0u;
-            if (ksteps == 4) {
-              umma_bf16_x4(tmem_d, al, bl, TC_DESC_HI, idesc, acc0);
-            } else {
-              for (int k = 0; k < ksteps; ++k) umma_bf16(tmem_d, al + 2u * k, bl + 2u * k, TC_DESC_HI, idesc, (acc0 || k > 0) ? 1u : 0u);
+          const uint32_t acc0 = it > 0 ? 1u : 0u;
+          // every MMA of this stage (ks taps along dy x ksteps K-steps) in one PTX block
+          if (a.ks == 3) {
+            switch (ksteps) {
+              case 4: umma_stage_ks3_k4(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+              case 3: umma_stage_ks3_k3(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+              case 2: umma_stage_ks3_k2(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+              default: umma_stage_ks3_k1(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
             }
-            al += TC_ROW_BYTES >> 4;
-            bl += b_step;
+          } else {
+            switch (ksteps) {
+              case 4: umma_stage_ks1_k4(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+              case 3: umma_stage_ks1_k3(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+              case 2: umma_stage_ks1_k2(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+              default: umma_stage_ks1_k1(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+            }
           }
           umma_commit(&empty[s]);                       // smem slot reusable once these MMAs retire
           if (it == kiters - 1) umma_commit(&tfull[as]);  // accumulator complete
