@@ -274,6 +274,38 @@ __device__ __forceinline__ float load_res(const void* base, int is_bf16, long lo
                  : reinterpret_cast<const float*>(base)[off];
 }
 
+// Static round-robin tile walk without per-tile divisions: (tx, ty, n, nb) advance by the
+// decomposed grid stride with carries.  The issuing threads of the producer and MMA warps are
+// instruction-bound on small layers, so every instruction in their per-tile path counts.
+struct TileIter {
+  int tx, ty, n, nb;
+  int dtx, dty, dn, dnb;
+  long long t;
+  __device__ __forceinline__ void init(const TcArgs& a) {
+    unsigned r = blockIdx.x;
+    tx = r % a.tiles_x; r /= a.tiles_x;
+    ty = r % a.tiles_y; r /= a.tiles_y;
+    n = r % a.N; nb = r / a.N;
+    unsigned d = gridDim.x;
+    dtx = d % a.tiles_x; d /= a.tiles_x;
+    dty = d % a.tiles_y; d /= a.tiles_y;
+    dn = d % a.N; dnb = d / a.N;
+    t = blockIdx.x;
+  }
+  __device__ __forceinline__ bool valid(const TcArgs& a) const { return t < a.total_tiles; }
+  __device__ __forceinline__ void next(const TcArgs& a) {
+    t += gridDim.x;
+    tx += dtx;
+    int c = 0;
+    if (tx >= a.tiles_x) { tx -= a.tiles_x; c = 1; }
+    ty += dty + c; c = 0;
+    if (ty >= a.tiles_y) { ty -= a.tiles_y; c = 1; }
+    n += dn + c; c = 0;
+    if (n >= a.N) { n -= a.N; c = 1; }
+    nb += dnb + c;
+  }
+};
+
 // ---------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -320,13 +352,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       int cur_g = -1, cur_nb = -1, last_s = 0;
       uint32_t last_ph = 0;
       bool have_last = false;
-      for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-        long long r = t;
-        const int tx = (int)(r % a.tiles_x); r /= a.tiles_x;
-        const int ty = (int)(r % a.tiles_y); r /= a.tiles_y;
-        const int n = (int)(r % a.N); r /= a.N;
-        const int nb = (int)r;                              // cout block varies slowest: resident weights change rarely
-        const int g = n % a.groups;
+      TileIter ti;
+      for (ti.init(a); ti.valid(a); ti.next(a)) {
+        const int tx = ti.tx, ty = ti.ty, n = ti.n, nb = ti.nb;   // cout block varies slowest: resident weights change rarely
+        const int g = a.groups > 1 ? n % a.groups : 0;
         if (a.b_resident && (g != cur_g || nb != cur_nb)) {
           // new weight set: every MMA that reads the old one must have retired first
           if (have_last) mbar_wait(&empty[last_s], last_ph);
@@ -359,11 +388,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint32_t aph = 0;
     int cur_g = -1, cur_nb = -1;
     uint32_t bph = 0;
-    for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+    const uint32_t stages_u32 = smem_u32(stages), bres_u32 = smem_u32(bres);
+    const uint32_t b_step = (uint32_t)(a.nblk * 128) >> 4;
+    const int last_chunk_it = (a.nchunks - 1) * a.ks;        // stages of the last (possibly partial) K chunk
+    TileIter ti;
+    for (ti.init(a); ti.valid(a); ti.next(a)) {
       if (a.b_resident) {
-        const long long per_nb = (long long)a.tiles_x * a.tiles_y * a.N;
-        const int nb = (int)(t / per_nb);
-        const int g = (int)((t / ((long long)a.tiles_x * a.tiles_y)) % a.N) % a.groups;
+        const int nb = ti.nb;
+        const int g = a.groups > 1 ? ti.n % a.groups : 0;
         if (g != cur_g || nb != cur_nb) {
           mbar_wait(bfull, bph);
           bph ^= 1;
@@ -378,13 +410,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         mbar_wait(&full[s], ph);
         tc_fence_after();
         {
-          const uint32_t a_addr = smem_u32(stages + s * a.stage_bytes);
-          const int ch = it / a.ks;
+          const uint32_t a_addr = stages_u32 + (uint32_t)s * (uint32_t)a.stage_bytes;
           // weights: streamed next to the A copy, or the resident slice of this (chunk, dx)
-          const uint32_t b_addr = a.b_resident ? smem_u32(bres + it * a.b_bytes) : a_addr + (uint32_t)a.a_bytes;
-          const int ksteps = (ch == a.nchunks - 1) ? a.ksteps_last : 4;
+          const uint32_t b_addr = a.b_resident ? bres_u32 + (uint32_t)it * (uint32_t)a.b_bytes : a_addr + (uint32_t)a.a_bytes;
+          const int ksteps = (it >= last_chunk_it) ? a.ksteps_last : 4;
           const uint32_t al = desc_lo(a_addr), bl = desc_lo(b_addr);
-          const uint32_t b_step = (uint32_t)(a.nblk * 128) >> 4;
           const uint32_t acc0 = it > 0 ? 1u : 0u;
           // every MMA of this stage (ks taps along dy x ksteps K-steps) in one PTX block
           if (a.ks == 3) {
@@ -420,13 +450,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int mode = a.epi == FFSR_EPI_LKAGATE ? EM_LKAGATE : (a.epi == FFSR_EPI_RESIDUAL ? EM_RESIDUAL : a.act);
     int as = 0;
     uint32_t aph = 0;
-    for (long long t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-      long long r = t;
-      const int tx = (int)(r % a.tiles_x); r /= a.tiles_x;
-      const int ty = (int)(r % a.tiles_y); r /= a.tiles_y;
-      const int n = (int)(r % a.N); r /= a.N;
-      const int nb = (int)r;
-      const int g = n % a.groups;
+    TileIter ti;
+    for (ti.init(a); ti.valid(a); ti.next(a)) {
+      const int tx = ti.tx, ty = ti.ty, n = ti.n, nb = ti.nb;
+      const int g = a.groups > 1 ? n % a.groups : 0;
       const int y = ty * TC_TH + py, x = tx * TC_TW + px;
       const bool inside = (y < a.H) && (x < a.W);
       const long long opix = (long long)n * a.out_sN + (long long)y * a.out_sY + (long long)x * a.out_sX;
