@@ -450,8 +450,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int mode = a.epi == FFSR_EPI_LKAGATE ? EM_LKAGATE : (a.epi == FFSR_EPI_RESIDUAL ? EM_RESIDUAL : a.act);
     int as = 0;
     uint32_t aph = 0;
+    const int nch = a.nblk >> 4;                          // 16-column chunks of this layer (1..8)
+    int item0 = 0;                                        // (tile sequence * nch) mod 4: rotates the chunk->warp-group map
     TileIter ti;
-    for (ti.init(a); ti.valid(a); ti.next(a)) {
+    for (ti.init(a); ti.valid(a); ti.next(a), item0 = (item0 + nch) & 3) {
       const int tx = ti.tx, ty = ti.ty, n = ti.n, nb = ti.nb;
       const int g = a.groups > 1 ? n % a.groups : 0;
       const int y = ty * TC_TH + py, x = tx * TC_TW + px;
@@ -463,7 +465,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const bool has_r2 = inside && mode == EM_RESIDUAL && a.r2 != nullptr;
       bool waited = false;
       uint32_t taddr = 0;
-      for (int c0 = cgp * 16; c0 < a.nblk; c0 += 64) {
+      // chunk c of this tile belongs to warp group (item0 + c) & 3: with fewer than 4 chunks per
+      // tile (N <= 48) consecutive tiles go to different warp groups, so all 16 warps share the work
+      for (int c = (cgp - item0) & 3; c < nch; c += 4) {
+        const int c0 = c * 16;
         const int ocb = nb * a.nblk + c0;
         const int nvalid = min(16, a.Cout - ocb);        // may be <= 0 for padded columns
         float f[16], r1v[16], r2v[16];
