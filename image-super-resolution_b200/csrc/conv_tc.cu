@@ -306,6 +306,152 @@ struct TileIter {
   }
 };
 
+// 16 fp32 -> 16 bf16 (two 16-byte stores) or 16 fp32 (four 16-byte stores); masked scalar tail
+template <bool OUT_BF16>
+__device__ __forceinline__ void store16_out(void* out, long long off, const float (&f)[16], int nvalid) {
+  if (OUT_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + off;
+    if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      uint32_t w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+        w[k] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < nvalid) o[k] = __float2bfloat16_rn(f[k]);
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(out) + off;
+    if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) reinterpret_cast<float4*>(o)[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < nvalid) o[k] = f[k];
+    }
+  }
+}
+
+// Epilogue of one warp: TMEM lane quarter `warp & 3`, warp group (warp-2)>>2.  Chunk c (16
+// accumulator columns) of the q-th tile of this CTA belongs to warp group (q*nch + c) & 3, so
+// layers with fewer than four chunks per tile still spread over all 16 warps.
+template <int MODE, bool OUT_BF16>
+__device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
+                                              int warp, int lane) {
+  const int wq = warp & 3;
+  const int cgp = (warp - 2) >> 2;
+  const int row = wq * 32 + lane;                       // pixel within the tile
+  const int py = row / TC_TW, px = row % TC_TW;
+  const int nch = a.nblk >> 4;
+  const int Cout = a.Cout, nblk = a.nblk, nacc = a.nacc, acc_slot = a.acc_slot;
+  const float* __restrict__ bias = a.bias;
+  float sa = 1.f, sb = 1.f;
+  if (MODE == EM_RESIDUAL || MODE == EM_LKAGATE) {
+    sa = a.sa * (a.sa_ptr ? a.sa_ptr[0] : 1.0f);
+    sb = a.sb * (a.sb_ptr ? a.sb_ptr[0] : 1.0f);
+  }
+  int as = 0, item0 = 0;
+  uint32_t aph = 0;
+  TileIter ti;
+  for (ti.init(a); ti.valid(a); ti.next(a), item0 = (item0 + nch) & 3) {
+    const int n = ti.n;
+    const int g = a.groups > 1 ? n % a.groups : 0;
+    const int y = ti.ty * TC_TH + py, x = ti.tx * TC_TW + px;
+    const bool inside = (y < a.H) && (x < a.W);
+    const long long opix = (long long)n * a.out_sN + (long long)y * a.out_sY + (long long)x * a.out_sX;
+    long long r1pix = 0, r2pix = 0;
+    if (MODE == EM_RESIDUAL || MODE == EM_LKAGATE) r1pix = (long long)n * a.r1_sN + (long long)y * a.r1_sY + (long long)x * a.r1_sX;
+    if (MODE == EM_RESIDUAL) r2pix = (long long)n * a.r2_sN + (long long)y * a.r2_sY + (long long)x * a.r2_sX;
+    bool waited = false;
+    uint32_t taddr = 0;
+    for (int c = (cgp - item0) & 3; c < nch; c += 4) {
+      const int ocb = ti.nb * nblk + c * 16;
+      const int nvalid = min(16, Cout - ocb);            // may be <= 0 for padded columns
+      float f[16];
+      // operands that do not depend on the accumulator are fetched before waiting for it
+      if (bias != nullptr && nvalid > 0) {
+        const float* bp = bias + (long long)g * Cout + ocb;
+        if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(bp) + k);
+            f[4 * k] = v4.x; f[4 * k + 1] = v4.y; f[4 * k + 2] = v4.z; f[4 * k + 3] = v4.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] = (k < nvalid) ? __ldg(bp + k) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] = 0.f;
+      }
+      float r1v[(MODE == EM_RESIDUAL || MODE == EM_LKAGATE) ? 16 : 1];
+      float r2v[MODE == EM_RESIDUAL ? 16 : 1];
+      const bool has_r2 = MODE == EM_RESIDUAL && a.r2 != nullptr;
+      if (MODE == EM_RESIDUAL || MODE == EM_LKAGATE) {
+        if (inside && nvalid > 0) load_res16(a.r1, a.r1_bf16, r1pix + ocb, nvalid, reinterpret_cast<float(&)[16]>(r1v));
+      }
+      if (MODE == EM_RESIDUAL) {
+        if (inside && has_r2 && nvalid > 0) load_res16(a.r2, a.r2_bf16, r2pix + ocb, nvalid, reinterpret_cast<float(&)[16]>(r2v));
+      }
+      if (!waited) {
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+        taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * acc_slot);
+        waited = true;
+      }
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)(c * 16), v);
+      tmem_wait_ld(v);
+      if (inside && nvalid > 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] += __uint_as_float(v[k]);
+        if (MODE == EM_GELU) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] = gelu_fast(f[k]);
+        } else if (MODE == EM_RELU) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
+        } else if (MODE == EM_SIGMOID) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] = sigmoid_acc(f[k]);
+        } else if (MODE == EM_RESIDUAL) {
+          if (a.act != ACT_NONE) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = apply_act(f[k], a.act);
+          }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] = fmaf(sa, f[k], r1v[k % (sizeof(r1v) / 4)]);
+          if (has_r2) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = fmaf(sb, r2v[k % (sizeof(r2v) / 4)], f[k]);
+          }
+        } else if (MODE == EM_LKAGATE) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            if (k < nvalid) {
+              const float xr = r1v[k % (sizeof(r1v) / 4)];
+              f[k] = xr + sa * (fmaf(xr, __ldg(a.ch_k + ocb + k), __ldg(a.ch_d + ocb + k)) * sigmoid_acc(f[k]));
+            }
+          }
+        }
+        store16_out<OUT_BF16>(a.out, opix + ocb, f, nvalid);
+      }
+    }
+    if (!waited) mbar_wait(&tfull[as], aph);          // warps without a column chunk still pace the ring
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty[as]);
+    if (++as == nacc) { as = 0; aph ^= 1; }
+  }
+}
+
 // ---------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -441,136 +587,27 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else {
     // ================================ epilogue (warps 2..17) ============================
-    const int wq = warp & 3;                              // TMEM lane quarter this warp may read
-    const int cgp = (warp - 2) >> 2;                      // first 16-column chunk of this warp
-    const int row = wq * 32 + lane;                       // pixel within the tile
-    const int py = row / TC_TW, px = row % TC_TW;
-    const float sa = a.sa * (a.sa_ptr ? a.sa_ptr[0] : 1.0f);
-    const float sb = a.sb * (a.sb_ptr ? a.sb_ptr[0] : 1.0f);
     const int mode = a.epi == FFSR_EPI_LKAGATE ? EM_LKAGATE : (a.epi == FFSR_EPI_RESIDUAL ? EM_RESIDUAL : a.act);
-    int as = 0;
-    uint32_t aph = 0;
-    const int nch = a.nblk >> 4;                          // 16-column chunks of this layer (1..8)
-    int item0 = 0;                                        // (tile sequence * nch) mod 4: rotates the chunk->warp-group map
-    TileIter ti;
-    for (ti.init(a); ti.valid(a); ti.next(a), item0 = (item0 + nch) & 3) {
-      const int tx = ti.tx, ty = ti.ty, n = ti.n, nb = ti.nb;
-      const int g = a.groups > 1 ? n % a.groups : 0;
-      const int y = ty * TC_TH + py, x = tx * TC_TW + px;
-      const bool inside = (y < a.H) && (x < a.W);
-      const long long opix = (long long)n * a.out_sN + (long long)y * a.out_sY + (long long)x * a.out_sX;
-      const long long r1pix = (long long)n * a.r1_sN + (long long)y * a.r1_sY + (long long)x * a.r1_sX;
-      const long long r2pix = (long long)n * a.r2_sN + (long long)y * a.r2_sY + (long long)x * a.r2_sX;
-      const bool has_r1 = inside && (mode == EM_RESIDUAL || mode == EM_LKAGATE);
-      const bool has_r2 = inside && mode == EM_RESIDUAL && a.r2 != nullptr;
-      bool waited = false;
-      uint32_t taddr = 0;
-      // chunk c of this tile belongs to warp group (item0 + c) & 3: with fewer than 4 chunks per
-      // tile (N <= 48) consecutive tiles go to different warp groups, so all 16 warps share the work
-      for (int c = (cgp - item0) & 3; c < nch; c += 4) {
-        const int c0 = c * 16;
-        const int ocb = nb * a.nblk + c0;
-        const int nvalid = min(16, a.Cout - ocb);        // may be <= 0 for padded columns
-        float f[16], r1v[16], r2v[16];
-        // operands that do not depend on the accumulator are fetched before waiting for it
-        if (a.bias && nvalid > 0) {
-          const float* bp = a.bias + (long long)g * a.Cout + ocb;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) f[k] = (k < nvalid) ? __ldg(bp + k) : 0.f;
-        } else {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) f[k] = 0.f;
-        }
-        if (has_r1 && nvalid > 0) load_res16(a.r1, a.r1_bf16, r1pix + ocb, nvalid, r1v);
-        if (has_r2 && nvalid > 0) load_res16(a.r2, a.r2_bf16, r2pix + ocb, nvalid, r2v);
-        if (!waited) {
-          mbar_wait(&tfull[as], aph);
-          tc_fence_after();
-          taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * a.acc_slot);
-          waited = true;
-        }
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
-        tmem_wait_ld(v);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) f[k] += __uint_as_float(v[k]);
-        if (inside && nvalid > 0) {
-          switch (mode) {
-            case EM_GELU:
-#pragma unroll
-              for (int k = 0; k < 16; ++k) f[k] = gelu_fast(f[k]);
-              break;
-            case EM_RELU:
-#pragma unroll
-              for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
-              break;
-            case EM_SIGMOID:
-#pragma unroll
-              for (int k = 0; k < 16; ++k) f[k] = sigmoid_acc(f[k]);
-              break;
-            case EM_RESIDUAL:
-              if (a.act != ACT_NONE) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) f[k] = apply_act(f[k], a.act);
-              }
-#pragma unroll
-              for (int k = 0; k < 16; ++k) f[k] = fmaf(sa, f[k], r1v[k]);
-              if (has_r2) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) f[k] = fmaf(sb, r2v[k], f[k]);
-              }
-              break;
-            case EM_LKAGATE:
-#pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                if (k < nvalid) {
-                  const float xr = r1v[k];
-                  f[k] = xr + sa * (fmaf(xr, __ldg(a.ch_k + ocb + k), __ldg(a.ch_d + ocb + k)) * sigmoid_acc(f[k]));
-                }
-              }
-              break;
-            default:
-              break;
-          }
-          const bool full16 = (ocb + 16 <= a.Cout);
-          if (a.out_bf16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + opix + ocb;
-            if (full16 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-              uint4 u0, u1;
-              __nv_bfloat162 h;
-              h = __floats2bfloat162_rn(f[0], f[1]);   u0.x = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2bfloat162_rn(f[2], f[3]);   u0.y = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2bfloat162_rn(f[4], f[5]);   u0.z = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2bfloat162_rn(f[6], f[7]);   u0.w = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2bfloat162_rn(f[8], f[9]);   u1.x = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2bfloat162_rn(f[10], f[11]); u1.y = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2bfloat162_rn(f[12], f[13]); u1.z = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2bfloat162_rn(f[14], f[15]); u1.w = *reinterpret_cast<uint32_t*>(&h);
-              reinterpret_cast<uint4*>(o)[0] = u0;
-              reinterpret_cast<uint4*>(o)[1] = u1;
-            } else {
-#pragma unroll
-              for (int k = 0; k < 16; ++k)
-                if (ocb + k < a.Cout) o[k] = __float2bfloat16_rn(f[k]);
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(a.out) + opix + ocb;
-            if (full16 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-              for (int k = 0; k < 16; k += 4) reinterpret_cast<float4*>(o)[k >> 2] = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 16; ++k)
-                if (ocb + k < a.Cout) o[k] = f[k];
-            }
-          }
-        }
+    // one specialised loop per (epilogue mode, output type): no per-element switches, and the
+    // plain modes do not carry the residual registers
+    if (a.out_bf16) {
+      switch (mode) {
+        case EM_GELU: epilogue_loop<EM_GELU, true>(a, tfull, tempty, tmem_base, warp, lane); break;
+        case EM_RELU: epilogue_loop<EM_RELU, true>(a, tfull, tempty, tmem_base, warp, lane); break;
+        case EM_SIGMOID: epilogue_loop<EM_SIGMOID, true>(a, tfull, tempty, tmem_base, warp, lane); break;
+        case EM_RESIDUAL: epilogue_loop<EM_RESIDUAL, true>(a, tfull, tempty, tmem_base, warp, lane); break;
+        case EM_LKAGATE: epilogue_loop<EM_LKAGATE, true>(a, tfull, tempty, tmem_base, warp, lane); break;
+        default: epilogue_loop<EM_NONE, true>(a, tfull, tempty, tmem_base, warp, lane); break;
       }
-      if (!waited) mbar_wait(&tfull[as], aph);          // warps without a column chunk still pace the ring
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
-      if (++as == a.nacc) { as = 0; aph ^= 1; }
+    } else {
+      switch (mode) {
+        case EM_GELU: epilogue_loop<EM_GELU, false>(a, tfull, tempty, tmem_base, warp, lane); break;
+        case EM_RELU: epilogue_loop<EM_RELU, false>(a, tfull, tempty, tmem_base, warp, lane); break;
+        case EM_SIGMOID: epilogue_loop<EM_SIGMOID, false>(a, tfull, tempty, tmem_base, warp, lane); break;
+        case EM_RESIDUAL: epilogue_loop<EM_RESIDUAL, false>(a, tfull, tempty, tmem_base, warp, lane); break;
+        case EM_LKAGATE: epilogue_loop<EM_LKAGATE, false>(a, tfull, tempty, tmem_base, warp, lane); break;
+        default: epilogue_loop<EM_NONE, false>(a, tfull, tempty, tmem_base, warp, lane); break;
+      }
     }
   }
 
