@@ -199,21 +199,25 @@ def main():
     # ---- e2e: pinned host buffers, H2D + D2H inside the timed region -----------------------
     out_host = torch.empty(B, 3, 4 * H, 4 * W).pin_memory()
 
+    # the repo's public serving loop: copies of image i+1 overlap the forward of image i
+    from isr_b200.serving import PipelinedFusion
+    pipe = PipelinedFusion(m, depth=2, device=dev)
+
     def e2e_step():
-        l = host["lr"].to(dev, non_blocking=True)
-        im = {k: v.to(dev, non_blocking=True) for k, v in host["imgs"].items()}
-        ft = {k: v.to(dev, non_blocking=True) for k, v in host["fts"].items()}
-        out_host.copy_(m.forward_with_precomputed(l, im, ft), non_blocking=True)
+        pipe.submit(host["lr"], host["imgs"], host["fts"], out_host)
 
     for _ in range(2):
         e2e_step()
+    pipe.finish()
     barrier()
+    t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
+    pipe.finish()                       # every copy-out has landed in host memory
     e1.record()
     barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
 
     if rank == 0:
         tensor_peak, hbm_peak, peak_src = _peaks()

@@ -407,3 +407,23 @@ def test_bf16_mode_psnr_and_indices(B, H, W, realistic):
     m.precision = "fp32"
     sr32 = m.forward_with_precomputed(lrd, imd, ftd).cpu()
     assert (sr32 - ref).abs().max().item() <= FP32_TOL
+
+
+def test_pipelined_serving_matches_direct_calls():
+    """serving.PipelinedFusion (copy-in / compute / copy-out streams) returns exactly what
+    forward_with_precomputed returns, for a stream of different images."""
+    dev = _cuda()
+    from isr_b200.serving import PipelinedFusion
+    m = _model(True).to(dev)
+    pipe = PipelinedFusion(m, depth=2, device=dev)
+    items, outs = [], []
+    for seed in range(5):
+        lr, imgs, fts, _ = O.synthetic_inputs(1, 24, 32, seed=100 + seed)
+        items.append((lr.pin_memory(), {k: v.pin_memory() for k, v in imgs.items()}, {k: v.pin_memory() for k, v in fts.items()}))
+        outs.append(torch.empty(1, 3, 96, 128).pin_memory())
+    for (lr, imgs, fts), o in zip(items, outs):
+        pipe.submit(lr, imgs, fts, o)
+    pipe.finish()
+    for (lr, imgs, fts), o in zip(items, outs):
+        ref = m.forward_with_precomputed(lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()})
+        assert torch.equal(o, ref.cpu())
