@@ -40,7 +40,21 @@ class ConvParams(C.Structure):
     ]
 
 
+class WgradParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("x_sN", C.c_longlong), ("x_sY", C.c_longlong), ("x_sX", C.c_longlong), ("x_sC", C.c_longlong),
+        ("x_dtype", C.c_int),
+        ("dy", C.c_void_p),
+        ("dy_sN", C.c_longlong), ("dy_sY", C.c_longlong), ("dy_sX", C.c_longlong),
+        ("dy_dtype", C.c_int),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int), ("ksize", C.c_int),
+        ("dw", C.c_void_p), ("dbias", C.c_void_p),
+    ]
+
+
 _P, _I, _L, _LL, _SZ = C.c_void_p, C.c_int, C.c_long, C.c_longlong, C.c_size_t
+_F, _U64 = C.c_float, C.c_ulonglong
 
 # name -> (restype, argtypes); the authoritative list of exported symbols (tests check it
 # against include/ffsr_b200.h)
@@ -73,6 +87,20 @@ PROTOTYPES = {
     "ffsr_nchw_to_nhwc_bf16": (_I, [_P, _I, _I, _L, _P, _LL, _LL, _P]),
     "ffsr_cast_f32_to_bf16": (_I, [_P, _P, _L, _P]),
     "ffsr_final_combine": (_I, [_P, _LL, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    # ---- train-mode / backward ----
+    "ffsr_conv2d_wgrad": (_I, [C.POINTER(WgradParams), _P]),
+    "ffsr_wgrad_params_size": (_SZ, []),
+    "ffsr_colsum": (_I, [_P, _I, _I, _I, _I, _I, _LL, _LL, _LL, _P, _P]),
+    "ffsr_act_forward": (_I, [_P, _P, _L, _I, _I, _P]),
+    "ffsr_act_backward": (_I, [_P, _P, _P, _L, _I, _I, _P]),
+    "ffsr_layernorm_backward": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P]),
+    "ffsr_bn_stats": (_I, [_P, _I, _L, _I, _P, _P, _P]),
+    "ffsr_bn_apply": (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _P, _P]),
+    "ffsr_bn_backward": (_I, [_P, _P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "ffsr_token_attention_train": (_I, [_P, _I, _I, _L, _I, _P, _P, _F, _U64, _P]),
+    "ffsr_token_attention_backward": (_I, [_P, _P, _P, _I, _I, _L, _I, _P, _P, _F, _U64, _P]),
+    "ffsr_dwconv_stage": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "ffsr_dwconv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
 }
 
 _lib = None
@@ -94,6 +122,8 @@ def load():
         fn.argtypes = args
     if lib.ffsr_conv_params_size() != C.sizeof(ConvParams):
         raise FusionLibraryError("ffsr_conv_params layout mismatch between _cabi.py and the built library; rebuild")
+    if lib.ffsr_wgrad_params_size() != C.sizeof(WgradParams):
+        raise FusionLibraryError("ffsr_wgrad_params layout mismatch between _cabi.py and the built library; rebuild")
     _lib = lib
     return lib
 

@@ -118,9 +118,14 @@ class CompleteEnhancedFusionSR(nn.Module):
                 "the sm_100a path implements the all-phases-on 4-expert x4 configuration "
                 "(configs/train_config.yaml:63-80); other flag combinations are not built")
         if self.training:
-            raise NotImplementedError(
-                "train-mode forward/backward kernels are not built yet; call .eval() "
-                "(inference hot path: io.py:280, generate_fast_submission.py:232)")
+            # train mode: differentiable graph of library kernels (BN batch statistics, attention
+            # dropout, no output clamps) -- train.py:331-357 calls this under autograd
+            from .training import train_forward
+            sr, inter = train_forward(self, lr_input, expert_output_list, expert_features, return_intermediates)
+            if return_intermediates:
+                intermediates.update(inter)
+                return sr, intermediates
+            return sr
         from .pipeline import FusionEngine
         if self._engine is None:
             self._engine = FusionEngine(self)

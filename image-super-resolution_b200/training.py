@@ -1,0 +1,661 @@
+"""Train-mode forward + backward of the fusion path on the sm_100a kernels.
+
+``train_forward`` is what ``CompleteEnhancedFusionSR._run_pipeline`` runs when the module is
+in ``.train()`` mode (reference: ``src/models/enhanced_fusion_v2.py:681-799`` driven by
+``train.py:331-357``).  The differentiable graph is assembled from ``torch.autograd.Function``
+nodes whose forward AND backward are ``libffsr_b200.so`` kernels:
+
+  conv2d        ffsr_conv2d (forward; input gradient = same kernel, rotated weights),
+                ffsr_conv2d_wgrad (+ bias column sums)
+  act           ffsr_act_forward / ffsr_act_backward        (GELU / ReLU / sigmoid)
+  batchnorm     ffsr_bn_stats / ffsr_bn_apply / ffsr_bn_backward   (batch statistics per LKABlock call)
+  layernorm     ffsr_layernorm / ffsr_layernorm_backward
+  token_attn    ffsr_token_attention_train / ffsr_token_attention_backward  (dropout on the probabilities)
+  dwconv        ffsr_dwconv_stage / ffsr_dwconv_wgrad       (LKA 5x5, 1x21, 21x1)
+
+PyTorch autograd is the plumbing between those nodes: tensor bookkeeping, concatenation,
+bilinear resampling and the few-channel elementwise blends are ordinary CUDA tensor ops
+(DESIGN.md section 8 lists them).  There is no CPU path: CPU tensors raise.
+
+Tensors are logical NCHW in channels-last memory ([N][H][W][C]), the layout every kernel of
+the library works in.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _cabi as K
+
+EXPERT_ORDER = ("drct", "grl", "nafnet", "mamba")
+_BN_EPS = 1e-5
+CL = torch.channels_last
+
+
+def _lib():
+    return K.load()
+
+
+def _S(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ck(rc, what):
+    if rc != 0:
+        K.check(rc, what)
+
+
+def _is_cl(t: torch.Tensor) -> bool:
+    return t.permute(0, 2, 3, 1).is_contiguous()
+
+
+def _cl(t: torch.Tensor) -> torch.Tensor:
+    """Dense channels-last copy (no-op when the memory already is [N][H][W][C])."""
+    if _is_cl(t):
+        return t
+    out = torch.empty(t.shape, device=t.device, dtype=t.dtype).contiguous(memory_format=CL)
+    if not _is_cl(out):                       # C == 1 or H == W == 1: layouts coincide
+        out = torch.empty_strided(t.shape, _cl_strides(t.shape), device=t.device, dtype=t.dtype)
+    out.copy_(t)
+    return out
+
+
+def _cl_strides(shape):
+    N, Cc, H, W = shape
+    return (H * W * Cc, 1, W * Cc, Cc)
+
+
+def _empty_cl(N, Cc, H, W, dev, dtype=torch.float32) -> torch.Tensor:
+    return torch.empty_strided((N, Cc, H, W), (H * W * Cc, 1, W * Cc, Cc), device=dev, dtype=dtype)
+
+
+def _zeros(shape, dev, dtype=torch.float32):
+    return torch.zeros(shape, device=dev, dtype=dtype)
+
+
+def _dt(t):
+    return K.DT_BF16 if t.dtype == torch.bfloat16 else K.DT_F32
+
+
+# --------------------------------------------------------------------------------------
+# convolution
+# --------------------------------------------------------------------------------------
+def _launch_conv(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, ks: int):
+    """x: [N,Cin,H,W] any strides (fp32); wp: [ks*ks][Cin][Cout] fp32; out: channels-last [N,Cout,H,W]."""
+    N, Cin, H, W = x.shape
+    Cout = out.shape[1]
+    p = K.ConvParams()
+    p.inp = x.data_ptr()
+    p.in_sN, p.in_sC, p.in_sY, p.in_sX = x.stride(0), x.stride(1), x.stride(2), x.stride(3)
+    if Cin == 1:
+        p.in_sC = 1
+    p.N, p.H, p.W, p.Cin, p.Cout, p.ksize = N, H, W, Cin, Cout, ks
+    p.w = wp.data_ptr()
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.groups = 1
+    p.out = out.data_ptr()
+    p.out_sN, p.out_sY, p.out_sX = H * W * Cout, W * Cout, Cout
+    p.act, p.epi = K.ACT_NONE, K.EPI_PLAIN
+    p.sa = p.sb = 1.0
+    p.in_dtype = p.out_dtype = p.w_dtype = K.DT_F32
+    _ck(_lib().ffsr_conv2d(C.byref(p), _S(x)), "conv2d")
+
+
+class _Conv2d(torch.autograd.Function):
+    """nn.Conv2d (1x1 / 3x3, stride 1, zero pad k//2)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        co, ci, kh, kw = weight.shape
+        assert kh == kw and kh in (1, 3) and x.shape[1] == ci, (tuple(weight.shape), tuple(x.shape))
+        x = x if x.dtype == torch.float32 else x.float()
+        wp = weight.detach().permute(2, 3, 1, 0).reshape(kh * kw, ci, co).contiguous()
+        N, _, H, W = x.shape
+        out = _empty_cl(N, co, H, W, x.device)
+        b = bias.detach().contiguous() if bias is not None else None
+        _launch_conv(x, wp, b, out, kh)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        co, ci, kh, kw = weight.shape
+        N, _, H, W = x.shape
+        gy = _cl(gy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wr = weight.detach().flip(2, 3).permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
+            dx = _empty_cl(N, ci, H, W, x.device)
+            _launch_conv(gy, wr, None, dx, kh)
+        dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dwp = _zeros((kh * kw, ci, co), x.device)
+            dbp = _zeros((co,), x.device) if ctx.has_bias else None
+            p = K.WgradParams()
+            p.x = x.data_ptr()
+            p.x_sN, p.x_sC, p.x_sY, p.x_sX = x.stride(0), x.stride(1), x.stride(2), x.stride(3)
+            if ci == 1:
+                p.x_sC = 1
+            p.x_dtype = K.DT_F32
+            p.dy = gy.data_ptr()
+            p.dy_sN, p.dy_sY, p.dy_sX = H * W * co, W * co, co
+            p.dy_dtype = K.DT_F32
+            p.N, p.H, p.W, p.Cin, p.Cout, p.ksize = N, H, W, ci, co, kh
+            p.dw = dwp.data_ptr()
+            p.dbias = dbp.data_ptr() if dbp is not None else None
+            _ck(_lib().ffsr_conv2d_wgrad(C.byref(p), _S(x)), "conv2d_wgrad")
+            dw = dwp.view(kh, kw, ci, co).permute(3, 2, 0, 1)
+            db = dbp
+        return dx, dw, db
+
+
+def conv2d(x, weight, bias=None):
+    if weight.dim() == 2:                      # nn.Linear weight [out, in] == 1x1 conv
+        weight = weight[:, :, None, None]
+    return _Conv2d.apply(x, weight, bias)
+
+
+def conv_mod(x, mod):
+    return conv2d(x, mod.weight, mod.bias)
+
+
+# --------------------------------------------------------------------------------------
+# pointwise activations
+# --------------------------------------------------------------------------------------
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kind):
+        x = x if x.is_contiguous() or _is_cl(x) else x.contiguous()
+        y = torch.empty_like(x)               # preserves the (dense) strides
+        _ck(_lib().ffsr_act_forward(x.data_ptr(), y.data_ptr(), x.numel(), kind, _dt(x), _S(x)), "act_forward")
+        ctx.save_for_backward(x)
+        ctx.kind = kind
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        if gy.stride() != x.stride() or gy.dtype != x.dtype:
+            g2 = torch.empty_like(x)
+            g2.copy_(gy)
+            gy = g2
+        dx = torch.empty_like(x)
+        _ck(_lib().ffsr_act_backward(x.data_ptr(), gy.data_ptr(), dx.data_ptr(), x.numel(), ctx.kind, _dt(x), _S(x)),
+            "act_backward")
+        return dx, None
+
+
+def gelu(x):
+    return _Act.apply(x, K.ACT_GELU)
+
+
+def relu(x):
+    return _Act.apply(x, K.ACT_RELU)
+
+
+def sigmoid(x):
+    return _Act.apply(x, K.ACT_SIGMOID)
+
+
+# --------------------------------------------------------------------------------------
+# BatchNorm2d, train mode, G statistic groups (group-major images)
+# --------------------------------------------------------------------------------------
+class _BatchNormTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, G):
+        x = _cl(x)
+        N, Cc, H, W = x.shape
+        assert N % G == 0
+        R = (N // G) * H * W
+        dev = x.device
+        s = _zeros((2, G, Cc), dev, torch.float64)
+        lib = _lib()
+        _ck(lib.ffsr_bn_stats(x.data_ptr(), G, R, Cc, s[0].data_ptr(), s[1].data_ptr(), _S(x)), "bn_stats")
+        mean64 = s[0] / R
+        var64 = (s[1] / R - mean64 * mean64).clamp_(min=0.0)
+        mean = mean64.float()
+        var = var64.float()
+        rstd = torch.rsqrt(var + _BN_EPS)
+        y = torch.empty_like(x)
+        w = weight.detach().contiguous()
+        b = bias.detach().contiguous()
+        _ck(lib.ffsr_bn_apply(x.data_ptr(), G, R, Cc, mean.data_ptr(), rstd.data_ptr(), w.data_ptr(), b.data_ptr(),
+                              y.data_ptr(), _S(x)), "bn_apply")
+        ctx.save_for_backward(x, mean, rstd, w)
+        ctx.G, ctx.R = G, R
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, _gm, _gv):
+        x, mean, rstd, w = ctx.saved_tensors
+        G, R = ctx.G, ctx.R
+        Cc = x.shape[1]
+        gy = _cl(gy)
+        red = _zeros((2, G, Cc), x.device)
+        dx = torch.empty_like(x)
+        _ck(_lib().ffsr_bn_backward(x.data_ptr(), gy.data_ptr(), G, R, Cc, mean.data_ptr(), rstd.data_ptr(),
+                                    w.data_ptr(), red[0].data_ptr(), red[1].data_ptr(), dx.data_ptr(), _S(x)),
+            "bn_backward")
+        return dx, red[1].sum(0), red[0].sum(0), None
+
+
+def batchnorm_train(x, bn: torch.nn.BatchNorm2d, G: int, stats_sink: list):
+    """Batch-statistic BN over G groups; the per-group (mean, biased var, n) are appended to
+    ``stats_sink`` so the caller can fold the running-stat EMA in call order."""
+    y, mean, var = _BatchNormTrain.apply(x, bn.weight, bn.bias, G)
+    n = x.numel() // (x.shape[1] * G)
+    stats_sink.append((bn, mean, var, n))
+    return y
+
+
+@torch.no_grad()
+def fold_running_stats(records):
+    """nn.BatchNorm2d side effect (momentum 0.1, unbiased variance, counter += 1 per call),
+    applied for the G sequential LKABlock calls of one forward.  records: [(bn, mean[G,C], var[G,C], n)]
+    in call order per BN module (large_kernel_attention.py:84,128,131)."""
+    by_mod: Dict[int, list] = {}
+    for bn, mean, var, n in records:
+        by_mod.setdefault(id(bn), [bn, [], [], n])
+        by_mod[id(bn)][1].append(mean)
+        by_mod[id(bn)][2].append(var)
+    for bn, means, vars_, n in by_mod.values():
+        mean = torch.cat(means, 0)
+        var = torch.cat(vars_, 0) * (n / max(n - 1, 1))
+        G = mean.shape[0]
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        wts = mom * (1.0 - mom) ** torch.arange(G - 1, -1, -1, device=mean.device, dtype=torch.float32)
+        keep = (1.0 - mom) ** G
+        bn.running_mean.mul_(keep).add_((wts[:, None] * mean).sum(0))
+        bn.running_var.mul_(keep).add_((wts[:, None] * var).sum(0))
+        bn.num_batches_tracked.add_(G)
+
+
+# --------------------------------------------------------------------------------------
+# LayerNorm over channels of a channels-last tensor
+# --------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _cl(x)
+        N, E, H, W = x.shape
+        rows = N * H * W
+        y = torch.empty_like(x)
+        w = weight.detach().contiguous()
+        b = bias.detach().contiguous()
+        _ck(_lib().ffsr_layernorm(x.data_ptr(), rows, E, w.data_ptr(), b.data_ptr(), y.data_ptr(), 0, _S(x)), "layernorm")
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        N, E, H, W = x.shape
+        gy = _cl(gy)
+        dx = torch.empty_like(x)
+        dwb = _zeros((2, E), x.device)
+        _ck(_lib().ffsr_layernorm_backward(x.data_ptr(), gy.data_ptr(), N * H * W, E, w.data_ptr(), dx.data_ptr(),
+                                           dwb[0].data_ptr(), dwb[1].data_ptr(), _S(x)), "layernorm_backward")
+        return dx, dwb[0], dwb[1]
+
+
+def layernorm(x, ln):
+    return _LayerNorm.apply(x, ln.weight, ln.bias)
+
+
+# --------------------------------------------------------------------------------------
+# token attention core
+# --------------------------------------------------------------------------------------
+class _TokenAttention(torch.autograd.Function):
+    """qkv: [B*T, 3E, H, W] channels-last (memory [B][T][HW][3E]) -> ctx [B*T, E, H, W]."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, T, drop_p, seed):
+        qkv = _cl(qkv)
+        BT, E3, H, W = qkv.shape
+        E = E3 // 3
+        HW = H * W
+        out = _empty_cl(BT, E, H, W, qkv.device)
+        probs = torch.empty(B * HW * (E // 16) * T * T, device=qkv.device, dtype=torch.float32)
+        _ck(_lib().ffsr_token_attention_train(qkv.data_ptr(), B, T, HW, E, out.data_ptr(), probs.data_ptr(),
+                                              float(drop_p), int(seed), _S(qkv)), "token_attention_train")
+        ctx.save_for_backward(qkv, probs)
+        ctx.cfg = (B, T, HW, E, float(drop_p), int(seed))
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        qkv, probs = ctx.saved_tensors
+        B, T, HW, E, drop_p, seed = ctx.cfg
+        gy = _cl(gy)
+        dqkv = torch.empty_like(qkv)
+        ds = torch.empty_like(probs)
+        _ck(_lib().ffsr_token_attention_backward(qkv.data_ptr(), probs.data_ptr(), gy.data_ptr(), B, T, HW, E,
+                                                 ds.data_ptr(), dqkv.data_ptr(), drop_p, seed, _S(qkv)),
+            "token_attention_backward")
+        return dqkv, None, None, None, None
+
+
+def _draw_seed() -> int:
+    # CPU default generator: reproducible under torch.manual_seed, no device sync
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+def mha_tokens(x, mha: torch.nn.MultiheadAttention, B: int, T: int, training: bool):
+    """nn.MultiheadAttention self-attention over the T tokens of every LR pixel.
+    x: [B*T, E, H, W] channels-last token-major.  (large_kernel_attention.py:192-197, 294-299)"""
+    qkv = conv2d(x, mha.in_proj_weight, mha.in_proj_bias)
+    p = float(mha.dropout) if training else 0.0
+    ctx = _TokenAttention.apply(qkv, B, T, p, _draw_seed() if p > 0 else 0)
+    return conv2d(ctx, mha.out_proj.weight, mha.out_proj.bias)
+
+
+# --------------------------------------------------------------------------------------
+# depthwise stages of the LKA chain
+# --------------------------------------------------------------------------------------
+class _DwStage(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, kind):
+        x = _cl(x)
+        N, Cc, H, W = x.shape
+        w = weight.detach().reshape(Cc, -1).contiguous()
+        out = torch.empty_like(x)
+        ones = torch.ones(Cc, device=x.device)
+        zeros = torch.zeros(Cc, device=x.device)
+        _ck(_lib().ffsr_dwconv_stage(x.data_ptr(), N, H, W, Cc, kind, w.data_ptr(), ones.data_ptr(), zeros.data_ptr(),
+                                     out.data_ptr(), _S(x)), "dwconv_stage")
+        ctx.save_for_backward(x, weight)
+        ctx.kind = kind
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        kind = ctx.kind
+        N, Cc, H, W = x.shape
+        gy = _cl(gy)
+        lib = _lib()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wf = weight.detach().reshape(Cc, -1).flip(1).contiguous()
+            dx = torch.empty_like(x)
+            ones = torch.ones(Cc, device=x.device)
+            zeros = torch.zeros(Cc, device=x.device)
+            _ck(lib.ffsr_dwconv_stage(gy.data_ptr(), N, H, W, Cc, kind, wf.data_ptr(), ones.data_ptr(), zeros.data_ptr(),
+                                      dx.data_ptr(), _S(x)), "dwconv_stage(bwd)")
+        dw = _zeros((Cc, weight.numel() // Cc), x.device)
+        _ck(lib.ffsr_dwconv_wgrad(x.data_ptr(), gy.data_ptr(), N, H, W, Cc, kind, dw.data_ptr(), _S(x)), "dwconv_wgrad")
+        return dx, dw.view(weight.shape), None
+
+
+# --------------------------------------------------------------------------------------
+# LKABlock (large_kernel_attention.py:92-105, 143-149), train mode, G statistic groups
+# --------------------------------------------------------------------------------------
+def lka_block_train(x, blk, G: int, sink: list, stats_only: bool = False):
+    n = batchnorm_train(x, blk.norm1, G, sink)
+    a = _DwStage.apply(n, blk.lka.local_conv.weight, 0)
+    a = _DwStage.apply(a, blk.lka.h_conv.weight, 1)
+    a = _DwStage.apply(a, blk.lka.v_conv.weight, 2)
+    a = conv2d(a, blk.lka.pw_conv.weight, None)
+    a = sigmoid(batchnorm_train(a, blk.lka.bn, G, sink))
+    x1 = x + blk.scale1 * (n * a)
+    h = batchnorm_train(x1, blk.norm2, G, sink)
+    if stats_only:
+        return None
+    h = gelu(conv_mod(h, blk.ffn[0]))
+    h = conv_mod(h, blk.ffn[2])
+    return x1 + blk.scale2 * h
+
+
+def _bilinear(x, size):
+    return F.interpolate(x, size=size, mode="bilinear", align_corners=False)
+
+
+def _to_group_major(x, B, T):
+    """[B*T, C, H, W] token-major (image b*T+t) -> [T*B, C, H, W] group-major (image t*B+b), channels-last."""
+    BT, Cc, H, W = x.shape
+    v = _cl(x).permute(0, 2, 3, 1).reshape(B, T, H, W, Cc).transpose(0, 1).contiguous()
+    return v.view(T * B, H, W, Cc).permute(0, 3, 1, 2)
+
+
+# --------------------------------------------------------------------------------------
+# Phase 2 in train mode
+# --------------------------------------------------------------------------------------
+def _phase2_train(m, lr):
+    """9 sub-bands [B,9,3,H,W] with gradients to band_scale / subband_scale / FFT mask parameters.
+    The DCT and DWT analysis run on the library kernels with unit scales (the input needs no
+    gradient, so they are constants of the graph) and are scaled by the learnable factors here;
+    the learnable FFT mask path (3 transforms of a 3-channel LR image) is differentiated through
+    torch.fft (cuFFT)."""
+    lib = _lib()
+    fd = m.freq_decomp
+    B, _, H, W = lr.shape
+    dev = lr.device
+    S = _S(lr)
+    with torch.no_grad():
+        raw = torch.zeros(B, 9, 3, H, W, device=dev)
+        ones = torch.ones(4, device=dev)
+
+        def c32(t):
+            t = t.detach()
+            return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+        d = fd.dct
+        keep = [c32(d.dct_basis), c32(d.dct_basis_t), c32(d.low_mask), c32(d.mid_mask), c32(d.high_mask)]
+        _ck(lib.ffsr_dct_bands(lr.data_ptr(), B, H, W, keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(),
+                               keep[3].data_ptr(), keep[4].data_ptr(), ones.data_ptr(), raw.data_ptr(), S), "dct_bands")
+        hs, ws_ = C.c_int(), C.c_int()
+        lib.ffsr_dwt_sub_size(H, W, C.byref(hs), C.byref(ws_))
+        sub = torch.empty(B, 4, 3, hs.value, ws_.value, device=dev)
+        w_ = fd.dwt
+        k2 = [c32(w_.lo_row), c32(w_.hi_row), c32(w_.lo_col), c32(w_.hi_col)]
+        _ck(lib.ffsr_dwt_bands(lr.data_ptr(), B, H, W, k2[0].data_ptr(), k2[1].data_ptr(), k2[2].data_ptr(),
+                               k2[3].data_ptr(), ones.data_ptr(), sub.data_ptr(), raw.data_ptr(), S), "dwt_bands")
+    scale7 = torch.cat([fd.dct.band_scale, fd.dwt.subband_scale])
+    b7 = raw[:, :7] * scale7[None, :, None, None, None]
+    X = torch.fft.rfft2(lr, norm="ortho")
+    Hf, Wf = X.shape[-2:]
+    msk = _bilinear(fd.fft.freq_mask_logits, (Hf, Wf))
+    msk = torch.sigmoid(msk * fd.fft.temperature.clamp(min=1.0))
+    low = torch.fft.irfft2(X * msk, s=(H, W), norm="ortho") * fd.fft.band_scale[0]
+    high = torch.fft.irfft2(X * (1 - msk), s=(H, W), norm="ortho") * fd.fft.band_scale[1]
+    return torch.cat([b7, low[:, None], high[:, None]], dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# whole pipeline, train mode
+# --------------------------------------------------------------------------------------
+def train_forward(m, lr: torch.Tensor, img_list: List[torch.Tensor], feats: Dict[str, torch.Tensor],
+                  want_inter: bool = False):
+    if not lr.is_cuda:
+        raise RuntimeError("CompleteEnhancedFusionSR (sm_100a build) needs CUDA tensors: there is no CPU path")
+    lib = _lib()
+    with torch.cuda.device(lr.device):
+        _ck(lib.ffsr_device_check(), "device_check")
+        return _train_forward(m, lr, img_list, feats, want_inter)
+
+
+def _train_forward(m, lr, img_list, feats, want_inter):
+    if len(img_list) != 4:
+        raise ValueError(f"expected the 4 expert outputs drct/grl/nafnet/mamba, got {len(img_list)}")
+    B, _, H, W = lr.shape
+    Hh, Wh = 4 * H, 4 * W
+    lr = lr.detach().float().contiguous()
+    imgs = [t.detach().float() for t in img_list]
+    training = m.training
+    sink: list = []
+    inter: Dict = {}
+
+    # ---------------- Phase 2 ----------------
+    raw9 = _phase2_train(m, lr)                                           # [B,9,3,H,W]
+
+    # ---------------- Phase 3 ----------------
+    cb = m.cross_band
+    tok_in = raw9.reshape(B * 9, 3, H, W)                                 # token-major images, NCHW planes
+    proj = conv_mod(tok_in, cb.band_proj)                                 # [B*9,64,H,W]
+    att = mha_tokens(layernorm(proj, cb.norm), cb.band_attention, B, 9, training) + proj
+    gm = _to_group_major(att, B, 9)                                       # [9*B,64,H,W], band-major
+    x_used = lka_block_train(gm[:3 * B], cb.lka_block, 3, sink)
+    with torch.no_grad():                                                 # bands 3..8 feed nothing downstream:
+        lka_block_train(gm[3 * B:].detach(), cb.lka_block, 6, sink, stats_only=True)   # BN running stats only
+    enh = conv_mod(x_used, cb.out_proj).reshape(3, B, 3, H, W) + raw9[:, :3].transpose(0, 1)
+    routing = enh.sum(0)                                                  # [B,3,H,W]
+
+    # ---------------- Phase 6 nets ----------------
+    ds = m.dynamic_selector
+    d = relu(conv_mod(routing, ds.difficulty_net[0]))
+    d = relu(conv_mod(d, ds.difficulty_net[2]))
+    diff = sigmoid(conv_mod(d, ds.difficulty_net[4]))
+    g = relu(conv_mod(routing, ds.gate_net[0]))
+    g = relu(conv_mod(g, ds.gate_net[2]))
+    graw = conv_mod(g, ds.gate_net[4])
+    gt = torch.sigmoid(ds.temperature * (graw - (0.7 - 0.5 * diff)))
+    gates = gt / (gt.sum(dim=1, keepdim=True) + 1e-8).clamp(min=0.3)
+
+    # ---------------- Phase 4 ----------------
+    co = m.collaborative
+    have = [n for n in EXPERT_ORDER if n in feats]
+    if have:
+        aligned = []
+        for n in EXPERT_ORDER:
+            if n not in feats:
+                aligned.append(None)
+                continue
+            f = feats[n].detach().float()
+            if f.dim() != 4 or f.shape[0] != B or tuple(f.shape[2:]) != (H, W):
+                raise NotImplementedError(
+                    f"expert feature '{n}' has shape {tuple(f.shape)}; the sm_100a path needs [B,C,{H},{W}]")
+            al = co.align_layers[n]
+            cin_w = al.weight.shape[1]
+            wgt = al.weight
+            if f.shape[1] > cin_w:
+                f = f[:, :cin_w]
+            elif f.shape[1] < cin_w:
+                wgt = wgt[:, :f.shape[1]]                                  # zero-padded channels contribute nothing
+            aligned.append(conv2d(f, wgt, al.bias))
+        E = co.norm1.weight.shape[0]
+        zero = None
+        rows = []
+        for a in aligned:
+            if a is None:
+                if zero is None:
+                    zero = torch.zeros(B, H, W, E, device=lr.device)
+                rows.append(zero)
+            else:
+                rows.append(a.permute(0, 2, 3, 1))
+        tokens = torch.stack(rows, dim=1).reshape(B * 4, H, W, E).permute(0, 3, 1, 2)   # token-major, channels-last
+        x = tokens + mha_tokens(layernorm(tokens, co.norm1), co.cross_attn, B, 4, training)
+        hdn = gelu(conv2d(layernorm(x, co.norm2), co.ffn[0].weight, co.ffn[0].bias))
+        x = x + conv2d(hdn, co.ffn[2].weight, co.ffn[2].bias)
+        xg = lka_block_train(_to_group_major(x, B, 4), co.lka_global, 4, sink)             # [4*B,128,H,W]
+        ecol = []
+        for i in range(4):
+            mod = co.modulation[i]
+            f_i = xg[i * B:(i + 1) * B]
+            m32 = conv_mod(f_i, mod[0])                       # 1x1 conv commutes with the bilinear upsampling
+            up = gelu(_bilinear(m32, (Hh, Wh)))
+            mk = sigmoid(conv_mod(up, mod[2]))
+            o = imgs[i] * (1.0 + 0.2 * (mk - 0.5))
+            if not training:
+                o = o.clamp(0, 1)
+            ecol.append(o)
+    else:
+        ecol = imgs
+
+    # ---------------- Phase 5 ----------------
+    mr = m.multi_res
+    stack = torch.cat(ecol, dim=1)                                          # [B,12,Hh,Wh]
+
+    def stage(xin, name):
+        cv = getattr(mr, name + "_conv")
+        y = gelu(conv_mod(xin, cv[0]))
+        y = gelu(conv_mod(y, cv[2]))
+        gate = getattr(mr, name + "_gate").gate
+        y = y * sigmoid(conv_mod(gelu(conv_mod(y, gate[0])), gate[2]))
+        res = getattr(mr, name + "_res")
+        r = conv2d(gelu(conv2d(y, res.block[0].weight, None)), res.block[2].weight, None)
+        return y + res.scale * r
+
+    f1 = stage(_bilinear(stack, (H, W)), "stage1")
+    f1u = _bilinear(f1, (2 * H, 2 * W))
+    f2 = stage(torch.cat([f1u, _bilinear(stack, (2 * H, 2 * W))], dim=1), "stage2")
+    f2 = f2 + mr.residual_weight_1_2 * f1u
+    f2u = _bilinear(f2, (Hh, Wh))
+    f3 = stage(torch.cat([f2u, stack], dim=1), "stage3")
+    f3 = f3 + mr.residual_weight_2_3 * f2u[:, :f3.shape[1]]
+    hier = sigmoid(conv_mod(gelu(conv_mod(f3, mr.to_rgb[0])), mr.to_rgb[2]))
+
+    # ---------------- Phase 5b / 6 blend ----------------
+    r_hr = _bilinear(routing, (Hh, Wh))
+    fl = conv_mod(gelu(conv_mod(r_hr, m.freq_weight_conv[0])), m.freq_weight_conv[2])
+    fw = torch.softmax(fl, dim=1)
+    freq = sum(o * fw[:, i:i + 1] for i, o in enumerate(ecol))
+    fused = hier * 0.7 + freq * 0.3
+    fused_before = fused
+    g_hr = _bilinear(gates, (Hh, Wh))
+    dyn = sum(o * g_hr[:, i:i + 1] for i, o in enumerate(ecol))
+    dyn = dyn / (g_hr.sum(dim=1, keepdim=True) + 1e-8)
+    bw = 0.3 + 0.4 * _bilinear(diff, (Hh, Wh))
+    fused = (1 - bw) * fused + bw * dyn
+
+    # ---------------- Phase 7a ----------------
+    convs = [l for l in m.refine if isinstance(l, torch.nn.Conv2d)]
+    y = fused
+    for j, cv in enumerate(convs):
+        y = conv_mod(y, cv)
+        if j < len(convs) - 1:
+            y = gelu(y)
+    fused = fused + 0.1 * y
+
+    # ---------------- Phase 7b ----------------
+    ee = m.edge_enhance
+    kern = ee.gaussian.kernel
+    pyr, cur = [], fused
+    for lv in range(3):
+        if lv < 2:
+            hh, ww = cur.shape[2:]
+            down = F.avg_pool2d(F.conv2d(cur, kern, padding=2, groups=3), 2, 2)
+            pyr.append(cur - _bilinear(down, (hh, ww)))
+            cur = down
+        else:
+            pyr.append(cur)
+    lw = torch.softmax(ee.level_weights, dim=0)
+    fl_ = []
+    for lv, lap in enumerate(pyr):
+        r = ee.edge_refiners[lv]
+        idt = conv_mod(lap, r.proj)
+        o = gelu(conv_mod(lap, r.conv1))
+        o = gelu(conv_mod(o, r.conv2))
+        o = conv_mod(o, r.conv3) + idt
+        a = sigmoid(conv_mod(gelu(conv_mod(o, r.attn.attn[0])), r.attn.attn[2]))
+        f = o * a
+        if f.shape[2:] != (Hh, Wh):
+            f = _bilinear(f, (Hh, Wh))
+        fl_.append(f * lw[lv])
+    e = conv_mod(gelu(conv_mod(torch.cat(fl_, dim=1), ee.fusion[0])), ee.fusion[2])
+    gte = sigmoid(conv_mod(gelu(conv_mod(torch.cat([fused, e], dim=1), ee.edge_gate[0])), ee.edge_gate[2]))
+    fused = (fused + gte * ee.edge_strength * e).clamp(0, 1)
+
+    # ---------------- output ----------------
+    out = fused + m.residual_scale * _bilinear(lr, (Hh, Wh))
+    if not training:
+        out = out.clamp(0, 1)
+    out = out.contiguous()
+    if training:
+        fold_running_stats(sink)
+    if want_inter:
+        inter["raw_9_bands"] = [raw9[:, i] for i in range(9)]
+        inter["guidance_bands"] = inter["raw_9_bands"][:3]
+        inter["enhanced_9_bands"] = [enh[i] for i in range(3)]
+        inter["routing_lr"] = routing
+        if have:
+            inter["collaborative_outputs"] = ecol
+        inter["fused_before_dynamic"] = fused_before
+        inter["gates"] = gates
+        inter["difficulty"] = diff
+    return out, inter

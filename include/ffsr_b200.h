@@ -186,6 +186,72 @@ int ffsr_nchw_to_nhwc_bf16(const float* src, int N, int C, long HW, void* dst, l
                            cudaStream_t stream);
 int ffsr_cast_f32_to_bf16(const float* src, void* dst, long n, cudaStream_t stream);
 
+/* =========================================================================================
+ * Train-mode / backward entry points.  The reference relies on ATen autograd for these
+ * (loss.backward() in train.py:331-357 over the modules cited below); each entry point is the
+ * hand-written counterpart of one autograd node.  Gradient outputs marked ACCUMULATED are
+ * added into (the caller zeroes them), everything else is overwritten.
+ * ========================================================================================= */
+
+/* nn.Conv2d weight / bias gradient (every conv of enhanced_fusion_v2.py:681-799):
+ *   dw[tap][ci][co] += sum_{n,y,x} x[n, y+dy, x+dx, ci] * dy[n, y, x, co];  dbias[co] += sum dy
+ * x: strided view (NHWC or NCHW, like ffsr_conv2d's input); dy channels-last. */
+typedef struct ffsr_wgrad_params {
+  const void* x;
+  long long x_sN, x_sY, x_sX, x_sC;
+  int x_dtype;
+  const void* dy;
+  long long dy_sN, dy_sY, dy_sX;
+  int dy_dtype;
+  int N, H, W, Cin, Cout, ksize;
+  float* dw;    /* [k*k][Cin][Cout] fp32, ACCUMULATED */
+  float* dbias; /* [Cout] fp32, ACCUMULATED, or NULL */
+} ffsr_wgrad_params;
+int ffsr_conv2d_wgrad(const ffsr_wgrad_params* p, cudaStream_t stream);
+size_t ffsr_wgrad_params_size(void);
+/* out[c] += sum over (n,y,x) of a channels-last tensor (bias / scale gradients) */
+int ffsr_colsum(const void* v, int dtype, int N, int H, int W, int C, long long sN, long long sY, long long sX,
+                float* out, cudaStream_t stream);
+
+/* nn.GELU / nn.ReLU / nn.Sigmoid forward on contiguous data and backward on the saved
+ * pre-activation: dx = dy * act'(x) */
+int ffsr_act_forward(const void* x, void* y, long n, int act, int dtype, cudaStream_t stream);
+int ffsr_act_backward(const void* x, const void* dy, void* dx, long n, int act, int dtype, cudaStream_t stream);
+
+/* nn.LayerNorm backward (large_kernel_attention.py:223, 389, 392); dw/db ACCUMULATED */
+int ffsr_layernorm_backward(const float* x, const float* dy, long rows, int E, const float* w, float* dx, float* dw,
+                            float* db, cudaStream_t stream);
+
+/* nn.BatchNorm2d in train mode (large_kernel_attention.py:84,128,131) on channels-last data
+ * viewed as [G][R][C]: G independent statistic groups (one LKABlock call each), R rows per group.
+ *   ffsr_bn_stats:    sum[g][c], sumsq[g][c] += (fp64; ACCUMULATED)
+ *   ffsr_bn_apply:    y = (x - mean[g][c]) * rstd[g][c] * w[c] + b[c]
+ *   ffsr_bn_backward: sdy[g][c] += sum dy, sdyx[g][c] += sum dy*xhat (ACCUMULATED), then
+ *                     dx = w*rstd*(dy - sdy/R - xhat*sdyx/R) */
+int ffsr_bn_stats(const float* x, int G, long R, int C, double* sum, double* sumsq, cudaStream_t stream);
+int ffsr_bn_apply(const float* x, int G, long R, int C, const float* mean, const float* rstd, const float* w,
+                  const float* b, float* y, cudaStream_t stream);
+int ffsr_bn_backward(const float* x, const float* dy, int G, long R, int C, const float* mean, const float* rstd,
+                     const float* w, float* sdy, float* sdyx, float* dx, cudaStream_t stream);
+
+/* nn.MultiheadAttention core in train mode (T = 4 or 9 tokens per LR pixel, head_dim 16,
+ * attention-probability dropout): probs[B][HW][E/16][T][T] saved for the backward; the dropout
+ * mask is a counter-based hash of (seed, element index), regenerated by the backward.
+ * ds_scratch: same size as probs. */
+int ffsr_token_attention_train(const float* qkv, int B, int T, long HW, int E, float* ctx, float* probs, float drop_p,
+                               unsigned long long seed, cudaStream_t stream);
+int ffsr_token_attention_backward(const float* qkv, const float* probs, const float* dctx, int B, int T, long HW, int E,
+                                  float* ds_scratch, float* dqkv, float drop_p, unsigned long long seed,
+                                  cudaStream_t stream);
+
+/* single stages of the LKA depthwise chain (kind 0: 5x5 pad 2 with input affine bn_k/bn_d,
+ * 1: 1x21 pad 10, 2: 21x1 pad 10; w: [C][taps]) -- the backward runs them with reversed taps --
+ * and their weight gradients dw[C][taps] (ACCUMULATED).  large_kernel_attention.py:98-100 */
+int ffsr_dwconv_stage(const float* in, int N, int H, int W, int C, int kind, const float* w, const float* bn_k,
+                      const float* bn_d, float* out, cudaStream_t stream);
+int ffsr_dwconv_wgrad(const float* in, const float* g, int N, int H, int W, int C, int kind, float* dw,
+                      cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
