@@ -101,6 +101,21 @@ PROTOTYPES = {
     "ffsr_token_attention_backward": (_I, [_P, _P, _P, _I, _I, _L, _I, _P, _P, _F, _U64, _P]),
     "ffsr_dwconv_stage": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ffsr_dwconv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    # ---- fused losses ----
+    "ffsr_loss_l1": (_I, [_P, _P, _L, _F, _P, _P, _P]),
+    "ffsr_loss_swt_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ffsr_loss_swt": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _SZ, _P, _P]),
+    "ffsr_loss_ssim_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ffsr_loss_ssim": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _SZ, _P, _P]),
+    "ffsr_loss_fft_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ffsr_loss_fft": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _SZ, _P, _P]),
+    # ---- bf16 / tcgen05 training path ----
+    "ffsr_to_bf16_nhwc": (_I, [_P, _I, _LL, _LL, _LL, _LL, _I, _I, _I, _I, _I, _P, _P]),
+    "ffsr_conv2d_wgrad_tc_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
+    "ffsr_conv2d_wgrad_tc": (_I, [C.POINTER(WgradParams), _P, _SZ, _P]),
+    # ---- fused optimizer ----
+    "ffsr_sumsq": (_I, [_P, _L, _P, _P]),
+    "ffsr_adamw_ema_step": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _F, _F, _P]),
 }
 
 _lib = None

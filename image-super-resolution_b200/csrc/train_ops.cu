@@ -525,6 +525,22 @@ __global__ void k_tokattn_bwd_kv(const float* __restrict__ qkv, const float* __r
   for (int d = 0; d < 16; ++d) { ok[E + d] = dk[d]; ok[2 * E + d] = dv[d]; }
 }
 
+// strided (NCHW / NHWC, fp32 / bf16) -> dense bf16 channels-last with the channel pitch padded to Cpad
+__global__ void __launch_bounds__(256) k_to_bf16_nhwc(const void* __restrict__ src, int dtype, long long sN, long long sY,
+                                                      long long sX, long long sC, int H, int W, int C, int Cpad,
+                                                      long total, __nv_bfloat16* __restrict__ dst) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    long r = i / Cpad;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H);
+    const long n = r / H;
+    const float v = c < C ? ld_any(src, dtype, n * sN + (long long)y * sY + (long long)x * sX + (long long)c * sC) : 0.f;
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
 inline void colsum_geom(int C, dim3& block, int& CT) {
   CT = 1;
   while (CT < C && CT < 64) CT <<= 1;
@@ -661,4 +677,13 @@ extern "C" int ffsr_token_attention_backward(const float* qkv, const float* prob
     k_tokattn_bwd_kv<9><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, probs, ds_scratch, dctx, B, HW, E, dqkv, drop_p, seed);
   }
   return ffsr_check_launch("token_attention_backward");
+}
+
+extern "C" int ffsr_to_bf16_nhwc(const void* src, int src_dtype, long long sN, long long sY, long long sX, long long sC,
+                                 int N, int H, int W, int C, int Cpad, void* dst, cudaStream_t stream) {
+  FFSR_REQUIRE(src && dst && N > 0 && H > 0 && W > 0 && C > 0 && Cpad >= C, FFSR_ERR_ARG, "to_bf16_nhwc: bad argument");
+  const long total = (long)N * H * W * Cpad;
+  k_to_bf16_nhwc<<<(int)min((long)148 * 16, (total + 255) / 256), 256, 0, stream>>>(src, src_dtype, sN, sY, sX, sC, H, W, C,
+                                                                                     Cpad, total, (__nv_bfloat16*)dst);
+  return ffsr_check_launch("to_bf16_nhwc");
 }

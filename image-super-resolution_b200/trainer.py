@@ -1,0 +1,185 @@
+"""Data-parallel training step of the fusion network: flat parameter / gradient buckets, ONE
+NCCL all-reduce per optimizer step, fused clip + AdamW + EMA kernel.
+
+Mirrors the reference's cached training loop (``train.py:300-357``: forward_with_precomputed ->
+clamp -> criterion -> backward -> clip_grad_norm_(1.0) -> AdamW.step -> EMA.update) with the
+per-tensor ATen loops replaced by two kernels over a flat bucket (``csrc/optim.cu``) and, under
+``torchrun``, one ``ncclAllReduce`` of the 1,433,217-float gradient bucket over NVLink/NVSwitch
+(the reference has no DDP; an N-rank step equals its own ``accumulation_steps=N`` run over
+the same N micro-batches, including per-micro-batch BatchNorm statistics).
+
+``FusedAdamW`` is a ``torch.optim.Optimizer`` so LR schedulers and ``optimizer.state_dict()`` keep
+working in an unchanged ``train.py``; parameters stay ordinary leaf ``nn.Parameter``s whose storage
+is re-pointed into the flat bucket.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi as K
+
+
+class FlatBucket:
+    """Flattens tensors into one contiguous fp32 buffer and re-points them at views of it."""
+
+    def __init__(self, tensors: List[torch.Tensor], align: int = 4):
+        self.shapes = [tuple(t.shape) for t in tensors]
+        self.offsets, off = [], 0
+        for t in tensors:
+            self.offsets.append(off)
+            off += (t.numel() + align - 1) // align * align
+        self.numel = off
+        dev = tensors[0].device if tensors else torch.device("cpu")
+        self.flat = torch.zeros(self.numel, device=dev, dtype=torch.float32)
+        for t, o in zip(tensors, self.offsets):
+            self.flat[o:o + t.numel()].view(t.shape).copy_(t.detach())
+
+    def view(self, i: int) -> torch.Tensor:
+        o, s = self.offsets[i], self.shapes[i]
+        n = 1
+        for d in s:
+            n *= d
+        return self.flat[o:o + n].view(s)
+
+    def new_like(self) -> torch.Tensor:
+        return torch.zeros_like(self.flat)
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def allreduce_mean_(flat: torch.Tensor) -> None:
+    """In-place mean over ranks (sum + scale; gloo has no AVG)."""
+    w = _world()
+    if w > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.mul_(1.0 / w)
+
+
+def sync_bn_buffers(model: torch.nn.Module) -> None:
+    """Per-rank BatchNorm statistics (no SyncBN in the reference); the running buffers are
+    mean-all-reduced so every rank checkpoints the same state."""
+    if _world() == 1:
+        return
+    bufs = [b for n, b in model.named_buffers() if n.endswith("running_mean") or n.endswith("running_var")]
+    if not bufs:
+        return
+    flat = torch.cat([b.reshape(-1) for b in bufs])
+    allreduce_mean_(flat)
+    o = 0
+    for b in bufs:
+        b.copy_(flat[o:o + b.numel()].view_as(b))
+        o += b.numel()
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """AdamW over a flat bucket with optional fused global-norm clipping, data-parallel gradient
+    all-reduce and EMA shadow update (one kernel pass: csrc/optim.cu)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-4, max_grad_norm: float = 0.0, ema_decay: Optional[float] = None):
+        params = [p for p in params if p.requires_grad]
+        if not params:
+            raise ValueError("FusedAdamW got no trainable parameters")
+        if not all(p.is_cuda and p.dtype == torch.float32 for p in params):
+            raise RuntimeError("FusedAdamW (sm_100a build) needs fp32 CUDA parameters: there is no CPU path")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.lib = K.load()
+        self.max_grad_norm = float(max_grad_norm)
+        self.ema_decay = ema_decay
+        self._params = params
+        self.bucket = FlatBucket(params)
+        self.grads = self.bucket.new_like()
+        self.exp_avg = self.bucket.new_like()
+        self.exp_avg_sq = self.bucket.new_like()
+        self.ema = self.bucket.flat.clone() if ema_decay is not None else None
+        self._gsq = torch.zeros(1, device=self.bucket.flat.device, dtype=torch.float64)
+        self.steps = 0
+        for i, p in enumerate(params):
+            p.data = self.bucket.view(i)                       # same values, storage now inside the bucket
+            o = self.bucket.offsets[i]
+            p.grad = self.grads[o:o + p.numel()].view(p.shape)  # autograd accumulates in place into the bucket
+
+    # -- torch.optim API -------------------------------------------------------------------
+    def zero_grad(self, set_to_none: bool = False):
+        self.grads.zero_()
+        for i, p in enumerate(self._params):                   # re-attach if a caller set .grad = None
+            if p.grad is None or p.grad.data_ptr() != self.grads.data_ptr() + 4 * self.bucket.offsets[i]:
+                o = self.bucket.offsets[i]
+                p.grad = self.grads[o:o + p.numel()].view(p.shape)
+
+    def _gather_stray_grads(self):
+        for i, p in enumerate(self._params):
+            o = self.bucket.offsets[i]
+            if p.grad is not None and p.grad.data_ptr() != self.grads.data_ptr() + 4 * o:
+                self.grads[o:o + p.numel()].view(p.shape).copy_(p.grad)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        self._gather_stray_grads()
+        g = self.param_groups[0]
+        world = _world()
+        if world > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)   # ONE collective: the flat 5.7 MB gradient bucket
+        self.steps += 1
+        dev = self.bucket.flat.device
+        with torch.cuda.device(dev):
+            S = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            n = self.bucket.numel
+            gsq = None
+            if self.max_grad_norm > 0:
+                self._gsq.zero_()
+                K.check(self.lib.ffsr_sumsq(self.grads.data_ptr(), n, self._gsq.data_ptr(), S), "sumsq")
+                gsq = self._gsq.data_ptr()
+            K.check(self.lib.ffsr_adamw_ema_step(
+                self.bucket.flat.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                self.ema.data_ptr() if self.ema is not None else None, n, float(g["lr"]), float(g["betas"][0]),
+                float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self.steps, gsq, 1.0 / world,
+                self.max_grad_norm, float(self.ema_decay or 0.0), S), "adamw_ema_step")
+        for p in self._params:                                  # the kernel wrote through raw pointers: tell the
+            torch.autograd.graph.increment_version(p)           # version-keyed weight caches (pipeline.py) about it
+        return loss
+
+    # -- extras ----------------------------------------------------------------------------
+    def grad_norm(self) -> torch.Tensor:
+        """Global gradient norm seen by the last step (device scalar, no sync)."""
+        return self._gsq.sqrt() / _world()
+
+    def ema_shadow(self, names: List[str]) -> Dict[str, torch.Tensor]:
+        """EMAModel.shadow-compatible dict (checkpoint_manager.py:344-350): name -> view of the flat shadow."""
+        if self.ema is None:
+            raise RuntimeError("EMA is disabled (ema_decay=None)")
+        out = {}
+        for i, nme in enumerate(names):
+            o, s = self.bucket.offsets[i], self.bucket.shapes[i]
+            out[nme] = self.ema[o:o + self._params[i].numel()].view(s)
+        return out
+
+
+class FusionTrainer:
+    """One data-parallel training step (BASELINE configs[1] / configs[3])."""
+
+    def __init__(self, model, criterion, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-4, max_grad_norm: float = 1.0, ema_decay: Optional[float] = 0.999):
+        self.model, self.criterion = model, criterion
+        self.names = [n for n, p in model.named_parameters() if p.requires_grad]
+        self.optimizer = FusedAdamW(model.parameters(), lr, betas, eps, weight_decay, max_grad_norm, ema_decay)
+        self.optimizer.zero_grad()
+
+    def step(self, lr_img, expert_imgs, expert_feats, hr_img):
+        """forward -> clamp -> loss -> backward -> all-reduce -> clip + AdamW + EMA.  Returns the
+        (device) loss and its components; nothing here synchronises the host."""
+        self.model.train()
+        sr = self.model.forward_with_precomputed(lr_img, expert_imgs, expert_feats).clamp(0, 1)   # train.py:326
+        loss, comps = self.criterion(sr, hr_img, return_components=True)
+        loss.backward()
+        self.optimizer.step()
+        sync_bn_buffers(self.model)
+        self.optimizer.zero_grad()
+        return loss.detach(), comps

@@ -154,14 +154,120 @@ class _Conv2d(torch.autograd.Function):
         return dx, dw, db
 
 
-def conv2d(x, weight, bias=None):
+# ---- tcgen05 path: bf16 operands (channel pitch padded to 8 for TMA), fp32 accumulation --------------
+def _bf16_operand(x: torch.Tensor):
+    """-> (buffer [N,H,W,Cpad] bf16 contiguous, C).  Zero-copy when x already is bf16 channels-last with a
+    16-byte-multiple pixel pitch; otherwise one cast/pad kernel."""
+    N, Cc, H, W = x.shape
+    if x.dtype == torch.bfloat16 and x.stride(1) == 1 and Cc > 1:
+        sN, sY, sX = x.stride(0), x.stride(2), x.stride(3)
+        if sX % 8 == 0 and sX >= Cc and sY == W * sX and sN == H * W * sX and x.data_ptr() % 16 == 0:
+            return torch.as_strided(x, (N, H, W, sX), (sN, sY, sX, 1)), Cc
+    cpad = (Cc + 7) // 8 * 8
+    buf = torch.empty(N, H, W, cpad, device=x.device, dtype=torch.bfloat16)
+    sC = x.stride(1) if Cc > 1 else 1
+    _ck(_lib().ffsr_to_bf16_nhwc(x.data_ptr(), _dt(x), x.stride(0), x.stride(2), x.stride(3), sC, N, H, W, Cc, cpad,
+                                 buf.data_ptr(), _S(x)), "to_bf16_nhwc")
+    return buf, Cc
+
+
+def _pack_tc(wp: torch.Tensor) -> torch.Tensor:
+    """[taps][Cin][Cout] fp32 -> [taps][CoutPad][CinPad] bf16 K-major (layout of ffsr_conv2d's tcgen05 path)."""
+    taps, ci, co = wp.shape
+    cip = (ci + 63) // 64 * 64
+    cop = (co + 15) // 16 * 16
+    if cop > 128:
+        cop = (cop + 127) // 128 * 128
+    out = torch.zeros(taps, cop, cip, device=wp.device, dtype=torch.bfloat16)
+    out[:, :co, :ci] = wp.transpose(1, 2)
+    return out
+
+
+def _launch_conv_tc(xb: torch.Tensor, Cin: int, wtc: torch.Tensor, bias, out: torch.Tensor, ks: int):
+    """xb: [N,H,W,Cpad] bf16; out: channels-last [N,Cout,H,W] fp32 or bf16."""
+    N, H, W, cpad = xb.shape
+    Cout = out.shape[1]
+    p = K.ConvParams()
+    p.inp = xb.data_ptr()
+    p.in_sN, p.in_sY, p.in_sX, p.in_sC = H * W * cpad, W * cpad, cpad, 1
+    p.N, p.H, p.W, p.Cin, p.Cout, p.ksize = N, H, W, Cin, Cout, ks
+    p.w = wtc.data_ptr()
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.groups = 1
+    p.out = out.data_ptr()
+    p.out_sN, p.out_sY, p.out_sX = H * W * Cout, W * Cout, Cout
+    p.act, p.epi = K.ACT_NONE, K.EPI_PLAIN
+    p.sa = p.sb = 1.0
+    p.in_dtype, p.w_dtype = K.DT_BF16, K.DT_BF16
+    p.out_dtype = _dt(out)
+    _ck(_lib().ffsr_conv2d(C.byref(p), _S(xb)), "conv2d(tc)")
+
+
+class _Conv2dTC(torch.autograd.Function):
+    """nn.Conv2d on the tcgen05 kernels: forward and input gradient through ffsr_conv2d's bf16 path,
+    weight gradient through ffsr_conv2d_wgrad_tc.  Master weights / weight gradients stay fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_bf16):
+        co, ci, kh, kw = weight.shape
+        assert kh == kw and kh in (1, 3) and x.shape[1] == ci, (tuple(weight.shape), tuple(x.shape))
+        xb, _ = _bf16_operand(x)
+        N, _, H, W = x.shape
+        wtc = _pack_tc(weight.detach().permute(2, 3, 1, 0).reshape(kh * kw, ci, co))
+        out = _empty_cl(N, co, H, W, x.device, torch.bfloat16 if out_bf16 else torch.float32)
+        b = bias.detach().float().contiguous() if bias is not None else None
+        _launch_conv_tc(xb, ci, wtc, b, out, kh)
+        ctx.save_for_backward(xb, weight)
+        ctx.has_bias = bias is not None
+        ctx.x_dtype = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, weight = ctx.saved_tensors
+        co, ci, kh, kw = weight.shape
+        N, H, W, cpad = xb.shape
+        gb, _ = _bf16_operand(gy)
+        gpad = gb.shape[3]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wr = _pack_tc(weight.detach().flip(2, 3).permute(2, 3, 0, 1).reshape(kh * kw, co, ci))
+            dx = _empty_cl(N, ci, H, W, xb.device, ctx.x_dtype if ctx.x_dtype == torch.bfloat16 else torch.float32)
+            _launch_conv_tc(gb, co, wr, None, dx, kh)
+        dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            lib = _lib()
+            dwp = _zeros((kh * kw, ci, co), xb.device)
+            dbp = _zeros((co,), xb.device) if ctx.has_bias else None
+            p = K.WgradParams()
+            p.x = xb.data_ptr()
+            p.x_sN, p.x_sY, p.x_sX, p.x_sC = H * W * cpad, W * cpad, cpad, 1
+            p.x_dtype = K.DT_BF16
+            p.dy = gb.data_ptr()
+            p.dy_sN, p.dy_sY, p.dy_sX = H * W * gpad, W * gpad, gpad
+            p.dy_dtype = K.DT_BF16
+            p.N, p.H, p.W, p.Cin, p.Cout, p.ksize = N, H, W, ci, co, kh
+            p.dw = dwp.data_ptr()
+            p.dbias = dbp.data_ptr() if dbp is not None else None
+            nb = lib.ffsr_conv2d_wgrad_tc_workspace_bytes(N, H, W, ci, co, kh)
+            ws = torch.empty(nb, device=xb.device, dtype=torch.uint8)
+            _ck(lib.ffsr_conv2d_wgrad_tc(C.byref(p), ws.data_ptr(), nb, _S(xb)), "conv2d_wgrad_tc")
+            dw = dwp.view(kh, kw, ci, co).permute(3, 2, 0, 1)
+            db = dbp
+        return dx, dw, db, None
+
+
+def conv2d(x, weight, bias=None, tc: bool = False, out_bf16: bool = False):
+    """tc=False: fp32 CUDA-core kernels; tc=True: tcgen05 kernels (bf16 operands), output fp32 or bf16."""
     if weight.dim() == 2:                      # nn.Linear weight [out, in] == 1x1 conv
         weight = weight[:, :, None, None]
+    if tc:
+        return _Conv2dTC.apply(x, weight, bias, out_bf16)
     return _Conv2d.apply(x, weight, bias)
 
 
-def conv_mod(x, mod):
-    return conv2d(x, mod.weight, mod.bias)
+def conv_mod(x, mod, tc: bool = False, out_bf16: bool = False):
+    return conv2d(x, mod.weight, mod.bias, tc, out_bf16)
 
 
 # --------------------------------------------------------------------------------------
@@ -346,13 +452,13 @@ def _draw_seed() -> int:
     return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 
-def mha_tokens(x, mha: torch.nn.MultiheadAttention, B: int, T: int, training: bool):
+def mha_tokens(x, mha: torch.nn.MultiheadAttention, B: int, T: int, training: bool, tc: bool = False):
     """nn.MultiheadAttention self-attention over the T tokens of every LR pixel.
     x: [B*T, E, H, W] channels-last token-major.  (large_kernel_attention.py:192-197, 294-299)"""
-    qkv = conv2d(x, mha.in_proj_weight, mha.in_proj_bias)
+    qkv = conv2d(x, mha.in_proj_weight, mha.in_proj_bias, tc)
     p = float(mha.dropout) if training else 0.0
     ctx = _TokenAttention.apply(qkv, B, T, p, _draw_seed() if p > 0 else 0)
-    return conv2d(ctx, mha.out_proj.weight, mha.out_proj.bias)
+    return conv2d(ctx, mha.out_proj.weight, mha.out_proj.bias, tc)
 
 
 # --------------------------------------------------------------------------------------
@@ -396,19 +502,19 @@ class _DwStage(torch.autograd.Function):
 # --------------------------------------------------------------------------------------
 # LKABlock (large_kernel_attention.py:92-105, 143-149), train mode, G statistic groups
 # --------------------------------------------------------------------------------------
-def lka_block_train(x, blk, G: int, sink: list, stats_only: bool = False):
+def lka_block_train(x, blk, G: int, sink: list, stats_only: bool = False, tc: bool = False):
     n = batchnorm_train(x, blk.norm1, G, sink)
     a = _DwStage.apply(n, blk.lka.local_conv.weight, 0)
     a = _DwStage.apply(a, blk.lka.h_conv.weight, 1)
     a = _DwStage.apply(a, blk.lka.v_conv.weight, 2)
-    a = conv2d(a, blk.lka.pw_conv.weight, None)
+    a = conv2d(a, blk.lka.pw_conv.weight, None, tc)
     a = sigmoid(batchnorm_train(a, blk.lka.bn, G, sink))
     x1 = x + blk.scale1 * (n * a)
     h = batchnorm_train(x1, blk.norm2, G, sink)
     if stats_only:
         return None
-    h = gelu(conv_mod(h, blk.ffn[0]))
-    h = conv_mod(h, blk.ffn[2])
+    h = gelu(conv_mod(h, blk.ffn[0], tc))
+    h = conv_mod(h, blk.ffn[2], tc)
     return x1 + blk.scale2 * h
 
 
@@ -490,6 +596,17 @@ def _train_forward(m, lr, img_list, feats, want_inter):
     training = m.training
     sink: list = []
     inter: Dict = {}
+    if m.precision not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {m.precision!r}")
+    # bf16 mode: tcgen05 kernels for the contractions of phases 4/5/7 (bf16 operands, fp32 accumulate, HR feature
+    # maps stored bf16); phases 2/3/6 and every residual / image stream stay fp32 like the eval path
+    tc = m.precision == "bf16"
+
+    def cv(x, mod, lp_out=False):
+        return conv_mod(x, mod, tc, tc and lp_out)
+
+    def cw(x, weight, bias=None, lp_out=False):
+        return conv2d(x, weight, bias, tc, tc and lp_out)
 
     # ---------------- Phase 2 ----------------
     raw9 = _phase2_train(m, lr)                                           # [B,9,3,H,W]
@@ -537,7 +654,7 @@ def _train_forward(m, lr, img_list, feats, want_inter):
                 f = f[:, :cin_w]
             elif f.shape[1] < cin_w:
                 wgt = wgt[:, :f.shape[1]]                                  # zero-padded channels contribute nothing
-            aligned.append(conv2d(f, wgt, al.bias))
+            aligned.append(cw(f, wgt, al.bias))
         E = co.norm1.weight.shape[0]
         zero = None
         rows = []
@@ -549,17 +666,17 @@ def _train_forward(m, lr, img_list, feats, want_inter):
             else:
                 rows.append(a.permute(0, 2, 3, 1))
         tokens = torch.stack(rows, dim=1).reshape(B * 4, H, W, E).permute(0, 3, 1, 2)   # token-major, channels-last
-        x = tokens + mha_tokens(layernorm(tokens, co.norm1), co.cross_attn, B, 4, training)
-        hdn = gelu(conv2d(layernorm(x, co.norm2), co.ffn[0].weight, co.ffn[0].bias))
-        x = x + conv2d(hdn, co.ffn[2].weight, co.ffn[2].bias)
-        xg = lka_block_train(_to_group_major(x, B, 4), co.lka_global, 4, sink)             # [4*B,128,H,W]
+        x = tokens + mha_tokens(layernorm(tokens, co.norm1), co.cross_attn, B, 4, training, tc)
+        hdn = gelu(cw(layernorm(x, co.norm2), co.ffn[0].weight, co.ffn[0].bias))
+        x = x + cw(hdn, co.ffn[2].weight, co.ffn[2].bias)
+        xg = lka_block_train(_to_group_major(x, B, 4), co.lka_global, 4, sink, tc=tc)      # [4*B,128,H,W]
         ecol = []
         for i in range(4):
             mod = co.modulation[i]
             f_i = xg[i * B:(i + 1) * B]
-            m32 = conv_mod(f_i, mod[0])                       # 1x1 conv commutes with the bilinear upsampling
+            m32 = cv(f_i, mod[0])                             # 1x1 conv commutes with the bilinear upsampling
             up = gelu(_bilinear(m32, (Hh, Wh)))
-            mk = sigmoid(conv_mod(up, mod[2]))
+            mk = sigmoid(cv(up, mod[2]))
             o = imgs[i] * (1.0 + 0.2 * (mk - 0.5))
             if not training:
                 o = o.clamp(0, 1)
@@ -572,27 +689,27 @@ def _train_forward(m, lr, img_list, feats, want_inter):
     stack = torch.cat(ecol, dim=1)                                          # [B,12,Hh,Wh]
 
     def stage(xin, name):
-        cv = getattr(mr, name + "_conv")
-        y = gelu(conv_mod(xin, cv[0]))
-        y = gelu(conv_mod(y, cv[2]))
+        cvs = getattr(mr, name + "_conv")
+        y = gelu(cv(xin, cvs[0], True))
+        y = gelu(cv(y, cvs[2], True))
         gate = getattr(mr, name + "_gate").gate
-        y = y * sigmoid(conv_mod(gelu(conv_mod(y, gate[0])), gate[2]))
+        y = y * sigmoid(cv(gelu(cv(y, gate[0], True)), gate[2])).to(y.dtype)
         res = getattr(mr, name + "_res")
-        r = conv2d(gelu(conv2d(y, res.block[0].weight, None)), res.block[2].weight, None)
+        r = cw(gelu(cw(y, res.block[0].weight, None, True)), res.block[2].weight, None, True)
         return y + res.scale * r
 
     f1 = stage(_bilinear(stack, (H, W)), "stage1")
     f1u = _bilinear(f1, (2 * H, 2 * W))
-    f2 = stage(torch.cat([f1u, _bilinear(stack, (2 * H, 2 * W))], dim=1), "stage2")
+    f2 = stage(torch.cat([f1u, _bilinear(stack, (2 * H, 2 * W)).to(f1u.dtype)], dim=1), "stage2")
     f2 = f2 + mr.residual_weight_1_2 * f1u
     f2u = _bilinear(f2, (Hh, Wh))
-    f3 = stage(torch.cat([f2u, stack], dim=1), "stage3")
+    f3 = stage(torch.cat([f2u, stack.to(f2u.dtype)], dim=1), "stage3")
     f3 = f3 + mr.residual_weight_2_3 * f2u[:, :f3.shape[1]]
-    hier = sigmoid(conv_mod(gelu(conv_mod(f3, mr.to_rgb[0])), mr.to_rgb[2]))
+    hier = sigmoid(cv(gelu(cv(f3, mr.to_rgb[0], True)), mr.to_rgb[2]))
 
     # ---------------- Phase 5b / 6 blend ----------------
     r_hr = _bilinear(routing, (Hh, Wh))
-    fl = conv_mod(gelu(conv_mod(r_hr, m.freq_weight_conv[0])), m.freq_weight_conv[2])
+    fl = cv(gelu(cv(r_hr, m.freq_weight_conv[0])), m.freq_weight_conv[2])
     fw = torch.softmax(fl, dim=1)
     freq = sum(o * fw[:, i:i + 1] for i, o in enumerate(ecol))
     fused = hier * 0.7 + freq * 0.3
@@ -606,8 +723,8 @@ def _train_forward(m, lr, img_list, feats, want_inter):
     # ---------------- Phase 7a ----------------
     convs = [l for l in m.refine if isinstance(l, torch.nn.Conv2d)]
     y = fused
-    for j, cv in enumerate(convs):
-        y = conv_mod(y, cv)
+    for j, layer in enumerate(convs):
+        y = cv(y, layer, j < len(convs) - 1)
         if j < len(convs) - 1:
             y = gelu(y)
     fused = fused + 0.1 * y
@@ -628,17 +745,17 @@ def _train_forward(m, lr, img_list, feats, want_inter):
     fl_ = []
     for lv, lap in enumerate(pyr):
         r = ee.edge_refiners[lv]
-        idt = conv_mod(lap, r.proj)
-        o = gelu(conv_mod(lap, r.conv1))
-        o = gelu(conv_mod(o, r.conv2))
-        o = conv_mod(o, r.conv3) + idt
-        a = sigmoid(conv_mod(gelu(conv_mod(o, r.attn.attn[0])), r.attn.attn[2]))
-        f = o * a
+        idt = cv(lap, r.proj, True)
+        o = gelu(cv(lap, r.conv1, True))
+        o = gelu(cv(o, r.conv2, True))
+        o = cv(o, r.conv3, True) + idt
+        a = sigmoid(cv(gelu(cv(o, r.attn.attn[0], True)), r.attn.attn[2]))
+        f = o * a.to(o.dtype)
         if f.shape[2:] != (Hh, Wh):
             f = _bilinear(f, (Hh, Wh))
         fl_.append(f * lw[lv])
-    e = conv_mod(gelu(conv_mod(torch.cat(fl_, dim=1), ee.fusion[0])), ee.fusion[2])
-    gte = sigmoid(conv_mod(gelu(conv_mod(torch.cat([fused, e], dim=1), ee.edge_gate[0])), ee.edge_gate[2]))
+    e = cv(gelu(cv(torch.cat(fl_, dim=1), ee.fusion[0], True)), ee.fusion[2])
+    gte = sigmoid(cv(gelu(cv(torch.cat([fused, e], dim=1), ee.edge_gate[0], True)), ee.edge_gate[2]))
     fused = (fused + gte * ee.edge_strength * e).clamp(0, 1)
 
     # ---------------- output ----------------

@@ -252,6 +252,48 @@ int ffsr_dwconv_stage(const float* in, int N, int H, int W, int C, int kind, con
 int ffsr_dwconv_wgrad(const float* in, const float* g, int N, int H, int W, int C, int kind, float* dw,
                       cudaStream_t stream);
 
+/* ---- fused training losses (forward value + gradient w.r.t. pred in one pass) --------------
+ * pred / target / dpred: [P][H][W] fp32 planes (P = B*C of an NCHW-contiguous tensor).
+ * Each call ADDS its partial sums into the fp64 accumulators and ADDS gscale * dLoss/dPred into
+ * dpred (the caller zeroes both); gscale = loss weight / element count (see losses.py).
+ *   ffsr_loss_l1    L1Loss        src/losses/perceptual_loss.py:86-104      sum[0] = sum |p-t|
+ *   ffsr_loss_swt   SWTLoss       :661-733, 797-813   sums8 = sum|cA|,|cH|,|cV|,|cD| for level 0 then level 1
+ *   ffsr_loss_ssim  SSIMLoss      :225-291            sum[0] = sum of the SSIM map
+ *   ffsr_loss_fft   FFTLoss       :533-598            sums2 = sum w*||P|-|T||, sum w*|angle P - angle T|
+ *                   (H, W must factor into 2,3,5,7: training patches are 256 / 384) */
+int ffsr_loss_l1(const float* pred, const float* target, long n, float gscale, double* sum, float* dpred,
+                 cudaStream_t stream);
+size_t ffsr_loss_swt_workspace_bytes(int P, int H, int W);
+int ffsr_loss_swt(const float* pred, const float* target, int P, int H, int W, float gscale, double* sums8, void* ws,
+                  size_t ws_bytes, float* dpred, cudaStream_t stream);
+size_t ffsr_loss_ssim_workspace_bytes(int P, int H, int W);
+int ffsr_loss_ssim(const float* pred, const float* target, int P, int H, int W, float gscale, double* sum, void* ws,
+                   size_t ws_bytes, float* dpred, cudaStream_t stream);
+size_t ffsr_loss_fft_workspace_bytes(int P, int H, int W);
+int ffsr_loss_fft(const float* pred, const float* target, int P, int H, int W, float gscale, double* sums2, void* ws,
+                  size_t ws_bytes, float* dpred, cudaStream_t stream);
+
+/* ---- fused optimizer step over a flat fp32 bucket ------------------------------------------
+ * ffsr_sumsq: out[0] += sum g^2 (fp64) -- the global gradient norm of clip_grad_norm_ (train.py:344-348)
+ * ffsr_adamw_ema_step: g' = g*grad_scale*min(1, max_norm/(grad_scale*sqrt(*gsumsq)+1e-6)) (no clipping when
+ *   gsumsq is NULL or max_norm <= 0); torch.optim.AdamW update with bias correction for `step` (1-based)
+ *   (train.py:847-853); ema = decay*ema + (1-decay)*p (checkpoint_manager.py:352-359; ema may be NULL). */
+int ffsr_sumsq(const float* g, long n, double* out, cudaStream_t stream);
+int ffsr_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, long n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, int step, const double* gsumsq, float grad_scale,
+                        float max_norm, float ema_decay, cudaStream_t stream);
+
+/* ---- bf16 / tcgen05 training path ------------------------------------------------------------
+ * ffsr_to_bf16_nhwc: strided fp32/bf16 view (NCHW or NHWC) -> dense bf16 channels-last with the channel
+ *   pitch padded to Cpad (zeros), the operand format of the TMA-fed tensor-core kernels.
+ * ffsr_conv2d_wgrad_tc: same contract as ffsr_conv2d_wgrad for bf16 channels-last x / dy whose strides are
+ *   multiples of 16 bytes; tcgen05 MMAs with both operands MN-major (no transposed copies), per-CTA partial
+ *   results in `ws` (ffsr_conv2d_wgrad_tc_workspace_bytes) reduced deterministically into dw. */
+int ffsr_to_bf16_nhwc(const void* src, int src_dtype, long long sN, long long sY, long long sX, long long sC, int N,
+                      int H, int W, int C, int Cpad, void* dst, cudaStream_t stream);
+size_t ffsr_conv2d_wgrad_tc_workspace_bytes(int N, int H, int W, int Cin, int Cout, int ksize);
+int ffsr_conv2d_wgrad_tc(const ffsr_wgrad_params* p, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

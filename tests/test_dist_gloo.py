@@ -52,3 +52,61 @@ def test_shard_edge_cases():
     assert D.shard_indices(3, 3, 8) == []                                     # more ranks than images
     assert D.shard(list("abcde"), 1, 2) == ["b", "d"]
     assert D.max_over_ranks(3.5) == 3.5                                       # no process group: identity
+
+
+def _train_worker(rank, world, port, out):
+    """N-rank flat-bucket step == single-process gradient accumulation over the same N micro-batches
+    (what the reference's accumulation_steps does, train.py:331-357).  CPU tensors + gloo: exercises
+    FlatBucket / allreduce_mean_ / sync_bn_buffers, the host logic of the NCCL path."""
+    sys.path.insert(0, ROOT)
+    import isr_b200  # noqa: F401
+    from isr_b200.trainer import FlatBucket, allreduce_mean_, sync_bn_buffers
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.BatchNorm2d(8), torch.nn.ReLU(),
+                              torch.nn.Conv2d(8, 3, 1))
+    g = torch.Generator().manual_seed(42)
+    xs = [torch.randn(2, 3, 8, 8, generator=g) for _ in range(world)]
+    params = list(net.parameters())
+    bucket = FlatBucket(params)
+    grads = bucket.new_like()
+    for i, p in enumerate(params):
+        p.data = bucket.view(i)
+        o = bucket.offsets[i]
+        p.grad = grads[o:o + p.numel()].view(p.shape)
+    net(xs[rank]).square().mean().backward()
+    assert params[0].grad.data_ptr() == grads.data_ptr()            # autograd accumulated in place into the bucket
+    allreduce_mean_(grads)
+    sync_bn_buffers(net)
+    if rank == 0:
+        out.put((grads.clone(), net[1].running_mean.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_equals_gradient_accumulation_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 2
+    procs = [ctx.Process(target=_train_worker, args=(r, world, 29643, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    grads, rmean = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference: accumulate loss/world over the same micro-batches
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.BatchNorm2d(8), torch.nn.ReLU(),
+                              torch.nn.Conv2d(8, 3, 1))
+    g = torch.Generator().manual_seed(42)
+    xs = [torch.randn(2, 3, 8, 8, generator=g) for _ in range(world)]
+    rms = []
+    for x in xs:
+        net[1].running_mean.zero_()
+        (net(x).square().mean() / world).backward()
+        rms.append(net[1].running_mean.clone())
+    ref = torch.cat([torch.nn.functional.pad(p.grad.reshape(-1), (0, (-p.numel()) % 4)) for p in net.parameters()])
+    assert torch.allclose(grads, ref, atol=1e-7)
+    assert torch.allclose(rmean, sum(rms) / world, atol=1e-7)

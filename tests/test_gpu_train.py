@@ -217,13 +217,17 @@ def test_train_forward_backward_matches_oracle_autograd(B, H, W, with_feats):
     sd0 = {k: v.clone() for k, v in m.state_dict().items()}
     lr, imgs, fts, hr = O.synthetic_inputs(B, H, W, feats=with_feats)
 
-    # oracle: fp32 autograd on the CPU
-    sd = {k: (v.clone().requires_grad_() if v.is_floating_point() and k in dict(m.named_parameters()) else v.clone())
+    # oracle: fp64 autograd on the CPU (an fp32 reference would add its own ~1e-5 rounding noise to the
+    # gradients of the scalar scale parameters, which are sums of millions of cancelling terms)
+    pnames = dict(m.named_parameters())
+    sd = {k: (v.double().requires_grad_() if k in pnames else (v.double() if v.is_floating_point() else v.clone()))
           for k, v in sd0.items()}
     upd = {}
-    ref = O.run_pipeline(sd, lr, imgs, fts, training=True, bn_updates=upd)
-    loss_ref = ((ref - hr) ** 2).mean() * 100.0
+    d64 = lambda t: {k: v.double() for k, v in t.items()} if t else None
+    ref = O.run_pipeline(sd, lr.double(), d64(imgs), d64(fts), training=True, bn_updates=upd)
+    loss_ref = ((ref - hr.double()) ** 2).mean() * 100.0
     loss_ref.backward()
+    ref = ref.float()
 
     m.to(dev)
     out = m.forward_with_precomputed(lr.to(dev), {k: v.to(dev) for k, v in imgs.items()},
@@ -247,7 +251,9 @@ def test_train_forward_backward_matches_oracle_autograd(B, H, W, with_feats):
         r = err / denom if denom > 1e-12 else err
         if r > worst[0]:
             worst = (r, name)
-        assert r <= 1e-4, f"{name}: rel-L2 {r:.3e} (|g_ref| {denom:.3e})"
+        # absolute floor: the scalar scale parameters' gradients are cancelling sums of ~1e5 fp32 terms
+        # (|g| ~ 4e-5); 1e-8 absolute is the fp32 summation noise of such a reduction, not a kernel error
+        assert r <= 1e-4 or err <= 1e-8, f"{name}: rel-L2 {r:.3e} (|g_ref| {denom:.3e}, abs err {err:.3e})"
     if with_feats:
         assert n_params == 198
     # BatchNorm side effects
@@ -256,7 +262,7 @@ def test_train_forward_backward_matches_oracle_autograd(B, H, W, with_feats):
         if k.endswith("num_batches_tracked"):
             assert int(after[k]) == int(v), k
         else:
-            assert (after[k].cpu() - v).abs().max().item() <= 1e-6, k
+            assert (after[k].cpu().double() - v.double()).abs().max().item() <= 1e-6, k
     print(f"worst gradient rel-L2 {worst[0]:.2e} at {worst[1]}")
 
 
@@ -278,3 +284,135 @@ def test_train_step_with_dropout_runs_and_is_seeded():
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
     assert int(m.cross_band.lka_block.norm1.num_batches_tracked) == 27        # 3 forwards x 9 band calls
     assert int(m.collaborative.lka_global.norm1.num_batches_tracked) == 12    # 3 forwards x 4 expert calls
+
+
+# ------------------------------------------------------------------------------------------
+# fused optimizer / trainer
+# ------------------------------------------------------------------------------------------
+def test_fused_adamw_matches_torch_adamw_clip_ema():
+    from isr_b200.trainer import FusedAdamW
+    dev = _cuda()
+    g = torch.Generator().manual_seed(1)
+    shapes = [(64, 3, 3, 3), (64,), (128, 64, 1, 1), (), (7, 5)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, generator=g).to(dev)) for s in shapes]
+    new_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    opt_ref = torch.optim.AdamW(ref_p, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    opt_new = FusedAdamW(new_p, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_grad_norm=1.0, ema_decay=0.999)
+    shadow = [p.detach().clone() for p in ref_p]
+    for it in range(3):
+        grads = [torch.randn(s, generator=g).to(dev) * (3.0 if it == 0 else 0.01) for s in shapes]   # clipped, then not
+        for p, q, gr in zip(ref_p, new_p, grads):
+            p.grad = gr.clone()
+            q.grad.copy_(gr)
+        torch.nn.utils.clip_grad_norm_(ref_p, 1.0)
+        opt_ref.step()
+        shadow = [0.999 * s_ + (1 - 0.999) * p.detach() for s_, p in zip(shadow, ref_p)]      # EMAModel.update
+        opt_new.step()
+        opt_new.zero_grad()
+        if it == 1:
+            opt_new.param_groups[0]["lr"] = opt_ref.param_groups[0]["lr"] = 1e-4               # scheduler-style change
+    ema = opt_new.ema_shadow([str(i) for i in range(len(shapes))])
+    for i, (p, q) in enumerate(zip(ref_p, new_p)):
+        assert (p - q).abs().max().item() <= 2e-7, i
+        assert (shadow[i] - ema[str(i)]).abs().max().item() <= 2e-7, i
+        assert q.grad is not None and float(q.grad.abs().max()) == 0.0
+
+
+def test_trainer_step_reduces_loss_and_keeps_module_contract():
+    from isr_b200.trainer import FusionTrainer
+    from isr_b200.losses import CombinedLoss
+    dev = _cuda()
+    torch.manual_seed(0)
+    m = isr_b200.CompleteEnhancedFusionSR(None).to(dev)
+    crit = CombinedLoss()
+    crit.set_weights({"charbonnier": 0, "l2": 0, "vgg": 0, "edge": 0, "clip": 0, "l1": 0.6, "swt": 0.25, "fft": 0.1, "ssim": 0.05})
+    tr = FusionTrainer(m, crit, lr=2e-4)
+    lr, imgs, fts, hr = O.synthetic_inputs(2, 16, 16)
+    args = (lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()}, hr.to(dev))
+    keys_before = list(m.state_dict().keys())
+    losses = [float(tr.step(*args)[0]) for _ in range(6)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+    assert list(m.state_dict().keys()) == keys_before and len(keys_before) == 226
+    assert all(p.is_leaf and p.grad is not None for p in m.parameters())
+    # eval forward after training picks up the kernel-updated weights (version-keyed caches)
+    m.eval()
+    with torch.no_grad():
+        a = m.forward_with_precomputed(*args[:3])
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    ref = O.run_pipeline(sd, lr, imgs, fts)
+    assert (a.cpu() - ref).abs().max().item() <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------
+# bf16 / tcgen05 training path
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,ks,N,H,W", [
+    (128, 128, 3, 2, 24, 40), (64, 64, 3, 1, 19, 37), (76, 64, 3, 2, 16, 16), (3, 128, 3, 1, 33, 21),
+    (128, 3, 3, 2, 17, 16), (32, 32, 3, 1, 64, 64), (96, 32, 3, 1, 20, 28), (128, 384, 1, 3, 9, 11),
+    (256, 128, 1, 2, 12, 20), (180, 128, 1, 1, 24, 24), (12, 64, 3, 2, 8, 8), (16, 1, 3, 1, 40, 24),
+    (64, 32, 3, 1, 128, 128), (6, 16, 3, 1, 31, 47),
+])
+def test_tc_conv_forward_dgrad_wgrad(cin, cout, ks, N, H, W):
+    """tcgen05 forward / input-gradient / MN-major weight-gradient against torch on bf16-representable
+    operands (products exact in fp32, so only the accumulation order differs)."""
+    dev = _cuda()
+    g = torch.Generator().manual_seed(cin * 31 + cout * 5 + ks + H)
+    bf = lambda t: t.bfloat16().float()
+    x = bf(torch.randn(N, cin, H, W, generator=g))
+    w = bf(torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    gy = bf(torch.randn(N, cout, H, W, generator=g))
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    yr = F.conv2d(xr, wr, br, padding=ks // 2)
+    yr.backward(gy)
+    xd = x.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_()
+    wd, bd = w.to(dev).requires_grad_(), b.to(dev).requires_grad_()
+    y = T.conv2d(xd, wd, bd, tc=True, out_bf16=False)
+    y.backward(gy.to(dev))
+    torch.cuda.synchronize()
+    assert _rel(y, yr) < 1e-5
+    assert _rel(xd.grad, xr.grad) < 1e-5
+    assert _rel(wd.grad, wr.grad) < 1e-5, _rel(wd.grad, wr.grad)
+    assert _rel(bd.grad, br.grad) < 1e-5
+    # bf16 output variant + bf16 upstream gradient
+    xd2 = x.to(dev).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_()
+    y2 = T.conv2d(xd2, wd, bd, tc=True, out_bf16=True)
+    assert y2.dtype == torch.bfloat16 and _rel(y2.float(), yr) < 1e-2
+    y2.backward(gy.to(dev).bfloat16())
+    assert xd2.grad.dtype == torch.bfloat16 and _rel(xd2.grad.float(), xr.grad) < 1e-2
+
+
+def test_train_bf16_gradients_close_to_fp32_oracle():
+    """bf16 mode: loss within 1e-3 relative and every large gradient tensor within 5% rel-L2 /
+    cosine > 0.995 of the fp32 oracle (bf16 operand rounding, fp32 accumulation and master weights)."""
+    dev = _cuda()
+    m = _train_model()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    B, H, W = 2, 16, 16
+    lr, imgs, fts, hr = O.synthetic_inputs(B, H, W)
+    pn = dict(m.named_parameters())
+    sd = {k: (v.clone().requires_grad_() if k in pn else v.clone()) for k, v in sd0.items()}
+    ref = O.run_pipeline(sd, lr, imgs, fts, training=True, bn_updates={})
+    loss_ref = (ref - hr).abs().mean()
+    loss_ref.backward()
+    m.to(dev)
+    m.precision = "bf16"
+    out = m.forward_with_precomputed(lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()})
+    assert out.dtype == torch.float32
+    loss = (out - hr.to(dev)).abs().mean()
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-3 * float(loss_ref)
+    mse = float(((out.detach().cpu() - ref.detach()) ** 2).mean())
+    assert mse < 1e-5, mse                                             # > 50 dB between the two outputs
+    bad = []
+    for name, p in m.named_parameters():
+        g_ref = sd[name].grad
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        if g_ref.numel() < 256:
+            continue
+        a, b_ = p.grad.double().cpu().reshape(-1), g_ref.double().reshape(-1)
+        cos = float((a @ b_) / (a.norm() * b_.norm() + 1e-30))
+        rel = float((a - b_).norm() / (b_.norm() + 1e-30))
+        if cos < 0.995 or rel > 0.05:
+            bad.append((name, cos, rel))
+    assert not bad, bad[:8]

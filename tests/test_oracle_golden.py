@@ -89,3 +89,17 @@ def test_train_forward_and_bn_side_effects(golden_dir):
             assert int(upd[k]) == int(ref), k        # +9 (cross_band) / +4 (collaborative) per forward
         else:
             assert (upd[k] - ref).abs().max().item() <= 1e-6, k
+
+
+def test_loss_oracle_matches_reference_losses(golden_dir):
+    """oracle/loss_oracle.py against the values the reference's own L1Loss / SSIMLoss / FFTLoss /
+    SWTLoss classes produced (oracle/make_golden.py, losses_24x24.npz)."""
+    import numpy as np
+    from oracle import loss_oracle as L
+    d = np.load(os.path.join(golden_dir, "losses_24x24.npz"))
+    a, b = torch.from_numpy(d["pred"]), torch.from_numpy(d["target"])
+    for name, fn in L.LOSSES.items():
+        assert abs(float(fn(a, b)) - float(d[name])) <= 2e-7, name
+    total, comps = L.combined_loss(a, b, L.STAGE_WEIGHTS[3])
+    want = sum(L.STAGE_WEIGHTS[3][k] * float(d[k]) for k in L.STAGE_WEIGHTS[3])
+    assert abs(float(total) - want) <= 1e-6 and set(comps) == {"l1", "swt", "fft", "ssim"}
