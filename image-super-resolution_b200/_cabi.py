@@ -97,8 +97,8 @@ PROTOTYPES = {
     "ffsr_bn_stats": (_I, [_P, _I, _L, _I, _P, _P, _P]),
     "ffsr_bn_apply": (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _P, _P]),
     "ffsr_bn_backward": (_I, [_P, _P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P]),
-    "ffsr_token_attention_train": (_I, [_P, _I, _I, _L, _I, _P, _P, _F, _U64, _P]),
-    "ffsr_token_attention_backward": (_I, [_P, _P, _P, _I, _I, _L, _I, _P, _P, _F, _U64, _P]),
+    "ffsr_token_attention_train": (_I, [_P, _I, _I, _L, _I, _P, _P, _F, _U64, _P, _P]),
+    "ffsr_token_attention_backward": (_I, [_P, _P, _P, _I, _I, _L, _I, _P, _P, _F, _U64, _P, _P]),
     "ffsr_dwconv_stage": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ffsr_dwconv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     # ---- fused losses ----
@@ -115,7 +115,7 @@ PROTOTYPES = {
     "ffsr_conv2d_wgrad_tc": (_I, [C.POINTER(WgradParams), _P, _SZ, _P]),
     # ---- fused optimizer ----
     "ffsr_sumsq": (_I, [_P, _L, _P, _P]),
-    "ffsr_adamw_ema_step": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _F, _F, _P]),
+    "ffsr_adamw_ema_step": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _P, _P, _F, _F, _F, _P]),
 }
 
 _lib = None

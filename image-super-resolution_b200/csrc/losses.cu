@@ -481,9 +481,16 @@ extern "C" int ffsr_loss_fft(const float* pred, const float* target, int P, int 
   float2* Z = (float2*)ws;
   float2* G = Z + total;
   const size_t sm_rows = (size_t)2 * FFT_ROWS * W * sizeof(float2), sm_cols = (size_t)2 * FFT_ROWS * H * sizeof(float2);
-  cudaFuncSetAttribute(k_fft_rows<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rows);
-  cudaFuncSetAttribute(k_fft_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rows);
-  cudaFuncSetAttribute(k_fft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cols);
+  static size_t attr_rows = 0, attr_cols = 0;     // raise the opt-in shared-memory limit only when it has to grow
+  if (sm_rows > attr_rows) {
+    cudaFuncSetAttribute(k_fft_rows<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rows);
+    cudaFuncSetAttribute(k_fft_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rows);
+    attr_rows = sm_rows;
+  }
+  if (sm_cols > attr_cols) {
+    cudaFuncSetAttribute(k_fft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cols);
+    attr_cols = sm_cols;
+  }
   const long nrows = (long)P * H;
   const float sc_w = 1.0f / sqrtf((float)W), sc_h = 1.0f / sqrtf((float)H);
   k_fft_rows<0><<<(unsigned)ceil_div(nrows, FFT_ROWS), 256, sm_rows, stream>>>(pred, target, Z, nrows, W, rw, sc_w, nullptr);

@@ -33,22 +33,27 @@ __global__ void __launch_bounds__(256) k_sumsq(const float* __restrict__ g, long
 __global__ void __launch_bounds__(256) k_adamw_ema(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v,
                                                    float* __restrict__ ema, long n, float lr, float b1, float b2,
-                                                   float eps, float wd, float bc1, float bc2_sqrt,
+                                                   float eps, float wd, int step, const int* __restrict__ step_dev,
+                                                   const float* __restrict__ lr_dev,
                                                    const double* __restrict__ gsumsq, float grad_scale,
                                                    float max_norm, float ema_decay) {
+  if (step_dev) step += *step_dev;
+  if (lr_dev) lr = *lr_dev;
+  const float bc1 = 1.0f - (float)pow((double)b1, (double)step);
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)step));
   float clip = 1.0f;
   if (gsumsq && max_norm > 0.f) {
     const float norm = grad_scale * (float)sqrt(*gsumsq);
     clip = fminf(1.0f, max_norm / (norm + 1e-6f));
   }
   const float gs = grad_scale * clip;
-  const float step = lr / bc1;
+  const float step_size = lr / bc1;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
     float pi = p[i] * (1.0f - lr * wd);
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
     const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-    pi -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    pi -= step_size * mi / (sqrtf(vi) / bc2_sqrt + eps);
     p[i] = pi; m[i] = mi; v[i] = vi;
     if (ema) ema[i] = ema_decay * ema[i] + (1.0f - ema_decay) * pi;
   }
@@ -64,13 +69,11 @@ extern "C" int ffsr_sumsq(const float* g, long n, double* out, cudaStream_t stre
 
 extern "C" int ffsr_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, long n, float lr,
                                    float beta1, float beta2, float eps, float weight_decay, int step,
-                                   const double* gsumsq, float grad_scale, float max_norm, float ema_decay,
-                                   cudaStream_t stream) {
-  FFSR_REQUIRE(p && g && m && v && n > 0 && step >= 1, FFSR_ERR_ARG, "adamw_ema_step: bad argument");
-  const float bc1 = 1.0f - (float)pow((double)beta1, (double)step);
-  const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+                                   const int* step_dev, const float* lr_dev, const double* gsumsq, float grad_scale,
+                                   float max_norm, float ema_decay, cudaStream_t stream) {
+  FFSR_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || step_dev), FFSR_ERR_ARG, "adamw_ema_step: bad argument");
   const int grid = (int)((n + 255) / 256 < 148L * 8 ? (n + 255) / 256 : 148L * 8);
-  k_adamw_ema<<<grid, 256, 0, stream>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, gsumsq,
-                                        grad_scale, max_norm, ema_decay);
+  k_adamw_ema<<<grid, 256, 0, stream>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, step, step_dev, lr_dev,
+                                        gsumsq, grad_scale, max_norm, ema_decay);
   return ffsr_check_launch("adamw_ema_step");
 }

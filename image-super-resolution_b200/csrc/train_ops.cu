@@ -184,6 +184,48 @@ __global__ void __launch_bounds__(256) k_colsum(const void* __restrict__ v, int 
   }
 }
 
+// dense channels-last fast path: rows of `pitch` elements, no index arithmetic per element, VEC channels per thread
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) k_colsum_rows(const T* __restrict__ v, long NP, int C, long pitch, int TPR,
+                                                     long rows_per_block, float* __restrict__ out) {
+  __shared__ float sred[256 * VEC];
+  const int lane_c = threadIdx.x % TPR, rt = threadIdx.x / TPR, RT = 256 / TPR;
+  const int c0 = lane_c * VEC;
+  const long r0 = (long)blockIdx.x * rows_per_block, r1 = min(NP, r0 + rows_per_block);
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  if (c0 < C) {
+    long r = r0 + rt;
+    for (; r + 3 * RT < r1; r += 4 * RT) {
+      float t[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) t[u][i] = (c0 + i < C) ? to_f32<T>(v[(r + (long)u * RT) * pitch + c0 + i]) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] += t[u][i];
+    }
+    for (; r < r1; r += RT)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] += (c0 + i < C) ? to_f32<T>(v[r * pitch + c0 + i]) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) sred[(rt * TPR + lane_c) * VEC + i] = acc[i];
+  __syncthreads();
+  if (rt == 0 && c0 < C) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      if (c0 + i >= C) continue;
+      float s = 0.f;
+      for (int k = 0; k < RT; ++k) s += sred[(k * TPR + lane_c) * VEC + i];
+      atomicAdd(out + c0 + i, s);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // pointwise activations
 // ------------------------------------------------------------------------------------
@@ -398,7 +440,9 @@ __device__ __forceinline__ float keep_scale(unsigned long long seed, unsigned lo
 
 template <int T>
 __global__ void k_tokattn_fwd(const float* __restrict__ qkv, int B, long HW, int E, float* __restrict__ ctx,
-                              float* __restrict__ probs, float drop_p, unsigned long long seed) {
+                              float* __restrict__ probs, float drop_p, unsigned long long seed,
+                              const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;
   const int heads = E / 16;
   const long it = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= (long)B * HW * T * heads) return;
@@ -447,7 +491,9 @@ __global__ void k_tokattn_fwd(const float* __restrict__ qkv, int B, long HW, int
 template <int T>
 __global__ void k_tokattn_bwd_q(const float* __restrict__ qkv, const float* __restrict__ probs,
                                 const float* __restrict__ dctx, int B, long HW, int E, float* __restrict__ ds,
-                                float* __restrict__ dqkv, float drop_p, unsigned long long seed) {
+                                float* __restrict__ dqkv, float drop_p, unsigned long long seed,
+                                const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;
   const int heads = E / 16;
   const long it = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= (long)B * HW * T * heads) return;
@@ -493,7 +539,9 @@ __global__ void k_tokattn_bwd_q(const float* __restrict__ qkv, const float* __re
 template <int T>
 __global__ void k_tokattn_bwd_kv(const float* __restrict__ qkv, const float* __restrict__ probs,
                                  const float* __restrict__ ds, const float* __restrict__ dctx, int B, long HW, int E,
-                                 float* __restrict__ dqkv, float drop_p, unsigned long long seed) {
+                                 float* __restrict__ dqkv, float drop_p, unsigned long long seed,
+                                const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev;
   const int heads = E / 16;
   const long it = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= (long)B * HW * T * heads) return;
@@ -541,6 +589,28 @@ __global__ void __launch_bounds__(256) k_to_bf16_nhwc(const void* __restrict__ s
   }
 }
 
+// dense channels-last source (pixel pitch sX, channel stride 1): one thread per (pixel, 8-channel group), 16-byte stores
+template <typename T>
+__global__ void __launch_bounds__(256) k_to_bf16_rows(const T* __restrict__ src, long long sX, long NP, int C, int Cpad,
+                                                      __nv_bfloat16* __restrict__ dst) {
+  const int G = Cpad >> 3;
+  const long total = NP * G;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / G;
+    const int c0 = (int)(i - pix * G) << 3;
+    const T* s = src + pix * sX + c0;
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = (c0 + 2 * k < C) ? to_f32<T>(s[2 * k]) : 0.f;
+      const float b = (c0 + 2 * k + 1 < C) ? to_f32<T>(s[2 * k + 1]) : 0.f;
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      w[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(dst + pix * Cpad + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 inline void colsum_geom(int C, dim3& block, int& CT) {
   CT = 1;
   while (CT < C && CT < 64) CT <<= 1;
@@ -569,6 +639,24 @@ extern "C" size_t ffsr_wgrad_params_size(void) { return sizeof(ffsr_wgrad_params
 extern "C" int ffsr_colsum(const void* v, int dtype, int N, int H, int W, int C, long long sN, long long sY,
                            long long sX, float* out, cudaStream_t stream) {
   FFSR_REQUIRE(v && out && N > 0 && H > 0 && W > 0 && C > 0, FFSR_ERR_ARG, "colsum: bad argument");
+  if (sY == (long long)W * sX && sN == (long long)H * W * sX && C <= 512) {      // dense channels-last rows
+    const long NP = (long)N * H * W;
+    const int VEC = C >= 64 ? 4 : 1;
+    int TPR = 1;
+    while (TPR * VEC < C) TPR <<= 1;                   // power of two, <= 128
+    long blocks = 148 * 8;
+    long rpb = (NP + blocks - 1) / blocks;
+    if (rpb < 256) rpb = 256;
+    const unsigned grid = (unsigned)((NP + rpb - 1) / rpb);
+    if (dtype == FFSR_DT_BF16) {
+      if (VEC == 4) k_colsum_rows<__nv_bfloat16, 4><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)v, NP, C, sX, TPR, rpb, out);
+      else k_colsum_rows<__nv_bfloat16, 1><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)v, NP, C, sX, TPR, rpb, out);
+    } else {
+      if (VEC == 4) k_colsum_rows<float, 4><<<grid, 256, 0, stream>>>((const float*)v, NP, C, sX, TPR, rpb, out);
+      else k_colsum_rows<float, 1><<<grid, 256, 0, stream>>>((const float*)v, NP, C, sX, TPR, rpb, out);
+    }
+    return ffsr_check_launch("colsum_rows");
+  }
   dim3 block;
   int CT;
   colsum_geom(C, block, CT);
@@ -653,28 +741,30 @@ extern "C" int ffsr_bn_backward(const float* x, const float* dy, int G, long R, 
 }
 
 extern "C" int ffsr_token_attention_train(const float* qkv, int B, int T, long HW, int E, float* ctx, float* probs,
-                                          float drop_p, unsigned long long seed, cudaStream_t stream) {
+                                          float drop_p, unsigned long long seed, const unsigned long long* seed_dev,
+                                          cudaStream_t stream) {
   FFSR_REQUIRE(qkv && ctx && probs, FFSR_ERR_ARG, "token_attention_train: null pointer");
   FFSR_REQUIRE((T == 4 || T == 9) && E % 16 == 0 && B > 0 && HW > 0, FFSR_ERR_ARG, "token_attention_train: T must be 4 or 9, E%%16==0");
   FFSR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, FFSR_ERR_ARG, "token_attention_train: dropout p must be in [0,1)");
   const long n = (long)B * HW * T * (E / 16);
-  if (T == 4) k_tokattn_fwd<4><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, B, HW, E, ctx, probs, drop_p, seed);
-  else k_tokattn_fwd<9><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, B, HW, E, ctx, probs, drop_p, seed);
+  if (T == 4) k_tokattn_fwd<4><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, B, HW, E, ctx, probs, drop_p, seed, seed_dev);
+  else k_tokattn_fwd<9><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, B, HW, E, ctx, probs, drop_p, seed, seed_dev);
   return ffsr_check_launch("token_attention_train");
 }
 
 extern "C" int ffsr_token_attention_backward(const float* qkv, const float* probs, const float* dctx, int B, int T,
                                              long HW, int E, float* ds_scratch, float* dqkv, float drop_p,
-                                             unsigned long long seed, cudaStream_t stream) {
+                                             unsigned long long seed, const unsigned long long* seed_dev,
+                                             cudaStream_t stream) {
   FFSR_REQUIRE(qkv && probs && dctx && ds_scratch && dqkv, FFSR_ERR_ARG, "token_attention_backward: null pointer");
   FFSR_REQUIRE((T == 4 || T == 9) && E % 16 == 0 && B > 0 && HW > 0, FFSR_ERR_ARG, "token_attention_backward: T must be 4 or 9");
   const long n = (long)B * HW * T * (E / 16);
   if (T == 4) {
-    k_tokattn_bwd_q<4><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, probs, dctx, B, HW, E, ds_scratch, dqkv, drop_p, seed);
-    k_tokattn_bwd_kv<4><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, probs, ds_scratch, dctx, B, HW, E, dqkv, drop_p, seed);
+    k_tokattn_bwd_q<4><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, probs, dctx, B, HW, E, ds_scratch, dqkv, drop_p, seed, seed_dev);
+    k_tokattn_bwd_kv<4><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, probs, ds_scratch, dctx, B, HW, E, dqkv, drop_p, seed, seed_dev);
   } else {
-    k_tokattn_bwd_q<9><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, probs, dctx, B, HW, E, ds_scratch, dqkv, drop_p, seed);
-    k_tokattn_bwd_kv<9><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, probs, ds_scratch, dctx, B, HW, E, dqkv, drop_p, seed);
+    k_tokattn_bwd_q<9><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, probs, dctx, B, HW, E, ds_scratch, dqkv, drop_p, seed, seed_dev);
+    k_tokattn_bwd_kv<9><<<ceil_div(n, 128), 128, 0, stream>>>(qkv, probs, ds_scratch, dctx, B, HW, E, dqkv, drop_p, seed, seed_dev);
   }
   return ffsr_check_launch("token_attention_backward");
 }
@@ -682,6 +772,14 @@ extern "C" int ffsr_token_attention_backward(const float* qkv, const float* prob
 extern "C" int ffsr_to_bf16_nhwc(const void* src, int src_dtype, long long sN, long long sY, long long sX, long long sC,
                                  int N, int H, int W, int C, int Cpad, void* dst, cudaStream_t stream) {
   FFSR_REQUIRE(src && dst && N > 0 && H > 0 && W > 0 && C > 0 && Cpad >= C, FFSR_ERR_ARG, "to_bf16_nhwc: bad argument");
+  if (sC == 1 && sY == (long long)W * sX && sN == (long long)H * W * sX && Cpad % 8 == 0 && ((uintptr_t)dst % 16) == 0) {
+    const long NP = (long)N * H * W;
+    const long work = NP * (Cpad >> 3);
+    const int grid = (int)min((long)148 * 16, (work + 255) / 256);
+    if (src_dtype == FFSR_DT_BF16) k_to_bf16_rows<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, sX, NP, C, Cpad, (__nv_bfloat16*)dst);
+    else k_to_bf16_rows<float><<<grid, 256, 0, stream>>>((const float*)src, sX, NP, C, Cpad, (__nv_bfloat16*)dst);
+    return ffsr_check_launch("to_bf16_rows");
+  }
   const long total = (long)N * H * W * Cpad;
   k_to_bf16_nhwc<<<(int)min((long)148 * 16, (total + 255) / 256), 256, 0, stream>>>(src, src_dtype, sN, sY, sX, sC, H, W, C,
                                                                                      Cpad, total, (__nv_bfloat16*)dst);

@@ -32,6 +32,18 @@ def _S(t):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+_CONSTS: Dict = {}
+
+
+def _const(dev, name, values, dtype):
+    """Small device constants, cached so that no host->device copy happens inside a CUDA-graph capture."""
+    key = (str(dev), name, tuple(values), dtype)
+    t = _CONSTS.get(key)
+    if t is None:
+        t = _CONSTS[key] = torch.tensor(list(values), device=dev, dtype=dtype)
+    return t
+
+
 class _FusedLosses(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target, w_l1, w_swt, w_fft, w_ssim):
@@ -66,13 +78,13 @@ class _FusedLosses(torch.autograd.Function):
                 ws = torch.empty(nb, device=dev, dtype=torch.uint8)
                 K.check(lib.ffsr_loss_fft(p.data_ptr(), t.data_ptr(), P, H, W, w_fft / n, sums.data_ptr() + 10 * 8,
                                           ws.data_ptr(), nb, dpred.data_ptr(), S), "loss_fft")
-        bw = torch.tensor(_SWT_BANDS * _SWT_LEVELS, device=dev, dtype=torch.float64)
+        bw = _const(dev, "swt_bands", _SWT_BANDS * _SWT_LEVELS, torch.float64)
         l1 = sums[0] / n
         swt = (sums[1:9] * bw).sum() / (n * _SWT_LEVELS)
         ssim = 1.0 - sums[9] / n
         fft = (sums[10] + 0.1 * sums[11]) / n
         comps = torch.stack([l1, swt, fft, ssim]).float()
-        wts = torch.tensor([w_l1, w_swt, w_fft, w_ssim], device=dev, dtype=torch.float32)
+        wts = _const(dev, "weights", (w_l1, w_swt, w_fft, w_ssim), torch.float32)
         total = (comps * wts).sum()
         ctx.save_for_backward(dpred)
         ctx.pred_dtype = pred.dtype

@@ -98,7 +98,12 @@ class FusedAdamW(torch.optim.Optimizer):
         self.exp_avg = self.bucket.new_like()
         self.exp_avg_sq = self.bucket.new_like()
         self.ema = self.bucket.flat.clone() if ema_decay is not None else None
-        self._gsq = torch.zeros(1, device=self.bucket.flat.device, dtype=torch.float64)
+        dev = self.bucket.flat.device
+        self._gsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        # step counter and learning rate live on the device so that a CUDA-graph replay sees fresh values
+        self._step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
+        self._lr_host = float(lr)
         self.steps = 0
         for i, p in enumerate(params):
             p.data = self.bucket.view(i)                       # same values, storage now inside the bucket
@@ -129,6 +134,11 @@ class FusedAdamW(torch.optim.Optimizer):
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)   # ONE collective: the flat 5.7 MB gradient bucket
         self.steps += 1
         dev = self.bucket.flat.device
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing and float(g["lr"]) != self._lr_host:   # scheduler changed the LR: refresh the device scalar
+            self._lr_host = float(g["lr"])
+            self._lr_dev.fill_(self._lr_host)
+        self._step_dev.add_(1)
         with torch.cuda.device(dev):
             S = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             n = self.bucket.numel
@@ -140,13 +150,23 @@ class FusedAdamW(torch.optim.Optimizer):
             K.check(self.lib.ffsr_adamw_ema_step(
                 self.bucket.flat.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                 self.ema.data_ptr() if self.ema is not None else None, n, float(g["lr"]), float(g["betas"][0]),
-                float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self.steps, gsq, 1.0 / world,
-                self.max_grad_norm, float(self.ema_decay or 0.0), S), "adamw_ema_step")
-        for p in self._params:                                  # the kernel wrote through raw pointers: tell the
-            torch.autograd.graph.increment_version(p)           # version-keyed weight caches (pipeline.py) about it
+                float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), 0, self._step_dev.data_ptr(),
+                self._lr_dev.data_ptr(), gsq, 1.0 / world, self.max_grad_norm, float(self.ema_decay or 0.0), S),
+                "adamw_ema_step")
+        self.bump_versions()      # the kernel wrote through raw pointers: tell the version-keyed weight caches (pipeline.py)
         return loss
 
     # -- extras ----------------------------------------------------------------------------
+    def set_lr(self, lr: float) -> None:
+        """Scheduler hook usable between CUDA-graph replays (also picked up from param_groups[0]['lr'])."""
+        self.param_groups[0]["lr"] = float(lr)
+        self._lr_host = float(lr)
+        self._lr_dev.fill_(float(lr))
+
+    def bump_versions(self) -> None:
+        for p in self._params:
+            torch.autograd.graph.increment_version(p)
+
     def grad_norm(self) -> torch.Tensor:
         """Global gradient norm seen by the last step (device scalar, no sync)."""
         return self._gsq.sqrt() / _world()
@@ -163,23 +183,81 @@ class FusedAdamW(torch.optim.Optimizer):
 
 
 class FusionTrainer:
-    """One data-parallel training step (BASELINE configs[1] / configs[3])."""
+    """One data-parallel training step (BASELINE configs[1] / configs[3]).
+
+    ``cuda_graph=True`` (default): after ``graph_warmup`` eager steps the whole step -- forward, fused losses,
+    backward, gradient all-reduce, clip + AdamW + EMA, BatchNorm buffer sync -- is captured once into a CUDA
+    graph and replayed from static input buffers: the ~2,000 kernel launches of a step cost one graph launch
+    instead of ~80 us of Python / driver time each.  The values that change between steps (optimizer step
+    count, learning rate, dropout seed) are device-side scalars.  A change of input shapes re-captures."""
 
     def __init__(self, model, criterion, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-4, max_grad_norm: float = 1.0, ema_decay: Optional[float] = 0.999):
+                 weight_decay: float = 1e-4, max_grad_norm: float = 1.0, ema_decay: Optional[float] = 0.999,
+                 cuda_graph: bool = True, graph_warmup: int = 3):
         self.model, self.criterion = model, criterion
         self.names = [n for n, p in model.named_parameters() if p.requires_grad]
         self.optimizer = FusedAdamW(model.parameters(), lr, betas, eps, weight_decay, max_grad_norm, ema_decay)
         self.optimizer.zero_grad()
+        self.cuda_graph = cuda_graph
+        self.graph_warmup = graph_warmup
+        self._eager_steps = 0
+        self._graph = None
+        self._static = None
+        self._sig = None
 
-    def step(self, lr_img, expert_imgs, expert_feats, hr_img):
-        """forward -> clamp -> loss -> backward -> all-reduce -> clip + AdamW + EMA.  Returns the
-        (device) loss and its components; nothing here synchronises the host."""
-        self.model.train()
+    def _step_body(self, lr_img, expert_imgs, expert_feats, hr_img):
+        from .training import seed_counter
         sr = self.model.forward_with_precomputed(lr_img, expert_imgs, expert_feats).clamp(0, 1)   # train.py:326
         loss, comps = self.criterion(sr, hr_img, return_components=True)
         loss.backward()
         self.optimizer.step()
         sync_bn_buffers(self.model)
         self.optimizer.zero_grad()
-        return loss.detach(), comps
+        seed_counter(lr_img.device).add_(1)
+        return loss.detach(), {k: v.detach() for k, v in comps.items()}
+
+    @staticmethod
+    def _signature(lr_img, expert_imgs, expert_feats, hr_img):
+        f = expert_feats or {}
+        return (tuple(lr_img.shape), lr_img.dtype, tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in expert_imgs.items())),
+                tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in f.items())), tuple(hr_img.shape))
+
+    def _capture(self, lr_img, expert_imgs, expert_feats, hr_img):
+        self._static = (lr_img.clone(), {k: v.clone() for k, v in expert_imgs.items()},
+                        {k: v.clone() for k, v in expert_feats.items()} if expert_feats else None, hr_img.clone())
+        self._graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self._graph):
+            self._out = self._step_body(*self._static)
+        self._sig = self._signature(lr_img, expert_imgs, expert_feats, hr_img)
+
+    def step(self, lr_img, expert_imgs, expert_feats, hr_img):
+        """forward -> clamp -> loss -> backward -> all-reduce -> clip + AdamW + EMA.  Returns the
+        (device) loss and its components; nothing here synchronises the host."""
+        self.model.train()
+        opt = self.optimizer
+        if not self.cuda_graph:
+            return self._step_body(lr_img, expert_imgs, expert_feats, hr_img)
+        sig = self._signature(lr_img, expert_imgs, expert_feats, hr_img)
+        if self._graph is not None and sig != self._sig:
+            self._graph, self._static, self._eager_steps = None, None, 0       # new shapes: warm up and re-capture
+        if self._graph is None:
+            if self._eager_steps < self.graph_warmup:
+                self._eager_steps += 1
+                return self._step_body(lr_img, expert_imgs, expert_feats, hr_img)
+            self._capture(lr_img, expert_imgs, expert_feats, hr_img)     # capture does not execute the step
+        lr_now = float(opt.param_groups[0]["lr"])
+        if lr_now != opt._lr_host:
+            opt.set_lr(lr_now)
+        s_lr, s_imgs, s_feats, s_hr = self._static
+        s_lr.copy_(lr_img, non_blocking=True)
+        for k, v in expert_imgs.items():
+            s_imgs[k].copy_(v, non_blocking=True)
+        if s_feats:
+            for k, v in expert_feats.items():
+                s_feats[k].copy_(v, non_blocking=True)
+        s_hr.copy_(hr_img, non_blocking=True)
+        self._graph.replay()
+        opt.steps += 1
+        opt.bump_versions()
+        return self._out

@@ -421,17 +421,19 @@ class _TokenAttention(torch.autograd.Function):
     """qkv: [B*T, 3E, H, W] channels-last (memory [B][T][HW][3E]) -> ctx [B*T, E, H, W]."""
 
     @staticmethod
-    def forward(ctx, qkv, B, T, drop_p, seed):
+    def forward(ctx, qkv, B, T, drop_p, seed, seed_dev=None):
         qkv = _cl(qkv)
         BT, E3, H, W = qkv.shape
         E = E3 // 3
         HW = H * W
         out = _empty_cl(BT, E, H, W, qkv.device)
         probs = torch.empty(B * HW * (E // 16) * T * T, device=qkv.device, dtype=torch.float32)
+        sd_ptr = seed_dev.data_ptr() if (seed_dev is not None and drop_p > 0) else None
         _ck(_lib().ffsr_token_attention_train(qkv.data_ptr(), B, T, HW, E, out.data_ptr(), probs.data_ptr(),
-                                              float(drop_p), int(seed), _S(qkv)), "token_attention_train")
+                                              float(drop_p), int(seed), sd_ptr, _S(qkv)), "token_attention_train")
         ctx.save_for_backward(qkv, probs)
         ctx.cfg = (B, T, HW, E, float(drop_p), int(seed))
+        ctx.seed_dev = seed_dev if sd_ptr is not None else None
         return out
 
     @staticmethod
@@ -441,10 +443,11 @@ class _TokenAttention(torch.autograd.Function):
         gy = _cl(gy)
         dqkv = torch.empty_like(qkv)
         ds = torch.empty_like(probs)
+        sd_ptr = ctx.seed_dev.data_ptr() if ctx.seed_dev is not None else None
         _ck(_lib().ffsr_token_attention_backward(qkv.data_ptr(), probs.data_ptr(), gy.data_ptr(), B, T, HW, E,
-                                                 ds.data_ptr(), dqkv.data_ptr(), drop_p, seed, _S(qkv)),
+                                                 ds.data_ptr(), dqkv.data_ptr(), drop_p, seed, sd_ptr, _S(qkv)),
             "token_attention_backward")
-        return dqkv, None, None, None, None
+        return dqkv, None, None, None, None, None
 
 
 def _draw_seed() -> int:
@@ -452,12 +455,27 @@ def _draw_seed() -> int:
     return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 
+_SEED_COUNTERS: Dict[str, torch.Tensor] = {}
+_CHECKED = set()
+
+
+def seed_counter(dev) -> torch.Tensor:
+    """Device-side int64 added to every dropout seed.  Eager steps draw a fresh host seed per call; a step
+    replayed from a CUDA graph has its host seed frozen at capture time, so the trainer bumps this counter
+    inside the graph instead (trainer.py)."""
+    key = str(dev)
+    t = _SEED_COUNTERS.get(key)
+    if t is None:
+        t = _SEED_COUNTERS[key] = torch.zeros(1, device=dev, dtype=torch.int64)
+    return t
+
+
 def mha_tokens(x, mha: torch.nn.MultiheadAttention, B: int, T: int, training: bool, tc: bool = False):
     """nn.MultiheadAttention self-attention over the T tokens of every LR pixel.
     x: [B*T, E, H, W] channels-last token-major.  (large_kernel_attention.py:192-197, 294-299)"""
     qkv = conv2d(x, mha.in_proj_weight, mha.in_proj_bias, tc)
     p = float(mha.dropout) if training else 0.0
-    ctx = _TokenAttention.apply(qkv, B, T, p, _draw_seed() if p > 0 else 0)
+    ctx = _TokenAttention.apply(qkv, B, T, p, _draw_seed() if p > 0 else 0, seed_counter(x.device) if p > 0 else None)
     return conv2d(ctx, mha.out_proj.weight, mha.out_proj.bias, tc)
 
 
@@ -582,7 +600,9 @@ def train_forward(m, lr: torch.Tensor, img_list: List[torch.Tensor], feats: Dict
         raise RuntimeError("CompleteEnhancedFusionSR (sm_100a build) needs CUDA tensors: there is no CPU path")
     lib = _lib()
     with torch.cuda.device(lr.device):
-        _ck(lib.ffsr_device_check(), "device_check")
+        if str(lr.device) not in _CHECKED:
+            _ck(lib.ffsr_device_check(), "device_check")
+            _CHECKED.add(str(lr.device))
         return _train_forward(m, lr, img_list, feats, want_inter)
 
 
@@ -598,8 +618,8 @@ def _train_forward(m, lr, img_list, feats, want_inter):
     inter: Dict = {}
     if m.precision not in ("fp32", "bf16"):
         raise ValueError(f"precision must be 'fp32' or 'bf16', got {m.precision!r}")
-    # bf16 mode: tcgen05 kernels for the contractions of phases 4/5/7 (bf16 operands, fp32 accumulate, HR feature
-    # maps stored bf16); phases 2/3/6 and every residual / image stream stay fp32 like the eval path
+    # bf16 mode: tcgen05 kernels for the contractions of phases 3/4/5/7 (bf16 operands, fp32 accumulate, HR feature
+    # maps stored bf16); phases 2/6, the LR token streams and every residual / image stream stay fp32
     tc = m.precision == "bf16"
 
     def cv(x, mod, lp_out=False):
@@ -614,13 +634,13 @@ def _train_forward(m, lr, img_list, feats, want_inter):
     # ---------------- Phase 3 ----------------
     cb = m.cross_band
     tok_in = raw9.reshape(B * 9, 3, H, W)                                 # token-major images, NCHW planes
-    proj = conv_mod(tok_in, cb.band_proj)                                 # [B*9,64,H,W]
-    att = mha_tokens(layernorm(proj, cb.norm), cb.band_attention, B, 9, training) + proj
+    proj = cv(tok_in, cb.band_proj)                                       # [B*9,64,H,W]
+    att = mha_tokens(layernorm(proj, cb.norm), cb.band_attention, B, 9, training, tc) + proj
     gm = _to_group_major(att, B, 9)                                       # [9*B,64,H,W], band-major
-    x_used = lka_block_train(gm[:3 * B], cb.lka_block, 3, sink)
+    x_used = lka_block_train(gm[:3 * B], cb.lka_block, 3, sink, tc=tc)
     with torch.no_grad():                                                 # bands 3..8 feed nothing downstream:
-        lka_block_train(gm[3 * B:].detach(), cb.lka_block, 6, sink, stats_only=True)   # BN running stats only
-    enh = conv_mod(x_used, cb.out_proj).reshape(3, B, 3, H, W) + raw9[:, :3].transpose(0, 1)
+        lka_block_train(gm[3 * B:].detach(), cb.lka_block, 6, sink, stats_only=True, tc=tc)   # BN running stats only
+    enh = cv(x_used, cb.out_proj).reshape(3, B, 3, H, W) + raw9[:, :3].transpose(0, 1)
     routing = enh.sum(0)                                                  # [B,3,H,W]
 
     # ---------------- Phase 6 nets ----------------
@@ -674,7 +694,7 @@ def _train_forward(m, lr, img_list, feats, want_inter):
         for i in range(4):
             mod = co.modulation[i]
             f_i = xg[i * B:(i + 1) * B]
-            m32 = cv(f_i, mod[0])                             # 1x1 conv commutes with the bilinear upsampling
+            m32 = cv(f_i, mod[0], True)                       # 1x1 conv commutes with the bilinear upsampling
             up = gelu(_bilinear(m32, (Hh, Wh)))
             mk = sigmoid(cv(up, mod[2]))
             o = imgs[i] * (1.0 + 0.2 * (mk - 0.5))

@@ -237,12 +237,13 @@ int ffsr_bn_backward(const float* x, const float* dy, int G, long R, int C, cons
 /* nn.MultiheadAttention core in train mode (T = 4 or 9 tokens per LR pixel, head_dim 16,
  * attention-probability dropout): probs[B][HW][E/16][T][T] saved for the backward; the dropout
  * mask is a counter-based hash of (seed, element index), regenerated by the backward.
- * ds_scratch: same size as probs. */
+ * ds_scratch: same size as probs.  The effective seed is seed + *seed_dev (seed_dev may be NULL): a device-side
+ * counter keeps the masks changing when the step is replayed from a CUDA graph. */
 int ffsr_token_attention_train(const float* qkv, int B, int T, long HW, int E, float* ctx, float* probs, float drop_p,
-                               unsigned long long seed, cudaStream_t stream);
+                               unsigned long long seed, const unsigned long long* seed_dev, cudaStream_t stream);
 int ffsr_token_attention_backward(const float* qkv, const float* probs, const float* dctx, int B, int T, long HW, int E,
                                   float* ds_scratch, float* dqkv, float drop_p, unsigned long long seed,
-                                  cudaStream_t stream);
+                                  const unsigned long long* seed_dev, cudaStream_t stream);
 
 /* single stages of the LKA depthwise chain (kind 0: 5x5 pad 2 with input affine bn_k/bn_d,
  * 1: 1x21 pad 10, 2: 21x1 pad 10; w: [C][taps]) -- the backward runs them with reversed taps --
@@ -277,11 +278,13 @@ int ffsr_loss_fft(const float* pred, const float* target, int P, int H, int W, f
  * ffsr_sumsq: out[0] += sum g^2 (fp64) -- the global gradient norm of clip_grad_norm_ (train.py:344-348)
  * ffsr_adamw_ema_step: g' = g*grad_scale*min(1, max_norm/(grad_scale*sqrt(*gsumsq)+1e-6)) (no clipping when
  *   gsumsq is NULL or max_norm <= 0); torch.optim.AdamW update with bias correction for `step` (1-based)
- *   (train.py:847-853); ema = decay*ema + (1-decay)*p (checkpoint_manager.py:352-359; ema may be NULL). */
+ *   (train.py:847-853); ema = decay*ema + (1-decay)*p (checkpoint_manager.py:352-359; ema may be NULL).
+ *   step_dev / lr_dev (optional device scalars): effective step = step + *step_dev, lr = *lr_dev -- the values
+ *   that change between replays of a CUDA-graph-captured training step. */
 int ffsr_sumsq(const float* g, long n, double* out, cudaStream_t stream);
 int ffsr_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, long n, float lr, float beta1,
-                        float beta2, float eps, float weight_decay, int step, const double* gsumsq, float grad_scale,
-                        float max_norm, float ema_decay, cudaStream_t stream);
+                        float beta2, float eps, float weight_decay, int step, const int* step_dev, const float* lr_dev,
+                        const double* gsumsq, float grad_scale, float max_norm, float ema_decay, cudaStream_t stream);
 
 /* ---- bf16 / tcgen05 training path ------------------------------------------------------------
  * ffsr_to_bf16_nhwc: strided fp32/bf16 view (NCHW or NHWC) -> dense bf16 channels-last with the channel

@@ -223,10 +223,10 @@ def test_interface_edge_cases():
         m.forward_with_precomputed(lrd, {k: imd[k] for k in ["drct", "grl"]}, None)
     with pytest.raises(ValueError):
         m.forward_with_precomputed(lrd[:, :, :4, :4], imd, None)
-    m.train()
-    with pytest.raises(NotImplementedError):
-        m.forward_with_precomputed(lrd, imd, ftd)
+    m.train()                                   # train mode is the differentiable path (tests/test_gpu_train.py)
+    assert m.forward_with_precomputed(lrd, imd, ftd).requires_grad
     m.eval()
+    m.load_state_dict({k: v.to(dev) for k, v in sd.items()})     # undo the BatchNorm running-stat side effect
     # weights edited in place (optimizer / EMA) must be picked up
     with torch.no_grad():
         m.residual_scale.add_(0.05)
