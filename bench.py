@@ -249,7 +249,15 @@ def run_train(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured CUDA graph holds NCCL kernels; tearing the communicator down underneath it can hang at
+        # exit (seen at N=2).  Drop the graph, drain the device, then leave without the NCCL destructor.
+        tr._graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -8,6 +8,11 @@ is pre-seeded in ``sys.modules`` before the script runs:
 
 or, from Python:  ``import isr_b200.install as I; I.install()`` before importing ``src.models``.
 
+``--fused-losses`` (``install(losses=True)``) additionally pre-seeds ``src.losses`` with the fused
+L1 / SWT / FFT / SSIM ``CombinedLoss`` (``from src.losses import CombinedLoss, PYWT_AVAILABLE``,
+train.py:549), which also removes the reference's eager VGG19 download (perceptual_loss.py:1122-1125)
+that makes ``train.py`` unstartable offline.
+
 Exports the names the reference re-exports from that module (src/models/__init__.py:50-58).
 The four legacy classes are dead code upstream (never instantiated by CompleteEnhancedFusionSR,
 SURVEY §2.1 #7); they are importable here and raise on construction.
@@ -20,12 +25,13 @@ from .fusion import CompleteEnhancedFusionSR, create_enhanced_fusion
 from .modules import DynamicExpertSelector
 
 TARGET = "src.models.enhanced_fusion_v2"
+LOSSES_TARGET = "src.losses"
 
 
 def _legacy(name):
     def __init__(self, *a, **k):
-        raise NotImplementedError(f"{name} is legacy code that CompleteEnhancedFusionSR never instantiates; "
-                                  "it is not part of the sm_100a hot path")
+        raise NotImplementedError(f"{name} is not used by the cached-fusion hot path (legacy fusion classes / "
+                                  "loss components outside the stage-1/2/3 curriculum); it is not built for sm_100a")
     return type(name, (), {"__init__": __init__})
 
 
@@ -41,19 +47,36 @@ def make_module() -> types.ModuleType:
     return mod
 
 
-def install() -> types.ModuleType:
+def make_losses_module() -> types.ModuleType:
+    from . import losses as FL
+    mod = types.ModuleType(LOSSES_TARGET)
+    mod.__doc__ = "sm_100a fused stage-1/2/3 losses (isr_b200.losses) behind the reference's src.losses names"
+    for n in ("CombinedLoss", "L1Loss", "SSIMLoss", "FFTLoss", "SWTLoss", "PYWT_AVAILABLE", "LPIPS_AVAILABLE",
+              "CLIP_AVAILABLE"):
+        setattr(mod, n, getattr(FL, n))
+    for n in ("L2Loss", "CharbonnierLoss", "VGGPerceptualLoss", "VGGFeatureExtractor", "EdgeLoss", "CLIPPerceptualLoss"):
+        setattr(mod, n, _legacy(n))        # outside the stage-1/2/3 curriculum: importable, raise on construction
+    return mod
+
+
+def install(losses: bool = False) -> types.ModuleType:
     mod = sys.modules.get(TARGET)
     if mod is None or getattr(mod, "CompleteEnhancedFusionSR", None) is not CompleteEnhancedFusionSR:
         mod = make_module()
         sys.modules[TARGET] = mod
+    if losses and LOSSES_TARGET not in sys.modules:
+        sys.modules[LOSSES_TARGET] = make_losses_module()
     return mod
 
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
+    fused = False
+    if argv and argv[0] == "--fused-losses":
+        fused, argv = True, argv[1:]
     if not argv:
-        raise SystemExit("usage: python -m isr_b200.install <reference script.py> [script args...]")
-    install()
+        raise SystemExit("usage: python -m isr_b200.install [--fused-losses] <reference script.py> [script args...]")
+    install(losses=fused)
     sys.argv = argv
     runpy.run_path(argv[0], run_name="__main__")
 

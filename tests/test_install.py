@@ -36,3 +36,17 @@ def test_reference_package_import_resolves_to_our_module():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_install_fused_losses_module():
+    from isr_b200 import install as I
+    from isr_b200 import losses as FL
+    I.install(losses=True)
+    mod = sys.modules["src.losses"]
+    assert mod.CombinedLoss is FL.CombinedLoss and mod.PYWT_AVAILABLE is True
+    crit = mod.CombinedLoss()
+    crit.set_weights({"l1": 0.6, "swt": 0.25, "fft": 0.1, "ssim": 0.05})
+    assert crit.current_stage == 3 and crit.weights["swt"] == 0.25
+    with pytest.raises(NotImplementedError):
+        mod.VGGPerceptualLoss()
+    del sys.modules["src.losses"], sys.modules["src.models.enhanced_fusion_v2"]
