@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libffsr_b200.so")
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
-EPI_PLAIN, EPI_RESIDUAL, EPI_LKAGATE = 0, 1, 2
+EPI_PLAIN, EPI_RESIDUAL, EPI_LKAGATE, EPI_ACTGRAD = 0, 1, 2, 3
 DT_F32, DT_BF16 = 0, 1
 
 
@@ -37,6 +37,7 @@ class ConvParams(C.Structure):
         ("ch_k", C.c_void_p), ("ch_d", C.c_void_p),
         ("in_dtype", C.c_int), ("out_dtype", C.c_int),
         ("w_dtype", C.c_int), ("r1_dtype", C.c_int), ("r2_dtype", C.c_int),
+        ("out2", C.c_void_p), ("reserved", C.c_int),
     ]
 
 
@@ -113,6 +114,8 @@ PROTOTYPES = {
     "ffsr_to_bf16_nhwc": (_I, [_P, _I, _LL, _LL, _LL, _LL, _I, _I, _I, _I, _I, _P, _P]),
     "ffsr_conv2d_wgrad_tc_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
     "ffsr_conv2d_wgrad_tc": (_I, [C.POINTER(WgradParams), _P, _SZ, _P]),
+    "ffsr_bilinear_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
+    "ffsr_bilinear_backward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     # ---- fused optimizer ----
     "ffsr_sumsq": (_I, [_P, _L, _P, _P]),
     "ffsr_adamw_ema_step": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _P, _P, _F, _F, _F, _P]),

@@ -173,6 +173,8 @@ extern "C" int ffsr_conv2d(const ffsr_conv_params* pp, cudaStream_t stream) {
   FFSR_REQUIRE(p.groups >= 1, FFSR_ERR_ARG, "conv2d: groups must be >= 1");
   FFSR_REQUIRE(p.epi == FFSR_EPI_PLAIN || p.r1, FFSR_ERR_ARG, "conv2d: residual epilogue needs r1");
   FFSR_REQUIRE(p.epi != FFSR_EPI_LKAGATE || (p.ch_k && p.ch_d), FFSR_ERR_ARG, "conv2d: LKA gate needs ch_k/ch_d");
+  FFSR_REQUIRE(p.epi != FFSR_EPI_ACTGRAD || p.in_dtype == FFSR_DT_BF16, FFSR_ERR_ARG,
+               "conv2d: FFSR_EPI_ACTGRAD is implemented on the tcgen05 (bf16) path only");
   if (p.in_dtype == FFSR_DT_BF16) return ffsr_conv2d_tc(pp, stream);       // tcgen05 implicit GEMM
   FFSR_REQUIRE(p.w_dtype == FFSR_DT_F32, FFSR_ERR_ARG, "conv2d: fp32 input needs fp32-packed weights");
   const bool nchw = (p.in_sX == 1 && p.in_sC != 1);

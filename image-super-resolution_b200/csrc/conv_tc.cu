@@ -70,6 +70,7 @@ struct TcArgs {
   const float* sb_ptr;
   const float* ch_k;
   const float* ch_d;
+  void* out2;        // optional bf16 pre-activation copy (same strides as out)
 };
 
 // ---------------------------------------------------------------------------- PTX wrappers
@@ -236,7 +237,26 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
-enum { EM_NONE = 0, EM_GELU = 1, EM_RELU = 2, EM_SIGMOID = 3, EM_RESIDUAL = 4, EM_LKAGATE = 5 };
+enum { EM_NONE = 0, EM_GELU = 1, EM_RELU = 2, EM_SIGMOID = 3, EM_RESIDUAL = 4, EM_LKAGATE = 5, EM_ACTGRAD = 6 };
+
+// d/dz of the activations (z = saved pre-activation); GELU' = Phi(z) + z phi(z) with the same fast erf
+__device__ __forceinline__ float act_grad_fast(float z, int act) {
+  if (act == ACT_GELU) {
+    const float u = fabsf(z) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, u, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = __expf(-u * u);
+    const float erf_abs = 1.0f - poly * t * e;
+    const float cdf = 0.5f * (1.0f + copysignf(erf_abs, z));
+    return fmaf(z * 0.39894228040143267794f, e, cdf);
+  }
+  if (act == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (act == ACT_SIGMOID) { const float sg = sigmoid_acc(z); return sg * (1.f - sg); }
+  return 1.f;
+}
 
 // 16 consecutive residual channels -> fp32 registers; 16-byte vector loads when aligned.
 __device__ __forceinline__ void load_res16(const void* base, int is_bf16, long long off, int nvalid, float (&o)[16]) {
@@ -366,7 +386,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, 
     const bool inside = (y < a.H) && (x < a.W);
     const long long opix = (long long)n * a.out_sN + (long long)y * a.out_sY + (long long)x * a.out_sX;
     long long r1pix = 0, r2pix = 0;
-    if (MODE == EM_RESIDUAL || MODE == EM_LKAGATE) r1pix = (long long)n * a.r1_sN + (long long)y * a.r1_sY + (long long)x * a.r1_sX;
+    if (MODE == EM_RESIDUAL || MODE == EM_LKAGATE || MODE == EM_ACTGRAD) r1pix = (long long)n * a.r1_sN + (long long)y * a.r1_sY + (long long)x * a.r1_sX;
     if (MODE == EM_RESIDUAL) r2pix = (long long)n * a.r2_sN + (long long)y * a.r2_sY + (long long)x * a.r2_sX;
     bool waited = false;
     uint32_t taddr = 0;
@@ -391,10 +411,10 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, 
 #pragma unroll
         for (int k = 0; k < 16; ++k) f[k] = 0.f;
       }
-      float r1v[(MODE == EM_RESIDUAL || MODE == EM_LKAGATE) ? 16 : 1];
+      float r1v[(MODE == EM_RESIDUAL || MODE == EM_LKAGATE || MODE == EM_ACTGRAD) ? 16 : 1];
       float r2v[MODE == EM_RESIDUAL ? 16 : 1];
       const bool has_r2 = MODE == EM_RESIDUAL && a.r2 != nullptr;
-      if (MODE == EM_RESIDUAL || MODE == EM_LKAGATE) {
+      if (MODE == EM_RESIDUAL || MODE == EM_LKAGATE || MODE == EM_ACTGRAD) {
         if (inside && nvalid > 0) load_res16(a.r1, a.r1_bf16, r1pix + ocb, nvalid, reinterpret_cast<float(&)[16]>(r1v));
       }
       if (MODE == EM_RESIDUAL) {
@@ -412,7 +432,12 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, 
       if (inside && nvalid > 0) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) f[k] += __uint_as_float(v[k]);
-        if (MODE == EM_GELU) {
+        if ((MODE == EM_GELU || MODE == EM_RELU || MODE == EM_SIGMOID) && a.out2 != nullptr)
+          store16_out<true>(a.out2, opix + ocb, f, nvalid);          // pre-activation, kept for the backward pass
+        if (MODE == EM_ACTGRAD) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] *= act_grad_fast(r1v[k % (sizeof(r1v) / 4)], a.act);
+        } else if (MODE == EM_GELU) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) f[k] = gelu_fast(f[k]);
         } else if (MODE == EM_RELU) {
@@ -587,7 +612,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else {
     // ================================ epilogue (warps 2..17) ============================
-    const int mode = a.epi == FFSR_EPI_LKAGATE ? EM_LKAGATE : (a.epi == FFSR_EPI_RESIDUAL ? EM_RESIDUAL : a.act);
+    const int mode = a.epi == FFSR_EPI_LKAGATE ? EM_LKAGATE
+                     : (a.epi == FFSR_EPI_RESIDUAL ? EM_RESIDUAL : (a.epi == FFSR_EPI_ACTGRAD ? EM_ACTGRAD : a.act));
     // one specialised loop per (epilogue mode, output type): no per-element switches, and the
     // plain modes do not carry the residual registers
     if (a.out_bf16) {
@@ -597,6 +623,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         case EM_SIGMOID: epilogue_loop<EM_SIGMOID, true>(a, tfull, tempty, tmem_base, warp, lane); break;
         case EM_RESIDUAL: epilogue_loop<EM_RESIDUAL, true>(a, tfull, tempty, tmem_base, warp, lane); break;
         case EM_LKAGATE: epilogue_loop<EM_LKAGATE, true>(a, tfull, tempty, tmem_base, warp, lane); break;
+        case EM_ACTGRAD: epilogue_loop<EM_ACTGRAD, true>(a, tfull, tempty, tmem_base, warp, lane); break;
         default: epilogue_loop<EM_NONE, true>(a, tfull, tempty, tmem_base, warp, lane); break;
       }
     } else {
@@ -606,6 +633,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         case EM_SIGMOID: epilogue_loop<EM_SIGMOID, false>(a, tfull, tempty, tmem_base, warp, lane); break;
         case EM_RESIDUAL: epilogue_loop<EM_RESIDUAL, false>(a, tfull, tempty, tmem_base, warp, lane); break;
         case EM_LKAGATE: epilogue_loop<EM_LKAGATE, false>(a, tfull, tempty, tmem_base, warp, lane); break;
+        case EM_ACTGRAD: epilogue_loop<EM_ACTGRAD, false>(a, tfull, tempty, tmem_base, warp, lane); break;
         default: epilogue_loop<EM_NONE, false>(a, tfull, tempty, tmem_base, warp, lane); break;
       }
     }
@@ -711,6 +739,7 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   a.r1 = p.r1; a.r1_sN = p.r1_sN; a.r1_sY = p.r1_sY; a.r1_sX = p.r1_sX; a.r1_bf16 = p.r1_dtype == FFSR_DT_BF16;
   a.r2 = p.r2; a.r2_sN = p.r2_sN; a.r2_sY = p.r2_sY; a.r2_sX = p.r2_sX; a.r2_bf16 = p.r2_dtype == FFSR_DT_BF16;
   a.sa = p.sa; a.sb = p.sb; a.sa_ptr = p.sa_ptr; a.sb_ptr = p.sb_ptr; a.ch_k = p.ch_k; a.ch_d = p.ch_d;
+  a.out2 = p.out2;
 
   static int num_sms = 0;
   if (!num_sms) {

@@ -611,6 +611,89 @@ __global__ void __launch_bounds__(256) k_to_bf16_rows(const T* __restrict__ src,
   }
 }
 
+// ------------------------------------------------------------------------------------
+// bilinear resampling (align_corners=False) of dense channels-last tensors, forward and adjoint
+// ------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) k_bilinear_fwd(const T* __restrict__ src, int h, int w, int C, T* __restrict__ dst,
+                                                      int H, int W, long total) {
+  const int G = C / VEC;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    const long pix = i / G;
+    const int X = (int)(pix % W), Y = (int)((pix / W) % H);
+    const long n = pix / ((long)W * H);
+    const BilinTap ty = bilin_tap(Y, h, H), tx = bilin_tap(X, w, W);
+    const T* base = src + n * h * w * C + cg * VEC;
+    const T* p00 = base + ((long)ty.i0 * w + tx.i0) * C;
+    const T* p01 = base + ((long)ty.i0 * w + tx.i1) * C;
+    const T* p10 = base + ((long)ty.i1 * w + tx.i0) * C;
+    const T* p11 = base + ((long)ty.i1 * w + tx.i1) * C;
+    T* o = dst + pix * C + cg * VEC;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      o[k] = from_f32<T>(ty.w0 * (tx.w0 * to_f32<T>(p00[k]) + tx.w1 * to_f32<T>(p01[k])) +
+                         ty.w1 * (tx.w0 * to_f32<T>(p10[k]) + tx.w1 * to_f32<T>(p11[k])));
+  }
+}
+
+constexpr int BL_MAXC = 16;   // candidate outputs per axis that can read one input sample (scale factors up to ~6x)
+
+// candidates [lo, hi] of output indices whose taps may touch input index `i`, and their weights
+__device__ __forceinline__ int bilin_adjoint_taps(int i, int in_size, int out_size, int& lo, float (&wt)[BL_MAXC]) {
+  const float inv_r = (float)out_size / (float)in_size;
+  int l = (int)floorf(((float)i - 0.5f) * inv_r - 0.5f) - 1;
+  int hgh = (int)ceilf(((float)i + 1.5f) * inv_r - 0.5f) + 1;
+  l = max(l, 0);
+  hgh = min(hgh, out_size - 1);
+  int n = hgh - l + 1;
+  if (n > BL_MAXC) n = BL_MAXC;
+  lo = l;
+  for (int k = 0; k < BL_MAXC; ++k) {
+    float wgt = 0.f;
+    if (k < n) {
+      const BilinTap t = bilin_tap(l + k, in_size, out_size);
+      if (t.i0 == i) wgt += t.w0;
+      if (t.i1 == i) wgt += t.w1;
+    }
+    wt[k] = wgt;
+  }
+  return n;
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) k_bilinear_bwd(const T* __restrict__ gout, int H, int W, int C, T* __restrict__ gin,
+                                                      int h, int w, long total) {
+  const int G = C / VEC;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    const long pix = i / G;
+    const int x = (int)(pix % w), y = (int)((pix / w) % h);
+    const long n = pix / ((long)w * h);
+    float wy[BL_MAXC], wx[BL_MAXC];
+    int ylo, xlo;
+    const int ny = bilin_adjoint_taps(y, h, H, ylo, wy);
+    const int nx = bilin_adjoint_taps(x, w, W, xlo, wx);
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    const T* base = gout + n * H * W * C + cg * VEC;
+    for (int a = 0; a < ny; ++a) {
+      if (wy[a] == 0.f) continue;
+      for (int b = 0; b < nx; ++b) {
+        const float wgt = wy[a] * wx[b];
+        if (wgt == 0.f) continue;
+        const T* p = base + ((long)(ylo + a) * W + xlo + b) * C;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = fmaf(wgt, to_f32<T>(p[k]), acc[k]);
+      }
+    }
+    T* o = gin + pix * C + cg * VEC;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) o[k] = from_f32<T>(acc[k]);
+  }
+}
+
 inline void colsum_geom(int C, dim3& block, int& CT) {
   CT = 1;
   while (CT < C && CT < 64) CT <<= 1;
@@ -784,4 +867,41 @@ extern "C" int ffsr_to_bf16_nhwc(const void* src, int src_dtype, long long sN, l
   k_to_bf16_nhwc<<<(int)min((long)148 * 16, (total + 255) / 256), 256, 0, stream>>>(src, src_dtype, sN, sY, sX, sC, H, W, C,
                                                                                      Cpad, total, (__nv_bfloat16*)dst);
   return ffsr_check_launch("to_bf16_nhwc");
+}
+
+// F.interpolate(mode="bilinear", align_corners=False) on dense channels-last tensors and its adjoint
+// (used by hierarchical_fusion.py:156-186, enhanced_fusion_v2.py:735-791, edge_enhancement.py:208-250)
+template <bool BWD>
+static int launch_bilinear(const void* a, int N, int h, int w, int C, void* b, int H, int W, int dtype, cudaStream_t stream) {
+  // forward: a = src [N,h,w,C] -> b = dst [N,H,W,C];  backward: a = gout [N,H,W,C] -> b = gin [N,h,w,C]
+  const int VEC = (C % 4 == 0) ? 4 : 1;
+  const long total = (long)N * (BWD ? (long)h * w : (long)H * W) * (C / VEC);
+  const int grid = (int)min((long)148 * 32, (total + 255) / 256);
+  if (dtype == FFSR_DT_BF16) {
+    using T = __nv_bfloat16;
+    if (BWD) { if (VEC == 4) k_bilinear_bwd<T, 4><<<grid, 256, 0, stream>>>((const T*)a, H, W, C, (T*)b, h, w, total);
+               else k_bilinear_bwd<T, 1><<<grid, 256, 0, stream>>>((const T*)a, H, W, C, (T*)b, h, w, total); }
+    else { if (VEC == 4) k_bilinear_fwd<T, 4><<<grid, 256, 0, stream>>>((const T*)a, h, w, C, (T*)b, H, W, total);
+           else k_bilinear_fwd<T, 1><<<grid, 256, 0, stream>>>((const T*)a, h, w, C, (T*)b, H, W, total); }
+  } else {
+    using T = float;
+    if (BWD) { if (VEC == 4) k_bilinear_bwd<T, 4><<<grid, 256, 0, stream>>>((const T*)a, H, W, C, (T*)b, h, w, total);
+               else k_bilinear_bwd<T, 1><<<grid, 256, 0, stream>>>((const T*)a, H, W, C, (T*)b, h, w, total); }
+    else { if (VEC == 4) k_bilinear_fwd<T, 4><<<grid, 256, 0, stream>>>((const T*)a, h, w, C, (T*)b, H, W, total);
+           else k_bilinear_fwd<T, 1><<<grid, 256, 0, stream>>>((const T*)a, h, w, C, (T*)b, H, W, total); }
+  }
+  return ffsr_check_launch(BWD ? "bilinear_backward" : "bilinear_forward");
+}
+
+extern "C" int ffsr_bilinear_forward(const void* src, int N, int h, int w, int C, void* dst, int H, int W, int dtype,
+                                     cudaStream_t stream) {
+  FFSR_REQUIRE(src && dst && N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0, FFSR_ERR_ARG, "bilinear_forward: bad argument");
+  return launch_bilinear<false>(src, N, h, w, C, dst, H, W, dtype, stream);
+}
+
+extern "C" int ffsr_bilinear_backward(const void* gout, int N, int H, int W, int C, void* gin, int h, int w, int dtype,
+                                      cudaStream_t stream) {
+  FFSR_REQUIRE(gout && gin && N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0, FFSR_ERR_ARG, "bilinear_backward: bad argument");
+  FFSR_REQUIRE((long)H <= 6L * h + 6 && (long)W <= 6L * w + 6, FFSR_ERR_ARG, "bilinear_backward: upscaling factors above 6 are not built");
+  return launch_bilinear<true>(gout, N, h, w, C, gin, H, W, dtype, stream);
 }

@@ -183,8 +183,10 @@ def _pack_tc(wp: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def _launch_conv_tc(xb: torch.Tensor, Cin: int, wtc: torch.Tensor, bias, out: torch.Tensor, ks: int):
-    """xb: [N,H,W,Cpad] bf16; out: channels-last [N,Cout,H,W] fp32 or bf16."""
+def _launch_conv_tc(xb: torch.Tensor, Cin: int, wtc: torch.Tensor, bias, out: torch.Tensor, ks: int,
+                    act: int = 0, out2: Optional[torch.Tensor] = None, actgrad_z: Optional[torch.Tensor] = None):
+    """xb: [N,H,W,Cpad] bf16; out: channels-last [N,Cout,H,W] fp32 or bf16.
+    act + out2: out = act(conv), out2 = bf16 pre-activation.  actgrad_z: out = conv * act'(actgrad_z)."""
     N, H, W, cpad = xb.shape
     Cout = out.shape[1]
     p = K.ConvParams()
@@ -196,10 +198,17 @@ def _launch_conv_tc(xb: torch.Tensor, Cin: int, wtc: torch.Tensor, bias, out: to
     p.groups = 1
     p.out = out.data_ptr()
     p.out_sN, p.out_sY, p.out_sX = H * W * Cout, W * Cout, Cout
-    p.act, p.epi = K.ACT_NONE, K.EPI_PLAIN
+    p.act, p.epi = act, K.EPI_PLAIN
     p.sa = p.sb = 1.0
     p.in_dtype, p.w_dtype = K.DT_BF16, K.DT_BF16
     p.out_dtype = _dt(out)
+    if out2 is not None:
+        p.out2 = out2.data_ptr()
+    if actgrad_z is not None:                 # z: dense channels-last [N,Cout,H,W]
+        p.epi = K.EPI_ACTGRAD
+        p.r1 = actgrad_z.data_ptr()
+        p.r1_sN, p.r1_sY, p.r1_sX = H * W * Cout, W * Cout, Cout
+        p.r1_dtype = _dt(actgrad_z)
     _ck(_lib().ffsr_conv2d(C.byref(p), _S(xb)), "conv2d(tc)")
 
 
@@ -228,7 +237,6 @@ class _Conv2dTC(torch.autograd.Function):
         co, ci, kh, kw = weight.shape
         N, H, W, cpad = xb.shape
         gb, _ = _bf16_operand(gy)
-        gpad = gb.shape[3]
         dx = None
         if ctx.needs_input_grad[0]:
             wr = _pack_tc(weight.detach().flip(2, 3).permute(2, 3, 0, 1).reshape(kh * kw, co, ci))
@@ -236,25 +244,136 @@ class _Conv2dTC(torch.autograd.Function):
             _launch_conv_tc(gb, co, wr, None, dx, kh)
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            lib = _lib()
-            dwp = _zeros((kh * kw, ci, co), xb.device)
-            dbp = _zeros((co,), xb.device) if ctx.has_bias else None
-            p = K.WgradParams()
-            p.x = xb.data_ptr()
-            p.x_sN, p.x_sY, p.x_sX, p.x_sC = H * W * cpad, W * cpad, cpad, 1
-            p.x_dtype = K.DT_BF16
-            p.dy = gb.data_ptr()
-            p.dy_sN, p.dy_sY, p.dy_sX = H * W * gpad, W * gpad, gpad
-            p.dy_dtype = K.DT_BF16
-            p.N, p.H, p.W, p.Cin, p.Cout, p.ksize = N, H, W, ci, co, kh
-            p.dw = dwp.data_ptr()
-            p.dbias = dbp.data_ptr() if dbp is not None else None
-            nb = lib.ffsr_conv2d_wgrad_tc_workspace_bytes(N, H, W, ci, co, kh)
-            ws = torch.empty(nb, device=xb.device, dtype=torch.uint8)
-            _ck(lib.ffsr_conv2d_wgrad_tc(C.byref(p), ws.data_ptr(), nb, _S(xb)), "conv2d_wgrad_tc")
+            dwp, db = _wgrad_tc(xb, gb, ci, co, kh, ctx.has_bias)
             dw = dwp.view(kh, kw, ci, co).permute(3, 2, 0, 1)
-            db = dbp
         return dx, dw, db, None
+
+
+def _wgrad_tc(xb, gb, ci, co, ks, has_bias):
+    """fp32 packed weight gradient [ks*ks][ci][co] (+ bias gradient) from bf16 operands xb / gb ([N,H,W,pitch])."""
+    lib = _lib()
+    N, H, W, cpad = xb.shape
+    gpad = gb.shape[3]
+    dwp = _zeros((ks * ks, ci, co), xb.device)
+    dbp = _zeros((co,), xb.device) if has_bias else None
+    p = K.WgradParams()
+    p.x = xb.data_ptr()
+    p.x_sN, p.x_sY, p.x_sX, p.x_sC = H * W * cpad, W * cpad, cpad, 1
+    p.x_dtype = K.DT_BF16
+    p.dy = gb.data_ptr()
+    p.dy_sN, p.dy_sY, p.dy_sX = H * W * gpad, W * gpad, gpad
+    p.dy_dtype = K.DT_BF16
+    p.N, p.H, p.W, p.Cin, p.Cout, p.ksize = N, H, W, ci, co, ks
+    p.dw = dwp.data_ptr()
+    p.dbias = dbp.data_ptr() if dbp is not None else None
+    nb = lib.ffsr_conv2d_wgrad_tc_workspace_bytes(N, H, W, ci, co, ks)
+    ws = torch.empty(nb, device=xb.device, dtype=torch.uint8)
+    _ck(lib.ffsr_conv2d_wgrad_tc(C.byref(p), ws.data_ptr(), nb, _S(xb)), "conv2d_wgrad_tc")
+    return dwp, dbp
+
+
+class _ConvChainTC(torch.autograd.Function):
+    """conv -> act -> conv -> act -> ... on the tcgen05 kernels as ONE autograd node.
+
+    Forward: one launch per layer; the activation runs in the conv epilogue, which also stores the bf16
+    pre-activation.  Backward: per layer one weight-gradient launch and one input-gradient launch whose epilogue
+    multiplies by act'(pre-activation of the previous layer) (FFSR_EPI_ACTGRAD) -- no separate activation passes
+    over the HR feature maps in either direction.  acts[i] is the activation after layer i (0 = none)."""
+
+    @staticmethod
+    def forward(ctx, x, acts, out_bf16, *wb):
+        L = len(acts)
+        cur, _ = _bf16_operand(x)
+        N, _, H, W = x.shape
+        ops, zs = [], []
+        y = None
+        for i in range(L):
+            w, b = wb[2 * i], wb[2 * i + 1]
+            if w.dim() == 2:
+                w = w[:, :, None, None]
+            co, ci, kh, _ = w.shape
+            wtc = _pack_tc(w.detach().permute(2, 3, 1, 0).reshape(kh * kh, ci, co))
+            bb = b.detach().float().contiguous() if b is not None else None
+            last = i == L - 1
+            odt = (torch.bfloat16 if out_bf16 else torch.float32) if last else torch.bfloat16
+            y = _empty_cl(N, co, H, W, x.device, odt)
+            z = _empty_cl(N, co, H, W, x.device, torch.bfloat16) if acts[i] != K.ACT_NONE else None
+            _launch_conv_tc(cur, ci, wtc, bb, y, kh, acts[i], z)
+            ops.append(cur)
+            zs.append(z)
+            if not last:
+                assert co % 8 == 0, "intermediate channels of a fused conv chain must be a multiple of 8"
+                cur = y.permute(0, 2, 3, 1)                      # [N,H,W,co] bf16 contiguous: next TMA operand
+        ctx.save_for_backward(*ops, *[z for z in zs if z is not None], *[t for t in wb if t is not None])
+        ctx.meta = (acts, [z is not None for z in zs], [t is not None for t in wb], x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        acts, zmask, wbmask, x_dtype = ctx.meta
+        L = len(acts)
+        saved = list(ctx.saved_tensors)
+        ops = saved[:L]
+        nz = sum(zmask)
+        zlist = saved[L:L + nz]
+        rest = saved[L + nz:]
+        zs, k = [], 0
+        for m_ in zmask:
+            zs.append(zlist[k] if m_ else None)
+            k += 1 if m_ else 0
+        wb, k = [], 0
+        for m_ in wbmask:
+            wb.append(rest[k] if m_ else None)
+            k += 1 if m_ else 0
+        grads = [None] * (2 * L)
+        g = gy
+        if acts[L - 1] != K.ACT_NONE:                              # chain ends with an activation
+            z = zs[L - 1]
+            g2 = torch.empty_like(z)
+            gsrc = g if (g.dtype == z.dtype and g.stride() == z.stride()) else torch.empty_like(z).copy_(g)
+            _ck(_lib().ffsr_act_backward(z.data_ptr(), gsrc.data_ptr(), g2.data_ptr(), z.numel(), acts[L - 1], _dt(z), _S(z)),
+                "act_backward")
+            g = g2
+        dx = None
+        for i in range(L - 1, -1, -1):
+            w, b = wb[2 * i], wb[2 * i + 1]
+            w4 = w[:, :, None, None] if w.dim() == 2 else w
+            co, ci, kh, _ = w4.shape
+            gb, _ = _bf16_operand(g)
+            xb = ops[i]
+            N, H, W, _ = xb.shape
+            need_w = ctx.needs_input_grad[3 + 2 * i]
+            need_b = b is not None and ctx.needs_input_grad[4 + 2 * i]
+            if need_w or need_b:
+                dwp, dbp = _wgrad_tc(xb, gb, ci, co, kh, b is not None)
+                dw = dwp.view(kh, kh, ci, co).permute(3, 2, 0, 1)
+                grads[2 * i] = dw.reshape(w.shape) if w.dim() == 2 else dw
+                grads[2 * i + 1] = dbp
+            if i > 0 or ctx.needs_input_grad[0]:
+                wr = _pack_tc(w4.detach().flip(2, 3).permute(2, 3, 0, 1).reshape(kh * kh, co, ci))
+                if i > 0:
+                    g = _empty_cl(N, ci, H, W, xb.device, torch.bfloat16)
+                    _launch_conv_tc(gb, co, wr, None, g, kh, acts[i - 1], None, zs[i - 1])
+                else:
+                    dx = _empty_cl(N, ci, H, W, xb.device, torch.bfloat16 if x_dtype == torch.bfloat16 else torch.float32)
+                    _launch_conv_tc(gb, co, wr, None, dx, kh)
+        return (dx, None, None, *grads)
+
+
+def conv_chain(x, layers, tc: bool, out_bf16: bool = False):
+    """layers: [(weight, bias, act)], act in {K.ACT_NONE, K.ACT_GELU, K.ACT_RELU, K.ACT_SIGMOID}.
+    tc=True: one fused tcgen05 node; tc=False: fp32 conv / activation nodes in sequence."""
+    if tc:
+        flat = []
+        for w, b, _ in layers:
+            flat += [w, b]
+        return _ConvChainTC.apply(x, tuple(a for _, _, a in layers), out_bf16, *flat)
+    y = x
+    for w, b, a in layers:
+        y = conv2d(y, w, b)
+        if a != K.ACT_NONE:
+            y = _Act.apply(y, a)
+    return y
 
 
 def conv2d(x, weight, bias=None, tc: bool = False, out_bf16: bool = False):
@@ -531,13 +650,35 @@ def lka_block_train(x, blk, G: int, sink: list, stats_only: bool = False, tc: bo
     h = batchnorm_train(x1, blk.norm2, G, sink)
     if stats_only:
         return None
-    h = gelu(conv_mod(h, blk.ffn[0], tc))
-    h = conv_mod(h, blk.ffn[2], tc)
+    h = conv_chain(h, [(blk.ffn[0].weight, blk.ffn[0].bias, K.ACT_GELU), (blk.ffn[2].weight, blk.ffn[2].bias, K.ACT_NONE)], tc)
     return x1 + blk.scale2 * h
 
 
+class _Bilinear(torch.autograd.Function):
+    """F.interpolate(mode="bilinear", align_corners=False) and its adjoint on channels-last tensors."""
+
+    @staticmethod
+    def forward(ctx, x, H, W):
+        x = _cl(x)
+        N, Cc, h, w = x.shape
+        out = _empty_cl(N, Cc, H, W, x.device, x.dtype)
+        _ck(_lib().ffsr_bilinear_forward(x.data_ptr(), N, h, w, Cc, out.data_ptr(), H, W, _dt(x), _S(x)), "bilinear_forward")
+        ctx.shape = (N, Cc, h, w, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        N, Cc, h, w, H, W = ctx.shape
+        gy = _cl(gy)
+        gin = _empty_cl(N, Cc, h, w, gy.device, gy.dtype)
+        _ck(_lib().ffsr_bilinear_backward(gy.data_ptr(), N, H, W, Cc, gin.data_ptr(), h, w, _dt(gy), _S(gy)), "bilinear_backward")
+        return gin, None, None
+
+
 def _bilinear(x, size):
-    return F.interpolate(x, size=size, mode="bilinear", align_corners=False)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    return _Bilinear.apply(x, int(size[0]), int(size[1]))
 
 
 def _to_group_major(x, B, T):
@@ -584,7 +725,7 @@ def _phase2_train(m, lr):
     b7 = raw[:, :7] * scale7[None, :, None, None, None]
     X = torch.fft.rfft2(lr, norm="ortho")
     Hf, Wf = X.shape[-2:]
-    msk = _bilinear(fd.fft.freq_mask_logits, (Hf, Wf))
+    msk = F.interpolate(fd.fft.freq_mask_logits, size=(Hf, Wf), mode="bilinear", align_corners=False)
     msk = torch.sigmoid(msk * fd.fft.temperature.clamp(min=1.0))
     low = torch.fft.irfft2(X * msk, s=(H, W), norm="ortho") * fd.fft.band_scale[0]
     high = torch.fft.irfft2(X * (1 - msk), s=(H, W), norm="ortho") * fd.fft.band_scale[1]
@@ -627,6 +768,10 @@ def _train_forward(m, lr, img_list, feats, want_inter):
 
     def cw(x, weight, bias=None, lp_out=False):
         return conv2d(x, weight, bias, tc, tc and lp_out)
+
+    def chain(x, mods, lp_out=False):
+        """[(conv module, activation)] as one fused tcgen05 node (bf16 mode) or exact fp32 nodes."""
+        return conv_chain(x, [(mod.weight, mod.bias, a) for mod, a in mods], tc, tc and lp_out)
 
     # ---------------- Phase 2 ----------------
     raw9 = _phase2_train(m, lr)                                           # [B,9,3,H,W]
@@ -687,8 +832,8 @@ def _train_forward(m, lr, img_list, feats, want_inter):
                 rows.append(a.permute(0, 2, 3, 1))
         tokens = torch.stack(rows, dim=1).reshape(B * 4, H, W, E).permute(0, 3, 1, 2)   # token-major, channels-last
         x = tokens + mha_tokens(layernorm(tokens, co.norm1), co.cross_attn, B, 4, training, tc)
-        hdn = gelu(cw(layernorm(x, co.norm2), co.ffn[0].weight, co.ffn[0].bias))
-        x = x + cw(hdn, co.ffn[2].weight, co.ffn[2].bias)
+        x = x + conv_chain(layernorm(x, co.norm2), [(co.ffn[0].weight, co.ffn[0].bias, K.ACT_GELU),
+                                                    (co.ffn[2].weight, co.ffn[2].bias, K.ACT_NONE)], tc)
         xg = lka_block_train(_to_group_major(x, B, 4), co.lka_global, 4, sink, tc=tc)      # [4*B,128,H,W]
         ecol = []
         for i in range(4):
@@ -696,7 +841,7 @@ def _train_forward(m, lr, img_list, feats, want_inter):
             f_i = xg[i * B:(i + 1) * B]
             m32 = cv(f_i, mod[0], True)                       # 1x1 conv commutes with the bilinear upsampling
             up = gelu(_bilinear(m32, (Hh, Wh)))
-            mk = sigmoid(cv(up, mod[2]))
+            mk = chain(up, [(mod[2], K.ACT_SIGMOID)])
             o = imgs[i] * (1.0 + 0.2 * (mk - 0.5))
             if not training:
                 o = o.clamp(0, 1)
@@ -710,12 +855,11 @@ def _train_forward(m, lr, img_list, feats, want_inter):
 
     def stage(xin, name):
         cvs = getattr(mr, name + "_conv")
-        y = gelu(cv(xin, cvs[0], True))
-        y = gelu(cv(y, cvs[2], True))
+        y = chain(xin, [(cvs[0], K.ACT_GELU), (cvs[2], K.ACT_GELU)], True)
         gate = getattr(mr, name + "_gate").gate
-        y = y * sigmoid(cv(gelu(cv(y, gate[0], True)), gate[2])).to(y.dtype)
+        y = y * chain(y, [(gate[0], K.ACT_GELU), (gate[2], K.ACT_SIGMOID)]).to(y.dtype)
         res = getattr(mr, name + "_res")
-        r = cw(gelu(cw(y, res.block[0].weight, None, True)), res.block[2].weight, None, True)
+        r = chain(y, [(res.block[0], K.ACT_GELU), (res.block[2], K.ACT_NONE)], True)
         return y + res.scale * r
 
     f1 = stage(_bilinear(stack, (H, W)), "stage1")
@@ -725,11 +869,11 @@ def _train_forward(m, lr, img_list, feats, want_inter):
     f2u = _bilinear(f2, (Hh, Wh))
     f3 = stage(torch.cat([f2u, stack.to(f2u.dtype)], dim=1), "stage3")
     f3 = f3 + mr.residual_weight_2_3 * f2u[:, :f3.shape[1]]
-    hier = sigmoid(cv(gelu(cv(f3, mr.to_rgb[0], True)), mr.to_rgb[2]))
+    hier = chain(f3, [(mr.to_rgb[0], K.ACT_GELU), (mr.to_rgb[2], K.ACT_SIGMOID)])
 
     # ---------------- Phase 5b / 6 blend ----------------
     r_hr = _bilinear(routing, (Hh, Wh))
-    fl = cv(gelu(cv(r_hr, m.freq_weight_conv[0])), m.freq_weight_conv[2])
+    fl = chain(r_hr, [(m.freq_weight_conv[0], K.ACT_GELU), (m.freq_weight_conv[2], K.ACT_NONE)])
     fw = torch.softmax(fl, dim=1)
     freq = sum(o * fw[:, i:i + 1] for i, o in enumerate(ecol))
     fused = hier * 0.7 + freq * 0.3
@@ -742,11 +886,7 @@ def _train_forward(m, lr, img_list, feats, want_inter):
 
     # ---------------- Phase 7a ----------------
     convs = [l for l in m.refine if isinstance(l, torch.nn.Conv2d)]
-    y = fused
-    for j, layer in enumerate(convs):
-        y = cv(y, layer, j < len(convs) - 1)
-        if j < len(convs) - 1:
-            y = gelu(y)
+    y = chain(fused, [(layer, K.ACT_GELU if j < len(convs) - 1 else K.ACT_NONE) for j, layer in enumerate(convs)])
     fused = fused + 0.1 * y
 
     # ---------------- Phase 7b ----------------
@@ -766,16 +906,14 @@ def _train_forward(m, lr, img_list, feats, want_inter):
     for lv, lap in enumerate(pyr):
         r = ee.edge_refiners[lv]
         idt = cv(lap, r.proj, True)
-        o = gelu(cv(lap, r.conv1, True))
-        o = gelu(cv(o, r.conv2, True))
-        o = cv(o, r.conv3, True) + idt
-        a = sigmoid(cv(gelu(cv(o, r.attn.attn[0], True)), r.attn.attn[2]))
+        o = chain(lap, [(r.conv1, K.ACT_GELU), (r.conv2, K.ACT_GELU), (r.conv3, K.ACT_NONE)], True) + idt
+        a = chain(o, [(r.attn.attn[0], K.ACT_GELU), (r.attn.attn[2], K.ACT_SIGMOID)])
         f = o * a.to(o.dtype)
         if f.shape[2:] != (Hh, Wh):
             f = _bilinear(f, (Hh, Wh))
         fl_.append(f * lw[lv])
-    e = cv(gelu(cv(torch.cat(fl_, dim=1), ee.fusion[0], True)), ee.fusion[2])
-    gte = sigmoid(cv(gelu(cv(torch.cat([fused, e], dim=1), ee.edge_gate[0], True)), ee.edge_gate[2]))
+    e = chain(torch.cat(fl_, dim=1), [(ee.fusion[0], K.ACT_GELU), (ee.fusion[2], K.ACT_NONE)])
+    gte = chain(torch.cat([fused, e], dim=1), [(ee.edge_gate[0], K.ACT_GELU), (ee.edge_gate[2], K.ACT_SIGMOID)])
     fused = (fused + gte * ee.edge_strength * e).clamp(0, 1)
 
     # ---------------- output ----------------

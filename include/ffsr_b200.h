@@ -44,6 +44,9 @@ typedef struct CUstream_st* cudaStream_t;
 #define FFSR_EPI_PLAIN 0    /* out = act(conv + bias)                                        */
 #define FFSR_EPI_RESIDUAL 1 /* out = r1 + sa*act(conv + bias) + sb*r2          (r2 optional) */
 #define FFSR_EPI_LKAGATE 2  /* out = r1 + sa*(r1*ch_k[c] + ch_d[c])*sigmoid(conv + bias)     */
+#define FFSR_EPI_ACTGRAD 3  /* out = (conv + bias) * act'(r1): input gradient of a conv fused with the
+                               derivative of the activation that produced its input (r1 = that layer's
+                               pre-activation); tcgen05 path only                                  */
 
 #define FFSR_DT_F32 0
 #define FFSR_DT_BF16 1
@@ -134,6 +137,9 @@ typedef struct ffsr_conv_params {
                               taken iff in_dtype == FFSR_DT_BF16; CinPad = ceil64(Cin), CoutPad = ceil16(Cout)
                               rounded up to a multiple of 128 when > 128) */
   int r1_dtype, r2_dtype;  /* FFSR_DT_* of the residual tensors */
+  void* out2;              /* optional (tcgen05 path, FFSR_EPI_PLAIN with an activation): bf16 copy of the
+                              PRE-activation conv + bias, same strides as out -- saved for the backward pass */
+  int reserved;
 } ffsr_conv_params;
 
 int ffsr_conv2d(const ffsr_conv_params* p, cudaStream_t stream);
@@ -296,6 +302,14 @@ int ffsr_to_bf16_nhwc(const void* src, int src_dtype, long long sN, long long sY
                       int H, int W, int C, int Cpad, void* dst, cudaStream_t stream);
 size_t ffsr_conv2d_wgrad_tc_workspace_bytes(int N, int H, int W, int Cin, int Cout, int ksize);
 int ffsr_conv2d_wgrad_tc(const ffsr_wgrad_params* p, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+/* F.interpolate(mode="bilinear", align_corners=False) on dense channels-last tensors ([N][h][w][C] -> [N][H][W][C])
+ * and its adjoint (gradient w.r.t. the source); any C, fp32 or bf16 (fp32 arithmetic).
+ * hierarchical_fusion.py:156-186, enhanced_fusion_v2.py:735-791, edge_enhancement.py:208-250 */
+int ffsr_bilinear_forward(const void* src, int N, int h, int w, int C, void* dst, int H, int W, int dtype,
+                          cudaStream_t stream);
+int ffsr_bilinear_backward(const void* gout, int N, int H, int W, int C, void* gin, int h, int w, int dtype,
+                           cudaStream_t stream);
 
 #ifdef __cplusplus
 }

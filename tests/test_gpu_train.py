@@ -446,7 +446,9 @@ def test_cuda_graph_step_matches_eager_step():
     (l0, p0, rm0, nb0, _), (l1, p1, rm1, nb1, tr1) = results
     assert tr1._graph is not None
     assert max(abs(a - b) for a, b in zip(l0, l1)) < 2e-5, (l0, l1)
-    assert max(float((a - b).abs().max()) for a, b in zip(p0, p1)) < 2e-5     # atomics order differs run to run
+    # fp32 atomics order differs run to run; Adam turns a sign flip of a ~0 gradient into a 2*lr step, so the
+    # bound on individual weights is a few lr (2e-4), while the losses above agree to 2e-5
+    assert max(float((a - b).abs().max()) for a, b in zip(p0, p1)) < 6e-4
     assert nb0 == nb1 == 54 and float((rm0 - rm1).abs().max()) < 1e-5
 
 
@@ -465,3 +467,65 @@ def test_cuda_graph_dropout_masks_change_between_replays():
     assert tr._graph is not None
     # BN uses batch statistics and the weights are frozen, so replayed losses differ only through the dropout masks
     assert len({round(v, 9) for v in vals[3:]}) > 1, vals
+
+
+@pytest.mark.parametrize("C,h,w,H,W,dtype", [
+    (3, 17, 23, 68, 92, torch.float32), (64, 16, 16, 32, 32, torch.float32), (12, 64, 48, 16, 12, torch.float32),
+    (12, 64, 48, 32, 24, torch.float32), (1, 9, 11, 36, 44, torch.float32), (32, 12, 20, 48, 80, torch.bfloat16),
+    (4, 13, 7, 52, 28, torch.float32), (8, 10, 10, 25, 37, torch.float32),
+])
+def test_bilinear_forward_and_adjoint(C, h, w, H, W, dtype):
+    dev = _cuda()
+    g = torch.Generator().manual_seed(C * 100 + h)
+    x = torch.randn(2, C, h, w, generator=g)
+    gy = torch.randn(2, C, H, W, generator=g)
+    if dtype == torch.bfloat16:
+        x, gy = x.bfloat16().float(), gy.bfloat16().float()
+    xr = x.clone().requires_grad_()
+    yr = F.interpolate(xr, size=(H, W), mode="bilinear", align_corners=False)
+    yr.backward(gy)
+    xd = x.to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = T._bilinear(xd, (H, W))
+    y.backward(gy.to(dev).to(dtype))
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-6
+    assert _rel(y.float(), yr) < tol
+    assert _rel(xd.grad.float(), xr.grad) < tol
+
+
+@pytest.mark.parametrize("chans,ks,acts,N,H,W,out_bf16", [
+    ((3, 128, 128, 3), (3, 3, 3), ("gelu", "gelu", "none"), 1, 24, 40, False),
+    ((76, 64, 64), (3, 3), ("gelu", "gelu"), 2, 16, 16, True),
+    ((64, 16, 1), (1, 1), ("gelu", "sigmoid"), 1, 19, 37, False),
+    ((32, 32, 32, 32), (3, 3, 3), ("gelu", "gelu", "none"), 1, 33, 21, True),
+    ((32, 3), (1,), ("sigmoid",), 2, 16, 24, False),
+    ((128, 256, 128), (1, 1), ("gelu", "none"), 2, 9, 11, False),
+])
+def test_fused_conv_chain_against_sequential_reference(chans, ks, acts, N, H, W, out_bf16):
+    """_ConvChainTC (activation in the conv epilogue, act' in the input-gradient epilogue) against the same chain
+    in fp32 torch: bf16 operand rounding only."""
+    dev = _cuda()
+    amap = {"gelu": (K.ACT_GELU, F.gelu), "sigmoid": (K.ACT_SIGMOID, torch.sigmoid), "none": (K.ACT_NONE, lambda t: t)}
+    g = torch.Generator().manual_seed(sum(chans) + H)
+    x = torch.randn(N, chans[0], H, W, generator=g)
+    ws = [torch.randn(chans[i + 1], chans[i], k, k, generator=g) / (chans[i] * k * k) ** 0.5 * 1.5 for i, k in enumerate(ks)]
+    bs = [torch.randn(chans[i + 1], generator=g) * 0.1 if i % 2 == 0 else None for i in range(len(ks))]
+    gy = torch.randn(N, chans[-1], H, W, generator=g)
+    xr = x.clone().requires_grad_()
+    wr = [w.clone().requires_grad_() for w in ws]
+    br = [b.clone().requires_grad_() if b is not None else None for b in bs]
+    y = xr
+    for w, b, k, a in zip(wr, br, ks, acts):
+        y = amap[a][1](F.conv2d(y, w, b, padding=k // 2))
+    y.backward(gy)
+    xd = x.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_()
+    wd = [w.to(dev).requires_grad_() for w in ws]
+    bd = [b.to(dev).requires_grad_() if b is not None else None for b in bs]
+    out = T.conv_chain(xd, [(w, b, amap[a][0]) for w, b, a in zip(wd, bd, acts)], tc=True, out_bf16=out_bf16)
+    assert out.dtype == (torch.bfloat16 if out_bf16 else torch.float32)
+    out.backward(gy.to(dev).to(out.dtype))
+    assert _rel(out.float(), y) < 2e-2
+    assert _rel(xd.grad, xr.grad) < 3e-2
+    for i in range(len(ks)):
+        assert _rel(wd[i].grad, wr[i].grad) < 3e-2, i
+        if bs[i] is not None:
+            assert _rel(bd[i].grad, br[i].grad) < 3e-2, i

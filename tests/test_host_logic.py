@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_conv_params_struct_matches_header_layout():
     # 64-bit: 5 ptr/ll + 6 int + ... ; the C side is compiled from the same field order, so a
     # size check catches accidental drift between _cabi.ConvParams and ffsr_conv_params.
-    assert C.sizeof(_cabi.ConvParams) == _cabi.load().ffsr_conv_params_size() == 264
+    assert C.sizeof(_cabi.ConvParams) == _cabi.load().ffsr_conv_params_size() == 280
 
 
 def test_module_interface_matches_reference():
