@@ -148,41 +148,31 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+HOT_LAYER_DRAM_BYTES = 710.2e6 + 662.0e6       # per launch, bf16 path, from the ncu capture named in traffic_source
 TRAIN_FLOP_PER_HR_PIXEL = 5_921_000          # forward + backward (parameter gradients)
 STAGE_WEIGHTS = {"c2": {"l1": 1.0}, "c4": {"l1": 0.60, "swt": 0.25, "fft": 0.10, "ssim": 0.05}}
 
 
-def run_train(args):
-    """BASELINE configs[1] (c2: batch 32 x 64x64 LR, L1 + AdamW) / configs[3] (c4: batch 64 x 96x96 LR,
-    stage-3 fused losses): one data-parallel training step = forward + loss + backward + gradient
-    all-reduce + clip/AdamW/EMA.  Global batch fixed (strong scaling): each rank takes batch/world."""
+def measure_train(args, workload, dev, world, rank, local, steps, warmup, e2e=True):
+    """Device-timed data-parallel training steps of one workload; returns the result dict (rank 0 view)."""
     import torch
     import torch.distributed as dist
     import isr_b200
     from isr_b200.losses import CombinedLoss
     from isr_b200.trainer import FusionTrainer
+    from isr_b200.dist import max_over_ranks as _mor
     from oracle import fusion_oracle as O
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the fusion path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    gb, hw = (32, 64) if args.workload == "c2" else (64, 96)
+    gb, hw = (32, 64) if workload == "c2" else (64, 96)
     if args.batch:
         gb = args.batch
     B = max(gb // world, 1)
-    warmup = max(args.warmup, 3)
     torch.manual_seed(0)
     m = isr_b200.CompleteEnhancedFusionSR(None).to(dev)
     m.precision = args.precision
     crit = CombinedLoss()
     crit.set_weights({"charbonnier": 0, "l2": 0, "vgg": 0, "edge": 0, "clip": 0, "swt": 0, "fft": 0, "ssim": 0,
-                      **STAGE_WEIGHTS[args.workload]})
+                      **STAGE_WEIGHTS[workload]})
     tr = FusionTrainer(m, crit, lr=2e-4, betas=(0.9, 0.999), weight_decay=1e-4, max_grad_norm=1.0, ema_decay=0.999)
     lr, imgs, fts, hr = O.synthetic_inputs(B, hw, hw, seed=1234 + rank)
     host = [lr.pin_memory(), {k: v.pin_memory() for k, v in imgs.items()}, {k: v.pin_memory() for k, v in fts.items()},
@@ -195,69 +185,106 @@ def run_train(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    from isr_b200.dist import max_over_ranks as _mor
-    for _ in range(warmup):
+    for _ in range(max(warmup, 4)):                      # 3 eager steps + the CUDA-graph capture + 1 replay
         tr.step(*devs)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss, _ = tr.step(*devs)
     e1.record()
     barrier()
     ms = _mor(e0.elapsed_time(e1), dev)
     clocks = sampler.stop()
+    res = {"patches": B * world, "B": B, "hw": hw, "ms": ms / steps, "clocks": clocks, "h2d": h2d, "trainer": tr,
+           "launches": None}
+    if e2e:
+        def e2e_step():
+            d = [host[0].to(dev, non_blocking=True), {k: v.to(dev, non_blocking=True) for k, v in host[1].items()},
+                 {k: v.to(dev, non_blocking=True) for k, v in host[2].items()}, host[3].to(dev, non_blocking=True)]
+            l, _ = tr.step(*d)
+            return float(l)                                     # device -> host read of the step's loss
 
-    def e2e_step():
-        d = [host[0].to(dev, non_blocking=True), {k: v.to(dev, non_blocking=True) for k, v in host[1].items()},
-             {k: v.to(dev, non_blocking=True) for k, v in host[2].items()}, host[3].to(dev, non_blocking=True)]
-        l, _ = tr.step(*d)
-        return float(l)                                         # device -> host read of the step's loss
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            last = e2e_step()
+        e1.record()
+        barrier()
+        res["ms_e2e"] = _mor(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3), dev) / steps
+        res["last_loss"] = last
+    return res
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        last = e2e_step()
-    e1.record()
-    barrier()
-    ms_e2e = _mor(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3), dev)
-    if rank == 0:
-        tensor_peak, hbm_peak, peak_src = _peaks()
-        patches = B * world
-        tfl = TRAIN_FLOP_PER_HR_PIXEL * patches * 16 * hw * hw / (ms / args.steps * 1e-3) / 1e12
-        line = {
-            "metric": "fusion_train_patches_per_s", "value": patches * args.steps / (ms * 1e-3), "unit": "patches/s",
-            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload.upper()} fusion training step (BASELINE configs[{1 if args.workload == 'c2' else 3}]): "
-                                   f"global batch {patches} x {hw}x{hw} LR patches, losses {STAGE_WEIGHTS[args.workload]}, "
-                                   "clip 1.0 + AdamW + EMA, random-init weights",
-                       "global_batch": patches, "batch_per_gpu": B, "lr_patch": [hw, hw], "precision": args.precision,
-                       "partition": "data-parallel patches, one NCCL all-reduce of the flat 1.43M-float gradient bucket",
-                       "l2": "per-step activations (GBs) exceed the 126 MB L2; no explicit flush"},
-            "e2e": {"value": patches * args.steps / (ms_e2e * 1e-3), "unit": "patches/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last},
-            "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": tfl, "peak": tensor_peak, "unit": "TFLOP/s",
-                         "frac": tfl / tensor_peak, "traffic": None, "kernel": "whole training step (fwd+bwd), algorithmic FLOPs",
-                         "peak_source": peak_src},
-        }
-        print(json.dumps(line), flush=True)
+
+def _leave(world, trainer=None):
+    """The captured CUDA graph holds NCCL kernels; tearing the communicator down underneath it can hang at exit
+    (seen at N=2).  Drop the graph, drain the device, then leave without the NCCL destructor."""
+    import torch
+    import torch.distributed as dist
     if world > 1:
-        # The captured CUDA graph holds NCCL kernels; tearing the communicator down underneath it can hang at
-        # exit (seen at N=2).  Drop the graph, drain the device, then leave without the NCCL destructor.
-        tr._graph = None
+        if trainer is not None:
+            trainer._graph = None
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def run_train(args):
+    """BASELINE configs[1] (c2: batch 32 x 64x64 LR, L1 + AdamW) / configs[3] (c4: batch 64 x 96x96 LR,
+    stage-3 fused losses): one data-parallel training step = forward + loss + backward + gradient
+    all-reduce + clip/AdamW/EMA.  Global batch fixed (strong scaling): each rank takes batch/world."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the fusion path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 4)
+    r = measure_train(args, args.workload, dev, world, rank, local, args.steps, warmup)
+    if rank == 0:
+        tensor_peak, hbm_peak, peak_src = _peaks()
+        patches, hw, ms = r["patches"], r["hw"], r["ms"]
+        tfl = TRAIN_FLOP_PER_HR_PIXEL * patches * 16 * hw * hw / (ms * 1e-3) / 1e12
+        line = {
+            "metric": "fusion_train_patches_per_s", "value": patches / (ms * 1e-3), "unit": "patches/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": train_config(args.workload, patches, r["B"], hw, args.precision),
+            "e2e": {"value": patches / (r["ms_e2e"] * 1e-3), "unit": "patches/s", "h2d_bytes_per_step": r["h2d"],
+                    "d2h_bytes_per_step": 4, "ms_per_step": r["ms_e2e"], "last_loss": r["last_loss"]},
+            "gpu_launches": "one CUDA-graph replay per step (~2,000 captured kernel launches)",
+            "clocks": r["clocks"],
+            "roofline": {"bound": "tensor", "achieved": tfl, "peak": tensor_peak, "unit": "TFLOP/s",
+                         "frac": tfl / tensor_peak, "traffic": None,
+                         "kernel": "whole training step (fwd+bwd), algorithmic FLOPs; per-kernel figures: "
+                                   "profiles/r01_conv_train_microbench.txt, profiles/r01_wgrad_tc_128x128_ncu_full.txt",
+                         "peak_source": peak_src},
+        }
+        print(json.dumps(line), flush=True)
+    _leave(world, r["trainer"])
+
+
+def train_config(workload, patches, B, hw, precision):
+    return {"workload": f"{workload.upper()} fusion training step (BASELINE configs[{1 if workload == 'c2' else 3}]): "
+                        f"global batch {patches} x {hw}x{hw} LR patches, losses {STAGE_WEIGHTS[workload]}, "
+                        "clip 1.0 + AdamW + EMA, random-init weights",
+            "global_batch": patches, "batch_per_gpu": B, "lr_patch": [hw, hw], "precision": precision,
+            "partition": "data-parallel patches, one NCCL all-reduce of the flat 1.43M-float gradient bucket",
+            "l2": "per-step activations (GBs) exceed the 126 MB L2; no explicit flush"}
 
 
 def main():
@@ -272,6 +299,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("FFSR_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--lr", type=int, nargs=2, default=[LR_H, LR_W], help="LR size (parity/debug runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the C2 training-step figure added to the C3 line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -365,6 +393,23 @@ def main():
     barrier()
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
 
+    # ---- second half of BASELINE.json's metric: training patches/s (C2 step, same ranks) -------------
+    train = None
+    trainer = None
+    if not args.no_train and tuple(args.lr) == (LR_H, LR_W):
+        del pipe
+        m._engine = None
+        torch.cuda.empty_cache()
+        try:
+            r = measure_train(args, "c2", dev, world, rank, local, 5, 4, e2e=False)
+            trainer = r["trainer"]
+            train = {"metric": "fusion_train_patches_per_s", "value": r["patches"] / (r["ms"] * 1e-3), "unit": "patches/s",
+                     "ms_per_step": r["ms"], "steps": 5, "scaling": "strong",
+                     "config": train_config("c2", r["patches"], r["B"], r["hw"], args.precision),
+                     "tflops_algorithmic": TRAIN_FLOP_PER_HR_PIXEL * r["patches"] * 16 * r["hw"] ** 2 / (r["ms"] * 1e-3) / 1e12}
+        except Exception as exc:                               # the headline line must survive a training failure
+            train = {"error": repr(exc)[:300]}
+
     if rank == 0:
         tensor_peak, hbm_peak, peak_src = _peaks()
         hot_flop = HOT_LAYER_FLOP_PER_HR_PIXEL * B * 16 * H * W
@@ -385,13 +430,18 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                         "frac": (achieved / tensor_peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / tensor_peak) if achieved else None, "traffic": HOT_LAYER_DRAM_BYTES if args.precision == "bf16" else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
+                                           "kernel at this size (profiles/r01_convtc_refine_c3_ncu_full.txt); algorithmic "
+                                           "bytes = 128 ch x 2 B x 2.766 MPix in + out = 1.416e9",
                          "kernel": "3x3 128->128 refinement conv (refine.2/4/6/8), "
                                    + ("k_conv_ffma<64,3> fp32 CUDA-core path" if args.precision == "fp32" else "tcgen05 implicit GEMM"),
                          "launch_ms": hot_mean_ms, "launches_timed": len(hot_ms), "flop_per_launch": hot_flop,
                          "peak_source": peak_src,
                          "whole_forward_tflops": FLOP_PER_HR_PIXEL * B * 16 * H * W / (ms / args.steps * 1e-3) / 1e12},
         }
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             ch, cw = (H, W) if threads >= 16 else (H // 2, W // 2)
@@ -401,6 +451,8 @@ def main():
                                               f"{t:.1f} s on {threads} threads"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        if trainer is not None:
+            _leave(world, trainer)
         dist.destroy_process_group()
 
 
