@@ -31,6 +31,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// GELU with erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7) on the fast-math units: used where the
+// result is rounded to bf16 anyway (bf16 precision mode); ~2x cheaper than erff().
+__device__ __forceinline__ float gelu_as(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+template <bool FAST>
+__device__ __forceinline__ float gelu_sel(float x) { return FAST ? gelu_as(x) : gelu_erf(x); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {

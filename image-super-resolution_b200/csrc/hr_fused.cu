@@ -1,6 +1,7 @@
 // HR-side fused elementwise / resampling kernels (all HBM-bound; one thread per pixel or
 // per pixel x 4-channel group, coalesced planar reads, channels-last vector writes).
 // Each kernel cites the reference op sequence it replaces in include/ffsr_b200.h.
+#include <type_traits>
 #include "common.cuh"
 #include "../../include/ffsr_b200.h"
 
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(128) k_modulate_hr(Img4 imgs, const float* __r
   const long HWh = (long)Hh * Wh;
   const long pix = (long)Y * Wh + X;
   const BilinTap ty = bilin_tap(Y, H, Hh), tx = bilin_tap(X, W, Wh);
+  constexpr bool FAST = !std::is_same<T, float>::value;      // bf16 mode: A&S erf (1.5e-7), results are rounded to bf16
   float o[12];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -76,10 +78,10 @@ __global__ void __launch_bounds__(128) k_modulate_hr(Img4 imgs, const float* __r
       for (int c4 = 0; c4 < 8; ++c4) {
         const float4 a = p00[c4], bq = p01[c4], c = p10[c4], d = p11[c4];
         float g[4];
-        g[0] = gelu_erf(ty.w0 * (tx.w0 * a.x + tx.w1 * bq.x) + ty.w1 * (tx.w0 * c.x + tx.w1 * d.x));
-        g[1] = gelu_erf(ty.w0 * (tx.w0 * a.y + tx.w1 * bq.y) + ty.w1 * (tx.w0 * c.y + tx.w1 * d.y));
-        g[2] = gelu_erf(ty.w0 * (tx.w0 * a.z + tx.w1 * bq.z) + ty.w1 * (tx.w0 * c.z + tx.w1 * d.z));
-        g[3] = gelu_erf(ty.w0 * (tx.w0 * a.w + tx.w1 * bq.w) + ty.w1 * (tx.w0 * c.w + tx.w1 * d.w));
+        g[0] = gelu_sel<FAST>(ty.w0 * (tx.w0 * a.x + tx.w1 * bq.x) + ty.w1 * (tx.w0 * c.x + tx.w1 * d.x));
+        g[1] = gelu_sel<FAST>(ty.w0 * (tx.w0 * a.y + tx.w1 * bq.y) + ty.w1 * (tx.w0 * c.y + tx.w1 * d.y));
+        g[2] = gelu_sel<FAST>(ty.w0 * (tx.w0 * a.z + tx.w1 * bq.z) + ty.w1 * (tx.w0 * c.z + tx.w1 * d.z));
+        g[3] = gelu_sel<FAST>(ty.w0 * (tx.w0 * a.w + tx.w1 * bq.w) + ty.w1 * (tx.w0 * c.w + tx.w1 * d.w));
 #pragma unroll
         for (int k = 0; k < 3; ++k)
 #pragma unroll
@@ -209,6 +211,41 @@ __global__ void __launch_bounds__(256) k_resize_nhwc(const T* __restrict__ src, 
                 ty.w0 * (tx.w0 * a.w + tx.w1 * b.w) + ty.w1 * (tx.w0 * c.w + tx.w1 * d.w));
 }
 
+// bf16, 8 channels (16 bytes) per thread
+__global__ void __launch_bounds__(256) k_resize_nhwc_bf16x8(const __nv_bfloat16* __restrict__ src, int h, int w, int C8,
+                                                            long long src_sX, __nv_bfloat16* __restrict__ dst, int H, int W,
+                                                            long long dst_sX, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  const long pix = i / C8;
+  const int X = (int)(pix % W), Y = (int)((pix / W) % H);
+  const long n = pix / ((long)W * H);
+  const BilinTap ty = bilin_tap(Y, h, H), tx = bilin_tap(X, w, W);
+  const __nv_bfloat16* base = src + n * h * w * src_sX + 8 * c8;
+  const uint4 a = *reinterpret_cast<const uint4*>(base + ((long)ty.i0 * w + tx.i0) * src_sX);
+  const uint4 b = *reinterpret_cast<const uint4*>(base + ((long)ty.i0 * w + tx.i1) * src_sX);
+  const uint4 c = *reinterpret_cast<const uint4*>(base + ((long)ty.i1 * w + tx.i0) * src_sX);
+  const uint4 d = *reinterpret_cast<const uint4*>(base + ((long)ty.i1 * w + tx.i1) * src_sX);
+  const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
+  const float w00 = ty.w0 * tx.w0, w01 = ty.w0 * tx.w1, w10 = ty.w1 * tx.w0, w11 = ty.w1 * tx.w1;
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pa + k));
+    const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pb + k));
+    const float2 fc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pc + k));
+    const float2 fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pd + k));
+    // same association as the 4-channel kernel: ty.w0*(tx.w0*a + tx.w1*b) + ty.w1*(tx.w0*c + tx.w1*d)
+    const float r0 = ty.w0 * (tx.w0 * fa.x + tx.w1 * fb.x) + ty.w1 * (tx.w0 * fc.x + tx.w1 * fd.x);
+    const float r1 = ty.w0 * (tx.w0 * fa.y + tx.w1 * fb.y) + ty.w1 * (tx.w0 * fc.y + tx.w1 * fd.y);
+    __nv_bfloat162 hh = __floats2bfloat162_rn(r0, r1);
+    o[k] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  (void)w00; (void)w01; (void)w10; (void)w11;
+  *reinterpret_cast<uint4*>(dst + pix * dst_sX + 8 * c8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 extern "C" int ffsr_resize_nhwc(const void* src, int N, int h, int w, int C, long long src_sX, void* dst, int H, int W,
                                 long long dst_sX, int dtype, cudaStream_t stream) {
   FFSR_REQUIRE(src && dst, FFSR_ERR_ARG, "resize_nhwc: null pointer");
@@ -216,6 +253,13 @@ extern "C" int ffsr_resize_nhwc(const void* src, int N, int h, int w, int C, lon
   const int esz = dtype == FFSR_DT_BF16 ? 2 : 4;
   FFSR_REQUIRE(((uintptr_t)src % (4 * esz)) == 0 && ((uintptr_t)dst % (4 * esz)) == 0 && src_sX % 4 == 0 && dst_sX % 4 == 0,
                FFSR_ERR_ALIGN, "resize_nhwc: vector alignment");
+  if (dtype == FFSR_DT_BF16 && C % 8 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0 && src_sX % 8 == 0 &&
+      dst_sX % 8 == 0) {
+    const long total8 = (long)N * H * W * (C / 8);
+    k_resize_nhwc_bf16x8<<<ceil_div(total8, 256), 256, 0, stream>>>((const __nv_bfloat16*)src, h, w, C / 8, src_sX,
+                                                                    (__nv_bfloat16*)dst, H, W, dst_sX, total8);
+    return ffsr_check_launch("resize_nhwc");
+  }
   const long total = (long)N * H * W * (C / 4);
   if (dtype == FFSR_DT_BF16)
     k_resize_nhwc<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, stream>>>((const __nv_bfloat16*)src, h, w, C / 4, src_sX, (__nv_bfloat16*)dst, H, W, dst_sX, total);
@@ -251,7 +295,7 @@ __global__ void __launch_bounds__(128) k_spatial_gate(const T* __restrict__ x, l
     float a = sb1[h];
 #pragma unroll
     for (int c = 0; c < C; ++c) a = fmaf(sw1[h][c], v[c], a);
-    z = fmaf(sw2[h], gelu_erf(a), z);
+    z = fmaf(sw2[h], gelu_sel<!std::is_same<T, float>::value>(a), z);
   }
   const float g = sigmoid_acc(z);
 #pragma unroll

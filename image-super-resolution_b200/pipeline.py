@@ -83,6 +83,8 @@ class FusionEngine:
         # optional per-launch CUDA-event timing of named conv layers (bench.py roofline):
         # {weight name: [(start_event, end_event), ...]}
         self.timed_layers = None
+        self.overlap_routing = True    # phases 3 + 6 on a side stream, concurrent with phases 4 / 5
+        self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ weights
     def _state_key(self, dev):
@@ -377,6 +379,23 @@ class FusionEngine:
                    self._twiddles(W, dev).data_ptr(), fws.data_ptr(), fft_bytes, raw9.data_ptr(), S)
         self.launches += 4
 
+        # Phases 3 + 6 (the fp32 LR routing chain: FFMA-bound kernels) only meet the rest of the network at the
+        # blend, while phase 4 / the HR modulation / phase 5 depend on the expert features and images alone: run
+        # the routing chain on a side stream so its CUDA-core kernels fill the SMs between the short tcgen05 and
+        # latency-bound elementwise launches of the main chain.
+        main_handle = self._stream
+        overlap = self.overlap_routing and not want_inter and lr.is_cuda
+        if overlap:
+            side = self._side.get(str(dev))
+            if side is None:
+                side = self._side[str(dev)] = torch.cuda.Stream(dev)
+            main_stream = torch.cuda.current_stream(dev)
+            ev = torch.cuda.Event()
+            ev.record(main_stream)
+            side.wait_event(ev)
+            torch.cuda.set_stream(side)          # first-use workspace fills of this block must be ordered with it
+            S = self._stream = C.c_void_p(side.cuda_stream)
+
         # ---------------- Phase 3 ----------------
         cb = m.cross_band
         nq = 9 if want_inter else 3                       # bands 3..8 feed nothing downstream
@@ -409,6 +428,12 @@ class FusionEngine:
         self.conv(nhwc(s_b), B, H, W, 32, "ds.g4", 4, 1, nhwc(graw))
         self._call(lib.ffsr_gate_finalize, graw.data_ptr(), diff.data_ptr(), B, H, W, pp("dynamic_selector.temperature"),
                    gates.data_ptr(), S)
+
+        if overlap:
+            routing_done = torch.cuda.Event()
+            routing_done.record(side)
+            torch.cuda.set_stream(main_stream)
+            S = self._stream = main_handle
 
         # ---------------- Phase 4 (LR part) ----------------
         co = m.collaborative
@@ -516,6 +541,9 @@ class FusionEngine:
         hier = self._buf("mr.hier", (B, Hh, Wh, 4), dev, zero=True)
         self.conv(nhwc(f3), B, Hh, Wh, 32, "mr.rgb0", 16, 3, nhwc(u16), act=K.ACT_GELU)
         self.conv(nhwc(u16), B, Hh, Wh, 16, "mr.rgb2", 3, 3, nhwc(hier), act=K.ACT_SIGMOID)
+
+        if overlap:
+            torch.cuda.current_stream(dev).wait_event(routing_done)
 
         # ---------------- Phase 5b / 6 blend ----------------
         fused_before = torch.empty(B, 3, Hh, Wh, device=dev, dtype=f32) if want_inter else None
