@@ -396,7 +396,9 @@ def main():
     # ---- second half of BASELINE.json's metric: training patches/s (C2 step, same ranks) -------------
     train = None
     trainer = None
-    if not args.no_train and tuple(args.lr) == (LR_H, LR_W):
+    # (N=1 only: the multi-GPU scaling runs keep to the headline metric; `--workload c2 --gpus N` measures the
+    # data-parallel training step on its own)
+    if not args.no_train and world == 1 and tuple(args.lr) == (LR_H, LR_W):
         del pipe
         m._engine = None
         torch.cuda.empty_cache()

@@ -116,6 +116,10 @@ PROTOTYPES = {
     "ffsr_conv2d_wgrad_tc": (_I, [C.POINTER(WgradParams), _P, _SZ, _P]),
     "ffsr_bilinear_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     "ffsr_bilinear_backward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
+    "ffsr_gate_mul_forward": (_I, [_P, _P, _L, _I, _P, _I, _P]),
+    "ffsr_gate_mul_backward": (_I, [_P, _P, _P, _L, _I, _P, _P, _I, _P]),
+    "ffsr_axpby_forward": (_I, [_P, _P, _P, _L, _P, _P, _L, _I, _P, _I, _P]),
+    "ffsr_axpby_backward": (_I, [_P, _P, _P, _L, _P, _P, _L, _I, _P, _P, _P, _I, _P]),
     # ---- fused optimizer ----
     "ffsr_sumsq": (_I, [_P, _L, _P, _P]),
     "ffsr_adamw_ema_step": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _P, _P, _F, _F, _F, _P]),

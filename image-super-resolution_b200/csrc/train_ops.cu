@@ -393,31 +393,48 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
   }
 }
 
-// y = (x - mean) * rstd * w + b   (per group g, channel c)
-__global__ void k_bn_apply(const float* __restrict__ x, long R, int C, int G, const float* __restrict__ mean,
-                           const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
-                           float* __restrict__ y) {
-  const long total = (long)G * R * C;
+// y = (x - mean) * rstd * w + b   (per group g, channel c); float4 over channels (C % 4 == 0)
+__global__ void __launch_bounds__(256) k_bn_apply(const float* __restrict__ x, long R, int C, int G, const float* __restrict__ mean,
+                                                  const float* __restrict__ rstd, const float* __restrict__ w,
+                                                  const float* __restrict__ b, float* __restrict__ y) {
+  const int C4 = C >> 2;
+  const long per_g = R * C4, total = (long)G * per_g;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int g = (int)(i / (R * C));
-    const long gc = (long)g * C + c;
-    y[i] = fmaf((x[i] - mean[gc]) * rstd[gc], w[c], b[c]);
+    const int c = (int)(i % C4) << 2;
+    const long gc = (i / per_g) * C + c;
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 mu = *reinterpret_cast<const float4*>(mean + gc), rs = *reinterpret_cast<const float4*>(rstd + gc);
+    const float4 wv = *reinterpret_cast<const float4*>(w + c), bv = *reinterpret_cast<const float4*>(b + c);
+    float4 o;
+    o.x = fmaf((xv.x - mu.x) * rs.x, wv.x, bv.x);
+    o.y = fmaf((xv.y - mu.y) * rs.y, wv.y, bv.y);
+    o.z = fmaf((xv.z - mu.z) * rs.z, wv.z, bv.z);
+    o.w = fmaf((xv.w - mu.w) * rs.w, wv.w, bv.w);
+    reinterpret_cast<float4*>(y)[i] = o;
   }
 }
 // dx = w*rstd * (dy - sdy/R - xhat * sdyx/R)
-__global__ void k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, long R, int C, int G,
-                               const float* __restrict__ mean, const float* __restrict__ rstd,
-                               const float* __restrict__ w, const float* __restrict__ sdy,
-                               const float* __restrict__ sdyx, float* __restrict__ dx) {
-  const long total = (long)G * R * C;
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, long R, int C,
+                                                      int G, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                      const float* __restrict__ w, const float* __restrict__ sdy,
+                                                      const float* __restrict__ sdyx, float* __restrict__ dx) {
+  const int C4 = C >> 2;
+  const long per_g = R * C4, total = (long)G * per_g;
   const float invR = 1.0f / (float)R;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int g = (int)(i / (R * C));
-    const long gc = (long)g * C + c;
-    const float xh = (x[i] - mean[gc]) * rstd[gc];
-    dx[i] = w[c] * rstd[gc] * (dy[i] - sdy[gc] * invR - xh * sdyx[gc] * invR);
+    const int c = (int)(i % C4) << 2;
+    const long gc = (i / per_g) * C + c;
+    const float4 xv = reinterpret_cast<const float4*>(x)[i], gv = reinterpret_cast<const float4*>(dy)[i];
+    const float* xs = &xv.x;
+    const float* gs = &gv.x;
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float rs = rstd[gc + k];
+      const float xh = (xs[k] - mean[gc + k]) * rs;
+      o[k] = w[c + k] * rs * (gs[k] - sdy[gc + k] * invR - xh * sdyx[gc + k] * invR);
+    }
+    reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -694,6 +711,98 @@ __global__ void __launch_bounds__(256) k_bilinear_bwd(const T* __restrict__ gout
   }
 }
 
+// ------------------------------------------------------------------------------------
+// fused few-pass elementwise nodes of the training graph
+// ------------------------------------------------------------------------------------
+// out[p][c] = y[p][c] * g[p]        (SpatialGate / edge attention: a 1-channel map gating C channels)
+template <typename T>
+__global__ void __launch_bounds__(256) k_gate_mul_fwd(const T* __restrict__ y, const float* __restrict__ g, long NP, int C,
+                                                      T* __restrict__ out) {
+  const int G = C >> 2;
+  const long total = NP * G;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i / G;
+    const float gv = g[pix];
+    const T* s = y + i * 4;
+    T* o = out + i * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = from_f32<T>(to_f32<T>(s[k]) * gv);
+  }
+}
+// dy[p][c] = gout[p][c] * g[p];  dg[p] = sum_c gout[p][c] * y[p][c]   (one thread per pixel)
+template <typename T>
+__global__ void __launch_bounds__(128) k_gate_mul_bwd(const T* __restrict__ y, const float* __restrict__ g,
+                                                      const T* __restrict__ gout, long NP, int C, T* __restrict__ dy,
+                                                      float* __restrict__ dg) {
+  for (long pix = (long)blockIdx.x * blockDim.x + threadIdx.x; pix < NP; pix += (long)gridDim.x * blockDim.x) {
+    const float gv = g[pix];
+    const T* ys = y + pix * C;
+    const T* gs = gout + pix * C;
+    T* o = dy + pix * C;
+    float acc = 0.f;
+    for (int c = 0; c < C; c += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float go = to_f32<T>(gs[c + k]);
+        acc = fmaf(go, to_f32<T>(ys[c + k]), acc);
+        o[c + k] = from_f32<T>(go * gv);
+      }
+    }
+    dg[pix] = acc;
+  }
+}
+
+// out = a + s1*b (+ s2*c);  c may be a channel slice (pixel pitch c_pitch >= C)
+template <typename T>
+__global__ void __launch_bounds__(256) k_axpby_fwd(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
+                                                   long c_pitch, const float* __restrict__ s1, const float* __restrict__ s2,
+                                                   long NP, int C, T* __restrict__ out) {
+  const float k1 = s1[0], k2 = c ? s2[0] : 0.f;
+  const long total = NP * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float v = fmaf(k1, to_f32<T>(b[i]), to_f32<T>(a[i]));
+    if (c) {
+      const long pix = i / C;
+      v = fmaf(k2, to_f32<T>(c[pix * c_pitch + (i - pix * C)]), v);
+    }
+    out[i] = from_f32<T>(v);
+  }
+}
+// db = s1*g, dc = s2*g, ds1 += sum g*b, ds2 += sum g*c
+template <typename T>
+__global__ void __launch_bounds__(256) k_axpby_bwd(const T* __restrict__ g, const T* __restrict__ b, const T* __restrict__ c,
+                                                   long c_pitch, const float* __restrict__ s1, const float* __restrict__ s2,
+                                                   long NP, int C, T* __restrict__ db, T* __restrict__ dc,
+                                                   float* __restrict__ ds) {
+  __shared__ float sh[2][8];
+  const float k1 = s1[0], k2 = c ? s2[0] : 0.f;
+  const long total = NP * C;
+  float a1 = 0.f, a2 = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const float gv = to_f32<T>(g[i]);
+    a1 = fmaf(gv, to_f32<T>(b[i]), a1);
+    db[i] = from_f32<T>(k1 * gv);
+    if (c) {
+      const long pix = i / C;
+      a2 = fmaf(gv, to_f32<T>(c[pix * c_pitch + (i - pix * C)]), a2);
+      dc[i] = from_f32<T>(k2 * gv);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a1 += __shfl_down_sync(0xffffffffu, a1, o);
+    a2 += __shfl_down_sync(0xffffffffu, a2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a1; sh[1][threadIdx.x >> 5] = a2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int i = 0; i < 8; ++i) { t1 += sh[0][i]; t2 += sh[1][i]; }
+    atomicAdd(ds, t1);
+    if (c) atomicAdd(ds + 1, t2);
+  }
+}
+
 inline void colsum_geom(int C, dim3& block, int& CT) {
   CT = 1;
   while (CT < C && CT < 64) CT <<= 1;
@@ -796,8 +905,8 @@ extern "C" int ffsr_bn_stats(const float* x, int G, long R, int C, double* sum, 
 
 extern "C" int ffsr_bn_apply(const float* x, int G, long R, int C, const float* mean, const float* rstd, const float* w,
                              const float* b, float* y, cudaStream_t stream) {
-  FFSR_REQUIRE(x && mean && rstd && w && b && y && G > 0 && R > 0 && C > 0, FFSR_ERR_ARG, "bn_apply: bad argument");
-  const long total = (long)G * R * C;
+  FFSR_REQUIRE(x && mean && rstd && w && b && y && G > 0 && R > 0 && C > 0 && C % 4 == 0, FFSR_ERR_ARG, "bn_apply: bad argument (C %% 4 == 0)");
+  const long total = (long)G * R * (C / 4);
   k_bn_apply<<<(int)min((long)148 * 16, (total + 255) / 256), 256, 0, stream>>>(x, R, C, G, mean, rstd, w, b, y);
   return ffsr_check_launch("bn_apply");
 }
@@ -818,7 +927,8 @@ extern "C" int ffsr_bn_backward(const float* x, const float* dy, int G, long R, 
   k_bn_bwd_reduce<<<grid, block, 2 * 256 * sizeof(float), stream>>>(x, dy, R, C, rpb, mean, rstd, sdy, sdyx);
   int rc = ffsr_check_launch("bn_backward_reduce");
   if (rc) return rc;
-  const long total = (long)G * R * C;
+  FFSR_REQUIRE(C % 4 == 0, FFSR_ERR_ARG, "bn_backward: C must be a multiple of 4");
+  const long total = (long)G * R * (C / 4);
   k_bn_bwd_apply<<<(int)min((long)148 * 16, (total + 255) / 256), 256, 0, stream>>>(x, dy, R, C, G, mean, rstd, w, sdy, sdyx, dx);
   return ffsr_check_launch("bn_backward_apply");
 }
@@ -904,4 +1014,45 @@ extern "C" int ffsr_bilinear_backward(const void* gout, int N, int H, int W, int
   FFSR_REQUIRE(gout && gin && N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0, FFSR_ERR_ARG, "bilinear_backward: bad argument");
   FFSR_REQUIRE((long)H <= 6L * h + 6 && (long)W <= 6L * w + 6, FFSR_ERR_ARG, "bilinear_backward: upscaling factors above 6 are not built");
   return launch_bilinear<true>(gout, N, h, w, C, gin, H, W, dtype, stream);
+}
+
+extern "C" int ffsr_gate_mul_forward(const void* y, const float* g, long NP, int C, void* out, int dtype, cudaStream_t stream) {
+  FFSR_REQUIRE(y && g && out && NP > 0 && C > 0 && C % 4 == 0, FFSR_ERR_ARG, "gate_mul_forward: bad argument (C %% 4 == 0)");
+  const long total = NP * (C / 4);
+  const int grid = (int)min((long)148 * 16, (total + 255) / 256);
+  if (dtype == FFSR_DT_BF16) k_gate_mul_fwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)y, g, NP, C, (__nv_bfloat16*)out);
+  else k_gate_mul_fwd<float><<<grid, 256, 0, stream>>>((const float*)y, g, NP, C, (float*)out);
+  return ffsr_check_launch("gate_mul_forward");
+}
+
+extern "C" int ffsr_gate_mul_backward(const void* y, const float* g, const void* gout, long NP, int C, void* dy, float* dg,
+                                      int dtype, cudaStream_t stream) {
+  FFSR_REQUIRE(y && g && gout && dy && dg && NP > 0 && C > 0 && C % 4 == 0, FFSR_ERR_ARG, "gate_mul_backward: bad argument");
+  const int grid = (int)min((long)148 * 32, (NP + 127) / 128);
+  if (dtype == FFSR_DT_BF16)
+    k_gate_mul_bwd<__nv_bfloat16><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)y, g, (const __nv_bfloat16*)gout, NP, C, (__nv_bfloat16*)dy, dg);
+  else k_gate_mul_bwd<float><<<grid, 128, 0, stream>>>((const float*)y, g, (const float*)gout, NP, C, (float*)dy, dg);
+  return ffsr_check_launch("gate_mul_backward");
+}
+
+extern "C" int ffsr_axpby_forward(const void* a, const void* b, const void* c, long c_pitch, const float* s1, const float* s2,
+                                  long NP, int C, void* out, int dtype, cudaStream_t stream) {
+  FFSR_REQUIRE(a && b && s1 && out && NP > 0 && C > 0 && (!c || s2), FFSR_ERR_ARG, "axpby_forward: bad argument");
+  const long total = NP * C;
+  const int grid = (int)min((long)148 * 16, (total + 255) / 256);
+  if (dtype == FFSR_DT_BF16)
+    k_axpby_fwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)c, c_pitch, s1, s2, NP, C, (__nv_bfloat16*)out);
+  else k_axpby_fwd<float><<<grid, 256, 0, stream>>>((const float*)a, (const float*)b, (const float*)c, c_pitch, s1, s2, NP, C, (float*)out);
+  return ffsr_check_launch("axpby_forward");
+}
+
+extern "C" int ffsr_axpby_backward(const void* g, const void* b, const void* c, long c_pitch, const float* s1, const float* s2,
+                                   long NP, int C, void* db, void* dc, float* ds, int dtype, cudaStream_t stream) {
+  FFSR_REQUIRE(g && b && s1 && db && ds && NP > 0 && C > 0 && (!c || (s2 && dc)), FFSR_ERR_ARG, "axpby_backward: bad argument");
+  const long total = NP * C;
+  const int grid = (int)min((long)148 * 8, (total + 255) / 256);
+  if (dtype == FFSR_DT_BF16)
+    k_axpby_bwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)b, (const __nv_bfloat16*)c, c_pitch, s1, s2, NP, C, (__nv_bfloat16*)db, (__nv_bfloat16*)dc, ds);
+  else k_axpby_bwd<float><<<grid, 256, 0, stream>>>((const float*)g, (const float*)b, (const float*)c, c_pitch, s1, s2, NP, C, (float*)db, (float*)dc, ds);
+  return ffsr_check_launch("axpby_backward");
 }

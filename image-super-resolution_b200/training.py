@@ -165,6 +165,11 @@ def _bf16_operand(x: torch.Tensor):
             return torch.as_strided(x, (N, H, W, sX), (sN, sY, sX, 1)), Cc
     cpad = (Cc + 7) // 8 * 8
     buf = torch.empty(N, H, W, cpad, device=x.device, dtype=torch.bfloat16)
+    if x.dtype == torch.float32 and Cc >= 16 and x.is_contiguous() and N <= 65535:
+        # NCHW planes (cached expert features): tiled shared-memory transpose; pad channels are never read by TMA
+        _ck(_lib().ffsr_nchw_to_nhwc_bf16(x.data_ptr(), N, Cc, H * W, buf.data_ptr(), H * W * cpad, cpad, _S(x)),
+            "nchw_to_nhwc_bf16")
+        return buf, Cc
     sC = x.stride(1) if Cc > 1 else 1
     _ck(_lib().ffsr_to_bf16_nhwc(x.data_ptr(), _dt(x), x.stride(0), x.stride(2), x.stride(3), sC, N, H, W, Cc, cpad,
                                  buf.data_ptr(), _S(x)), "to_bf16_nhwc")
@@ -428,6 +433,88 @@ def sigmoid(x):
 
 
 # --------------------------------------------------------------------------------------
+# fused few-pass elementwise nodes
+# --------------------------------------------------------------------------------------
+class _GateMul(torch.autograd.Function):
+    """out = y * g, g a 1-channel fp32 map broadcast over the channels of y."""
+
+    @staticmethod
+    def forward(ctx, y, g):
+        y = _cl(y)
+        N, Cc, H, W = y.shape
+        g = g.float().contiguous()                       # [N,1,H,W]: layout-agnostic
+        out = torch.empty_like(y)
+        _ck(_lib().ffsr_gate_mul_forward(y.data_ptr(), g.data_ptr(), N * H * W, Cc, out.data_ptr(), _dt(y), _S(y)), "gate_mul_forward")
+        ctx.save_for_backward(y, g)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        y, g = ctx.saved_tensors
+        N, Cc, H, W = y.shape
+        if gout.dtype != y.dtype or gout.stride() != y.stride():
+            gout = torch.empty_like(y).copy_(gout)
+        dy = torch.empty_like(y)
+        dg = torch.empty_like(g)
+        _ck(_lib().ffsr_gate_mul_backward(y.data_ptr(), g.data_ptr(), gout.data_ptr(), N * H * W, Cc, dy.data_ptr(),
+                                          dg.data_ptr(), _dt(y), _S(y)), "gate_mul_backward")
+        return dy, dg
+
+
+def gate_mul(y, g):
+    if y.shape[1] % 4 != 0:
+        return y * g.to(y.dtype)
+    return _GateMul.apply(y, g)
+
+
+class _Axpby(torch.autograd.Function):
+    """out = a + s1*b (+ s2*c): learnable scalar-weighted residual sums in one pass each way."""
+
+    @staticmethod
+    def forward(ctx, a, b, s1, c, s2):
+        a = _cl(a)
+        b = _cl(b) if b.dtype == a.dtype else _cl(b.to(a.dtype))
+        N, Cc, H, W = a.shape
+        cp, cptr = 0, None
+        if c is not None:
+            if c.dtype != a.dtype:
+                c = c.to(a.dtype)
+            ok = c.stride(1) == 1 and c.stride(2) == W * c.stride(3) and c.stride(0) == H * W * c.stride(3)
+            if not ok:
+                c = _cl(c)
+            cp, cptr = c.stride(3), c.data_ptr()
+        out = torch.empty_like(a)
+        s1c = s1.detach().reshape(1).float()
+        s2c = s2.detach().reshape(1).float() if c is not None else None
+        _ck(_lib().ffsr_axpby_forward(a.data_ptr(), b.data_ptr(), cptr, cp, s1c.data_ptr(),
+                                      s2c.data_ptr() if s2c is not None else None, N * H * W, Cc, out.data_ptr(), _dt(a), _S(a)),
+            "axpby_forward")
+        ctx.save_for_backward(b, c if c is not None else b, s1c, s2c if s2c is not None else s1c)
+        ctx.has_c = c is not None
+        ctx.c_pitch = cp
+        ctx.shape = (N, Cc, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        b, c, s1c, s2c = ctx.saved_tensors
+        N, Cc, H, W = ctx.shape
+        if g.dtype != b.dtype or g.stride() != b.stride():
+            g = torch.empty_like(b).copy_(g)
+        db = torch.empty_like(b)
+        dc = torch.empty_like(b) if ctx.has_c else None
+        ds = _zeros((2,), b.device)
+        _ck(_lib().ffsr_axpby_backward(g.data_ptr(), b.data_ptr(), c.data_ptr() if ctx.has_c else None, ctx.c_pitch,
+                                       s1c.data_ptr(), s2c.data_ptr() if ctx.has_c else None, N * H * W, Cc, db.data_ptr(),
+                                       dc.data_ptr() if dc is not None else None, ds.data_ptr(), _dt(b), _S(b)), "axpby_backward")
+        return g, db, ds[0].reshape(()), dc, (ds[1].reshape(()) if ctx.has_c else None)
+
+
+def axpby(a, b, s1, c=None, s2=None):
+    return _Axpby.apply(a, b, s1, c, s2)
+
+
+# --------------------------------------------------------------------------------------
 # BatchNorm2d, train mode, G statistic groups (group-major images)
 # --------------------------------------------------------------------------------------
 class _BatchNormTrain(torch.autograd.Function):
@@ -646,12 +733,12 @@ def lka_block_train(x, blk, G: int, sink: list, stats_only: bool = False, tc: bo
     a = _DwStage.apply(a, blk.lka.v_conv.weight, 2)
     a = conv2d(a, blk.lka.pw_conv.weight, None, tc)
     a = sigmoid(batchnorm_train(a, blk.lka.bn, G, sink))
-    x1 = x + blk.scale1 * (n * a)
+    x1 = axpby(x, n * a, blk.scale1)
     h = batchnorm_train(x1, blk.norm2, G, sink)
     if stats_only:
         return None
     h = conv_chain(h, [(blk.ffn[0].weight, blk.ffn[0].bias, K.ACT_GELU), (blk.ffn[2].weight, blk.ffn[2].bias, K.ACT_NONE)], tc)
-    return x1 + blk.scale2 * h
+    return axpby(x1, h, blk.scale2)
 
 
 class _Bilinear(torch.autograd.Function):
@@ -853,22 +940,22 @@ def _train_forward(m, lr, img_list, feats, want_inter):
     mr = m.multi_res
     stack = torch.cat(ecol, dim=1)                                          # [B,12,Hh,Wh]
 
-    def stage(xin, name):
+    def stage(xin, name, up=None, up_w=None):
         cvs = getattr(mr, name + "_conv")
         y = chain(xin, [(cvs[0], K.ACT_GELU), (cvs[2], K.ACT_GELU)], True)
         gate = getattr(mr, name + "_gate").gate
-        y = y * chain(y, [(gate[0], K.ACT_GELU), (gate[2], K.ACT_SIGMOID)]).to(y.dtype)
+        y = gate_mul(y, chain(y, [(gate[0], K.ACT_GELU), (gate[2], K.ACT_SIGMOID)]))
         res = getattr(mr, name + "_res")
         r = chain(y, [(res.block[0], K.ACT_GELU), (res.block[2], K.ACT_NONE)], True)
-        return y + res.scale * r
+        if up is None:
+            return axpby(y, r, res.scale)
+        return axpby(y, r, res.scale, up[:, :y.shape[1]], up_w)        # + residual_weight * upsampled coarser stage
 
     f1 = stage(_bilinear(stack, (H, W)), "stage1")
     f1u = _bilinear(f1, (2 * H, 2 * W))
-    f2 = stage(torch.cat([f1u, _bilinear(stack, (2 * H, 2 * W)).to(f1u.dtype)], dim=1), "stage2")
-    f2 = f2 + mr.residual_weight_1_2 * f1u
+    f2 = stage(torch.cat([f1u, _bilinear(stack, (2 * H, 2 * W)).to(f1u.dtype)], dim=1), "stage2", f1u, mr.residual_weight_1_2)
     f2u = _bilinear(f2, (Hh, Wh))
-    f3 = stage(torch.cat([f2u, stack.to(f2u.dtype)], dim=1), "stage3")
-    f3 = f3 + mr.residual_weight_2_3 * f2u[:, :f3.shape[1]]
+    f3 = stage(torch.cat([f2u, stack.to(f2u.dtype)], dim=1), "stage3", f2u, mr.residual_weight_2_3)
     hier = chain(f3, [(mr.to_rgb[0], K.ACT_GELU), (mr.to_rgb[2], K.ACT_SIGMOID)])
 
     # ---------------- Phase 5b / 6 blend ----------------
@@ -908,7 +995,7 @@ def _train_forward(m, lr, img_list, feats, want_inter):
         idt = cv(lap, r.proj, True)
         o = chain(lap, [(r.conv1, K.ACT_GELU), (r.conv2, K.ACT_GELU), (r.conv3, K.ACT_NONE)], True) + idt
         a = chain(o, [(r.attn.attn[0], K.ACT_GELU), (r.attn.attn[2], K.ACT_SIGMOID)])
-        f = o * a.to(o.dtype)
+        f = gate_mul(o, a)
         if f.shape[2:] != (Hh, Wh):
             f = _bilinear(f, (Hh, Wh))
         fl_.append(f * lw[lv])

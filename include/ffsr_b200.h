@@ -311,6 +311,21 @@ int ffsr_bilinear_forward(const void* src, int N, int h, int w, int C, void* dst
 int ffsr_bilinear_backward(const void* gout, int N, int H, int W, int C, void* gin, int h, int w, int dtype,
                            cudaStream_t stream);
 
+/* fused elementwise nodes of the training graph on dense channels-last data ([NP pixels][C]):
+ *   gate_mul : out = y * g[p] (1-channel gate: hierarchical_fusion.py:25-43, edge_enhancement.py:118);
+ *              backward dy = gout*g, dg[p] = sum_c gout*y
+ *   axpby    : out = a + s1*b (+ s2*c), s1/s2 learnable device scalars, c optionally a channel slice with pixel
+ *              pitch c_pitch (ResBlock scale, residual_weight_1_2/2_3: hierarchical_fusion.py:46-64, 178-199;
+ *              LKABlock scale1/scale2: large_kernel_attention.py:143-149); backward db = s1*g, dc = s2*g,
+ *              ds[0] += sum g*b, ds[1] += sum g*c (ACCUMULATED); da = g is passed through by the caller */
+int ffsr_gate_mul_forward(const void* y, const float* g, long NP, int C, void* out, int dtype, cudaStream_t stream);
+int ffsr_gate_mul_backward(const void* y, const float* g, const void* gout, long NP, int C, void* dy, float* dg, int dtype,
+                           cudaStream_t stream);
+int ffsr_axpby_forward(const void* a, const void* b, const void* c, long c_pitch, const float* s1, const float* s2, long NP,
+                       int C, void* out, int dtype, cudaStream_t stream);
+int ffsr_axpby_backward(const void* g, const void* b, const void* c, long c_pitch, const float* s1, const float* s2, long NP,
+                        int C, void* db, void* dc, float* ds, int dtype, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -529,3 +529,38 @@ def test_fused_conv_chain_against_sequential_reference(chans, ks, acts, N, H, W,
         assert _rel(wd[i].grad, wr[i].grad) < 3e-2, i
         if bs[i] is not None:
             assert _rel(bd[i].grad, br[i].grad) < 3e-2, i
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gate_mul_and_axpby_nodes(dtype):
+    dev = _cuda()
+    g_ = torch.Generator().manual_seed(17)
+    N, Cc, H, W = 2, 32, 9, 13
+    rnd = lambda *s: torch.randn(*s, generator=g_)
+    y, gate, gout = rnd(N, Cc, H, W), torch.sigmoid(rnd(N, 1, H, W)), rnd(N, Cc, H, W)
+    a, b, up = rnd(N, Cc, H, W), rnd(N, Cc, H, W), rnd(N, 2 * Cc, H, W)
+    s1, s2 = torch.tensor(0.3), torch.tensor(-0.7)
+    if dtype == torch.bfloat16:
+        y, gout, a, b, up = (t.bfloat16().float() for t in (y, gout, a, b, up))
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-5
+    # reference
+    yr, gr = y.clone().requires_grad_(), gate.clone().requires_grad_()
+    (yr * gr).backward(gout)
+    ar, br, upr, s1r, s2r = (t.clone().requires_grad_() for t in (a, b, up, s1, s2))
+    (ar + s1r * br + s2r * upr[:, :Cc]).backward(gout)
+    cl = lambda t: t.to(dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_()
+    yd, gd = cl(y), gate.to(dev).requires_grad_()
+    o = T.gate_mul(yd, gd)
+    o.backward(gout.to(dev).to(dtype))
+    assert _rel(o.float(), y * gate) < tol and _rel(yd.grad.float(), yr.grad) < tol and _rel(gd.grad, gr.grad) < tol
+    ad, bd, upd = cl(a), cl(b), cl(up)
+    s1d, s2d = s1.to(dev).requires_grad_(), s2.to(dev).requires_grad_()
+    o2 = T.axpby(ad, bd, s1d, upd[:, :Cc], s2d)
+    o2.backward(gout.to(dev).to(dtype))
+    assert _rel(o2.float(), a + s1 * b + s2 * up[:, :Cc]) < tol
+    assert _rel(ad.grad.float(), ar.grad) < tol and _rel(bd.grad.float(), br.grad) < tol
+    assert _rel(upd.grad.float(), upr.grad) < tol
+    assert abs(float(s1d.grad) - float(s1r.grad)) < tol * max(1.0, abs(float(s1r.grad)))
+    assert abs(float(s2d.grad) - float(s2r.grad)) < tol * max(1.0, abs(float(s2r.grad)))
+    o3 = T.axpby(ad, bd, s1d)
+    assert _rel(o3.float(), a + s1 * b) < tol
