@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_crossband_attn(
 
     // C. packed in_proj: thread `tid` owns output channel tid of [q|k|v]
     for (int tk = 0; tk < CB_TOK; ++tk) {
+      // queries are only needed for the first nq bands (keys / values for all nine): the two q warps skip the rest
+      if (tid < CB_DIM && (tk % CB_BANDS) >= nq) continue;
       float acc = brow;
       const float4* nrow = reinterpret_cast<const float4*>(&s.n[tk][0]);
 #pragma unroll
