@@ -156,6 +156,30 @@ class FusedAdamW(torch.optim.Optimizer):
         self.bump_versions()      # the kernel wrote through raw pointers: tell the version-keyed weight caches (pipeline.py)
         return loss
 
+    # -- checkpointing (train.py saves optimizer.state_dict(): src/utils/checkpoint_manager.py:120-160) --------
+    def state_dict(self):
+        """param_groups as torch.optim does, plus the flat Adam moments, EMA shadow and step count."""
+        sd = super().state_dict()
+        sd["fused"] = {"exp_avg": self.exp_avg.detach().clone(), "exp_avg_sq": self.exp_avg_sq.detach().clone(),
+                       "ema": self.ema.detach().clone() if self.ema is not None else None, "steps": int(self.steps),
+                       "offsets": list(self.bucket.offsets), "numel": int(self.bucket.numel)}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        fused = state_dict.get("fused")
+        rest = {k: v for k, v in state_dict.items() if k != "fused"}
+        super().load_state_dict(rest)
+        if fused is not None:
+            if fused["numel"] != self.bucket.numel or list(fused["offsets"]) != list(self.bucket.offsets):
+                raise ValueError("FusedAdamW.load_state_dict: bucket layout differs from the checkpoint's")
+            self.exp_avg.copy_(fused["exp_avg"])
+            self.exp_avg_sq.copy_(fused["exp_avg_sq"])
+            if self.ema is not None and fused.get("ema") is not None:
+                self.ema.copy_(fused["ema"])
+            self.steps = int(fused["steps"])
+            self._step_dev.fill_(self.steps)
+        self.set_lr(float(self.param_groups[0]["lr"]))
+
     # -- extras ----------------------------------------------------------------------------
     def set_lr(self, lr: float) -> None:
         """Scheduler hook usable between CUDA-graph replays (also picked up from param_groups[0]['lr'])."""

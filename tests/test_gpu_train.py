@@ -564,3 +564,34 @@ def test_gate_mul_and_axpby_nodes(dtype):
     assert abs(float(s2d.grad) - float(s2r.grad)) < tol * max(1.0, abs(float(s2r.grad)))
     o3 = T.axpby(ad, bd, s1d)
     assert _rel(o3.float(), a + s1 * b) < tol
+
+
+def test_fused_adamw_state_dict_round_trip():
+    from isr_b200.trainer import FusedAdamW
+    dev = _cuda()
+    g = torch.Generator().manual_seed(2)
+    mk = lambda: [torch.nn.Parameter(torch.randn(s, generator=torch.Generator().manual_seed(5)).to(dev)) for s in [(16, 3, 3, 3), (16,), ()]]
+    pa, pb = mk(), mk()
+    oa = FusedAdamW(pa, lr=1e-3, max_grad_norm=1.0, ema_decay=0.99)
+    grads = [[torch.randn(p.shape, generator=g).to(dev) for p in pa] for _ in range(4)]
+    for it in range(2):
+        for p, gr in zip(pa, grads[it]):
+            p.grad.copy_(gr)
+        oa.step()
+        oa.zero_grad()
+    sd = oa.state_dict()
+    ob = FusedAdamW(pb, lr=5e-4, max_grad_norm=1.0, ema_decay=0.99)
+    with torch.no_grad():
+        for q, p in zip(pb, pa):
+            q.copy_(p)
+    ob.load_state_dict(sd)
+    assert ob.steps == 2 and ob.param_groups[0]["lr"] == 1e-3
+    for it in range(2, 4):
+        for opt, ps in ((oa, pa), (ob, pb)):
+            for p, gr in zip(ps, grads[it]):
+                p.grad.copy_(gr)
+            opt.step()
+            opt.zero_grad()
+    for p, q in zip(pa, pb):
+        assert torch.equal(p, q)
+    assert torch.equal(oa.ema, ob.ema)
