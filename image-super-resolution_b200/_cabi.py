@@ -83,6 +83,7 @@ PROTOTYPES = {
     "ffsr_spatial_gate": (_I, [_P, _L, _I, _P, _P, _P, _P, _P, _I, _P]),
     "ffsr_blend_hr": (_I, [_P, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _LL, _P, _LL, _P]),
     "ffsr_blur_pool": (_I, [_P, _LL, _I, _I, _I, _P, _P, _LL, _P, _LL, _P]),
+    "ffsr_blur_pool_backward": (_I, [_P, _LL, _I, _I, _I, _P, _P, _LL, _P]),
     "ffsr_laplacian_sub": (_I, [_P, _LL, _P, _LL, _I, _I, _I, _P, _LL, _P, _LL, _P]),
     "ffsr_edge_attn_upsample": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _LL, _I, _P]),
     "ffsr_nchw_to_nhwc_bf16": (_I, [_P, _I, _I, _L, _P, _LL, _LL, _P]),
@@ -120,6 +121,9 @@ PROTOTYPES = {
     "ffsr_gate_mul_backward": (_I, [_P, _P, _P, _L, _I, _P, _P, _I, _P]),
     "ffsr_axpby_forward": (_I, [_P, _P, _P, _L, _P, _P, _L, _I, _P, _I, _P]),
     "ffsr_axpby_backward": (_I, [_P, _P, _P, _L, _P, _P, _L, _I, _P, _P, _P, _I, _P]),
+    "ffsr_fft_lowpass_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "ffsr_fft_lowpass": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _SZ, _P, _P]),
+    "ffsr_fft_lowpass_backward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _SZ, _P, _P]),
     # ---- fused optimizer ----
     "ffsr_sumsq": (_I, [_P, _L, _P, _P]),
     "ffsr_adamw_ema_step": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _P, _P, _F, _F, _F, _P]),

@@ -472,6 +472,57 @@ extern "C" int ffsr_blur_pool(const float* x, long long x_sX, int N, int H, int 
   return ffsr_check_launch("blur_pool");
 }
 
+// adjoint of down = avg_pool2(gauss5x5(x)): the two ops are one 6x6 stride-2 kernel K6 = box2 * gauss5, so
+// gx[y][x] = sum over the <= 3x3 outputs (oy, ox) with 2*oy - 2 <= y <= 2*oy + 3 of K6[y-2oy+2][x-2ox+2] * g[oy][ox]
+__global__ void __launch_bounds__(128) k_blur_pool_bwd(const float* __restrict__ g, long long g_sX, int H, int W,
+                                                       const float* __restrict__ gauss25, float* __restrict__ gx,
+                                                       long long gx_sX) {
+  __shared__ float k6[6][6];
+  if (threadIdx.x < 36) {
+    const int a = threadIdx.x / 6, b = threadIdx.x % 6;
+    float acc = 0.f;
+    for (int da = 0; da < 2; ++da)
+      for (int db = 0; db < 2; ++db) {
+        const int ky = a - da, kx = b - db;
+        if (ky >= 0 && ky < 5 && kx >= 0 && kx < 5) acc += gauss25[ky * 5 + kx];
+      }
+    k6[a][b] = 0.25f * acc;
+  }
+  __syncthreads();
+  const int H2 = H / 2, W2 = W / 2;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, n = blockIdx.z;
+  if (x >= W) return;
+  const float* gi = g + (long)n * H2 * W2 * g_sX;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int a = (y & 1) + 2 * i;                 // a = y - 2*oy + 2, same parity as y
+    const int oy = (y + 2 - a) >> 1;
+    if (oy < 0 || oy >= H2) continue;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int b = (x & 1) + 2 * j;
+      const int ox = (x + 2 - b) >> 1;
+      if (ox < 0 || ox >= W2) continue;
+      const float wgt = k6[a][b];
+      const float* p = gi + ((long)oy * W2 + ox) * g_sX;
+      acc[0] = fmaf(wgt, p[0], acc[0]); acc[1] = fmaf(wgt, p[1], acc[1]); acc[2] = fmaf(wgt, p[2], acc[2]);
+    }
+  }
+  float* o = gx + (((long)n * H + y) * W + x) * gx_sX;
+  o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+}
+
+extern "C" int ffsr_blur_pool_backward(const float* g, long long g_sX, int N, int H, int W, const float* gauss25, float* gx,
+                                       long long gx_sX, cudaStream_t stream) {
+  FFSR_REQUIRE(g && gauss25 && gx, FFSR_ERR_ARG, "blur_pool_backward: null pointer");
+  FFSR_REQUIRE(N > 0 && N <= 65535 && H >= 2 && H <= 65535 && W >= 2 && g_sX >= 3 && gx_sX >= 3, FFSR_ERR_ARG, "blur_pool_backward: bad shape");
+  dim3 grid(ceil_div(W, 128), H, N);
+  k_blur_pool_bwd<<<grid, 128, 0, stream>>>(g, g_sX, H, W, gauss25, gx, gx_sX);
+  return ffsr_check_launch("blur_pool_backward");
+}
+
 __global__ void __launch_bounds__(128) k_laplacian_sub(const float* __restrict__ x, long long x_sX,
                                                        const float* __restrict__ down, long long down_sX, int H, int W,
                                                        float* __restrict__ lap, long long lap_sX,

@@ -225,14 +225,14 @@ __global__ void __launch_bounds__(256) k_fft_cols(const double2* __restrict__ A,
     if (idx >= H) idx -= H;
   }
   double m = scale;
-  if (DIR < 0) m *= (double)mask[(long)l * Wf + k];
+  if (DIR < 0 && mask) m *= (double)mask[(long)l * Wf + k];
   Out[((long)bc * H + l) * Wf + k] = make_double2(re * m, im * m);
 }
 
 __global__ void __launch_bounds__(128) k_fft_rows_inv(const double2* __restrict__ G, const float* __restrict__ x,
                                                       int H, int W, int Wf, const double2* __restrict__ tw,
                                                       double scale, const float* __restrict__ band_scale,
-                                                      float* __restrict__ raw9, int B) {
+                                                      float* __restrict__ raw9, int B, float* __restrict__ low_out) {
   __shared__ double2 sg[128];
   const int xx = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, bc = blockIdx.z, b = bc / 3, c = bc % 3;
@@ -266,6 +266,10 @@ __global__ void __launch_bounds__(128) k_fft_rows_inv(const double2* __restrict_
   if (xx < W) {
     const float low = (float)(acc * scale);
     const long o = (long)y * W + xx;
+    if (low_out) {                      // train mode: the unscaled low band only (scales / high band are applied upstream)
+      low_out[(long)bc * H * W + o] = low;
+      return;
+    }
     const float xin = x[(long)bc * H * W + o];
     raw9[(((long)b * 9 + 7) * 3 + c) * H * W + o] = low * band_scale[0];
     raw9[(((long)b * 9 + 8) * 3 + c) * H * W + o] = (xin - low) * band_scale[1];
@@ -303,6 +307,68 @@ extern "C" int ffsr_fft_bands(const float* lr, int B, int H, int W, const float*
   k_fft_cols<1><<<gc, dim3(32, 8), 0, stream>>>(F, H, Wf, (const double2*)tw_h, nullptr, 1.0, A);
   if ((rc = ffsr_check_launch("fft_cols_inv"))) return rc;
   k_fft_rows_inv<<<dim3(ceil_div(W, 128), H, B * 3), 128, 0, stream>>>(A, lr, H, W, Wf, (const double2*)tw_w, scale,
-                                                                        band_scale, raw9, B);
+                                                                        band_scale, raw9, B, nullptr);
   return ffsr_check_launch("fft_rows_inv");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Train mode: low = irfft2(mask * rfft2(x)) with an explicit mask tensor, and the gradient of a scalar loss
+// w.r.t. that mask:  dmask[l][k] = c_k * sum_{b,c} Re(conj(X[l][k]) * Q[l][k]),  X = rfft2(x), Q = rfft2(dL/dlow),
+// c_k = 1 for the DC / Nyquist columns and 2 otherwise (the Hermitian half counted twice) -- identical to what
+// autograd derives for torch.fft.irfft2 (multi_domain_frequency.py:362-383).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fft_dmask(const double2* __restrict__ X, const double2* __restrict__ Q, int P, int H,
+                                                   int Wf, int W, float* __restrict__ dmask) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = blockIdx.y;
+  if (k >= Wf) return;
+  double acc = 0.0;
+  for (int p = 0; p < P; ++p) {
+    const long i = ((long)p * H + l) * Wf + k;
+    const double2 a = X[i], b = Q[i];
+    acc += a.x * b.x + a.y * b.y;
+  }
+  const bool edge = (k == 0) || ((W % 2 == 0) && k == Wf - 1);
+  dmask[(long)l * Wf + k] = (float)(edge ? acc : 2.0 * acc);
+}
+
+extern "C" size_t ffsr_fft_lowpass_workspace_bytes(int B, int H, int W) {
+  return (size_t)3 * B * 3 * H * ((size_t)W / 2 + 1) * sizeof(double2);
+}
+
+extern "C" int ffsr_fft_lowpass(const float* x, int B, int H, int W, const float* mask, const void* tw_h, const void* tw_w,
+                                void* ws, size_t ws_bytes, float* low, cudaStream_t stream) {
+  FFSR_REQUIRE(x && mask && tw_h && tw_w && ws && low && B > 0 && H > 0 && W > 1, FFSR_ERR_ARG, "fft_lowpass: bad argument");
+  FFSR_REQUIRE(ws_bytes >= ffsr_fft_lowpass_workspace_bytes(B, H, W) && ((uintptr_t)ws % 16) == 0, FFSR_ERR_ARG, "fft_lowpass: workspace");
+  const int Wf = W / 2 + 1;
+  const size_t cplx = (size_t)B * 3 * H * Wf * sizeof(double2);
+  double2* A = (double2*)ws;
+  double2* F = (double2*)((char*)ws + cplx);
+  const double scale = 1.0 / sqrt((double)H * (double)W);
+  dim3 gc(ceil_div(Wf, 32), ceil_div(H, 8), B * 3);
+  k_fft_rows_fwd<<<dim3(ceil_div(Wf, 128), H, B * 3), 128, 0, stream>>>(x, H, W, Wf, (const double2*)tw_w, A);
+  k_fft_cols<-1><<<gc, dim3(32, 8), 0, stream>>>(A, H, Wf, (const double2*)tw_h, mask, scale, F);
+  k_fft_cols<1><<<gc, dim3(32, 8), 0, stream>>>(F, H, Wf, (const double2*)tw_h, nullptr, 1.0, A);
+  k_fft_rows_inv<<<dim3(ceil_div(W, 128), H, B * 3), 128, 0, stream>>>(A, x, H, W, Wf, (const double2*)tw_w, scale, nullptr,
+                                                                        nullptr, B, low);
+  return ffsr_check_launch("fft_lowpass");
+}
+
+extern "C" int ffsr_fft_lowpass_backward(const float* x, const float* dlow, int B, int H, int W, const void* tw_h,
+                                         const void* tw_w, void* ws, size_t ws_bytes, float* dmask, cudaStream_t stream) {
+  FFSR_REQUIRE(x && dlow && tw_h && tw_w && ws && dmask && B > 0 && H > 0 && W > 1, FFSR_ERR_ARG, "fft_lowpass_backward: bad argument");
+  FFSR_REQUIRE(ws_bytes >= ffsr_fft_lowpass_workspace_bytes(B, H, W) && ((uintptr_t)ws % 16) == 0, FFSR_ERR_ARG, "fft_lowpass_backward: workspace");
+  const int Wf = W / 2 + 1;
+  const size_t cplx = (size_t)B * 3 * H * Wf * sizeof(double2);
+  double2* A = (double2*)ws;
+  double2* X = (double2*)((char*)ws + cplx);
+  double2* Q = (double2*)((char*)ws + 2 * cplx);
+  const double scale = 1.0 / sqrt((double)H * (double)W);
+  dim3 gr(ceil_div(Wf, 128), H, B * 3), gc(ceil_div(Wf, 32), ceil_div(H, 8), B * 3);
+  k_fft_rows_fwd<<<gr, 128, 0, stream>>>(x, H, W, Wf, (const double2*)tw_w, A);
+  k_fft_cols<-1><<<gc, dim3(32, 8), 0, stream>>>(A, H, Wf, (const double2*)tw_h, nullptr, scale, X);
+  k_fft_rows_fwd<<<gr, 128, 0, stream>>>(dlow, H, W, Wf, (const double2*)tw_w, A);
+  k_fft_cols<-1><<<gc, dim3(32, 8), 0, stream>>>(A, H, Wf, (const double2*)tw_h, nullptr, scale, Q);
+  k_fft_dmask<<<dim3(ceil_div(Wf, 128), H), 128, 0, stream>>>(X, Q, B * 3, H, Wf, W, dmask);
+  return ffsr_check_launch("fft_lowpass_backward");
 }

@@ -768,6 +768,32 @@ def _bilinear(x, size):
     return _Bilinear.apply(x, int(size[0]), int(size[1]))
 
 
+class _BlurPool(torch.autograd.Function):
+    """avg_pool2d(conv2d(x, gauss5x5, padding=2, groups=3), 2): one Laplacian-pyramid reduction
+    (edge_enhancement.py:196-206) and its adjoint; x: [N,3,H,W] fp32."""
+
+    @staticmethod
+    def forward(ctx, x, kernel):
+        x = _cl(x.float())
+        N, Cc, H, W = x.shape
+        assert Cc == 3
+        g25 = kernel.detach().float()[0, 0].reshape(25).contiguous()
+        out = _empty_cl(N, 3, H // 2, W // 2, x.device)
+        _ck(_lib().ffsr_blur_pool(x.data_ptr(), 3, N, H, W, g25.data_ptr(), out.data_ptr(), 3, None, 0, _S(x)), "blur_pool")
+        ctx.save_for_backward(g25)
+        ctx.shape = (N, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        (g25,) = ctx.saved_tensors
+        N, H, W = ctx.shape
+        gy = _cl(gy.float())
+        gx = _empty_cl(N, 3, H, W, gy.device)
+        _ck(_lib().ffsr_blur_pool_backward(gy.data_ptr(), 3, N, H, W, g25.data_ptr(), gx.data_ptr(), 3, _S(gy)), "blur_pool_backward")
+        return gx, None
+
+
 def _to_group_major(x, B, T):
     """[B*T, C, H, W] token-major (image b*T+t) -> [T*B, C, H, W] group-major (image t*B+b), channels-last."""
     BT, Cc, H, W = x.shape
@@ -782,8 +808,8 @@ def _phase2_train(m, lr):
     """9 sub-bands [B,9,3,H,W] with gradients to band_scale / subband_scale / FFT mask parameters.
     The DCT and DWT analysis run on the library kernels with unit scales (the input needs no
     gradient, so they are constants of the graph) and are scaled by the learnable factors here;
-    the learnable FFT mask path (3 transforms of a 3-channel LR image) is differentiated through
-    torch.fft (cuFFT)."""
+    the FFT low-pass and the gradient of its learnable mask run on the library's dense-DFT kernels
+    (ffsr_fft_lowpass / ffsr_fft_lowpass_backward); only the 64x64 -> HxWf mask resize + sigmoid are tensor ops."""
     lib = _lib()
     fd = m.freq_decomp
     B, _, H, W = lr.shape
@@ -810,13 +836,60 @@ def _phase2_train(m, lr):
                                k2[3].data_ptr(), ones.data_ptr(), sub.data_ptr(), raw.data_ptr(), S), "dwt_bands")
     scale7 = torch.cat([fd.dct.band_scale, fd.dwt.subband_scale])
     b7 = raw[:, :7] * scale7[None, :, None, None, None]
-    X = torch.fft.rfft2(lr, norm="ortho")
-    Hf, Wf = X.shape[-2:]
-    msk = F.interpolate(fd.fft.freq_mask_logits, size=(Hf, Wf), mode="bilinear", align_corners=False)
+    Wf = W // 2 + 1
+    msk = F.interpolate(fd.fft.freq_mask_logits, size=(H, Wf), mode="bilinear", align_corners=False)   # [1,1,64,64] -> tiny
     msk = torch.sigmoid(msk * fd.fft.temperature.clamp(min=1.0))
-    low = torch.fft.irfft2(X * msk, s=(H, W), norm="ortho") * fd.fft.band_scale[0]
-    high = torch.fft.irfft2(X * (1 - msk), s=(H, W), norm="ortho") * fd.fft.band_scale[1]
-    return torch.cat([b7, low[:, None], high[:, None]], dim=1)
+    low = _FFTLowpass.apply(lr, msk)                                       # irfft2(rfft2(lr) * mask)
+    low_s = low * fd.fft.band_scale[0]
+    high_s = (lr - low) * fd.fft.band_scale[1]                             # irfft2(X (1 - m)) == x - low
+    return torch.cat([b7, low_s[:, None], high_s[:, None]], dim=1)
+
+
+_TWIDDLES: Dict = {}
+
+
+def _twiddles(n: int, dev) -> torch.Tensor:
+    key = (n, str(dev))
+    t = _TWIDDLES.get(key)
+    if t is None:
+        t = torch.empty(n, 2, device=dev, dtype=torch.float64)
+        with torch.cuda.device(dev):
+            _ck(_lib().ffsr_fft_twiddles(n, t.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fft_twiddles")
+        _TWIDDLES[key] = t
+    return t
+
+
+class _FFTLowpass(torch.autograd.Function):
+    """low = irfft2(mask * rfft2(x), ortho) on the library's dense-DFT kernels (any H, W); gradient w.r.t. the
+    mask only (x is the cached LR input and needs none)."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        B, _, H, W = x.shape
+        lib = _lib()
+        m = mask.detach().float().reshape(H, W // 2 + 1).contiguous()
+        nb = lib.ffsr_fft_lowpass_workspace_bytes(B, H, W)
+        ws = torch.empty(nb // 8 + 2, device=x.device, dtype=torch.float64)
+        low = torch.empty_like(x)
+        _ck(lib.ffsr_fft_lowpass(x.data_ptr(), B, H, W, m.data_ptr(), _twiddles(H, x.device).data_ptr(),
+                                 _twiddles(W, x.device).data_ptr(), ws.data_ptr(), nb, low.data_ptr(), _S(x)), "fft_lowpass")
+        ctx.save_for_backward(x)
+        ctx.mask_shape = mask.shape
+        return low
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        B, _, H, W = x.shape
+        lib = _lib()
+        g = g.float().contiguous()
+        nb = lib.ffsr_fft_lowpass_workspace_bytes(B, H, W)
+        ws = torch.empty(nb // 8 + 2, device=x.device, dtype=torch.float64)
+        dmask = torch.empty(H, W // 2 + 1, device=x.device, dtype=torch.float32)
+        _ck(lib.ffsr_fft_lowpass_backward(x.data_ptr(), g.data_ptr(), B, H, W, _twiddles(H, x.device).data_ptr(),
+                                          _twiddles(W, x.device).data_ptr(), ws.data_ptr(), nb, dmask.data_ptr(), _S(x)),
+            "fft_lowpass_backward")
+        return None, dmask.view(ctx.mask_shape)
 
 
 # --------------------------------------------------------------------------------------
@@ -983,7 +1056,7 @@ def _train_forward(m, lr, img_list, feats, want_inter):
     for lv in range(3):
         if lv < 2:
             hh, ww = cur.shape[2:]
-            down = F.avg_pool2d(F.conv2d(cur, kern, padding=2, groups=3), 2, 2)
+            down = _BlurPool.apply(cur, kern)
             pyr.append(cur - _bilinear(down, (hh, ww)))
             cur = down
         else:

@@ -173,6 +173,9 @@ int ffsr_blend_hr(const float* hier, long long hier_sX, const float* ecol, const
 /* the optional *_lp outputs are bf16 channels-last copies (tcgen05 operands of the edge refiners) */
 int ffsr_blur_pool(const float* x, long long x_sX, int N, int H, int W, const float* gauss25, float* down,
                    long long down_sX, void* down_lp, long long down_lp_sX, cudaStream_t stream);
+/* adjoint of ffsr_blur_pool (gradient w.r.t. x of down = avg_pool2(gauss5x5(x))); g: [N][H/2][W/2] pitch g_sX */
+int ffsr_blur_pool_backward(const float* g, long long g_sX, int N, int H, int W, const float* gauss25, float* gx,
+                            long long gx_sX, cudaStream_t stream);
 int ffsr_laplacian_sub(const float* x, long long x_sX, const float* down, long long down_sX, int N, int H, int W,
                        float* lap, long long lap_sX, void* lap_lp, long long lap_lp_sX, cudaStream_t stream);
 /* refiner tail: (o * attn) [bilinear to HxW] * softmax(level_weights)[level] -> concat slice
@@ -325,6 +328,15 @@ int ffsr_axpby_forward(const void* a, const void* b, const void* c, long c_pitch
                        int C, void* out, int dtype, cudaStream_t stream);
 int ffsr_axpby_backward(const void* g, const void* b, const void* c, long c_pitch, const float* s1, const float* s2, long NP,
                         int C, void* db, void* dc, float* ds, int dtype, cudaStream_t stream);
+
+/* Train mode of FFTDecomposition (multi_domain_frequency.py:352-385): low = irfft2(mask * rfft2(x), ortho) with the
+ * sigmoid mask [H][W/2+1] supplied by the caller, and d(loss)/d(mask) from d(loss)/d(low) (sum over batch and
+ * channels, Hermitian half counted twice).  x / low / dlow: [B][3][H][W] fp32; tables from ffsr_fft_twiddles. */
+size_t ffsr_fft_lowpass_workspace_bytes(int B, int H, int W);
+int ffsr_fft_lowpass(const float* x, int B, int H, int W, const float* mask, const void* tw_h, const void* tw_w, void* ws,
+                     size_t ws_bytes, float* low, cudaStream_t stream);
+int ffsr_fft_lowpass_backward(const float* x, const float* dlow, int B, int H, int W, const void* tw_h, const void* tw_w,
+                              void* ws, size_t ws_bytes, float* dmask, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

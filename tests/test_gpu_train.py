@@ -448,7 +448,10 @@ def test_cuda_graph_step_matches_eager_step():
     assert max(abs(a - b) for a, b in zip(l0, l1)) < 2e-5, (l0, l1)
     # fp32 atomics order differs run to run; Adam turns a sign flip of a ~0 gradient into a 2*lr step, so the
     # bound on individual weights is a few lr (2e-4), while the losses above agree to 2e-5
-    assert max(float((a - b).abs().max()) for a, b in zip(p0, p1)) < 6e-4
+    # (worst case 2*lr per step for a weight whose ~0 gradient flips sign: 6 steps x 2 x 2e-4), so bound the maximum
+    # loosely and the mean tightly
+    assert max(float((a - b).abs().max()) for a, b in zip(p0, p1)) < 3e-3
+    assert sum(float((a - b).abs().sum()) for a, b in zip(p0, p1)) / sum(a.numel() for a in p0) < 2e-5
     assert nb0 == nb1 == 54 and float((rm0 - rm1).abs().max()) < 1e-5
 
 
@@ -595,3 +598,22 @@ def test_fused_adamw_state_dict_round_trip():
     for p, q in zip(pa, pb):
         assert torch.equal(p, q)
     assert torch.equal(oa.ema, ob.ema)
+
+
+@pytest.mark.parametrize("H,W", [(16, 24), (17, 23), (64, 64)])
+def test_blur_pool_forward_and_adjoint(H, W):
+    dev = _cuda()
+    g = torch.Generator().manual_seed(H)
+    ax = torch.arange(5, dtype=torch.float32) - 2
+    k1 = torch.exp(-(ax ** 2) / (2 * 1.5 ** 2))
+    k1 = k1 / k1.sum()
+    kern = (k1[:, None] * k1[None, :]).expand(3, 1, 5, 5).contiguous()
+    x = torch.randn(2, 3, H, W, generator=g)
+    gy = torch.randn(2, 3, H // 2, W // 2, generator=g)
+    xr = x.clone().requires_grad_()
+    yr = F.avg_pool2d(F.conv2d(xr, kern, padding=2, groups=3), 2, 2)
+    yr.backward(gy)
+    xd = x.to(dev).requires_grad_()
+    y = T._BlurPool.apply(xd, kern.to(dev))
+    y.backward(gy.to(dev))
+    assert _rel(y, yr) < 2e-6 and _rel(xd.grad, xr.grad) < 2e-6
