@@ -211,24 +211,21 @@ __global__ void __launch_bounds__(256) k_resize_nhwc(const T* __restrict__ src, 
                 ty.w0 * (tx.w0 * a.w + tx.w1 * b.w) + ty.w1 * (tx.w0 * c.w + tx.w1 * d.w));
 }
 
-// bf16, 8 channels (16 bytes) per thread
+// bf16, 8 channels (16 bytes) per thread, row-structured grid (x = W*C8 items, y = output row, z = image)
 __global__ void __launch_bounds__(256) k_resize_nhwc_bf16x8(const __nv_bfloat16* __restrict__ src, int h, int w, int C8,
                                                             long long src_sX, __nv_bfloat16* __restrict__ dst, int H, int W,
-                                                            long long dst_sX, long total) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  const long pix = i / C8;
-  const int X = (int)(pix % W), Y = (int)((pix / W) % H);
-  const long n = pix / ((long)W * H);
+                                                            long long dst_sX) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int X = t / C8, c8 = t - X * C8;
+  const int Y = blockIdx.y, n = blockIdx.z;
+  if (X >= W) return;
   const BilinTap ty = bilin_tap(Y, h, H), tx = bilin_tap(X, w, W);
-  const __nv_bfloat16* base = src + n * h * w * src_sX + 8 * c8;
+  const __nv_bfloat16* base = src + (long)n * h * w * src_sX + 8 * c8;
   const uint4 a = *reinterpret_cast<const uint4*>(base + ((long)ty.i0 * w + tx.i0) * src_sX);
   const uint4 b = *reinterpret_cast<const uint4*>(base + ((long)ty.i0 * w + tx.i1) * src_sX);
   const uint4 c = *reinterpret_cast<const uint4*>(base + ((long)ty.i1 * w + tx.i0) * src_sX);
   const uint4 d = *reinterpret_cast<const uint4*>(base + ((long)ty.i1 * w + tx.i1) * src_sX);
   const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
-  const float w00 = ty.w0 * tx.w0, w01 = ty.w0 * tx.w1, w10 = ty.w1 * tx.w0, w11 = ty.w1 * tx.w1;
   uint32_t o[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -242,8 +239,7 @@ __global__ void __launch_bounds__(256) k_resize_nhwc_bf16x8(const __nv_bfloat16*
     __nv_bfloat162 hh = __floats2bfloat162_rn(r0, r1);
     o[k] = *reinterpret_cast<uint32_t*>(&hh);
   }
-  (void)w00; (void)w01; (void)w10; (void)w11;
-  *reinterpret_cast<uint4*>(dst + pix * dst_sX + 8 * c8) = make_uint4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<uint4*>(dst + (((long)n * H + Y) * W + X) * dst_sX + 8 * c8) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 extern "C" int ffsr_resize_nhwc(const void* src, int N, int h, int w, int C, long long src_sX, void* dst, int H, int W,
@@ -254,10 +250,10 @@ extern "C" int ffsr_resize_nhwc(const void* src, int N, int h, int w, int C, lon
   FFSR_REQUIRE(((uintptr_t)src % (4 * esz)) == 0 && ((uintptr_t)dst % (4 * esz)) == 0 && src_sX % 4 == 0 && dst_sX % 4 == 0,
                FFSR_ERR_ALIGN, "resize_nhwc: vector alignment");
   if (dtype == FFSR_DT_BF16 && C % 8 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0 && src_sX % 8 == 0 &&
-      dst_sX % 8 == 0) {
-    const long total8 = (long)N * H * W * (C / 8);
-    k_resize_nhwc_bf16x8<<<ceil_div(total8, 256), 256, 0, stream>>>((const __nv_bfloat16*)src, h, w, C / 8, src_sX,
-                                                                    (__nv_bfloat16*)dst, H, W, dst_sX, total8);
+      dst_sX % 8 == 0 && H <= 65535 && N <= 65535) {
+    dim3 grid(ceil_div((long)W * (C / 8), 256), H, N);
+    k_resize_nhwc_bf16x8<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, h, w, C / 8, src_sX, (__nv_bfloat16*)dst, H, W,
+                                                   dst_sX);
     return ffsr_check_launch("resize_nhwc");
   }
   const long total = (long)N * H * W * (C / 4);
@@ -600,6 +596,67 @@ __global__ void __launch_bounds__(256) k_edge_attn_up(const TI* __restrict__ o, 
   store_vec4<T>(dst + pix * dst_sX + 4 * c4, r.x * lw, r.y * lw, r.z * lw, r.w * lw);
 }
 
+// bf16 in / bf16 out, 8 channels (16 bytes) per thread, row-structured grid (no per-thread div/mod chain), the
+// level softmax computed once per block: the 4-channel kernel above was issue-bound (3 expf + 64-bit index
+// arithmetic per 8 output bytes).
+__global__ void __launch_bounds__(256) k_edge_attn_up_bf16x8(const __nv_bfloat16* __restrict__ o, const float* __restrict__ attn,
+                                                             int h, int w, int C8, const float* __restrict__ level_w,
+                                                             int level, __nv_bfloat16* __restrict__ dst, int H, int W,
+                                                             long long dst_sX) {
+  __shared__ float s_lw;
+  if (threadIdx.x == 0) {
+    const float l0 = level_w[0], l1 = level_w[1], l2 = level_w[2];
+    const float m = fmaxf(l0, fmaxf(l1, l2));
+    const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
+    s_lw = (level == 0 ? e0 : (level == 1 ? e1 : e2)) / ((e0 + e1) + e2);
+  }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;       // over W * C8
+  const int X = t / C8, c8 = t - X * C8;
+  const int Y = blockIdx.y, n = blockIdx.z;
+  if (X >= W) return;
+  const float lw = s_lw;
+  const int C = 8 * C8;
+  const __nv_bfloat16* ob = o + (long)n * h * w * C + 8 * c8;
+  const float* ab = attn + (long)n * h * w;
+  float r[8];
+  auto unpack = [](const uint4& u, float (&f)[8]) {
+    const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[k]));
+      f[2 * k] = f2.x; f[2 * k + 1] = f2.y;
+    }
+  };
+  if (h == H && w == W) {
+    const int q = Y * w + X;
+    float v[8];
+    unpack(*reinterpret_cast<const uint4*>(ob + (long)q * C), v);
+    const float a = ab[q];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = v[k] * a;
+  } else {
+    const BilinTap ty = bilin_tap(Y, h, H), tx = bilin_tap(X, w, W);
+    const int q00 = ty.i0 * w + tx.i0, q01 = ty.i0 * w + tx.i1, q10 = ty.i1 * w + tx.i0, q11 = ty.i1 * w + tx.i1;
+    float v00[8], v01[8], v10[8], v11[8];
+    unpack(*reinterpret_cast<const uint4*>(ob + (long)q00 * C), v00);
+    unpack(*reinterpret_cast<const uint4*>(ob + (long)q01 * C), v01);
+    unpack(*reinterpret_cast<const uint4*>(ob + (long)q10 * C), v10);
+    unpack(*reinterpret_cast<const uint4*>(ob + (long)q11 * C), v11);
+    const float a00 = ab[q00], a01 = ab[q01], a10 = ab[q10], a11 = ab[q11];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      r[k] = ty.w0 * (tx.w0 * (v00[k] * a00) + tx.w1 * (v01[k] * a01)) + ty.w1 * (tx.w0 * (v10[k] * a10) + tx.w1 * (v11[k] * a11));
+  }
+  uint32_t ow[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(r[2 * k] * lw, r[2 * k + 1] * lw);
+    ow[k] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  *reinterpret_cast<uint4*>(dst + (((long)n * H + Y) * W + X) * dst_sX + 8 * c8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
 extern "C" int ffsr_edge_attn_upsample(const void* o, int o_dtype, const float* attn, int N, int h, int w, int C,
                                        const float* level_w, int level, void* dst, int H, int W, long long dst_sX,
                                        int dtype, cudaStream_t stream) {
@@ -610,6 +667,12 @@ extern "C" int ffsr_edge_attn_upsample(const void* o, int o_dtype, const float* 
                "edge_attn_upsample: alignment");
   const long total = (long)N * H * W * (C / 4);
   FFSR_REQUIRE(o_dtype == FFSR_DT_F32 || dtype == FFSR_DT_BF16, FFSR_ERR_ARG, "edge_attn_upsample: bf16 input needs bf16 output");
+  if (o_dtype == FFSR_DT_BF16 && C % 8 == 0 && ((uintptr_t)dst % 16) == 0 && dst_sX % 8 == 0 && H <= 65535 && N <= 65535) {
+    dim3 grid(ceil_div((long)W * (C / 8), 256), H, N);
+    k_edge_attn_up_bf16x8<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)o, attn, h, w, C / 8, level_w, level,
+                                                    (__nv_bfloat16*)dst, H, W, dst_sX);
+    return ffsr_check_launch("edge_attn_upsample");
+  }
   if (o_dtype == FFSR_DT_BF16)
     k_edge_attn_up<__nv_bfloat16, __nv_bfloat16><<<ceil_div(total, 256), 256, 0, stream>>>((const __nv_bfloat16*)o, attn, h, w, C / 4, level_w, level, (__nv_bfloat16*)dst, H, W, dst_sX, total);
   else if (dtype == FFSR_DT_BF16)

@@ -21,6 +21,42 @@ __device__ __forceinline__ void st_any(void* base, int dtype, long long off, flo
   else reinterpret_cast<float*>(base)[off] = v;
 }
 
+// 8 consecutive elements <-> fp32 registers (16-byte accesses for bf16, 2 x 16 bytes for fp32); p must be 16B aligned
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+    f[2 * k] = f2.x; f[2 * k + 1] = f2.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&f)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+    w[k] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ------------------------------------------------------------------------------------
 // conv weight gradient.  grid = (pixel chunks, taps, ci tiles * co tiles); 256 threads as a
 // 16x16 grid of (TM/16)x(TN/16) register micro-tiles; K = pixels, staged 16 at a time.
@@ -245,17 +281,36 @@ __device__ __forceinline__ float act_grad(float x, int act) {
   }
 }
 
+// 8 elements per thread-iteration (vector accesses) + scalar tail
 template <typename T>
-__global__ void k_act_fwd(const T* __restrict__ x, T* __restrict__ y, long n, int act) {
+__global__ void __launch_bounds__(256) k_act_fwd(const T* __restrict__ x, T* __restrict__ y, long n, int act) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
-  for (long k = i; k < n; k += stride) y[k] = from_f32<T>(apply_act(to_f32<T>(x[k]), act));
+  const long n8 = n >> 3;
+  for (long k = i; k < n8; k += stride) {
+    float f[8];
+    load8<T>(x + 8 * k, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], act);
+    store8<T>(y + 8 * k, f);
+  }
+  for (long k = 8 * n8 + i; k < n; k += stride) y[k] = from_f32<T>(apply_act(to_f32<T>(x[k]), act));
 }
 template <typename T>
-__global__ void k_act_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long n, int act) {
+__global__ void __launch_bounds__(256) k_act_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long n,
+                                                 int act) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
-  for (long k = i; k < n; k += stride) dx[k] = from_f32<T>(to_f32<T>(dy[k]) * act_grad(to_f32<T>(x[k]), act));
+  const long n8 = n >> 3;
+  for (long k = i; k < n8; k += stride) {
+    float f[8], g[8];
+    load8<T>(x + 8 * k, f);
+    load8<T>(dy + 8 * k, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= act_grad(f[j], act);
+    store8<T>(dx + 8 * k, g);
+  }
+  for (long k = 8 * n8 + i; k < n; k += stride) dx[k] = from_f32<T>(to_f32<T>(dy[k]) * act_grad(to_f32<T>(x[k]), act));
 }
 
 // ------------------------------------------------------------------------------------
@@ -715,6 +770,52 @@ __global__ void __launch_bounds__(256) k_bilinear_bwd(const T* __restrict__ gout
 // fused few-pass elementwise nodes of the training graph
 // ------------------------------------------------------------------------------------
 // out[p][c] = y[p][c] * g[p]        (SpatialGate / edge attention: a 1-channel map gating C channels)
+// C % 8 == 0: 8 channels per thread-iteration with vector accesses
+template <typename T>
+__global__ void __launch_bounds__(256) k_gate_mul_fwd8(const T* __restrict__ y, const float* __restrict__ g, long NP, int C,
+                                                       T* __restrict__ out) {
+  const int G = C >> 3;
+  const long total = NP * G;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const float gv = g[i / G];
+    float f[8];
+    load8<T>(y + 8 * i, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] *= gv;
+    store8<T>(out + 8 * i, f);
+  }
+}
+// one warp-quarter (8 lanes) per pixel: each lane 8 channels per step, shuffle reduction for the gate gradient
+template <typename T>
+__global__ void __launch_bounds__(256) k_gate_mul_bwd8(const T* __restrict__ y, const float* __restrict__ g,
+                                                       const T* __restrict__ gout, long NP, int C, T* __restrict__ dy,
+                                                       float* __restrict__ dg) {
+  const int sub = threadIdx.x & 7;
+  const long pix0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const long pstride = ((long)gridDim.x * blockDim.x) >> 3;
+  const long trips = (NP + pstride - 1) / pstride;                 // uniform trip count: every lane joins the shuffles
+  for (long it = 0; it < trips; ++it) {
+    const long pix = pix0 + it * pstride;
+    const bool live = pix < NP;
+    float acc = 0.f;
+    if (live) {
+      const float gv = g[pix];
+      for (int c = 8 * sub; c < C; c += 64) {
+        float a[8], b[8];
+        load8<T>(gout + pix * C + c, a);
+        load8<T>(y + pix * C + c, b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc = fmaf(a[k], b[k], acc); a[k] *= gv; }
+        store8<T>(dy + pix * C + c, a);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (live && sub == 0) dg[pix] = acc;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_gate_mul_fwd(const T* __restrict__ y, const float* __restrict__ g, long NP, int C,
                                                       T* __restrict__ out) {
@@ -749,6 +850,71 @@ __global__ void __launch_bounds__(128) k_gate_mul_bwd(const T* __restrict__ y, c
       }
     }
     dg[pix] = acc;
+  }
+}
+
+// vector versions (C % 8 == 0, 16-byte aligned): item i = (pixel, 8-channel group)
+template <typename T>
+__global__ void __launch_bounds__(256) k_axpby_fwd8(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
+                                                    long c_pitch, const float* __restrict__ s1, const float* __restrict__ s2,
+                                                    long NP, int C, T* __restrict__ out) {
+  const float k1 = s1[0], k2 = c ? s2[0] : 0.f;
+  const int G = C >> 3;
+  const long total = NP * G;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float fa[8], fb[8];
+    load8<T>(a + 8 * i, fa);
+    load8<T>(b + 8 * i, fb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fa[k] = fmaf(k1, fb[k], fa[k]);
+    if (c) {
+      const long pix = i / G;
+      float fc[8];
+      load8<T>(c + pix * c_pitch + 8 * (i - pix * G), fc);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) fa[k] = fmaf(k2, fc[k], fa[k]);
+    }
+    store8<T>(out + 8 * i, fa);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_axpby_bwd8(const T* __restrict__ g, const T* __restrict__ b, const T* __restrict__ c,
+                                                    long c_pitch, const float* __restrict__ s1, const float* __restrict__ s2,
+                                                    long NP, int C, T* __restrict__ db, T* __restrict__ dc,
+                                                    float* __restrict__ ds) {
+  __shared__ float sh[2][8];
+  const float k1 = s1[0], k2 = c ? s2[0] : 0.f;
+  const int G = C >> 3;
+  const long total = NP * G;
+  float a1 = 0.f, a2 = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float fg[8], fb[8], o[8];
+    load8<T>(g + 8 * i, fg);
+    load8<T>(b + 8 * i, fb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a1 = fmaf(fg[k], fb[k], a1); o[k] = k1 * fg[k]; }
+    store8<T>(db + 8 * i, o);
+    if (c) {
+      const long pix = i / G;
+      float fc[8];
+      load8<T>(c + pix * c_pitch + 8 * (i - pix * G), fc);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a2 = fmaf(fg[k], fc[k], a2); o[k] = k2 * fg[k]; }
+      store8<T>(dc + 8 * i, o);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a1 += __shfl_down_sync(0xffffffffu, a1, o);
+    a2 += __shfl_down_sync(0xffffffffu, a2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a1; sh[1][threadIdx.x >> 5] = a2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int i = 0; i < 8; ++i) { t1 += sh[0][i]; t2 += sh[1][i]; }
+    atomicAdd(ds, t1);
+    if (c) atomicAdd(ds + 1, t2);
   }
 }
 
@@ -1018,6 +1184,13 @@ extern "C" int ffsr_bilinear_backward(const void* gout, int N, int H, int W, int
 
 extern "C" int ffsr_gate_mul_forward(const void* y, const float* g, long NP, int C, void* out, int dtype, cudaStream_t stream) {
   FFSR_REQUIRE(y && g && out && NP > 0 && C > 0 && C % 4 == 0, FFSR_ERR_ARG, "gate_mul_forward: bad argument (C %% 4 == 0)");
+  if (C % 8 == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)out % 16) == 0) {
+    const long total8 = NP * (C / 8);
+    const int grid8 = (int)min((long)148 * 16, (total8 + 255) / 256);
+    if (dtype == FFSR_DT_BF16) k_gate_mul_fwd8<__nv_bfloat16><<<grid8, 256, 0, stream>>>((const __nv_bfloat16*)y, g, NP, C, (__nv_bfloat16*)out);
+    else k_gate_mul_fwd8<float><<<grid8, 256, 0, stream>>>((const float*)y, g, NP, C, (float*)out);
+    return ffsr_check_launch("gate_mul_forward");
+  }
   const long total = NP * (C / 4);
   const int grid = (int)min((long)148 * 16, (total + 255) / 256);
   if (dtype == FFSR_DT_BF16) k_gate_mul_fwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)y, g, NP, C, (__nv_bfloat16*)out);
@@ -1028,6 +1201,13 @@ extern "C" int ffsr_gate_mul_forward(const void* y, const float* g, long NP, int
 extern "C" int ffsr_gate_mul_backward(const void* y, const float* g, const void* gout, long NP, int C, void* dy, float* dg,
                                       int dtype, cudaStream_t stream) {
   FFSR_REQUIRE(y && g && gout && dy && dg && NP > 0 && C > 0 && C % 4 == 0, FFSR_ERR_ARG, "gate_mul_backward: bad argument");
+  if (C % 8 == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)gout % 16) == 0 && ((uintptr_t)dy % 16) == 0) {
+    const int grid8 = (int)min((long)148 * 16, (NP * 8 + 255) / 256);
+    if (dtype == FFSR_DT_BF16)
+      k_gate_mul_bwd8<__nv_bfloat16><<<grid8, 256, 0, stream>>>((const __nv_bfloat16*)y, g, (const __nv_bfloat16*)gout, NP, C, (__nv_bfloat16*)dy, dg);
+    else k_gate_mul_bwd8<float><<<grid8, 256, 0, stream>>>((const float*)y, g, (const float*)gout, NP, C, (float*)dy, dg);
+    return ffsr_check_launch("gate_mul_backward");
+  }
   const int grid = (int)min((long)148 * 32, (NP + 127) / 128);
   if (dtype == FFSR_DT_BF16)
     k_gate_mul_bwd<__nv_bfloat16><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)y, g, (const __nv_bfloat16*)gout, NP, C, (__nv_bfloat16*)dy, dg);
@@ -1038,6 +1218,16 @@ extern "C" int ffsr_gate_mul_backward(const void* y, const float* g, const void*
 extern "C" int ffsr_axpby_forward(const void* a, const void* b, const void* c, long c_pitch, const float* s1, const float* s2,
                                   long NP, int C, void* out, int dtype, cudaStream_t stream) {
   FFSR_REQUIRE(a && b && s1 && out && NP > 0 && C > 0 && (!c || s2), FFSR_ERR_ARG, "axpby_forward: bad argument");
+  auto al16 = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
+  const int esz = dtype == FFSR_DT_BF16 ? 2 : 4;
+  if (C % 8 == 0 && al16(a) && al16(b) && al16(out) && (!c || (al16(c) && (c_pitch * esz) % 16 == 0))) {
+    const long total8 = NP * (C / 8);
+    const int grid8 = (int)min((long)148 * 16, (total8 + 255) / 256);
+    if (dtype == FFSR_DT_BF16)
+      k_axpby_fwd8<__nv_bfloat16><<<grid8, 256, 0, stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)c, c_pitch, s1, s2, NP, C, (__nv_bfloat16*)out);
+    else k_axpby_fwd8<float><<<grid8, 256, 0, stream>>>((const float*)a, (const float*)b, (const float*)c, c_pitch, s1, s2, NP, C, (float*)out);
+    return ffsr_check_launch("axpby_forward");
+  }
   const long total = NP * C;
   const int grid = (int)min((long)148 * 16, (total + 255) / 256);
   if (dtype == FFSR_DT_BF16)
@@ -1049,6 +1239,16 @@ extern "C" int ffsr_axpby_forward(const void* a, const void* b, const void* c, l
 extern "C" int ffsr_axpby_backward(const void* g, const void* b, const void* c, long c_pitch, const float* s1, const float* s2,
                                    long NP, int C, void* db, void* dc, float* ds, int dtype, cudaStream_t stream) {
   FFSR_REQUIRE(g && b && s1 && db && ds && NP > 0 && C > 0 && (!c || (s2 && dc)), FFSR_ERR_ARG, "axpby_backward: bad argument");
+  auto al16 = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
+  const int esz = dtype == FFSR_DT_BF16 ? 2 : 4;
+  if (C % 8 == 0 && al16(g) && al16(b) && al16(db) && (!c || (al16(c) && al16(dc) && (c_pitch * esz) % 16 == 0))) {
+    const long total8 = NP * (C / 8);
+    const int grid8 = (int)min((long)148 * 8, (total8 + 255) / 256);
+    if (dtype == FFSR_DT_BF16)
+      k_axpby_bwd8<__nv_bfloat16><<<grid8, 256, 0, stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)b, (const __nv_bfloat16*)c, c_pitch, s1, s2, NP, C, (__nv_bfloat16*)db, (__nv_bfloat16*)dc, ds);
+    else k_axpby_bwd8<float><<<grid8, 256, 0, stream>>>((const float*)g, (const float*)b, (const float*)c, c_pitch, s1, s2, NP, C, (float*)db, (float*)dc, ds);
+    return ffsr_check_launch("axpby_backward");
+  }
   const long total = NP * C;
   const int grid = (int)min((long)148 * 8, (total + 255) / 256);
   if (dtype == FFSR_DT_BF16)

@@ -132,9 +132,10 @@ class FusedAdamW(torch.optim.Optimizer):
         world = _world()
         if world > 1:
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)   # ONE collective: the flat 5.7 MB gradient bucket
-        self.steps += 1
         dev = self.bucket.flat.device
         capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:                    # a capture records the step without running it (the replay loop counts it)
+            self.steps += 1
         if not capturing and float(g["lr"]) != self._lr_host:   # scheduler changed the LR: refresh the device scalar
             self._lr_host = float(g["lr"])
             self._lr_dev.fill_(self._lr_host)
