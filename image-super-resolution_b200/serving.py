@@ -70,3 +70,45 @@ class PipelinedFusion:
         self.s_in.synchronize()
         self.s_compute.synchronize()
         self.s_out.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------------
+# 8x test-time augmentation over cached variants
+# ---------------------------------------------------------------------------------------------------
+def reverse_tta(t: torch.Tensor, hflip: bool, rot: int) -> torch.Tensor:
+    """Undo the geometric TTA transform on an SR output (scripts/generate_fast_submission.py:55-61)."""
+    if rot > 0:
+        t = torch.rot90(t, -rot, [2, 3])
+    if hflip:
+        t = torch.flip(t, [3])
+    return t
+
+
+@torch.no_grad()
+def fuse_tta(model, variants) -> torch.Tensor:
+    """Mean of the reverse-transformed fusion outputs of the cached TTA variants of ONE image, clamped to [0,1]
+    (scripts/generate_fast_submission.py:190-250), computed entirely on the device.
+
+    ``variants``: iterable of ``(lr [1,3,h,w], expert_imgs {name: [1,3,4h,4w]}, expert_feats {name: [1,C,h,w]} | None,
+    hflip, rot)`` as ``scripts/extract_test_tta_cache.py:253-256`` enumerates them (hflip in {F,T} x rot in 0..3).
+    Variants of equal LR shape (rot 0/2 vs rot 1/3) are batched into one forward each, so the 8 variants cost two
+    B=4 forwards instead of eight B=1 forwards with a device->host copy and an ``empty_cache()`` in between, which is
+    what the reference does."""
+    groups = {}
+    for lr, imgs, feats, hflip, rot in variants:
+        groups.setdefault(tuple(lr.shape[2:]), []).append((lr, imgs, feats, bool(hflip), int(rot)))
+    total, count = None, 0
+    for items in groups.values():
+        lr = torch.cat([it[0] for it in items], 0)
+        imgs = {k: torch.cat([it[1][k] for it in items], 0) for k in items[0][1]}
+        feats = None
+        if items[0][2]:
+            feats = {k: torch.cat([it[2][k] for it in items], 0) for k in items[0][2]}
+        sr = model.forward_with_precomputed(lr, imgs, feats)
+        for j, it in enumerate(items):
+            r = reverse_tta(sr[j:j + 1], it[3], it[4]).float()
+            total = r.clone() if total is None else total.add_(r)
+            count += 1
+    if total is None:
+        raise ValueError("fuse_tta: no variants")
+    return (total / count).clamp_(0, 1)

@@ -427,3 +427,35 @@ def test_pipelined_serving_matches_direct_calls():
     for (lr, imgs, fts), o in zip(items, outs):
         ref = m.forward_with_precomputed(lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()})
         assert torch.equal(o, ref.cpu())
+
+
+def test_tta_fusion_matches_per_variant_loop():
+    """serving.fuse_tta (two batched forwards, reverse + mean on the device) against the reference's loop:
+    one forward per variant, reverse_tta, CPU mean, clamp (scripts/generate_fast_submission.py:190-250)."""
+    from isr_b200.serving import fuse_tta, reverse_tta
+    dev = _cuda()
+    m = _model(True).to(dev)
+    lr, imgs, fts, _ = O.synthetic_inputs(1, 16, 24)
+
+    def tf(t, hflip, rot):                      # extract_test_tta_cache.py applies hflip then rot90 to the LR input
+        if hflip:
+            t = torch.flip(t, [3])
+        return torch.rot90(t, rot, [2, 3]) if rot else t
+
+    variants = []
+    for hflip in (False, True):
+        for rot in range(4):
+            g = torch.Generator().manual_seed(100 + rot + 4 * hflip)
+            v_lr = tf(lr, hflip, rot).contiguous()
+            h, w = v_lr.shape[2:]
+            v_imgs = {k: torch.rand(1, 3, 4 * h, 4 * w, generator=g) for k in imgs}      # per-variant expert outputs
+            v_fts = {k: torch.randn(1, fts[k].shape[1], h, w, generator=g) for k in fts}
+            variants.append((v_lr.to(dev), {k: v.to(dev) for k, v in v_imgs.items()}, {k: v.to(dev) for k, v in v_fts.items()},
+                             hflip, rot))
+    outs = []
+    for v_lr, v_imgs, v_fts, hflip, rot in variants:
+        outs.append(reverse_tta(m.forward_with_precomputed(v_lr, v_imgs, v_fts), hflip, rot).squeeze(0).cpu())
+    want = torch.stack(outs).float().mean(dim=0).clamp(0, 1)
+    got = fuse_tta(m, variants)
+    assert tuple(got.shape) == (1, 3, 64, 96)
+    assert (got.squeeze(0).cpu() - want).abs().max().item() <= 2e-6
