@@ -709,6 +709,29 @@ __global__ void __launch_bounds__(256) k_bilinear_fwd(const T* __restrict__ src,
   }
 }
 
+// 8-channel vector versions (C % 8 == 0, 16-byte aligned rows)
+template <typename T>
+__global__ void __launch_bounds__(256) k_bilinear_fwd8(const T* __restrict__ src, int h, int w, int C, T* __restrict__ dst,
+                                                       int H, int W, long total) {
+  const int G = C >> 3;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    const long pix = i / G;
+    const int X = (int)(pix % W), Y = (int)((pix / W) % H);
+    const long n = pix / ((long)W * H);
+    const BilinTap ty = bilin_tap(Y, h, H), tx = bilin_tap(X, w, W);
+    const T* base = src + n * h * w * C + cg * 8;
+    float a[8], b[8], c[8], d[8], o[8];
+    load8<T>(base + ((long)ty.i0 * w + tx.i0) * C, a);
+    load8<T>(base + ((long)ty.i0 * w + tx.i1) * C, b);
+    load8<T>(base + ((long)ty.i1 * w + tx.i0) * C, c);
+    load8<T>(base + ((long)ty.i1 * w + tx.i1) * C, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = ty.w0 * (tx.w0 * a[k] + tx.w1 * b[k]) + ty.w1 * (tx.w0 * c[k] + tx.w1 * d[k]);
+    store8<T>(dst + pix * C + cg * 8, o);
+  }
+}
+
 constexpr int BL_MAXC = 16;   // candidate outputs per axis that can read one input sample (scale factors up to ~6x)
 
 // candidates [lo, hi] of output indices whose taps may touch input index `i`, and their weights
@@ -969,6 +992,38 @@ __global__ void __launch_bounds__(256) k_axpby_bwd(const T* __restrict__ g, cons
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) k_bilinear_bwd8(const T* __restrict__ gout, int H, int W, int C, T* __restrict__ gin,
+                                                       int h, int w, long total) {
+  const int G = C >> 3;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    const long pix = i / G;
+    const int x = (int)(pix % w), y = (int)((pix / w) % h);
+    const long n = pix / ((long)w * h);
+    float wy[BL_MAXC], wx[BL_MAXC];
+    int ylo, xlo;
+    const int ny = bilin_adjoint_taps(y, h, H, ylo, wy);
+    const int nx = bilin_adjoint_taps(x, w, W, xlo, wx);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const T* base = gout + n * H * W * C + cg * 8;
+    for (int a = 0; a < ny; ++a) {
+      if (wy[a] == 0.f) continue;
+      for (int b = 0; b < nx; ++b) {
+        const float wgt = wy[a] * wx[b];
+        if (wgt == 0.f) continue;
+        float v[8];
+        load8<T>(base + ((long)(ylo + a) * W + xlo + b) * C, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+      }
+    }
+    store8<T>(gin + pix * C + cg * 8, acc);
+  }
+}
+
 inline void colsum_geom(int C, dim3& block, int& CT) {
   CT = 1;
   while (CT < C && CT < 64) CT <<= 1;
@@ -1150,6 +1205,19 @@ extern "C" int ffsr_to_bf16_nhwc(const void* src, int src_dtype, long long sN, l
 template <bool BWD>
 static int launch_bilinear(const void* a, int N, int h, int w, int C, void* b, int H, int W, int dtype, cudaStream_t stream) {
   // forward: a = src [N,h,w,C] -> b = dst [N,H,W,C];  backward: a = gout [N,H,W,C] -> b = gin [N,h,w,C]
+  if (C % 8 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0) {
+    const long total8 = (long)N * (BWD ? (long)h * w : (long)H * W) * (C / 8);
+    const int grid8 = (int)min((long)148 * 32, (total8 + 255) / 256);
+    if (dtype == FFSR_DT_BF16) {
+      using T = __nv_bfloat16;
+      if (BWD) k_bilinear_bwd8<T><<<grid8, 256, 0, stream>>>((const T*)a, H, W, C, (T*)b, h, w, total8);
+      else k_bilinear_fwd8<T><<<grid8, 256, 0, stream>>>((const T*)a, h, w, C, (T*)b, H, W, total8);
+    } else {
+      if (BWD) k_bilinear_bwd8<float><<<grid8, 256, 0, stream>>>((const float*)a, H, W, C, (float*)b, h, w, total8);
+      else k_bilinear_fwd8<float><<<grid8, 256, 0, stream>>>((const float*)a, h, w, C, (float*)b, H, W, total8);
+    }
+    return ffsr_check_launch(BWD ? "bilinear_backward" : "bilinear_forward");
+  }
   const int VEC = (C % 4 == 0) ? 4 : 1;
   const long total = (long)N * (BWD ? (long)h * w : (long)H * W) * (C / VEC);
   const int grid = (int)min((long)148 * 32, (total + 255) / 256);

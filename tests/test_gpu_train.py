@@ -562,8 +562,9 @@ def test_gate_mul_and_axpby_nodes(dtype):
     assert _rel(o2.float(), a + s1 * b + s2 * up[:, :Cc]) < tol
     assert _rel(ad.grad.float(), ar.grad) < tol and _rel(bd.grad.float(), br.grad) < tol
     assert _rel(upd.grad.float(), upr.grad) < tol
-    assert abs(float(s1d.grad) - float(s1r.grad)) < tol * max(1.0, abs(float(s1r.grad)))
-    assert abs(float(s2d.grad) - float(s2r.grad)) < tol * max(1.0, abs(float(s2r.grad)))
+    stol = max(tol, 1e-4)                       # scalar gradients: fp32 sums of ~1e4 cancelling products, order differs
+    assert abs(float(s1d.grad) - float(s1r.grad)) < stol * max(1.0, abs(float(s1r.grad)))
+    assert abs(float(s2d.grad) - float(s2r.grad)) < stol * max(1.0, abs(float(s2r.grad)))
     o3 = T.axpby(ad, bd, s1d)
     assert _rel(o3.float(), a + s1 * b) < tol
 
