@@ -617,3 +617,43 @@ def test_blur_pool_forward_and_adjoint(H, W):
     y = T._BlurPool.apply(xd, kern.to(dev))
     y.backward(gy.to(dev))
     assert _rel(y, yr) < 2e-6 and _rel(xd.grad, xr.grad) < 2e-6
+
+
+def test_full_patch_size_directional_derivative():
+    """Size-independent property at the BASELINE patch size (64x64 LR -> 256x256 HR, too large for the CPU oracle to
+    differentiate in seconds): the directional derivative of the L1 loss along the normalised gradient direction,
+    by central differences of the kernels' own forward, equals |grad| (fp32 path, dropout off)."""
+    dev = _cuda()
+    m = _train_model().to(dev)
+    B, H, W = 4, 64, 64
+    lr, imgs, fts, hr = O.synthetic_inputs(B, H, W)
+    args = (lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()})
+    hr = hr.to(dev)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}          # BN running stats change per forward: restore
+
+    def loss_at():
+        m.load_state_dict(sd0)
+        return (m.forward_with_precomputed(*args) - hr).abs().mean()
+
+    loss = loss_at()
+    loss.backward()
+    params = [p for p in m.parameters()]
+    grads = [p.grad.detach().clone() for p in params]
+    gnorm = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).item()
+    assert gnorm > 0
+    eps = 2e-3
+    vals = []
+    with torch.no_grad():
+        for sgn in (+1.0, -1.0):
+            for p, g in zip(params, grads):
+                p.add_(g, alpha=sgn * eps / gnorm)
+            sd_shift = {k: v.clone() for k, v in m.state_dict().items()}
+            for k in sd0:
+                if "running_" in k or "num_batches" in k:
+                    sd_shift[k] = sd0[k].clone()
+            m.load_state_dict(sd_shift)
+            vals.append(float((m.forward_with_precomputed(*args) - hr).abs().mean()))
+            for p, g in zip(params, grads):
+                p.add_(g, alpha=-sgn * eps / gnorm)
+    fd = (vals[0] - vals[1]) / (2 * eps)
+    assert abs(fd - gnorm) <= 0.03 * gnorm, (fd, gnorm)
