@@ -126,10 +126,62 @@ def cpu_oracle_throughput(H, W, steps, warmup, threads):
     return 16 * H * W / t / 1e6, t
 
 
+def cpu_oracle_train_throughput(hw, batch, steps, warmup, threads, weights):
+    """patches/s of one CPU training step of the oracle port (forward + losses + autograd backward + AdamW)."""
+    import torch
+    import isr_b200
+    from oracle import fusion_oracle as O
+    from oracle import loss_oracle as LO
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    m = isr_b200.CompleteEnhancedFusionSR(None)
+    pn = dict(m.named_parameters())
+    sd = {k: (v.detach().clone().requires_grad_() if k in pn else v.detach().clone()) for k, v in m.state_dict().items()}
+    opt = torch.optim.AdamW([sd[k] for k in pn], lr=2e-4, betas=(0.9, 0.999), weight_decay=1e-4)
+    lr, imgs, fts, hr = O.synthetic_inputs(batch, hw, hw)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        sr = O.run_pipeline(sd, lr, imgs, fts, training=True, bn_updates={}).clamp(0, 1)
+        loss, _ = LO.combined_loss(sr, hr, weights)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([sd[k] for k in pn], 1.0)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return batch / t, t
+
+
+def run_reference_train(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    hw = 64 if args.workload == "c2" else 96
+    batch = 2                                                   # bounded sample of the global batch
+    v, t = cpu_oracle_train_throughput(hw, batch, max(1, min(args.steps, 3)), 1, threads, STAGE_WEIGHTS[args.workload])
+    line = {
+        "impl": "reference", "metric": "fusion_train_patches_per_s", "value": v, "unit": "patches/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": train_config(args.workload, batch, batch, hw, "fp32"),
+        "cpu_baseline": {"value": v, "unit": "patches/s", "cores": threads, "kind": "port",
+                         "sample": f"each step = forward + losses + autograd backward + clip + AdamW of the oracle port on "
+                                   f"{batch} patches of {hw}x{hw} LR (the metric is linear in patches)"},
+        "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload != "c3":
+        return run_reference_train(args)
     threads = os.cpu_count() or 1
     h, w = 96, 128                                              # bounded sample of the C3 workload
     v, t = cpu_oracle_throughput(h, w, args.steps, args.warmup, threads)
@@ -274,6 +326,12 @@ def run_train(args):
                                    "profiles/r01_conv_train_microbench.txt, profiles/r01_wgrad_tc_128x128_ncu_full.txt",
                          "peak_source": peak_src},
         }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, t = cpu_oracle_train_throughput(hw, 2, 2, 1, threads, STAGE_WEIGHTS[args.workload])
+            line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": threads, "kind": "port",
+                                    "sample": f"2 training steps (forward + losses + autograd backward + clip + AdamW) of the "
+                                              f"fp32 oracle port on 2 patches of {hw}x{hw} LR, {t:.1f} s per step on {threads} threads"}
         print(json.dumps(line), flush=True)
     _leave(world, r["trainer"])
 

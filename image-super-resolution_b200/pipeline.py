@@ -331,7 +331,12 @@ class FusionEngine:
             if tuple(t.shape) != (B, 3, 4 * H, 4 * W):
                 raise ValueError(f"expert image shape {tuple(t.shape)} != {(B, 3, 4 * H, 4 * W)}")
         with torch.cuda.device(dev):
-            return self._forward(lr, img_list, feats, B, H, W, want_inter)
+            entry_stream = torch.cuda.current_stream(dev)
+            try:
+                return self._forward(lr, img_list, feats, B, H, W, want_inter)
+            finally:
+                if torch.cuda.current_stream(dev) != entry_stream:      # an error inside the side-stream section
+                    torch.cuda.set_stream(entry_stream)
 
     def _forward(self, lr, img_list, feats, B, H, W, want_inter):
         m, lib, w = self.m, self.lib, None
