@@ -71,6 +71,8 @@ struct TcArgs {
   const float* ch_k;
   const float* ch_d;
   void* out2;        // optional bf16 pre-activation copy (same strides as out)
+  int halves;        // 1: tile = 8x16 px (M=128); 2: tile = 16x16 px as two M=128 MMAs sharing every weight stage
+  int acc_half;      // TMEM columns of one half accumulator (acc_slot = halves * acc_half)
 };
 
 // ---------------------------------------------------------------------------- PTX wrappers
@@ -382,14 +384,15 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, 
   for (ti.init(a); ti.valid(a); ti.next(a), item0 = (item0 + nch) & 3) {
     const int n = ti.n;
     const int g = a.groups > 1 ? n % a.groups : 0;
-    const int y = ti.ty * TC_TH + py, x = ti.tx * TC_TW + px;
+    bool waited = false;
+    for (int half = 0; half < a.halves; ++half, item0 = (item0 + (half < a.halves ? nch : 0)) & 3) {
+    const int y = ti.ty * (TC_TH * a.halves) + half * TC_TH + py, x = ti.tx * TC_TW + px;
     const bool inside = (y < a.H) && (x < a.W);
     const long long opix = (long long)n * a.out_sN + (long long)y * a.out_sY + (long long)x * a.out_sX;
     long long r1pix = 0, r2pix = 0;
     if (MODE == EM_RESIDUAL || MODE == EM_LKAGATE || MODE == EM_ACTGRAD) r1pix = (long long)n * a.r1_sN + (long long)y * a.r1_sY + (long long)x * a.r1_sX;
     if (MODE == EM_RESIDUAL) r2pix = (long long)n * a.r2_sN + (long long)y * a.r2_sY + (long long)x * a.r2_sX;
-    bool waited = false;
-    uint32_t taddr = 0;
+    uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * acc_slot + half * a.acc_half);
     for (int c = (cgp - item0) & 3; c < nch; c += 4) {
       const int ocb = ti.nb * nblk + c * 16;
       const int nvalid = min(16, Cout - ocb);            // may be <= 0 for padded columns
@@ -423,7 +426,6 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, 
       if (!waited) {
         mbar_wait(&tfull[as], aph);
         tc_fence_after();
-        taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * acc_slot);
         waited = true;
       }
       uint32_t v[16];
@@ -469,6 +471,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, 
         store16_out<OUT_BF16>(a.out, opix + ocb, f, nvalid);
       }
     }
+    }   // halves
     if (!waited) mbar_wait(&tfull[as], aph);          // warps without a column chunk still pace the ring
     tc_fence_before();
     __syncwarp();
@@ -542,7 +545,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sa_ = stages + s * a.stage_bytes;
             mbar_expect_tx_e(&full[s], stage_tx);
-            tma_load_4d(sa_, &tmA, &full[s], ch * 64, tx * TC_TW + dxi - pad, ty * TC_TH - pad, n);
+            tma_load_4d(sa_, &tmA, &full[s], ch * 64, tx * TC_TW + dxi - pad, ty * (TC_TH * a.halves) - pad, n);
             if (!a.b_resident) tma_load_5d(sa_ + a.a_bytes, &tmB, &full[s], ch * 64, nb * a.nblk, dxi, 0, g);
             last_s = s; last_ph = ph; have_last = true;
             if (++s == a.nstages) { s = 0; ph ^= 1; }
@@ -585,22 +588,28 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           // weights: streamed next to the A copy, or the resident slice of this (chunk, dx)
           const uint32_t b_addr = a.b_resident ? bres_u32 + (uint32_t)it * (uint32_t)a.b_bytes : a_addr + (uint32_t)a.a_bytes;
           const int ksteps = (it >= last_chunk_it) ? a.ksteps_last : 4;
-          const uint32_t al = desc_lo(a_addr), bl = desc_lo(b_addr);
+          const uint32_t al0 = desc_lo(a_addr), bl = desc_lo(b_addr);
           const uint32_t acc0 = it > 0 ? 1u : 0u;
-          // every MMA of this stage (ks taps along dy x ksteps K-steps) in one PTX block
-          if (a.ks == 3) {
-            switch (ksteps) {
-              case 4: umma_stage_ks3_k4(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
-              case 3: umma_stage_ks3_k3(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
-              case 2: umma_stage_ks3_k2(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
-              default: umma_stage_ks3_k1(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
-            }
-          } else {
-            switch (ksteps) {
-              case 4: umma_stage_ks1_k4(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
-              case 3: umma_stage_ks1_k3(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
-              case 2: umma_stage_ks1_k2(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
-              default: umma_stage_ks1_k1(tmem_d, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+          // every MMA of this stage (ks taps along dy x ksteps K-steps) in one PTX block per tile half; the second
+          // half (output rows 8..15 of a 16-row tile) reads the same haloed copy 8 image rows further down and the
+          // SAME weight stage
+          for (int half = 0; half < a.halves; ++half) {
+            const uint32_t al = al0 + (uint32_t)half * (uint32_t)((TC_TH * TC_ROW_BYTES) >> 4);
+            const uint32_t td = tmem_d + (uint32_t)(half * a.acc_half);
+            if (a.ks == 3) {
+              switch (ksteps) {
+                case 4: umma_stage_ks3_k4(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+                case 3: umma_stage_ks3_k3(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+                case 2: umma_stage_ks3_k2(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+                default: umma_stage_ks3_k1(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+              }
+            } else {
+              switch (ksteps) {
+                case 4: umma_stage_ks1_k4(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+                case 3: umma_stage_ks1_k3(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+                case 2: umma_stage_ks1_k2(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+                default: umma_stage_ks1_k1(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
+              }
             }
           }
           umma_commit(&empty[s]);                       // smem slot reusable once these MMAs retire
@@ -685,11 +694,24 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   const int cout_pad = (cout_pad16 + nblk - 1) / nblk * nblk;
   FFSR_REQUIRE(((uintptr_t)p.w % 16) == 0, FFSR_ERR_ALIGN, "conv2d(tc): weights must be 16B aligned");
 
+  // Streamed weights (the whole 3x3 set of a cout block does not fit beside three A stages: 128->128) are re-fetched
+  // for every pixel tile and dominate the TMA traffic (2304 of 3264 128-byte rows per tile).  Those layers use
+  // 16x16-pixel tiles: two M=128 MMAs per (tap, K-step) share each weight stage, halving the weight rows per pixel.
+  int halves = 1;
+  {
+    const int nch0 = (p.Cin + 63) / 64;
+    const int a8 = (TC_TH + 2 * (p.ksize / 2)) * TC_ROW_BYTES;
+    const int a16 = (2 * TC_TH + 2 * (p.ksize / 2)) * TC_ROW_BYTES;
+    const int bb = p.ksize * nblk * 128;
+    const int avail0 = TC_SMEM_MAX - 1024 - TC_SMEM_HDR;
+    const bool resident = nch0 * p.ksize * bb + 3 * a8 <= avail0;
+    if (!resident && p.ksize == 3 && p.H >= 16 && 2 * (a16 + bb) <= avail0 && nblk * 2 * 2 <= TC_TMEM_COLS) halves = 2;
+  }
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
     cuuint64_t strides[3] = {(cuuint64_t)p.in_sX * 2, (cuuint64_t)p.in_sY * 2, (cuuint64_t)p.in_sN * 2};
-    cuuint32_t box[4] = {64, TC_TW, (cuuint32_t)(TC_TH + 2 * (p.ksize / 2)), 1};
+    cuuint32_t box[4] = {64, TC_TW, (cuuint32_t)(TC_TH * halves + 2 * (p.ksize / 2)), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.in), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -716,7 +738,8 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   a.nchunks = cin_pad / 64;
   const int last = p.Cin - (a.nchunks - 1) * 64;
   a.ksteps_last = (last + 15) / 16;
-  a.a_bytes = (TC_TH + 2 * (p.ksize / 2)) * TC_ROW_BYTES;
+  a.halves = halves;
+  a.a_bytes = (TC_TH * halves + 2 * (p.ksize / 2)) * TC_ROW_BYTES;
   a.b_bytes = p.ksize * nblk * 128;
   const int smem_avail = TC_SMEM_MAX - 1024 - TC_SMEM_HDR;
   const int b_all = a.nchunks * p.ksize * a.b_bytes;          // all taps, all K chunks of one cout block
@@ -726,12 +749,13 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   a.nstages = (smem_avail - a.bres_bytes) / a.stage_bytes;
   if (a.nstages > TC_MAX_STAGES) a.nstages = TC_MAX_STAGES;
   const int smem_bytes = 1024 + TC_SMEM_HDR + a.bres_bytes + a.nstages * a.stage_bytes;
-  a.acc_slot = nblk <= 32 ? 32 : (nblk <= 64 ? 64 : 128);
+  a.acc_half = nblk <= 32 ? 32 : (nblk <= 64 ? 64 : 128);
+  a.acc_slot = a.acc_half * halves;
   a.nacc = TC_TMEM_COLS / a.acc_slot;
   if (a.nacc > TC_MAX_ACC) a.nacc = TC_MAX_ACC;
   a.groups = p.groups;
   a.tiles_x = ceil_div(p.W, TC_TW);
-  a.tiles_y = ceil_div(p.H, TC_TH);
+  a.tiles_y = ceil_div(p.H, TC_TH * halves);
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * p.N * a.n_nblocks;
   a.out = p.out; a.out_sN = p.out_sN; a.out_sY = p.out_sY; a.out_sX = p.out_sX;
   a.out_bf16 = p.out_dtype == FFSR_DT_BF16;
