@@ -26,6 +26,7 @@
 //               tile (~2k issue cycles) hides under the MMAs of the next one.
 // Persistent: grid = min(tiles, #SMs), static round-robin over tiles.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/ffsr_b200.h"
 
@@ -73,6 +74,10 @@ struct TcArgs {
   void* out2;        // optional bf16 pre-activation copy (same strides as out)
   int halves;        // 1: tile = 8x16 px (M=128); 2: tile = 16x16 px as two M=128 MMAs sharing every weight stage
   int acc_half;      // TMEM columns of one half accumulator (acc_slot = halves * acc_half)
+  int geom;          // 0: 8x16-px tile rows, one haloed A copy per dx;  1: 16x8-px tiles, ONE haloed copy per K chunk
+  int tile_h;        // output rows per tile (8 * halves, or 16 for geom 1)
+  uint32_t a_step16; // geom 1: dy stride inside the haloed copy, in 16-byte units (10 px * 128 B)
+  uint32_t a_desc_hi;// geom 1: A descriptor high word (SBO = haloed image-row pitch)
 };
 
 // ---------------------------------------------------------------------------- PTX wrappers
@@ -368,8 +373,9 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, 
                                               int warp, int lane) {
   const int wq = warp & 3;
   const int cgp = (warp - 2) >> 2;
-  const int row = wq * 32 + lane;                       // pixel within the tile
-  const int py = row / TC_TW, px = row % TC_TW;
+  const int row = wq * 32 + lane;                       // pixel within the tile (accumulator row)
+  const int tw = a.geom ? 8 : TC_TW;
+  const int py = row / tw, px = row % tw;
   const int nch = a.nblk >> 4;
   const int Cout = a.Cout, nblk = a.nblk, nacc = a.nacc, acc_slot = a.acc_slot;
   const float* __restrict__ bias = a.bias;
@@ -386,7 +392,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, 
     const int g = a.groups > 1 ? n % a.groups : 0;
     bool waited = false;
     for (int half = 0; half < a.halves; ++half, item0 = (item0 + (half < a.halves ? nch : 0)) & 3) {
-    const int y = ti.ty * (TC_TH * a.halves) + half * TC_TH + py, x = ti.tx * TC_TW + px;
+    const int y = ti.ty * a.tile_h + half * TC_TH + py, x = ti.tx * tw + px;
     const bool inside = (y < a.H) && (x < a.W);
     const long long opix = (long long)n * a.out_sN + (long long)y * a.out_sY + (long long)x * a.out_sX;
     long long r1pix = 0, r2pix = 0;
@@ -515,7 +521,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t tmem_base = *tmem_slot;
 
   const int pad = a.ks / 2;
-  const int kiters = a.ks * a.nchunks;               // one pipeline stage per (chunk, dx)
+  const int kiters = a.geom ? a.nchunks : a.ks * a.nchunks;   // one pipeline stage per (chunk, dx) / per chunk (geom 1)
   const uint32_t stage_tx = (uint32_t)(a.a_bytes + (a.b_resident ? 0 : a.b_bytes));
 
   if (warp == 0) {
@@ -540,12 +546,23 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           cur_g = g;
           cur_nb = nb;
         }
+        if (a.geom) {
+          // one row-haloed, column-haloed copy {64 ch, 10 px, 18 rows} per K chunk serves all nine taps
+          for (int ch = 0; ch < a.nchunks; ++ch) {
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sa_ = stages + s * a.stage_bytes;
+            mbar_expect_tx_e(&full[s], stage_tx);
+            tma_load_4d(sa_, &tmA, &full[s], ch * 64, tx * 8 - pad, ty * a.tile_h - pad, n);
+            last_s = s; last_ph = ph; have_last = true;
+            if (++s == a.nstages) { s = 0; ph ^= 1; }
+          }
+        } else
         for (int ch = 0; ch < a.nchunks; ++ch) {
           for (int dxi = 0; dxi < a.ks; ++dxi) {
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sa_ = stages + s * a.stage_bytes;
             mbar_expect_tx_e(&full[s], stage_tx);
-            tma_load_4d(sa_, &tmA, &full[s], ch * 64, tx * TC_TW + dxi - pad, ty * (TC_TH * a.halves) - pad, n);
+            tma_load_4d(sa_, &tmA, &full[s], ch * 64, tx * TC_TW + dxi - pad, ty * a.tile_h - pad, n);
             if (!a.b_resident) tma_load_5d(sa_ + a.a_bytes, &tmB, &full[s], ch * 64, nb * a.nblk, dxi, 0, g);
             last_s = s; last_ph = ph; have_last = true;
             if (++s == a.nstages) { s = 0; ph ^= 1; }
@@ -564,7 +581,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint32_t bph = 0;
     const uint32_t stages_u32 = smem_u32(stages), bres_u32 = smem_u32(bres);
     const uint32_t b_step = (uint32_t)(a.nblk * 128) >> 4;
-    const int last_chunk_it = (a.nchunks - 1) * a.ks;        // stages of the last (possibly partial) K chunk
+    const int last_chunk_it = a.geom ? a.nchunks - 1 : (a.nchunks - 1) * a.ks;   // stages of the last (possibly partial) K chunk
     TileIter ti;
     for (ti.init(a); ti.valid(a); ti.next(a)) {
       if (a.b_resident) {
@@ -588,6 +605,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           // weights: streamed next to the A copy, or the resident slice of this (chunk, dx)
           const uint32_t b_addr = a.b_resident ? bres_u32 + (uint32_t)it * (uint32_t)a.b_bytes : a_addr + (uint32_t)a.a_bytes;
           const int ksteps = (it >= last_chunk_it) ? a.ksteps_last : 4;
+          if (a.geom) {
+            // tap (dy, dx) = the same copy at byte offset dy*1280 + dx*128: the 128B swizzle is a function of the
+            // absolute shared-memory address (measured), so unaligned starts and SBO = 1280 need no base offset
+            for (int dxi = 0; dxi < 3; ++dxi) {
+              const uint32_t al = desc_lo(a_addr + 128u * (uint32_t)dxi);
+              const uint32_t blx = desc_lo(bres_u32 + (uint32_t)(it * 3 + dxi) * (uint32_t)a.b_bytes);
+              const uint32_t accx = (it > 0 || dxi > 0) ? 1u : 0u;
+              switch (ksteps) {
+                case 4: umma_stage1c_ks3_k4(tmem_d, al, blx, idesc, accx, a.a_desc_hi, b_step, a.a_step16, TC_DESC_HI); break;
+                case 3: umma_stage1c_ks3_k3(tmem_d, al, blx, idesc, accx, a.a_desc_hi, b_step, a.a_step16, TC_DESC_HI); break;
+                case 2: umma_stage1c_ks3_k2(tmem_d, al, blx, idesc, accx, a.a_desc_hi, b_step, a.a_step16, TC_DESC_HI); break;
+                default: umma_stage1c_ks3_k1(tmem_d, al, blx, idesc, accx, a.a_desc_hi, b_step, a.a_step16, TC_DESC_HI); break;
+              }
+            }
+          } else {
           const uint32_t al0 = desc_lo(a_addr), bl = desc_lo(b_addr);
           const uint32_t acc0 = it > 0 ? 1u : 0u;
           // every MMA of this stage (ks taps along dy x ksteps K-steps) in one PTX block per tile half; the second
@@ -611,6 +643,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 default: umma_stage_ks1_k1(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
               }
             }
+          }
           }
           umma_commit(&empty[s]);                       // smem slot reusable once these MMAs retire
           if (it == kiters - 1) umma_commit(&tfull[as]);  // accumulator complete
@@ -707,11 +740,24 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
     const bool resident = nch0 * p.ksize * bb + 3 * a8 <= avail0;
     if (!resident && p.ksize == 3 && p.H >= 16 && 2 * (a16 + bb) <= avail0 && nblk * 2 * 2 <= TC_TMEM_COLS) halves = 2;
   }
+  // 3x3 layers whose weights stay resident use 16x8-pixel tiles fed by ONE haloed copy per 64-channel chunk
+  // ({64 ch, 10 px, 18 rows} = 23 KB instead of three 20 KB copies per 128 output pixels): these layers are bound by
+  // the L2 -> shared-memory traffic of the haloed A copies, not by the tensor pipe.
+  int geom = 0;
+  constexpr int A1C_BYTES = 18 * 10 * 128, A1C_STAGE = (A1C_BYTES + 1023) / 1024 * 1024;
+  {
+    const int nch0 = (p.Cin + 63) / 64;
+    const int bb = p.ksize * nblk * 128;
+    const int avail0 = TC_SMEM_MAX - 1024 - TC_SMEM_HDR;
+    if (p.ksize == 3 && halves == 1 && nch0 * p.ksize * bb + 3 * A1C_STAGE <= avail0 && p.H >= 8 && getenv("FFSR_TC_GEOM0") == nullptr)
+      geom = 1;
+  }
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
     cuuint64_t strides[3] = {(cuuint64_t)p.in_sX * 2, (cuuint64_t)p.in_sY * 2, (cuuint64_t)p.in_sN * 2};
     cuuint32_t box[4] = {64, TC_TW, (cuuint32_t)(TC_TH * halves + 2 * (p.ksize / 2)), 1};
+    if (geom) { box[1] = 10; box[2] = 18; }
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.in), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -739,13 +785,21 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   const int last = p.Cin - (a.nchunks - 1) * 64;
   a.ksteps_last = (last + 15) / 16;
   a.halves = halves;
-  a.a_bytes = (TC_TH * halves + 2 * (p.ksize / 2)) * TC_ROW_BYTES;
+  a.geom = geom;
+  a.tile_h = geom ? 16 : TC_TH * halves;
+  a.a_step16 = (10u * 128u) >> 4;
+  a.a_desc_hi = ((10u * 128u) >> 4) | (1u << 14) | (2u << 29);
+  a.a_bytes = geom ? A1C_BYTES : (TC_TH * halves + 2 * (p.ksize / 2)) * TC_ROW_BYTES;
   a.b_bytes = p.ksize * nblk * 128;
   const int smem_avail = TC_SMEM_MAX - 1024 - TC_SMEM_HDR;
   const int b_all = a.nchunks * p.ksize * a.b_bytes;          // all taps, all K chunks of one cout block
   a.b_resident = (b_all + 3 * a.a_bytes <= smem_avail) ? 1 : 0;
   a.bres_bytes = a.b_resident ? b_all : 0;
-  a.stage_bytes = a.a_bytes + (a.b_resident ? 0 : a.b_bytes);
+  a.stage_bytes = geom ? A1C_STAGE : a.a_bytes + (a.b_resident ? 0 : a.b_bytes);
+  if (geom) {                                                  // decided above with the same residency test
+    a.b_resident = 1;
+    a.bres_bytes = b_all;
+  }
   a.nstages = (smem_avail - a.bres_bytes) / a.stage_bytes;
   if (a.nstages > TC_MAX_STAGES) a.nstages = TC_MAX_STAGES;
   const int smem_bytes = 1024 + TC_SMEM_HDR + a.bres_bytes + a.nstages * a.stage_bytes;
@@ -754,8 +808,8 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   a.nacc = TC_TMEM_COLS / a.acc_slot;
   if (a.nacc > TC_MAX_ACC) a.nacc = TC_MAX_ACC;
   a.groups = p.groups;
-  a.tiles_x = ceil_div(p.W, TC_TW);
-  a.tiles_y = ceil_div(p.H, TC_TH * halves);
+  a.tiles_x = ceil_div(p.W, geom ? 8 : TC_TW);
+  a.tiles_y = ceil_div(p.H, a.tile_h);
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * p.N * a.n_nblocks;
   a.out = p.out; a.out_sN = p.out_sN; a.out_sY = p.out_sY; a.out_sX = p.out_sX;
   a.out_bf16 = p.out_dtype == FFSR_DT_BF16;
