@@ -21,10 +21,19 @@ struct CBSmem {
   float wo[CB_DIM][CB_DIM];            // out_proj weight transposed: wo[c][o]
   float pw[CB_DIM][4];                 // band_proj weight [o][3] + bias in slot 3
   float lnw[CB_DIM], lnb[CB_DIM], ob[CB_DIM];
+  float fa[CB_DIM][4];                 // folded path: centred band_proj rows A[c][0..2] and centred bias c[c]
+  float rstd[CB_TOK];                  // folded path: LayerNorm 1/std per token
 };
 }  // namespace
 
+// FOLD: band_proj -> LayerNorm -> in_proj collapsed algebraically.  A token is an affine function of the 3 band
+// values x:  t = Wp x + b;  t - mean(t) = A x + c;  LN(t) = (A x + c) * rstd * gamma + beta;  so
+//   qkv = W_in LN(t) + b_in = rstd * (M x + m0) + n0,   M = W_in diag(gamma) A  [192x3],  m0 = W_in diag(gamma) c,
+//   n0 = W_in beta + b_in  (folded on the host in fp64): 4 FMAs per qkv channel instead of 64, with the variance
+// still taken from the 64 centred values themselves.  fold = [A|c : 64x4][M|m0 : 192x4][n0 : 192].
+template <bool FOLD>
 __global__ void __launch_bounds__(CB_THREADS, 2) k_crossband_attn(
+    const float* __restrict__ fold,
     const float* __restrict__ raw9, int B, int HW,
     const float* __restrict__ proj_w, const float* __restrict__ proj_b,
     const float* __restrict__ ln_w, const float* __restrict__ ln_b,
@@ -49,13 +58,24 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_crossband_attn(
     s.lnb[tid] = ln_b[tid];
     s.ob[tid] = out_b[tid];
   }
-  float wrow[CB_DIM];                  // this thread's in_proj row (q|k|v output channel tid)
+  float wrow[FOLD ? 4 : CB_DIM];       // this thread's in_proj row (q|k|v output channel tid), or its folded 3+1 row
+  float brow;
+  if (FOLD) {
+    const float4 v = *reinterpret_cast<const float4*>(fold + CB_DIM * 4 + (long)tid * 4);
+    wrow[0] = v.x; wrow[1] = v.y; wrow[2] = v.z; wrow[3] = v.w;
+    brow = fold[CB_DIM * 4 + 3 * CB_DIM * 4 + tid];
+    if (tid < CB_DIM) {
+      const float4 a = *reinterpret_cast<const float4*>(fold + tid * 4);
+      s.fa[tid][0] = a.x; s.fa[tid][1] = a.y; s.fa[tid][2] = a.z; s.fa[tid][3] = a.w;
+    }
+  } else {
 #pragma unroll
-  for (int c = 0; c < CB_DIM; c += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(in_w + (long)tid * CB_DIM + c);
-    wrow[c] = v.x; wrow[c + 1] = v.y; wrow[c + 2] = v.z; wrow[c + 3] = v.w;
+    for (int c = 0; c < (FOLD ? 4 : CB_DIM); c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(in_w + (long)tid * CB_DIM + c);
+      wrow[c] = v.x; wrow[c + 1] = v.y; wrow[c + 2] = v.z; wrow[c + 3] = v.w;
+    }
+    brow = in_b[tid];
   }
-  const float brow = in_b[tid];
   __syncthreads();
 
   const int tiles_per_img = (HW + CB_PX - 1) / CB_PX;
@@ -77,6 +97,15 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_crossband_attn(
       const int px = tk / CB_BANDS, band = tk % CB_BANDS;
       const float x0 = s.in[px][band * 3], x1 = s.in[px][band * 3 + 1], x2 = s.in[px][band * 3 + 2];
       const int c0 = lane, c1 = lane + 32;
+      if (FOLD) {                        // only 1/std is needed: the centred values come straight from A x + c
+        const float d0 = fmaf(s.fa[c0][2], x2, fmaf(s.fa[c0][1], x1, fmaf(s.fa[c0][0], x0, s.fa[c0][3])));
+        const float d1 = fmaf(s.fa[c1][2], x2, fmaf(s.fa[c1][1], x1, fmaf(s.fa[c1][0], x0, s.fa[c1][3])));
+        float sq = d0 * d0 + d1 * d1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) s.rstd[tk] = rsqrtf(sq * (1.0f / CB_DIM) + 1e-5f);
+        continue;
+      }
       const float v0 = fmaf(s.pw[c0][2], x2, fmaf(s.pw[c0][1], x1, fmaf(s.pw[c0][0], x0, s.pw[c0][3])));
       const float v1 = fmaf(s.pw[c1][2], x2, fmaf(s.pw[c1][1], x1, fmaf(s.pw[c1][0], x0, s.pw[c1][3])));
       float sum = v0 + v1;
@@ -97,15 +126,24 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_crossband_attn(
     for (int tk = 0; tk < CB_TOK; ++tk) {
       // queries are only needed for the first nq bands (keys / values for all nine): the two q warps skip the rest
       if (tid < CB_DIM && (tk % CB_BANDS) >= nq) continue;
+      if (FOLD) {
+        const int px = tk / CB_BANDS, band = tk % CB_BANDS;
+        const float x0 = s.in[px][band * 3], x1 = s.in[px][band * 3 + 1], x2 = s.in[px][band * 3 + 2];
+        const float lin = fmaf(wrow[2], x2, fmaf(wrow[1], x1, fmaf(wrow[0], x0, wrow[3])));
+        s.qkv[tk][tid] = fmaf(lin, s.rstd[tk], brow);
+        continue;
+      }
       float acc = brow;
-      const float4* nrow = reinterpret_cast<const float4*>(&s.n[tk][0]);
+      if constexpr (!FOLD) {
+        const float4* nrow = reinterpret_cast<const float4*>(&s.n[tk][0]);
 #pragma unroll
-      for (int c4 = 0; c4 < CB_DIM / 4; ++c4) {
-        const float4 v = nrow[c4];
-        acc = fmaf(v.x, wrow[4 * c4], acc);
-        acc = fmaf(v.y, wrow[4 * c4 + 1], acc);
-        acc = fmaf(v.z, wrow[4 * c4 + 2], acc);
-        acc = fmaf(v.w, wrow[4 * c4 + 3], acc);
+        for (int c4 = 0; c4 < CB_DIM / 4; ++c4) {
+          const float4 v = nrow[c4];
+          acc = fmaf(v.x, wrow[4 * c4], acc);
+          acc = fmaf(v.y, wrow[4 * c4 + 1], acc);
+          acc = fmaf(v.z, wrow[4 * c4 + 2], acc);
+          acc = fmaf(v.w, wrow[4 * c4 + 3], acc);
+        }
       }
       s.qkv[tk][tid] = acc;
     }
@@ -171,7 +209,7 @@ extern "C" int ffsr_crossband_attention(const float* raw9, int B, int H, int W, 
                                         const float* proj_b, const float* ln_w, const float* ln_b,
                                         const float* in_w, const float* in_b, const float* out_w,
                                         const float* out_b, int nq, float* tok_out, int num_sms,
-                                        cudaStream_t stream) {
+                                        const float* fold, cudaStream_t stream) {
   FFSR_REQUIRE(raw9 && proj_w && proj_b && ln_w && ln_b && in_w && in_b && out_w && out_b && tok_out, FFSR_ERR_ARG,
                "crossband_attention: null pointer");
   FFSR_REQUIRE(B > 0 && H > 0 && W > 0 && nq >= 1 && nq <= CB_BANDS, FFSR_ERR_ARG, "crossband_attention: bad shape");
@@ -180,12 +218,19 @@ extern "C" int ffsr_crossband_attention(const float* raw9, int B, int H, int W, 
   const int tiles = B * ((HW + CB_PX - 1) / CB_PX);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_crossband_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CBSmem));
+    cudaFuncSetAttribute(k_crossband_attn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CBSmem));
+    cudaFuncSetAttribute(k_crossband_attn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CBSmem));
     attr_set = true;
   }
   const int grid = tiles < 2 * num_sms ? tiles : 2 * num_sms;
-  k_crossband_attn<<<grid, CB_THREADS, sizeof(CBSmem), stream>>>(raw9, B, HW, proj_w, proj_b, ln_w, ln_b, in_w, in_b,
-                                                                 out_w, out_b, nq, tok_out);
+  if (fold) {
+    FFSR_REQUIRE(((uintptr_t)fold % 16) == 0, FFSR_ERR_ALIGN, "crossband_attention: fold buffer must be 16B aligned");
+    k_crossband_attn<true><<<grid, CB_THREADS, sizeof(CBSmem), stream>>>(fold, raw9, B, HW, proj_w, proj_b, ln_w, ln_b, in_w,
+                                                                         in_b, out_w, out_b, nq, tok_out);
+  } else {
+    k_crossband_attn<false><<<grid, CB_THREADS, sizeof(CBSmem), stream>>>(nullptr, raw9, B, HW, proj_w, proj_b, ln_w, ln_b,
+                                                                          in_w, in_b, out_w, out_b, nq, tok_out);
+  }
   return ffsr_check_launch("crossband_attention");
 }
 

@@ -84,6 +84,7 @@ class FusionEngine:
         # {weight name: [(start_event, end_event), ...]}
         self.timed_layers = None
         self.overlap_routing = True    # phases 3 + 6 on a side stream, concurrent with phases 4 / 5
+        self.fold_crossband = True     # band_proj -> LayerNorm -> in_proj folded to 3+1 MACs per qkv channel
         self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ weights
@@ -140,6 +141,18 @@ class FusionEngine:
             cb = m.cross_band
             w["cb.proj_w"] = cb.band_proj.weight.detach().float().reshape(64, 3).contiguous()
             w["cb.out_w"] = cb.out_proj.weight.detach().float().reshape(3, 64).contiguous()
+            # band_proj -> LayerNorm -> in_proj folded in fp64 (see k_crossband_attn<FOLD>)
+            Wp = cb.band_proj.weight.detach().double().reshape(64, 3)
+            bp = cb.band_proj.bias.detach().double()
+            A_ = Wp - Wp.mean(dim=0, keepdim=True)
+            c_ = bp - bp.mean()
+            Win = cb.band_attention.in_proj_weight.detach().double()            # [192, 64]
+            gam, bet = cb.norm.weight.detach().double(), cb.norm.bias.detach().double()
+            Wg = Win * gam[None, :]
+            fold = torch.cat([torch.cat([A_, c_[:, None]], 1).reshape(-1),
+                              torch.cat([Wg @ A_, (Wg @ c_)[:, None]], 1).reshape(-1),
+                              Win @ bet + cb.band_attention.in_proj_bias.detach().double()])
+            w["cb.fold"] = fold.float().contiguous()
             co = m.collaborative
             for n in EXPERT_ORDER:
                 conv("co.align." + n, co.align_layers[n])
@@ -410,7 +423,7 @@ class FusionEngine:
                    pp("cross_band.band_proj.bias"), pp("cross_band.norm.weight"), pp("cross_band.norm.bias"),
                    pp("cross_band.band_attention.in_proj_weight"), pp("cross_band.band_attention.in_proj_bias"),
                    pp("cross_band.band_attention.out_proj.weight"), pp("cross_band.band_attention.out_proj.bias"),
-                   nq, tok.data_ptr(), nsm, S)
+                   nq, tok.data_ptr(), nsm, w["cb.fold"].data_ptr() if self.fold_crossband else None, S)
         x2 = self._lka_block("cb.lka", "cross_band.lka_block", tok, "cb%d" % nq)
         enh9 = self._buf("enh9", (B, 9, 3, H, W), dev, fresh=fr)
         routing = self._buf("routing", (B, 3, H, W), dev, fresh=fr)
