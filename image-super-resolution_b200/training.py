@@ -72,6 +72,17 @@ def _empty_cl(N, Cc, H, W, dev, dtype=torch.float32) -> torch.Tensor:
     return torch.empty_strided((N, Cc, H, W), (H * W * Cc, 1, W * Cc, Cc), device=dev, dtype=dtype)
 
 
+def _empty_cl_padded(N, Cc, H, W, dev, dtype) -> torch.Tensor:
+    """Channels-last [N,Cc,H,W] view of a buffer whose pixel pitch is padded to a multiple of 8 channels: keeps the
+    16-byte vector stores of the conv epilogue aligned when Cc is e.g. 76 (a 152-byte bf16 pitch falls back to 2-byte
+    stores: the stage-3 input gradient took 0.99 ms instead of ~0.4 ms)."""
+    cp = (Cc + 7) // 8 * 8
+    if cp == Cc:
+        return _empty_cl(N, Cc, H, W, dev, dtype)
+    buf = torch.empty(N, H, W, cp, device=dev, dtype=dtype)
+    return buf.permute(0, 3, 1, 2)[:, :Cc]
+
+
 def _zeros(shape, dev, dtype=torch.float32):
     return torch.zeros(shape, device=dev, dtype=dtype)
 
@@ -202,7 +213,7 @@ def _launch_conv_tc(xb: torch.Tensor, Cin: int, wtc: torch.Tensor, bias, out: to
     p.bias = bias.data_ptr() if bias is not None else None
     p.groups = 1
     p.out = out.data_ptr()
-    p.out_sN, p.out_sY, p.out_sX = H * W * Cout, W * Cout, Cout
+    p.out_sN, p.out_sY, p.out_sX = out.stride(0), out.stride(2), out.stride(3)      # dense or padded-pitch channels-last
     p.act, p.epi = act, K.EPI_PLAIN
     p.sa = p.sb = 1.0
     p.in_dtype, p.w_dtype = K.DT_BF16, K.DT_BF16
@@ -245,7 +256,7 @@ class _Conv2dTC(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             wr = _pack_tc(weight.detach().flip(2, 3).permute(2, 3, 0, 1).reshape(kh * kw, co, ci))
-            dx = _empty_cl(N, ci, H, W, xb.device, ctx.x_dtype if ctx.x_dtype == torch.bfloat16 else torch.float32)
+            dx = _empty_cl_padded(N, ci, H, W, xb.device, ctx.x_dtype if ctx.x_dtype == torch.bfloat16 else torch.float32)
             _launch_conv_tc(gb, co, wr, None, dx, kh)
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
@@ -360,7 +371,7 @@ class _ConvChainTC(torch.autograd.Function):
                     g = _empty_cl(N, ci, H, W, xb.device, torch.bfloat16)
                     _launch_conv_tc(gb, co, wr, None, g, kh, acts[i - 1], None, zs[i - 1])
                 else:
-                    dx = _empty_cl(N, ci, H, W, xb.device, torch.bfloat16 if x_dtype == torch.bfloat16 else torch.float32)
+                    dx = _empty_cl_padded(N, ci, H, W, xb.device, torch.bfloat16 if x_dtype == torch.bfloat16 else torch.float32)
                     _launch_conv_tc(gb, co, wr, None, dx, kh)
         return (dx, None, None, *grads)
 
