@@ -25,6 +25,18 @@
 //               all four SM sub-partitions busy with the GELU math so that the epilogue of a
 //               tile (~2k issue cycles) hides under the MMAs of the next one.
 // Persistent: grid = min(tiles, #SMs), static round-robin over tiles.
+//
+// Three tile geometries, chosen per layer in ffsr_conv2d_tc:
+//   g0   : the 8x16-pixel tile described above (1x1 layers; 3x3 layers only as a fallback);
+//   g0x2 : 16x16-pixel tiles = two M=128 MMAs per (tap, K-step) that share every STREAMED weight stage (128->128 3x3,
+//          whose nine-tap weight set does not fit beside the A stages);
+//   g1   : 16x8-pixel tiles fed by ONE haloed copy {64 ch, 10 px, 18 rows} per 64-channel chunk -- every other 3x3
+//          layer.  Measured: the 128-byte swizzle of tcgen05 shared-memory operands is a function of the ABSOLUTE
+//          shared-memory address, so the operand of tap (dy, dx) is the same copy at byte offset dy*1280 + dx*128
+//          (SBO = 1280, base offset 0).  These layers were bound by the L2 -> shared-memory traffic of three haloed
+//          copies per tile, not by the tensor pipe.
+// Epilogue extras for the training graph: an optional bf16 copy of the pre-activation (out2) and FFSR_EPI_ACTGRAD
+// (input gradient multiplied by act'(saved pre-activation of the previous layer)).
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"

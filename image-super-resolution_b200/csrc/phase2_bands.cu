@@ -175,6 +175,12 @@ __global__ void k_fft_mask(const float* __restrict__ logits, int ms, int H, int 
 __global__ void __launch_bounds__(128) k_fft_rows_fwd(const float* __restrict__ x, int H, int W, int Wf,
                                                       const double2* __restrict__ tw, double2* __restrict__ A) {
   __shared__ float srow[256];
+  __shared__ double2 stw[1024];               // twiddle table in shared memory (W <= 1024): the inner loop is
+  const bool tw_s = W <= 1024;                // latency-bound on the table look-up, not on fp64 throughput
+  if (tw_s)
+    for (int t = threadIdx.x; t < W; t += blockDim.x) stw[t] = tw[t];
+  const double2* __restrict__ twp = tw_s ? stw : tw;
+  __syncthreads();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, bc = blockIdx.z;
   const float* row = x + ((long)bc * H + y) * W;
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(128) k_fft_rows_fwd(const float* __restrict__ 
     if (k < Wf) {
       for (int t = 0; t < n; ++t) {
         const double v = (double)srow[t];
-        const double2 w = tw[idx];
+        const double2 w = twp[idx];
         re = fma(v, w.x, re);
         im = fma(-v, w.y, im);
         idx += k;
@@ -204,6 +210,12 @@ template <int DIR>
 __global__ void __launch_bounds__(256) k_fft_cols(const double2* __restrict__ A, int H, int Wf,
                                                   const double2* __restrict__ tw, const float* __restrict__ mask,
                                                   double scale, double2* __restrict__ Out) {
+  __shared__ double2 stw[1024];
+  const bool tw_s = H <= 1024;
+  if (tw_s)
+    for (int t = threadIdx.y * 32 + threadIdx.x; t < H; t += 256) stw[t] = tw[t];
+  const double2* __restrict__ twp = tw_s ? stw : tw;
+  __syncthreads();
   const int k = blockIdx.x * 32 + threadIdx.x;
   const int l = blockIdx.y * 8 + threadIdx.y;
   const int bc = blockIdx.z;
@@ -213,7 +225,7 @@ __global__ void __launch_bounds__(256) k_fft_cols(const double2* __restrict__ A,
   int idx = 0;
   for (int y = 0; y < H; ++y) {
     const double2 a = col[(long)y * Wf];
-    const double2 w = tw[idx];
+    const double2 w = twp[idx];
     if (DIR < 0) {            // (a)(c - i s)
       re = fma(a.x, w.x, fma(a.y, w.y, re));
       im = fma(a.y, w.x, fma(-a.x, w.y, im));
@@ -234,6 +246,12 @@ __global__ void __launch_bounds__(128) k_fft_rows_inv(const double2* __restrict_
                                                       double scale, const float* __restrict__ band_scale,
                                                       float* __restrict__ raw9, int B, float* __restrict__ low_out) {
   __shared__ double2 sg[128];
+  __shared__ double2 stw[1024];
+  const bool tw_s = W <= 1024;
+  if (tw_s)
+    for (int t = threadIdx.x; t < W; t += blockDim.x) stw[t] = tw[t];
+  const double2* __restrict__ twp = tw_s ? stw : tw;
+  __syncthreads();
   const int xx = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, bc = blockIdx.z, b = bc / 3, c = bc % 3;
   const double2* row = G + ((long)bc * H + y) * Wf;
@@ -252,7 +270,7 @@ __global__ void __launch_bounds__(128) k_fft_rows_inv(const double2* __restrict_
         if (k == 0) {
           acc += g.x;
         } else if (k <= kmax) {
-          const double2 w = tw[idx];
+          const double2 w = twp[idx];
           acc += 2.0 * fma(g.x, w.x, -g.y * w.y);
         } else {   // Nyquist column (W even): cos(pi*x) = (-1)^x, imaginary part ignored
           acc += (xx & 1) ? -g.x : g.x;

@@ -6,16 +6,24 @@ in ``.train()`` mode (reference: ``src/models/enhanced_fusion_v2.py:681-799`` dr
 nodes whose forward AND backward are ``libffsr_b200.so`` kernels:
 
   conv2d        ffsr_conv2d (forward; input gradient = same kernel, rotated weights),
-                ffsr_conv2d_wgrad (+ bias column sums)
+                ffsr_conv2d_wgrad / ffsr_conv2d_wgrad_tc (+ bias column sums)
+  conv_chain    bf16 mode: conv -> act -> conv ... as ONE node on the tcgen05 kernels (activation in the forward
+                epilogue, act' in the input-gradient epilogue)
   act           ffsr_act_forward / ffsr_act_backward        (GELU / ReLU / sigmoid)
+  bilinear      ffsr_bilinear_forward / ffsr_bilinear_backward
+  gate_mul      ffsr_gate_mul_forward / ffsr_gate_mul_backward     (1-channel gate x C channels)
+  axpby         ffsr_axpby_forward / ffsr_axpby_backward           (x + s1*a (+ s2*b), learnable scalars)
+  blur_pool     ffsr_blur_pool / ffsr_blur_pool_backward           (Laplacian pyramid reduction)
+  fft_lowpass   ffsr_fft_lowpass / ffsr_fft_lowpass_backward       (learnable FFT mask, dense-DFT kernels)
   batchnorm     ffsr_bn_stats / ffsr_bn_apply / ffsr_bn_backward   (batch statistics per LKABlock call)
   layernorm     ffsr_layernorm / ffsr_layernorm_backward
   token_attn    ffsr_token_attention_train / ffsr_token_attention_backward  (dropout on the probabilities)
   dwconv        ffsr_dwconv_stage / ffsr_dwconv_wgrad       (LKA 5x5, 1x21, 21x1)
 
-PyTorch autograd is the plumbing between those nodes: tensor bookkeeping, concatenation,
-bilinear resampling and the few-channel elementwise blends are ordinary CUDA tensor ops
-(DESIGN.md section 8 lists them).  There is no CPU path: CPU tensors raise.
+PyTorch autograd is the plumbing between those nodes: tensor bookkeeping, concatenation, dtype
+casts and the 3/4-channel elementwise blends (softmax over experts, gate normalisation, image
+modulation) are ordinary CUDA tensor ops (DESIGN.md section 4b lists them with their time share).
+There is no CPU path: CPU tensors raise.
 
 Tensors are logical NCHW in channels-last memory ([N][H][W][C]), the layout every kernel of
 the library works in.
