@@ -20,9 +20,17 @@ import torch
 
 
 class PipelinedFusion:
-    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None):
+    """``cuda_graph=True`` (default): the forward of each input set is captured once into a CUDA graph (the device
+    buffers of a set are static, so are the engine's workspaces) and replayed; a change of weights, precision or
+    shapes re-captures.  The ~100 launches of a forward then cost one graph launch of host time and no inter-kernel
+    launch gaps, which matters once a 2040x1356 forward is down to ~16 ms."""
+
+    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None, cuda_graph: bool = True):
         self.model = model
         self.depth = depth
+        self.cuda_graph = cuda_graph
+        self._graphs = [None] * depth         # (key, CUDAGraph, static output)
+        self._out_free = [None] * depth       # event: the copy-out of this set's static output finished
         self.dev = device or next(model.parameters()).device
         self.s_in = torch.cuda.Stream(self.dev)
         self.s_out = torch.cuda.Stream(self.dev)
@@ -56,7 +64,7 @@ class PipelinedFusion:
             copied = torch.cuda.Event()
             copied.record(self.s_in)
         self.s_compute.wait_event(copied)
-        sr = self.model.forward_with_precomputed(d_lr, d_imgs, d_feats if feats else None)
+        sr, static = self._forward(i, d_lr, d_imgs, d_feats if feats else None)
         done = torch.cuda.Event()
         done.record(self.s_compute)
         self._free[i] = done
@@ -64,7 +72,45 @@ class PipelinedFusion:
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(done)
             out_host.copy_(sr, non_blocking=True)
-            sr.record_stream(self.s_out)
+            if static:
+                ev = torch.cuda.Event()
+                ev.record(self.s_out)
+                self._out_free[i] = ev
+            else:
+                sr.record_stream(self.s_out)
+
+    def _graph_key(self, d_lr, d_imgs, d_feats):
+        m = self.model
+        return (tuple(d_lr.shape), d_lr.dtype, tuple(sorted((k, v.dtype) for k, v in d_imgs.items())),
+                tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in (d_feats or {}).items())), m.precision, m.training,
+                tuple(p._version for p in m.parameters()), tuple(b._version for b in m.buffers()))
+
+    def _forward(self, i, d_lr, d_imgs, d_feats):
+        """-> (SR tensor, is_static_graph_output)"""
+        m = self.model
+        if not self.cuda_graph or m.training:
+            return m.forward_with_precomputed(d_lr, d_imgs, d_feats), False
+        key = self._graph_key(d_lr, d_imgs, d_feats)
+        entry = self._graphs[i]
+        if entry is not None and entry[0] == key:
+            if self._out_free[i] is not None:
+                self.s_compute.wait_event(self._out_free[i])     # the previous copy-out of this static output is done
+            entry[1].replay()
+            return entry[2], True
+        # first use of this set (or weights / shapes changed): one eager forward serves this submission and warms the
+        # engine up (workspaces, packed weights); then the same call is captured for the following submissions
+        sr = m.forward_with_precomputed(d_lr, d_imgs, d_feats)
+        eng = m._engine
+        prev = eng.overlap_routing
+        eng.overlap_routing = False                              # no stream switching inside a capture
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = m.forward_with_precomputed(d_lr, d_imgs, d_feats)
+            self._graphs[i] = (key, g, out)
+        finally:
+            eng.overlap_routing = prev
+        return sr, False
 
     def finish(self) -> None:
         self.s_in.synchronize()
