@@ -79,7 +79,12 @@ def sync_bn_buffers(model: torch.nn.Module) -> None:
 
 class FusedAdamW(torch.optim.Optimizer):
     """AdamW over a flat bucket with optional fused global-norm clipping, data-parallel gradient
-    all-reduce and EMA shadow update (one kernel pass: csrc/optim.cu)."""
+    all-reduce and EMA shadow update (one kernel pass: csrc/optim.cu).
+
+    One documented difference from ``torch.optim.AdamW``: a parameter that received no gradient in a step has a
+    zero gradient in the bucket (not ``None``), so it still gets weight decay and moment decay.  In the cached
+    training loop every parameter receives a gradient every step (198/198, scripts/test_cached_training.py:212-218);
+    the difference only shows when ``expert_feats`` is omitted and Phase 4 is skipped."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-4, max_grad_norm: float = 0.0, ema_decay: Optional[float] = None):
