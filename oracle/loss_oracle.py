@@ -140,3 +140,37 @@ def fft_branch_cut_slack(pred, target, high_freq_weight=2.0) -> float:
             neg = (P[..., ky, kx].real < 0) | (T[..., ky, kx].real < 0)
             slack += float(neg.sum()) * 0.1 * w * 2 * math.pi
     return slack / pred.numel()
+
+
+# ----------------------------------------------------------------------------------------------
+# validation metrics (src/utils/metrics.py) -- oracle for image-super-resolution_b200/metrics.py
+# ----------------------------------------------------------------------------------------------
+def metric_rgb_to_y(img):
+    """metrics.py:30-52."""
+    r, g, b = img[:, 0:1], img[:, 1:2], img[:, 2:3]
+    return (65.481 * r + 128.553 * g + 24.966 * b + 16.0) / 255.0
+
+
+def _metric_prep(a, b, crop_border, test_y_channel):
+    a, b = a.clamp(0, 1), b.clamp(0, 1)
+    if a.dim() == 3:
+        a, b = a[None], b[None]
+    if crop_border > 0:
+        a = a[:, :, crop_border:-crop_border, crop_border:-crop_border]
+        b = b[:, :, crop_border:-crop_border, crop_border:-crop_border]
+    if test_y_channel and a.shape[1] == 3:
+        a, b = metric_rgb_to_y(a), metric_rgb_to_y(b)
+    return a, b
+
+
+def metric_psnr(a, b, crop_border=0, test_y_channel=False) -> float:
+    """calculate_psnr, metrics.py:75-126."""
+    a, b = _metric_prep(a, b, crop_border, test_y_channel)
+    mse = float(((a - b) ** 2).mean())
+    return float("inf") if mse < 1e-10 else 10 * math.log10(1.0 / mse)
+
+
+def metric_ssim(a, b, crop_border=0, test_y_channel=False) -> float:
+    """calculate_ssim on its torch path (calculate_ssim_torch, metrics.py:128-186): the SSIM-loss map mean."""
+    a, b = _metric_prep(a, b, crop_border, test_y_channel)
+    return float(1 - ssim_loss(a, b))

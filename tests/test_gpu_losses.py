@@ -135,3 +135,22 @@ def test_full_size_properties():
         X = torch.fft.fft2(x, norm="ortho").abs().mean()
         v = float(FL.fused_losses(x, z, {"fft": 1.0})[0])
         assert float(X) <= v <= 2 * float(X) + 0.1 * 2 * np.pi * 2
+
+
+def test_device_metrics_against_oracle():
+    """metrics.psnr_ssim_per_image / calculate_* (device, no per-image sync) against the metric oracle."""
+    from isr_b200 import metrics as MT
+    dev = _cuda()
+    a, b = _pair(3, 3, 72, 88, seed=11, noise=0.04)
+    b[2] = a[2]                                            # one identical pair: PSNR inf, SSIM 1
+    p, s = MT.psnr_ssim_per_image(a.to(dev), b.to(dev), crop_border=4, test_y_channel=True)
+    for i in range(3):
+        wp = L.metric_psnr(a[i], b[i], 4, True)
+        ws = L.metric_ssim(a[i], b[i], 4, True)
+        assert (np.isinf(wp) and np.isinf(float(p[i]))) or abs(float(p[i]) - wp) < 2e-3, (i, float(p[i]), wp)
+        assert abs(float(s[i]) - ws) < 2e-5, (i, float(s[i]), ws)
+    assert abs(MT.calculate_psnr(a.to(dev), b.to(dev), 0, False) - L.metric_psnr(a, b, 0, False)) < 2e-3
+    assert abs(MT.calculate_ssim(a.to(dev), b.to(dev), 4, False) - L.metric_ssim(a, b, 4, False)) < 2e-5
+    ap, as_ = MT.calculate_psnr_ssim_batch(a.to(dev), b.to(dev))
+    want_p = np.mean([L.metric_psnr(a[i], b[i], 4, True) for i in range(2)])
+    assert abs(ap - want_p) < 2e-3 and abs(as_ - np.mean([L.metric_ssim(a[i], b[i], 4, True) for i in range(3)])) < 2e-5
