@@ -336,6 +336,74 @@ def run_train(args):
     _leave(world, r["trainer"])
 
 
+def run_tiled(args):
+    """`--workload c3t`: ONE C3 image across all ranks -- halo tiles, bands of the whole image on every
+    rank, cores assembled by one NCCL all-reduce.  Strong scaling: value = the image's HR pixels / max-over-ranks time."""
+    import torch
+    import torch.distributed as dist
+    import isr_b200
+    from isr_b200.serving import fuse_tiled, tile_grid, TILE_HALO_LR
+    from isr_b200.dist import max_over_ranks
+    from oracle import fusion_oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the fusion path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    H, W = args.lr
+    grid = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}.get(world, (1, world))
+    torch.manual_seed(0)
+    m = isr_b200.CompleteEnhancedFusionSR(None).eval().to(dev)
+    m.precision = args.precision
+    lr, imgs, fts, _ = O.synthetic_inputs(1, H, W, seed=1234)            # the SAME image on every rank (replicated inputs)
+    lrd, imd, ftd = lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        sr = fuse_tiled(m, lrd, imd, ftd, grid=grid, rank=rank, world=world)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sr = fuse_tiled(m, lrd, imd, ftd, grid=grid, rank=rank, world=world)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    clocks = sampler.stop()
+    launches_tile = m._engine.launches
+    whole = m.forward_with_precomputed(lrd, imd, ftd)
+    err = float((whole - sr).abs().max())
+    if rank == 0:
+        tiles = tile_grid(H, W, *grid)
+        y0, y1, x0, x1 = tiles[0]
+        hal = TILE_HALO_LR
+        win = (min(H, y1 + hal) - max(0, y0 - hal)) * (min(W, x1 + hal) - max(0, x0 - hal))
+        print(json.dumps({
+            "metric": "fusion_forward_hr_mpix_per_s", "value": 16 * H * W / 1e6 * args.steps / (ms * 1e-3), "unit": "HR MPix/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "C3 fusion forward, ONE 2040x1356 image split over all ranks (latency mode)",
+                       "lr": [H, W], "grid": list(grid), "halo_lr_px": hal, "window_over_core": win * len(tiles) / (H * W),
+                       "partition": "halo tiles; phase-2 bands recomputed on the whole LR image by every rank; cores "
+                                    "assembled by one all-reduce(sum) of the fp32 output" if world > 1 else "single tile",
+                       "precision": args.precision},
+            "max_abs_vs_whole_image": err, "gpu_launches": (launches_tile + 7) * args.steps, "clocks": clocks}), flush=True)
+    if world > 1:
+        _leave(world)
+
+
 def train_config(workload, patches, B, hw, precision):
     return {"workload": f"{workload.upper()} fusion training step (BASELINE configs[{1 if workload == 'c2' else 3}]): "
                         f"global batch {patches} x {hw}x{hw} LR patches, losses {STAGE_WEIGHTS[workload]}, "
@@ -347,7 +415,7 @@ def train_config(workload, patches, B, hw, precision):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c3t"],
                     help="c3: full-res inference (headline, default); c2 / c4: training steps (BASELINE configs[1] / [3])")
     ap.add_argument("--batch", type=int, default=0, help="override the global batch of a training workload")
     ap.add_argument("--gpus", type=int, default=1)
@@ -361,6 +429,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c3t":
+        return run_tiled(args)
     if args.workload != "c3":
         return run_train(args)
 

@@ -326,7 +326,9 @@ class FusionEngine:
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, lr: torch.Tensor, img_list: List[torch.Tensor], feats: Dict[str, torch.Tensor],
-                Hh: int, Wh: int, want_inter: bool):
+                Hh: int, Wh: int, want_inter: bool, bands: Optional[torch.Tensor] = None):
+        """``bands``: phase-2 output [B,9,3,H,W] computed elsewhere (tiled inference crops it from the bands of
+        the WHOLE image, because the FFT / DWT bands of a window are not the window of the bands)."""
         m, lib = self.m, self.lib
         if not lr.is_cuda:
             raise RuntimeError("CompleteEnhancedFusionSR (sm_100a build) needs CUDA tensors: there is no CPU path")
@@ -346,12 +348,54 @@ class FusionEngine:
         with torch.cuda.device(dev):
             entry_stream = torch.cuda.current_stream(dev)
             try:
-                return self._forward(lr, img_list, feats, B, H, W, want_inter)
+                return self._forward(lr, img_list, feats, B, H, W, want_inter, bands)
             finally:
                 if torch.cuda.current_stream(dev) != entry_stream:      # an error inside the side-stream section
                     torch.cuda.set_stream(entry_stream)
 
-    def _forward(self, lr, img_list, feats, B, H, W, want_inter):
+    @torch.no_grad()
+    def frequency_bands(self, lr: torch.Tensor) -> torch.Tensor:
+        """Phase 2 alone: the nine raw bands [B,9,3,H,W] (dct low/mid/high, dwt LL/LH/HL/HH, fft low/high) of ``lr``."""
+        if not lr.is_cuda:
+            raise RuntimeError("CompleteEnhancedFusionSR (sm_100a build) needs CUDA tensors: there is no CPU path")
+        B, Cc, H, W = lr.shape
+        if Cc != 3 or H < 8 or W < 8:
+            raise ValueError("lr_input must be [B,3,H,W] with H,W >= 8 (7-px reflect pad of the db4 DWT)")
+        dev = lr.device
+        with torch.cuda.device(dev):
+            self._stream = self._get_stream(dev)
+            self._prepare(dev)
+            self.launches = 0
+            return self._phase2(lr.detach().to(torch.float32).contiguous(), B, H, W, True)
+
+    def _phase2(self, lr, B, H, W, fresh):
+        m, lib, P, S, dev = self.m, self.lib, self._P, self._stream, lr.device
+
+        def pp(name):
+            return P[name].data_ptr()
+
+        fd = m.freq_decomp
+        raw9 = self._buf("raw9", (B, 9, 3, H, W), dev, fresh=fresh)
+        self._call(lib.ffsr_dct_bands, lr.data_ptr(), B, H, W, pp("freq_decomp.dct.dct_basis"), pp("freq_decomp.dct.dct_basis_t"),
+                   pp("freq_decomp.dct.low_mask"), pp("freq_decomp.dct.mid_mask"), pp("freq_decomp.dct.high_mask"),
+                   pp("freq_decomp.dct.band_scale"), raw9.data_ptr(), S)
+        hs, ws_ = C.c_int(), C.c_int()
+        lib.ffsr_dwt_sub_size(H, W, C.byref(hs), C.byref(ws_))
+        sub = self._buf("dwt.sub", (B, 4, 3, hs.value, ws_.value), dev)
+        self._call(lib.ffsr_dwt_bands, lr.data_ptr(), B, H, W, pp("freq_decomp.dwt.lo_row"), pp("freq_decomp.dwt.hi_row"),
+                   pp("freq_decomp.dwt.lo_col"), pp("freq_decomp.dwt.hi_col"), pp("freq_decomp.dwt.subband_scale"),
+                   sub.data_ptr(), raw9.data_ptr(), S)
+        self.launches += 1
+        fft_bytes = lib.ffsr_fft_workspace_bytes(B, H, W)
+        fws = self._buf("fft.ws", (fft_bytes // 8 + 2,), dev, dtype=torch.float64)
+        ms = fd.fft.freq_mask_logits.shape[-1]
+        self._call(lib.ffsr_fft_bands, lr.data_ptr(), B, H, W, pp("freq_decomp.fft.freq_mask_logits"), ms,
+                   pp("freq_decomp.fft.temperature"), pp("freq_decomp.fft.band_scale"), self._twiddles(H, dev).data_ptr(),
+                   self._twiddles(W, dev).data_ptr(), fws.data_ptr(), fft_bytes, raw9.data_ptr(), S)
+        self.launches += 4
+        return raw9
+
+    def _forward(self, lr, img_list, feats, B, H, W, want_inter, bands=None):
         m, lib, w = self.m, self.lib, None
         dev = lr.device
         self._stream = self._get_stream(dev)
@@ -377,25 +421,12 @@ class FusionEngine:
         fr = want_inter                                   # intermediates are handed out: use fresh buffers
 
         # ---------------- Phase 2 ----------------
-        fd = m.freq_decomp
-        raw9 = self._buf("raw9", (B, 9, 3, H, W), dev, fresh=fr)
-        self._call(lib.ffsr_dct_bands, lr.data_ptr(), B, H, W, pp("freq_decomp.dct.dct_basis"), pp("freq_decomp.dct.dct_basis_t"),
-                   pp("freq_decomp.dct.low_mask"), pp("freq_decomp.dct.mid_mask"), pp("freq_decomp.dct.high_mask"),
-                   pp("freq_decomp.dct.band_scale"), raw9.data_ptr(), S)
-        hs, ws_ = C.c_int(), C.c_int()
-        lib.ffsr_dwt_sub_size(H, W, C.byref(hs), C.byref(ws_))
-        sub = self._buf("dwt.sub", (B, 4, 3, hs.value, ws_.value), dev)
-        self._call(lib.ffsr_dwt_bands, lr.data_ptr(), B, H, W, pp("freq_decomp.dwt.lo_row"), pp("freq_decomp.dwt.hi_row"),
-                   pp("freq_decomp.dwt.lo_col"), pp("freq_decomp.dwt.hi_col"), pp("freq_decomp.dwt.subband_scale"),
-                   sub.data_ptr(), raw9.data_ptr(), S)
-        self.launches += 1
-        fft_bytes = lib.ffsr_fft_workspace_bytes(B, H, W)
-        fws = self._buf("fft.ws", (fft_bytes // 8 + 2,), dev, dtype=torch.float64)
-        ms = fd.fft.freq_mask_logits.shape[-1]
-        self._call(lib.ffsr_fft_bands, lr.data_ptr(), B, H, W, pp("freq_decomp.fft.freq_mask_logits"), ms,
-                   pp("freq_decomp.fft.temperature"), pp("freq_decomp.fft.band_scale"), self._twiddles(H, dev).data_ptr(),
-                   self._twiddles(W, dev).data_ptr(), fws.data_ptr(), fft_bytes, raw9.data_ptr(), S)
-        self.launches += 4
+        if bands is None:
+            raw9 = self._phase2(lr, B, H, W, fr)
+        else:
+            if tuple(bands.shape) != (B, 9, 3, H, W) or bands.dtype != f32 or bands.device != dev:
+                raise ValueError(f"bands must be fp32 [B,9,3,H,W] = {(B, 9, 3, H, W)} on {dev}, got {tuple(bands.shape)}")
+            raw9 = bands.contiguous()
 
         # Phases 3 + 6 (the fp32 LR routing chain: FFMA-bound kernels) only meet the rest of the network at the
         # blend, while phase 4 / the HR modulation / phase 5 depend on the expert features and images alone: run

@@ -158,3 +158,65 @@ def fuse_tta(model, variants) -> torch.Tensor:
     if total is None:
         raise ValueError("fuse_tta: no variants")
     return (total / count).clamp_(0, 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# One image across GPUs: halo tiles, bands of the whole image, no halo exchange
+# ---------------------------------------------------------------------------------------------------
+TILE_HALO_LR = 40       # LR px.  Receptive field of phases 3-7 behind the bands: LKA 12 + selector 3 + bilinear 1 LR px,
+                        # then refine 6 + Laplacian pyramid / edge nets <= 46 HR px  =>  <= 110 HR px < 4 * 40
+                        # (measured on the reference: a feature/image perturbation reaches 94 HR px).
+
+
+def tile_grid(H: int, W: int, ty: int, tx: int):
+    """Split an H x W LR image into ty x tx core rectangles (y0, y1, x0, x1); inner boundaries are multiples of 8 LR px
+    (the DCT block grid; also keeps every HR / half / quarter resolution boundary aligned)."""
+    def cuts(n, k):
+        c = [0] + [min(n, max(8, int(round(n * i / k / 8.0)) * 8)) for i in range(1, k)] + [n]
+        if any(b <= a for a, b in zip(c, c[1:])):
+            raise ValueError(f"cannot cut {n} LR px into {k} tiles on the 8-px grid")
+        return c
+    ys, xs = cuts(H, ty), cuts(W, tx)
+    return [(ys[i], ys[i + 1], xs[j], xs[j + 1]) for i in range(ty) for j in range(tx)]
+
+
+@torch.no_grad()
+def fuse_tiled(model, lr: torch.Tensor, expert_imgs: Dict[str, torch.Tensor],
+               expert_feats: Optional[Dict[str, torch.Tensor]] = None, grid=(1, 2), halo: int = TILE_HALO_LR,
+               rank: int = 0, world: int = 1, assemble: bool = True) -> torch.Tensor:
+    """``forward_with_precomputed`` of ONE (batch of) image(s) computed tile by tile; rank r takes tiles r, r+world, ...
+
+    Everything behind phase 2 has a finite receptive field, so a tile is the model applied to a window = core + halo
+    (clipped at the image border, where the zero / clamp boundary rules then apply exactly as in the whole image).  The
+    nine frequency bands are NOT local (global FFT mask; DWT resize ratio depends on H, W): every rank computes them on
+    the whole 3-channel LR image (31 FLOP per HR pixel) and crops.  Halos are re-read from the inputs, never exchanged.
+    With ``assemble`` (and world > 1) the cores are summed into the full image with one all-reduce (x + 0 is exact);
+    without it the full-size tensor holds this rank's cores and zeros elsewhere."""
+    eng_model = model
+    if eng_model.training:
+        raise RuntimeError("fuse_tiled is an inference path: call model.eval() first")
+    from .fusion import EXPERT_ORDER
+    from .pipeline import FusionEngine
+    if eng_model._engine is None:
+        eng_model._engine = FusionEngine(eng_model)
+    eng = eng_model._engine
+    B, _, H, W = lr.shape
+    tiles = tile_grid(H, W, int(grid[0]), int(grid[1]))
+    imgs = [expert_imgs[k] for k in EXPERT_ORDER if k in expert_imgs]
+    feats = {k: expert_feats[k] for k in EXPERT_ORDER if k in expert_feats} if expert_feats is not None else {}
+    bands = eng.frequency_bands(lr)
+    out = torch.zeros(B, 3, 4 * H, 4 * W, device=lr.device, dtype=torch.float32)
+    for t in range(rank, len(tiles), world):
+        y0, y1, x0, x1 = tiles[t]
+        wy0, wy1, wx0, wx1 = max(0, y0 - halo), min(H, y1 + halo), max(0, x0 - halo), min(W, x1 + halo)
+        sr, _ = eng.forward(lr[:, :, wy0:wy1, wx0:wx1],
+                            [im[:, :, 4 * wy0:4 * wy1, 4 * wx0:4 * wx1] for im in imgs],
+                            {k: f[:, :, wy0:wy1, wx0:wx1] for k, f in feats.items()},
+                            4 * (wy1 - wy0), 4 * (wx1 - wx0), False,
+                            bands=bands[:, :, :, wy0:wy1, wx0:wx1].contiguous())
+        oy, ox = 4 * (y0 - wy0), 4 * (x0 - wx0)
+        out[:, :, 4 * y0:4 * y1, 4 * x0:4 * x1] = sr[:, :, oy:oy + 4 * (y1 - y0), ox:ox + 4 * (x1 - x0)]
+    if assemble and world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(out)
+    return out

@@ -459,3 +459,36 @@ def test_tta_fusion_matches_per_variant_loop():
     got = fuse_tta(m, variants)
     assert tuple(got.shape) == (1, 3, 64, 96)
     assert (got.squeeze(0).cpu() - want).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 4e-3)])
+def test_tiled_single_image_matches_whole_image(precision, tol):
+    """one image as halo tiles (bands of the whole image, no halo exchange) = the whole-image forward.
+    Ranks are simulated one after the other on one device (rank r of 2 / of 4 fills its cores, zeros elsewhere; the sum
+    is what the all-reduce assembles).  LR size is deliberately not a multiple of 8 and larger than 2 halos."""
+    from isr_b200.serving import fuse_tiled, tile_grid, TILE_HALO_LR
+    dev = _cuda()
+    m = _model(True).to(dev)
+    m.precision = precision
+    H, W = 139, 203
+    lr, imgs, fts, _ = O.synthetic_inputs(1, H, W)
+    lr, imgs, fts = lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()}
+    whole = m.forward_with_precomputed(lr, imgs, fts)
+    for grid, world in (((1, 2), 2), ((2, 2), 4), ((2, 3), 1)):
+        parts = [fuse_tiled(m, lr, imgs, fts, grid=grid, rank=r, world=world, assemble=False) for r in range(world)]
+        # cores are disjoint: every pixel is written by exactly one rank
+        nz = sum((p != 0).float() for p in parts)
+        assert float(nz.max()) <= 1.0
+        got = sum(parts)
+        err = float((got - whole).abs().max())
+        assert err <= tol, (precision, grid, err)
+    # the halo is what makes it exact: without one the seams show
+    if precision == "fp32":
+        bad = fuse_tiled(m, lr, imgs, fts, grid=(2, 2), halo=0)
+        assert float((bad - whole).abs().max()) > 1e-3
+    # cuts sit on the 8-px grid and cover the image once
+    t = tile_grid(H, W, 2, 3)
+    assert sum((y1 - y0) * (x1 - x0) for y0, y1, x0, x1 in t) == H * W
+    assert all(y0 % 8 == 0 and x0 % 8 == 0 for y0, _, x0, _ in t) and TILE_HALO_LR % 8 == 0
+    with pytest.raises(ValueError):
+        tile_grid(16, 16, 4, 1)
