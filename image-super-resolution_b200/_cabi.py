@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libffsr_b200.so")
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 EPI_PLAIN, EPI_RESIDUAL, EPI_LKAGATE, EPI_ACTGRAD = 0, 1, 2, 3
-DT_F32, DT_BF16 = 0, 1
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 
 
 class FusionLibraryError(RuntimeError):
@@ -51,6 +51,14 @@ class WgradParams(C.Structure):
         ("dy_dtype", C.c_int),
         ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int), ("ksize", C.c_int),
         ("dw", C.c_void_p), ("dbias", C.c_void_p),
+    ]
+
+
+class CacheSegment(C.Structure):
+    _fields_ = [
+        ("src_offset", C.c_ulonglong), ("dst", C.c_void_p),
+        ("C", C.c_int), ("h", C.c_int), ("w", C.c_int),
+        ("src_dtype", C.c_int), ("dst_dtype", C.c_int), ("reserved", C.c_int),
     ]
 
 
@@ -124,6 +132,9 @@ PROTOTYPES = {
     "ffsr_fft_lowpass_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ffsr_fft_lowpass": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _SZ, _P, _P]),
     "ffsr_fft_lowpass_backward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _SZ, _P, _P]),
+    # ---- cache-shard collate ----
+    "ffsr_cache_unpack": (_I, [_P, _SZ, _I, _P, _I, _P, _I, _P]),
+    "ffsr_cache_segment_size": (_I, []),
     # ---- fused optimizer ----
     "ffsr_sumsq": (_I, [_P, _L, _P, _P]),
     "ffsr_adamw_ema_step": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _P, _P, _F, _F, _F, _P]),
@@ -150,6 +161,8 @@ def load():
         raise FusionLibraryError("ffsr_conv_params layout mismatch between _cabi.py and the built library; rebuild")
     if lib.ffsr_wgrad_params_size() != C.sizeof(WgradParams):
         raise FusionLibraryError("ffsr_wgrad_params layout mismatch between _cabi.py and the built library; rebuild")
+    if lib.ffsr_cache_segment_size() != C.sizeof(CacheSegment):
+        raise FusionLibraryError("ffsr_cache_segment layout mismatch between _cabi.py and the built library; rebuild")
     _lib = lib
     return lib
 

@@ -1,0 +1,529 @@
+"""Flat cache shards and the device-side batch loader.
+
+The reference stores one training sample as three ``torch.save`` pickles (``{stem}_{drct,rest,mamba}_part.pt``) and
+reads them with ``torch.load(weights_only=False)`` in DataLoader workers, up-casting and flipping on the CPU
+(``src/data/cached_dataset.py:135-282``).  One 64x64 sample is 13.9 MB of fp32, so a B200 that trains hundreds of
+patches per second needs several GB/s of unpickling -- the loader, not the GPU, sets the pace.  Here:
+
+* ``pack_cache`` converts a reference cache directory once into ONE flat file: a JSON header and fixed-layout raw
+  records (every tensor dense ``[C][h][w]``, 16-byte aligned), readable through ``mmap`` with no parsing.
+  ``dtype="source"`` keeps the stored dtypes (fp32, fp16 for the MambaIR part) and is bit-exact with the reference
+  loader; ``dtype="fp16"`` stores expert images / features as fp16 (what the reference's own val / TTA caches do).
+* ``ShardDataset`` has ``CachedSRDataset``'s constructor and ``__getitem__`` contract on top of a shard (host tensors,
+  same ``random`` draws for the augmentation) -- the drop-in for unchanged callers.
+* ``DeviceBatchLoader`` is the B200 path: B records are gathered into a pinned staging buffer, cross PCIe in ONE copy
+  on a side stream, and ONE kernel (``ffsr_cache_unpack``) up-casts, applies each sample's flip / rot90 and writes the
+  dense batch tensors; the next batch is in flight while the current one trains.
+
+No pickles of our own are ever written.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import mmap
+import os
+import queue
+import random
+import struct
+import threading
+from pathlib import Path
+from typing import Dict, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+EXPERT_ORDER = ("drct", "grl", "nafnet", "mamba")
+MAGIC = b"FFSRC1\x00\x00"
+_ALIGN_SEG, _ALIGN_REC, _ALIGN_DATA = 16, 512, 4096
+_NP = {"f32": np.float32, "f16": np.float16}
+_TORCH = {"f32": torch.float32, "f16": torch.float16}
+
+
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+def _dihedral_table() -> Dict[Tuple[bool, bool, int], int]:
+    """Brute force over a non-square index tensor: for each (hflip, vflip, rot_k) the code whose gather reproduces the
+    torch ops (built once at import: 16 tiny tensor ops)."""
+    h, w = 2, 3
+    src = torch.arange(h * w).view(h, w)
+    table = {}
+    for hf in (False, True):
+        for vf in (False, True):
+            for k in range(4):
+                t = src
+                if hf:
+                    t = torch.flip(t, dims=[-1])
+                if vf:
+                    t = torch.flip(t, dims=[-2])
+                if k:
+                    t = torch.rot90(t, k=k, dims=[-2, -1])
+                hit = None
+                for code in range(8):
+                    tr, fy, fx = code & 1, code & 2, code & 4
+                    ho, wo = (w, h) if tr else (h, w)
+                    if tuple(t.shape) != (ho, wo):
+                        continue
+                    ok = True
+                    for y in range(ho):
+                        for x in range(wo):
+                            sy, sx = (x, y) if tr else (y, x)
+                            if fy:
+                                sy = h - 1 - sy
+                            if fx:
+                                sx = w - 1 - sx
+                            ok = ok and int(t[y, x]) == int(src[sy, sx])
+                    if ok:
+                        hit = code
+                        break
+                assert hit is not None
+                table[(hf, vf, k)] = hit
+    return table
+
+
+_DIHEDRAL = _dihedral_table()
+
+
+def dihedral_code(hflip: bool, vflip: bool, rot_k: int) -> int:
+    """The loader's ``hflip -> vflip -> rot90(k)`` (cached_dataset.py:266-274) as one of the 8 dihedral maps of
+    ``ffsr_cache_unpack``: bit 0 transpose, bit 1 reverse source rows, bit 2 reverse source columns, i.e.
+    ``out[y][x] = in[sy][sx]`` with ``(sy, sx) = (x, y) if transpose else (y, x)``, then ``sy = h-1-sy`` / ``sx = w-1-sx``."""
+    return _DIHEDRAL[(bool(hflip), bool(vflip), int(rot_k) % 4)]
+
+
+# ---------------------------------------------------------------------------------------------------
+# record layout
+# ---------------------------------------------------------------------------------------------------
+def _layout(tensors: Sequence[dict], h: int, w: int, scale: int):
+    """[(key, C, hh, ww, dtype, offset)], record_bytes for an LR size (h, w)."""
+    segs, off = [], 0
+    for t in tensors:
+        s = scale if t["hr"] else 1
+        hh, ww = h * s, w * s
+        nbytes = t["C"] * hh * ww * (2 if t["dtype"] == "f16" else 4)
+        segs.append((t["key"], t["C"], hh, ww, t["dtype"], off))
+        off = _round_up(off + nbytes, _ALIGN_SEG)
+    return segs, _round_up(off, _ALIGN_REC)
+
+
+def _read_parts(d: Path, stem: str):
+    """The three pickles of one sample in their STORED dtypes (no up-cast), batch dim squeezed
+    (cached_dataset.py:150-214); a missing mamba part is ``None`` (zero-filled by the caller, as :178-185 does)."""
+    a = torch.load(d / f"{stem}_drct_part.pt", weights_only=False)
+    b = torch.load(d / f"{stem}_rest_part.pt", weights_only=False)
+    mp = d / f"{stem}_mamba_part.pt"
+    c = torch.load(mp, weights_only=False) if mp.exists() else None
+    imgs, feats = dict(a["outputs"]), dict(a.get("features") or {})
+    imgs.update(b["outputs"])
+    feats.update(b.get("features") or {})
+    if c is not None:
+        imgs.update(c["outputs"])
+        feats.update(c.get("features") or {})
+    sq = lambda t: t.squeeze(0) if t.dim() == 4 else t                      # noqa: E731
+    imgs = {k: sq(v) for k, v in imgs.items() if v is not None}
+    feats = {k: sq(v) for k, v in feats.items() if v is not None}
+    meta = {k: a[k] for k in ("original_stem", "original_size", "tta_info") if k in a}
+    return a["lr"], a.get("hr"), imgs, feats, c is not None, meta
+
+
+def pack_cache(feature_dir: str, out_path: str, dtype: str = "source", load_features: bool = True) -> dict:
+    """Convert a reference cache directory (``*_drct_part.pt`` + ``*_rest_part.pt`` [+ ``*_mamba_part.pt``]) into one
+    flat shard.  Stems follow the reference's rule (cached_dataset.py:84-109: sorted, incomplete pairs dropped).
+    Returns the header."""
+    if dtype not in ("source", "fp16"):
+        raise ValueError("dtype must be 'source' (bit-exact with the reference loader) or 'fp16'")
+    d = Path(feature_dir)
+    if not d.exists():
+        raise RuntimeError(f"Feature cache directory not found: {feature_dir}")
+    stems = [f.name.replace("_drct_part.pt", "") for f in sorted(d.glob("*_drct_part.pt"))]
+    if not stems:
+        raise RuntimeError(f"No cached features found in {feature_dir}!")
+    stems = [s for s in stems if (d / f"{s}_rest_part.pt").exists()]
+
+    def sdt(t: torch.Tensor, lossy: bool) -> str:
+        if t.dtype not in (torch.float32, torch.float16):
+            raise ValueError(f"unsupported cache dtype {t.dtype}")
+        return "f16" if (t.dtype == torch.float16 or (lossy and dtype == "fp16")) else "f32"
+
+    tensors: Optional[List[dict]] = None
+    hw, offsets, has_mamba, metas = [], [], [], []
+    scale = 4
+    tmp = str(out_path) + ".records.tmp"
+    pos = 0
+    with open(tmp, "wb") as rec:
+        for stem in stems:
+            lr, hr, imgs, feats, hm, meta = _read_parts(d, stem)
+            h, w = int(lr.shape[-2]), int(lr.shape[-1])
+            if tensors is None:                       # the first sample with a mamba part fixes the tensor table
+                ref_img = next(iter(imgs.values()))
+                scale = int(ref_img.shape[-1]) // w
+                tensors = [{"key": "lr", "C": int(lr.shape[0]), "hr": False, "dtype": sdt(lr, False)}]
+                if hr is not None:
+                    tensors.append({"key": "hr", "C": int(hr.shape[0]), "hr": True, "dtype": sdt(hr, False)})
+                for n in EXPERT_ORDER:
+                    if n in imgs or n == "mamba":
+                        dt = sdt(imgs[n], True) if n in imgs else "f16"
+                        tensors.append({"key": "img." + n, "C": 3, "hr": True, "dtype": dt})
+                if load_features:
+                    for n in EXPERT_ORDER:
+                        if n in feats or n == "mamba":
+                            dt = sdt(feats[n], True) if n in feats else "f16"
+                            tensors.append({"key": "feat." + n, "C": int(feats[n].shape[0]) if n in feats else 180,
+                                            "hr": False, "dtype": dt})
+            segs, rbytes = _layout(tensors, h, w, scale)
+            buf = np.zeros(rbytes, dtype=np.uint8)
+            src = {"lr": lr, "hr": hr}
+            src.update({"img." + k: v for k, v in imgs.items()})
+            src.update({"feat." + k: v for k, v in feats.items()})
+            for key, Cc, hh, ww, dt, off in segs:
+                t = src.get(key)
+                if t is None:
+                    if key.endswith(".mamba"):
+                        continue                      # zeros: the reference's fallback for a missing MambaIR part
+                    raise ValueError(f"sample '{stem}' has no tensor '{key}' (the first sample defines the tensor set)")
+                if tuple(t.shape) != (Cc, hh, ww):
+                    raise ValueError(f"sample '{stem}': '{key}' is {tuple(t.shape)}, expected {(Cc, hh, ww)}")
+                arr = t.detach().contiguous().numpy().astype(_NP[dt], copy=False)
+                buf[off:off + arr.nbytes] = arr.reshape(-1).view(np.uint8)
+            rec.write(buf.tobytes())
+            hw.append([h, w])
+            offsets.append(pos)
+            pos += rbytes
+            has_mamba.append(bool(hm))
+            metas.append(meta)
+    header = {"version": 1, "count": len(stems), "scale": scale, "dtype_mode": dtype, "tensors": tensors or [],
+              "hw": hw, "offsets": offsets, "stems": stems, "has_mamba": has_mamba, "load_features": bool(load_features),
+              "uniform": len({tuple(x) for x in hw}) <= 1}
+    if any(metas):
+        header["meta"] = [json.loads(json.dumps(m, default=lambda o: list(o) if isinstance(o, tuple) else str(o))) for m in metas]
+    hj = json.dumps(header).encode("utf-8")
+    data_start = _round_up(len(MAGIC) + 8 + len(hj), _ALIGN_DATA)
+    with open(out_path, "wb") as f:
+        f.write(MAGIC)
+        f.write(struct.pack("<Q", len(hj)))
+        f.write(hj)
+        f.write(b"\x00" * (data_start - f.tell()))
+        with open(tmp, "rb") as rec:
+            while True:
+                chunk = rec.read(64 << 20)
+                if not chunk:
+                    break
+                f.write(chunk)
+    os.remove(tmp)
+    return header
+
+
+class ShardCache:
+    """Read-only view of a shard: header + memory-mapped records."""
+
+    def __init__(self, path: str):
+        self.path = str(path)
+        with open(self.path, "rb") as f:
+            if f.read(len(MAGIC)) != MAGIC:
+                raise ValueError(f"{path} is not an FFSRC1 cache shard")
+            (n,) = struct.unpack("<Q", f.read(8))
+            self.header = json.loads(f.read(n).decode("utf-8"))
+        if self.header.get("version") != 1:
+            raise ValueError(f"unsupported shard version {self.header.get('version')}")
+        self.data_start = _round_up(len(MAGIC) + 8 + n, _ALIGN_DATA)
+        self._file = open(self.path, "rb")
+        self._mm = mmap.mmap(self._file.fileno(), 0, access=mmap.ACCESS_READ)
+        self._bytes = np.frombuffer(self._mm, dtype=np.uint8)
+        self.count = int(self.header["count"])
+        self.stems: List[str] = self.header["stems"]
+        self.scale = int(self.header["scale"])
+        self.tensors = self.header["tensors"]
+        self.uniform = bool(self.header["uniform"])
+        self._layouts: Dict[Tuple[int, int], tuple] = {}
+
+    def layout(self, i: int):
+        h, w = self.header["hw"][i]
+        lay = self._layouts.get((h, w))
+        if lay is None:
+            lay = self._layouts[(h, w)] = _layout(self.tensors, h, w, self.scale)
+        return lay
+
+    def record(self, i: int) -> np.ndarray:
+        """The raw bytes of record i (a view into the mapping)."""
+        _, rbytes = self.layout(i)
+        o = self.data_start + self.header["offsets"][i]
+        return self._bytes[o:o + rbytes]
+
+    def sample(self, i: int, load_features: bool = True) -> dict:
+        """Record i as host tensors in their stored dtypes (copies; the mapping is read-only)."""
+        segs, _ = self.layout(i)
+        rec = self.record(i)
+        out = {"lr": None, "hr": None, "expert_imgs": {}, "expert_feats": {} if load_features else None,
+               "filename": self.stems[i]}
+        for key, Cc, hh, ww, dt, off in segs:
+            if key.startswith("feat.") and not load_features:
+                continue
+            n = Cc * hh * ww * (2 if dt == "f16" else 4)
+            t = torch.from_numpy(rec[off:off + n].view(_NP[dt]).reshape(Cc, hh, ww).copy())
+            if key in ("lr", "hr"):
+                out[key] = t
+            elif key.startswith("img."):
+                out["expert_imgs"][key[4:]] = t
+            else:
+                out["expert_feats"][key[5:]] = t
+        return out
+
+    def close(self):
+        self._bytes = None
+        try:
+            self._mm.close()
+        except BufferError:            # views handed out are still alive; the mapping goes with them
+            pass
+        self._file.close()
+
+
+class ShardDataset(torch.utils.data.Dataset):
+    """``CachedSRDataset`` (cached_dataset.py:50-232) over a shard: same arguments, same sample dict, same ``random``
+    draws.  With a ``dtype="source"`` shard every tensor is bit-identical to what the reference class returns."""
+
+    def __init__(self, feature_dir: str, augment: bool = True, repeat_factor: int = 1, load_features: bool = True):
+        super().__init__()
+        p = Path(feature_dir)
+        if not p.exists():
+            raise RuntimeError(f"Feature cache shard not found: {feature_dir}")
+        self.cache = ShardCache(str(p))
+        self.file_stems = self.cache.stems
+        self.has_mamba = dict(zip(self.cache.stems, self.cache.header["has_mamba"]))
+        self.augment, self.repeat_factor = augment, repeat_factor
+        self.load_features = load_features and self.cache.header["load_features"]
+        self._upcast_all = self.cache.header["dtype_mode"] == "fp16"
+
+    def __len__(self) -> int:
+        return self.cache.count * self.repeat_factor
+
+    def __getitem__(self, idx: int) -> dict:
+        s = self.cache.sample(idx % self.cache.count, self.load_features)
+        up = (lambda k, t: t.float()) if self._upcast_all else (lambda k, t: t.float() if k == "mamba" else t)
+        lr, hr = s["lr"], s["hr"]
+        imgs = {k: up(k, v) for k, v in s["expert_imgs"].items()}
+        feats = {k: up(k, v) for k, v in s["expert_feats"].items()} if s["expert_feats"] is not None else None
+        if self.augment:
+            hflip = random.random() < 0.5                    # the reference's three draws, in its order (:262-264)
+            vflip = random.random() < 0.5
+            rot_k = random.randint(0, 3)
+
+            def tf(t):
+                if hflip:
+                    t = torch.flip(t, dims=[-1])
+                if vflip:
+                    t = torch.flip(t, dims=[-2])
+                return torch.rot90(t, k=rot_k, dims=[-2, -1]) if rot_k > 0 else t
+            lr, hr = tf(lr), (tf(hr) if hr is not None else None)
+            imgs = {k: tf(v) for k, v in imgs.items()}
+            feats = {k: tf(v) for k, v in feats.items()} if feats is not None else None
+        out = {"lr": lr, "hr": hr, "expert_imgs": imgs, "filename": s["filename"]}
+        if hr is None:
+            del out["hr"]
+        if feats is not None:
+            out["expert_feats"] = feats
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# device loader
+# ---------------------------------------------------------------------------------------------------
+class DeviceBatchLoader:
+    """Batches of a shard as DEVICE tensors, shaped like the reference DataLoader's collated dict
+    (``lr [B,3,h,w]``, ``hr``, ``expert_imgs{name}``, ``expert_feats{name}``, ``filename`` list; train.py:300-322).
+
+    Per batch: B records -> pinned staging (a few host threads; plain memcpy out of the page cache), one async H2D on a
+    copy stream, one ``ffsr_cache_unpack`` launch (up-cast + per-sample flip/rot90 + collate).  ``depth`` batches are
+    in flight; the consumer's stream waits on the batch's event, never the host.
+
+    ``rng``: a ``random.Random`` (default seeded from ``seed``) from which the augmentation of every sample is drawn in
+    the reference's order, so a run seeded like ``random.seed(s)`` reproduces the reference's augmentations.
+    Under ``world > 1`` rank r takes every world-th index of the (shared-seed) epoch permutation."""
+
+    def __init__(self, shard: str, batch_size: int, device, augment: bool = True, shuffle: bool = True,
+                 drop_last: bool = True, load_features: bool = True, repeat_factor: int = 1, rank: int = 0, world: int = 1,
+                 seed: int = 0, depth: int = 2, copy_threads: int = 4, rng: Optional[random.Random] = None,
+                 out_dtype: torch.dtype = torch.float32):
+        from . import _cabi as K
+        self.K = K
+        self.lib = K.load()                                   # raises FusionLibraryError when the library is missing
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DeviceBatchLoader needs a CUDA device: there is no CPU path (use ShardDataset on the host)")
+        self.cache = shard if isinstance(shard, ShardCache) else ShardCache(shard)
+        if batch_size > 1 and not self.cache.uniform:
+            raise ValueError("batch_size > 1 needs a shard whose samples all have the same LR size")
+        if out_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("out_dtype must be torch.float32 or torch.bfloat16")
+        self.B, self.augment, self.shuffle, self.drop_last = int(batch_size), augment, shuffle, drop_last
+        self.load_features = load_features and self.cache.header["load_features"]
+        self.repeat_factor, self.rank, self.world, self.seed = repeat_factor, rank, world, seed
+        self.depth = max(2, int(depth))
+        self.rng = rng if rng is not None else random.Random(seed * 1000003 + rank)
+        self.out_dtype = out_dtype
+        self.epoch = 0
+        self.copy_threads = max(1, int(copy_threads))
+        self._codes_bytes = _round_up(4 * self.B, _ALIGN_REC)
+        self._slots = None
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.launches = 0
+
+    def __len__(self) -> int:
+        n = len(range(self.rank, self.cache.count * self.repeat_factor, self.world))
+        return n // self.B if self.drop_last else (n + self.B - 1) // self.B
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = int(epoch)
+
+    # ---- one batch --------------------------------------------------------------------------------
+    def _slot(self, k: int, rbytes: int):
+        if self._slots is None or self._slots[0]["host"].numel() < self._codes_bytes + self.B * rbytes:
+            n = self._codes_bytes + self.B * rbytes
+            self._slots = [{"host": torch.empty(n, dtype=torch.uint8).pin_memory(),
+                            "dev": torch.empty(n, dtype=torch.uint8, device=self.device), "ev": None}
+                           for _ in range(self.depth + 1)]
+        return self._slots[k % len(self._slots)]
+
+    def _produce(self, k: int, idxs: List[int]) -> dict:
+        K, cache = self.K, self.cache
+        n = len(idxs)
+        recs = [i % cache.count for i in idxs]
+        segs, rbytes = cache.layout(recs[0])
+        slot = self._slot(k, rbytes)
+        if slot["ev"] is not None:
+            slot["ev"].synchronize()                          # the H2D that last used this staging buffer has finished
+        host = slot["host"].numpy()
+        codes = np.zeros(self.B, dtype=np.int32)
+        if self.augment:
+            for j in range(n):
+                hflip = self.rng.random() < 0.5
+                vflip = self.rng.random() < 0.5
+                rot_k = self.rng.randint(0, 3)
+                codes[j] = dihedral_code(hflip, vflip, rot_k)
+        host[:4 * self.B] = codes.view(np.uint8)
+        base = self._codes_bytes
+
+        def copy(j):
+            host[base + j * rbytes: base + (j + 1) * rbytes] = cache.record(recs[j])
+        if self.copy_threads > 1 and n > 1:
+            ts = [threading.Thread(target=lambda a=a: [copy(j) for j in range(a, n, self.copy_threads)])
+                  for a in range(min(self.copy_threads, n))]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        else:
+            for j in range(n):
+                copy(j)
+
+        h0, w0 = cache.header["hw"][recs[0]]
+        transposed = {bool(c & 1) for c in codes[:n]}
+        if h0 != w0 and len(transposed) > 1:
+            raise ValueError("quarter-turn augmentation of non-square samples changes the shape per sample: "
+                             "use batch_size=1 or square patches")
+        tr = bool(codes[0] & 1)
+        nbytes = base + n * rbytes
+        out = {"lr": None, "expert_imgs": {}, "filename": [cache.stems[r] for r in recs]}
+        if self.load_features:
+            out["expert_feats"] = {}
+        with torch.cuda.stream(self._copy_stream):
+            slot["dev"][:nbytes].copy_(slot["host"][:nbytes], non_blocking=True)
+            arr = (K.CacheSegment * len(segs))()
+            m = 0
+            tensors = []
+            for key, Cc, hh, ww, dt, off in segs:
+                if key.startswith("feat.") and not self.load_features:
+                    continue
+                ho, wo = (ww, hh) if tr else (hh, ww)
+                t = torch.empty(n, Cc, ho, wo, device=self.device, dtype=self.out_dtype)
+                tensors.append(t)
+                s = arr[m]
+                s.src_offset, s.dst, s.C, s.h, s.w = off, t.data_ptr(), Cc, hh, ww
+                s.src_dtype = K.DT_F16 if dt == "f16" else K.DT_F32
+                s.dst_dtype = K.DT_BF16 if self.out_dtype == torch.bfloat16 else K.DT_F32
+                m += 1
+                if key in ("lr", "hr"):
+                    out[key] = t
+                elif key.startswith("img."):
+                    out["expert_imgs"][key[4:]] = t
+                else:
+                    out["expert_feats"][key[5:]] = t
+            dev_ptr = slot["dev"].data_ptr()
+            K.check(self.lib.ffsr_cache_unpack(dev_ptr + base, rbytes, n, arr, m, dev_ptr if self.augment else None, self._sm,
+                                               C.c_void_p(self._copy_stream.cuda_stream)), "cache_unpack")
+            self.launches += 1
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        slot["ev"] = ev
+        out["_event"], out["_tensors"] = ev, tensors
+        return out
+
+    def _batches(self) -> List[List[int]]:
+        total = self.cache.count * self.repeat_factor
+        if self.shuffle:
+            g = torch.Generator().manual_seed(self.seed + self.epoch)
+            order = torch.randperm(total, generator=g).tolist()
+        else:
+            order = list(range(total))
+        order = order[self.rank::self.world]
+        out = [order[i:i + self.B] for i in range(0, len(order), self.B)]
+        if out and self.drop_last and len(out[-1]) < self.B:
+            out.pop()
+        return out
+
+    def __iter__(self) -> Iterator[dict]:
+        batches = self._batches()
+        self.epoch += 1
+        q: "queue.Queue" = queue.Queue(maxsize=self.depth - 1)
+        stop = threading.Event()
+
+        def worker():
+            try:
+                with torch.cuda.device(self.device):
+                    for k, idxs in enumerate(batches):
+                        if stop.is_set():
+                            return
+                        q.put(self._produce(k, idxs))
+                q.put(None)
+            except BaseException as exc:                      # surface loader errors in the consumer
+                q.put(exc)
+
+        th = threading.Thread(target=worker, daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(item.pop("_event"))
+                for t in item.pop("_tensors"):
+                    t.record_stream(cur)
+                yield item
+        finally:
+            stop.set()
+            while th.is_alive():
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    pass
+                th.join(timeout=0.05)
+
+
+def create_cached_dataloader(feature_dir: str, batch_size: int = 16, num_workers: int = 4, augment: bool = True,
+                             repeat_factor: int = 20, pin_memory: bool = True, persistent_workers: bool = True,
+                             prefetch_factor: int = 4, load_features: bool = True, device=None, **kw):
+    """``create_cached_dataloader`` of the reference (cached_dataset.py:285-337) over a shard.  With ``device`` it returns
+    the ``DeviceBatchLoader`` (batches already on the GPU); without, a torch ``DataLoader`` over ``ShardDataset`` with the
+    reference's settings (shuffle, drop_last, workers)."""
+    if device is not None:
+        return DeviceBatchLoader(feature_dir, batch_size, device, augment=augment, shuffle=True, drop_last=True,
+                                 load_features=load_features, repeat_factor=repeat_factor, **kw)
+    ds = ShardDataset(feature_dir, augment=augment, repeat_factor=repeat_factor, load_features=load_features)
+    return torch.utils.data.DataLoader(ds, batch_size=batch_size, shuffle=True, num_workers=num_workers, pin_memory=pin_memory,
+                                       drop_last=True, persistent_workers=persistent_workers and num_workers > 0,
+                                       prefetch_factor=prefetch_factor if num_workers > 0 else None)

@@ -50,6 +50,7 @@ typedef struct CUstream_st* cudaStream_t;
 
 #define FFSR_DT_F32 0
 #define FFSR_DT_BF16 1
+#define FFSR_DT_F16 2  /* source dtype of cache records only (ffsr_cache_unpack) */
 
 const char* ffsr_last_error(void);
 const char* ffsr_version(void);
@@ -340,6 +341,24 @@ int ffsr_fft_lowpass(const float* x, int B, int H, int W, const float* mask, con
                      size_t ws_bytes, float* low, cudaStream_t stream);
 int ffsr_fft_lowpass_backward(const float* x, const float* dlow, int B, int H, int W, const void* tw_h, const void* tw_w,
                               void* ws, size_t ws_bytes, float* dmask, cudaStream_t stream);
+
+/* Cache-shard records -> batch tensors (the collate step of src/data/cached_dataset.py:135-282 on the device).
+ * `records`: B raw records of `record_bytes` each, already in device memory (one H2D copy of the pinned staging buffer).
+ * Every segment describes one tensor of a record, stored dense [C][h][w] as fp32 or fp16 at `src_offset`; it is written
+ * to dst[b] (dense [C][Ho][Wo], fp32 or bf16) after sample b's dihedral transform tf_codes[b] (device array, NULL = none):
+ * out[y][x] = in[sy][sx], (sy, sx) = (code & 1) ? (x, y) : (y, x); sy = h-1-sy if (code & 2); sx = w-1-sx if (code & 4)
+ * -- the 8 compositions of the loader's hflip / vflip / rot90 (cached_dataset.py:236-282).  At most 16 segments. */
+typedef struct ffsr_cache_segment {
+  unsigned long long src_offset; /* byte offset inside a record, multiple of 16 */
+  void* dst;                     /* [B][C][Ho][Wo] dense, 16-byte aligned */
+  int C, h, w;                   /* stored shape */
+  int src_dtype;                 /* FFSR_DT_F32 | FFSR_DT_F16 */
+  int dst_dtype;                 /* FFSR_DT_F32 | FFSR_DT_BF16 */
+  int reserved;
+} ffsr_cache_segment;
+int ffsr_cache_segment_size(void); /* sizeof(ffsr_cache_segment), for binding layout checks */
+int ffsr_cache_unpack(const void* records, size_t record_bytes, int B, const ffsr_cache_segment* segs, int nseg,
+                      const int* tf_codes, int sm_count, cudaStream_t stream);
 
 #ifdef __cplusplus
 }
