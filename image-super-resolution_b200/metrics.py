@@ -69,3 +69,36 @@ def calculate_psnr_ssim_batch(sr_images, hr_images, crop_border: int = 4, test_y
     finite = torch.isfinite(p)                                 # identical images are left out of the PSNR average
     avg_p = float(p[finite].mean()) if bool(finite.any()) else float("inf")
     return avg_p, float(s.mean())
+
+
+class MetricCalculator:
+    """``src.utils.metrics.MetricCalculator`` (metrics.py:291-375) without the two host syncs per image: ``update`` keeps
+    the per-image PSNR / SSIM as device tensors, ``get_metrics`` reduces them with ONE synchronisation.  Same results:
+    infinite PSNR values are left out of the PSNR mean, every image counts for SSIM, empty -> zeros."""
+
+    def __init__(self, crop_border: int = 4, test_y_channel: bool = True):
+        self.crop_border, self.test_y_channel = crop_border, test_y_channel
+        self.reset()
+
+    def reset(self) -> None:
+        self._psnr, self._ssim, self.count = [], [], 0
+
+    @torch.no_grad()
+    def update(self, sr: torch.Tensor, hr: torch.Tensor) -> None:
+        p, s = psnr_ssim_per_image(sr, hr, self.crop_border, self.test_y_channel)
+        self._psnr.append(p)
+        self._ssim.append(s)
+        self.count += int(sr.shape[0]) if sr.dim() == 4 else 1
+
+    def get_metrics(self):
+        if self.count == 0:
+            return {"psnr": 0.0, "ssim": 0.0}
+        p, s = torch.cat(self._psnr), torch.cat(self._ssim)
+        finite = torch.isfinite(p)
+        both = torch.stack([torch.where(finite, p, torch.zeros_like(p)).double().sum(), finite.double().sum(),
+                            s.double().mean()]).tolist()                                   # the one sync
+        return {"psnr": both[0] / both[1] if both[1] > 0 else 0.0, "ssim": both[2]}
+
+    def __str__(self) -> str:
+        m = self.get_metrics()
+        return f"PSNR: {m['psnr']:.2f} dB, SSIM: {m['ssim']:.4f}"

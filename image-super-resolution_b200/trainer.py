@@ -201,6 +201,19 @@ class FusedAdamW(torch.optim.Optimizer):
         """Global gradient norm seen by the last step (device scalar, no sync)."""
         return self._gsq.sqrt() / _world()
 
+    @torch.no_grad()
+    def swap_ema(self) -> None:
+        """Exchange the parameters with their EMA shadow in place (call again to undo).  ``EMAModel.save`` + ``apply``
+        + ``restore`` (checkpoint_manager.py:359-377, train.py:450-452, 515) clone every parameter twice and copy 198
+        tensors three times; with flat buckets the swap is three copies of one 5.7 MB buffer and no allocation beyond
+        the temporary."""
+        if self.ema is None:
+            raise RuntimeError("EMA is disabled (ema_decay=None)")
+        tmp = self.bucket.flat.clone()
+        self.bucket.flat.copy_(self.ema)
+        self.ema.copy_(tmp)
+        self.bump_versions()                                   # packed / bf16 weight caches are keyed on _version
+
     def ema_shadow(self, names: List[str]) -> Dict[str, torch.Tensor]:
         """EMAModel.shadow-compatible dict (checkpoint_manager.py:344-350): name -> view of the flat shadow."""
         if self.ema is None:
@@ -291,3 +304,53 @@ class FusionTrainer:
         opt.steps += 1
         opt.bump_versions()
         return self._out
+
+    # ---- validation -----------------------------------------------------------------------------
+    def ema_weights(self):
+        """``with trainer.ema_weights():`` -- the model runs on its EMA weights inside the block."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            self.optimizer.swap_ema()
+            try:
+                yield self.model
+            finally:
+                self.optimizer.swap_ema()
+        return cm()
+
+    def validate(self, val_loader, crop_border: int = 4, test_y_channel: bool = True, use_ema: bool = True) -> Dict[str, float]:
+        """``validate_epoch`` of the reference's cached mode (train.py:415-515) on this trainer's model."""
+        return validate_epoch(self.model, val_loader, self.model.residual_scale.device, crop_border, test_y_channel,
+                              self.optimizer if (use_ema and self.optimizer.ema is not None) else None)
+
+
+@torch.no_grad()
+def validate_epoch(model, val_loader, device, crop_border: int = 4, test_y_channel: bool = True,
+                   ema: Optional[FusedAdamW] = None) -> Dict[str, float]:
+    """Cached-mode ``validate_epoch`` (train.py:415-515): eval mode, EMA weights if given, full-image
+    ``forward_with_precomputed`` per batch, clamp, Y-channel PSNR / SSIM with border crop -- with the metrics kept on
+    the device (ONE host sync per epoch instead of two per image) and the EMA exchange done on the flat bucket.
+    ``val_loader`` yields the reference's batch dict (host tensors from a DataLoader, fp16 allowed) or device batches
+    (``cache.DeviceBatchLoader``).  The model's train / eval mode is restored on exit."""
+    from .metrics import MetricCalculator
+    was_training = model.training
+    model.eval()
+    if ema is not None:
+        ema.swap_ema()
+    calc = MetricCalculator(crop_border, test_y_channel)
+    try:
+        for batch in val_loader:
+            lr_img = batch["lr"].to(device, non_blocking=True).float()
+            hr_img = batch["hr"].to(device, non_blocking=True).float()
+            imgs = {k: v.to(device, non_blocking=True).float() for k, v in batch["expert_imgs"].items()}
+            feats = None
+            if batch.get("expert_feats") is not None:
+                feats = {k: v.to(device, non_blocking=True).float() for k, v in batch["expert_feats"].items()}
+            sr = model.forward_with_precomputed(lr_img, imgs, feats).clamp(0, 1)
+            calc.update(sr, hr_img)
+    finally:
+        if ema is not None:
+            ema.swap_ema()
+        model.train(was_training)
+    return calc.get_metrics()

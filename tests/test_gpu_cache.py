@@ -124,3 +124,56 @@ def test_cache_unpack_rejects_bad_arguments():
     assert lib.ffsr_cache_unpack(4096, 1024, 1, seg, 1, None, 148, None) == -1            # bf16 is not a storage dtype
     assert b"cache_unpack" in lib.ffsr_last_error()
     assert C.sizeof(K.CacheSegment) == lib.ffsr_cache_segment_size() == 40
+
+
+@pytest.mark.gpu
+def test_validate_epoch_and_ema_swap(tmp_path):
+    """trainer.validate_epoch (train.py:415-515, cached mode) over a device loader of per-image-sized samples: metrics equal
+    the metric oracle applied to the same outputs; the EMA exchange puts the shadow in, and the weights back, bit-exactly."""
+    import numpy as np
+    from isr_b200 import losses as FL
+    from isr_b200.trainer import FusionTrainer, validate_epoch
+    from oracle import loss_oracle as L
+    dev = torch.device("cuda:0")
+    d = tmp_path / "val"
+    d.mkdir()
+    for i, hw in enumerate([(16, 24), (24, 16), (16, 16)]):               # val caches: one full image per sample
+        CO.write_mock_cache(d / f"p{i}", n=1, lr_hw=hw, seed=30 + i)
+        for f in os.listdir(d / f"p{i}"):
+            os.rename(d / f"p{i}" / f, d / f.replace("img_000", f"img_{i:03d}"))
+    CA.pack_cache(str(d), str(tmp_path / "val.ffsrc"), dtype="fp16")
+    torch.manual_seed(0)
+    m = isr_b200.CompleteEnhancedFusionSR(None).to(dev)
+    crit = FL.CombinedLoss()
+    crit.set_weights({"charbonnier": 0, "l2": 0, "vgg": 0, "edge": 0, "clip": 0, "l1": 1.0, "swt": 0, "fft": 0, "ssim": 0})
+    tr = FusionTrainer(m, crit, lr=1e-2, ema_decay=0.9, cuda_graph=False)
+    lr, imgs, fts, hr = __import__("oracle.fusion_oracle", fromlist=["x"]).synthetic_inputs(2, 12, 12)
+    for _ in range(2):                                                      # move the weights away from their EMA
+        tr.step(lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()}, hr.to(dev))
+    opt = tr.optimizer
+    w0, e0 = opt.bucket.flat.clone(), opt.ema.clone()
+    assert not torch.equal(w0, e0)
+    names = [n for n, _ in m.named_parameters()]
+    with tr.ema_weights():
+        assert torch.equal(opt.bucket.flat, e0) and torch.equal(opt.ema, w0)
+        o = opt.bucket.offsets[5]
+        p5 = dict(m.named_parameters())[names[5]]
+        assert torch.equal(p5.data.reshape(-1), e0[o:o + p5.numel()])        # parameters are views of the bucket
+    assert torch.equal(opt.bucket.flat, w0) and torch.equal(opt.ema, e0)
+
+    loader = CA.DeviceBatchLoader(str(tmp_path / "val.ffsrc"), 1, dev, augment=False, shuffle=False, drop_last=False)
+    got = tr.validate(loader, crop_border=4, test_y_channel=True, use_ema=True)
+    assert m.training and torch.equal(opt.bucket.flat, w0)                  # mode and weights restored
+    # the same thing by hand: EMA weights, eval forward, oracle metrics on the host
+    opt.swap_ema()
+    m.eval()
+    ps, ss = [], []
+    for batch in CA.DeviceBatchLoader(str(tmp_path / "val.ffsrc"), 1, dev, augment=False, shuffle=False, drop_last=False):
+        sr = m.forward_with_precomputed(batch["lr"], batch["expert_imgs"], batch["expert_feats"]).clamp(0, 1)
+        ps.append(L.metric_psnr(sr[0].cpu(), batch["hr"][0].cpu(), 4, True))
+        ss.append(L.metric_ssim(sr[0].cpu(), batch["hr"][0].cpu(), 4, True))
+    opt.swap_ema()
+    m.train()
+    assert abs(got["psnr"] - float(np.mean(ps))) < 2e-3 and abs(got["ssim"] - float(np.mean(ss))) < 2e-5
+    no_ema = validate_epoch(m, loader, dev, 4, True, None)
+    assert no_ema["psnr"] != got["psnr"]
