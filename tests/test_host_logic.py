@@ -100,3 +100,32 @@ def test_orchestration_dry_run(with_feats, want_inter, precision):
         assert set(inter) >= {"raw_9_bands", "enhanced_9_bands", "routing_lr", "collaborative_outputs",
                               "fused_before_dynamic", "gates", "difficulty"}
         assert len(inter["raw_9_bands"]) == 9 and inter["gates"].shape == (B, 4, H, W)
+
+
+def test_tile_grid_covers_the_image_on_the_8px_grid():
+    from isr_b200.serving import tile_grid, TILE_HALO_LR
+    for (H, W, ty, tx) in [(339, 510, 1, 2), (339, 510, 2, 4), (64, 64, 2, 2), (17, 200, 1, 8)]:
+        t = tile_grid(H, W, ty, tx)
+        assert len(t) == ty * tx
+        cover = set()
+        for y0, y1, x0, x1 in t:
+            assert 0 <= y0 < y1 <= H and 0 <= x0 < x1 <= W and y0 % 8 == 0 and x0 % 8 == 0
+            cover.update((y, x) for y in range(y0, y1, 7) for x in range(x0, x1, 7))
+        assert sum((y1 - y0) * (x1 - x0) for y0, y1, x0, x1 in t) == H * W
+    assert TILE_HALO_LR % 8 == 0 and TILE_HALO_LR * 4 >= 110        # receptive field behind the bands: <= 110 HR px
+    import pytest
+    with pytest.raises(ValueError):
+        tile_grid(16, 16, 4, 1)
+
+
+def test_device_only_entry_points_refuse_cpu_tensors():
+    import pytest
+    import torch
+    from isr_b200 import metrics as MT
+    from isr_b200.serving import fuse_tiled
+    a = torch.rand(1, 3, 16, 16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        MT.psnr_ssim_per_image(a, a)
+    m = isr_b200.CompleteEnhancedFusionSR(None).eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fuse_tiled(m, torch.rand(1, 3, 16, 16), {k: torch.rand(1, 3, 64, 64) for k in ("drct", "grl", "nafnet", "mamba")}, None)

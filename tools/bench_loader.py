@@ -79,11 +79,35 @@ def main():
                     t0 = time.perf_counter()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            # the kernel alone: records resident on the device
-            b = next(iter(loader))
-            del b
+            # the kernel alone: records resident on the device, CUDA events on the stream it is launched on
+            import ctypes as C
+            from isr_b200 import _cabi as K
             slot = loader._slots[0]
+            segs, rbytes = loader.cache.layout(0)
+            outs = [torch.empty(args.batch, Cc, hh, ww, device=dev) for _, Cc, hh, ww, _, _ in segs]
+            arr = (K.CacheSegment * len(segs))()
+            rd = wr = 0
+            for i, (key, Cc, hh, ww, dt, off) in enumerate(segs):
+                arr[i].src_offset, arr[i].dst, arr[i].C, arr[i].h, arr[i].w = off, outs[i].data_ptr(), Cc, hh, ww
+                arr[i].src_dtype, arr[i].dst_dtype = (K.DT_F16 if dt == "f16" else K.DT_F32), K.DT_F32
+                rd += args.batch * Cc * hh * ww * (2 if dt == "f16" else 4)
+                wr += args.batch * Cc * hh * ww * 4
+            st = torch.cuda.Stream(dev)
+            base = loader._codes_bytes
+            ptr = slot["dev"].data_ptr()
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    K.check(loader.lib.ffsr_cache_unpack(ptr + base, rbytes, args.batch, arr, len(segs), ptr, 148, C.c_void_p(st.cuda_stream)))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                for _ in range(20):
+                    K.check(loader.lib.ffsr_cache_unpack(ptr + base, rbytes, args.batch, arr, len(segs), ptr, 148, C.c_void_p(st.cuda_stream)))
+                e1.record(st)
             torch.cuda.synchronize()
+            k_ms = e0.elapsed_time(e1) / 20
+            print(json.dumps({"kernel": "k_cache_unpack", "mode": mode, "batch": args.batch, "ms": k_ms, "bytes_read": rd, "bytes_written": wr,
+                              "GB_per_s": (rd + wr) / k_ms / 1e6, "note": "augmentation codes of the last batch (mixed flips / quarter turns); "
+                              "working set > L2 (126 MB)"}), flush=True)
             print(json.dumps({"arm": f"pack_cache({mode}) + DeviceBatchLoader", "samples_per_s": n / dt,
                               "GB_per_s_fp32_equivalent": n * 13.9e-3 / dt, "shard_MB_per_sample": os.path.getsize(shard) / args.samples / 1e6,
                               "pack_seconds": pack_s, "kernel_launches_per_batch": 1, "batch": args.batch,
