@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--epochs", type=int, default=3)
     ap.add_argument("--workers", type=int, default=4)
+    ap.add_argument("--skip-reference", action="store_true", help="only the shard arms (e.g. under ncu)")
     args = ap.parse_args()
     import isr_b200  # noqa: F401
     from isr_b200 import cache as CA
@@ -38,7 +39,7 @@ def main():
         sample_mb = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d)) / args.samples / 1e6
 
         # ---- reference-style arm ------------------------------------------------------------------
-        for workers in (0, args.workers):
+        for workers in (() if args.skip_reference else (0, args.workers)):
             ds = CO.OracleCachedDataset(d, augment=True, repeat_factor=repeat)
             dl = torch.utils.data.DataLoader(ds, batch_size=args.batch, shuffle=True, num_workers=workers, pin_memory=True,
                                              drop_last=True, persistent_workers=workers > 0,
@@ -87,10 +88,10 @@ def main():
             outs = [torch.empty(args.batch, Cc, hh, ww, device=dev) for _, Cc, hh, ww, _, _ in segs]
             arr = (K.CacheSegment * len(segs))()
             rd = wr = 0
-            for i, (key, Cc, hh, ww, dt, off) in enumerate(segs):
+            for i, (key, Cc, hh, ww, sdt, off) in enumerate(segs):
                 arr[i].src_offset, arr[i].dst, arr[i].C, arr[i].h, arr[i].w = off, outs[i].data_ptr(), Cc, hh, ww
-                arr[i].src_dtype, arr[i].dst_dtype = (K.DT_F16 if dt == "f16" else K.DT_F32), K.DT_F32
-                rd += args.batch * Cc * hh * ww * (2 if dt == "f16" else 4)
+                arr[i].src_dtype, arr[i].dst_dtype = (K.DT_F16 if sdt == "f16" else K.DT_F32), K.DT_F32
+                rd += args.batch * Cc * hh * ww * (2 if sdt == "f16" else 4)
                 wr += args.batch * Cc * hh * ww * 4
             st = torch.cuda.Stream(dev)
             base = loader._codes_bytes
