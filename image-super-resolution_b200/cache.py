@@ -367,6 +367,22 @@ class ShardDataset(torch.utils.data.Dataset):
 # ---------------------------------------------------------------------------------------------------
 # device loader
 # ---------------------------------------------------------------------------------------------------
+def epoch_batches(total: int, batch_size: int, shuffle: bool, seed: int, epoch: int, rank: int = 0, world: int = 1,
+                  drop_last: bool = True) -> List[List[int]]:
+    """Index batches of one epoch for one rank: a permutation shared by all ranks (seeded by ``seed + epoch``), every
+    world-th index from position ``rank``, cut into batches.  Ranks never share an index within an epoch."""
+    if shuffle:
+        g = torch.Generator().manual_seed(seed + epoch)
+        order = torch.randperm(total, generator=g).tolist()
+    else:
+        order = list(range(total))
+    order = order[rank::world]
+    out = [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
+    if out and drop_last and len(out[-1]) < batch_size:
+        out.pop()
+    return out
+
+
 class DeviceBatchLoader:
     """Batches of a shard as DEVICE tensors, shaped like the reference DataLoader's collated dict
     (``lr [B,3,h,w]``, ``hr``, ``expert_imgs{name}``, ``expert_feats{name}``, ``filename`` list; train.py:300-322).
@@ -510,17 +526,8 @@ class DeviceBatchLoader:
         return out
 
     def _batches(self) -> List[List[int]]:
-        total = self.cache.count * self.repeat_factor
-        if self.shuffle:
-            g = torch.Generator().manual_seed(self.seed + self.epoch)
-            order = torch.randperm(total, generator=g).tolist()
-        else:
-            order = list(range(total))
-        order = order[self.rank::self.world]
-        out = [order[i:i + self.B] for i in range(0, len(order), self.B)]
-        if out and self.drop_last and len(out[-1]) < self.B:
-            out.pop()
-        return out
+        return epoch_batches(self.cache.count * self.repeat_factor, self.B, self.shuffle, self.seed, self.epoch, self.rank,
+                             self.world, self.drop_last)
 
     def __iter__(self) -> Iterator[dict]:
         batches = self._batches()

@@ -180,3 +180,41 @@ def test_device_loader_refuses_cpu(tmp_path):
     CA.pack_cache(str(d), str(tmp_path / "s.ffsrc"))
     with pytest.raises(RuntimeError, match="no CPU path"):
         CA.DeviceBatchLoader(str(tmp_path / "s.ffsrc"), 1, "cpu")
+
+
+def test_epoch_batches_partition_the_epoch_over_ranks():
+    for world in (1, 2, 8):
+        seen = []
+        for rank in range(world):
+            bs = CA.epoch_batches(103, 4, True, seed=7, epoch=2, rank=rank, world=world, drop_last=False)
+            assert all(len(b) == 4 for b in bs[:-1]) and 1 <= len(bs[-1]) <= 4
+            seen += [i for b in bs for i in b]
+        assert sorted(seen) == list(range(103))                       # disjoint cover, every rank the same permutation
+    a = CA.epoch_batches(50, 8, True, 1, 0)
+    assert a == CA.epoch_batches(50, 8, True, 1, 0) and a != CA.epoch_batches(50, 8, True, 1, 1)
+    assert len(a) == 6 and all(len(b) == 8 for b in a)                # drop_last
+    assert CA.epoch_batches(10, 4, False, 0, 0, drop_last=False) == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+
+
+def test_shard_writer_rejects_inconsistent_samples(tmp_path):
+    lr, hr = torch.rand(3, 8, 8), torch.rand(3, 32, 32)
+    imgs = {k: torch.rand(3, 32, 32) for k in ("drct", "grl", "nafnet", "mamba")}
+    feats = {"drct": torch.randn(180, 8, 8), "grl": torch.randn(180, 8, 8), "nafnet": torch.randn(64, 8, 8), "mamba": torch.randn(180, 8, 8)}
+    with pytest.raises(ValueError, match="expected"):
+        with CA.ShardWriter(str(tmp_path / "a.ffsrc")) as w:
+            w.add("a", lr, hr, imgs, feats)
+            w.add("b", lr, hr, {**imgs, "grl": torch.rand(3, 16, 16)}, feats)
+    assert not os.path.exists(tmp_path / "a.ffsrc") and not os.path.exists(str(tmp_path / "a.ffsrc") + ".records.tmp")
+    with pytest.raises(ValueError, match="no tensor"):
+        with CA.ShardWriter(str(tmp_path / "b.ffsrc")) as w:
+            w.add("a", lr, hr, imgs, feats)
+            w.add("b", lr, hr, {k: v for k, v in imgs.items() if k != "grl"}, feats)
+    with pytest.raises(ValueError):
+        CA.ShardWriter(str(tmp_path / "c.ffsrc"), dtype="int8")
+    with CA.ShardWriter(str(tmp_path / "d.ffsrc"), dtype="fp16") as w:       # in-memory samples straight into a shard
+        w.add("a", lr, hr, imgs, feats)
+        w.add("b", lr, hr, {k: v for k, v in imgs.items() if k != "mamba"}, {k: v for k, v in feats.items() if k != "mamba"})
+    c = CA.ShardCache(str(tmp_path / "d.ffsrc"))
+    assert c.count == 2 and c.header["has_mamba"] == [True, False]
+    s1 = c.sample(1)
+    assert float(s1["expert_imgs"]["mamba"].abs().max()) == 0.0 and torch.equal(s1["expert_imgs"]["drct"], imgs["drct"].half())
