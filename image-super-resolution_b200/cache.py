@@ -253,6 +253,28 @@ def pack_cache(feature_dir: str, out_path: str, dtype: str = "source", load_feat
     return w.header
 
 
+SHARD_NAME = "_cache.ffsrc"
+
+
+def resolve_shard(feature_dir: str, dtype: str = "source", load_features: bool = True) -> str:
+    """A shard path for what the reference calls ``feature_dir``: a shard file is returned as is; a reference cache
+    DIRECTORY (the argument unchanged callers pass, train.py:594-646) is packed once into ``<dir>/_cache.ffsrc`` and
+    that file is reused afterwards (re-packed when a ``*_part.pt`` is newer than the shard)."""
+    p = Path(feature_dir)
+    if p.is_file():
+        return str(p)
+    if not p.exists():
+        raise RuntimeError(f"Feature cache directory not found: {feature_dir}")
+    shard = p / SHARD_NAME
+    parts = list(p.glob("*_part.pt"))
+    if not parts and not shard.exists():
+        raise RuntimeError(f"No cached features found in {feature_dir}!")
+    if not shard.exists() or (parts and max(f.stat().st_mtime for f in parts) > shard.stat().st_mtime):
+        print(f"[isr_b200.cache] packing {feature_dir} -> {shard} ({dtype}) ...", flush=True)
+        pack_cache(str(p), str(shard), dtype=dtype, load_features=load_features)
+    return str(shard)
+
+
 class ShardCache:
     """Read-only view of a shard: header + memory-mapped records."""
 
@@ -323,10 +345,7 @@ class ShardDataset(torch.utils.data.Dataset):
 
     def __init__(self, feature_dir: str, augment: bool = True, repeat_factor: int = 1, load_features: bool = True):
         super().__init__()
-        p = Path(feature_dir)
-        if not p.exists():
-            raise RuntimeError(f"Feature cache shard not found: {feature_dir}")
-        self.cache = ShardCache(str(p))
+        self.cache = ShardCache(resolve_shard(feature_dir))          # a reference cache directory is packed on first use
         self.file_stems = self.cache.stems
         self.has_mamba = dict(zip(self.cache.stems, self.cache.header["has_mamba"]))
         self.augment, self.repeat_factor = augment, repeat_factor
@@ -578,9 +597,10 @@ class DeviceBatchLoader:
 def create_cached_dataloader(feature_dir: str, batch_size: int = 16, num_workers: int = 4, augment: bool = True,
                              repeat_factor: int = 20, pin_memory: bool = True, persistent_workers: bool = True,
                              prefetch_factor: int = 4, load_features: bool = True, device=None, **kw):
-    """``create_cached_dataloader`` of the reference (cached_dataset.py:285-337) over a shard.  With ``device`` it returns
-    the ``DeviceBatchLoader`` (batches already on the GPU); without, a torch ``DataLoader`` over ``ShardDataset`` with the
-    reference's settings (shuffle, drop_last, workers)."""
+    """``create_cached_dataloader`` of the reference (cached_dataset.py:285-337) over a shard (or a reference cache
+    directory, packed on first use).  With ``device`` it returns the ``DeviceBatchLoader`` (batches already on the GPU);
+    without, a torch ``DataLoader`` over ``ShardDataset`` with the reference's settings (shuffle, drop_last, workers)."""
+    feature_dir = resolve_shard(feature_dir)
     if device is not None:
         return DeviceBatchLoader(feature_dir, batch_size, device, augment=augment, shuffle=True, drop_last=True,
                                  load_features=load_features, repeat_factor=repeat_factor, **kw)
