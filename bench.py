@@ -126,6 +126,40 @@ def cpu_oracle_throughput(H, W, steps, warmup, threads):
     return 16 * H * W / t / 1e6, t
 
 
+def gpu_eager_throughput(model, dev, H, W, steps=5, warmup=2):
+    """BASELINE.md §3 item 2, "the real bar": the same algorithm in PyTorch eager (cuDNN / cuBLAS / cuFFT / ATen) on the
+    SAME B200.  The reference tree does not travel to the GPU box, so this times the oracle's restatement of the module
+    (plain torch ops, pinned to the reference on CPU) with its tensors on the device: fp32 and under bf16 autocast."""
+    import torch
+    from oracle import fusion_oracle as O
+    sd = {k: v.detach().to(dev) for k, v in model.state_dict().items()}
+    lr, imgs, fts, _ = O.synthetic_inputs(1, H, W, seed=1234)
+    lr, imgs, fts = lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()}
+    out = {}
+    for name, ctx in (("fp32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        def fwd():
+            with torch.no_grad():
+                if ctx is None:
+                    return O.run_pipeline(sd, lr, imgs, fts)
+                with ctx:
+                    return O.run_pipeline(sd, lr, imgs, fts)
+        for _ in range(warmup):
+            fwd()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fwd()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"value": 16 * H * W / 1e6 / (ms * 1e-3), "unit": "HR MPix/s", "ms_per_image": ms}
+    out["kind"] = "port: oracle restatement in PyTorch eager on the same GPU (cudnn.allow_tf32=%s, matmul.allow_tf32=%s)" % (
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    out["steps"] = steps
+    return out
+
+
 def cpu_oracle_train_throughput(hw, batch, steps, warmup, threads, weights):
     """patches/s of one CPU training step of the oracle port (forward + losses + autograd backward + AdamW)."""
     import torch
@@ -463,6 +497,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("FFSR_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--lr", type=int, nargs=2, default=[LR_H, LR_W], help="LR size (parity/debug runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager-on-the-same-GPU baseline of the C3 line")
     ap.add_argument("--no-train", action="store_true", help="skip the C2 training-step figure added to the C3 line")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -596,8 +631,24 @@ def main():
                      "ms_per_step": r["ms"], "steps": 5, "scaling": "strong",
                      "config": train_config("c2", r["patches"], r["B"], r["hw"], args.precision),
                      "tflops_algorithmic": TRAIN_FLOP_PER_HR_PIXEL * r["patches"] * 16 * r["hw"] ** 2 / (r["ms"] * 1e-3) / 1e12}
+            r = None
         except Exception as exc:                               # the headline line must survive a training failure
             train = {"error": repr(exc)[:300]}
+
+    gpu_eager = None
+    if world == 1 and not args.no_gpu_eager:
+        if trainer is not None:
+            trainer._graph = None
+        trainer = None
+        m._engine = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            gpu_eager = gpu_eager_throughput(m, dev, H, W)
+        except Exception as exc:                                   # a baseline must not take the headline line down
+            gpu_eager = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         tensor_peak, hbm_peak, peak_src = _peaks()
@@ -635,6 +686,8 @@ def main():
         }
         if train is not None:
             line["train"] = train
+        if gpu_eager is not None:
+            line["gpu_eager_baseline"] = gpu_eager
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             ch, cw = (H, W) if threads >= 16 else (H // 2, W // 2)
