@@ -188,6 +188,54 @@ def cpu_oracle_train_throughput(hw, batch, steps, warmup, threads, weights):
     return batch / t, t
 
 
+def gpu_eager_train_throughput(dev, hw, batch, weights, steps=4, warmup=2):
+    """The training step as plain PyTorch eager on the SAME GPU (autograd over the oracle's restatement, torch losses,
+    clip_grad_norm_, torch.optim.AdamW, EMA as a foreach lerp): fp32 and with the forward under bf16 autocast."""
+    import torch
+    import isr_b200
+    from oracle import fusion_oracle as O
+    from oracle import loss_oracle as LO
+    out = {}
+    lr, imgs, fts, hr = O.synthetic_inputs(batch, hw, hw)
+    lr, hr = lr.to(dev), hr.to(dev)
+    imgs, fts = {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()}
+    for name, auto in (("fp32", False), ("bf16_autocast", True)):
+        torch.manual_seed(0)
+        m = isr_b200.CompleteEnhancedFusionSR(None)
+        pn = dict(m.named_parameters())
+        sd = {k: (v.detach().to(dev).requires_grad_() if k in pn else v.detach().to(dev)) for k, v in m.state_dict().items()}
+        params = [sd[k] for k in pn]
+        ema = [p.detach().clone() for p in params]
+        opt = torch.optim.AdamW(params, lr=2e-4, betas=(0.9, 0.999), weight_decay=1e-4)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=auto):
+                sr = O.run_pipeline(sd, lr, imgs, fts, training=True, bn_updates={})
+            loss, _ = LO.combined_loss(sr.float().clamp(0, 1), hr, weights)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            with torch.no_grad():
+                torch._foreach_lerp_(ema, params, 1.0 - 0.999)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"value": batch / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms}
+        del sd, params, ema, opt
+        torch.cuda.empty_cache()
+    out["kind"] = "port: oracle restatement + torch autograd / AdamW in PyTorch eager on the same GPU"
+    out["steps"] = steps
+    return out
+
+
 def run_reference_train(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -398,6 +446,18 @@ def run_train(args):
                                    "profiles/r01_conv_train_microbench.txt, profiles/r01_wgrad_tc_128x128_ncu_full.txt",
                          "peak_source": peak_src},
         }
+        if world == 1 and not args.no_gpu_eager:
+            try:
+                import gc
+                import torch
+                tr_ = r.pop("trainer")
+                tr_._graph = None
+                del tr_
+                gc.collect()
+                torch.cuda.empty_cache()
+                line["gpu_eager_baseline"] = gpu_eager_train_throughput(dev, hw, r["B"], STAGE_WEIGHTS[args.workload])
+            except Exception as exc:
+                line["gpu_eager_baseline"] = {"error": repr(exc)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, t = cpu_oracle_train_throughput(hw, 2, 2, 1, threads, STAGE_WEIGHTS[args.workload])
@@ -405,7 +465,7 @@ def run_train(args):
                                     "sample": f"2 training steps (forward + losses + autograd backward + clip + AdamW) of the "
                                               f"fp32 oracle port on 2 patches of {hw}x{hw} LR, {t:.1f} s per step on {threads} threads"}
         print(json.dumps(line), flush=True)
-    _leave(world, r["trainer"])
+    _leave(world, r.get("trainer"))
 
 
 def run_tiled(args):

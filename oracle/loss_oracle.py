@@ -42,7 +42,7 @@ def _gauss_window(size=11, sigma=1.5, channels=3):
 def ssim_loss(pred, target):
     """SSIMLoss._ssim/forward, perceptual_loss.py:243-291 (zero pad 5, C1=1e-4, C2=9e-4)."""
     Cc = pred.shape[1]
-    w = _gauss_window(11, 1.5, Cc).to(pred.dtype)
+    w = _gauss_window(11, 1.5, Cc).to(device=pred.device, dtype=pred.dtype)
     C1, C2 = 0.01 ** 2, 0.03 ** 2
     mu1 = F.conv2d(pred, w, padding=5, groups=Cc)
     mu2 = F.conv2d(target, w, padding=5, groups=Cc)
@@ -60,7 +60,7 @@ def fft_loss(pred, target, high_freq_weight=2.0):
     T = torch.fft.fftshift(torch.fft.fft2(target, norm="ortho"), dim=(-2, -1))
     cy, cx = H // 2, W // 2
     yy, xx = torch.meshgrid(torch.arange(H).float() - cy, torch.arange(W).float() - cx, indexing="ij")
-    wts = (1.0 + (high_freq_weight - 1.0) * torch.sqrt(xx ** 2 + yy ** 2) / math.sqrt(cy ** 2 + cx ** 2)).to(pred.dtype)
+    wts = (1.0 + (high_freq_weight - 1.0) * torch.sqrt(xx ** 2 + yy ** 2) / math.sqrt(cy ** 2 + cx ** 2)).to(device=pred.device, dtype=pred.dtype)
     mag = (P.abs() - T.abs()).abs() * wts
     ph = (P.angle() - T.angle()).abs() * wts
     return mag.mean() + 0.1 * ph.mean()
@@ -79,7 +79,7 @@ def _haar_filters(dtype):
 def swt_coeffs(x, level=2):
     """SWTLoss._swt2d_gpu, perceptual_loss.py:684-733."""
     B, Cc, H, W = x.shape
-    filt = _haar_filters(x.dtype)
+    filt = _haar_filters(x.dtype).to(x.device)
     out, cur = [], x
     for lv in range(level):
         pad = 2 ** lv
