@@ -455,7 +455,9 @@ def run_train(args):
                 del tr_
                 gc.collect()
                 torch.cuda.empty_cache()
-                line["gpu_eager_baseline"] = gpu_eager_train_throughput(dev, hw, r["B"], STAGE_WEIGHTS[args.workload])
+                eb = min(r["B"], 32 if hw <= 64 else 16)       # autograd keeps every fp32 activation: bound the footprint
+                line["gpu_eager_baseline"] = gpu_eager_train_throughput(dev, hw, eb, STAGE_WEIGHTS[args.workload])
+                line["gpu_eager_baseline"]["batch"] = eb
             except Exception as exc:
                 line["gpu_eager_baseline"] = {"error": repr(exc)[:300]}
         if world == 1 and not args.no_cpu_baseline:
