@@ -37,7 +37,6 @@ EXPERT_ORDER = ("drct", "grl", "nafnet", "mamba")
 MAGIC = b"FFSRC1\x00\x00"
 _ALIGN_SEG, _ALIGN_REC, _ALIGN_DATA = 16, 512, 4096
 _NP = {"f32": np.float32, "f16": np.float16}
-_TORCH = {"f32": torch.float32, "f16": torch.float16}
 
 
 def _round_up(x: int, a: int) -> int:

@@ -14,7 +14,7 @@ from __future__ import annotations
 import hashlib
 import random
 from pathlib import Path
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 
