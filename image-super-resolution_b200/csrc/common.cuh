@@ -43,8 +43,17 @@ __device__ __forceinline__ float gelu_as(float x) {
   const float erf_abs = 1.0f - poly * t * __expf(-z * z);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
+// tanh-form GELU on the MUFU (6 instructions): |error| <= 4.8e-4 against the erf form.  Only for bf16-mode INFERENCE
+// kernels whose GELU feeds a sigmoid gate head (k_modulate_hr, k_spatial_gate), where the error is damped again.
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
 template <bool FAST>
-__device__ __forceinline__ float gelu_sel(float x) { return FAST ? gelu_as(x) : gelu_erf(x); }
+__device__ __forceinline__ float gelu_sel(float x) { return FAST ? gelu_tanh(x) : gelu_erf(x); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
