@@ -1,0 +1,72 @@
+"""DRCT-L expert forward: the oracle restatement pinned to the reference class -- prepared ahead of the
+CUDA path.  CPU only."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import drct_oracle as DO  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden", "drct_small.npz")
+
+
+def test_oracle_reproduces_the_reference_class_golden():
+    g = np.load(GOLD)
+    cfg = json.loads(str(g["cfg"]))
+    sd = DO.synth_state_dict(DO.state_shapes(**cfg), seed=int(g["seed"]), img_size=cfg["img_size"])
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        y, feat = DO.forward(sd, x, return_feature=True)
+    assert tuple(y.shape) == (1, 3, 64, 96) and tuple(feat.shape) == (1, 180, 16, 24)
+    assert float((y - torch.from_numpy(g["y"])).abs().max()) <= 2e-5
+    assert float((feat.reshape(-1)[::5] - torch.from_numpy(g["feat_sub"])).abs().max()) <= 2e-5
+
+
+def test_full_drct_l_state_layout_matches_the_reference():
+    """Names, shapes and order of the DRCT-L state_dict (create_drct_model) as digested when the golden was made."""
+    g = np.load(GOLD)
+    ours = [(k, s) for k, (s, _) in DO.state_shapes().items()]
+    assert hashlib.sha256(repr(ours).encode()).hexdigest() == bytes(g["full_shapes_sha"]).decode()
+    n_float = sum(int(np.prod(s)) for k, (s, kind) in DO.state_shapes().items() if kind == "float")
+    assert 27_000_000 < n_float < 29_000_000                          # DRCT-L: ~27.6 M parameters
+    dims = DO.swin_dims(180, 6, 32, 2)
+    assert [(d, h) for d, h, _, _ in dims] == [(180, 6), (212, 4), (244, 2), (276, 6), (308, 4)]
+    assert [hid for _, _, hid, _ in dims] == [360, 424, 488, 276, 308]
+
+
+def test_shift_mask_and_window_round_trip():
+    m = DO.shift_mask(16, 24, 8, 4)
+    assert tuple(m.shape) == (6, 64, 64) and set(m.unique().tolist()) == {-100.0, 0.0}
+    assert float(m[0].abs().max()) == 0.0                              # an interior window attends everywhere
+    x = torch.arange(2 * 16 * 24 * 3, dtype=torch.float32).view(2, 16, 24, 3)
+    assert torch.equal(DO._reverse(DO._partition(x, 8), 8, 16, 24), x)
+    idx = DO.relative_position_index(16)
+    assert tuple(idx.shape) == (256, 256) and int(idx.max()) == 31 * 31 - 1 and int(idx.min()) == 0
+    assert DO.flops_per_lr_pixel() > 2.0e7
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
+def test_oracle_matches_reference_class_at_another_size():
+    """Input resolution != the constructed one: the reference recomputes the shift mask (drct_arch.py:398-401)."""
+    code = (
+        "import sys, json, torch\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, '/root/reference')\n"
+        "from oracle import make_drct_golden as G, drct_oracle as DO\n"
+        "m, sd = G.build_reference(seed=9)\n"
+        "x = torch.rand(2, 3, 24, 8, generator=torch.Generator().manual_seed(5))\n"
+        "with torch.no_grad():\n"
+        "    a = m(x); b = DO.forward(sd, x)\n"
+        "print(json.dumps({'err': float((a - b).abs().max()), 'mean': float(a.mean())}))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env={**os.environ, "PYTHONDONTWRITEBYTECODE": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["err"] <= 2e-5, res
