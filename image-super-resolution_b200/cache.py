@@ -27,6 +27,7 @@ import queue
 import random
 import struct
 import threading
+import warnings
 from pathlib import Path
 from typing import Dict, Iterator, List, Optional, Sequence, Tuple
 
@@ -310,8 +311,9 @@ class ShardCache:
         o = self.data_start + self.header["offsets"][i]
         return self._bytes[o:o + rbytes]
 
-    def sample(self, i: int, load_features: bool = True) -> dict:
-        """Record i as host tensors in their stored dtypes (copies; the mapping is read-only)."""
+    def sample(self, i: int, load_features: bool = True, copy: bool = True) -> dict:
+        """Record i as host tensors in their stored dtypes.  ``copy=False`` returns read-only VIEWS of the mapping (for
+        callers that transform every tensor into a new one anyway); the default copies."""
         segs, _ = self.layout(i)
         rec = self.record(i)
         out = {"lr": None, "hr": None, "expert_imgs": {}, "expert_feats": {} if load_features else None,
@@ -320,7 +322,13 @@ class ShardCache:
             if key.startswith("feat.") and not load_features:
                 continue
             n = Cc * hh * ww * (2 if dt == "f16" else 4)
-            t = torch.from_numpy(rec[off:off + n].view(_NP[dt]).reshape(Cc, hh, ww).copy())
+            arr = rec[off:off + n].view(_NP[dt]).reshape(Cc, hh, ww)
+            if copy:
+                t = torch.from_numpy(arr.copy())
+            else:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore", UserWarning)         # "array is not writable": it is never written
+                    t = torch.from_numpy(arr)
             if key in ("lr", "hr"):
                 out[key] = t
             elif key.startswith("img."):
@@ -355,25 +363,34 @@ class ShardDataset(torch.utils.data.Dataset):
         return self.cache.count * self.repeat_factor
 
     def __getitem__(self, idx: int) -> dict:
-        s = self.cache.sample(idx % self.cache.count, self.load_features)
-        up = (lambda k, t: t.float()) if self._upcast_all else (lambda k, t: t.float() if k == "mamba" else t)
-        lr, hr = s["lr"], s["hr"]
-        imgs = {k: up(k, v) for k, v in s["expert_imgs"].items()}
-        feats = {k: up(k, v) for k, v in s["expert_feats"].items()} if s["expert_feats"] is not None else None
+        # every returned tensor is produced by exactly ONE pass over its bytes: views of the mapping go through a single
+        # fused flip (+ transpose) / up-cast / clone, instead of copy -> flip -> flip -> rot90 (each a full copy)
+        s = self.cache.sample(idx % self.cache.count, self.load_features, copy=False)
+        code = 0
         if self.augment:
             hflip = random.random() < 0.5                    # the reference's three draws, in its order (:262-264)
             vflip = random.random() < 0.5
             rot_k = random.randint(0, 3)
+            code = dihedral_code(hflip, vflip, rot_k)
+        tr, fy, fx = bool(code & 1), bool(code & 2), bool(code & 4)
 
-            def tf(t):
-                if hflip:
-                    t = torch.flip(t, dims=[-1])
-                if vflip:
-                    t = torch.flip(t, dims=[-2])
-                return torch.rot90(t, k=rot_k, dims=[-2, -1]) if rot_k > 0 else t
-            lr, hr = tf(lr), (tf(hr) if hr is not None else None)
-            imgs = {k: tf(v) for k, v in imgs.items()}
-            feats = {k: tf(v) for k, v in feats.items()} if feats is not None else None
+        def tf(t, up):
+            # out = T?(flip_rows_if_fy(flip_cols_if_fx(t)))  ==  flip(t.T, rows if fx, cols if fy) when transposed
+            v = t.transpose(-1, -2) if tr else t
+            dims = [d for d, f in ((-2, fx if tr else fy), (-1, fy if tr else fx)) if f]
+            if dims:
+                v = torch.flip(v, dims)
+                v = v.float() if (up and v.dtype != torch.float32) else v
+                return v.contiguous()
+            if up and v.dtype != torch.float32:
+                return v.float().contiguous()
+            return v.contiguous().clone() if v.is_contiguous() else v.contiguous()
+        lr = tf(s["lr"], False)                              # lr / hr keep their stored dtype, as in the reference
+        hr = tf(s["hr"], False) if s["hr"] is not None else None
+        imgs = {k: tf(v, self._upcast_all or k == "mamba") for k, v in s["expert_imgs"].items()}
+        feats = None
+        if s["expert_feats"] is not None:
+            feats = {k: tf(v, self._upcast_all or k == "mamba") for k, v in s["expert_feats"].items()}
         out = {"lr": lr, "hr": hr, "expert_imgs": imgs, "filename": s["filename"]}
         if hr is None:
             del out["hr"]
