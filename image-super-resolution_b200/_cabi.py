@@ -132,6 +132,8 @@ PROTOTYPES = {
     "ffsr_fft_lowpass_workspace_bytes": (_SZ, [_I, _I, _I]),
     "ffsr_fft_lowpass": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _SZ, _P, _P]),
     "ffsr_fft_lowpass_backward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _SZ, _P, _P]),
+    # ---- DRCT-L window attention (N1: first kernel of the expert forward) ----
+    "ffsr_window_attention": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     # ---- cache-shard collate ----
     "ffsr_cache_unpack": (_I, [_P, _SZ, _I, _P, _I, _P, _I, _P]),
     "ffsr_cache_segment_size": (_I, []),

@@ -360,6 +360,15 @@ int ffsr_cache_segment_size(void); /* sizeof(ffsr_cache_segment), for binding la
 int ffsr_cache_unpack(const void* records, size_t record_bytes, int B, const ffsr_cache_segment* segs, int nseg,
                       const int* tf_codes, int sm_count, cudaStream_t stream);
 
+/* (Shifted-)window multi-head attention of the DRCT-L expert (src/models/drct/drct_arch.py:175-206,
+ * 385-412): everything between the qkv and the proj Linear of one SwinTransformerBlock -- cyclic shift, window
+ * partition, q k^T / sqrt(dh) + relative-position bias (+ the -100 shift mask), softmax, attn @ v, window merge and
+ * reverse shift.  qkv: [B][H][W][3*C] channels-last with channel = which*C + head*dh + d; out: [B][H][W][C] at the
+ * un-shifted pixel; bias_table: [(2*window-1)^2][heads] fp32.  H, W multiples of window (callers pad), window^2 <= 256,
+ * dh <= 128.  First CUDA-core version (parity-tested on a B200; not yet timed or used by a product path). */
+int ffsr_window_attention(const void* qkv, int B, int H, int W, int C, int heads, int window, int shift,
+                          const float* bias_table, void* out, int dtype, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
