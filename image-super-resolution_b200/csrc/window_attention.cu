@@ -1,8 +1,8 @@
 // (Shifted-)window multi-head attention of the DRCT-L expert -- FIRST, CUDA-core version.
 //
 // STATUS: parity-green on a B200 for every (dim, heads) pair of DRCT-L, shifted and not (tests/test_gpu_drct.py: fp32
-// <= 2e-5, bf16 <= 2e-2 against the torch restatement of the reference block); not yet timed, and nothing in the
-// product path calls it yet -- the rest of the expert forward (N1) is the next round's work.
+// <= 2e-5, bf16 <= 2e-2 against the torch restatement of the reference block) and inside isr_b200.drct.DRCT.forward;
+// not yet timed -- a tcgen05 version of the two products is the next step.
 //
 // Replaces, for one SwinTransformerBlock, everything between the qkv Linear and the proj Linear
 // (src/models/drct/drct_arch.py:175-206 and 385-412): cyclic shift, window partition, q k^T / sqrt(dh) + relative

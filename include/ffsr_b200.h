@@ -365,9 +365,25 @@ int ffsr_cache_unpack(const void* records, size_t record_bytes, int B, const ffs
  * partition, q k^T / sqrt(dh) + relative-position bias (+ the -100 shift mask), softmax, attn @ v, window merge and
  * reverse shift.  qkv: [B][H][W][3*C] channels-last with channel = which*C + head*dh + d; out: [B][H][W][C] at the
  * un-shifted pixel; bias_table: [(2*window-1)^2][heads] fp32.  H, W multiples of window (callers pad), window^2 <= 256,
- * dh <= 128.  First CUDA-core version (parity-tested on a B200; not yet timed or used by a product path). */
+ * dh <= 128.  First CUDA-core version (parity-tested on a B200, used by isr_b200.drct; not yet timed). */
 int ffsr_window_attention(const void* qkv, int B, int H, int W, int C, int heads, int window, int shift,
                           const float* bias_table, void* out, int dtype, cudaStream_t stream);
+
+/* Small ops of the DRCT-L expert forward (src/models/drct/drct_arch.py), used by isr_b200.drct.
+ *   layernorm_strided : nn.LayerNorm(C) (eps 1e-5) over the first C channels of rows with pitch x_pitch (:292-299, the
+ *                       dense-growth buffer of an RDG; :769 final norm)
+ *   leaky_relu        : in place on a channel slice (rows x C at `pitch`)  (:283, slope 0.2; :728, slope 0.01)
+ *   pixel_shuffle2    : nn.PixelShuffle(2) on channels-last data, x [B][H][W][4C] -> y [B][2H][2W][C]  (:612-614)
+ *   rgb_shift_in/out  : (x - mean) * img_range from planar fp32 [B][3][H][W] into channels-last rows of `pitch`
+ *                       channels, and back (x / img_range + mean) (:778-779, :787); mean3_host is a HOST array of 3 */
+int ffsr_layernorm_strided(const void* x, long rows, int C, long x_pitch, const float* w, const float* b, void* y,
+                           long y_pitch, int in_dtype, int out_dtype, cudaStream_t stream);
+int ffsr_leaky_relu(void* x, long rows, int C, long pitch, float slope, int dtype, cudaStream_t stream);
+int ffsr_pixel_shuffle2(const void* x, int B, int H, int W, int C, void* y, int dtype, cudaStream_t stream);
+int ffsr_rgb_shift_in(const float* x, int B, int H, int W, const float* mean3_host, float range, void* y, int pitch, int dtype,
+                      cudaStream_t stream);
+int ffsr_rgb_shift_out(const void* x, int B, int H, int W, int pitch, const float* mean3_host, float range, float* y, int dtype,
+                       cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -70,3 +70,31 @@ def test_oracle_matches_reference_class_at_another_size():
     assert r.returncode == 0, r.stderr[-2000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
     assert res["err"] <= 2e-5, res
+
+
+def test_module_mirror_has_the_reference_state_layout():
+    """isr_b200.drct.DRCT (parameter holders of the WIP sm_100a expert) against the reference layout restated in the oracle,
+    itself checked against create_drct_model(): names, shapes, order; strict load of a synthesised checkpoint."""
+    import isr_b200  # noqa: F401
+    from isr_b200 import drct as D
+    g = np.load(GOLD)
+    cfg = json.loads(str(g["cfg"]))
+    small = D.DRCT(img_size=cfg["img_size"], window_size=cfg["window"], embed_dim=cfg["embed_dim"], depths=[6] * cfg["n_rdg"],
+                   num_heads=[cfg["num_heads"]] * cfg["n_rdg"], mlp_ratio=cfg["mlp_ratio"])
+    want = [(k, s) for k, (s, _) in DO.state_shapes(**cfg).items()]
+    assert [(k, tuple(v.shape)) for k, v in small.state_dict().items()] == want
+    sd = DO.synth_state_dict(DO.state_shapes(**cfg), seed=1, img_size=cfg["img_size"])
+    small.load_state_dict(sd, strict=True)
+    for k, v in small.state_dict().items():                       # our index / mask buffers equal the reference's
+        if DO.state_shapes(**cfg)[k][1] != "float":
+            assert torch.equal(v.float(), sd[k].float()), k
+    full = D.create_drct_model()
+    assert [(k, tuple(v.shape)) for k, v in full.state_dict().items()] == [(k, s) for k, (s, _) in DO.state_shapes().items()]
+    assert abs(D.flops_per_lr_pixel(full) - DO.flops_per_lr_pixel()) < 1.0
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        full(torch.zeros(1, 3, 16, 16))
+    if torch.cuda.is_available():
+        with pytest.raises(ValueError, match="multiples of the window"):
+            full.cuda()(torch.zeros(1, 3, 20, 16, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        D.DRCT(upsampler="nearest+conv")

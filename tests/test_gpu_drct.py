@@ -93,3 +93,28 @@ def test_window_attention_matches_the_reference_block(Cc, heads, ws, dtype):
         want = expected_attention(qd.float().cpu(), heads, ws, shift, table)
         err = float((out.float().cpu() - want).abs().max())
         assert err <= (2e-2 if dtype == "bf16" else 2e-5), (Cc, heads, ws, shift, err)
+
+
+@pytest.mark.gpu
+def test_drct_forward_matches_oracle():
+    """isr_b200.drct.DRCT.forward (fp32, C ABI kernels) against oracle/drct_oracle.py on the reduced configuration of the
+    golden (2 RDGs, window 8, all DRCT-L channel counts), synthesised weights, a 16x24 input (shifted windows, 2x3 grid)."""
+    import json
+    import numpy as np
+    from isr_b200 import drct as D
+    g = np.load(os.path.join(ROOT, "tests", "golden", "drct_small.npz"))
+    cfg = json.loads(str(g["cfg"]))
+    m = D.DRCT(img_size=cfg["img_size"], window_size=cfg["window"], embed_dim=cfg["embed_dim"], depths=[6] * cfg["n_rdg"],
+               num_heads=[cfg["num_heads"]] * cfg["n_rdg"], mlp_ratio=cfg["mlp_ratio"])
+    sd = DO.synth_state_dict(DO.state_shapes(**cfg), seed=int(g["seed"]), img_size=cfg["img_size"])
+    m.load_state_dict(sd, strict=True)
+    dev = torch.device("cuda:0")
+    m.to(dev).eval()
+    x = torch.from_numpy(g["x"])
+    y = m(x.to(dev))
+    torch.cuda.synchronize()
+    assert float((y.cpu() - torch.from_numpy(g["y"])).abs().max()) <= 1e-4           # the reference class's own output
+    with torch.no_grad():
+        want, feat = DO.forward(sd, x, return_feature=True)
+    assert float((y.cpu() - want).abs().max()) <= 1e-4
+    assert float((m.last_feature.cpu() - feat).abs().max()) <= 1e-4
