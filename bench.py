@@ -538,6 +538,60 @@ def run_tiled(args):
         _leave(world)
 
 
+def run_drct(args):
+    """`--workload n1`: the DRCT-L expert forward on one C3-sized LR image padded to the window
+    (352x512), fp32 first version, against the same algorithm as PyTorch eager ops on the same GPU (the oracle's
+    restatement).  Not a headline line: N=1 only, reports HR MPix/s of the x4 output and algorithmic TFLOP/s."""
+    import torch
+    from isr_b200 import drct as D
+    from oracle import drct_oracle as DO
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"workload": "n1", "unavailable": "single-GPU measurement only"}), flush=True)
+        return
+    dev = torch.device("cuda", 0)
+    H, W = (352, 512) if tuple(args.lr) == (LR_H, LR_W) else tuple(args.lr)
+    torch.manual_seed(0)
+    m = D.create_drct_model().to(dev).eval()
+    x = torch.rand(1, 3, H, W, generator=torch.Generator().manual_seed(1234)).to(dev)
+    warmup, steps = max(args.warmup, 3), args.steps
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = timed(lambda: m(x))
+    clocks = sampler.stop()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ms_eager = timed(lambda: DO.forward(sd, x))
+        err = float((m(x) - DO.forward(sd, x)).abs().max())
+    flop = D.flops_per_lr_pixel(m) * H * W
+    tensor_peak, hbm_peak, peak_src = _peaks()
+    print(json.dumps({
+        "metric": "drct_forward_hr_mpix_per_s", "value": 16 * H * W / 1e6 / (ms * 1e-3), "unit": "HR MPix/s", "n_gpus": 1,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "N1 DRCT-L x4 expert forward, one LR image padded to the 16-px window, random-init weights",
+                   "lr": [H, W], "precision": "fp32 (CUDA-core convs; tcgen05 path not built)"},
+        "tflops_algorithmic": flop / (ms * 1e-3) / 1e12, "tensor_peak": tensor_peak, "peak_source": peak_src,
+        "gpu_eager_baseline": {"value": 16 * H * W / 1e6 / (ms_eager * 1e-3), "unit": "HR MPix/s", "ms_per_image": ms_eager,
+                               "kind": "port: oracle restatement in PyTorch eager on the same GPU"},
+        "max_abs_vs_eager": err, "clocks": clocks}), flush=True)
+
+
 def train_config(workload, patches, B, hw, precision):
     return {"workload": f"{workload.upper()} fusion training step (BASELINE configs[{1 if workload == 'c2' else 3}]): "
                         f"global batch {patches} x {hw}x{hw} LR patches, losses {STAGE_WEIGHTS[workload]}, "
@@ -549,7 +603,7 @@ def train_config(workload, patches, B, hw, precision):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c3t"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c3t", "n1"],
                     help="c3: full-res inference (headline, default); c2 / c4: training steps (BASELINE configs[1] / [3])")
     ap.add_argument("--batch", type=int, default=0, help="override the global batch of a training workload")
     ap.add_argument("--gpus", type=int, default=1)
@@ -566,6 +620,8 @@ def main():
         return run_reference(args)
     if args.workload == "c3t":
         return run_tiled(args)
+    if args.workload == "n1":
+        return run_drct(args)
     if args.workload != "c3":
         return run_train(args)
 
