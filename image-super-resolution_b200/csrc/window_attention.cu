@@ -41,16 +41,18 @@ __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return
 // region index of the shift mask (calculate_mask, drct_arch.py:353-374) along one axis of the SHIFTED frame
 __device__ __forceinline__ int mask_region(int p, int n, int ws, int shift) { return p < n - ws ? 0 : (p < n - shift ? 1 : 2); }
 
-// T: tensor element type; TS: shared-memory storage type of K / V (float, or bf16 when T is bf16 and fp32 would not fit)
-template <typename T, typename TS>
+// T: tensor element type; TS: shared-memory storage type of K / V (float, or bf16 when T is bf16 and fp32 would not fit).
+// VGLOBAL: only K is staged and V is read from global memory / L2 in the p.V loop -- the fp32 fallback for the one shape
+// whose fp32 K + V exceed shared memory (DRCT-L swin3: 256 tokens x head dim 122 = 2 x 126 KB).
+template <typename T, typename TS, bool VGLOBAL = false>
 __global__ void __launch_bounds__(WA_THREADS) k_window_attn(const T* __restrict__ qkv, int B, int H, int W, int C, int heads, int ws,
                                                             int shift, const float* __restrict__ table, T* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char wa_smem[];
   const int N = ws * ws, dh = C / heads;
   const int P = dh | 1;                                        // odd pitch: lanes reading one column hit distinct banks
   TS* Ks = reinterpret_cast<TS*>(wa_smem);
-  TS* Vs = Ks + (size_t)N * P;
-  float* qs = reinterpret_cast<float*>(wa_smem + (((size_t)2 * N * P * sizeof(TS) + 15) & ~(size_t)15));   // [8][WA_MAXD]
+  TS* Vs = Ks + (size_t)N * P;                                 // (unused when VGLOBAL)
+  float* qs = reinterpret_cast<float*>(wa_smem + (((size_t)(VGLOBAL ? 1 : 2) * N * P * sizeof(TS) + 15) & ~(size_t)15));   // [8][WA_MAXD]
   int* pix = reinterpret_cast<int*>(qs + 8 * WA_MAXD);         // [N] original pixel index y*W + x of token t
   unsigned char* rid = reinterpret_cast<unsigned char*>(pix + N);   // [N] mask region of token t
 
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(WA_THREADS) k_window_attn(const T* __restrict_
     const int t = i / dh, d = i - t * dh;
     const T* src = qkv + (img + pix[t]) * (size_t)(3 * C) + h * dh + d;
     Ks[t * P + d] = from_f<TS>(to_f<T>(src[C]));
-    Vs[t * P + d] = from_f<TS>(to_f<T>(src[2 * C]));
+    if (!VGLOBAL) Vs[t * P + d] = from_f<TS>(to_f<T>(src[2 * C]));
   }
   __syncthreads();
 
@@ -127,11 +129,20 @@ __global__ void __launch_bounds__(WA_THREADS) k_window_attn(const T* __restrict_
           const float pj = __shfl_sync(0xffffffffu, s[kk], l);
           const int j = l + 32 * kk;
           if (j < N) {
-            const TS* vr = Vs + j * P;
+            if (VGLOBAL) {
+              const T* vg = qkv + (img + pix[j]) * (size_t)(3 * C) + 2 * C + h * dh;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int d = lane + 32 * m;
-              if (d < dh) acc[m] = fmaf(pj, to_f<TS>(vr[d]), acc[m]);
+              for (int m = 0; m < 4; ++m) {
+                const int d = lane + 32 * m;
+                if (d < dh) acc[m] = fmaf(pj, to_f<T>(vg[d]), acc[m]);
+              }
+            } else {
+              const TS* vr = Vs + j * P;
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {
+                const int d = lane + 32 * m;
+                if (d < dh) acc[m] = fmaf(pj, to_f<TS>(vr[d]), acc[m]);
+              }
             }
           }
         }
@@ -146,9 +157,9 @@ __global__ void __launch_bounds__(WA_THREADS) k_window_attn(const T* __restrict_
   }
 }
 
-size_t wa_smem_bytes(int N, int dh, size_t esz) {
+size_t wa_smem_bytes(int N, int dh, size_t esz, int copies = 2) {
   const size_t P = (size_t)(dh | 1);
-  return ((2 * (size_t)N * P * esz + 15) & ~(size_t)15) + 8 * WA_MAXD * sizeof(float) + (size_t)N * sizeof(int) + (size_t)N + 16;
+  return (((size_t)copies * N * P * esz + 15) & ~(size_t)15) + 8 * WA_MAXD * sizeof(float) + (size_t)N * sizeof(int) + (size_t)N + 16;
 }
 
 }  // namespace
@@ -179,11 +190,19 @@ extern "C" int ffsr_window_attention(const void* qkv, int B, int H, int W, int C
       k<<<grid, WA_THREADS, s16, stream>>>((const __nv_bfloat16*)qkv, B, H, W, C, heads, window, shift, bias_table, (__nv_bfloat16*)out);
     }
   } else {
-    FFSR_REQUIRE(s32 <= limit, FFSR_ERR_ARG,
-                 "window_attention: fp32 K/V of a %d-token window x head dim %d need %zu B of shared memory (> %zu): use bf16", N, dh, s32, limit);
-    auto k = k_window_attn<float, float>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s32);
-    k<<<grid, WA_THREADS, s32, stream>>>((const float*)qkv, B, H, W, C, heads, window, shift, bias_table, (float*)out);
+    if (s32 <= limit) {
+      auto k = k_window_attn<float, float>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s32);
+      k<<<grid, WA_THREADS, s32, stream>>>((const float*)qkv, B, H, W, C, heads, window, shift, bias_table, (float*)out);
+    } else {
+      // fp32 K + V do not fit (DRCT-L swin3, head dim 122 at window 16): stage K only, read V through L2.
+      // NOT yet run on hardware (written after the round's GPU budget was spent); same arithmetic as the staged path.
+      const size_t s1 = wa_smem_bytes(N, dh, 4, 1);
+      FFSR_REQUIRE(s1 <= limit, FFSR_ERR_ARG, "window_attention: fp32 K of a %d-token window x head dim %d needs %zu B of shared memory (> %zu)", N, dh, s1, limit);
+      auto k = k_window_attn<float, float, true>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
+      k<<<grid, WA_THREADS, s1, stream>>>((const float*)qkv, B, H, W, C, heads, window, shift, bias_table, (float*)out);
+    }
   }
   return ffsr_check_launch("k_window_attn");
 }

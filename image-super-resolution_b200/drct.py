@@ -12,7 +12,9 @@ it: no concatenation is ever materialised (``drct_arch.py:292-299``).
 STATUS: parity-green on a B200 against the reference class's own output (``tests/golden/drct_small.npz``: 2 RDGs,
 window 8, every channel count / head rule of DRCT-L; <= 1e-4 on the SR image and on the cached feature) and, kernel by
 kernel, for the window attention at window 16 (``tests/test_gpu_drct.py``).  Every Linear / Conv2d still runs on the
-fp32 CUDA-core path: bf16 / tcgen05 execution, timing and the roofline comparison are the next round's work.
+fp32 CUDA-core path: bf16 / tcgen05 execution, timing and the roofline comparison are the next round's work.  One
+shape of the FULL DRCT-L configuration has not run on hardware: swin3 (dim 244, 2 heads, head dim 122) at window 16,
+whose fp32 K + V exceed shared memory and take the K-staged / V-through-L2 variant of the attention kernel.
 """
 from __future__ import annotations
 

@@ -68,13 +68,16 @@ def test_window_attention_rejects_bad_arguments():
     ]
     for a in bad:
         assert f(*a) == -1, a
-    assert f(4096, 1, 16, 16, 244, 2, 16, 8, 4096, 4096, K.DT_F32, None) == -1   # fp32 K/V of head dim 122 do not fit
     assert b"window_attention" in lib.ffsr_last_error()
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("Cc,heads,ws,dtype", [(180, 6, 16, "fp32"), (212, 4, 16, "fp32"), (244, 2, 16, "bf16"), (276, 6, 8, "fp32"),
-                                               (308, 4, 16, "bf16"), (60, 6, 8, "fp32")])
+                                               (308, 4, 16, "bf16"), (60, 6, 8, "fp32"),
+                                               # fp32 K + V of head dim 122 do not fit in shared memory: K staged, V read through
+                                               # L2 -- a path written after the GPU budget was spent, gated until it has run once
+                                               pytest.param(244, 2, 16, "fp32", marks=pytest.mark.skipif(
+                                                   os.environ.get("FFSR_RUN_WIP") != "1", reason="fp32 fallback for head dim 122 not yet run on hardware"))])
 def test_window_attention_matches_the_reference_block(Cc, heads, ws, dtype):
     dev = torch.device("cuda:0")
     lib = K.load()
