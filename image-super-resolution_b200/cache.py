@@ -298,6 +298,12 @@ class ShardCache:
         self.uniform = bool(self.header["uniform"])
         self._layouts: Dict[Tuple[int, int], tuple] = {}
 
+    def __getstate__(self):
+        return {"path": self.path}                     # DataLoader workers started by spawn re-open the mapping
+
+    def __setstate__(self, state):
+        self.__init__(state["path"])
+
     def layout(self, i: int):
         h, w = self.header["hw"][i]
         lay = self._layouts.get((h, w))

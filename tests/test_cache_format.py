@@ -218,3 +218,17 @@ def test_shard_writer_rejects_inconsistent_samples(tmp_path):
     assert c.count == 2 and c.header["has_mamba"] == [True, False]
     s1 = c.sample(1)
     assert float(s1["expert_imgs"]["mamba"].abs().max()) == 0.0 and torch.equal(s1["expert_imgs"]["drct"], imgs["drct"].half())
+
+
+def test_shard_dataset_survives_pickling_and_worker_processes(tmp_path):
+    """DataLoader workers: fork inherits the mapping, spawn pickles the dataset -- the cache re-opens itself."""
+    import pickle
+    d = tmp_path / "cache"
+    CO.write_mock_cache(d, n=4, lr_hw=(8, 8), seed=3)
+    ds = CA.ShardDataset(str(d), augment=False)
+    ds2 = pickle.loads(pickle.dumps(ds))
+    assert ds2.cache is not ds.cache and len(ds2) == 4
+    _same(ds2[2], ds[2])
+    dl = torch.utils.data.DataLoader(ds, batch_size=2, num_workers=2, multiprocessing_context="spawn")
+    names = [f for b in dl for f in b["filename"]]
+    assert names == ["img_000", "img_001", "img_002", "img_003"]
