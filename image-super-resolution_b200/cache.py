@@ -207,7 +207,8 @@ class ShardWriter:
                               for m in self.metas]
         hj = json.dumps(header).encode("utf-8")
         data_start = _round_up(len(MAGIC) + 8 + len(hj), _ALIGN_DATA)
-        with open(self.out_path, "wb") as f:
+        part = self.out_path + ".part"                 # written beside the target and renamed: readers never see half a shard
+        with open(part, "wb") as f:
             f.write(MAGIC)
             f.write(struct.pack("<Q", len(hj)))
             f.write(hj)
@@ -219,6 +220,7 @@ class ShardWriter:
                         break
                     f.write(chunk)
         os.remove(self._tmp)
+        os.replace(part, self.out_path)
         self.header = header
         return header
 
