@@ -134,6 +134,7 @@ PROTOTYPES = {
     "ffsr_fft_lowpass_backward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _SZ, _P, _P]),
     # ---- DRCT-L window attention (N1: first kernel of the expert forward) ----
     "ffsr_window_attention": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "ffsr_window_attention_pitched": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P]),
     "ffsr_layernorm_strided": (_I, [_P, _L, _I, _L, _P, _P, _P, _L, _I, _I, _P]),
     "ffsr_leaky_relu": (_I, [_P, _L, _I, _L, _F, _I, _P]),
     "ffsr_pixel_shuffle2": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),

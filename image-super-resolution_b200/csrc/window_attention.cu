@@ -44,9 +44,15 @@ __device__ __forceinline__ int mask_region(int p, int n, int ws, int shift) { re
 // T: tensor element type; TS: shared-memory storage type of K / V (float, or bf16 when T is bf16 and fp32 would not fit).
 // VGLOBAL: only K is staged and V is read from global memory / L2 in the p.V loop -- the fp32 fallback for the one shape
 // whose fp32 K + V exceed shared memory (DRCT-L swin3: 256 tokens x head dim 122 = 2 x 126 KB).
-template <typename T, typename TS, bool VGLOBAL = false>
+// PITCHED: token rows of qkv / out have pitches qp / op (elements) instead of 3*C / C -- bf16 buffers of the DRCT channel
+// counts (all 4 mod 8) are padded to a multiple of 8 channels for the 16-byte TMA stride rule of the tcgen05 Linears.
+// The two trailing parameters are ignored otherwise (kept last so the un-pitched instantiations compile to the same code).
+template <typename T, typename TS, bool VGLOBAL = false, bool PITCHED = false>
 __global__ void __launch_bounds__(WA_THREADS) k_window_attn(const T* __restrict__ qkv, int B, int H, int W, int C, int heads, int ws,
-                                                            int shift, const float* __restrict__ table, T* __restrict__ out) {
+                                                            int shift, const float* __restrict__ table, T* __restrict__ out,
+                                                            long qp_arg, long op_arg) {
+#define WA_QP (PITCHED ? (size_t)qp_arg : (size_t)(3 * C))
+#define WA_OP (PITCHED ? (size_t)op_arg : (size_t)C)
   extern __shared__ __align__(16) unsigned char wa_smem[];
   const int N = ws * ws, dh = C / heads;
   const int P = dh | 1;                                        // odd pitch: lanes reading one column hit distinct banks
@@ -76,7 +82,7 @@ __global__ void __launch_bounds__(WA_THREADS) k_window_attn(const T* __restrict_
   const size_t img = (size_t)b * H * W;
   for (int i = tid; i < N * dh; i += WA_THREADS) {
     const int t = i / dh, d = i - t * dh;
-    const T* src = qkv + (img + pix[t]) * (size_t)(3 * C) + h * dh + d;
+    const T* src = qkv + (img + pix[t]) * WA_QP + h * dh + d;
     Ks[t * P + d] = from_f<TS>(to_f<T>(src[C]));
     if (!VGLOBAL) Vs[t * P + d] = from_f<TS>(to_f<T>(src[2 * C]));
   }
@@ -86,7 +92,7 @@ __global__ void __launch_bounds__(WA_THREADS) k_window_attn(const T* __restrict_
   float* q = qs + warp * WA_MAXD;
   const int nk = (N + 31) >> 5;                                // key slots per lane (<= 8)
   for (int tq = warp; tq < N; tq += WA_THREADS / 32) {
-    const T* qsrc = qkv + (img + pix[tq]) * (size_t)(3 * C) + h * dh;
+    const T* qsrc = qkv + (img + pix[tq]) * WA_QP + h * dh;
     __syncwarp();
     for (int d = lane; d < dh; d += 32) q[d] = to_f<T>(qsrc[d]) * scale;
     __syncwarp();
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(WA_THREADS) k_window_attn(const T* __restrict_
           const int j = l + 32 * kk;
           if (j < N) {
             if (VGLOBAL) {
-              const T* vg = qkv + (img + pix[j]) * (size_t)(3 * C) + 2 * C + h * dh;
+              const T* vg = qkv + (img + pix[j]) * WA_QP + 2 * C + h * dh;
 #pragma unroll
               for (int m = 0; m < 4; ++m) {
                 const int d = lane + 32 * m;
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(WA_THREADS) k_window_attn(const T* __restrict_
         }
       }
     }
-    T* dst = out + (img + pix[tq]) * (size_t)C + h * dh;
+    T* dst = out + (img + pix[tq]) * WA_OP + h * dh;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       const int d = lane + 32 * m;
@@ -156,6 +162,9 @@ __global__ void __launch_bounds__(WA_THREADS) k_window_attn(const T* __restrict_
     }
   }
 }
+
+#undef WA_QP
+#undef WA_OP
 
 size_t wa_smem_bytes(int N, int dh, size_t esz, int copies = 2) {
   const size_t P = (size_t)(dh | 1);
@@ -182,18 +191,18 @@ extern "C" int ffsr_window_attention(const void* qkv, int B, int H, int W, int C
     if (s32 <= limit) {
       auto k = k_window_attn<__nv_bfloat16, float>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s32);
-      k<<<grid, WA_THREADS, s32, stream>>>((const __nv_bfloat16*)qkv, B, H, W, C, heads, window, shift, bias_table, (__nv_bfloat16*)out);
+      k<<<grid, WA_THREADS, s32, stream>>>((const __nv_bfloat16*)qkv, B, H, W, C, heads, window, shift, bias_table, (__nv_bfloat16*)out, 0L, 0L);
     } else {
       FFSR_REQUIRE(s16 <= limit, FFSR_ERR_ARG, "window_attention: K/V of a %d-token window x head dim %d do not fit in shared memory", N, dh);
       auto k = k_window_attn<__nv_bfloat16, __nv_bfloat16>;      // K / V are bf16 values already: storing them as bf16 is exact
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s16);
-      k<<<grid, WA_THREADS, s16, stream>>>((const __nv_bfloat16*)qkv, B, H, W, C, heads, window, shift, bias_table, (__nv_bfloat16*)out);
+      k<<<grid, WA_THREADS, s16, stream>>>((const __nv_bfloat16*)qkv, B, H, W, C, heads, window, shift, bias_table, (__nv_bfloat16*)out, 0L, 0L);
     }
   } else {
     if (s32 <= limit) {
       auto k = k_window_attn<float, float>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s32);
-      k<<<grid, WA_THREADS, s32, stream>>>((const float*)qkv, B, H, W, C, heads, window, shift, bias_table, (float*)out);
+      k<<<grid, WA_THREADS, s32, stream>>>((const float*)qkv, B, H, W, C, heads, window, shift, bias_table, (float*)out, 0L, 0L);
     } else {
       // fp32 K + V do not fit (DRCT-L swin3, head dim 122 at window 16): stage K only, read V through L2.
       // NOT yet run on hardware (written after the round's GPU budget was spent); same arithmetic as the staged path.
@@ -201,8 +210,35 @@ extern "C" int ffsr_window_attention(const void* qkv, int B, int H, int W, int C
       FFSR_REQUIRE(s1 <= limit, FFSR_ERR_ARG, "window_attention: fp32 K of a %d-token window x head dim %d needs %zu B of shared memory (> %zu)", N, dh, s1, limit);
       auto k = k_window_attn<float, float, true>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
-      k<<<grid, WA_THREADS, s1, stream>>>((const float*)qkv, B, H, W, C, heads, window, shift, bias_table, (float*)out);
+      k<<<grid, WA_THREADS, s1, stream>>>((const float*)qkv, B, H, W, C, heads, window, shift, bias_table, (float*)out, 0L, 0L);
     }
   }
   return ffsr_check_launch("k_window_attn");
+}
+
+// Same operation on PADDED rows: qkv rows of pitch qkv_pitch >= 3*C, out rows of pitch out_pitch >= C (elements).  bf16 only
+// (the layout exists for the tcgen05 Linears around it).  NOT yet run on hardware: its caller (isr_b200.drct, precision
+// "bf16") and its test are gated behind FFSR_RUN_WIP=1.
+extern "C" int ffsr_window_attention_pitched(const void* qkv, long qkv_pitch, int B, int H, int W, int C, int heads, int window, int shift,
+                                             const float* bias_table, void* out, long out_pitch, cudaStream_t stream) {
+  FFSR_REQUIRE(qkv && out && bias_table, FFSR_ERR_ARG, "window_attention_pitched: null pointer");
+  FFSR_REQUIRE(B > 0 && H > 0 && W > 0 && heads > 0 && C > 0 && C % heads == 0 && qkv_pitch >= 3L * C && out_pitch >= C, FFSR_ERR_ARG,
+               "window_attention_pitched: B=%d H=%d W=%d C=%d heads=%d pitches %ld / %ld", B, H, W, C, heads, qkv_pitch, out_pitch);
+  FFSR_REQUIRE(window > 0 && window * window <= WA_MAXN && H % window == 0 && W % window == 0 && shift >= 0 && shift < window &&
+                   C / heads <= WA_MAXD, FFSR_ERR_ARG, "window_attention_pitched: window %d shift %d head dim %d", window, shift, C / heads);
+  const int N = window * window, dh = C / heads;
+  const size_t limit = 227 * 1024;
+  const dim3 grid((unsigned)((long)B * (H / window) * (W / window)), (unsigned)heads);
+  const size_t s32 = wa_smem_bytes(N, dh, 4), s16 = wa_smem_bytes(N, dh, 2);
+  if (s32 <= limit) {
+    auto k = k_window_attn<__nv_bfloat16, float, false, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s32);
+    k<<<grid, WA_THREADS, s32, stream>>>((const __nv_bfloat16*)qkv, B, H, W, C, heads, window, shift, bias_table, (__nv_bfloat16*)out, qkv_pitch, out_pitch);
+  } else {
+    FFSR_REQUIRE(s16 <= limit, FFSR_ERR_ARG, "window_attention_pitched: K/V of a %d-token window x head dim %d do not fit in shared memory", N, dh);
+    auto k = k_window_attn<__nv_bfloat16, __nv_bfloat16, false, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s16);
+    k<<<grid, WA_THREADS, s16, stream>>>((const __nv_bfloat16*)qkv, B, H, W, C, heads, window, shift, bias_table, (__nv_bfloat16*)out, qkv_pitch, out_pitch);
+  }
+  return ffsr_check_launch("k_window_attn(pitched)");
 }

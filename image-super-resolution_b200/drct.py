@@ -19,13 +19,14 @@ whose fp32 K + V exceed shared memory and take the K-staged / V-through-L2 varia
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn as nn
 
 from . import _cabi as K
-from .pipeline import _View, _pack_conv, _pack_linear, nhwc
+from .pipeline import _View, _pack_conv, _pack_linear, _pack_tc, nhwc
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)          # drct_arch.py:665-666
 
@@ -120,6 +121,10 @@ class DRCT(nn.Module):
         self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, 64, 3, 1, 1), nn.LeakyReLU(inplace=True))
         self.upsample = nn.Sequential(nn.Conv2d(64, 256, 3, 1, 1), nn.PixelShuffle(2), nn.Conv2d(64, 256, 3, 1, 1), nn.PixelShuffle(2))
         self.conv_last = nn.Conv2d(64, 3, 3, 1, 1)
+        # "fp32": every Linear / Conv2d on the CUDA-core path (validated).  "bf16": LayerNorm outputs, qkv, attention output and
+        # the MLP hidden activations are bf16 rows padded to 8 channels and the Linears run on tcgen05; the residual stream
+        # stays fp32.  The bf16 mode was written after the round's GPU budget was spent: gated behind FFSR_RUN_WIP=1.
+        self.precision = "fp32"
         self._packed: Optional[Tuple] = None
         self._ws: Dict[Tuple, torch.Tensor] = {}
         self.last_feature: Optional[torch.Tensor] = None     # conv_after_body output of the last forward ([B,180,H,W] view)
@@ -146,10 +151,10 @@ class DRCT(nn.Module):
         self._packed = (key, w)
         return w
 
-    def _buf(self, name, shape, dev):
-        t = self._ws.get((name, tuple(shape), str(dev)))
+    def _buf(self, name, shape, dev, dtype=torch.float32):
+        t = self._ws.get((name, tuple(shape), str(dev), dtype))
         if t is None:
-            t = self._ws[(name, tuple(shape), str(dev))] = torch.zeros(shape, device=dev, dtype=torch.float32)
+            t = self._ws[(name, tuple(shape), str(dev), dtype)] = torch.zeros(shape, device=dev, dtype=dtype)
         return t
 
     # ---------------------------------------------------------------------------------- forward
@@ -157,6 +162,11 @@ class DRCT(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
             raise RuntimeError("DRCT (sm_100a build) needs CUDA tensors: there is no CPU path")
+        if self.precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision!r}")
+        lp = self.precision == "bf16"
+        if lp and os.environ.get("FFSR_RUN_WIP") != "1":
+            raise NotImplementedError("DRCT precision='bf16' (tcgen05 Linears) has not run on hardware yet; set FFSR_RUN_WIP=1 to try it")
         B, Cc, H, W = x.shape
         ws = self.window_size
         if Cc != 3 or H % ws or W % ws:
@@ -177,11 +187,19 @@ class DRCT(nn.Module):
             p = K.ConvParams()
             p.inp, p.in_sN, p.in_sY, p.in_sX, p.in_sC = xv.ptr, xv.sN, xv.sY, xv.sX, xv.sC
             p.N, p.H, p.W, p.Cin, p.Cout, p.ksize = B, h, wd, cin, cout, ks
-            p.w, p.bias, p.groups = w[name].data_ptr(), w[name + ".b"].data_ptr(), 1
+            wt = w[name]
+            if xv.t.dtype == torch.bfloat16:                   # tcgen05 path: K-major bf16 weights, packed on first use
+                wt = w.get(name + ".tc")
+                if wt is None:
+                    wt = w[name + ".tc"] = _pack_tc(w[name])
+                p.w_dtype, p.in_dtype = K.DT_BF16, K.DT_BF16
+            p.w, p.bias, p.groups = wt.data_ptr(), w[name + ".b"].data_ptr(), 1
             p.out, p.out_sN, p.out_sY, p.out_sX = out.ptr, out.sN, out.sY, out.sX
+            p.out_dtype = K.DT_BF16 if out.t.dtype == torch.bfloat16 else K.DT_F32
             p.act, p.epi = act, (K.EPI_RESIDUAL if r1 is not None else K.EPI_PLAIN)
             if r1 is not None:
                 p.r1, p.r1_sN, p.r1_sY, p.r1_sX = r1.ptr, r1.sN, r1.sY, r1.sX
+                p.r1_dtype = K.DT_BF16 if r1.t.dtype == torch.bfloat16 else K.DT_F32
             p.sa, p.sb = sa, 1.0
             call(lib.ffsr_conv2d, C.byref(p), S)
 
@@ -203,22 +221,30 @@ class DRCT(nn.Module):
                 sw: _Swin = getattr(rdg, f"swin{j + 1}")
                 d, p = sw.dim, f"layers.{i}.swin{j + 1}"
                 hid = sw.mlp.fc1.out_features
-                n1 = self._buf("n", (B, H, W, d), dev)
+                adt = torch.bfloat16 if lp else torch.float32
+                ADT = K.DT_BF16 if lp else K.DT_F32
+                pad = (lambda c: (c + 7) // 8 * 8) if lp else (lambda c: c)     # bf16 rows: 16-byte pitch for the TMA loads
+                n1 = self._buf("n", (B, H, W, pad(d)), dev, adt)
                 call(lib.ffsr_layernorm_strided, G.data_ptr(), NP, d, GW, w[p + ".norm1.w"].data_ptr(), w[p + ".norm1.b"].data_ptr(),
-                     n1.data_ptr(), d, K.DT_F32, K.DT_F32, S)
-                qkv = self._buf("qkv", (B, H, W, 3 * d), dev)
+                     n1.data_ptr(), pad(d), K.DT_F32, ADT, S)
+                qkv = self._buf("qkv", (B, H, W, pad(3 * d)), dev, adt)
                 conv(nhwc(n1), H, W, d, p + ".attn.qkv", 3 * d, 1, nhwc(qkv))
-                att = self._buf("att", (B, H, W, d), dev)
-                call(lib.ffsr_window_attention, qkv.data_ptr(), B, H, W, d, sw.heads, ws, ws // 2 if j % 2 else 0,
-                     w[p + ".attn.table"].data_ptr(), att.data_ptr(), K.DT_F32, S)
+                att = self._buf("att", (B, H, W, pad(d)), dev, adt)
+                shift = ws // 2 if j % 2 else 0
+                if lp:
+                    call(lib.ffsr_window_attention_pitched, qkv.data_ptr(), pad(3 * d), B, H, W, d, sw.heads, ws, shift,
+                         w[p + ".attn.table"].data_ptr(), att.data_ptr(), pad(d), S)
+                else:
+                    call(lib.ffsr_window_attention, qkv.data_ptr(), B, H, W, d, sw.heads, ws, shift,
+                         w[p + ".attn.table"].data_ptr(), att.data_ptr(), K.DT_F32, S)
                 y1 = self._buf("y1", (B, H, W, d), dev)
                 conv(nhwc(att), H, W, d, p + ".attn.proj", d, 1, nhwc(y1), r1=prefix(G))          # x + proj(attn)
                 n2 = n1
                 call(lib.ffsr_layernorm_strided, y1.data_ptr(), NP, d, d, w[p + ".norm2.w"].data_ptr(), w[p + ".norm2.b"].data_ptr(),
-                     n2.data_ptr(), d, K.DT_F32, K.DT_F32, S)
-                hd = self._buf("hid", (B, H, W, hid), dev)
+                     n2.data_ptr(), pad(d), K.DT_F32, ADT, S)
+                hd = self._buf("hid", (B, H, W, pad(hid)), dev, adt)
                 conv(nhwc(n2), H, W, d, p + ".mlp.fc1", hid, 1, nhwc(hd), act=K.ACT_GELU)
-                y2 = att
+                y2 = self._buf("y2", (B, H, W, d), dev) if lp else att
                 conv(nhwc(hd), H, W, hid, p + ".mlp.fc2", d, 1, nhwc(y2), r1=nhwc(y1))             # + mlp
                 a = f"layers.{i}.adjust{j + 1}"
                 if j < 4:                                      # 32 new channels straight into the growth buffer, LeakyReLU 0.2

@@ -368,6 +368,10 @@ int ffsr_cache_unpack(const void* records, size_t record_bytes, int B, const ffs
  * dh <= 128.  First CUDA-core version (parity-tested on a B200, used by isr_b200.drct; not yet timed). */
 int ffsr_window_attention(const void* qkv, int B, int H, int W, int C, int heads, int window, int shift,
                           const float* bias_table, void* out, int dtype, cudaStream_t stream);
+/* Same on bf16 rows PADDED to qkv_pitch >= 3*C / out_pitch >= C elements (the DRCT channel counts are 4 mod 8; bf16
+ * operands of the tcgen05 Linears need 16-byte row pitches).  NOT yet run on hardware (caller and test gated). */
+int ffsr_window_attention_pitched(const void* qkv, long qkv_pitch, int B, int H, int W, int C, int heads, int window,
+                                  int shift, const float* bias_table, void* out, long out_pitch, cudaStream_t stream);
 
 /* Small ops of the DRCT-L expert forward (src/models/drct/drct_arch.py), used by isr_b200.drct.
  *   layernorm_strided : nn.LayerNorm(C) (eps 1e-5) over the first C channels of rows with pitch x_pitch (:292-299, the

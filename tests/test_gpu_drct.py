@@ -121,3 +121,49 @@ def test_drct_forward_matches_oracle():
         want, feat = DO.forward(sd, x, return_feature=True)
     assert float((y.cpu() - want).abs().max()) <= 1e-4
     assert float((m.last_feature.cpu() - feat).abs().max()) <= 1e-4
+
+
+_WIP = pytest.mark.skipif(os.environ.get("FFSR_RUN_WIP") != "1", reason="bf16 / tcgen05 mode of the DRCT path has not run on hardware yet")
+
+
+@pytest.mark.gpu
+@_WIP
+@pytest.mark.parametrize("Cc,heads,ws", [(180, 6, 16), (244, 2, 16), (308, 4, 8)])
+def test_pitched_window_attention_bf16(Cc, heads, ws):
+    dev = torch.device("cuda:0")
+    lib = K.load()
+    g = torch.Generator().manual_seed(Cc)
+    B, H, W = 1, 2 * ws, 2 * ws
+    qp, op = (3 * Cc + 7) // 8 * 8, (Cc + 7) // 8 * 8
+    qkv = torch.randn(B, H, W, 3 * Cc, generator=g)
+    table = 0.5 * torch.randn((2 * ws - 1) ** 2, heads, generator=g)
+    qd = torch.zeros(B, H, W, qp, device=dev, dtype=torch.bfloat16)
+    qd[..., :3 * Cc] = qkv.to(dev)
+    td = table.to(dev)
+    for shift in (0, ws // 2):
+        out = torch.full((B, H, W, op), 7.0, device=dev, dtype=torch.bfloat16)
+        K.check(lib.ffsr_window_attention_pitched(qd.data_ptr(), qp, B, H, W, Cc, heads, ws, shift, td.data_ptr(), out.data_ptr(), op,
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)), "window_attention_pitched")
+        want = expected_attention(qd[..., :3 * Cc].float().cpu(), heads, ws, shift, table)
+        assert float((out[..., :Cc].float().cpu() - want).abs().max()) <= 2e-2
+        assert bool((out[..., Cc:] == 7.0).all())                      # padding channels are not touched
+
+
+@pytest.mark.gpu
+@_WIP
+def test_drct_forward_bf16_mode():
+    import json
+    import numpy as np
+    from isr_b200 import drct as D
+    g = np.load(os.path.join(ROOT, "tests", "golden", "drct_small.npz"))
+    cfg = json.loads(str(g["cfg"]))
+    m = D.DRCT(img_size=cfg["img_size"], window_size=cfg["window"], embed_dim=cfg["embed_dim"], depths=[6] * cfg["n_rdg"],
+               num_heads=[cfg["num_heads"]] * cfg["n_rdg"], mlp_ratio=cfg["mlp_ratio"])
+    m.load_state_dict(DO.synth_state_dict(DO.state_shapes(**cfg), seed=int(g["seed"]), img_size=cfg["img_size"]), strict=True)
+    dev = torch.device("cuda:0")
+    m.to(dev).eval()
+    m.precision = "bf16"
+    y = m(torch.from_numpy(g["x"]).to(dev)).cpu()
+    want = torch.from_numpy(g["y"])
+    rel = float((y - want).norm() / want.norm())
+    assert rel <= 2e-2, rel
