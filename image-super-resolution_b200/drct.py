@@ -172,9 +172,15 @@ class DRCT(nn.Module):
         if Cc != 3 or H % ws or W % ws:
             raise ValueError(f"DRCT input must be [B,3,H,W] with H, W multiples of the window ({ws}); callers pad "
                              "(scripts/extract_test_tta_cache.py)")
-        lib, dev = K.load(), x.device
+        return self._run(x, K.load(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+
+    def _run(self, x: torch.Tensor, lib, S) -> torch.Tensor:
+        """The launch sequence (also driven with a recording fake of the library in the CPU tests)."""
+        lp = self.precision == "bf16"
+        B, Cc, H, W = x.shape
+        ws = self.window_size
+        dev = x.device
         w = self._weights(dev)
-        S = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         mean3 = (C.c_float * 3)(*RGB_MEAN)
         E, gc = self.embed_dim, self.gc
         GW = E + 4 * gc                                        # width of the dense-growth buffer

@@ -98,3 +98,39 @@ def test_module_mirror_has_the_reference_state_layout():
             full.cuda()(torch.zeros(1, 3, 20, 16, device="cuda"))
     with pytest.raises(NotImplementedError):
         D.DRCT(upsampler="nearest+conv")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_drct_launch_sequence_dry_run(precision):
+    """Every line of the orchestration runs against a recording fake of the library (no compute without a GPU)."""
+    import ctypes as C
+    import isr_b200  # noqa: F401
+    from isr_b200 import drct as D
+
+    class Fake:
+        def __init__(self):
+            self.calls = []
+
+        def __getattr__(self, name):
+            def f(*a):
+                self.calls.append((name, a))
+                return 0
+            f.__name__ = name
+            return f
+
+    n = 2
+    m = D.DRCT(img_size=16, window_size=8, depths=[6] * n, num_heads=[6] * n).eval()
+    m.precision = precision
+    lib = Fake()
+    y = m._run(torch.rand(1, 3, 16, 24), lib, C.c_void_p(0))
+    assert tuple(y.shape) == (1, 3, 64, 96) and tuple(m.last_feature.shape) == (1, 180, 16, 24)
+    names = [c[0] for c in lib.calls]
+    assert names.count("ffsr_conv2d") == 1 + 25 * n + 5
+    assert names.count("ffsr_layernorm_strided") == 1 + 10 * n + 1
+    att = "ffsr_window_attention_pitched" if precision == "bf16" else "ffsr_window_attention"
+    assert names.count(att) == 5 * n and names.count("ffsr_leaky_relu") == 4 * n + 1
+    assert names.count("ffsr_pixel_shuffle2") == 2 and names[0] == "ffsr_rgb_shift_in" and names[-1] == "ffsr_rgb_shift_out"
+    heads = [c[1][5] if precision == "fp32" else c[1][6] for c in lib.calls if c[0] == att]
+    assert heads[:5] == [6, 4, 2, 6, 4]
+    shifts = [c[1][7] if precision == "fp32" else c[1][8] for c in lib.calls if c[0] == att]
+    assert shifts[:5] == [0, 4, 0, 4, 0]
