@@ -19,7 +19,7 @@
 //   MMA       : tcgen05.mma.cta_group::1.kind::f16, M=128, N=nblk, K=16, issued by one thread;
 //               accumulators double-buffered in TMEM (2 x 128 columns) so the epilogue of
 //               tile i overlaps the MMAs of tile i+1.
-//   warps     : 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..17 = epilogue: warp w reads
+//   warps     : 0 = TMA producer, 1..3 = MMA issuers (warp 1 also allocates TMEM), 4..19 = epilogue: warp w reads
 //               TMEM lane quarter w%4 (hardware rule) and the 16-column chunks (w-2)/4, +4, ...;
 //               tcgen05.ld 32x32b -> bias/act/residual -> 16-byte vector stores.  16 warps keep
 //               all four SM sub-partitions busy with the GELU math so that the epilogue of a
@@ -48,11 +48,16 @@ constexpr int TC_TH = 8, TC_TW = 16;           // output pixel tile (M = 128)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_ROW_BYTES = TC_TW * 128;      // one image row of the tile: 16 px x 64 bf16
 constexpr int TC_SMEM_MAX = 232448;            // 227 KB opt-in limit per CTA
-constexpr int TC_SMEM_HDR = 1024;              // barriers + TMEM slot (after 1024B alignment)
+constexpr int TC_SMEM_HDR = 3072;              // barriers + TMEM slot (first 1 KB) + staged bias (512 floats)
+constexpr int TC_BIAS_OFF = 1024;              // byte offset of the staged bias inside the header
+constexpr int TC_BIAS_MAX = 512;               // output columns whose bias is staged (lean epilogue)
 constexpr int TC_EPI_WARPS = 16;              // 4 per TMEM lane quarter: each owns a 16-column slice
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_MMA_WARPS = 3;               // warps 1..3 can issue MMAs (TcArgs.nmma of them do; see the MMA issuers).  20 warps = 5
+                                              // per SM sub-partition keep the 96-register budget; a 21st would cut it to 80
+constexpr int TC_EPI_WARP0 = 1 + TC_MMA_WARPS; // first epilogue warp
+constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS);
 constexpr int TC_TMEM_COLS = 512;             // whole TMEM: ring of 512/slot accumulators (1 CTA per SM)
-constexpr int TC_MAX_ACC = 8;
+constexpr int TC_MAX_ACC = 12;
 
 struct TcArgs {
   int N, H, W, Cin, Cout, taps, ks;
@@ -93,6 +98,8 @@ struct TcArgs {
   int gelu_tanh;     // tanh-form GELU for bf16 outputs of inference launches (see gelu_tanh_fast)
   int epi_own;       // 1: epilogue warp group g owns every 4th tile of the CTA (all its column chunks); 0: chunks of every
                      //    tile are spread over the four groups.  See epilogue_loop.
+  int lean;          // 1: lean_epilogue (bf16 inference outputs, bias staged in shared memory); see there
+  int nmma;          // MMA-issuing warps (1, 2 or 3): warp 1+g issues the MMAs of tiles g, g+nmma, ... of this CTA
 };
 
 // ---------------------------------------------------------------------------- PTX wrappers
@@ -402,7 +409,7 @@ template <int MODE, bool OUT_BF16>
 __device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
                                               int warp, int lane) {
   const int wq = warp & 3;
-  const int cgp = (warp - 2) >> 2;
+  const int cgp = (warp - TC_EPI_WARP0) >> 2;
   const int row = wq * 32 + lane;                       // pixel within the tile (accumulator row)
   const int tw = a.geom ? 8 : TC_TW;
   const int py = row / tw, px = row % tw;
@@ -530,6 +537,132 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, 
   }
 }
 
+
+// ---------------------------------------------------------------------------- lean epilogue
+// The generic epilogue_loop above spends most of its instructions on bookkeeping (round-1 ncu of a 32->32 layer:
+// 46 executed instructions per output value, 72 % of the issue slots, 14 % tensor pipe): per 16-column chunk it
+// recomputes three 64-bit pixel addresses, tests pointer alignment, fetches the bias from global memory and waits
+// for its own TMEM load.  lean_epilogue serves the launches that dominate an inference forward -- bf16 outputs,
+// Cout a multiple of 8, 16-byte aligned rows, one cout block, plain / activation / residual modes:
+//   * the bias is staged once per CTA in shared memory (float4 broadcast reads);
+//   * pixel addresses are computed once per tile (half);
+//   * two chunks (32 accumulator columns) are fetched with back-to-back tcgen05.ld and one wait (four would spill: the
+//     576-thread CTA caps a thread at 96 registers);
+//   * the accumulator is handed back to the MMA warp as soon as the last tcgen05.ld of the tile has completed, before
+//     the activation math and the stores;
+//   * `own` layers (N <= 128 single-half tiles, >= 4 accumulators in flight): warp group g takes every 4th tile whole;
+//     split layers (two-half 128-column tiles): warp group g takes columns [32 g, 32 g + 32) of both halves.
+template <int MODE, bool TANH>
+__device__ __forceinline__ void lean_chunk(const uint32_t (&v)[16], const float* __restrict__ sb16, __nv_bfloat16* __restrict__ o,
+                                           int nv8, const TcArgs& a, long long r1off, long long r2off, float sa, float sb,
+                                           bool has_r2) {
+  float f[16];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sb16 + 4 * k);
+    f[4 * k] = __uint_as_float(v[4 * k]) + b4.x;
+    f[4 * k + 1] = __uint_as_float(v[4 * k + 1]) + b4.y;
+    f[4 * k + 2] = __uint_as_float(v[4 * k + 2]) + b4.z;
+    f[4 * k + 3] = __uint_as_float(v[4 * k + 3]) + b4.w;
+  }
+  if (MODE == EM_GELU) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = TANH ? gelu_tanh_fast(f[k]) : gelu_fast(f[k]);
+  } else if (MODE == EM_RELU) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = fmaxf(f[k], 0.f);
+  } else if (MODE == EM_SIGMOID) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = sigmoid_acc(f[k]);
+  } else if (MODE == EM_RESIDUAL) {
+    float r[16];
+    load_res16(a.r1, a.r1_bf16, r1off, nv8 * 8, r);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = fmaf(sa, f[k], r[k]);
+    if (has_r2) {
+      load_res16(a.r2, a.r2_bf16, r2off, nv8 * 8, r);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) f[k] = fmaf(sb, r[k], f[k]);
+    }
+  }
+  uint32_t w[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+    w[k] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  if (nv8 > 1) reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+template <int MODE, bool TANH>
+__device__ __forceinline__ void lean_epilogue(const TcArgs& a, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base, int warp,
+                                              int lane, const float* __restrict__ sbias) {
+  const int wq = warp & 3;
+  const int cgp = (warp - TC_EPI_WARP0) >> 2;
+  const int row = wq * 32 + lane;
+  const int tw = a.geom ? 8 : TC_TW;
+  const int py = row / tw, px = row % tw;
+  const int nch = a.nblk >> 4;
+  const int nv8_total = a.Cout >> 3;                   // Cout % 8 == 0 on this path
+  const bool own = a.epi_own != 0;
+  const int c_lo = own ? 0 : cgp * (nch >> 2);         // split mode: nch % 4 == 0
+  const int c_hi = own ? nch : c_lo + (nch >> 2);
+  const int nacc = a.nacc, halves = a.halves;
+  float sa = 1.f, sb = 1.f;
+  if (MODE == EM_RESIDUAL) {
+    sa = a.sa * (a.sa_ptr ? a.sa_ptr[0] : 1.0f);
+    sb = a.sb * (a.sb_ptr ? a.sb_ptr[0] : 1.0f);
+  }
+  const bool has_r2 = MODE == EM_RESIDUAL && a.r2 != nullptr;
+  __nv_bfloat16* const outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+  int as = 0, q = 0;
+  uint32_t aph = 0;
+  TileIter ti;
+  for (ti.init(a); ti.valid(a); ti.next(a), ++q) {
+    if (own && (q & 3) != cgp) {
+      if (++as == nacc) { as = 0; aph ^= 1; }
+      continue;
+    }
+    const int n = ti.n;
+    const int cb = ti.nb * a.nblk;                      // first output column of this cout block
+    const int x = ti.tx * tw + px;
+    mbar_wait(&tfull[as], aph);
+    tc_fence_after();
+    for (int half = 0; half < halves; ++half) {
+      const int y = ti.ty * a.tile_h + half * TC_TH + py;
+      const bool inside = (y < a.H) && (x < a.W);
+      const long long opix = (long long)n * a.out_sN + (long long)y * a.out_sY + (long long)x * a.out_sX + cb;
+      long long r1pix = 0, r2pix = 0;
+      if (MODE == EM_RESIDUAL) {
+        r1pix = (long long)n * a.r1_sN + (long long)y * a.r1_sY + (long long)x * a.r1_sX + cb;
+        if (has_r2) r2pix = (long long)n * a.r2_sN + (long long)y * a.r2_sY + (long long)x * a.r2_sX + cb;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * a.acc_slot + half * a.acc_half);
+      for (int c0 = c_lo; c0 < c_hi; c0 += 2) {
+        const int nc = min(2, c_hi - c0);
+        uint32_t v0[16], v1[16];
+        tmem_ld16(taddr + (uint32_t)(c0 * 16), v0);
+        if (nc > 1) tmem_ld16(taddr + (uint32_t)(c0 * 16 + 16), v1);
+        tmem_wait_ld(v0);
+        if (nc > 1) tmem_wait_ld(v1);
+        if (half == halves - 1 && c0 + 2 >= c_hi) {      // every column of this tile is in registers: free the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+        if (inside) {
+          const int col = cb + c0 * 16;                  // global output column of v0[0]
+          const int g8 = nv8_total - (col >> 3);         // valid 8-column groups from here on
+          if (g8 > 0) lean_chunk<MODE, TANH>(v0, sbias + col, outp + opix + c0 * 16, min(g8, 2), a, r1pix + c0 * 16, r2pix + c0 * 16, sa, sb, has_r2);
+          if (nc > 1 && g8 > 2) lean_chunk<MODE, TANH>(v1, sbias + col + 16, outp + opix + c0 * 16 + 16, min(g8 - 2, 2), a, r1pix + c0 * 16 + 16, r2pix + c0 * 16 + 16, sa, sb, has_r2);
+        }
+      }
+    }
+    if (++as == nacc) { as = 0; aph ^= 1; }
+  }
+}
+
 // ---------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -542,6 +675,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* tempty = bars + 2 * TC_MAX_STAGES + TC_MAX_ACC;    // [TC_MAX_ACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 2 * TC_MAX_ACC);
   uint64_t* bfull = bars + 2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1;   // resident-weights barrier
+  float* sbias = reinterpret_cast<float*>(smem + TC_BIAS_OFF);       // lean epilogue: bias of every output column
   uint8_t* bres = smem + TC_SMEM_HDR;                                // resident weights (may be empty)
   uint8_t* stages = bres + a.bres_bytes;
 
@@ -554,6 +688,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     for (int i = 0; i < TC_MAX_ACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], a.epi_own ? 4 : TC_EPI_WARPS); }
     mbar_init(bfull, 1);
     fence_barrier_init();
+  }
+  if (a.lean && threadIdx.x >= 32 * TC_EPI_WARP0) {
+    const int ncols = a.n_nblocks * a.nblk;
+    for (int c = threadIdx.x - 32 * TC_EPI_WARP0; c < ncols; c += TC_THREADS - 32 * TC_EPI_WARP0) sbias[c] = (a.bias != nullptr && c < a.Cout) ? a.bias[c] : 0.f;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
@@ -614,27 +752,40 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ========================================
+  } else if (warp < TC_EPI_WARP0) {
+    // ================================ MMA issuers ========================================
+    // One issuing warp is enough when a tile is many large MMAs (128->128 3x3: 144 x 64 cycles).  Small-N / small-K
+    // layers are bound by the ISSUE path instead: ncu of a 32->32 3x3 layer shows the epilogue and producer warps
+    // waiting while the MMA warp spends ~1,900 cycles on the ~300 instructions (descriptor assembly on the uniform
+    // datapath, barrier waits, commits) that surround the 18 sixteen-cycle MMAs of a tile.  Tiles are independent
+    // (own accumulator, own pipeline stages), so warp 1+g takes tiles g, g+nmma, ... of this CTA: stage and accumulator
+    // positions advance by whole tiles, tcgen05.commit tracks the issuing thread's own MMAs.
+    const int g = warp - 1;
+    if (g < a.nmma) {
+    const int nmma = a.nmma;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.nblk >> 3) << 17) | ((128u >> 4) << 24);
-    int s = 0;
-    uint32_t ph = 0;
-    int as = 0;
+    const int k0 = g * kiters;
+    int s = k0 % a.nstages;
+    uint32_t ph = (uint32_t)((k0 / a.nstages) & 1);
+    int as = g;                                     // nmma <= nacc, nacc % nmma == 0
     uint32_t aph = 0;
     int cur_g = -1, cur_nb = -1;
     uint32_t bph = 0;
     const uint32_t stages_u32 = smem_u32(stages), bres_u32 = smem_u32(bres);
     const uint32_t b_step = (uint32_t)(a.nblk * 128) >> 4;
     const int last_chunk_it = a.geom ? a.nchunks - 1 : (a.nchunks - 1) * a.ks;   // stages of the last (possibly partial) K chunk
+    const int skip = (nmma - 1) * kiters;
     TileIter ti;
-    for (ti.init(a); ti.valid(a); ti.next(a)) {
+    ti.init(a);                                     // tile coordinates matter only for weight-set changes (nmma == 1)
+    for (int q = 0; q < g; ++q) ti.next(a);
+    for (; ti.valid(a);) {
       if (a.b_resident) {
         const int nb = ti.nb;
-        const int g = a.groups > 1 ? ti.n % a.groups : 0;
-        if (g != cur_g || nb != cur_nb) {
+        const int gg = a.groups > 1 ? ti.n % a.groups : 0;
+        if (gg != cur_g || nb != cur_nb) {           // nmma > 1 launches have ONE weight set: every warp waits for phase 0 once
           mbar_wait(bfull, bph);
           bph ^= 1;
-          cur_g = g;
+          cur_g = gg;
           cur_nb = nb;
         }
       }
@@ -694,15 +845,32 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         if (++s == a.nstages) { s = 0; ph ^= 1; }
       }
-      if (++as == a.nacc) { as = 0; aph ^= 1; }
+      // on to this warp's next tile: skip the stages and accumulators of the other issuing warps' tiles
+      s += skip;
+      while (s >= a.nstages) { s -= a.nstages; ph ^= 1; }
+      as += nmma;
+      if (as >= a.nacc) { as -= a.nacc; aph ^= 1; }
+      for (int q = 0; q < nmma; ++q) ti.next(a);
+    }
     }
   } else {
-    // ================================ epilogue (warps 2..17) ============================
+    // ================================ epilogue (warps 4..19) ============================
     const int mode = a.epi == FFSR_EPI_LKAGATE ? EM_LKAGATE
                      : (a.epi == FFSR_EPI_RESIDUAL ? EM_RESIDUAL : (a.epi == FFSR_EPI_ACTGRAD ? EM_ACTGRAD : a.act));
     // one specialised loop per (epilogue mode, output type): no per-element switches, and the
     // plain modes do not carry the residual registers
-    if (a.out_bf16) {
+    if (a.lean) {
+      switch (mode) {
+        case EM_GELU:
+          if (a.gelu_tanh) lean_epilogue<EM_GELU, true>(a, tfull, tempty, tmem_base, warp, lane, sbias);
+          else lean_epilogue<EM_GELU, false>(a, tfull, tempty, tmem_base, warp, lane, sbias);
+          break;
+        case EM_RELU: lean_epilogue<EM_RELU, false>(a, tfull, tempty, tmem_base, warp, lane, sbias); break;
+        case EM_SIGMOID: lean_epilogue<EM_SIGMOID, false>(a, tfull, tempty, tmem_base, warp, lane, sbias); break;
+        case EM_RESIDUAL: lean_epilogue<EM_RESIDUAL, false>(a, tfull, tempty, tmem_base, warp, lane, sbias); break;
+        default: lean_epilogue<EM_NONE, false>(a, tfull, tempty, tmem_base, warp, lane, sbias); break;
+      }
+    } else if (a.out_bf16) {
       switch (mode) {
         case EM_GELU: epilogue_loop<EM_GELU, true>(a, tfull, tempty, tmem_base, warp, lane); break;
         case EM_RELU: epilogue_loop<EM_RELU, true>(a, tfull, tempty, tmem_base, warp, lane); break;
@@ -876,7 +1044,48 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   static const bool own_off = getenv("FFSR_TC_EPI_OWN0") != nullptr;
   static const bool erf_forced = getenv("FFSR_TC_GELU_ERF") != nullptr;
   a.gelu_tanh = (!erf_forced && p.out2 == nullptr) ? 1 : 0;
-  a.epi_own = (!own_off && halves == 1 && a.nacc >= 8 && a.total_tiles >= 8LL * grid) ? 1 : 0;
+  const bool own_force = getenv("FFSR_TC_EPI_OWN_FORCE") != nullptr;     // tests: small images take the own path too (read per call)
+  const bool lean_off = getenv("FFSR_TC_LEAN0") != nullptr;
+  a.epi_own = (!own_off && halves == 1 && a.nacc >= 8 && (own_force || a.total_tiles >= 8LL * grid)) ? 1 : 0;
+  {
+    // lean epilogue: bf16 inference outputs in 16-byte groups; own mode also for 128-column single-half tiles (4 accumulators)
+    const bool mode_ok = p.epi == FFSR_EPI_PLAIN || (p.epi == FFSR_EPI_RESIDUAL && p.act == ACT_NONE);
+    const bool out_ok = a.out_bf16 && p.out2 == nullptr && p.groups == 1 && p.Cout % 8 == 0 && ((uintptr_t)p.out % 16) == 0 &&
+                        p.out_sX % 8 == 0 && p.out_sY % 8 == 0 && p.out_sN % 8 == 0 && a.n_nblocks * a.nblk <= TC_BIAS_MAX;
+    bool res_ok = true;
+    if (p.epi == FFSR_EPI_RESIDUAL) {
+      const int r1q = p.r1_dtype == FFSR_DT_BF16 ? 8 : 4, r2q = p.r2_dtype == FFSR_DT_BF16 ? 8 : 4;
+      res_ok = p.r1 != nullptr && ((uintptr_t)p.r1 % 16) == 0 && p.r1_sX % r1q == 0 && p.r1_sY % r1q == 0 && p.r1_sN % r1q == 0 &&
+               (p.r2 == nullptr || (((uintptr_t)p.r2 % 16) == 0 && p.r2_sX % r2q == 0 && p.r2_sY % r2q == 0 && p.r2_sN % r2q == 0));
+    }
+    const bool own_lean = halves == 1 && a.nacc >= 4 && (own_force || a.total_tiles >= 8LL * grid);
+    const bool split_lean = (a.nblk % 64) == 0;
+    a.lean = (!lean_off && mode_ok && out_ok && res_ok && (own_lean || split_lean)) ? 1 : 0;
+    if (a.lean) a.epi_own = (!own_off && own_lean) ? 1 : 0;
+    if (a.lean && !a.epi_own && !split_lean) a.lean = 0;
+  }
+  // several MMA-issuing warps for launches whose tiles are a few small MMAs (issue-bound, see the kernel): needs one weight
+  // set for the whole launch and an accumulator ring that is a multiple of the warp count (3 warps: ring of 6)
+  {
+    int want = TC_MMA_WARPS;
+    if (const char* e = getenv("FFSR_TC_NMMA")) want = atoi(e);
+    a.nmma = 1;
+    // An issuing warp waits for pipeline stages by PARITY, which tells a phase only from its neighbours: when it starts to
+    // wait for use k of a stage, use k - nstages must already have been filled.  The producer fills in order and is at
+    // least as far as the stages this warp consumed last, so this holds iff nmma * (stages per tile) <= nstages.
+    const int kiters = geom ? a.nchunks : p.ksize * a.nchunks;
+    if (want > 1 && a.b_resident && p.groups == 1 && a.n_nblocks == 1 && halves == 1) {
+      int n = want >= 3 ? 3 : 2;
+      while (n > 1 && n * kiters > a.nstages) --n;
+      // The accumulator ring must be a multiple of the issuing warps (a slot always belongs to the same warp) AND, with
+      // tile ownership in the epilogue, of the four epilogue warp groups: a group waits for its tile's accumulator by
+      // parity too, so the previous use of that slot must have been its own tile.  3 warps -> ring of 12 (N <= 32).
+      if (n == 3 && TC_TMEM_COLS / a.acc_slot >= 12) { a.nmma = 3; a.nacc = 12; }
+      else if (n >= 2 && a.nacc >= 8) { a.nmma = 2; a.nacc = 8; }
+      else if (n >= 2 && a.nacc >= 4) { a.nmma = 2; a.nacc = 4; }
+      else if (n >= 2 && a.nacc >= 2 && !a.epi_own) { a.nmma = 2; a.nacc = 2; }
+    }
+  }
   k_conv_tc<<<grid, TC_THREADS, smem_bytes, stream>>>(tmA, tmB, a);
   return ffsr_check_launch("conv2d_tc");
 }

@@ -83,6 +83,8 @@ class FusionEngine:
         # optional per-launch CUDA-event timing of named conv layers (bench.py roofline):
         # {weight name: [(start_event, end_event), ...]}
         self.timed_layers = None
+        # optional in-situ trace of EVERY launch: [(label, start_event, end_event), ...] (tools/trace_forward.py)
+        self.trace = None
         self.overlap_routing = True    # phases 3 + 6 on a side stream, concurrent with phases 4 / 5
         self.fold_crossband = True     # band_proj -> LayerNorm -> in_proj folded to 3+1 MACs per qkv channel
         self._side: Dict[str, torch.cuda.Stream] = {}
@@ -240,8 +242,16 @@ class FusionEngine:
             raise KeyError(name)
         return hits[-1]
 
-    def _call(self, fn, *args):
-        rc = fn(*args)
+    def _call(self, fn, *args, label=None):
+        if self.trace is not None:
+            st = torch.cuda.current_stream()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            rc = fn(*args)
+            e1.record(st)
+            self.trace.append((label or fn.__name__, e0, e1))
+        else:
+            rc = fn(*args)
         self.launches += 1
         if rc != 0:
             K.check(rc, fn.__name__)
@@ -288,7 +298,8 @@ class FusionEngine:
             e1.record(torch.cuda.current_stream())
             ev.append((e0, e1))
             return
-        self._call(self.lib.ffsr_conv2d, C.byref(p), self._stream)
+        self._call(self.lib.ffsr_conv2d, C.byref(p), self._stream,
+                   label=f"conv {wname} {Cin}->{Cout} k{ks} {H}x{W}" + (" tc" if x.t.dtype == torch.bfloat16 else ""))
 
     def _lka_block(self, key, blk: str, x: torch.Tensor, name: str, lp: bool = False) -> torch.Tensor:
         """x: [N,H,W,C] fp32 -> LKABlock(x) (large_kernel_attention.py:143-149), eval-mode BN folded.

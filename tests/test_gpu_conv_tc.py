@@ -87,3 +87,34 @@ def test_conv_tc_concat_slice_and_groups():
     # per-image weight sets (modulation heads: image n uses weights n % 4), bf16 residuals
     _run(128, 32, 1, 8, 12, 20, K.ACT_NONE, K.EPI_PLAIN, False, groups=4)
     _run(64, 64, 3, 2, 12, 20, K.ACT_NONE, K.EPI_RESIDUAL, True, r_bf16=True)
+
+
+# ---- lean epilogue (bf16 inference outputs): both tile-ownership modes, every activation, residual dtypes, Cout % 16 == 8
+@pytest.mark.parametrize("force_own", [False, True])
+@pytest.mark.parametrize("cin,cout,ks,act,epi,r_bf16", [
+    (32, 32, 3, K.ACT_GELU, K.EPI_PLAIN, False),
+    (64, 64, 3, K.ACT_GELU, K.EPI_PLAIN, False),
+    (76, 64, 3, K.ACT_RELU, K.EPI_PLAIN, False),
+    (32, 16, 3, K.ACT_GELU, K.EPI_PLAIN, False),
+    (32, 8, 1, K.ACT_GELU, K.EPI_PLAIN, False),
+    (32, 24, 3, K.ACT_SIGMOID, K.EPI_PLAIN, False),
+    (32, 32, 3, K.ACT_NONE, K.EPI_RESIDUAL, False),
+    (32, 32, 3, K.ACT_NONE, K.EPI_RESIDUAL, True),
+    (16, 128, 3, K.ACT_GELU, K.EPI_PLAIN, False),
+    (128, 128, 3, K.ACT_GELU, K.EPI_PLAIN, False),
+    (128, 256, 1, K.ACT_GELU, K.EPI_PLAIN, False),
+    (128, 384, 1, K.ACT_NONE, K.EPI_PLAIN, False),
+    (64, 128, 1, K.ACT_NONE, K.EPI_RESIDUAL, True),
+])
+def test_conv_tc_lean_epilogue(monkeypatch, force_own, cin, cout, ks, act, epi, r_bf16):
+    if force_own:
+        monkeypatch.setenv("FFSR_TC_EPI_OWN_FORCE", "1")
+    else:
+        monkeypatch.delenv("FFSR_TC_EPI_OWN_FORCE", raising=False)
+    _run(cin, cout, ks, 2, 37, 45, act, epi, True, r_bf16=r_bf16)
+
+
+def test_conv_tc_lean_epilogue_many_tiles():
+    # enough tiles per CTA (>= 8 x #SMs) for the tile-ownership heuristic to switch on by itself
+    _run(32, 32, 3, 1, 400, 416, K.ACT_GELU, K.EPI_PLAIN, True)
+    _run(64, 32, 3, 1, 400, 416, K.ACT_NONE, K.EPI_RESIDUAL, True, r_bf16=True)
