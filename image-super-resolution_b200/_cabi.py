@@ -94,6 +94,9 @@ PROTOTYPES = {
     "ffsr_blur_pool_backward": (_I, [_P, _LL, _I, _I, _I, _P, _P, _LL, _P]),
     "ffsr_laplacian_sub": (_I, [_P, _LL, _P, _LL, _I, _I, _I, _P, _LL, _P, _LL, _P]),
     "ffsr_edge_attn_upsample": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _LL, _I, _P]),
+    "ffsr_edge_chain_weight_bytes": (_SZ, []),
+    "ffsr_edge_chain_param_floats": (_SZ, []),
+    "ffsr_edge_refiner_chain": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _LL, _LL, _LL, _P, _I, _P]),
     "ffsr_nchw_to_nhwc_bf16": (_I, [_P, _I, _I, _L, _P, _LL, _LL, _P]),
     "ffsr_cast_f32_to_bf16": (_I, [_P, _P, _L, _P]),
     "ffsr_final_combine": (_I, [_P, _LL, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),

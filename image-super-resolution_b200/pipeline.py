@@ -15,6 +15,7 @@ Phase map (reference file:line in include/ffsr_b200.h):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -65,6 +66,30 @@ def _pack_tc(w_f32: torch.Tensor) -> torch.Tensor:
     return out.contiguous()
 
 
+def _pack_planes(w: torch.Tensor, kgn: int, nout: int) -> torch.Tensor:
+    """[Cout,Cin,kh,kw] -> [kh*kw][kgn][nout][8] fp32: the no-swizzle K-major shared-memory layout of the tile-resident
+    kernels (8-input-channel groups, zero padded in both channel dimensions)."""
+    co, ci, kh, kw = w.shape
+    t = torch.zeros(kh * kw, kgn * 8, nout, device=w.device, dtype=torch.float32)
+    t[:, :ci, :co] = w.detach().float().permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
+    return t.view(kh * kw, kgn, 8, nout).permute(0, 1, 3, 2).contiguous()
+
+
+def pack_edge_chain(r):
+    """EdgeRefineBlock -> (bf16 weight blob, fp32 parameter blob) of ffsr_edge_refiner_chain (layout: csrc/edge_chain.cu)."""
+    a0, a2 = r.attn.attn[0], r.attn.attn[2]
+    wb = torch.cat([_pack_planes(r.conv1.weight, 2, 32).reshape(-1), _pack_planes(r.conv2.weight, 4, 32).reshape(-1),
+                    _pack_planes(r.conv3.weight, 4, 32).reshape(-1), _pack_planes(a0.weight, 4, 16).reshape(-1)]).to(torch.bfloat16)
+    f = lambda t: t.detach().float().reshape(-1)
+    ba = torch.zeros(16, device=wb.device)
+    ba[:8] = f(a0.bias)
+    wp = torch.cat([r.proj.weight.detach().float().reshape(32, 3), r.proj.bias.detach().float().reshape(32, 1)], 1)
+    pb = torch.cat([f(r.conv1.bias), f(r.conv2.bias), f(r.conv3.bias), ba, wp.reshape(-1),
+                    a2.weight.detach().float().permute(2, 3, 1, 0).reshape(-1), f(a2.bias),
+                    torch.zeros(7, device=wb.device)])
+    return wb.contiguous(), pb.contiguous()
+
+
 def _pack_linear(w: torch.Tensor) -> torch.Tensor:
     """[out,in] -> [1][in][out]."""
     return w.detach().float().t().contiguous().unsqueeze(0)
@@ -87,6 +112,8 @@ class FusionEngine:
         self.trace = None
         self.overlap_routing = True    # phases 3 + 6 on a side stream, concurrent with phases 4 / 5
         self.fold_crossband = True     # band_proj -> LayerNorm -> in_proj folded to 3+1 MACs per qkv channel
+        # bf16 mode: each edge refiner as ONE tile-resident kernel (csrc/edge_chain.cu) instead of six conv launches
+        self.edge_chain = os.environ.get("FFSR_EDGE_CHAIN0") is None
         self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ weights
@@ -207,6 +234,8 @@ class FusionEngine:
                 conv(f"ee.{lv}.proj", r.proj)
                 conv(f"ee.{lv}.a0", r.attn.attn[0])
                 conv(f"ee.{lv}.a2", r.attn.attn[2])
+                if tuple(r.conv1.weight.shape) == (32, 3, 3, 3) and tuple(r.attn.attn[0].weight.shape[:2]) == (8, 32):
+                    w[f"ee.{lv}.chain_w"], w[f"ee.{lv}.chain_p"] = pack_edge_chain(r)
             conv("ee.f0", ee.fusion[0])
             conv("ee.f2", ee.fusion[2])
             conv("ee.g0", ee.edge_gate[0])
@@ -654,6 +683,20 @@ class FusionEngine:
         for lv, (lap, lap_lp, h, wd) in enumerate(levels):
             nm = f"ee{lv}"
             src = lap_lp if lp else lap                       # bf16 mode: every refiner conv is a tcgen05 launch
+            if lp and self.edge_chain and f"ee.{lv}.chain_w" in w:
+                # one tile-resident kernel per level; level 0 writes its weighted product straight into the concat slice
+                cw, cp = w[f"ee.{lv}.chain_w"], w[f"ee.{lv}.chain_p"]
+                if lv == 0:
+                    self._call(lib.ffsr_edge_refiner_chain, src.data_ptr(), B, h, wd, cw.data_ptr(), cp.data_ptr(),
+                               pp("edge_enhance.level_weights"), 0, cat96.data_ptr(), Hh * Wh * 96, Wh * 96, 96, None, 0, S)
+                else:
+                    o3 = self._buf(nm + ".o3", (B, h, wd, 32), dev, dtype=adt)
+                    at = self._buf(nm + ".at", (B, h, wd, 1), dev)
+                    self._call(lib.ffsr_edge_refiner_chain, src.data_ptr(), B, h, wd, cw.data_ptr(), cp.data_ptr(),
+                               None, lv, o3.data_ptr(), h * wd * 32, wd * 32, 32, at.data_ptr(), 1, S)
+                    self._call(lib.ffsr_edge_attn_upsample, o3.data_ptr(), ADT, at.data_ptr(), B, h, wd, 32,
+                               pp("edge_enhance.level_weights"), lv, cat96.data_ptr() + 32 * lv * esz, Hh, Wh, 96, ADT, S)
+                continue
             idt = self._buf(nm + ".idt", (B, h, wd, 32), dev)
             o1 = self._buf(nm + ".o1", (B, h, wd, 32), dev, dtype=adt)
             o2 = self._buf(nm + ".o2", (B, h, wd, 32), dev, dtype=adt)

@@ -187,6 +187,20 @@ int ffsr_laplacian_sub(const float* x, long long x_sX, const float* down, long l
 int ffsr_edge_attn_upsample(const void* o, int o_dtype, const float* attn, int N, int h, int w, int C,
                             const float* level_w, int level, void* dst, int H, int W, long long dst_sX, int dtype,
                             cudaStream_t stream);
+
+/* Tile-resident edge refiner of ONE pyramid level (bf16 mode): EdgeRefineBlock + SpatialEdgeAttention in one tcgen05
+ * kernel, 32-channel intermediates in shared memory (csrc/edge_chain.cu).
+ * Replaces: r.proj / conv1 / conv2 / conv3 + identity, attn.attn[0..3] and the x * attn product --
+ *   src/models/edge_enhancement.py:69-83 (SpatialEdgeAttention), :96-118 (EdgeRefineBlock.forward).
+ * x: bf16 [N][H][W][8] (3 Laplacian channels + 5 zero); wblob / pblob: weights packed by the host into the kernel's
+ * shared-memory layout (ffsr_edge_chain_weight_bytes() bytes of bf16, ffsr_edge_chain_param_floats() floats; layout in
+ * csrc/edge_chain.cu).  mode 0: dst[n][y][x][0..31] = o3 * at * softmax(level_w)[level] (strided bf16 view, e.g. a slice
+ * of the 96-channel concat); mode 1: dst = o3 (bf16) and attn_out[N][H][W] = at (fp32), for ffsr_edge_attn_upsample. */
+size_t ffsr_edge_chain_weight_bytes(void);
+size_t ffsr_edge_chain_param_floats(void);
+int ffsr_edge_refiner_chain(const void* x, int N, int H, int W, const void* wblob, const float* pblob,
+                            const float* level_w, int level, void* dst, long long dst_sN, long long dst_sY,
+                            long long dst_sX, float* attn_out, int mode, cudaStream_t stream);
 /* out = clamp(x + gate*strength*edge, 0, 1) + residual_scale*bilinear_x4(lr) [clamp in eval]
  * src/models/edge_enhancement.py:259-260, src/models/enhanced_fusion_v2.py:788-795 */
 int ffsr_final_combine(const float* xe, long long xe_sX, const float* gate, const float* strength, const float* lr,
