@@ -86,6 +86,7 @@ PROTOTYPES = {
     "ffsr_conv2d": (_I, [C.POINTER(ConvParams), _P]),
     "ffsr_conv_params_size": (_SZ, []),
     "ffsr_modulate_hr": (_I, [C.POINTER(_P), _P, _P, _P, _I, _I, _I, _I, _P, _P, _LL, _I, _P]),
+    "ffsr_modulate_hr_v2": (_I, [C.POINTER(_P), _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _LL, _I, _P]),
     "ffsr_expert_downsample": (_I, [_P, _I, _I, _I, _P, _LL, _P, _LL, _I, _P]),
     "ffsr_resize_nhwc": (_I, [_P, _I, _I, _I, _I, _LL, _P, _I, _I, _LL, _I, _P]),
     "ffsr_spatial_gate": (_I, [_P, _L, _I, _P, _P, _P, _P, _P, _I, _P]),

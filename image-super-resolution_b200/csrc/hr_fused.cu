@@ -127,6 +127,138 @@ extern "C" int ffsr_modulate_hr(const float* const* imgs, const float* m32, cons
   return ffsr_check_launch("modulate_hr");
 }
 
+// v2: one thread = the four HR pixels 4k+2 .. 4k+5 of one row (they share the LR taps k, k+1 with x-weights 1/8, 3/8, 5/8,
+// 7/8) x all four experts.  The v1 kernel above is bound by its loads and its erf: one thread per HR pixel issues 128 sixteen-
+// byte loads, each of a different 128-byte line than its neighbours', for 128 GELUs.  Here the four taps are loaded once per
+// four pixels (8x fewer load instructions per pixel with bf16 features), the vertical blend is shared by the four pixels, and the
+// bf16 mode uses the tanh-form GELU (the result only feeds a sigmoid that is damped by 0.2).
+template <typename TM>
+struct ModLoad;
+template <>
+struct ModLoad<float> {
+  static constexpr int CH = 4;
+  __device__ static __forceinline__ void ld(const float* p, float (&f)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+};
+template <>
+struct ModLoad<__nv_bfloat16> {
+  static constexpr int CH = 8;
+  __device__ static __forceinline__ void ld(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+      f[2 * k] = f2.x; f[2 * k + 1] = f2.y;
+    }
+  }
+};
+
+template <typename TM, typename T, bool FAST>
+__global__ void __launch_bounds__(128) k_modulate_hr4(Img4 imgs, const TM* __restrict__ m32, const float* __restrict__ w2,
+                                                      const float* __restrict__ b2, int B, int H, int W, int clamp01,
+                                                      float* __restrict__ ecol, T* __restrict__ cat3, long long cat3_sX) {
+  __shared__ float sw[4][3][32];
+  __shared__ float sb[4][3];
+  for (int i = threadIdx.x; i < 384; i += blockDim.x) (&sw[0][0][0])[i] = w2[i];
+  if (threadIdx.x < 12) (&sb[0][0])[threadIdx.x] = b2[threadIdx.x];
+  __syncthreads();
+  const int Hh = 4 * H, Wh = 4 * W;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x - 1;       // LR column of the left tap: -1 .. W-1
+  const int Y = blockIdx.y, b = blockIdx.z;
+  if (k > W - 1) return;
+  const int x0 = 4 * k + 2;                                      // HR column of pixel 0 (pixels 0,1 exist iff k >= 0; 2,3 iff k <= W-2)
+  const int i0 = k < 0 ? 0 : k, i1 = k + 1 > W - 1 ? W - 1 : k + 1;
+  const BilinTap ty = bilin_tap(Y, H, Hh);
+  constexpr int CH = ModLoad<TM>::CH;
+  float mod[4][12];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int q = 0; q < 12; ++q) mod[j][q] = sb[q / 3][q % 3];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const TM* base = m32 + ((long)(b * 4 + e) * H) * W * 32;
+    const TM* p00 = base + ((long)ty.i0 * W + i0) * 32;
+    const TM* p01 = base + ((long)ty.i0 * W + i1) * 32;
+    const TM* p10 = base + ((long)ty.i1 * W + i0) * 32;
+    const TM* p11 = base + ((long)ty.i1 * W + i1) * 32;
+#pragma unroll 2
+    for (int c = 0; c < 32; c += CH) {
+      float a[CH], bq[CH], cc[CH], d[CH];
+      ModLoad<TM>::ld(p00 + c, a);
+      ModLoad<TM>::ld(p01 + c, bq);
+      ModLoad<TM>::ld(p10 + c, cc);
+      ModLoad<TM>::ld(p11 + c, d);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const float l = ty.w0 * a[i] + ty.w1 * cc[i];            // vertical blend of the left / right tap column
+        const float r = ty.w0 * bq[i] + ty.w1 * d[i];
+        const float dlr = r - l;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float g = gelu_sel<FAST>(fmaf(0.125f + 0.25f * (float)j, dlr, l));
+#pragma unroll
+          for (int q = 0; q < 3; ++q) mod[j][e * 3 + q] = fmaf(sw[e][q][c + i], g, mod[j][e * 3 + q]);
+        }
+      }
+    }
+  }
+  const long HWh = (long)Hh * Wh;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if (half == 0 ? (k < 0) : (k > W - 2)) continue;
+    const int X = x0 + 2 * half;
+    const long pix = (long)Y * Wh + X;
+    float o[2][12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+      const long off = ((long)(b * 4 + q / 3) * 3 + q % 3) * HWh + pix;
+      const float2 v = *reinterpret_cast<const float2*>(imgs.p[q / 3] + ((long)b * 3 + q % 3) * HWh + pix);
+      float v0 = v.x * (1.0f + 0.2f * (sigmoid_acc(mod[2 * half][q]) - 0.5f));
+      float v1 = v.y * (1.0f + 0.2f * (sigmoid_acc(mod[2 * half + 1][q]) - 0.5f));
+      if (clamp01) { v0 = fminf(fmaxf(v0, 0.f), 1.f); v1 = fminf(fmaxf(v1, 0.f), 1.f); }
+      o[0][q] = v0; o[1][q] = v1;
+      *reinterpret_cast<float2*>(ecol + off) = make_float2(v0, v1);
+    }
+    if (cat3) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        T* dst = cat3 + ((long)b * HWh + pix + j) * cat3_sX;
+        store_vec4<T>(dst, o[j][0], o[j][1], o[j][2], o[j][3]);
+        store_vec4<T>(dst + 4, o[j][4], o[j][5], o[j][6], o[j][7]);
+        store_vec4<T>(dst + 8, o[j][8], o[j][9], o[j][10], o[j][11]);
+      }
+    }
+  }
+}
+
+extern "C" int ffsr_modulate_hr_v2(const float* const* imgs, const void* m32, int m32_dtype, const float* w2, const float* b2,
+                                   int B, int H, int W, int clamp01, float* ecol, void* cat3, long long cat3_sX,
+                                   int cat3_dtype, cudaStream_t stream) {
+  FFSR_REQUIRE(imgs && imgs[0] && imgs[1] && imgs[2] && imgs[3] && ecol && m32 && w2 && b2, FFSR_ERR_ARG, "modulate_hr_v2: null pointer");
+  FFSR_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && 4 * H <= 65535, FFSR_ERR_ARG, "modulate_hr_v2: bad shape");
+  FFSR_REQUIRE(m32_dtype == FFSR_DT_F32 || (m32_dtype == FFSR_DT_BF16 && cat3_dtype == FFSR_DT_BF16), FFSR_ERR_ARG,
+               "modulate_hr_v2: bf16 features belong to the bf16 mode (bf16 concat slice)");
+  const int esz = cat3_dtype == FFSR_DT_BF16 ? 2 : 4;
+  FFSR_REQUIRE(!cat3 || (((uintptr_t)cat3 % 16) == 0 && (cat3_sX * esz) % 16 == 0 && cat3_sX >= 12), FFSR_ERR_ALIGN,
+               "modulate_hr_v2: concat slice must be 16B aligned with a 16B-multiple pixel stride");
+  FFSR_REQUIRE(((uintptr_t)m32 % 16) == 0 && ((uintptr_t)ecol % 8) == 0, FFSR_ERR_ALIGN, "modulate_hr_v2: m32 must be 16B aligned");
+  for (int e = 0; e < 4; ++e) FFSR_REQUIRE(((uintptr_t)imgs[e] % 8) == 0, FFSR_ERR_ALIGN, "modulate_hr_v2: expert images must be 8B aligned");
+  Img4 im;
+  for (int e = 0; e < 4; ++e) im.p[e] = imgs[e];
+  dim3 grid(ceil_div(W + 1, 128), 4 * H, B);
+  if (m32_dtype == FFSR_DT_BF16)
+    k_modulate_hr4<__nv_bfloat16, __nv_bfloat16, true><<<grid, 128, 0, stream>>>(im, (const __nv_bfloat16*)m32, w2, b2, B, H, W, clamp01, ecol, (__nv_bfloat16*)cat3, cat3_sX);
+  else if (cat3_dtype == FFSR_DT_BF16)
+    k_modulate_hr4<float, __nv_bfloat16, true><<<grid, 128, 0, stream>>>(im, (const float*)m32, w2, b2, B, H, W, clamp01, ecol, (__nv_bfloat16*)cat3, cat3_sX);
+  else
+    k_modulate_hr4<float, float, false><<<grid, 128, 0, stream>>>(im, (const float*)m32, w2, b2, B, H, W, clamp01, ecol, (float*)cat3, cat3_sX);
+  return ffsr_check_launch("modulate_hr_v2");
+}
+
 // ------------------------------------------------------------------------------------------
 // /2 and /4 bilinear (exact 2-tap averages) of the 12-channel expert stack
 // ------------------------------------------------------------------------------------------

@@ -114,6 +114,7 @@ class FusionEngine:
         self.fold_crossband = True     # band_proj -> LayerNorm -> in_proj folded to 3+1 MACs per qkv channel
         # bf16 mode: each edge refiner as ONE tile-resident kernel (csrc/edge_chain.cu) instead of six conv launches
         self.edge_chain = os.environ.get("FFSR_EDGE_CHAIN0") is None
+        self.modulate_v2 = os.environ.get("FFSR_MODULATE_V1") is None   # 4 HR px x 4 experts per thread, bf16 features
         self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ weights
@@ -587,7 +588,7 @@ class FusionEngine:
             t2 = self._buf("co.t2", (N4, H, W, 128), dev)
             self.conv(nhwc(hdn), N4, H, W, 256, "co.f2", 128, 1, nhwc(t2), epi=K.EPI_RESIDUAL, r1=nhwc(t1))
             xg = self._lka_block("co.lka", "collaborative.lka_global", t2, "co", lp=lp)
-            m32 = self._buf("co.m32", (N4, H, W, 32), dev)
+            m32 = self._buf("co.m32", (N4, H, W, 32), dev, dtype=adt if self.modulate_v2 else f32)
             self.conv(nhwc(xg), N4, H, W, 128, "co.m0", 32, 1, nhwc(m32), groups=4, bias_name="co.m0b")
 
         # ---------------- HR: modulation + expert pyramid ----------------
@@ -596,9 +597,14 @@ class FusionEngine:
         cat2 = self._buf("cat2", (B, 2 * H, 2 * W, 80), dev, dtype=adt, zero=True)
         s1in = self._buf("s1in", (B, H, W, 16), dev, dtype=adt, zero=True)
         ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in imgs])
-        self._call(lib.ffsr_modulate_hr, ptrs, m32.data_ptr() if m32 is not None else None,
-                   w["co.m2"].data_ptr(), w["co.m2b"].data_ptr(), B, H, W, 0 if m.training else 1, ecol.data_ptr(),
-                   cat3.data_ptr() + 64 * esz, 80, ADT, S)
+        if m32 is not None and self.modulate_v2:
+            self._call(lib.ffsr_modulate_hr_v2, ptrs, m32.data_ptr(), K.DT_BF16 if m32.dtype == torch.bfloat16 else K.DT_F32,
+                       w["co.m2"].data_ptr(), w["co.m2b"].data_ptr(), B, H, W, 0 if m.training else 1, ecol.data_ptr(),
+                       cat3.data_ptr() + 64 * esz, 80, ADT, S)
+        else:
+            self._call(lib.ffsr_modulate_hr, ptrs, m32.data_ptr() if m32 is not None else None,
+                       w["co.m2"].data_ptr(), w["co.m2b"].data_ptr(), B, H, W, 0 if m.training else 1, ecol.data_ptr(),
+                       cat3.data_ptr() + 64 * esz, 80, ADT, S)
         self._call(lib.ffsr_expert_downsample, ecol.data_ptr(), B, Hh, Wh, cat2.data_ptr() + 64 * esz, 80,
                    s1in.data_ptr(), 16, ADT, S)
 

@@ -158,6 +158,11 @@ size_t ffsr_conv_params_size(void);
 int ffsr_modulate_hr(const float* const* imgs, const float* m32, const float* w2, const float* b2, int B, int H,
                      int W, int clamp01, float* ecol, void* cat3, long long cat3_sX, int cat3_dtype,
                      cudaStream_t stream);
+/* Same operation, four HR pixels (one LR cell phase) x four experts per thread; m32 may be bf16 ([B][4][H][W][32], bf16 mode).
+ * Requires m32 != NULL (use ffsr_modulate_hr for the pass-through case). */
+int ffsr_modulate_hr_v2(const float* const* imgs, const void* m32, int m32_dtype, const float* w2, const float* b2, int B,
+                        int H, int W, int clamp01, float* ecol, void* cat3, long long cat3_sX, int cat3_dtype,
+                        cudaStream_t stream);
 /* bilinear /2 and /4 of the expert stack (hierarchical_fusion.py:156-159, 171-174) into the
  * stage-2 concat buffer slice and the stage-1 input */
 int ffsr_expert_downsample(const float* ecol, int B, int Hh, int Wh, void* cat2, long long cat2_sX, void* s1in,
