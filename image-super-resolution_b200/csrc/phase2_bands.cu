@@ -3,6 +3,7 @@
 // (src/models/multi_domain_frequency.py:146-196, 251-299, 352-385).
 // Output layout: raw9[B][9][3][H][W] fp32 (band-major planar), so raw9[:, i] is the
 // reference's i-th [B,3,H,W] band.  HBM-bound, tiny next to the HR phases.
+#include <stdlib.h>
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------
@@ -294,6 +295,215 @@ __global__ void __launch_bounds__(128) k_fft_rows_inv(const double2* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Staged shared-memory FFT path (the default for H, W <= 2048: 212 KB of shared memory at 2048).  The dense-DFT kernels above cost O(N) complex MACs per
+// point in fp64 with one thread per output (0.55 ms per 339x510 image, 0.5 % of the HBM roofline).  Here every 1-D transform is
+// one Cooley-Tukey split N = N1 * N2 (N1 the divisor closest to sqrt(N); 510 = 17 * 30, 339 = 3 * 113, primes degenerate to the
+// dense form) evaluated on CW independent sequences held in shared memory as [n][CW]:
+//     t[n2][k1] = W_N^{n2 k1} * sum_{n1} x[N2 n1 + n2] W_N1^{n1 k1}        (N1 terms)
+//     X[k1 + N1 k2] =          sum_{n2} t[n2][k1]    W_N2^{n2 k2}        (N2 terms)
+// in fp32 with twiddles read from the fp64-generated table (all three twiddle families are powers of W_N).  Rows: CW image
+// rows per block; columns: a strip of CW spectrum columns per block does forward transform, mask * scale and inverse
+// transform without leaving shared memory.  Three launches, ~4 MB of fp32 complex intermediates.
+// ------------------------------------------------------------------------------------
+constexpr int FFT2_CW = 4;
+constexpr int FFT2_THREADS = 256;
+
+// in -> out over [N][CW] shared-memory arrays (tmp: scratch of the same size).  dir = -1: e^{-i...} (forward), +1: inverse.
+// Callers synchronise before (inputs written) and after (outputs read).
+template <int CW>
+__device__ __forceinline__ void strip_fft(const float2* __restrict__ in, float2* __restrict__ tmp, float2* __restrict__ out,
+                                          const float2* __restrict__ tw, int N, int N1, int N2, float sg) {
+  const int total = N * CW;
+  for (int o = threadIdx.x; o < total; o += blockDim.x) {
+    const int c = o % CW, q = o / CW;
+    const int n2 = q / N1, k1 = q - n2 * N1;
+    const int inc = k1 * N2;                       // W_N1^{k1} = W_N^{k1 N2}
+    const float2* p = in + n2 * CW + c;
+    const int pstride = N2 * CW;
+    float re = 0.f, im = 0.f;
+    int idx = 0;
+    for (int n1 = 0; n1 < N1; ++n1) {
+      const float2 v = p[n1 * pstride];
+      const float2 w = tw[idx];
+      const float ws = sg * w.y;
+      re = fmaf(v.x, w.x, fmaf(-v.y, ws, re));
+      im = fmaf(v.x, ws, fmaf(v.y, w.x, im));
+      idx += inc;
+      if (idx >= N) idx -= N;
+    }
+    const float2 w = tw[n2 * k1];
+    const float ws = sg * w.y;
+    tmp[o] = make_float2(re * w.x - im * ws, re * ws + im * w.x);      // o = (n2 * N1 + k1) * CW + c
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < total; o += blockDim.x) {
+    const int c = o % CW, k = o / CW;
+    const int k2 = k / N1, k1 = k - k2 * N1;
+    const int inc = k2 * N1;                       // W_N2^{k2} = W_N^{k2 N1}
+    const float2* p = tmp + k1 * CW + c;
+    const int pstride = N1 * CW;
+    float re = 0.f, im = 0.f;
+    int idx = 0;
+    for (int n2 = 0; n2 < N2; ++n2) {
+      const float2 v = p[n2 * pstride];
+      const float2 w = tw[idx];
+      const float ws = sg * w.y;
+      re = fmaf(v.x, w.x, fmaf(-v.y, ws, re));
+      im = fmaf(v.x, ws, fmaf(v.y, w.x, im));
+      idx += inc;
+      if (idx >= N) idx -= N;
+    }
+    out[o] = make_float2(re, im);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void fft2_load_tw(float2* stw, const double2* __restrict__ tw, int N) {
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    const double2 w = tw[t];
+    stw[t] = make_float2((float)w.x, (float)w.y);
+  }
+}
+
+// rows, real -> half spectrum: A[bc][y][0..Wf)
+__global__ void __launch_bounds__(FFT2_THREADS) k_fft2_rows_fwd(const float* __restrict__ x, int H, int W, int Wf, int N1, int N2,
+                                                                const double2* __restrict__ tw, float2* __restrict__ A) {
+  extern __shared__ float2 fsm[];
+  constexpr int CW = FFT2_CW;
+  float2* b0 = fsm;
+  float2* b1 = b0 + W * CW;
+  float2* b2 = b1 + W * CW;
+  float2* stw = b2 + W * CW;
+  fft2_load_tw(stw, tw, W);
+  const int y0 = blockIdx.x * CW, bc = blockIdx.y;
+  for (int o = threadIdx.x; o < W * CW; o += blockDim.x) {
+    const int r = o / W, n = o - r * W;            // coalesced along the row
+    const int y = y0 + r;
+    b0[n * CW + r] = make_float2(y < H ? x[((long)bc * H + y) * W + n] : 0.f, 0.f);
+  }
+  __syncthreads();
+  strip_fft<CW>(b0, b1, b2, stw, W, N1, N2, -1.f);
+  for (int o = threadIdx.x; o < Wf * CW; o += blockDim.x) {
+    const int r = o / Wf, k = o - r * Wf;
+    const int y = y0 + r;
+    if (y < H) A[((long)bc * H + y) * Wf + k] = b2[k * CW + r];
+  }
+}
+
+// columns: forward, * mask * scale, inverse; in place on A (each block owns its CW columns)
+__global__ void __launch_bounds__(FFT2_THREADS) k_fft2_cols(float2* __restrict__ A, int H, int Wf, int N1, int N2,
+                                                            const double2* __restrict__ tw, const float* __restrict__ mask,
+                                                            float scale, float2* __restrict__ spec_out) {
+  extern __shared__ float2 fsm[];
+  constexpr int CW = FFT2_CW;
+  float2* b0 = fsm;
+  float2* b1 = b0 + H * CW;
+  float2* b2 = b1 + H * CW;
+  float2* stw = b2 + H * CW;
+  fft2_load_tw(stw, tw, H);
+  const int k0 = blockIdx.x * CW, bc = blockIdx.y;
+  float2* base = A + (long)bc * H * Wf;
+  for (int o = threadIdx.x; o < H * CW; o += blockDim.x) {
+    const int y = o / CW, c = o - y * CW;
+    b0[o] = (k0 + c < Wf) ? base[(long)y * Wf + k0 + c] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  strip_fft<CW>(b0, b1, b2, stw, H, N1, N2, -1.f);
+  for (int o = threadIdx.x; o < H * CW; o += blockDim.x) {
+    const int l = o / CW, c = o - l * CW;
+    float mm = scale;
+    if (mask && k0 + c < Wf) mm *= mask[(long)l * Wf + k0 + c];
+    const float2 v = b2[o];
+    b2[o] = make_float2(v.x * mm, v.y * mm);
+    if (spec_out && k0 + c < Wf) spec_out[((long)bc * H + l) * Wf + k0 + c] = b2[o];    // training: the (scaled) spectrum itself
+  }
+  __syncthreads();
+  if (spec_out) return;
+  strip_fft<CW>(b2, b1, b0, stw, H, N1, N2, 1.f);
+  for (int o = threadIdx.x; o < H * CW; o += blockDim.x) {
+    const int y = o / CW, c = o - y * CW;
+    if (k0 + c < Wf) base[(long)y * Wf + k0 + c] = b0[o];
+  }
+}
+
+// rows, half spectrum -> real (irfft semantics: imaginary parts of the DC and Nyquist bins ignored), then the two bands
+__global__ void __launch_bounds__(FFT2_THREADS) k_fft2_rows_inv(const float2* __restrict__ G, const float* __restrict__ x, int H,
+                                                                int W, int Wf, int N1, int N2, const double2* __restrict__ tw,
+                                                                float scale, const float* __restrict__ band_scale,
+                                                                float* __restrict__ raw9, float* __restrict__ low_out) {
+  extern __shared__ float2 fsm[];
+  constexpr int CW = FFT2_CW;
+  float2* b0 = fsm;
+  float2* b1 = b0 + W * CW;
+  float2* b2 = b1 + W * CW;
+  float2* stw = b2 + W * CW;
+  fft2_load_tw(stw, tw, W);
+  const int y0 = blockIdx.x * CW, bc = blockIdx.y, b = bc / 3, ch = bc % 3;
+  const bool even = (W % 2) == 0;
+  for (int o = threadIdx.x; o < W * CW; o += blockDim.x) {
+    const int r = o / W, k = o - r * W;
+    const int y = y0 + r;
+    float2 v = make_float2(0.f, 0.f);
+    if (y < H) {
+      const float2* row = G + ((long)bc * H + y) * Wf;
+      if (k == 0 || (even && k == W / 2)) v = make_float2(row[k].x, 0.f);
+      else if (k < Wf) v = row[k];
+      else { const float2 g = row[W - k]; v = make_float2(g.x, -g.y); }
+    }
+    b0[k * CW + r] = v;
+  }
+  __syncthreads();
+  strip_fft<CW>(b0, b1, b2, stw, W, N1, N2, 1.f);
+  const float s0 = band_scale ? band_scale[0] : 1.f, s1 = band_scale ? band_scale[1] : 1.f;
+  for (int o = threadIdx.x; o < W * CW; o += blockDim.x) {
+    const int r = o / W, n = o - r * W;
+    const int y = y0 + r;
+    if (y >= H) continue;
+    const float low = b2[n * CW + r].x * scale;
+    const long pix = (long)y * W + n;
+    if (low_out) { low_out[(long)bc * H * W + pix] = low; continue; }
+    const float xin = x[(long)bc * H * W + pix];
+    raw9[(((long)b * 9 + 7) * 3 + ch) * H * W + pix] = low * s0;
+    raw9[(((long)b * 9 + 8) * 3 + ch) * H * W + pix] = (xin - low) * s1;
+  }
+}
+
+static void fft2_split(int N, int* n1, int* n2) {
+  int best = 1;
+  for (int d = 1; (long)d * d <= N; ++d)
+    if (N % d == 0) best = d;
+  *n1 = best;
+  *n2 = N / best;
+}
+static bool fft2_ok(int H, int W) { return H <= 2048 && W <= 2048 && getenv("FFSR_FFT_DENSE") == nullptr; }
+static size_t fft2_smem(int N) { return (size_t)(3 * FFT2_CW + 1) * N * sizeof(float2); }
+
+// low-pass of B*3 planes through the staged path; A: fp32 complex scratch [B*3][H][Wf]
+static int fft2_lowpass(const float* x, int B, int H, int W, const float* mask, const void* tw_h, const void* tw_w, float2* A,
+                        const float* band_scale, float* raw9, float* low_out, cudaStream_t stream) {
+  const int Wf = W / 2 + 1;
+  int w1, w2, h1, h2;
+  fft2_split(W, &w1, &w2);
+  fft2_split(H, &h1, &h2);
+  const float scale = (float)(1.0 / sqrt((double)H * (double)W));
+  static bool attr = false;
+  if (!attr) {
+    attr = true;
+    cudaFuncSetAttribute(k_fft2_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft2_smem(2048));
+    cudaFuncSetAttribute(k_fft2_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft2_smem(2048));
+    cudaFuncSetAttribute(k_fft2_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft2_smem(2048));
+  }
+  int rc;
+  k_fft2_rows_fwd<<<dim3(ceil_div(H, FFT2_CW), B * 3), FFT2_THREADS, fft2_smem(W), stream>>>(x, H, W, Wf, w1, w2, (const double2*)tw_w, A);
+  if ((rc = ffsr_check_launch("fft2_rows_fwd"))) return rc;
+  k_fft2_cols<<<dim3(ceil_div(Wf, FFT2_CW), B * 3), FFT2_THREADS, fft2_smem(H), stream>>>(A, H, Wf, h1, h2, (const double2*)tw_h, mask, scale, nullptr);
+  if ((rc = ffsr_check_launch("fft2_cols"))) return rc;
+  k_fft2_rows_inv<<<dim3(ceil_div(H, FFT2_CW), B * 3), FFT2_THREADS, fft2_smem(W), stream>>>(A, x, H, W, Wf, w1, w2, (const double2*)tw_w, scale,
+                                                                                               band_scale, raw9, low_out);
+  return ffsr_check_launch("fft2_rows_inv");
+}
+
 extern "C" size_t ffsr_fft_workspace_bytes(int B, int H, int W) {
   const size_t Wf = (size_t)W / 2 + 1;
   const size_t cplx = (size_t)B * 3 * H * Wf * sizeof(double2);
@@ -317,6 +527,7 @@ extern "C" int ffsr_fft_bands(const float* lr, int B, int H, int W, const float*
   int rc;
   k_fft_mask<<<dim3(ceil_div(Wf, 128), H), 128, 0, stream>>>(logits, mask_size, H, Wf, temperature, mask);
   if ((rc = ffsr_check_launch("fft_mask"))) return rc;
+  if (fft2_ok(H, W)) return fft2_lowpass(lr, B, H, W, mask, tw_h, tw_w, (float2*)A, band_scale, raw9, nullptr, stream);
   k_fft_rows_fwd<<<dim3(ceil_div(Wf, 128), H, B * 3), 128, 0, stream>>>(lr, H, W, Wf, (const double2*)tw_w, A);
   if ((rc = ffsr_check_launch("fft_rows_fwd"))) return rc;
   dim3 gc(ceil_div(Wf, 32), ceil_div(H, 8), B * 3);
@@ -362,6 +573,7 @@ extern "C" int ffsr_fft_lowpass(const float* x, int B, int H, int W, const float
   const size_t cplx = (size_t)B * 3 * H * Wf * sizeof(double2);
   double2* A = (double2*)ws;
   double2* F = (double2*)((char*)ws + cplx);
+  if (fft2_ok(H, W)) return fft2_lowpass(x, B, H, W, mask, tw_h, tw_w, (float2*)A, nullptr, nullptr, low, stream);
   const double scale = 1.0 / sqrt((double)H * (double)W);
   dim3 gc(ceil_div(Wf, 32), ceil_div(H, 8), B * 3);
   k_fft_rows_fwd<<<dim3(ceil_div(Wf, 128), H, B * 3), 128, 0, stream>>>(x, H, W, Wf, (const double2*)tw_w, A);
