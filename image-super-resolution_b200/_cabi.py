@@ -81,6 +81,8 @@ PROTOTYPES = {
     "ffsr_crossband_out": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ffsr_lka_depthwise": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "ffsr_layernorm": (_I, [_P, _L, _I, _P, _P, _P, _I, _P]),
+    "ffsr_layernorm128_bf16": (_I, [_P, _L, _P, _P, _P, _P]),
+    "ffsr_lka_depthwise_in": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "ffsr_token_attention": (_I, [_P, _I, _I, _L, _I, _P, _I, _P]),
     "ffsr_gate_finalize": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "ffsr_conv2d": (_I, [C.POINTER(ConvParams), _P]),

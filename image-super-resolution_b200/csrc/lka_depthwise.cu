@@ -15,7 +15,8 @@ constexpr int R21 = 16;  // outputs per thread along the conv axis for the 21-ta
 }
 
 // BN is folded to y = x*k + d (eval: running stats; train: batch stats computed upstream).
-__global__ void __launch_bounds__(256) k_lka_dw5(const float* __restrict__ x, int H, int W, int C,
+template <typename TI>
+__global__ void __launch_bounds__(256) k_lka_dw5(const TI* __restrict__ x, int H, int W, int C,
                                                  const float* __restrict__ bn_k, const float* __restrict__ bn_d,
                                                  const float* __restrict__ w5, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -33,16 +34,16 @@ __global__ void __launch_bounds__(256) k_lka_dw5(const float* __restrict__ x, in
   for (int a = 0; a < R5; ++a)
 #pragma unroll
     for (int b = 0; b < R5; ++b) acc[a][b] = 0.f;
-  const float* img = x + (long)n * H * W * C;
+  const TI* img = x + (long)n * H * W * C;
   if (y0 >= 2 && y0 + R5 + 2 <= H && x0 >= 2 && x0 + R5 + 2 <= W) {
     // interior patch: no bounds tests, 32-bit strided offsets (the kernel is issue-bound, not HBM-bound)
-    const float* p = img + ((long)(y0 - 2) * W + (x0 - 2)) * C + c;
+    const TI* p = img + ((long)(y0 - 2) * W + (x0 - 2)) * C + c;
     const int rs = W * C;
 #pragma unroll
     for (int iy = 0; iy < R5 + 4; ++iy) {
       float v[R5 + 4];
 #pragma unroll
-      for (int i = 0; i < R5 + 4; ++i) v[i] = fmaf(p[iy * rs + i * C], k, d);
+      for (int i = 0; i < R5 + 4; ++i) v[i] = fmaf(to_f32<TI>(p[iy * rs + i * C]), k, d);
 #pragma unroll
       for (int a = 0; a < R5; ++a) {
         const int dy = iy - a;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) k_lka_dw5(const float* __restrict__ x, in
 #pragma unroll
     for (int i = 0; i < R5 + 4; ++i) {
       const int xx = x0 + i - 2;
-      v[i] = (xx >= 0 && xx < W) ? fmaf(img[((long)yy * W + xx) * C + c], k, d) : 0.f;
+      v[i] = (xx >= 0 && xx < W) ? fmaf(to_f32<TI>(img[((long)yy * W + xx) * C + c]), k, d) : 0.f;
     }
 #pragma unroll
     for (int a = 0; a < R5; ++a) {
@@ -156,9 +157,25 @@ __global__ void __launch_bounds__(256) k_lka_dw21(const float* __restrict__ in, 
 }
 
 // x: [N][H][W][C] -> out: [N][H][W][C]; tmp1/tmp2: same-size scratch (tmp2 may alias out? no: distinct)
+static int lka_depthwise_impl(const void* x, int x_dtype, int N, int H, int W, int C, const float* bn_k, const float* bn_d,
+                              const float* w5, const float* wh, const float* wv, float* tmp1, float* tmp2, void* out,
+                              int out_dtype, cudaStream_t stream);
+
 extern "C" int ffsr_lka_depthwise(const float* x, int N, int H, int W, int C, const float* bn_k, const float* bn_d,
                                   const float* w5, const float* wh, const float* wv, float* tmp1, float* tmp2,
                                   void* out, int out_dtype, cudaStream_t stream) {
+  return lka_depthwise_impl(x, 0, N, H, W, C, bn_k, bn_d, w5, wh, wv, tmp1, tmp2, out, out_dtype, stream);
+}
+// same chain with a bf16 input tensor (bf16 mode: the Phase-4 residual stream is stored as bf16)
+extern "C" int ffsr_lka_depthwise_in(const void* x, int x_dtype, int N, int H, int W, int C, const float* bn_k,
+                                     const float* bn_d, const float* w5, const float* wh, const float* wv, float* tmp1,
+                                     float* tmp2, void* out, int out_dtype, cudaStream_t stream) {
+  return lka_depthwise_impl(x, x_dtype, N, H, W, C, bn_k, bn_d, w5, wh, wv, tmp1, tmp2, out, out_dtype, stream);
+}
+
+static int lka_depthwise_impl(const void* x, int x_dtype, int N, int H, int W, int C, const float* bn_k, const float* bn_d,
+                              const float* w5, const float* wh, const float* wv, float* tmp1, float* tmp2, void* out,
+                              int out_dtype, cudaStream_t stream) {
   FFSR_REQUIRE(x && bn_k && bn_d && w5 && wh && wv && tmp1 && tmp2 && out, FFSR_ERR_ARG, "lka_depthwise: null pointer");
   FFSR_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 32 == 0, FFSR_ERR_ARG, "lka_depthwise: C must be a multiple of 32");
   FFSR_REQUIRE(N <= 65535 && (long)H * W / 4 < 65535L * 4, FFSR_ERR_ARG, "lka_depthwise: grid too large");
@@ -167,7 +184,8 @@ extern "C" int ffsr_lka_depthwise(const float* x, int N, int H, int W, int C, co
   {
     dim3 block(cx, ty);
     dim3 grid(C / cx, ceil_div((long)ceil_div(H, R5) * ceil_div(W, R5), ty), N);
-    k_lka_dw5<<<grid, block, 0, stream>>>(x, H, W, C, bn_k, bn_d, w5, tmp1);
+    if (x_dtype == 1) k_lka_dw5<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, H, W, C, bn_k, bn_d, w5, tmp1);
+    else k_lka_dw5<float><<<grid, block, 0, stream>>>((const float*)x, H, W, C, bn_k, bn_d, w5, tmp1);
     int rc = ffsr_check_launch("lka_dw5");
     if (rc) return rc;
   }
@@ -209,7 +227,7 @@ extern "C" int ffsr_dwconv_stage(const float* in, int N, int H, int W, int C, in
   dim3 block(cx, ty);
   if (kind == 0) {
     dim3 grid(C / cx, ceil_div((long)ceil_div(H, R5) * ceil_div(W, R5), ty), N);
-    k_lka_dw5<<<grid, block, 0, stream>>>(in, H, W, C, bn_k, bn_d, w, out);
+    k_lka_dw5<float><<<grid, block, 0, stream>>>(in, H, W, C, bn_k, bn_d, w, out);
   } else if (kind == 1) {
     dim3 grid(C / cx, ceil_div((long)H * ceil_div(W, R21), ty), N);
     k_lka_dw21<0, float><<<grid, block, 0, stream>>>(in, H, W, C, w, out);

@@ -329,6 +329,44 @@ extern "C" int ffsr_layernorm(const float* x, long rows, int E, const float* w, 
   return ffsr_check_launch("layernorm");
 }
 
+// bf16 rows of 128 channels -> bf16 (Phase 4 in bf16 mode, where the residual stream is stored as bf16): one warp per row, one
+// 8-byte load and store per lane, statistics in fp32.
+__global__ void __launch_bounds__(256) k_layernorm128_bf16(const __nv_bfloat16* __restrict__ x, long rows, const float* __restrict__ w,
+                                                           const float* __restrict__ b, __nv_bfloat16* __restrict__ y) {
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint2 u = *reinterpret_cast<const uint2*>(x + row * 128 + lane * 4);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  float v[4] = {a.x, a.y, c.x, c.y};
+  float sum = (v[0] + v[1]) + (v[2] + v[3]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / 128.0f);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[i] -= mean; sq = fmaf(v[i], v[i], sq); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.0f / 128.0f) + 1e-5f);
+  const float4 w4 = *reinterpret_cast<const float4*>(w + lane * 4), b4 = *reinterpret_cast<const float4*>(b + lane * 4);
+  __nv_bfloat162 o0 = __floats2bfloat162_rn(fmaf(v[0] * rstd, w4.x, b4.x), fmaf(v[1] * rstd, w4.y, b4.y));
+  __nv_bfloat162 o1 = __floats2bfloat162_rn(fmaf(v[2] * rstd, w4.z, b4.z), fmaf(v[3] * rstd, w4.w, b4.w));
+  uint2 ou;
+  ou.x = *reinterpret_cast<uint32_t*>(&o0);
+  ou.y = *reinterpret_cast<uint32_t*>(&o1);
+  *reinterpret_cast<uint2*>(y + row * 128 + lane * 4) = ou;
+}
+
+extern "C" int ffsr_layernorm128_bf16(const void* x, long rows, const float* w, const float* b, void* y, cudaStream_t stream) {
+  FFSR_REQUIRE(x && w && b && y && rows > 0, FFSR_ERR_ARG, "layernorm128_bf16: bad argument");
+  FFSR_REQUIRE(((uintptr_t)x % 8) == 0 && ((uintptr_t)y % 8) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)b % 16) == 0, FFSR_ERR_ALIGN,
+               "layernorm128_bf16: alignment");
+  k_layernorm128_bf16<<<ceil_div(rows, 8), 256, 0, stream>>>((const __nv_bfloat16*)x, rows, w, b, (__nv_bfloat16*)y);
+  return ffsr_check_launch("layernorm128_bf16");
+}
+
 // ------------------------------------------------------------------------------------
 // Token attention core (Phase 4): softmax(q k^T / 4) v over the T tokens of each LR pixel.
 // Token-major ("expert-major") layout: qkv[B][T][HW][3E] -> ctx[B][T][HW][E], head_dim 16.

@@ -115,6 +115,7 @@ class FusionEngine:
         # bf16 mode: each edge refiner as ONE tile-resident kernel (csrc/edge_chain.cu) instead of six conv launches
         self.edge_chain = os.environ.get("FFSR_EDGE_CHAIN0") is None
         self.modulate_v2 = os.environ.get("FFSR_MODULATE_V1") is None   # 4 HR px x 4 experts per thread, bf16 features
+        self.p4_bf16_stream = os.environ.get("FFSR_P4_F32_STREAM") is None  # bf16 mode: Phase-4 residual stream stored as bf16
         self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ weights
@@ -337,11 +338,11 @@ class FusionEngine:
         N, H, W, Cc = x.shape
         dev, w = x.device, self._w
         adt = torch.bfloat16 if lp else torch.float32
-        t1 = self._buf(name + ".lka_t1", x.shape, dev)
+        t1 = self._buf(name + ".lka_t1", x.shape, dev)                      # fp32 scratch of the depthwise chain
         t2 = self._buf(name + ".lka_t2", x.shape, dev)
         a = self._buf(name + ".lka_a", x.shape, dev, dtype=adt)
-        self._call(self.lib.ffsr_lka_depthwise, x.data_ptr(), N, H, W, Cc, w[key + ".k1"].data_ptr(),
-                   w[key + ".d1"].data_ptr(), w[key + ".w5"].data_ptr(), w[key + ".wh"].data_ptr(),
+        self._call(self.lib.ffsr_lka_depthwise_in, x.data_ptr(), K.DT_BF16 if x.dtype == torch.bfloat16 else K.DT_F32, N, H, W, Cc,
+                   w[key + ".k1"].data_ptr(), w[key + ".d1"].data_ptr(), w[key + ".w5"].data_ptr(), w[key + ".wh"].data_ptr(),
                    w[key + ".wv"].data_ptr(), t1.data_ptr(), t2.data_ptr(), a.data_ptr(),
                    K.DT_BF16 if lp else K.DT_F32, self._stream)
         self.launches += 2
@@ -536,9 +537,12 @@ class FusionEngine:
                     raise NotImplementedError(
                         f"expert feature '{n}' has shape {tuple(f.shape)}; the sm_100a path needs [B,C,{H},{W}] "
                         "(features at LR resolution, as CachedSRDataset provides)")
-            tokens = self._buf("co.tok", (B, 4, H, W, 128), dev, zero=True)
+            # bf16 mode: the residual stream (tokens, t1, t2) is stored as bf16 -- every Phase-4 launch is bound by the HBM
+            # round trip of these [4][H][W][128] tensors, and the phase only feeds a sigmoid damped by 0.2
             cin_exp = {n: co.align_layers[n].weight.shape[1] for n in EXPERT_ORDER}
             fast_align = lp and len(have) == 4 and all(feats[n].shape[1] == cin_exp[n] for n in EXPERT_ORDER)
+            rdt = torch.bfloat16 if (fast_align and self.p4_bf16_stream) else f32
+            tokens = self._buf("co.tok", (B, 4, H, W, 128), dev, dtype=rdt, zero=True)
             if fast_align:
                 # bf16 mode: NCHW fp32 features -> one bf16 channels-last buffer, then ONE grouped tcgen05 1x1 conv
                 cmax = max(cin_exp.values())
@@ -573,19 +577,23 @@ class FusionEngine:
             tok4 = tokens.view(N4, H, W, 128)
             rows = N4 * H * W
             n1 = self._buf("co.n", (N4, H, W, 128), dev, dtype=adt)
-            self._call(lib.ffsr_layernorm, tok4.data_ptr(), rows, 128, pp("collaborative.norm1.weight"),
-                       pp("collaborative.norm1.bias"), n1.data_ptr(), int(lp), S)
+            def layernorm(src, wn, bn):
+                if src.dtype == torch.bfloat16:
+                    self._call(lib.ffsr_layernorm128_bf16, src.data_ptr(), rows, pp(wn), pp(bn), n1.data_ptr(), S)
+                else:
+                    self._call(lib.ffsr_layernorm, src.data_ptr(), rows, 128, pp(wn), pp(bn), n1.data_ptr(), int(lp), S)
+
+            layernorm(tok4, "collaborative.norm1.weight", "collaborative.norm1.bias")
             qkv = self._buf("co.qkv", (N4, H, W, 384), dev, dtype=adt)
             self.conv(nhwc(n1), N4, H, W, 128, "co.qkv", 384, 1, nhwc(qkv))
             ctx = self._buf("co.ctx", (N4, H, W, 128), dev, dtype=adt)
             self._call(lib.ffsr_token_attention, qkv.data_ptr(), B, 4, H * W, 128, ctx.data_ptr(), int(lp), S)
-            t1 = self._buf("co.t1", (N4, H, W, 128), dev)          # residual stream stays fp32
+            t1 = self._buf("co.t1", (N4, H, W, 128), dev, dtype=rdt)
             self.conv(nhwc(ctx), N4, H, W, 128, "co.out", 128, 1, nhwc(t1), epi=K.EPI_RESIDUAL, r1=nhwc(tok4))
-            self._call(lib.ffsr_layernorm, t1.data_ptr(), rows, 128, pp("collaborative.norm2.weight"),
-                       pp("collaborative.norm2.bias"), n1.data_ptr(), int(lp), S)
+            layernorm(t1, "collaborative.norm2.weight", "collaborative.norm2.bias")
             hdn = self._buf("co.h", (N4, H, W, 256), dev, dtype=adt)
             self.conv(nhwc(n1), N4, H, W, 128, "co.f0", 256, 1, nhwc(hdn), act=K.ACT_GELU)
-            t2 = self._buf("co.t2", (N4, H, W, 128), dev)
+            t2 = self._buf("co.t2", (N4, H, W, 128), dev, dtype=rdt)
             self.conv(nhwc(hdn), N4, H, W, 256, "co.f2", 128, 1, nhwc(t2), epi=K.EPI_RESIDUAL, r1=nhwc(t1))
             xg = self._lka_block("co.lka", "collaborative.lka_global", t2, "co", lp=lp)
             m32 = self._buf("co.m32", (N4, H, W, 32), dev, dtype=adt if self.modulate_v2 else f32)

@@ -95,6 +95,10 @@ int ffsr_crossband_out(const float* x, const float* raw9, int B, int H, int W, i
 int ffsr_lka_depthwise(const float* x, int N, int H, int W, int C, const float* bn_k, const float* bn_d,
                        const float* w5, const float* wh, const float* wv, float* tmp1, float* tmp2, void* out,
                        int out_dtype, cudaStream_t stream);
+/* the same chain reading a bf16 (x_dtype = FFSR_DT_BF16) or fp32 input tensor */
+int ffsr_lka_depthwise_in(const void* x, int x_dtype, int N, int H, int W, int C, const float* bn_k, const float* bn_d,
+                          const float* w5, const float* wh, const float* wv, float* tmp1, float* tmp2, void* out,
+                          int out_dtype, cudaStream_t stream);
 
 /* ---- token helpers (Phase 4) -------------------------------------------------------------
  * nn.LayerNorm rows (large_kernel_attention.py:389,392) and the softmax(QK^T/4)V core of
@@ -102,6 +106,8 @@ int ffsr_lka_depthwise(const float* x, int N, int H, int W, int C, const float* 
  * qkv[B][T][HW][3E] -> ctx[B][T][HW][E] */
 int ffsr_layernorm(const float* x, long rows, int E, const float* w, const float* b, void* y, int out_bf16,
                    cudaStream_t stream);
+/* nn.LayerNorm(128) on bf16 rows -> bf16 rows (Phase 4, bf16 mode: residual stream stored as bf16) */
+int ffsr_layernorm128_bf16(const void* x, long rows, const float* w, const float* b, void* y, cudaStream_t stream);
 int ffsr_token_attention(const void* qkv, int B, int T, long HW, int E, void* ctx, int is_bf16, cudaStream_t stream);
 
 /* ---- Phase 6 gate normalisation  src/models/enhanced_fusion_v2.py:462-465 ---------------- */
