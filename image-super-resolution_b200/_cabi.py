@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libffsr_b200.so")
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 EPI_PLAIN, EPI_RESIDUAL, EPI_LKAGATE, EPI_ACTGRAD = 0, 1, 2, 3
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
+CONV_MULTI_ISSUE = 1          # ffsr_conv_params.flags
 
 
 class FusionLibraryError(RuntimeError):
@@ -37,7 +38,7 @@ class ConvParams(C.Structure):
         ("ch_k", C.c_void_p), ("ch_d", C.c_void_p),
         ("in_dtype", C.c_int), ("out_dtype", C.c_int),
         ("w_dtype", C.c_int), ("r1_dtype", C.c_int), ("r2_dtype", C.c_int),
-        ("out2", C.c_void_p), ("reserved", C.c_int),
+        ("out2", C.c_void_p), ("flags", C.c_int),
     ]
 
 

@@ -38,6 +38,7 @@
 // Epilogue extras for the training graph: an optional bf16 copy of the pre-activation (out2) and FFSR_EPI_ACTGRAD
 // (input gradient multiplied by act'(saved pre-activation of the previous layer)).
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "../../include/ffsr_b200.h"
@@ -1070,22 +1071,38 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
     int want = TC_MMA_WARPS;
     if (const char* e = getenv("FFSR_TC_NMMA")) want = atoi(e);
     a.nmma = 1;
-    // An issuing warp waits for pipeline stages by PARITY, which tells a phase only from its neighbours: when it starts to
-    // wait for use k of a stage, use k - nstages must already have been filled.  The producer fills in order and is at
-    // least as far as the stages this warp consumed last, so this holds iff nmma * (stages per tile) <= nstages.
+    // Every barrier wait is by PARITY, which tells a phase only from its neighbours: whoever waits for use k of a pipeline
+    // stage must KNOW that use k - nstages has completed.  With one issuer that is its own previous wait.  With several, a
+    // stage whose consecutive uses fall to different warps would rest on "the producer issued the earlier load first" --
+    // but TMA loads complete out of order, and a warp that starts waiting one phase early passes at once on the previous
+    // phase's parity (seen on hardware: K = 192, 3 stages per tile in a ring of 8, two issuers -> nondeterministic hangs).
+    // So the ring is trimmed to a multiple of nmma * (stages per tile): tile q and tile q + ring / kiters then use the same
+    // stages AND belong to the same warp, and every wait follows that warp's own wait for the previous phase.
     const int kiters = geom ? a.nchunks : p.ksize * a.nchunks;
-    if (want > 1 && a.b_resident && p.groups == 1 && a.n_nblocks == 1 && halves == 1) {
+    if (const char* e = getenv("FFSR_TC_NSTAGES")) { const int v = atoi(e); if (v >= 1 && v <= a.nstages) a.nstages = v; }   // debug
+    if (want > 1 && (p.flags & FFSR_CONV_MULTI_ISSUE) && a.b_resident && p.groups == 1 && a.n_nblocks == 1 && halves == 1) {
       int n = want >= 3 ? 3 : 2;
       while (n > 1 && n * kiters > a.nstages) --n;
-      // The accumulator ring must be a multiple of the issuing warps (a slot always belongs to the same warp) AND, with
-      // tile ownership in the epilogue, of the four epilogue warp groups: a group waits for its tile's accumulator by
-      // parity too, so the previous use of that slot must have been its own tile.  3 warps -> ring of 12 (N <= 32).
-      if (n == 3 && TC_TMEM_COLS / a.acc_slot >= 12) { a.nmma = 3; a.nacc = 12; }
-      else if (n >= 2 && a.nacc >= 8) { a.nmma = 2; a.nacc = 8; }
-      else if (n >= 2 && a.nacc >= 4) { a.nmma = 2; a.nacc = 4; }
-      else if (n >= 2 && a.nacc >= 2 && !a.epi_own) { a.nmma = 2; a.nacc = 2; }
+      // The accumulator ring must likewise be a multiple of the issuing warps (a slot always belongs to the same warp) AND,
+      // with tile ownership in the epilogue, of the four epilogue warp groups (a group waits for its tile's accumulator by
+      // parity too, so the previous use of that slot must have been its own tile).  3 warps -> ring of 12 (N <= 32).
+      int nm = 1, na = a.nacc;
+      if (n == 3 && TC_TMEM_COLS / a.acc_slot >= 12) { nm = 3; na = 12; }
+      else if (n >= 2 && a.nacc >= 8) { nm = 2; na = 8; }
+      else if (n >= 2 && a.nacc >= 4) { nm = 2; na = 4; }
+      else if (n >= 2 && a.nacc >= 2 && !a.epi_own) { nm = 2; na = 2; }
+      if (nm > 1) {
+        a.nmma = nm;
+        a.nacc = na;
+        a.nstages = a.nstages / (nm * kiters) * (nm * kiters);
+      }
     }
   }
+  if (getenv("FFSR_TC_DEBUG") != nullptr)
+    fprintf(stderr, "[conv_tc] N=%d H=%d W=%d Cin=%d Cout=%d ks=%d groups=%d epi=%d act=%d out_bf16=%d out2=%d | geom=%d halves=%d nblk=%d nchunks=%d "
+                    "kiters=%d nstages=%d resident=%d acc_slot=%d nacc=%d nmma=%d own=%d lean=%d tiles=%lld grid=%d\n",
+            p.N, p.H, p.W, p.Cin, p.Cout, p.ksize, p.groups, p.epi, p.act, a.out_bf16, p.out2 != nullptr, a.geom, a.halves, a.nblk, a.nchunks,
+            a.geom ? a.nchunks : p.ksize * a.nchunks, a.nstages, a.b_resident, a.acc_slot, a.nacc, a.nmma, a.epi_own, a.lean, a.total_tiles, grid);
   k_conv_tc<<<grid, TC_THREADS, smem_bytes, stream>>>(tmA, tmB, a);
   return ffsr_check_launch("conv2d_tc");
 }

@@ -308,6 +308,7 @@ class FusionEngine:
         p.groups = groups
         p.out, p.out_sN, p.out_sY, p.out_sX = out.ptr, out.sN, out.sY, out.sX
         p.act, p.epi = act, epi
+        p.flags = K.CONV_MULTI_ISSUE      # inference launches: up to three MMA-issuing warps on issue-bound layers
         if r1 is not None:
             p.r1, p.r1_sN, p.r1_sY, p.r1_sX = r1.ptr, r1.sN, r1.sY, r1.sX
             p.r1_dtype = K.DT_BF16 if r1.t.dtype == torch.bfloat16 else K.DT_F32
@@ -753,4 +754,8 @@ class FusionEngine:
             inter["fused_before_dynamic"] = fused_before
             inter["gates"] = gates
             inter["difficulty"] = diff
+            # beyond the reference's dict: the raw selector logits and the second derived index of SURVEY §8a-P6,
+            # active = gate_net(r) > 0.7 - 0.5 * difficulty_net(r)   (enhanced_fusion_v2.py:450-466)
+            inter["gate_logits"] = graw.permute(0, 3, 1, 2).clone()
+            inter["active"] = inter["gate_logits"] > (0.7 - 0.5 * diff)
         return out, inter

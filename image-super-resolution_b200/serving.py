@@ -19,6 +19,54 @@ from typing import Dict, Optional
 import torch
 
 
+class PackedImage:
+    """All cached inputs of one image in ONE pinned host buffer, so that staging it is a single cudaMemcpyAsync
+    (nine separate copies per image serialise on the copy engine's launch latency and, with several GPUs behind one
+    host, on the host's memory system).  ``dtype=torch.float16`` is the format the reference's val / TTA caches are
+    stored in (scripts/extract_val_cache.py:167-209, scripts/extract_test_tta_cache.py:296-326); the LR image stays
+    fp32.  Segments are 256-byte aligned; ``views(device_buffer)`` returns typed tensors over a device copy."""
+
+    def __init__(self, lr: torch.Tensor, imgs: Dict[str, torch.Tensor], feats: Optional[Dict[str, torch.Tensor]] = None,
+                 dtype: torch.dtype = torch.float16, pin: bool = True):
+        self.layout = []          # (kind, name, shape, dtype, offset, nbytes)
+        off = 0
+
+        def add(kind, name, t, dt):
+            nonlocal off
+            nb = t.numel() * torch.empty((), dtype=dt).element_size()
+            self.layout.append((kind, name, tuple(t.shape), dt, off, nb))
+            off = (off + nb + 255) // 256 * 256
+
+        add("lr", "lr", lr, torch.float32)
+        for k, v in imgs.items():
+            add("img", k, v, dtype)
+        for k, v in (feats or {}).items():
+            add("feat", k, v, dtype)
+        self.nbytes = off
+        self.buf = torch.empty(off, dtype=torch.uint8)
+        if pin:
+            self.buf = self.buf.pin_memory()
+        src = {"lr": {"lr": lr}, "img": imgs, "feat": feats or {}}
+        for kind, name, shape, dt, o, nb in self.layout:
+            self.buf[o:o + nb].view(dt).view(shape).copy_(src[kind][name])
+        self.payload_bytes = sum(e[5] for e in self.layout)
+
+    def key(self):
+        return tuple((e[0], e[1], e[2], e[3]) for e in self.layout)
+
+    def views(self, buf: torch.Tensor):
+        lr, imgs, feats = None, {}, {}
+        for kind, name, shape, dt, o, nb in self.layout:
+            t = buf[o:o + nb].view(dt).view(shape)
+            if kind == "lr":
+                lr = t
+            elif kind == "img":
+                imgs[name] = t
+            else:
+                feats[name] = t
+        return lr, imgs, (feats or None)
+
+
 class PipelinedFusion:
     """``cuda_graph=True`` (default): the forward of each input set is captured once into a CUDA graph (the device
     buffers of a set are static, so are the engine's workspaces) and replayed; a change of weights, precision or
@@ -50,8 +98,9 @@ class PipelinedFusion:
         """Enqueue one image: pinned host inputs -> SR written into the pinned ``out_host``."""
         i = self._k % self.depth
         self._k += 1
-        if self._sets[i] is None or self._sets[i][0].shape != lr.shape:
+        if self._sets[i] is None or len(self._sets[i]) != 3 or self._sets[i][0].shape != lr.shape:
             self._sets[i] = self._alloc_like(lr, imgs, feats)
+            self._graphs[i] = None
         d_lr, d_imgs, d_feats = self._sets[i]
         with torch.cuda.stream(self.s_in):
             if self._free[i] is not None:
@@ -65,6 +114,38 @@ class PipelinedFusion:
             copied.record(self.s_in)
         self.s_compute.wait_event(copied)
         sr, static = self._forward(i, d_lr, d_imgs, d_feats if feats else None)
+        done = torch.cuda.Event()
+        done.record(self.s_compute)
+        self._free[i] = done
+        self._outs[i] = sr
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(done)
+            out_host.copy_(sr, non_blocking=True)
+            if static:
+                ev = torch.cuda.Event()
+                ev.record(self.s_out)
+                self._out_free[i] = ev
+            else:
+                sr.record_stream(self.s_out)
+
+    def submit_packed(self, packed: "PackedImage", out_host: torch.Tensor) -> None:
+        """Like ``submit`` for a ``PackedImage``: ONE host->device copy of the whole input set."""
+        i = self._k % self.depth
+        self._k += 1
+        cur = self._sets[i]
+        if cur is None or not isinstance(cur, tuple) or len(cur) != 2 or cur[0] != packed.key():
+            dbuf = torch.empty(packed.nbytes, dtype=torch.uint8, device=self.dev)
+            self._sets[i] = (packed.key(), (dbuf,) + tuple(packed.views(dbuf)))
+            self._graphs[i] = None
+        dbuf, d_lr, d_imgs, d_feats = self._sets[i][1]
+        with torch.cuda.stream(self.s_in):
+            if self._free[i] is not None:
+                self.s_in.wait_event(self._free[i])
+            dbuf.copy_(packed.buf, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self.s_in)
+        self.s_compute.wait_event(copied)
+        sr, static = self._forward(i, d_lr, d_imgs, d_feats)
         done = torch.cuda.Event()
         done.record(self.s_compute)
         self._free[i] = done
@@ -183,7 +264,7 @@ def tile_grid(H: int, W: int, ty: int, tx: int):
 @torch.no_grad()
 def fuse_tiled(model, lr: torch.Tensor, expert_imgs: Dict[str, torch.Tensor],
                expert_feats: Optional[Dict[str, torch.Tensor]] = None, grid=(1, 2), halo: int = TILE_HALO_LR,
-               rank: int = 0, world: int = 1, assemble: bool = True) -> torch.Tensor:
+               rank: int = 0, world: int = 1, assemble: bool = True, group=None) -> torch.Tensor:
     """``forward_with_precomputed`` of ONE (batch of) image(s) computed tile by tile; rank r takes tiles r, r+world, ...
 
     Everything behind phase 2 has a finite receptive field, so a tile is the model applied to a window = core + halo
@@ -191,7 +272,8 @@ def fuse_tiled(model, lr: torch.Tensor, expert_imgs: Dict[str, torch.Tensor],
     nine frequency bands are NOT local (global FFT mask; DWT resize ratio depends on H, W): every rank computes them on
     the whole 3-channel LR image (31 FLOP per HR pixel) and crops.  Halos are re-read from the inputs, never exchanged.
     With ``assemble`` (and world > 1) the cores are summed into the full image with one all-reduce (x + 0 is exact);
-    without it the full-size tensor holds this rank's cores and zeros elsewhere."""
+    without it the full-size tensor holds this rank's cores and zeros elsewhere.  ``rank`` / ``world`` are positions inside
+    ``group`` (a torch.distributed process group of the ranks sharing this image; default: all ranks)."""
     eng_model = model
     if eng_model.training:
         raise RuntimeError("fuse_tiled is an inference path: call model.eval() first")
@@ -218,5 +300,5 @@ def fuse_tiled(model, lr: torch.Tensor, expert_imgs: Dict[str, torch.Tensor],
         out[:, :, 4 * y0:4 * y1, 4 * x0:4 * x1] = sr[:, :, oy:oy + 4 * (y1 - y0), ox:ox + 4 * (x1 - x0)]
     if assemble and world > 1:
         import torch.distributed as dist
-        dist.all_reduce(out)
+        dist.all_reduce(out, group=group)
     return out

@@ -48,6 +48,9 @@ typedef struct CUstream_st* cudaStream_t;
                                derivative of the activation that produced its input (r1 = that layer's
                                pre-activation); tcgen05 path only                                  */
 
+#define FFSR_CONV_MULTI_ISSUE 1 /* ffsr_conv_params.flags: the tcgen05 path may spread a CTA's tiles over up to three MMA-issuing
+                                  warps (issue-bound small layers; used by the inference pipeline) */
+
 #define FFSR_DT_F32 0
 #define FFSR_DT_BF16 1
 #define FFSR_DT_F16 2  /* source dtype of cache records only (ffsr_cache_unpack) */
@@ -149,7 +152,7 @@ typedef struct ffsr_conv_params {
   int r1_dtype, r2_dtype;  /* FFSR_DT_* of the residual tensors */
   void* out2;              /* optional (tcgen05 path, FFSR_EPI_PLAIN with an activation): bf16 copy of the
                               PRE-activation conv + bias, same strides as out -- saved for the backward pass */
-  int reserved;
+  int flags;      /* FFSR_CONV_* bits; 0 = defaults */
 } ffsr_conv_params;
 
 int ffsr_conv2d(const ffsr_conv_params* p, cudaStream_t stream);

@@ -54,6 +54,27 @@ def test_shard_edge_cases():
     assert D.max_over_ranks(3.5) == 3.5                                       # no process group: identity
 
 
+def test_job_schedule_covers_every_image_once_and_tiles_the_tail():
+    sys.path.insert(0, ROOT)
+    import isr_b200  # noqa: F401
+    from isr_b200 import dist as D
+    for n, world in [(100, 1), (100, 2), (100, 4), (100, 8), (7, 3), (5, 8), (0, 4), (9, 8)]:
+        whole, tail = D.job_schedule(n, world)
+        assert len(whole) == world
+        seen = sorted([i for w in whole for i in w] + [img for img, _, _ in tail])
+        assert seen == list(range(n)), (n, world)
+        for img, ranks, grid in tail:
+            assert grid[0] * grid[1] == len(ranks) > 1
+        used = [r for _, ranks, _ in tail for r in ranks]
+        assert len(used) == len(set(used))                                    # a rank works on one tail image at most
+    whole, tail = D.job_schedule(100, 8)
+    assert all(len(w) == 12 for w in whole) and whole[3][:2] == [3, 11]      # items[rank::world]
+    assert [(img, ranks, grid) for img, ranks, grid in tail] == [(96, [0, 1], (1, 2)), (97, [2, 3], (1, 2)),
+                                                                  (98, [4, 5], (1, 2)), (99, [6, 7], (1, 2))]
+    whole, tail = D.job_schedule(9, 8)                                        # one left-over image over all 8 ranks
+    assert tail == [(8, list(range(8)), (2, 4))]
+
+
 def _train_worker(rank, world, port, out):
     """N-rank flat-bucket step == single-process gradient accumulation over the same N micro-batches
     (what the reference's accumulation_steps does, train.py:331-357).  CPU tensors + gloo: exercises

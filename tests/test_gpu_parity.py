@@ -145,6 +145,8 @@ def test_phase2_and_phase3_and_gates(B, H, W):
     # bit-exact derived indices
     g_top1 = ints["gates"].cpu().argmax(1)
     assert torch.equal(g_top1, top1), f"{(g_top1 != top1).sum().item()} top-1 expert flips"
+    g_active = ints["active"].cpu()
+    assert torch.equal(g_active, active), f"{(g_active != active).sum().item()} active-expert flips"
 
 
 @pytest.mark.parametrize("B,H,W,perturbed,feats", [
@@ -492,3 +494,34 @@ def test_tiled_single_image_matches_whole_image(precision, tol):
     assert all(y0 % 8 == 0 and x0 % 8 == 0 for y0, _, x0, _ in t) and TILE_HALO_LR % 8 == 0
     with pytest.raises(ValueError):
         tile_grid(16, 16, 4, 1)
+
+
+@pytest.mark.timeout(600)
+def test_headline_size_against_oracle():
+    """BASELINE configs[2] itself (339x510 LR -> 1356x2040 HR): fp32 mode within 1e-4 of the CPU oracle, bf16 mode within
+    0.01 dB PSNR, both derived expert-selection indices bit-exact over all 172,890 LR pixels."""
+    dev = _cuda()
+    H, W = 339, 510
+    m = _model(True)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    lr, imgs, fts, hr = O.synthetic_inputs(1, H, W)
+    g = torch.Generator().manual_seed(77)
+    up = F.interpolate(lr, scale_factor=4, mode="bicubic", align_corners=False)
+    imgs = {k: (up + 0.02 * torch.randn(up.shape, generator=g)).clamp(0, 1) for k in O.EXPERT_ORDER}
+    hr = (up + 0.01 * torch.randn(up.shape, generator=g)).clamp(0, 1)
+    with torch.no_grad():
+        ref, rint = O.run_pipeline(sd, lr, imgs, fts, return_intermediates=True)
+        top1, active = O.derived_indices(sd, rint["routing_lr"], rint["gates"])
+    m.to(dev)
+    lrd, imd, ftd = _to(dev, lr, imgs, fts)
+    sr32, ints = m._run_pipeline(lrd, [imd[k] for k in O.EXPERT_ORDER], ftd, 4 * H, 4 * W, {}, True)
+    err32 = (sr32.cpu() - ref).abs().max().item()
+    assert err32 <= FP32_TOL, f"fp32 max-abs {err32:.3e}"
+    flips = (ints["gates"].cpu().argmax(1) != top1).sum().item()
+    aflips = (ints["active"].cpu() != active).sum().item()
+    assert flips == 0 and aflips == 0, f"{flips} top-1 flips, {aflips} active flips of {H * W} LR pixels"
+    m.precision = "bf16"
+    sr16, ints16 = m._run_pipeline(lrd, [imd[k] for k in O.EXPERT_ORDER], ftd, 4 * H, 4 * W, {}, True)
+    d_psnr = abs(_psnr(sr16.cpu(), hr) - _psnr(ref, hr))
+    assert d_psnr <= 0.01, f"|dPSNR| {d_psnr:.4f} dB"
+    assert torch.equal(ints16["gates"].cpu().argmax(1), top1) and torch.equal(ints16["active"].cpu(), active)
