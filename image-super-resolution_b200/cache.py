@@ -26,6 +26,7 @@ import os
 import queue
 import random
 import struct
+import tempfile
 import threading
 import warnings
 from pathlib import Path
@@ -144,8 +145,11 @@ class ShardWriter:
         self.tensors: Optional[List[dict]] = None
         self.hw, self.offsets, self.has_mamba, self.metas, self.stems = [], [], [], [], []
         self.scale, self._pos = 4, 0
-        self._tmp = self.out_path + ".records.tmp"
-        self._rec = open(self._tmp, "wb")
+        # unique temporaries beside the target (several processes may pack the same directory: torchrun ranks, DataLoader
+        # workers); the finished shard appears atomically through os.replace
+        fd, self._tmp = tempfile.mkstemp(prefix=os.path.basename(self.out_path) + ".", suffix=".records.tmp",
+                                         dir=os.path.dirname(os.path.abspath(self.out_path)))
+        self._rec = os.fdopen(fd, "wb")
         self.header: Optional[dict] = None
 
     def _sdt(self, t: torch.Tensor, lossy: bool) -> str:
@@ -207,8 +211,9 @@ class ShardWriter:
                               for m in self.metas]
         hj = json.dumps(header).encode("utf-8")
         data_start = _round_up(len(MAGIC) + 8 + len(hj), _ALIGN_DATA)
-        part = self.out_path + ".part"                 # written beside the target and renamed: readers never see half a shard
-        with open(part, "wb") as f:
+        fd, part = tempfile.mkstemp(prefix=os.path.basename(self.out_path) + ".", suffix=".part",
+                                    dir=os.path.dirname(os.path.abspath(self.out_path)))
+        with os.fdopen(fd, "wb") as f:                # written beside the target and renamed: readers never see half a shard
             f.write(MAGIC)
             f.write(struct.pack("<Q", len(hj)))
             f.write(hj)
@@ -271,14 +276,37 @@ def resolve_shard(feature_dir: str, dtype: str = "source", load_features: bool =
     parts = list(p.glob("*_part.pt"))
     if not parts and not shard.exists():
         raise RuntimeError(f"No cached features found in {feature_dir}!")
-    if not shard.exists() or (parts and max(f.stat().st_mtime for f in parts) > shard.stat().st_mtime):
+    def stale():
+        if not shard.exists():
+            return True
+        if parts and max(f.stat().st_mtime for f in parts) > shard.stat().st_mtime:
+            return True
+        try:                                          # an existing shard packed for another request (dtype / features)
+            hdr = ShardCache.read_header(str(shard))
+        except Exception:
+            return True
+        return hdr.get("dtype_mode") != dtype or (load_features and not hdr.get("load_features", False))
+
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if stale() and (not multi or dist.get_rank() == 0):           # one packer per job; the others wait at the barrier
         print(f"[isr_b200.cache] packing {feature_dir} -> {shard} ({dtype}) ...", flush=True)
         pack_cache(str(p), str(shard), dtype=dtype, load_features=load_features)
+    if multi:
+        dist.barrier()
     return str(shard)
 
 
 class ShardCache:
     """Read-only view of a shard: header + memory-mapped records."""
+
+    @staticmethod
+    def read_header(path: str) -> dict:
+        with open(path, "rb") as f:
+            if f.read(len(MAGIC)) != MAGIC:
+                raise ValueError(f"{path} is not an FFSRC1 cache shard")
+            (n,) = struct.unpack("<Q", f.read(8))
+            return json.loads(f.read(n).decode("utf-8"))
 
     def __init__(self, path: str):
         self.path = str(path)
@@ -419,11 +447,31 @@ def epoch_batches(total: int, batch_size: int, shuffle: bool, seed: int, epoch: 
         order = torch.randperm(total, generator=g).tolist()
     else:
         order = list(range(total))
+    if world > 1:
+        # every rank must run the SAME number of steps: each step is a collective (gradient all-reduce, BatchNorm buffer
+        # sync), so a rank with one batch more would wait in NCCL for ever at the end of the epoch.  With drop_last the
+        # permutation is cut to a multiple of world * batch_size; without it, it is padded by wrapping around, as
+        # torch.utils.data.DistributedSampler does.
+        if drop_last:
+            order = order[:len(order) // (world * batch_size) * (world * batch_size)]
+        elif order:
+            per = -(-len(order) // world)
+            order = (order * (1 + (per * world) // len(order)))[:per * world]
     order = order[rank::world]
     out = [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
     if out and drop_last and len(out[-1]) < batch_size:
         out.pop()
     return out
+
+
+def batches_per_epoch(total: int, batch_size: int, world: int = 1, drop_last: bool = True) -> int:
+    """len(epoch_batches(...)) without building them (identical on every rank)."""
+    if world > 1:
+        if drop_last:
+            return total // (world * batch_size)
+        per = -(-total // world) if total else 0
+        return -(-per // batch_size)
+    return total // batch_size if drop_last else -(-total // batch_size)
 
 
 class DeviceBatchLoader:
@@ -472,8 +520,7 @@ class DeviceBatchLoader:
         self.launches = 0
 
     def __len__(self) -> int:
-        n = len(range(self.rank, self.cache.count * self.repeat_factor, self.world))
-        return n // self.B if self.drop_last else (n + self.B - 1) // self.B
+        return batches_per_epoch(self.cache.count * self.repeat_factor, self.B, self.world, self.drop_last)
 
     def set_epoch(self, epoch: int) -> None:
         self.epoch = int(epoch)

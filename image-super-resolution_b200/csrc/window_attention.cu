@@ -217,8 +217,7 @@ extern "C" int ffsr_window_attention(const void* qkv, int B, int H, int W, int C
 }
 
 // Same operation on PADDED rows: qkv rows of pitch qkv_pitch >= 3*C, out rows of pitch out_pitch >= C (elements).  bf16 only
-// (the layout exists for the tcgen05 Linears around it).  NOT yet run on hardware: its caller (isr_b200.drct, precision
-// "bf16") and its test are gated behind FFSR_RUN_WIP=1.
+// (the layout exists for the tcgen05 Linears around it; caller: isr_b200.drct with precision "bf16").
 extern "C" int ffsr_window_attention_pitched(const void* qkv, long qkv_pitch, int B, int H, int W, int C, int heads, int window, int shift,
                                              const float* bias_table, void* out, long out_pitch, cudaStream_t stream) {
   FFSR_REQUIRE(qkv && out && bias_table, FFSR_ERR_ARG, "window_attention_pitched: null pointer");

@@ -123,7 +123,7 @@ class DRCT(nn.Module):
         self.conv_last = nn.Conv2d(64, 3, 3, 1, 1)
         # "fp32": every Linear / Conv2d on the CUDA-core path (validated).  "bf16": LayerNorm outputs, qkv, attention output and
         # the MLP hidden activations are bf16 rows padded to 8 channels and the Linears run on tcgen05; the residual stream
-        # stays fp32.  The bf16 mode was written after the round's GPU budget was spent: gated behind FFSR_RUN_WIP=1.
+        # stays fp32.  Both modes are validated on B200 (tests/test_gpu_drct.py).
         self.precision = "fp32"
         self._packed: Optional[Tuple] = None
         self._ws: Dict[Tuple, torch.Tensor] = {}
@@ -165,8 +165,6 @@ class DRCT(nn.Module):
         if self.precision not in ("fp32", "bf16"):
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision!r}")
         lp = self.precision == "bf16"
-        if lp and os.environ.get("FFSR_RUN_WIP") != "1":
-            raise NotImplementedError("DRCT precision='bf16' (tcgen05 Linears) has not run on hardware yet; set FFSR_RUN_WIP=1 to try it")
         B, Cc, H, W = x.shape
         ws = self.window_size
         if Cc != 3 or H % ws or W % ws:

@@ -114,6 +114,29 @@ class FusedAdamW(torch.optim.Optimizer):
             p.data = self.bucket.view(i)                       # same values, storage now inside the bucket
             o = self.bucket.offsets[i]
             p.grad = self.grads[o:o + p.numel()].view(p.shape)  # autograd accumulates in place into the bucket
+        self.sync_from_rank0()
+
+    @torch.no_grad()
+    def sync_from_rank0(self) -> None:
+        """Data-parallel replicas must start from (and resume with) ONE state: parameters, Adam moments, EMA shadow and
+        step count are broadcast from rank 0 (what DistributedDataParallel does for parameters at construction).  Only
+        gradients and BatchNorm statistics are reduced afterwards, so ranks that were seeded differently, or where only
+        rank 0 loaded a checkpoint, would otherwise train diverging replicas silently.  No-op without a process group."""
+        if _world() == 1:
+            return
+        for t in (self.bucket.flat, self.exp_avg, self.exp_avg_sq, self.ema):
+            if t is not None:
+                dist.broadcast(t, src=0)
+        dist.broadcast(self._step_dev, src=0)
+        self.steps = int(self._step_dev.item())
+        self.bump_versions()
+
+    @torch.no_grad()
+    def reset_ema(self) -> None:
+        """Re-initialise the EMA shadow from the current parameters (call after loading weights into the model once the
+        optimizer exists: the shadow was taken from the construction-time weights)."""
+        if self.ema is not None:
+            self.ema.copy_(self.bucket.flat)
 
     # -- torch.optim API -------------------------------------------------------------------
     def zero_grad(self, set_to_none: bool = False):
@@ -174,6 +197,31 @@ class FusedAdamW(torch.optim.Optimizer):
     def load_state_dict(self, state_dict):
         fused = state_dict.get("fused")
         rest = {k: v for k, v in state_dict.items() if k != "fused"}
+        per_param = rest.get("state") or {}
+        if fused is None and per_param:
+            # a torch.optim.AdamW checkpoint as the reference writes it (src/utils/checkpoint_manager.py:120-160):
+            # state[i] = {step, exp_avg, exp_avg_sq} per parameter index -> scatter into the flat buckets
+            if len(per_param) != len(self._params):
+                raise ValueError(f"FusedAdamW.load_state_dict: checkpoint has state for {len(per_param)} parameters, "
+                                 f"this optimizer owns {len(self._params)}")
+            steps = 0
+            for i, p in enumerate(self._params):
+                st = per_param.get(i, per_param.get(str(i)))
+                if st is None or tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"FusedAdamW.load_state_dict: no matching AdamW state for parameter {i}")
+                o = self.bucket.offsets[i]
+                self.exp_avg[o:o + p.numel()].view(p.shape).copy_(st["exp_avg"])
+                self.exp_avg_sq[o:o + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
+                steps = max(steps, int(st["step"]))
+            rest = dict(rest)
+            rest["state"] = {}
+            super().load_state_dict(rest)
+            self.steps = steps
+            self._step_dev.fill_(steps)
+            self.reset_ema()                 # a plain AdamW checkpoint carries no shadow: restart it from the weights
+            self.set_lr(float(self.param_groups[0]["lr"]))
+            self.sync_from_rank0()
+            return
         super().load_state_dict(rest)
         if fused is not None:
             if fused["numel"] != self.bucket.numel or list(fused["offsets"]) != list(self.bucket.offsets):
@@ -182,9 +230,12 @@ class FusedAdamW(torch.optim.Optimizer):
             self.exp_avg_sq.copy_(fused["exp_avg_sq"])
             if self.ema is not None and fused.get("ema") is not None:
                 self.ema.copy_(fused["ema"])
+            elif self.ema is not None:
+                self.reset_ema()             # checkpoint written with EMA disabled
             self.steps = int(fused["steps"])
             self._step_dev.fill_(self.steps)
         self.set_lr(float(self.param_groups[0]["lr"]))
+        self.sync_from_rank0()
 
     # -- extras ----------------------------------------------------------------------------
     def set_lr(self, lr: float) -> None:
@@ -240,6 +291,9 @@ class FusionTrainer:
         self.model, self.criterion = model, criterion
         self.names = [n for n, p in model.named_parameters() if p.requires_grad]
         self.optimizer = FusedAdamW(model.parameters(), lr, betas, eps, weight_decay, max_grad_norm, ema_decay)
+        if _world() > 1:                      # BatchNorm statistics / counters start from rank 0's too (parameters: FusedAdamW)
+            for b in model.buffers():
+                dist.broadcast(b, src=0)
         self.optimizer.zero_grad()
         self.cuda_graph = cuda_graph
         self.graph_warmup = graph_warmup
@@ -259,11 +313,18 @@ class FusionTrainer:
         seed_counter(lr_img.device).add_(1)
         return loss.detach(), {k: v.detach() for k, v in comps.items()}
 
-    @staticmethod
-    def _signature(lr_img, expert_imgs, expert_feats, hr_img):
+    def _signature(self, lr_img, expert_imgs, expert_feats, hr_img):
+        """Everything a capture bakes in: input shapes / dtypes, and the host scalars and Python control flow of the step --
+        the loss weights and component set (the curriculum calls ``criterion.set_weights`` every epoch, train.py:296), the
+        optimizer hyper-parameters passed by value, the precision mode.  A change re-warms and re-captures."""
         f = expert_feats or {}
+        crit, g = self.criterion, self.optimizer.param_groups[0]
+        cw = tuple(sorted((k, float(v)) for k, v in getattr(crit, "weights", {}).items()))
         return (tuple(lr_img.shape), lr_img.dtype, tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in expert_imgs.items())),
-                tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in f.items())), tuple(hr_img.shape))
+                tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in f.items())), tuple(hr_img.shape),
+                cw, bool(getattr(crit, "use_swt", True)), bool(getattr(crit, "use_fft", True)),
+                float(g["weight_decay"]), tuple(float(b) for b in g["betas"]), float(g["eps"]),
+                float(self.optimizer.max_grad_norm), self.optimizer.ema_decay, getattr(self.model, "precision", None))
 
     def _capture(self, lr_img, expert_imgs, expert_feats, hr_img):
         self._static = (lr_img.clone(), {k: v.clone() for k, v in expert_imgs.items()},

@@ -189,11 +189,41 @@ def test_epoch_batches_partition_the_epoch_over_ranks():
             bs = CA.epoch_batches(103, 4, True, seed=7, epoch=2, rank=rank, world=world, drop_last=False)
             assert all(len(b) == 4 for b in bs[:-1]) and 1 <= len(bs[-1]) <= 4
             seen += [i for b in bs for i in b]
-        assert sorted(seen) == list(range(103))                       # disjoint cover, every rank the same permutation
+        # every index at least once (padding wraps around, as DistributedSampler does), every rank the same permutation
+        assert sorted(set(seen)) == list(range(103)) and len(seen) == -(-103 // world) * world
     a = CA.epoch_batches(50, 8, True, 1, 0)
     assert a == CA.epoch_batches(50, 8, True, 1, 0) and a != CA.epoch_batches(50, 8, True, 1, 1)
     assert len(a) == 6 and all(len(b) == 8 for b in a)                # drop_last
     assert CA.epoch_batches(10, 4, False, 0, 0, drop_last=False) == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+
+
+def test_every_rank_gets_the_same_number_of_batches():
+    """Each training step is a collective: a rank with one batch more would hang in NCCL at the end of the epoch
+    (the advisor's case: total=65, world=8, B=3 used to give [3,2,2,2,2,2,2,2])."""
+    for total, world, B in [(65, 8, 3), (103, 2, 4), (7, 8, 1), (64, 8, 8), (1000, 4, 32)]:
+        for drop_last in (True, False):
+            counts = [len(CA.epoch_batches(total, B, True, 3, 1, rank=r, world=world, drop_last=drop_last)) for r in range(world)]
+            assert len(set(counts)) == 1, (total, world, B, drop_last, counts)
+            assert counts[0] == CA.batches_per_epoch(total, B, world, drop_last)
+            idx = [i for r in range(world) for b in CA.epoch_batches(total, B, True, 3, 1, rank=r, world=world, drop_last=drop_last) for i in b]
+            if drop_last:
+                assert len(idx) == len(set(idx)) == counts[0] * world * B          # no index twice, full batches only
+            else:
+                assert set(idx) == set(range(total))                               # padded by wrap-around
+
+
+def test_shard_writer_uses_unique_temporaries_and_resolve_repacks_on_dtype_change(tmp_path):
+    import glob
+    lr, hr = torch.rand(3, 8, 8), torch.rand(3, 32, 32)
+    imgs = {k: torch.rand(3, 32, 32) for k in ("drct", "grl", "nafnet", "mamba")}
+    out = str(tmp_path / "a.ffsrc")
+    w1, w2 = CA.ShardWriter(out), CA.ShardWriter(out)            # two writers of the same target (two ranks / workers)
+    assert w1._tmp != w2._tmp
+    for w in (w1, w2):
+        w.add("s0", lr, hr, imgs)
+        w.close()
+    assert CA.ShardCache(out).count == 1 and not glob.glob(str(tmp_path / "*.tmp")) and not glob.glob(str(tmp_path / "*.part"))
+    assert CA.ShardCache.read_header(out)["dtype_mode"] == "source"
 
 
 def test_shard_writer_rejects_inconsistent_samples(tmp_path):

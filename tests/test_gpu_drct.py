@@ -74,10 +74,8 @@ def test_window_attention_rejects_bad_arguments():
 @pytest.mark.gpu
 @pytest.mark.parametrize("Cc,heads,ws,dtype", [(180, 6, 16, "fp32"), (212, 4, 16, "fp32"), (244, 2, 16, "bf16"), (276, 6, 8, "fp32"),
                                                (308, 4, 16, "bf16"), (60, 6, 8, "fp32"),
-                                               # fp32 K + V of head dim 122 do not fit in shared memory: K staged, V read through
-                                               # L2 -- a path written after the GPU budget was spent, gated until it has run once
-                                               pytest.param(244, 2, 16, "fp32", marks=pytest.mark.skipif(
-                                                   os.environ.get("FFSR_RUN_WIP") != "1", reason="fp32 fallback for head dim 122 not yet run on hardware"))])
+                                               # fp32 K + V of head dim 122 do not fit in shared memory: K staged, V read through L2
+                                               (244, 2, 16, "fp32")])
 def test_window_attention_matches_the_reference_block(Cc, heads, ws, dtype):
     dev = torch.device("cuda:0")
     lib = K.load()
@@ -123,11 +121,9 @@ def test_drct_forward_matches_oracle():
     assert float((m.last_feature.cpu() - feat).abs().max()) <= 1e-4
 
 
-_WIP = pytest.mark.skipif(os.environ.get("FFSR_RUN_WIP") != "1", reason="bf16 / tcgen05 mode of the DRCT path has not run on hardware yet")
 
 
 @pytest.mark.gpu
-@_WIP
 @pytest.mark.parametrize("Cc,heads,ws", [(180, 6, 16), (244, 2, 16), (308, 4, 8)])
 def test_pitched_window_attention_bf16(Cc, heads, ws):
     dev = torch.device("cuda:0")
@@ -150,7 +146,6 @@ def test_pitched_window_attention_bf16(Cc, heads, ws):
 
 
 @pytest.mark.gpu
-@_WIP
 def test_drct_forward_bf16_mode():
     import json
     import numpy as np

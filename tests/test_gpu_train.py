@@ -210,6 +210,60 @@ def _train_model(seed=0):
     return m.train()
 
 
+@pytest.mark.timeout(900)
+def test_train_c4_patch_shape_against_oracle_autograd():
+    """BASELINE configs[3] patch geometry (96x96 LR -> 384x384 HR, stage-3 L1 + SWT + FFT + SSIM losses; two of the eight
+    patches a GPU holds at N = 8): forward, total loss and all 198 gradients against fp32 autograd over the oracle and the
+    loss oracle on the CPU, in both precision modes (bf16: cosine of the large gradient tensors)."""
+    from isr_b200.losses import CombinedLoss
+    from oracle import loss_oracle as LO
+    dev = _cuda()
+    B, H, W = 2, 96, 96
+    weights = {"l1": 0.60, "swt": 0.25, "fft": 0.10, "ssim": 0.05}
+    m = _train_model()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    lr, imgs, fts, hr = O.synthetic_inputs(B, H, W)
+    pnames = dict(m.named_parameters())
+    sd = {k: (v.clone().requires_grad_() if k in pnames else v.clone()) for k, v in sd0.items()}
+    ref = O.run_pipeline(sd, lr, imgs, fts, training=True, bn_updates={})
+    loss_ref, _ = LO.combined_loss(ref.clamp(0, 1), hr, weights)
+    loss_ref.backward()
+    crit = CombinedLoss()
+    crit.set_weights({"charbonnier": 0, "l2": 0, "vgg": 0, "edge": 0, "clip": 0, **weights})
+    m.to(dev)
+    args = (lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()})
+    for prec in ("fp32", "bf16"):
+        m.load_state_dict(sd0)
+        m.precision = prec
+        m.zero_grad(set_to_none=True)
+        out = m.forward_with_precomputed(*args)
+        loss = crit(out.clamp(0, 1), hr.to(dev))
+        loss.backward()
+        torch.cuda.synchronize()
+        rel_loss = abs(float(loss) - float(loss_ref)) / abs(float(loss_ref))
+        if prec == "fp32":
+            assert (out.detach().cpu() - ref.detach()).abs().max().item() <= 1e-4
+            assert rel_loss <= 1e-4, rel_loss
+        else:
+            assert rel_loss <= 2e-3, rel_loss
+        n = 0
+        for name, p in m.named_parameters():
+            g_ref = sd[name].grad
+            assert p.grad is not None and g_ref is not None, name
+            n += 1
+            a, b = p.grad.double().cpu().reshape(-1), g_ref.double().reshape(-1)
+            denom = b.norm().item()
+            err = (a - b).norm().item()
+            if prec == "fp32":
+                # fp32 reference on the CPU: its own summation noise is ~1e-5 relative on the cancelling sums
+                assert err <= 2e-3 * denom or err <= 1e-7, f"{name}: rel-L2 {err / max(denom, 1e-30):.3e} (|g| {denom:.3e})"
+            elif b.numel() >= 1024 and denom > 1e-6:
+                cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+                assert cos >= 0.99, f"{name}: cosine {cos:.4f}"
+        assert n == 198
+    m.precision = "fp32"
+
+
 @pytest.mark.parametrize("B,H,W,with_feats", [(2, 12, 12, True), (1, 17, 23, True), (2, 9, 11, False)])
 def test_train_forward_backward_matches_oracle_autograd(B, H, W, with_feats):
     dev = _cuda()
@@ -452,6 +506,42 @@ def test_cuda_graph_step_matches_eager_step():
     assert max(float((a - b).abs().max()) for a, b in zip(p0, p1)) < 3e-3
     assert sum(float((a - b).abs().sum()) for a, b in zip(p0, p1)) / sum(a.numel() for a in p0) < 1e-4
     assert nb0 == nb1 == 54 and float((rm0 - rm1).abs().max()) < 1e-3
+
+
+def test_cuda_graph_step_follows_loss_weight_changes():
+    """The multi-stage curriculum calls criterion.set_weights every epoch (reference train.py:296).  The loss weights and
+    the set of active components are host scalars / Python control flow baked into a capture, so a change must re-warm and
+    re-capture: the graph trainer has to keep tracking an eager trainer across a stage-1 -> stage-3 switch."""
+    from isr_b200.trainer import FusionTrainer
+    from isr_b200.losses import CombinedLoss
+    dev = _cuda()
+    lr, imgs, fts, hr = O.synthetic_inputs(2, 16, 16)
+    args = (lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()}, hr.to(dev))
+    off = {"charbonnier": 0, "l2": 0, "vgg": 0, "edge": 0, "clip": 0}
+    stage1 = {**off, "l1": 1.0, "swt": 0.0, "fft": 0.0, "ssim": 0.0}
+    stage3 = {**off, "l1": 0.6, "swt": 0.25, "fft": 0.1, "ssim": 0.05}
+    out = []
+    for graph in (False, True):
+        torch.manual_seed(0)
+        m = isr_b200.CompleteEnhancedFusionSR(None).to(dev)
+        m.cross_band.band_attention.dropout = 0.0
+        m.collaborative.cross_attn.dropout = 0.0
+        crit = CombinedLoss()
+        crit.set_weights(stage1)
+        tr = FusionTrainer(m, crit, lr=2e-4, cuda_graph=graph, graph_warmup=1)
+        losses, comps = [], []
+        for it in range(8):
+            if it == 4:
+                crit.set_weights(stage3)
+            l, c = tr.step(*args)
+            losses.append(float(l))
+            comps.append(sorted(k for k, v in c.items() if float(v) != 0.0))
+        out.append((losses, comps, tr))
+    (l0, c0, _), (l1, c1, tr1) = out
+    assert tr1._graph is not None                                  # re-captured after the switch
+    assert c0 == c1, (c0, c1)                                      # the stage-3 components appear in the replayed steps too
+    assert max(abs(a - b) / max(abs(a), 1e-6) for a, b in zip(l0, l1)) < 5e-3, (l0, l1)
+    assert abs(l1[4] - l1[3]) > 1e-3 * abs(l1[3])                  # the switch is visible in the loss value itself
 
 
 def test_cuda_graph_dropout_masks_change_between_replays():
