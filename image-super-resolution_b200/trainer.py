@@ -292,8 +292,9 @@ class FusionTrainer:
         self.names = [n for n, p in model.named_parameters() if p.requires_grad]
         self.optimizer = FusedAdamW(model.parameters(), lr, betas, eps, weight_decay, max_grad_norm, ema_decay)
         if _world() > 1:                      # BatchNorm statistics / counters start from rank 0's too (parameters: FusedAdamW)
-            for b in model.buffers():
-                dist.broadcast(b, src=0)
+            for n, b in model.named_buffers():
+                if n.endswith(("running_mean", "running_var", "num_batches_tracked")):
+                    dist.broadcast(b, src=0)
         self.optimizer.zero_grad()
         self.cuda_graph = cuda_graph
         self.graph_warmup = graph_warmup
