@@ -546,26 +546,43 @@ def run_drct(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
+    res = {}
     sampler = ClockSampler(0)
     sampler.start()
-    ms = timed(lambda: m(x))
+    for prec in ("fp32", "bf16"):
+        m.precision = prec
+        with torch.no_grad():
+            res[prec] = timed(lambda: m(x))
     clocks = sampler.stop()
     sd = {k: v.detach() for k, v in m.state_dict().items()}
     with torch.no_grad():
         ms_eager = timed(lambda: DO.forward(sd, x))
-        err = float((m(x) - DO.forward(sd, x)).abs().max())
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ms_eager16 = timed(lambda: DO.forward(sd, x))
+        ref = DO.forward(sd, x)
+        errs = {}
+        for prec in ("fp32", "bf16"):
+            m.precision = prec
+            errs[prec] = float((m(x) - ref).abs().max())
+    m.precision = args.precision
+    ms = res[args.precision]
     flop = D.flops_per_lr_pixel(m) * H * W
     tensor_peak, hbm_peak, peak_src = _peaks()
     print(json.dumps({
         "metric": "drct_forward_hr_mpix_per_s", "value": 16 * H * W / 1e6 / (ms * 1e-3), "unit": "HR MPix/s", "n_gpus": 1,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "N1 DRCT-L x4 expert forward, one LR image padded to the 16-px window, random-init weights",
-                   "lr": [H, W], "precision": "fp32 (CUDA-core convs; tcgen05 path not built)"},
-        "tflops_algorithmic": flop / (ms * 1e-3) / 1e12, "tensor_peak": tensor_peak, "peak_source": peak_src,
-        "gpu_eager_baseline": {"value": 16 * H * W / 1e6 / (ms_eager * 1e-3), "unit": "HR MPix/s", "ms_per_image": ms_eager,
-                               "kind": "port: oracle restatement in PyTorch eager on the same GPU"},
-        "max_abs_vs_eager": err, "clocks": clocks}), flush=True)
+        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": "N1 DRCT-L x4 expert forward (12 RDG x 5 Swin blocks, window 16, dims 180..308), one LR image "
+                               "padded to the 16-px window, random-init weights", "lr": [H, W], "precision": args.precision},
+        "modes": {p_: {"ms": res[p_], "hr_mpix_per_s": 16 * H * W / 1e6 / (res[p_] * 1e-3), "tflops_algorithmic": flop / (res[p_] * 1e-3) / 1e12,
+                       "max_abs_vs_fp32_eager": errs[p_]} for p_ in res},
+        "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
+                     "frac": flop / (ms * 1e-3) / 1e12 / tensor_peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "whole DRCT-L forward, algorithmic FLOPs (70.3 MFLOP per LR pixel)"},
+        "gpu_eager_baseline": {"fp32": {"value": 16 * H * W / 1e6 / (ms_eager * 1e-3), "ms_per_image": ms_eager},
+                               "bf16_autocast": {"value": 16 * H * W / 1e6 / (ms_eager16 * 1e-3), "ms_per_image": ms_eager16},
+                               "unit": "HR MPix/s", "kind": "port: oracle restatement in PyTorch eager on the same GPU"},
+        "clocks": clocks}), flush=True)
 
 
 def train_config(workload, patches, B, hw, precision):

@@ -5,5 +5,6 @@ hyphen, so it is registered under that alias).
 """
 from .fusion import CompleteEnhancedFusionSR, create_enhanced_fusion, EXPERT_ORDER  # noqa: F401
 from .modules import DynamicExpertSelector  # noqa: F401
+from . import torch_ops  # noqa: F401  (registers torch.ops.ffsr.*: the torch.library face of the C ABI)
 
 __all__ = ["CompleteEnhancedFusionSR", "create_enhanced_fusion", "DynamicExpertSelector", "EXPERT_ORDER"]

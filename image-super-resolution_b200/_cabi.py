@@ -89,6 +89,7 @@ PROTOTYPES = {
     "ffsr_conv2d": (_I, [C.POINTER(ConvParams), _P]),
     "ffsr_conv_params_size": (_SZ, []),
     "ffsr_modulate_hr": (_I, [C.POINTER(_P), _P, _P, _P, _I, _I, _I, _I, _P, _P, _LL, _I, _P]),
+    "ffsr_modulate_hr_sized": (_I, [C.POINTER(_P), _P, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _LL, _I, _P]),
     "ffsr_modulate_hr_v2": (_I, [C.POINTER(_P), _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _LL, _I, _P]),
     "ffsr_expert_downsample": (_I, [_P, _I, _I, _I, _P, _LL, _P, _LL, _I, _P]),
     "ffsr_resize_nhwc": (_I, [_P, _I, _I, _I, _I, _LL, _P, _I, _I, _LL, _I, _P]),
@@ -142,6 +143,8 @@ PROTOTYPES = {
     # ---- DRCT-L window attention (N1: first kernel of the expert forward) ----
     "ffsr_window_attention": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "ffsr_window_attention_pitched": (_I, [_P, _L, _I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P]),
+    "ffsr_window_attention_head_pad": (_I, [_I]),
+    "ffsr_window_attention_headpadded": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P]),
     "ffsr_layernorm_strided": (_I, [_P, _L, _I, _L, _P, _P, _P, _L, _I, _I, _P]),
     "ffsr_leaky_relu": (_I, [_P, _L, _I, _L, _F, _I, _P]),
     "ffsr_pixel_shuffle2": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),

@@ -46,8 +46,8 @@ __device__ __forceinline__ float4 load_vec4<__nv_bfloat16>(const __nv_bfloat16* 
 template <typename T>
 __global__ void __launch_bounds__(128) k_modulate_hr(Img4 imgs, const float* __restrict__ m32,
                                                      const float* __restrict__ w2, const float* __restrict__ b2,
-                                                     int B, int H, int W, int clamp01, float* __restrict__ ecol,
-                                                     T* __restrict__ cat3, long long cat3_sX) {
+                                                     int B, int H, int W, int mh, int mw, int clamp01,
+                                                     float* __restrict__ ecol, T* __restrict__ cat3, long long cat3_sX) {
   __shared__ float sw[4][3][32];
   __shared__ float sb[4][3];
   if (m32) {
@@ -61,18 +61,18 @@ __global__ void __launch_bounds__(128) k_modulate_hr(Img4 imgs, const float* __r
   if (X >= Wh) return;
   const long HWh = (long)Hh * Wh;
   const long pix = (long)Y * Wh + X;
-  const BilinTap ty = bilin_tap(Y, H, Hh), tx = bilin_tap(X, W, Wh);
+  const BilinTap ty = bilin_tap(Y, mh, Hh), tx = bilin_tap(X, mw, Wh);      // m32 lives on an mh x mw grid (usually the LR grid)
   constexpr bool FAST = !std::is_same<T, float>::value;      // bf16 mode: A&S erf (1.5e-7), results are rounded to bf16
   float o[12];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     float mod[3] = {0.f, 0.f, 0.f};
     if (m32) {
-      const float* base = m32 + ((long)(b * 4 + e) * H) * W * 32;
-      const float4* p00 = reinterpret_cast<const float4*>(base + ((long)ty.i0 * W + tx.i0) * 32);
-      const float4* p01 = reinterpret_cast<const float4*>(base + ((long)ty.i0 * W + tx.i1) * 32);
-      const float4* p10 = reinterpret_cast<const float4*>(base + ((long)ty.i1 * W + tx.i0) * 32);
-      const float4* p11 = reinterpret_cast<const float4*>(base + ((long)ty.i1 * W + tx.i1) * 32);
+      const float* base = m32 + ((long)(b * 4 + e) * mh) * mw * 32;
+      const float4* p00 = reinterpret_cast<const float4*>(base + ((long)ty.i0 * mw + tx.i0) * 32);
+      const float4* p01 = reinterpret_cast<const float4*>(base + ((long)ty.i0 * mw + tx.i1) * 32);
+      const float4* p10 = reinterpret_cast<const float4*>(base + ((long)ty.i1 * mw + tx.i0) * 32);
+      const float4* p11 = reinterpret_cast<const float4*>(base + ((long)ty.i1 * mw + tx.i1) * 32);
       mod[0] = sb[e][0]; mod[1] = sb[e][1]; mod[2] = sb[e][2];
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
@@ -107,9 +107,26 @@ __global__ void __launch_bounds__(128) k_modulate_hr(Img4 imgs, const float* __r
   }
 }
 
+static int modulate_hr_impl(const float* const* imgs, const float* m32, int mh, int mw, const float* w2, const float* b2,
+                            int B, int H, int W, int clamp01, float* ecol, void* cat3, long long cat3_sX, int cat3_dtype,
+                            cudaStream_t stream);
+
 extern "C" int ffsr_modulate_hr(const float* const* imgs, const float* m32, const float* w2, const float* b2, int B,
                                 int H, int W, int clamp01, float* ecol, void* cat3, long long cat3_sX, int cat3_dtype,
                                 cudaStream_t stream) {
+  return modulate_hr_impl(imgs, m32, H, W, w2, b2, B, H, W, clamp01, ecol, cat3, cat3_sX, cat3_dtype, stream);
+}
+// m32 on its own mh x mw grid (expert features cached at a resolution other than LR: large_kernel_attention.py:365-372, 410-414)
+extern "C" int ffsr_modulate_hr_sized(const float* const* imgs, const float* m32, int mh, int mw, const float* w2,
+                                      const float* b2, int B, int H, int W, int clamp01, float* ecol, void* cat3,
+                                      long long cat3_sX, int cat3_dtype, cudaStream_t stream) {
+  FFSR_REQUIRE(mh > 0 && mw > 0, FFSR_ERR_ARG, "modulate_hr_sized: bad feature grid");
+  return modulate_hr_impl(imgs, m32, mh, mw, w2, b2, B, H, W, clamp01, ecol, cat3, cat3_sX, cat3_dtype, stream);
+}
+
+static int modulate_hr_impl(const float* const* imgs, const float* m32, int mh, int mw, const float* w2, const float* b2,
+                            int B, int H, int W, int clamp01, float* ecol, void* cat3, long long cat3_sX, int cat3_dtype,
+                            cudaStream_t stream) {
   FFSR_REQUIRE(imgs && imgs[0] && imgs[1] && imgs[2] && imgs[3] && ecol, FFSR_ERR_ARG, "modulate_hr: null pointer");
   FFSR_REQUIRE(!m32 || (w2 && b2), FFSR_ERR_ARG, "modulate_hr: modulation weights missing");
   FFSR_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && 4 * H <= 65535, FFSR_ERR_ARG, "modulate_hr: bad shape");
@@ -121,9 +138,9 @@ extern "C" int ffsr_modulate_hr(const float* const* imgs, const float* m32, cons
   for (int e = 0; e < 4; ++e) im.p[e] = imgs[e];
   dim3 grid(ceil_div(4 * W, 128), 4 * H, B);
   if (cat3_dtype == FFSR_DT_BF16)
-    k_modulate_hr<__nv_bfloat16><<<grid, 128, 0, stream>>>(im, m32, w2, b2, B, H, W, clamp01, ecol, (__nv_bfloat16*)cat3, cat3_sX);
+    k_modulate_hr<__nv_bfloat16><<<grid, 128, 0, stream>>>(im, m32, w2, b2, B, H, W, mh, mw, clamp01, ecol, (__nv_bfloat16*)cat3, cat3_sX);
   else
-    k_modulate_hr<float><<<grid, 128, 0, stream>>>(im, m32, w2, b2, B, H, W, clamp01, ecol, (float*)cat3, cat3_sX);
+    k_modulate_hr<float><<<grid, 128, 0, stream>>>(im, m32, w2, b2, B, H, W, mh, mw, clamp01, ecol, (float*)cat3, cat3_sX);
   return ffsr_check_launch("modulate_hr");
 }
 

@@ -19,6 +19,9 @@
 #include "common.cuh"
 #include "../../include/ffsr_b200.h"
 
+int ffsr_window_attention_tc_try(const void* qkv, long qkv_pitch, int B, int H, int W, int C, int heads, int window, int shift,
+                                 const float* bias_table, void* out, long out_pitch, cudaStream_t stream);
+
 namespace {
 
 constexpr int WA_THREADS = 256;
@@ -225,6 +228,11 @@ extern "C" int ffsr_window_attention_pitched(const void* qkv, long qkv_pitch, in
                "window_attention_pitched: B=%d H=%d W=%d C=%d heads=%d pitches %ld / %ld", B, H, W, C, heads, qkv_pitch, out_pitch);
   FFSR_REQUIRE(window > 0 && window * window <= WA_MAXN && H % window == 0 && W % window == 0 && shift >= 0 && shift < window &&
                    C / heads <= WA_MAXD, FFSR_ERR_ARG, "window_attention_pitched: window %d shift %d head dim %d", window, shift, C / heads);
+  {
+    // 16 x 16 windows: both products on tcgen05 (window_attention_tc.cu); other shapes fall through to the CUDA-core kernel
+    const int r = ffsr_window_attention_tc_try(qkv, qkv_pitch, B, H, W, C, heads, window, shift, bias_table, out, out_pitch, stream);
+    if (r != 0) return r == 1 ? 0 : r;
+  }
   const int N = window * window, dh = C / heads;
   const size_t limit = 227 * 1024;
   const dim3 grid((unsigned)((long)B * (H / window) * (W / window)), (unsigned)heads);

@@ -125,6 +125,7 @@ class DRCT(nn.Module):
         # the MLP hidden activations are bf16 rows padded to 8 channels and the Linears run on tcgen05; the residual stream
         # stays fp32.  Both modes are validated on B200 (tests/test_gpu_drct.py).
         self.precision = "fp32"
+        self.headpad_qkv = os.environ.get("FFSR_DRCT_QKV_PLAIN") is None   # bf16 mode, 16 x 16 windows: head-padded qkv rows
         self._packed: Optional[Tuple] = None
         self._ws: Dict[Tuple, torch.Tensor] = {}
         self.last_feature: Optional[torch.Tensor] = None     # conv_after_body output of the last forward ([B,180,H,W] view)
@@ -147,6 +148,20 @@ class DRCT(nn.Module):
                 w[name + ".b"] = mod.bias.detach().float().contiguous().to(dev)
             elif isinstance(mod, _Attn):
                 w[name + ".table"] = mod.relative_position_bias_table.detach().float().contiguous().to(dev)
+                # bf16 mode: the qkv Linear writes HEAD-PADDED rows [q | k | v] x [heads][DP] (DP = head dim rounded up to 16):
+                # its weight rows are permuted and zero padded here, so every head slice is 16-byte aligned and already
+                # zero filled for the tcgen05 window attention (csrc/window_attention_tc.cu)
+                heads = mod.relative_position_bias_table.shape[1]
+                d = mod.qkv.in_features
+                dh = d // heads
+                DP = (dh + 15) // 16 * 16
+                wq = mod.qkv.weight.detach().float().reshape(3, heads, dh, d)
+                wp = torch.zeros(3, heads, DP, d)
+                wp[:, :, :dh] = wq
+                bp = torch.zeros(3, heads, DP)
+                bp[:, :, :dh] = mod.qkv.bias.detach().float().reshape(3, heads, dh)
+                w[name + ".qkvp"] = _pack_linear(wp.reshape(3 * heads * DP, d)).to(dev)
+                w[name + ".qkvp.b"] = bp.reshape(-1).contiguous().to(dev)
         w["one"] = torch.ones(1, device=dev)
         self._packed = (key, w)
         return w
@@ -231,11 +246,21 @@ class DRCT(nn.Module):
                 n1 = self._buf("n", (B, H, W, pad(d)), dev, adt)
                 call(lib.ffsr_layernorm_strided, G.data_ptr(), NP, d, GW, w[p + ".norm1.w"].data_ptr(), w[p + ".norm1.b"].data_ptr(),
                      n1.data_ptr(), pad(d), K.DT_F32, ADT, S)
-                qkv = self._buf("qkv", (B, H, W, pad(3 * d)), dev, adt)
-                conv(nhwc(n1), H, W, d, p + ".attn.qkv", 3 * d, 1, nhwc(qkv))
                 att = self._buf("att", (B, H, W, pad(d)), dev, adt)
                 shift = ws // 2 if j % 2 else 0
-                if lp:
+                headpad = lp and ws == 16 and self.headpad_qkv
+                if headpad:
+                    nqkv = 3 * sw.heads * lib.ffsr_window_attention_head_pad(d // sw.heads)
+                    qkv = self._buf("qkvp", (B, H, W, nqkv), dev, adt)
+                    conv(nhwc(n1), H, W, d, p + ".attn.qkvp", nqkv, 1, nhwc(qkv))
+                    call(lib.ffsr_window_attention_headpadded, qkv.data_ptr(), B, H, W, d, sw.heads, ws, shift,
+                         w[p + ".attn.table"].data_ptr(), att.data_ptr(), pad(d), S)
+                else:
+                    qkv = self._buf("qkv", (B, H, W, pad(3 * d)), dev, adt)
+                    conv(nhwc(n1), H, W, d, p + ".attn.qkv", 3 * d, 1, nhwc(qkv))
+                if headpad:
+                    pass
+                elif lp:
                     call(lib.ffsr_window_attention_pitched, qkv.data_ptr(), pad(3 * d), B, H, W, d, sw.heads, ws, shift,
                          w[p + ".attn.table"].data_ptr(), att.data_ptr(), pad(d), S)
                 else:

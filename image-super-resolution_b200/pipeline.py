@@ -534,27 +534,40 @@ class FusionEngine:
         if have:
             for n in have:
                 f = feats[n]
-                if f.dim() != 4 or f.shape[0] != B or tuple(f.shape[2:]) != (H, W):
-                    raise NotImplementedError(
-                        f"expert feature '{n}' has shape {tuple(f.shape)}; the sm_100a path needs [B,C,{H},{W}] "
-                        "(features at LR resolution, as CachedSRDataset provides)")
+                if f.dim() != 4 or f.shape[0] != B:
+                    raise ValueError(f"expert feature '{n}' has shape {tuple(f.shape)}; expected [B={B}, C, h, w]")
+            # Feature maps of different spatial sizes are brought to the smallest one (large_kernel_attention.py:365-372).
+            # The reference resizes AFTER the 1x1 align conv; a 1x1 conv (bias included: bilinear weights sum to 1) commutes
+            # with bilinear resampling, so the raw features are resized instead and the usual align path follows.  Phase 4
+            # then runs on that (Hq, Wq) grid, which need not be the LR grid; the modulation kernel upsamples it to HR.
+            Hq, Wq = min(feats[n].shape[2] for n in have), min(feats[n].shape[3] for n in have)
+            if any(tuple(feats[n].shape[2:]) != (Hq, Wq) for n in have):
+                feats = dict(feats)
+                for n in have:
+                    f = feats[n]
+                    if tuple(f.shape[2:]) != (Hq, Wq):
+                        src = f.detach().to(f32).permute(0, 2, 3, 1).contiguous()
+                        dst = torch.empty(B, Hq, Wq, f.shape[1], device=dev, dtype=f32)
+                        self._call(lib.ffsr_bilinear_forward, src.data_ptr(), B, f.shape[2], f.shape[3], f.shape[1],
+                                   dst.data_ptr(), Hq, Wq, K.DT_F32, S)
+                        feats[n] = dst.permute(0, 3, 1, 2).contiguous()
             # bf16 mode: the residual stream (tokens, t1, t2) is stored as bf16 -- every Phase-4 launch is bound by the HBM
             # round trip of these [4][H][W][128] tensors, and the phase only feeds a sigmoid damped by 0.2
             cin_exp = {n: co.align_layers[n].weight.shape[1] for n in EXPERT_ORDER}
             fast_align = lp and len(have) == 4 and all(feats[n].shape[1] == cin_exp[n] for n in EXPERT_ORDER)
             rdt = torch.bfloat16 if (fast_align and self.p4_bf16_stream) else f32
-            tokens = self._buf("co.tok", (B, 4, H, W, 128), dev, dtype=rdt, zero=True)
+            tokens = self._buf("co.tok", (B, 4, Hq, Wq, 128), dev, dtype=rdt, zero=True)
             if fast_align:
                 # bf16 mode: NCHW fp32 features -> one bf16 channels-last buffer, then ONE grouped tcgen05 1x1 conv
                 cmax = max(cin_exp.values())
                 cs = (cmax + 7) // 8 * 8
-                fbuf = self._buf("co.feat", (B, 4, H, W, cs), dev, dtype=torch.bfloat16, zero=True)
+                fbuf = self._buf("co.feat", (B, 4, Hq, Wq, cs), dev, dtype=torch.bfloat16, zero=True)
                 for e, n in enumerate(EXPERT_ORDER):
                     f = feats[n].detach().to(f32).contiguous()
-                    self._call(lib.ffsr_nchw_to_nhwc_bf16, f.data_ptr(), B, cin_exp[n], H * W,
-                               fbuf.data_ptr() + e * H * W * cs * 2, 4 * H * W * cs, cs, S)
-                self.conv(nhwc(fbuf.view(B * 4, H, W, cs)), B * 4, H, W, cmax, "co.align.all", 128, 1,
-                          nhwc(tokens.view(B * 4, H, W, 128)), groups=4)
+                    self._call(lib.ffsr_nchw_to_nhwc_bf16, f.data_ptr(), B, cin_exp[n], Hq * Wq,
+                               fbuf.data_ptr() + e * Hq * Wq * cs * 2, 4 * Hq * Wq * cs, cs, S)
+                self.conv(nhwc(fbuf.view(B * 4, Hq, Wq, cs)), B * 4, Hq, Wq, cmax, "co.align.all", 128, 1,
+                          nhwc(tokens.view(B * 4, Hq, Wq, 128)), groups=4)
             else:
                 if len(have) < 4:
                     tokens.zero_()                              # missing expert -> zero token (:378-381)
@@ -573,11 +586,11 @@ class FusionEngine:
                         wn = wn2
                     tv = tokens[:, e]
                     ov = _View(tv.data_ptr(), tokens.stride(0), tokens.stride(2), tokens.stride(3), 1, tokens)
-                    self.conv(nchw(f), B, H, W, cin, wn, 128, 1, ov)
+                    self.conv(nchw(f), B, Hq, Wq, cin, wn, 128, 1, ov)
             N4 = B * 4
-            tok4 = tokens.view(N4, H, W, 128)
-            rows = N4 * H * W
-            n1 = self._buf("co.n", (N4, H, W, 128), dev, dtype=adt)
+            tok4 = tokens.view(N4, Hq, Wq, 128)
+            rows = N4 * Hq * Wq
+            n1 = self._buf("co.n", (N4, Hq, Wq, 128), dev, dtype=adt)
             def layernorm(src, wn, bn):
                 if src.dtype == torch.bfloat16:
                     self._call(lib.ffsr_layernorm128_bf16, src.data_ptr(), rows, pp(wn), pp(bn), n1.data_ptr(), S)
@@ -585,20 +598,20 @@ class FusionEngine:
                     self._call(lib.ffsr_layernorm, src.data_ptr(), rows, 128, pp(wn), pp(bn), n1.data_ptr(), int(lp), S)
 
             layernorm(tok4, "collaborative.norm1.weight", "collaborative.norm1.bias")
-            qkv = self._buf("co.qkv", (N4, H, W, 384), dev, dtype=adt)
-            self.conv(nhwc(n1), N4, H, W, 128, "co.qkv", 384, 1, nhwc(qkv))
-            ctx = self._buf("co.ctx", (N4, H, W, 128), dev, dtype=adt)
-            self._call(lib.ffsr_token_attention, qkv.data_ptr(), B, 4, H * W, 128, ctx.data_ptr(), int(lp), S)
-            t1 = self._buf("co.t1", (N4, H, W, 128), dev, dtype=rdt)
-            self.conv(nhwc(ctx), N4, H, W, 128, "co.out", 128, 1, nhwc(t1), epi=K.EPI_RESIDUAL, r1=nhwc(tok4))
+            qkv = self._buf("co.qkv", (N4, Hq, Wq, 384), dev, dtype=adt)
+            self.conv(nhwc(n1), N4, Hq, Wq, 128, "co.qkv", 384, 1, nhwc(qkv))
+            ctx = self._buf("co.ctx", (N4, Hq, Wq, 128), dev, dtype=adt)
+            self._call(lib.ffsr_token_attention, qkv.data_ptr(), B, 4, Hq * Wq, 128, ctx.data_ptr(), int(lp), S)
+            t1 = self._buf("co.t1", (N4, Hq, Wq, 128), dev, dtype=rdt)
+            self.conv(nhwc(ctx), N4, Hq, Wq, 128, "co.out", 128, 1, nhwc(t1), epi=K.EPI_RESIDUAL, r1=nhwc(tok4))
             layernorm(t1, "collaborative.norm2.weight", "collaborative.norm2.bias")
-            hdn = self._buf("co.h", (N4, H, W, 256), dev, dtype=adt)
-            self.conv(nhwc(n1), N4, H, W, 128, "co.f0", 256, 1, nhwc(hdn), act=K.ACT_GELU)
-            t2 = self._buf("co.t2", (N4, H, W, 128), dev, dtype=rdt)
-            self.conv(nhwc(hdn), N4, H, W, 256, "co.f2", 128, 1, nhwc(t2), epi=K.EPI_RESIDUAL, r1=nhwc(t1))
+            hdn = self._buf("co.h", (N4, Hq, Wq, 256), dev, dtype=adt)
+            self.conv(nhwc(n1), N4, Hq, Wq, 128, "co.f0", 256, 1, nhwc(hdn), act=K.ACT_GELU)
+            t2 = self._buf("co.t2", (N4, Hq, Wq, 128), dev, dtype=rdt)
+            self.conv(nhwc(hdn), N4, Hq, Wq, 256, "co.f2", 128, 1, nhwc(t2), epi=K.EPI_RESIDUAL, r1=nhwc(t1))
             xg = self._lka_block("co.lka", "collaborative.lka_global", t2, "co", lp=lp)
-            m32 = self._buf("co.m32", (N4, H, W, 32), dev, dtype=adt if self.modulate_v2 else f32)
-            self.conv(nhwc(xg), N4, H, W, 128, "co.m0", 32, 1, nhwc(m32), groups=4, bias_name="co.m0b")
+            m32 = self._buf("co.m32", (N4, Hq, Wq, 32), dev, dtype=adt if (self.modulate_v2 and (Hq, Wq) == (H, W)) else f32)
+            self.conv(nhwc(xg), N4, Hq, Wq, 128, "co.m0", 32, 1, nhwc(m32), groups=4, bias_name="co.m0b")
 
         # ---------------- HR: modulation + expert pyramid ----------------
         ecol = self._buf("ecol", (B, 4, 3, Hh, Wh), dev, fresh=fr)
@@ -606,7 +619,10 @@ class FusionEngine:
         cat2 = self._buf("cat2", (B, 2 * H, 2 * W, 80), dev, dtype=adt, zero=True)
         s1in = self._buf("s1in", (B, H, W, 16), dev, dtype=adt, zero=True)
         ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in imgs])
-        if m32 is not None and self.modulate_v2:
+        if m32 is not None and tuple(m32.shape[1:3]) != (H, W):
+            self._call(lib.ffsr_modulate_hr_sized, ptrs, m32.data_ptr(), m32.shape[1], m32.shape[2], w["co.m2"].data_ptr(),
+                       w["co.m2b"].data_ptr(), B, H, W, 0 if m.training else 1, ecol.data_ptr(), cat3.data_ptr() + 64 * esz, 80, ADT, S)
+        elif m32 is not None and self.modulate_v2:
             self._call(lib.ffsr_modulate_hr_v2, ptrs, m32.data_ptr(), K.DT_BF16 if m32.dtype == torch.bfloat16 else K.DT_F32,
                        w["co.m2"].data_ptr(), w["co.m2b"].data_ptr(), B, H, W, 0 if m.training else 1, ecol.data_ptr(),
                        cat3.data_ptr() + 64 * esz, 80, ADT, S)

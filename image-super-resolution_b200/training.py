@@ -982,15 +982,24 @@ def _train_forward(m, lr, img_list, feats, want_inter):
     co = m.collaborative
     have = [n for n in EXPERT_ORDER if n in feats]
     if have:
+        for n in have:
+            if feats[n].dim() != 4 or feats[n].shape[0] != B:
+                raise ValueError(f"expert feature '{n}' has shape {tuple(feats[n].shape)}; expected [B={B}, C, h, w]")
+        # Feature maps of different spatial sizes are brought to the smallest one (large_kernel_attention.py:365-372).  The
+        # reference resizes AFTER the 1x1 align conv; a 1x1 conv (bias included: the bilinear weights sum to 1) commutes
+        # with bilinear resampling, so resizing the raw features first gives the same tensor up to fp32 rounding.  Phase 4
+        # then runs on that (Hp, Wp) grid, which need not be the LR grid; the modulation upsamples it to HR.
+        Hp, Wp = min(feats[n].shape[2] for n in have), min(feats[n].shape[3] for n in have)
+        H_lr, W_lr = H, W
+        H, W = Hp, Wp
         aligned = []
         for n in EXPERT_ORDER:
             if n not in feats:
                 aligned.append(None)
                 continue
             f = feats[n].detach().float()
-            if f.dim() != 4 or f.shape[0] != B or tuple(f.shape[2:]) != (H, W):
-                raise NotImplementedError(
-                    f"expert feature '{n}' has shape {tuple(f.shape)}; the sm_100a path needs [B,C,{H},{W}]")
+            if tuple(f.shape[2:]) != (H, W):
+                f = _bilinear(_cl(f), (H, W))
             al = co.align_layers[n]
             cin_w = al.weight.shape[1]
             wgt = al.weight
@@ -1025,6 +1034,7 @@ def _train_forward(m, lr, img_list, feats, want_inter):
             if not training:
                 o = o.clamp(0, 1)
             ecol.append(o)
+        H, W = H_lr, W_lr
     else:
         ecol = imgs
 

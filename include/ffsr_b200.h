@@ -169,6 +169,9 @@ int ffsr_modulate_hr(const float* const* imgs, const float* m32, const float* w2
                      cudaStream_t stream);
 /* Same operation, four HR pixels (one LR cell phase) x four experts per thread; m32 may be bf16 ([B][4][H][W][32], bf16 mode).
  * Requires m32 != NULL (use ffsr_modulate_hr for the pass-through case). */
+int ffsr_modulate_hr_sized(const float* const* imgs, const float* m32, int mh, int mw, const float* w2, const float* b2,
+                           int B, int H, int W, int clamp01, float* ecol, void* cat3, long long cat3_sX, int cat3_dtype,
+                           cudaStream_t stream);   /* m32 on an mh x mw grid != LR (large_kernel_attention.py:365-372) */
 int ffsr_modulate_hr_v2(const float* const* imgs, const void* m32, int m32_dtype, const float* w2, const float* b2, int B,
                         int H, int W, int clamp01, float* ecol, void* cat3, long long cat3_sX, int cat3_dtype,
                         cudaStream_t stream);
@@ -408,6 +411,12 @@ int ffsr_window_attention_pitched(const void* qkv, long qkv_pitch, int B, int H,
  *   pixel_shuffle2    : nn.PixelShuffle(2) on channels-last data, x [B][H][W][4C] -> y [B][2H][2W][C]  (:612-614)
  *   rgb_shift_in/out  : (x - mean) * img_range from planar fp32 [B][3][H][W] into channels-last rows of `pitch`
  *                       channels, and back (x / img_range + mean) (:778-779, :787); mean3_host is a HOST array of 3 */
+/* window attention on tcgen05 (16 x 16 windows, bf16) over HEAD-PADDED qkv rows [q | k | v] x [heads][DP], DP =
+ * ffsr_window_attention_head_pad(C / heads): the layout a qkv Linear produces when its weight rows are permuted and zero
+ * padded on the host (isr_b200.drct).  Same operation as ffsr_window_attention (drct_arch.py:175-206, 385-412). */
+int ffsr_window_attention_head_pad(int head_dim);
+int ffsr_window_attention_headpadded(const void* qkv, int B, int H, int W, int C, int heads, int window, int shift,
+                                     const float* bias_table, void* out, long out_pitch, cudaStream_t stream);
 int ffsr_layernorm_strided(const void* x, long rows, int C, long x_pitch, const float* w, const float* b, void* y,
                            long y_pitch, int in_dtype, int out_dtype, cudaStream_t stream);
 int ffsr_leaky_relu(void* x, long rows, int C, long pitch, float slope, int dtype, cudaStream_t stream);

@@ -124,7 +124,7 @@ def test_drct_forward_matches_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("Cc,heads,ws", [(180, 6, 16), (244, 2, 16), (308, 4, 8)])
+@pytest.mark.parametrize("Cc,heads,ws", [(180, 6, 16), (212, 4, 16), (244, 2, 16), (276, 6, 16), (308, 4, 16), (308, 4, 8)])
 def test_pitched_window_attention_bf16(Cc, heads, ws):
     dev = torch.device("cuda:0")
     lib = K.load()

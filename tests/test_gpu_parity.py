@@ -525,3 +525,38 @@ def test_headline_size_against_oracle():
     d_psnr = abs(_psnr(sr16.cpu(), hr) - _psnr(ref, hr))
     assert d_psnr <= 0.01, f"|dPSNR| {d_psnr:.4f} dB"
     assert torch.equal(ints16["gates"].cpu().argmax(1), top1) and torch.equal(ints16["active"].cpu(), active)
+
+
+@pytest.mark.parametrize("sizes", [
+    {"drct": (20, 28), "grl": (16, 24), "nafnet": (16, 24), "mamba": (19, 31)},     # common size = the LR grid
+    {"drct": (12, 18), "grl": (16, 24), "nafnet": (13, 19), "mamba": (12, 18)},     # common size below the LR grid (x5.33 to HR)
+])
+def test_expert_features_at_other_resolutions(sizes):
+    """large_kernel_attention.py:365-372: aligned feature maps of different spatial sizes are resized to the smallest one;
+    Phase 4 then runs on that grid and the modulation upsamples it to HR.  Eval (fp32 within 1e-4 of the oracle, bf16 by
+    PSNR) and the train-mode forward."""
+    dev = _cuda()
+    B, H, W = 1, 16, 24
+    m = _model(True)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    lr, imgs, fts, hr = O.synthetic_inputs(B, H, W)
+    g = torch.Generator().manual_seed(5)
+    fts = {k: torch.randn(B, v.shape[1], *sizes[k], generator=g) for k, v in fts.items()}
+    with torch.no_grad():
+        ref = O.run_pipeline(sd, lr, imgs, fts)
+    m.to(dev)
+    lrd, imd, ftd = _to(dev, lr, imgs, fts)
+    sr = m.forward_with_precomputed(lrd, imd, ftd).cpu()
+    assert (sr - ref).abs().max().item() <= FP32_TOL
+    m.precision = "bf16"
+    sr16 = m.forward_with_precomputed(lrd, imd, ftd).cpu()
+    assert abs(_psnr(sr16, hr) - _psnr(ref, hr)) <= 0.01 and (sr16 - ref).abs().max().item() < 0.05
+    m.precision = "fp32"
+    m.train()
+    m.cross_band.band_attention.dropout = 0.0
+    m.collaborative.cross_attn.dropout = 0.0
+    ref_t = O.run_pipeline(sd, lr, imgs, fts, training=True, bn_updates={})
+    out_t = m.forward_with_precomputed(lrd, imd, ftd)
+    assert (out_t.detach().cpu() - ref_t).abs().max().item() <= FP32_TOL
+    out_t.mean().backward()
+    assert m.collaborative.align_layers["drct"].weight.grad is not None
