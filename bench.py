@@ -585,6 +585,111 @@ def run_drct(args):
         "clocks": clocks}), flush=True)
 
 
+def run_c5(args):
+    """`--workload c5` = BASELINE configs[4]: end-to-end x4 SR of one 2040x1356 image per rank per step with the DRCT-L expert
+    forward (180-dim, window 16) feeding the fusion, x8 self-ensemble TTA.  Per image: the 8 dihedral variants of the LR image
+    (scripts/extract_test_tta_cache.py:253-256) are padded to the 16-px window (reflect), DRCT-L produces the SR image and the
+    180-channel feature of each (io.py:226-235), the other three experts' outputs come from the cache (synthetic here), the fusion
+    runs on the variants batched by shape (serving.fuse_tta), outputs are un-transformed and averaged on the device
+    (scripts/generate_fast_submission.py:190-250).  Images are independent: rank r takes images r, r+N, ... (weak scaling)."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    import isr_b200
+    from isr_b200 import drct as D
+    from isr_b200.serving import fuse_tta
+    from isr_b200.dist import max_over_ranks as _mor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, W = args.lr
+    warmup, steps = max(args.warmup, 3), args.steps
+    torch.manual_seed(0)
+    fusion = isr_b200.CompleteEnhancedFusionSR(None).eval().to(dev)
+    fusion.precision = args.precision
+    drct = D.create_drct_model().to(dev).eval()
+    drct.precision = args.precision
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    lr0 = torch.rand(1, 3, H, W, device=dev, generator=g)
+    others = {}                                   # cached outputs / features of the experts that are not built (per variant shape)
+
+    def cached(shape_key, h, w):
+        if shape_key not in others:
+            gg = torch.Generator(device=dev).manual_seed(99 + len(others))
+            others[shape_key] = ({k: torch.rand(1, 3, 4 * h, 4 * w, device=dev, generator=gg) for k in ("grl", "nafnet", "mamba")},
+                                 {k: torch.randn(1, 64 if k == "nafnet" else 180, h, w, device=dev, generator=gg) for k in ("grl", "nafnet", "mamba")})
+        return others[shape_key]
+
+    def one_image():
+        variants = []
+        for hflip in (False, True):
+            for rot in range(4):
+                x = torch.flip(lr0, [3]) if hflip else lr0
+                x = torch.rot90(x, rot, [2, 3]) if rot else x
+                h, w = x.shape[2:]
+                ph, pw = (16 - h % 16) % 16, (16 - w % 16) % 16
+                xp = F.pad(x, (0, pw, 0, ph), mode="reflect") if (ph or pw) else x
+                sr_d = drct(xp)[:, :, :4 * h, :4 * w].float().clamp(0, 1)
+                feat_d = drct.last_feature[:, :, :h, :w].float()
+                imgs_o, feats_o = cached((h, w), h, w)
+                variants.append((x, {"drct": sr_d, **imgs_o}, {"drct": feat_d, **feats_o}, hflip, rot))
+        return fuse_tta(fusion, variants)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            out = one_image()
+        sampler = ClockSampler(local)
+        sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = one_image()
+        e1.record()
+        barrier()
+        ms = _mor(e0.elapsed_time(e1), dev) / steps
+        clocks = sampler.stop()
+        # split of one image: expert vs fusion
+        torch.cuda.synchronize()
+        e0.record()
+        xp = F.pad(lr0, (0, (16 - W % 16) % 16, 0, (16 - H % 16) % 16), mode="reflect")
+        for _ in range(3):
+            drct(xp)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_drct = e0.elapsed_time(e1) / 3
+    if rank == 0:
+        tensor_peak, hbm_peak, peak_src = _peaks()
+        flop = (D.flops_per_lr_pixel(drct) * xp.shape[2] * xp.shape[3] + FLOP_PER_HR_PIXEL * 16 * H * W) * 8
+        print(json.dumps({
+            "metric": "end_to_end_sr_hr_mpix_per_s", "value": world * 16 * H * W / 1e6 / (ms * 1e-3), "unit": "HR MPix/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "C5 (BASELINE configs[4]): end-to-end x4 SR, DRCT-L expert forward (180-dim, window 16) feeding the fusion, "
+                                   "x8 self-ensemble TTA, one 2040x1356 HR image per GPU per step; the GRL / NAFNet / MambaIR expert outputs "
+                                   "come from the cache (synthetic)", "lr": [H, W], "hr": [4 * H, 4 * W], "tta_variants": 8,
+                       "precision": args.precision, "partition": "independent images round-robin over ranks, no collective"},
+            "ms_per_image": ms, "ms_drct_forward_one_variant": ms_drct, "drct_share_of_image": 8 * ms_drct / ms,
+            "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
+                         "frac": flop / (ms * 1e-3) / 1e12 / tensor_peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "whole image: 8 x (DRCT-L forward + fusion forward), algorithmic FLOPs"},
+            "output_range": [float(out.min()), float(out.max())], "clocks": clocks}), flush=True)
+    if world > 1:
+        _leave(world)
+
+
 def train_config(workload, patches, B, hw, precision):
     return {"workload": f"{workload.upper()} fusion training step (BASELINE configs[{1 if workload == 'c2' else 3}]): "
                         f"global batch {patches} x {hw}x{hw} LR patches, losses {STAGE_WEIGHTS[workload]}, "
@@ -780,9 +885,9 @@ def gpu_reference_eager_throughput(dev, H, W, steps=3, warmup=1):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c3t", "n1"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c3t", "n1", "c5"],
                     help="c3: the 100-image full-res inference job (headline, default); c2 / c4: training steps (BASELINE "
-                         "configs[1] / [3]); c3t: one image across all ranks; n1: DRCT-L expert forward")
+                         "configs[1] / [3]); c3t: one image across all ranks; n1: DRCT-L expert forward; c5: configs[4], DRCT-L -> fusion, x8 TTA")
     ap.add_argument("--batch", type=int, default=0, help="override the global batch of a training workload")
     ap.add_argument("--images", type=int, default=N_JOB_IMAGES, help="images per job step (debug runs only)")
     ap.add_argument("--gpus", type=int, default=1)
@@ -801,6 +906,8 @@ def main():
         return run_tiled(args)
     if args.workload == "n1":
         return run_drct(args)
+    if args.workload == "c5":
+        return run_c5(args)
     if args.workload != "c3":
         return run_train(args)
 
