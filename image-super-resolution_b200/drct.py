@@ -216,6 +216,7 @@ class DRCT(nn.Module):
             p.out, p.out_sN, p.out_sY, p.out_sX = out.ptr, out.sN, out.sY, out.sX
             p.out_dtype = K.DT_BF16 if out.t.dtype == torch.bfloat16 else K.DT_F32
             p.act, p.epi = act, (K.EPI_RESIDUAL if r1 is not None else K.EPI_PLAIN)
+            p.flags = K.CONV_MULTI_ISSUE
             if r1 is not None:
                 p.r1, p.r1_sN, p.r1_sY, p.r1_sX = r1.ptr, r1.sN, r1.sY, r1.sX
                 p.r1_dtype = K.DT_BF16 if r1.t.dtype == torch.bfloat16 else K.DT_F32

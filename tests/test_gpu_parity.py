@@ -280,7 +280,7 @@ def test_full_resolution_forward_properties():
 # finer-grained checks (localise a failure to one kernel)
 # --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("prefix,key,C_", [("cross_band.lka_block", "cb.lka", 64), ("collaborative.lka_global", "co.lka", 128)])
-@pytest.mark.parametrize("N,H,W", [(2, 13, 29), (1, 40, 9)])
+@pytest.mark.parametrize("N,H,W", [(2, 13, 29), (1, 40, 9), (1, 37, 101)])
 def test_lka_block_against_oracle(prefix, key, C_, N, H, W):
     dev = _cuda()
     m = _model(True)
