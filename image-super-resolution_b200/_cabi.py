@@ -81,6 +81,9 @@ PROTOTYPES = {
     "ffsr_crossband_attention": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P]),
     "ffsr_crossband_out": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ffsr_lka_depthwise": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "ffsr_lka_tail_weight_bytes": (_SZ, []),
+    "ffsr_lka_tail_param_floats": (_SZ, []),
+    "ffsr_lka_tail64": (_I, [_P, _P, _L, _P, _P, _P, _P, _P, _P]),
     "ffsr_layernorm": (_I, [_P, _L, _I, _P, _P, _P, _I, _P]),
     "ffsr_layernorm128_bf16": (_I, [_P, _L, _P, _P, _P, _P]),
     "ffsr_lka_depthwise_in": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),

@@ -1,0 +1,274 @@
+// Tile-resident tail of an LKABlock on 64-channel fp32 token rows (Phase 3, the routing chain), on tcgen05 at fp32 accuracy:
+//   x1 = x + s1 * BN1(x) * sigmoid(BN(pw(a)))        a = depthwise chain output          large_kernel_attention.py:96-105, 143-149
+//   x2 = x1 + s2 * ffn2(GELU(ffn0(BN2(x1))))
+// Three 1x1 contractions (64->64, 64->128, 128->64) that the fp32 path ran as three CUDA-core SGEMM launches (0.98 ms per
+// 2040x1356 image at ~70 % of the FFMA peak, each streaming its operands through HBM).  Here a CTA keeps a 128-token tile on
+// chip through all three, and the products run on the tensor cores WITHOUT giving up fp32 accuracy (the routing chain feeds
+// the expert-selection indices, which must stay bit-exact): every fp32 operand is split into three bf16 terms
+//   v = v1 + v2 + v3,   v1 = bf16(v), v2 = bf16(v - v1), v3 = bf16(v - v1 - v2)          (24 mantissa bits)
+// and the six products that matter are accumulated in fp32 in TMEM:  a1 w1 + a1 w2 + a2 w1 + a2 w2 + a1 w3 + a3 w1;  the
+// dropped terms are below 2^-24 of the result, i.e. below the rounding of an fp32 FMA chain.
+//   operands : no-swizzle K-major planes (tc_ptx.cuh): activations [split][kg][row] = 16 B, weights [split][kg][n] = 16 B, all
+//              three weight matrices resident (120 KB); the 128-wide hidden layer is consumed in two 64-channel halves.
+//   threads  : 256 = 8 warps; warp w owns TMEM lanes 32 (w % 4) .. (the tcgen05.ld rule) = token rows, and column half w / 4;
+//              warp 0 issues the MMAs (one PTX block of four K steps per split pair) between the epilogue phases.
+#include <cuda.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/ffsr_b200.h"
+
+namespace {
+using namespace tcx;
+
+constexpr int LT_C = 64, LT_HID = 128;
+constexpr int LT_THREADS = 256;
+constexpr int LT_TMEM_COLS = 256;                 // [0,64): stage 1 then stage 3; [64,192): stage 2
+constexpr int LT_W1 = 3 * LT_C * LT_C * 2;        // 24,576 B  pw        [split][kg 8][n 64][8]
+constexpr int LT_W0 = 3 * LT_HID * LT_C * 2;      // 49,152 B  ffn0      [split][kg 8][n 128][8]
+constexpr int LT_W2 = 3 * LT_C * LT_HID * 2;      // 49,152 B  ffn2      [split][kg 16][n 64][8]
+constexpr int LT_WBYTES = LT_W1 + LT_W0 + LT_W2;  // 122,880 B
+constexpr int LT_SA = 3 * 8 * 128 * 16;           // 49,152 B  activation planes [split][kg 8][row 128]
+constexpr int LT_PF = 64 * 3 + 128 + 64 + 8;      // fp32 parameters: b_pw[64] k1[64] d1[64] b0[128] b2[64] (s1 s2 come by pointer)
+constexpr int LT_S_PAR = 64;
+constexpr int LT_S_W = 2048;
+constexpr int LT_S_A = LT_S_W + LT_WBYTES;
+constexpr int LT_S_H = LT_S_A + LT_SA;
+constexpr int LT_SMEM = LT_S_H + LT_SA;           // 223,232 B
+
+// 8 fp32 values -> their three bf16 terms, as three 16-byte cells
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& c1, uint4& c2, uint4& c3) {
+  uint32_t w1[4], w2[4], w3[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float a = v[2 * k], b = v[2 * k + 1];
+    const __nv_bfloat16 a1 = __float2bfloat16_rn(a), b1 = __float2bfloat16_rn(b);
+    const float ra = a - __bfloat162float(a1), rb = b - __bfloat162float(b1);
+    const __nv_bfloat16 a2 = __float2bfloat16_rn(ra), b2 = __float2bfloat16_rn(rb);
+    const float sa = ra - __bfloat162float(a2), sb = rb - __bfloat162float(b2);
+    const __nv_bfloat16 a3 = __float2bfloat16_rn(sa), b3 = __float2bfloat16_rn(sb);
+    w1[k] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+    w2[k] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+    w3[k] = (uint32_t)__bfloat16_as_ushort(a3) | ((uint32_t)__bfloat16_as_ushort(b3) << 16);
+  }
+  c1 = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+  c2 = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+  c3 = make_uint4(w3[0], w3[1], w3[2], w3[3]);
+}
+
+// the six split products of one contraction: A planes [split][kg][128 rows], B planes [split][kg][n]; ksteps K=16 steps starting
+// at activation plane 0 and weight plane kg0
+__device__ __forceinline__ void lt_gemm(uint32_t tmem_d, uint32_t a32, uint32_t b32, int n, int kg_total_b, int kg0_b, int ksteps,
+                                        uint32_t idesc, bool overwrite) {
+  const uint32_t a_hi = desc_hi(128), b_hi = desc_hi(128);
+  const uint32_t a_split = 8u * 2048u, b_split = (uint32_t)(kg_total_b * n * 16);
+  const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+  // (ksteps is 4 for every contraction here: one asm block per split pair issues its four K = 16 steps)
+  (void)ksteps;
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+    const uint32_t al = desc_lo(a32 + (uint32_t)pa[t] * a_split, 2048u);
+    const uint32_t bl = desc_lo(b32 + (uint32_t)pb[t] * b_split + (uint32_t)kg0_b * (uint32_t)(n * 16), (uint32_t)(n * 16));
+    umma_taps_1x4(tmem_d, al, bl, idesc, (t == 0 && overwrite) ? 0u : 1u, a_hi, b_hi, (2u * 2048u) >> 4, (uint32_t)(2 * n), 0u);
+  }
+}
+
+__global__ void __launch_bounds__(LT_THREADS, 1) k_lka_tail(const float* __restrict__ xin, const float* __restrict__ ain, long rows,
+                                                            const uint8_t* __restrict__ wblob, const float* __restrict__ pblob,
+                                                            const float* __restrict__ s1p, const float* __restrict__ s2p,
+                                                            float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8);
+  float* par = reinterpret_cast<float*>(smem + LT_S_PAR);
+  uint8_t* sW = smem + LT_S_W;
+  uint8_t* sA = smem + LT_S_A;
+  uint8_t* sH = smem + LT_S_H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane;           // token row of the tile = TMEM lane
+  const int half = warp >> 2;                        // column half (32 of 64 columns)
+
+  for (int i = tid; i < LT_WBYTES / 16; i += LT_THREADS) reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(wblob) + i);
+  for (int i = tid; i < LT_PF; i += LT_THREADS) par[i] = __ldg(pblob + i);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(LT_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float s1 = s1p[0], s2 = s2p[0];
+  const float* b_pw = par;
+  const float* k1 = par + 64;
+  const float* d1 = par + 128;
+  const float* b0 = par + 192;
+  const float* b2 = par + 320;
+  const uint32_t w1_32 = smem_u32(sW), w0_32 = w1_32 + LT_W1, w2_32 = w0_32 + LT_W0, a32 = smem_u32(sA), h32 = smem_u32(sH);
+  const uint32_t id64 = idesc_bf16_m128(64), id128 = idesc_bf16_m128(128);
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t phase = 0;
+  const long tiles = (rows + 127) / 128;
+
+  for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long r = tile * 128 + row;
+    const bool live = r < rows;
+    float x[32];
+    // ---- a -> split planes; x (this thread's 32 channels) stays in registers
+    {
+      const float4* ap = reinterpret_cast<const float4*>(ain + r * LT_C + half * 32);
+      const float4* xp = reinterpret_cast<const float4*>(xin + r * LT_C + half * 32);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {                  // 8 channels = one 16-byte cell of each split
+        float v[8];
+        const float4 p0 = live ? __ldg(ap + 2 * g) : make_float4(0.f, 0.f, 0.f, 0.f), p1 = live ? __ldg(ap + 2 * g + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+        uint4 c1, c2, c3;
+        split8(v, c1, c2, c3);
+        uint8_t* cell = sA + (half * 4 + g) * 2048 + row * 16;
+        *reinterpret_cast<uint4*>(cell) = c1;
+        *reinterpret_cast<uint4*>(cell + 8 * 2048) = c2;
+        *reinterpret_cast<uint4*>(cell + 16 * 2048) = c3;
+        const float4 q0 = live ? __ldg(xp + 2 * g) : make_float4(0.f, 0.f, 0.f, 0.f), q1 = live ? __ldg(xp + 2 * g + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[8 * g] = q0.x; x[8 * g + 1] = q0.y; x[8 * g + 2] = q0.z; x[8 * g + 3] = q0.w;
+        x[8 * g + 4] = q1.x; x[8 * g + 5] = q1.y; x[8 * g + 6] = q1.z; x[8 * g + 7] = q1.w;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- stage 1: G = a . Wpw^T
+    if (warp == 0) {
+      tc_fence_after();
+      lt_gemm(tmem, a32, w1_32, 64, 8, 0, 4, id64, true);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 1: x1 = x + s1 * (x k1 + d1) * sigmoid(G + b); x1 -> registers and split planes
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)(half * 32 + c * 16), v);
+      tmem_wait_ld(v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int ch = half * 32 + c * 16 + i;
+        const float xr = x[c * 16 + i];
+        x[c * 16 + i] = xr + s1 * (fmaf(xr, k1[ch], d1[ch]) * sigmoid_acc(__uint_as_float(v[i]) + b_pw[ch]));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                 // stage-1 operands and accumulator are dead
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = x[8 * g + i];
+      uint4 c1, c2, c3;
+      split8(v, c1, c2, c3);
+      uint8_t* cell = sA + (half * 4 + g) * 2048 + row * 16;
+      *reinterpret_cast<uint4*>(cell) = c1;
+      *reinterpret_cast<uint4*>(cell + 8 * 2048) = c2;
+      *reinterpret_cast<uint4*>(cell + 16 * 2048) = c3;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- stage 2: Hd = x1 . W0^T  (128 columns at TMEM column 64)
+    if (warp == 0) {
+      tc_fence_after();
+      lt_gemm(tmem + 64, a32, w0_32, 128, 8, 0, 4, id128, true);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- stage 3 in two hidden halves: GELU(Hd + b0) -> split planes -> x2 += . W2^T
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)(64 + hh * 64 + half * 32 + c * 16), v);
+        tmem_wait_ld(v);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = gelu_erf(__uint_as_float(v[g * 8 + i]) + b0[hh * 64 + half * 32 + c * 16 + g * 8 + i]);
+          uint4 c1, c2, c3;
+          split8(y, c1, c2, c3);
+          uint8_t* cell = sH + (half * 4 + c * 2 + g) * 2048 + row * 16;
+          *reinterpret_cast<uint4*>(cell) = c1;
+          *reinterpret_cast<uint4*>(cell + 8 * 2048) = c2;
+          *reinterpret_cast<uint4*>(cell + 16 * 2048) = c3;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        tc_fence_after();
+        lt_gemm(tmem, h32, w2_32, 64, 16, hh * 8, 4, id64, hh == 0);
+        umma_commit(bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+    }
+    // ---- epilogue 3: x2 = x1 + s2 * (acc + b2)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)(half * 32 + c * 16), v);
+      tmem_wait_ld(v);
+      if (live) {
+        float4* op = reinterpret_cast<float4*>(out + r * LT_C + half * 32 + c * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = q * 4 + i;
+            o[i] = fmaf(s2, __uint_as_float(v[j]) + b2[half * 32 + c * 16 + j], x[c * 16 + j]);
+          }
+          op[q] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                 // TMEM and the planes are free for the next tile
+    tc_fence_after();
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(LT_TMEM_COLS));
+}
+}  // namespace
+
+extern "C" size_t ffsr_lka_tail_weight_bytes(void) { return (size_t)LT_WBYTES; }
+extern "C" size_t ffsr_lka_tail_param_floats(void) { return (size_t)LT_PF; }
+
+// x, a, out: fp32 [rows][64] (out may alias neither input); wblob / pblob: isr_b200.pipeline.pack_lka_tail
+extern "C" int ffsr_lka_tail64(const float* x, const float* a, long rows, const void* wblob, const float* pblob, const float* scale1,
+                               const float* scale2, float* out, cudaStream_t stream) {
+  FFSR_REQUIRE(x && a && wblob && pblob && scale1 && scale2 && out && rows > 0, FFSR_ERR_ARG, "lka_tail64: bad argument");
+  FFSR_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)wblob % 16) == 0,
+               FFSR_ERR_ALIGN, "lka_tail64: 16-byte alignment required");
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_lka_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
+  }
+  const long tiles = (rows + 127) / 128;
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  k_lka_tail<<<grid, LT_THREADS, LT_SMEM, stream>>>(x, a, rows, (const uint8_t*)wblob, pblob, scale1, scale2, out);
+  return ffsr_check_launch("lka_tail64");
+}

@@ -90,6 +90,18 @@ def pack_edge_chain(r):
     return wb.contiguous(), pb.contiguous()
 
 
+def _split3_planes(w2d: torch.Tensor) -> torch.Tensor:
+    """fp32 [n][k] -> its three bf16 terms w = w1 + w2 + w3 (24 mantissa bits) in the no-swizzle K-major plane layout
+    [split][k/8][n][8] of the tile-resident kernels (csrc/lka_tail.cu)."""
+    w = w2d.detach().float()
+    w1 = w.to(torch.bfloat16)
+    r = w - w1.float()
+    w2 = r.to(torch.bfloat16)
+    w3 = (r - w2.float()).to(torch.bfloat16)
+    n, k = w.shape
+    return torch.stack([w1, w2, w3]).view(3, n, k // 8, 8).permute(0, 2, 1, 3).contiguous()
+
+
 def _pack_linear(w: torch.Tensor) -> torch.Tensor:
     """[out,in] -> [1][in][out]."""
     return w.detach().float().t().contiguous().unsqueeze(0)
@@ -116,6 +128,7 @@ class FusionEngine:
         self.edge_chain = os.environ.get("FFSR_EDGE_CHAIN0") is None
         self.modulate_v2 = os.environ.get("FFSR_MODULATE_V1") is None   # 4 HR px x 4 experts per thread, bf16 features
         self.p4_bf16_stream = os.environ.get("FFSR_P4_F32_STREAM") is None  # bf16 mode: Phase-4 residual stream stored as bf16
+        self.lka_tail_tc = os.environ.get("FFSR_LKA_TAIL_FFMA") is None     # fp32 LKA tail (Phase 3) on tcgen05, 3-term bf16 split
         self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ weights
@@ -146,6 +159,12 @@ class FusionEngine:
         w[key + ".f0b"] = (blk.ffn[0].bias.detach().float() + f0 @ d2).contiguous()
         w[key + ".f2"] = _pack_conv(blk.ffn[2].weight)
         w[key + ".f2b"] = blk.ffn[2].bias.detach().float().contiguous()
+        if C_ == 64:
+            # tile-resident tail on tcgen05 at fp32 accuracy (three-term bf16 split of both operands): csrc/lka_tail.cu
+            w[key + ".tail_w"] = torch.cat([_split3_planes(pw * kb[:, None]).reshape(-1), _split3_planes(f0 * k2[None, :]).reshape(-1),
+                                            _split3_planes(blk.ffn[2].weight.detach().float().reshape(C_, 2 * C_)).reshape(-1)]).contiguous()
+            w[key + ".tail_p"] = torch.cat([db, w[key + ".k1"], w[key + ".d1"], w[key + ".f0b"], w[key + ".f2b"],
+                                            torch.zeros(8, device=db.device)]).contiguous()
 
     def _prepare(self, dev):
         key = self._state_key(dev)
@@ -347,6 +366,12 @@ class FusionEngine:
                    w[key + ".wv"].data_ptr(), t1.data_ptr(), t2.data_ptr(), a.data_ptr(),
                    K.DT_BF16 if lp else K.DT_F32, self._stream)
         self.launches += 2
+        if not lp and self.lka_tail_tc and (key + ".tail_w") in w and x.dtype == torch.float32:
+            x2 = self._buf(name + ".lka_x2f", x.shape, dev)
+            self._call(self.lib.ffsr_lka_tail64, x.data_ptr(), a.data_ptr(), N * H * W, w[key + ".tail_w"].data_ptr(),
+                       w[key + ".tail_p"].data_ptr(), self._P[blk + ".scale1"].data_ptr(), self._P[blk + ".scale2"].data_ptr(),
+                       x2.data_ptr(), self._stream)
+            return x2
         x1 = self._buf(name + ".lka_x1", x.shape, dev, dtype=adt) if lp else t1   # fp32: t1 is free again
         self.conv(nhwc(a), N, H, W, Cc, key + ".pw", Cc, 1, nhwc(x1), epi=K.EPI_LKAGATE, bias_name=key + ".pwb",
                   r1=nhwc(x), sa_ptr=self._P[blk + ".scale1"], ch_k=w[key + ".k1"], ch_d=w[key + ".d1"])

@@ -107,6 +107,14 @@ int ffsr_lka_depthwise_in(const void* x, int x_dtype, int N, int H, int W, int C
  * nn.LayerNorm rows (large_kernel_attention.py:389,392) and the softmax(QK^T/4)V core of
  * nn.MultiheadAttention (:390) for T tokens per LR pixel, head_dim 16; token-major layout
  * qkv[B][T][HW][3E] -> ctx[B][T][HW][E] */
+/* Tail of an LKABlock on fp32 64-channel token rows, tile-resident on tcgen05 at fp32 accuracy (three-term bf16 split of
+ * both operands, six products accumulated in fp32): x1 = x + s1 * BN1(x) * sigmoid(BN(pw(a))); out = x1 + s2 * ffn(BN2(x1))
+ * src/models/large_kernel_attention.py:96-105 (pw + bn + sigmoid gate), :143-149 (LKABlock.forward).  Weights / parameters
+ * are packed by the host into the kernel's shared-memory layout (isr_b200.pipeline: _prep_lka). */
+size_t ffsr_lka_tail_weight_bytes(void);
+size_t ffsr_lka_tail_param_floats(void);
+int ffsr_lka_tail64(const float* x, const float* a, long rows, const void* wblob, const float* pblob, const float* scale1,
+                    const float* scale2, float* out, cudaStream_t stream);
 int ffsr_layernorm(const float* x, long rows, int E, const float* w, const float* b, void* y, int out_bf16,
                    cudaStream_t stream);
 /* nn.LayerNorm(128) on bf16 rows -> bf16 rows (Phase 4, bf16 mode: residual stream stored as bf16) */
