@@ -84,6 +84,9 @@ PROTOTYPES = {
     "ffsr_lka_tail_weight_bytes": (_SZ, []),
     "ffsr_lka_tail_param_floats": (_SZ, []),
     "ffsr_lka_tail64": (_I, [_P, _P, _L, _P, _P, _P, _P, _P, _P]),
+    "ffsr_lka_tail128_weight_bytes": (_SZ, []),
+    "ffsr_lka_tail128_param_floats": (_SZ, []),
+    "ffsr_lka_tail128_mod": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "ffsr_layernorm": (_I, [_P, _L, _I, _P, _P, _P, _I, _P]),
     "ffsr_layernorm128_bf16": (_I, [_P, _L, _P, _P, _P, _P]),
     "ffsr_lka_depthwise_in": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),

@@ -90,6 +90,12 @@ def pack_edge_chain(r):
     return wb.contiguous(), pb.contiguous()
 
 
+def _planes_bf16(w2d: torch.Tensor) -> torch.Tensor:
+    """fp32 [n][k] -> bf16 no-swizzle K-major planes [k/8][n][8] (B operand of the tile-resident kernels)."""
+    n, k = w2d.shape
+    return w2d.detach().float().to(torch.bfloat16).view(n, k // 8, 8).permute(1, 0, 2).contiguous()
+
+
 def _split3_planes(w2d: torch.Tensor) -> torch.Tensor:
     """fp32 [n][k] -> its three bf16 terms w = w1 + w2 + w3 (24 mantissa bits) in the no-swizzle K-major plane layout
     [split][k/8][n][8] of the tile-resident kernels (csrc/lka_tail.cu)."""
@@ -129,6 +135,7 @@ class FusionEngine:
         self.modulate_v2 = os.environ.get("FFSR_MODULATE_V1") is None   # 4 HR px x 4 experts per thread, bf16 features
         self.p4_bf16_stream = os.environ.get("FFSR_P4_F32_STREAM") is None  # bf16 mode: Phase-4 residual stream stored as bf16
         self.lka_tail_tc = os.environ.get("FFSR_LKA_TAIL_FFMA") is None     # fp32 LKA tail (Phase 3) on tcgen05, 3-term bf16 split
+        self.lka_tail128 = os.environ.get("FFSR_LKA_TAIL128_OFF") is None   # bf16 mode: Phase-4 LKA tail + modulation layer 0 fused
         self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ weights
@@ -223,6 +230,19 @@ class FusionEngine:
             w["co.f2.b"] = co.ffn[2].bias.detach().float().contiguous()
             w["co.m0"] = torch.stack([_pack_conv(co.modulation[i][0].weight) for i in range(4)]).contiguous()
             w["co.m0b"] = torch.stack([co.modulation[i][0].bias.detach().float() for i in range(4)]).contiguous()
+            lg = co.lka_global
+            if lg.norm1.weight.shape[0] == 128 and all(tuple(co.modulation[i][0].weight.shape[:2]) == (32, 128) for i in range(4)):
+                # bf16 mode: LKA tail + modulation layer 0 as one tile-resident kernel (csrc/lka_tail.cu, k_lka_tail128)
+                kb, db = self._bn_fold(lg.lka.bn)
+                k2, d2 = self._bn_fold(lg.norm2)
+                pw = lg.lka.pw_conv.weight.detach().float().reshape(128, 128) * kb[:, None]
+                f0 = lg.ffn[0].weight.detach().float().reshape(256, 128)
+                w["co.tail_w"] = torch.cat([_planes_bf16(pw).reshape(-1), _planes_bf16(f0 * k2[None, :]).reshape(-1),
+                                            _planes_bf16(lg.ffn[2].weight.detach().float().reshape(128, 256)).reshape(-1)]
+                                           + [_planes_bf16(co.modulation[i][0].weight.detach().float().reshape(32, 128)).reshape(-1)
+                                              for i in range(4)]).contiguous()
+                w["co.tail_p"] = torch.cat([db, w["co.lka.k1"], w["co.lka.d1"], w["co.lka.f0b"], w["co.lka.f2b"]]
+                                           + [co.modulation[i][0].bias.detach().float() for i in range(4)]).contiguous()
             w["co.m2"] = torch.stack([co.modulation[i][2].weight.detach().float().reshape(3, 32) for i in range(4)]).contiguous()
             w["co.m2b"] = torch.stack([co.modulation[i][2].bias.detach().float() for i in range(4)]).contiguous()
             mr = m.multi_res
@@ -634,9 +654,22 @@ class FusionEngine:
             self.conv(nhwc(n1), N4, Hq, Wq, 128, "co.f0", 256, 1, nhwc(hdn), act=K.ACT_GELU)
             t2 = self._buf("co.t2", (N4, Hq, Wq, 128), dev, dtype=rdt)
             self.conv(nhwc(hdn), N4, Hq, Wq, 256, "co.f2", 128, 1, nhwc(t2), epi=K.EPI_RESIDUAL, r1=nhwc(t1))
-            xg = self._lka_block("co.lka", "collaborative.lka_global", t2, "co", lp=lp)
             m32 = self._buf("co.m32", (N4, Hq, Wq, 32), dev, dtype=adt if (self.modulate_v2 and (Hq, Wq) == (H, W)) else f32)
-            self.conv(nhwc(xg), N4, Hq, Wq, 128, "co.m0", 32, 1, nhwc(m32), groups=4, bias_name="co.m0b")
+            if lp and self.lka_tail128 and "co.tail_w" in w and t2.dtype == torch.bfloat16 and m32.dtype == torch.bfloat16:
+                # depthwise chain, then ONE tile-resident kernel: pw + gate, ffn0 + GELU, ffn2 + residual, modulation layer 0
+                ta = self._buf("co.lka_t1", t2.shape, dev)
+                tb = self._buf("co.lka_t2", t2.shape, dev)
+                a_ = self._buf("co.lka_a", t2.shape, dev, dtype=adt)
+                self._call(lib.ffsr_lka_depthwise_in, t2.data_ptr(), K.DT_BF16, N4, Hq, Wq, 128, w["co.lka.k1"].data_ptr(),
+                           w["co.lka.d1"].data_ptr(), w["co.lka.w5"].data_ptr(), w["co.lka.wh"].data_ptr(), w["co.lka.wv"].data_ptr(),
+                           ta.data_ptr(), tb.data_ptr(), a_.data_ptr(), K.DT_BF16, S)
+                self.launches += 2
+                self._call(lib.ffsr_lka_tail128_mod, t2.data_ptr(), a_.data_ptr(), N4, Hq * Wq, w["co.tail_w"].data_ptr(),
+                           w["co.tail_p"].data_ptr(), P["collaborative.lka_global.scale1"].data_ptr(),
+                           P["collaborative.lka_global.scale2"].data_ptr(), m32.data_ptr(), S)
+            else:
+                xg = self._lka_block("co.lka", "collaborative.lka_global", t2, "co", lp=lp)
+                self.conv(nhwc(xg), N4, Hq, Wq, 128, "co.m0", 32, 1, nhwc(m32), groups=4, bias_name="co.m0b")
 
         # ---------------- HR: modulation + expert pyramid ----------------
         ecol = self._buf("ecol", (B, 4, 3, Hh, Wh), dev, fresh=fr)

@@ -115,6 +115,12 @@ size_t ffsr_lka_tail_weight_bytes(void);
 size_t ffsr_lka_tail_param_floats(void);
 int ffsr_lka_tail64(const float* x, const float* a, long rows, const void* wblob, const float* pblob, const float* scale1,
                     const float* scale2, float* out, cudaStream_t stream);
+/* bf16 variant for Phase 4 (128-channel tokens): the same tail followed by the first modulation layer (128 -> 32 per
+ * expert, large_kernel_attention.py:415-416), x / a bf16 [nimg][HW][128] with expert = image index % 4, m32 bf16 [nimg][HW][32]. */
+size_t ffsr_lka_tail128_weight_bytes(void);
+size_t ffsr_lka_tail128_param_floats(void);
+int ffsr_lka_tail128_mod(const void* x, const void* a, int nimg, int HW, const void* wblob, const float* pblob,
+                         const float* scale1, const float* scale2, void* m32, cudaStream_t stream);
 int ffsr_layernorm(const float* x, long rows, int E, const float* w, const float* b, void* y, int out_bf16,
                    cudaStream_t stream);
 /* nn.LayerNorm(128) on bf16 rows -> bf16 rows (Phase 4, bf16 mode: residual stream stored as bf16) */
