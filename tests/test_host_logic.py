@@ -92,8 +92,16 @@ def test_orchestration_dry_run(with_feats, want_inter, precision):
     out, inter = eng._forward(lr, imgs, feats, B, H, W, want_inter)
     assert out.shape == (B, 3, 4 * H, 4 * W)
     calls = eng.lib.calls
-    expect = (63 if with_feats else 51) - (3 if precision == "bf16" else 0)   # bf16: one grouped align conv
+    # conv launches: the Phase-3 LKA tail (3 convs) is one ffsr_lka_tail64 launch in both modes; bf16 mode also has one
+    # grouped align conv instead of four, each edge refiner (6 convs x 3 levels) as one ffsr_edge_refiner_chain launch and
+    # the Phase-4 LKA tail + modulation layer 0 (4 convs) as one ffsr_lka_tail128_mod launch
+    expect = (63 if with_feats else 51) - 3
+    if precision == "bf16":
+        expect -= 3 + 18 + 4
     assert calls.count("ffsr_conv2d") == expect, calls.count("ffsr_conv2d")
+    assert calls.count("ffsr_lka_tail64") == 1
+    assert calls.count("ffsr_edge_refiner_chain") == (3 if precision == "bf16" else 0)
+    assert calls.count("ffsr_lka_tail128_mod") == (1 if (precision == "bf16" and with_feats) else 0)
     assert ("ffsr_token_attention" in calls) == with_feats
     assert calls[-1] == "ffsr_final_combine"
     if want_inter:
