@@ -91,6 +91,12 @@ PROTOTYPES = {
     "ffsr_layernorm128_bf16": (_I, [_P, _L, _P, _P, _P, _P]),
     "ffsr_lka_depthwise_in": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "ffsr_token_attention": (_I, [_P, _I, _I, _L, _I, _P, _I, _P]),
+    "ffsr_token_attn_weight_bytes": (_SZ, []),
+    "ffsr_token_attn_param_floats": (_SZ, []),
+    "ffsr_token_attn_chain": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "ffsr_token_ffn_weight_bytes": (_SZ, []),
+    "ffsr_token_ffn_param_floats": (_SZ, []),
+    "ffsr_token_ffn_chain": (_I, [_P, _L, _P, _P, _P, _P]),
     "ffsr_gate_finalize": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "ffsr_conv2d": (_I, [C.POINTER(ConvParams), _P]),
     "ffsr_conv_params_size": (_SZ, []),

@@ -108,6 +108,34 @@ def _split3_planes(w2d: torch.Tensor) -> torch.Tensor:
     return torch.stack([w1, w2, w3]).view(3, n, k // 8, 8).permute(0, 2, 1, 3).contiguous()
 
 
+def pack_token_attn(co):
+    """CollaborativeFeatureLearning norm1 + cross_attn -> (bf16 weight blob, fp32 parameter blob) of ffsr_token_attn_chain
+    (layout: csrc/token_chain.cu).  LayerNorm folded into in_proj: g = gamma o W_in, colsum of the bf16-ROUNDED g (what the
+    tensor cores multiply by), bias W_in beta + b_in; the 1/sqrt(head_dim) = 1/4 of the scores is folded into the q rows."""
+    Win = co.cross_attn.in_proj_weight.detach().double()
+    g = Win * co.norm1.weight.detach().double()[None, :]
+    b = Win @ co.norm1.bias.detach().double() + co.cross_attn.in_proj_bias.detach().double()
+    E = Win.shape[1]
+    g[:E] *= 0.25
+    b[:E] *= 0.25
+    g16 = g.float().to(torch.bfloat16)
+    wo = co.cross_attn.out_proj.weight.detach().float()
+    wb = torch.cat([_planes_bf16(g16.float()).reshape(-1), _planes_bf16(wo).reshape(-1)]).contiguous()
+    pb = torch.cat([g16.double().sum(1).float(), b.float(), co.cross_attn.out_proj.bias.detach().float()]).contiguous()
+    return wb, pb
+
+
+def pack_token_ffn(co):
+    """norm2 + ffn -> blobs of ffsr_token_ffn_chain (LayerNorm folded into ffn.0 as in pack_token_attn)."""
+    W0 = co.ffn[0].weight.detach().double()
+    g = W0 * co.norm2.weight.detach().double()[None, :]
+    b = W0 @ co.norm2.bias.detach().double() + co.ffn[0].bias.detach().double()
+    g16 = g.float().to(torch.bfloat16)
+    wb = torch.cat([_planes_bf16(g16.float()).reshape(-1), _planes_bf16(co.ffn[2].weight.detach().float()).reshape(-1)]).contiguous()
+    pb = torch.cat([g16.double().sum(1).float(), b.float(), co.ffn[2].bias.detach().float()]).contiguous()
+    return wb, pb
+
+
 def _pack_linear(w: torch.Tensor) -> torch.Tensor:
     """[out,in] -> [1][in][out]."""
     return w.detach().float().t().contiguous().unsqueeze(0)
@@ -136,6 +164,7 @@ class FusionEngine:
         self.p4_bf16_stream = os.environ.get("FFSR_P4_F32_STREAM") is None  # bf16 mode: Phase-4 residual stream stored as bf16
         self.lka_tail_tc = os.environ.get("FFSR_LKA_TAIL_FFMA") is None     # fp32 LKA tail (Phase 3) on tcgen05, 3-term bf16 split
         self.lka_tail128 = os.environ.get("FFSR_LKA_TAIL128_OFF") is None   # bf16 mode: Phase-4 LKA tail + modulation layer 0 fused
+        self.token_chain = os.environ.get("FFSR_TOKEN_CHAIN_OFF") is None   # bf16 mode: Phase-4 token pipeline as two tile-resident kernels
         self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ weights
@@ -228,6 +257,9 @@ class FusionEngine:
             w["co.f0.b"] = co.ffn[0].bias.detach().float().contiguous()
             w["co.f2"] = _pack_linear(co.ffn[2].weight)
             w["co.f2.b"] = co.ffn[2].bias.detach().float().contiguous()
+            if (co.cross_attn.embed_dim, co.cross_attn.num_heads) == (128, 8) and tuple(co.ffn[0].weight.shape) == (256, 128):
+                w["co.attn_w"], w["co.attn_p"] = pack_token_attn(co)
+                w["co.ffn_w"], w["co.ffn_p"] = pack_token_ffn(co)
             w["co.m0"] = torch.stack([_pack_conv(co.modulation[i][0].weight) for i in range(4)]).contiguous()
             w["co.m0b"] = torch.stack([co.modulation[i][0].bias.detach().float() for i in range(4)]).contiguous()
             lg = co.lka_global
@@ -642,18 +674,26 @@ class FusionEngine:
                 else:
                     self._call(lib.ffsr_layernorm, src.data_ptr(), rows, 128, pp(wn), pp(bn), n1.data_ptr(), int(lp), S)
 
-            layernorm(tok4, "collaborative.norm1.weight", "collaborative.norm1.bias")
-            qkv = self._buf("co.qkv", (N4, Hq, Wq, 384), dev, dtype=adt)
-            self.conv(nhwc(n1), N4, Hq, Wq, 128, "co.qkv", 384, 1, nhwc(qkv))
-            ctx = self._buf("co.ctx", (N4, Hq, Wq, 128), dev, dtype=adt)
-            self._call(lib.ffsr_token_attention, qkv.data_ptr(), B, 4, Hq * Wq, 128, ctx.data_ptr(), int(lp), S)
             t1 = self._buf("co.t1", (N4, Hq, Wq, 128), dev, dtype=rdt)
-            self.conv(nhwc(ctx), N4, Hq, Wq, 128, "co.out", 128, 1, nhwc(t1), epi=K.EPI_RESIDUAL, r1=nhwc(tok4))
-            layernorm(t1, "collaborative.norm2.weight", "collaborative.norm2.bias")
-            hdn = self._buf("co.h", (N4, Hq, Wq, 256), dev, dtype=adt)
-            self.conv(nhwc(n1), N4, Hq, Wq, 128, "co.f0", 256, 1, nhwc(hdn), act=K.ACT_GELU)
             t2 = self._buf("co.t2", (N4, Hq, Wq, 128), dev, dtype=rdt)
-            self.conv(nhwc(hdn), N4, Hq, Wq, 256, "co.f2", 128, 1, nhwc(t2), epi=K.EPI_RESIDUAL, r1=nhwc(t1))
+            if lp and self.token_chain and rdt == torch.bfloat16 and "co.attn_w" in w:
+                # LN1 -> qkv -> 4-token attention -> out_proj + residual, then LN2 -> ffn0 -> GELU -> ffn2 + residual: two
+                # tile-resident tcgen05 kernels instead of seven launches (csrc/token_chain.cu)
+                self._call(lib.ffsr_token_attn_chain, tok4.data_ptr(), B, Hq * Wq, w["co.attn_w"].data_ptr(), w["co.attn_p"].data_ptr(),
+                           t1.data_ptr(), S)
+                self._call(lib.ffsr_token_ffn_chain, t1.data_ptr(), rows, w["co.ffn_w"].data_ptr(), w["co.ffn_p"].data_ptr(),
+                           t2.data_ptr(), S)
+            else:
+                layernorm(tok4, "collaborative.norm1.weight", "collaborative.norm1.bias")
+                qkv = self._buf("co.qkv", (N4, Hq, Wq, 384), dev, dtype=adt)
+                self.conv(nhwc(n1), N4, Hq, Wq, 128, "co.qkv", 384, 1, nhwc(qkv))
+                ctx = self._buf("co.ctx", (N4, Hq, Wq, 128), dev, dtype=adt)
+                self._call(lib.ffsr_token_attention, qkv.data_ptr(), B, 4, Hq * Wq, 128, ctx.data_ptr(), int(lp), S)
+                self.conv(nhwc(ctx), N4, Hq, Wq, 128, "co.out", 128, 1, nhwc(t1), epi=K.EPI_RESIDUAL, r1=nhwc(tok4))
+                layernorm(t1, "collaborative.norm2.weight", "collaborative.norm2.bias")
+                hdn = self._buf("co.h", (N4, Hq, Wq, 256), dev, dtype=adt)
+                self.conv(nhwc(n1), N4, Hq, Wq, 128, "co.f0", 256, 1, nhwc(hdn), act=K.ACT_GELU)
+                self.conv(nhwc(hdn), N4, Hq, Wq, 256, "co.f2", 128, 1, nhwc(t2), epi=K.EPI_RESIDUAL, r1=nhwc(t1))
             m32 = self._buf("co.m32", (N4, Hq, Wq, 32), dev, dtype=adt if (self.modulate_v2 and (Hq, Wq) == (H, W)) else f32)
             if lp and self.lka_tail128 and "co.tail_w" in w and t2.dtype == torch.bfloat16 and m32.dtype == torch.bfloat16:
                 # depthwise chain, then ONE tile-resident kernel: pw + gate, ffn0 + GELU, ffn2 + residual, modulation layer 0

@@ -126,6 +126,18 @@ int ffsr_layernorm(const float* x, long rows, int E, const float* w, const float
 /* nn.LayerNorm(128) on bf16 rows -> bf16 rows (Phase 4, bf16 mode: residual stream stored as bf16) */
 int ffsr_layernorm128_bf16(const void* x, long rows, const float* w, const float* b, void* y, cudaStream_t stream);
 int ffsr_token_attention(const void* qkv, int B, int T, long HW, int E, void* ctx, int is_bf16, cudaStream_t stream);
+/* Phase 4 token pipeline (bf16 mode) as two tile-resident tcgen05 kernels (csrc/token_chain.cu), LayerNorm folded into the
+ * contraction that follows it:
+ *   ffsr_token_attn_chain: out = x + out_proj(MultiheadAttention(LN1(x)))  over the 4 expert tokens of every pixel
+ *                          (large_kernel_attention.py:389-391); x / out bf16 [B][4][HW][128], out may alias x
+ *   ffsr_token_ffn_chain : out = x + ffn2(GELU(ffn0(LN2(x))))  (:392); x / out bf16 [rows][128]
+ * Weight / parameter blobs in the kernels' shared-memory layout: isr_b200.pipeline.pack_token_attn / pack_token_ffn. */
+size_t ffsr_token_attn_weight_bytes(void);
+size_t ffsr_token_attn_param_floats(void);
+int ffsr_token_attn_chain(const void* x, int B, int HW, const void* wblob, const float* pblob, void* out, cudaStream_t stream);
+size_t ffsr_token_ffn_weight_bytes(void);
+size_t ffsr_token_ffn_param_floats(void);
+int ffsr_token_ffn_chain(const void* x, long rows, const void* wblob, const float* pblob, void* out, cudaStream_t stream);
 
 /* ---- Phase 6 gate normalisation  src/models/enhanced_fusion_v2.py:462-465 ---------------- */
 int ffsr_gate_finalize(const float* raw, const float* diff, int B, int H, int W, const float* temperature,

@@ -52,3 +52,64 @@ def test_edge_refiner_chain_matches_layer_by_layer(B, H, W):
         assert err <= 0.04 * max(scale, 1e-3), f"level {lv}: max-abs {err:.4e} (feature scale {scale:.3e})"
         assert torch.nn.functional.cosine_similarity(a.reshape(-1), b.reshape(-1), dim=0).item() > 0.9995, lv
     assert (sr_chain - sr_ref).abs().max().item() <= 5e-3
+
+
+@pytest.mark.parametrize("B,HW", [(1, 32), (2, 77), (1, 4999)])
+def test_token_chain_against_torch(B, HW):
+    """ffsr_token_attn_chain / ffsr_token_ffn_chain (csrc/token_chain.cu) against nn.LayerNorm -> nn.MultiheadAttention -> residual
+    and nn.LayerNorm -> ffn -> residual in fp32 (large_kernel_attention.py:389-392) on the same bf16-rounded token rows.
+    Tolerance: bf16 operands (weights and the attention context / hidden row) with fp32 accumulation, bf16 output rows."""
+    import torch.nn.functional as F
+    from isr_b200.pipeline import pack_token_attn, pack_token_ffn
+    dev = _cuda()
+    m = _model(dev)
+    co = m.collaborative
+    lib = K.load()
+    g = torch.Generator().manual_seed(HW)
+    x = (torch.randn(B, 4, HW, 128, generator=g) * 0.7 + 0.15 * torch.randn(B, 4, HW, 1, generator=g)).to(torch.bfloat16).to(dev)
+    t1 = torch.full_like(x, float("nan"))
+    t2 = torch.full_like(x, float("nan"))
+    wa, pa = pack_token_attn(co)
+    wf, pf = pack_token_ffn(co)
+    assert wa.numel() * 2 == lib.ffsr_token_attn_weight_bytes() and pa.numel() == lib.ffsr_token_attn_param_floats()
+    assert wf.numel() * 2 == lib.ffsr_token_ffn_weight_bytes() and pf.numel() == lib.ffsr_token_ffn_param_floats()
+    K.check(lib.ffsr_token_attn_chain(x.data_ptr(), B, HW, wa.data_ptr(), pa.data_ptr(), t1.data_ptr(), None))
+    K.check(lib.ffsr_token_ffn_chain(t1.data_ptr(), B * 4 * HW, wf.data_ptr(), pf.data_ptr(), t2.data_ptr(), None))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        xf = x.float().permute(0, 2, 1, 3).reshape(B * HW, 4, 128)                # [pixel][expert token][128]
+        n = co.norm1(xf)
+        r1 = xf + co.cross_attn(n, n, n)[0]
+        r1_rows = r1.reshape(B, HW, 4, 128).permute(0, 2, 1, 3)
+        t1f = t1.float()
+        r2 = t1f + co.ffn(co.norm2(t1f))                                           # the FFN kernel's own input
+    s1, s2 = r1_rows.abs().max().item(), r2.abs().max().item()
+    e1 = (t1f - r1_rows).abs().max().item()
+    e2 = (t2.float() - r2).abs().max().item()
+    assert torch.isfinite(t2.float()).all()
+    assert e1 <= 0.02 * s1, f"attention chain: max-abs {e1:.4e} (scale {s1:.3e})"
+    assert e2 <= 0.02 * s2, f"ffn chain: max-abs {e2:.4e} (scale {s2:.3e})"
+    assert F.cosine_similarity((t1f - x.float()).reshape(-1), (r1_rows - x.float()).reshape(-1), dim=0).item() > 0.999
+    assert F.cosine_similarity((t2.float() - t1f).reshape(-1), (r2 - t1f).reshape(-1), dim=0).item() > 0.999
+
+
+def test_token_chain_matches_layer_by_layer_forward():
+    """Whole bf16 forward with the token chain on and off (seven-launch path): same image within bf16 storage error."""
+    dev = _cuda()
+    m = _model(dev)
+    lr, imgs, fts, _ = O.synthetic_inputs(1, 40, 56)
+    lr, imgs, fts = lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()}
+    with torch.no_grad():
+        m.forward_with_precomputed(lr, imgs, fts)
+        eng = m._engine
+        assert eng.token_chain
+        sr_chain = m.forward_with_precomputed(lr, imgs, fts).float().cpu()
+        t2_chain = eng.workspace("co.t2").float().cpu().clone()
+        eng.token_chain = False
+        sr_ref = m.forward_with_precomputed(lr, imgs, fts).float().cpu()
+        t2_ref = eng.workspace("co.t2").float().cpu().clone()
+        eng.token_chain = True
+    scale = t2_ref.abs().max().item()
+    assert (t2_chain - t2_ref).abs().max().item() <= 0.03 * scale
+    assert torch.nn.functional.cosine_similarity(t2_chain.reshape(-1), t2_ref.reshape(-1), dim=0).item() > 0.9995
+    assert (sr_chain - sr_ref).abs().max().item() <= 5e-3

@@ -94,15 +94,18 @@ def test_orchestration_dry_run(with_feats, want_inter, precision):
     calls = eng.lib.calls
     # conv launches: the Phase-3 LKA tail (3 convs) is one ffsr_lka_tail64 launch in both modes; bf16 mode also has one
     # grouped align conv instead of four, each edge refiner (6 convs x 3 levels) as one ffsr_edge_refiner_chain launch and
-    # the Phase-4 LKA tail + modulation layer 0 (4 convs) as one ffsr_lka_tail128_mod launch
+    # the Phase-4 LKA tail + modulation layer 0 (4 convs) as one ffsr_lka_tail128_mod launch, and the Phase-4 token pipeline
+    # (qkv, out, ffn0, ffn2 convs + two LayerNorms + the attention core) as ffsr_token_attn_chain + ffsr_token_ffn_chain
     expect = (63 if with_feats else 51) - 3
     if precision == "bf16":
-        expect -= 3 + 18 + 4
+        expect -= 3 + 18 + 4 + 4
     assert calls.count("ffsr_conv2d") == expect, calls.count("ffsr_conv2d")
     assert calls.count("ffsr_lka_tail64") == 1
     assert calls.count("ffsr_edge_refiner_chain") == (3 if precision == "bf16" else 0)
     assert calls.count("ffsr_lka_tail128_mod") == (1 if (precision == "bf16" and with_feats) else 0)
-    assert ("ffsr_token_attention" in calls) == with_feats
+    chain = precision == "bf16" and with_feats
+    assert ("ffsr_token_attention" in calls) == (with_feats and not chain)
+    assert calls.count("ffsr_token_attn_chain") == calls.count("ffsr_token_ffn_chain") == (1 if chain else 0)
     assert calls[-1] == "ffsr_final_combine"
     if want_inter:
         assert set(inter) >= {"raw_9_bands", "enhanced_9_bands", "routing_lr", "collaborative_outputs",
