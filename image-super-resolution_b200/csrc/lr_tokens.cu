@@ -5,6 +5,7 @@
 //   * LayerNorm rows and the 4-token x 8-head attention core used by Phase 4 (:389-392)
 //   * Phase 6 gate normalisation (DynamicExpertSelector.forward, enhanced_fusion_v2.py:462-465)
 // All fp32: routing_lr feeds the expert-selection indices that must be bit-exact.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -205,6 +206,209 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_crossband_attn(
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Folded cross-band attention, register-blocked (replaces k_crossband_attn<true>: 0.87 ms per C3 image at ~15 % of the FMA
+// peak, bound by one shared-memory load per FMA in the attention and out_proj loops and by five block barriers per 8 pixels).
+// A WARP owns 8 pixels per iteration and never meets a block barrier; lane = (pixel, head):
+//   * 1/std of the 9 tokens: each of a pixel's four lanes sums 16 of the 64 centred channels, two xor-shuffles combine them;
+//   * q, k, v are never stored: channel d of head h is  rstd * (M[d] . x + m0[d]) + n0[d]  (4 FMAs), computed where it is used,
+//     k / v once per pixel and head for all three query bands of a group;
+//   * softmax(q k^T / 4) v in registers, context -> a per-warp shared tile [24 tokens][64];
+//   * out_proj as a 6-token x 8-channel register tile per lane (48 FMAs per 14 vector loads), + bias + band_proj residual.
+// Summation orders of the scores (d = 0..15), the context (j = 0..8) and out_proj (c = 0..63) are those of the kernel above.
+// ------------------------------------------------------------------------------------
+namespace {
+constexpr int CB2_WARPS = 8, CB2_PX = 8, CB2_LD = 68;
+struct CB2Smem {
+  float4 fa[CB_DIM];                   // centred band_proj rows A | c
+  float4 fm[3 * CB_DIM];               // folded in_proj rows M | m0   (q, k, v)
+  float4 pw[CB_DIM];                   // band_proj rows W | b (residual)
+  float n0[3 * CB_DIM];
+  float ob[CB_DIM];
+  float wo[CB_DIM][CB_DIM];            // out_proj transposed: wo[c][o]
+  float xs[CB2_WARPS][CB2_PX][28];     // the 27 band values of the warp's pixels
+  float ctx[CB2_WARPS][3 * CB2_PX][CB2_LD];
+};
+__device__ __forceinline__ float aff3(const float4& m, float x0, float x1, float x2) {
+  return fmaf(m.z, x2, fmaf(m.y, x1, fmaf(m.x, x0, m.w)));
+}
+}  // namespace
+
+template <int NG>   // query-band groups of three: 1 for the production nq = 3 (x and rstd die before out_proj), 3 for nq up to 9
+__global__ void __launch_bounds__(CB2_WARPS * 32, 2) k_crossband_attn2(
+    const float* __restrict__ fold, const float* __restrict__ raw9, int B, int HW, const float* __restrict__ proj_w,
+    const float* __restrict__ proj_b, const float* __restrict__ out_w, const float* __restrict__ out_b, int nq,
+    float* __restrict__ tok_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CB2Smem& s = *reinterpret_cast<CB2Smem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < CB_DIM * CB_DIM; i += CB2_WARPS * 32) s.wo[i % CB_DIM][i / CB_DIM] = out_w[i];
+  for (int i = tid; i < 3 * CB_DIM; i += CB2_WARPS * 32) {
+    s.fm[i] = *reinterpret_cast<const float4*>(fold + CB_DIM * 4 + (long)i * 4);
+    s.n0[i] = fold[CB_DIM * 4 + 3 * CB_DIM * 4 + i];
+  }
+  if (tid < CB_DIM) {
+    s.fa[tid] = *reinterpret_cast<const float4*>(fold + tid * 4);
+    s.pw[tid] = make_float4(proj_w[tid * 3], proj_w[tid * 3 + 1], proj_w[tid * 3 + 2], proj_b[tid]);
+    s.ob[tid] = out_b[tid];
+  }
+  __syncthreads();
+
+  const int px = lane >> 2, h = lane & 3;
+  const int tb = lane >> 3, cb = lane & 7;            // out_proj tile: tokens 6 tb .. 6 tb + 5, channels 8 cb .. 8 cb + 7
+  const int tiles_per_img = (HW + CB2_PX - 1) / CB2_PX;
+  const long total = (long)B * tiles_per_img;
+  float (*xs)[28] = s.xs[warp];
+  float (*ctx)[CB2_LD] = s.ctx[warp];
+  for (long tile = (long)blockIdx.x * CB2_WARPS + warp; tile < total; tile += (long)gridDim.x * CB2_WARPS) {
+    const int b = (int)(tile / tiles_per_img);
+    const int p0 = (int)(tile - (long)b * tiles_per_img) * CB2_PX;
+    const int p = p0 + px;
+    float x[27];
+#pragma unroll
+    for (int r = 0; r < 27; ++r) x[r] = (p < HW) ? __ldg(raw9 + ((long)b * 27 + r) * HW + p) : 0.f;
+    if (h == 0) {
+#pragma unroll
+      for (int r = 0; r < 27; ++r) xs[px][r] = x[r];
+    }
+    // 1/std of the nine tokens
+    float rstd[CB_BANDS];
+    {
+      float sq[CB_BANDS];
+#pragma unroll
+      for (int j = 0; j < CB_BANDS; ++j) sq[j] = 0.f;
+#pragma unroll 4
+      for (int cc = 0; cc < 16; ++cc) {
+        const float4 a = s.fa[h * 16 + cc];
+#pragma unroll
+        for (int j = 0; j < CB_BANDS; ++j) {
+          const float d = aff3(a, x[3 * j], x[3 * j + 1], x[3 * j + 2]);
+          sq[j] = fmaf(d, d, sq[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CB_BANDS; ++j) {
+        sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 1);
+        sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 2);
+        rstd[j] = rsqrtf(sq[j] * (1.0f / CB_DIM) + 1e-5f);
+      }
+    }
+#pragma unroll
+    for (int qg = 0; qg < NG; ++qg) {
+      if (qg * 3 >= nq) break;
+      // scores of this head for the three query bands of the group
+      float sc[3][CB_BANDS];
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int j = 0; j < CB_BANDS; ++j) sc[t][j] = 0.f;
+#pragma unroll 2
+      for (int d = 0; d < CB_HD; ++d) {
+        const int ch = h * CB_HD + d;
+        const float4 mk = s.fm[CB_DIM + ch], mq = s.fm[ch];
+        const float nk = s.n0[CB_DIM + ch], nqv = s.n0[ch];
+        float kd[CB_BANDS];
+#pragma unroll
+        for (int j = 0; j < CB_BANDS; ++j) kd[j] = fmaf(aff3(mk, x[3 * j], x[3 * j + 1], x[3 * j + 2]), rstd[j], nk);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const int qt = qg * 3 + t;
+          const float qv = fmaf(aff3(mq, x[3 * qt], x[3 * qt + 1], x[3 * qt + 2]), rstd[qt], nqv);
+#pragma unroll
+          for (int j = 0; j < CB_BANDS; ++j) sc[t][j] = fmaf(qv, kd[j], sc[t][j]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < CB_BANDS; ++j) {
+          sc[t][j] *= 0.25f;
+          mx = fmaxf(mx, sc[t][j]);
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int j = 0; j < CB_BANDS; ++j) {
+          sc[t][j] = expf(sc[t][j] - mx);
+          den += sc[t][j];
+        }
+        const float inv = 1.0f / den;
+#pragma unroll
+        for (int j = 0; j < CB_BANDS; ++j) sc[t][j] *= inv;
+      }
+      __syncwarp();                                    // the previous group's out_proj reads of ctx are done
+#pragma unroll 1
+      for (int d4 = 0; d4 < CB_HD / 4; ++d4) {
+        float cv[3][4];
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) {
+          const int ch = h * CB_HD + d4 * 4 + dd;
+          const float4 mv = s.fm[2 * CB_DIM + ch];
+          const float nv = s.n0[2 * CB_DIM + ch];
+          float vd[CB_BANDS];
+#pragma unroll
+          for (int j = 0; j < CB_BANDS; ++j) vd[j] = fmaf(aff3(mv, x[3 * j], x[3 * j + 1], x[3 * j + 2]), rstd[j], nv);
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < CB_BANDS; ++j) a = fmaf(sc[t][j], vd[j], a);
+            cv[t][dd] = a;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          *reinterpret_cast<float4*>(&ctx[px * 3 + t][h * CB_HD + d4 * 4]) = make_float4(cv[t][0], cv[t][1], cv[t][2], cv[t][3]);
+      }
+      __syncwarp();
+      // out_proj + bias + band_proj residual for tokens 6 tb .. 6 tb + 5, channels 8 cb .. 8 cb + 7
+      float acc[6][8];
+      {
+        const float4 o0 = *reinterpret_cast<const float4*>(&s.ob[cb * 8]), o1 = *reinterpret_cast<const float4*>(&s.ob[cb * 8 + 4]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          acc[i][0] = o0.x; acc[i][1] = o0.y; acc[i][2] = o0.z; acc[i][3] = o0.w;
+          acc[i][4] = o1.x; acc[i][5] = o1.y; acc[i][6] = o1.z; acc[i][7] = o1.w;
+        }
+      }
+#pragma unroll 2
+      for (int k4 = 0; k4 < CB_DIM / 4; ++k4) {
+        float4 c4[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) c4[i] = *reinterpret_cast<const float4*>(&ctx[tb * 6 + i][k4 * 4]);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 w0 = *reinterpret_cast<const float4*>(&s.wo[k4 * 4 + kk][cb * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&s.wo[k4 * 4 + kk][cb * 8 + 4]);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const float cvv = kk == 0 ? c4[i].x : kk == 1 ? c4[i].y : kk == 2 ? c4[i].z : c4[i].w;
+            acc[i][0] = fmaf(cvv, w0.x, acc[i][0]); acc[i][1] = fmaf(cvv, w0.y, acc[i][1]);
+            acc[i][2] = fmaf(cvv, w0.z, acc[i][2]); acc[i][3] = fmaf(cvv, w0.w, acc[i][3]);
+            acc[i][4] = fmaf(cvv, w1.x, acc[i][4]); acc[i][5] = fmaf(cvv, w1.y, acc[i][5]);
+            acc[i][6] = fmaf(cvv, w1.z, acc[i][6]); acc[i][7] = fmaf(cvv, w1.w, acc[i][7]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int tk = tb * 6 + i, pxo = tk / 3, qt = qg * 3 + tk % 3;
+        const int po = p0 + pxo;
+        if (po < HW && qt < nq) {
+          const float x0 = xs[pxo][qt * 3], x1 = xs[pxo][qt * 3 + 1], x2 = xs[pxo][qt * 3 + 2];
+          float r[8];
+#pragma unroll
+          for (int o = 0; o < 8; ++o) r[o] = acc[i][o] + aff3(s.pw[cb * 8 + o], x0, x1, x2);
+          float4* dst = reinterpret_cast<float4*>(tok_out + (((long)b * nq + qt) * HW + po) * CB_DIM + cb * 8);
+          dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+          dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+        }
+      }
+    }
+    __syncwarp();                                      // xs / ctx are rewritten by the next tile
+  }
+}
+
 extern "C" int ffsr_crossband_attention(const float* raw9, int B, int H, int W, const float* proj_w,
                                         const float* proj_b, const float* ln_w, const float* ln_b,
                                         const float* in_w, const float* in_b, const float* out_w,
@@ -223,7 +427,21 @@ extern "C" int ffsr_crossband_attention(const float* raw9, int B, int H, int W, 
     attr_set = true;
   }
   const int grid = tiles < 2 * num_sms ? tiles : 2 * num_sms;
-  if (fold) {
+  static const bool v1 = getenv("FFSR_CROSSBAND_V1") != nullptr;
+  if (fold && !v1) {
+    FFSR_REQUIRE(((uintptr_t)fold % 16) == 0 && ((uintptr_t)tok_out % 16) == 0, FFSR_ERR_ALIGN, "crossband_attention: fold / tok_out must be 16B aligned");
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaFuncSetAttribute(k_crossband_attn2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CB2Smem));
+      cudaFuncSetAttribute(k_crossband_attn2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CB2Smem));
+      attr2 = true;
+    }
+    const long wtiles = (long)B * ((HW + CB2_PX - 1) / CB2_PX);
+    const long blocks = (wtiles + CB2_WARPS - 1) / CB2_WARPS;
+    const int grid2 = (int)(blocks < 2L * num_sms ? blocks : 2L * num_sms);
+    if (nq <= 3) k_crossband_attn2<1><<<grid2, CB2_WARPS * 32, sizeof(CB2Smem), stream>>>(fold, raw9, B, HW, proj_w, proj_b, out_w, out_b, nq, tok_out);
+    else k_crossband_attn2<3><<<grid2, CB2_WARPS * 32, sizeof(CB2Smem), stream>>>(fold, raw9, B, HW, proj_w, proj_b, out_w, out_b, nq, tok_out);
+  } else if (fold) {
     FFSR_REQUIRE(((uintptr_t)fold % 16) == 0, FFSR_ERR_ALIGN, "crossband_attention: fold buffer must be 16B aligned");
     k_crossband_attn<true><<<grid, CB_THREADS, sizeof(CBSmem), stream>>>(fold, raw9, B, HW, proj_w, proj_b, ln_w, ln_b, in_w,
                                                                          in_b, out_w, out_b, nq, tok_out);
