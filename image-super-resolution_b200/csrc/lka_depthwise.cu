@@ -7,6 +7,7 @@
 // (three separately padded convs != one 25x25 conv at the borders; SURVEY §7 hard part 5).
 // HBM/L1-bound: each thread owns one channel and a short run of outputs along the conv
 // axis, keeps the sliding window in registers, and warps read 32 consecutive channels.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -15,10 +16,14 @@ constexpr int R21 = 16;  // outputs per thread along the conv axis for the 21-ta
 }
 
 // BN is folded to y = x*k + d (eval: running stats; train: batch stats computed upstream).
-template <typename TI>
-__global__ void __launch_bounds__(256) k_lka_dw5(const TI* __restrict__ x, int H, int W, int C,
+// CT: compile-time channel count (0 = run time).  With CT the x-direction offsets i * C of the interior path are immediates of
+// the load / store instructions: the kernels are issue-bound and the address arithmetic was more than a third of their
+// instructions (ncu: 125 M warp instructions for 58 M warp FFMAs in the Phase-4 1x21 pass).
+template <typename TI, int CT = 0>
+__global__ void __launch_bounds__(256) k_lka_dw5(const TI* __restrict__ x, int H, int W, int C_rt,
                                                  const float* __restrict__ bn_k, const float* __restrict__ bn_d,
                                                  const float* __restrict__ w5, float* __restrict__ out) {
+  const int C = CT > 0 ? CT : C_rt;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int runs_x = (W + R5 - 1) / R5, runs_y = (H + R5 - 1) / R5;
   const int idx = blockIdx.y * blockDim.y + threadIdx.y;      // over runs_y * runs_x
@@ -89,9 +94,10 @@ __global__ void __launch_bounds__(256) k_lka_dw5(const TI* __restrict__ x, int H
 }
 
 // AXIS = 0: taps along W (1x21); AXIS = 1: taps along H (21x1)
-template <int AXIS, typename TO>
-__global__ void __launch_bounds__(256) k_lka_dw21(const float* __restrict__ in, int H, int W, int C,
+template <int AXIS, typename TO, int CT = 0>
+__global__ void __launch_bounds__(256) k_lka_dw21(const float* __restrict__ in, int H, int W, int C_rt,
                                                   const float* __restrict__ w21, TO* __restrict__ out) {
+  const int C = CT > 0 ? CT : C_rt;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.z;
   int y, x;
@@ -156,6 +162,73 @@ __global__ void __launch_bounds__(256) k_lka_dw21(const float* __restrict__ in, 
   }
 }
 
+// Rolling-window 21-tap pass: a thread owns one channel and a STRIP of up to `strip` outputs along the conv axis and walks it
+// in chunks of 16.  The 36-value window stays in registers; each chunk loads only its 16 new values, and loads them one
+// chunk AHEAD, so their latency hides behind the 336 FMAs of the current chunk (the one-shot kernel above loads 36 values per
+// 16 outputs and then waits: ncu showed 44 % of the issue cycles without an eligible warp at 29 % occupancy).
+// Tap order of every output is t = 0..20 as above: results are bit-identical to k_lka_dw21.
+template <int AXIS, typename TO, int CT>
+__global__ void __launch_bounds__(256) k_lka_dw21_roll(const float* __restrict__ in, int H, int W, int C_rt, const float* __restrict__ w21,
+                                                       TO* __restrict__ out, int strip, int nstrips) {
+  const int C = CT > 0 ? CT : C_rt;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.z;
+  const int L = (AXIS == 0) ? W : H, lines = (AXIS == 0) ? H : W;
+  const int idx = blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= C || idx >= lines * nstrips) return;
+  const int line = idx / nstrips, s0 = (idx - line * nstrips) * strip;
+  const int s1 = min(s0 + strip, L);
+  if (s0 >= s1) return;
+  const long stride = (AXIS == 0) ? C : (long)W * C;
+  const long lbase = (long)n * H * W * C + ((AXIS == 0) ? (long)line * W * C : (long)line * C) + c;
+  const float* base = in + lbase;
+  TO* obase = out + lbase;
+  float w[21];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) w[i] = w21[c * 21 + i];
+  float v[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) {
+    const int q = s0 - 10 + i;
+    v[i] = (q >= 0 && q < L) ? base[q * stride] : 0.f;
+  }
+#pragma unroll 1
+  for (int pos = s0; pos < s1; pos += 16) {
+    float nv[16];
+    const bool more = pos + 16 < s1;
+    const float* pn = base + (long)(pos + 26) * stride;
+    if (more && pos + 42 <= L) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) nv[i] = pn[i * stride];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) nv[i] = (more && pos + 26 + i < L) ? pn[i * stride] : 0.f;
+    }
+    TO* po = obase + (long)pos * stride;
+    if (pos + 16 <= s1) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 21; ++t) acc = fmaf(w[t], v[r + t], acc);
+        po[r * stride] = from_f32<TO>(acc);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 21; ++t) acc = fmaf(w[t], v[r + t], acc);
+        if (pos + r < s1) po[r * stride] = from_f32<TO>(acc);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 20; ++i) v[i] = v[i + 16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[20 + i] = nv[i];
+  }
+}
+
 // x: [N][H][W][C] -> out: [N][H][W][C]; tmp1/tmp2: same-size scratch (tmp2 may alias out? no: distinct)
 static int lka_depthwise_impl(const void* x, int x_dtype, int N, int H, int W, int C, const float* bn_k, const float* bn_d,
                               const float* w5, const float* wh, const float* wv, float* tmp1, float* tmp2, void* out,
@@ -181,32 +254,36 @@ static int lka_depthwise_impl(const void* x, int x_dtype, int N, int H, int W, i
   FFSR_REQUIRE(N <= 65535 && (long)H * W / 4 < 65535L * 4, FFSR_ERR_ARG, "lka_depthwise: grid too large");
   const int cx = C < 64 ? C : 64;
   const int ty = 256 / cx;
-  {
-    dim3 block(cx, ty);
-    dim3 grid(C / cx, ceil_div((long)ceil_div(H, R5) * ceil_div(W, R5), ty), N);
-    if (x_dtype == 1) k_lka_dw5<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, H, W, C, bn_k, bn_d, w5, tmp1);
-    else k_lka_dw5<float><<<grid, block, 0, stream>>>((const float*)x, H, W, C, bn_k, bn_d, w5, tmp1);
-    int rc = ffsr_check_launch("lka_dw5");
-    if (rc) return rc;
+  const dim3 block(cx, ty);
+  const dim3 g5(C / cx, ceil_div((long)ceil_div(H, R5) * ceil_div(W, R5), ty), N);
+  const dim3 gh(C / cx, ceil_div((long)H * ceil_div(W, R21), ty), N);
+  const dim3 gv(C / cx, ceil_div((long)ceil_div(H, R21) * W, ty), N);
+  typedef __nv_bfloat16 bf;
+  // rolling-window 21-tap passes: strips of <= `target` outputs (a multiple of 16) along the conv axis
+  static const int target = getenv("FFSR_DW_STRIP") ? atoi(getenv("FFSR_DW_STRIP")) : 256;
+  const bool roll = target > 0;
+  const int tg = target > 0 ? target : 128;
+  const int nsw = ceil_div(W, tg), sw = ceil_div(ceil_div(W, nsw), 16) * 16;
+  const int nsh = ceil_div(H, tg), sh = ceil_div(ceil_div(H, nsh), 16) * 16;
+  const dim3 rh(C / cx, ceil_div((long)H * nsw, ty), N);
+  const dim3 rv(C / cx, ceil_div((long)W * nsh, ty), N);
+#define FFSR_DW_CHAIN(CT)                                                                                              \
+  {                                                                                                                    \
+    if (x_dtype == 1) k_lka_dw5<bf, CT><<<g5, block, 0, stream>>>((const bf*)x, H, W, C, bn_k, bn_d, w5, tmp1);        \
+    else k_lka_dw5<float, CT><<<g5, block, 0, stream>>>((const float*)x, H, W, C, bn_k, bn_d, w5, tmp1);               \
+    if (!roll) {                                                                                                       \
+      k_lka_dw21<0, float, CT><<<gh, block, 0, stream>>>(tmp1, H, W, C, wh, tmp2);                                     \
+      if (out_dtype == 1) k_lka_dw21<1, bf, CT><<<gv, block, 0, stream>>>(tmp2, H, W, C, wv, (bf*)out);                \
+      else k_lka_dw21<1, float, CT><<<gv, block, 0, stream>>>(tmp2, H, W, C, wv, (float*)out);                         \
+    } else {                                                                                                           \
+      k_lka_dw21_roll<0, float, CT><<<rh, block, 0, stream>>>(tmp1, H, W, C, wh, tmp2, sw, nsw);                       \
+      if (out_dtype == 1) k_lka_dw21_roll<1, bf, CT><<<rv, block, 0, stream>>>(tmp2, H, W, C, wv, (bf*)out, sh, nsh);  \
+      else k_lka_dw21_roll<1, float, CT><<<rv, block, 0, stream>>>(tmp2, H, W, C, wv, (float*)out, sh, nsh);           \
+    }                                                                                                                  \
   }
-  {
-    dim3 block(cx, ty);
-    const long items = (long)H * ceil_div(W, R21);
-    dim3 grid(C / cx, ceil_div(items, ty), N);
-    k_lka_dw21<0, float><<<grid, block, 0, stream>>>(tmp1, H, W, C, wh, tmp2);
-    int rc = ffsr_check_launch("lka_dw21_h");
-    if (rc) return rc;
-  }
-  {
-    dim3 block(cx, ty);
-    const long items = (long)ceil_div(H, R21) * W;
-    dim3 grid(C / cx, ceil_div(items, ty), N);
-    if (out_dtype == 1)
-      k_lka_dw21<1, __nv_bfloat16><<<grid, block, 0, stream>>>(tmp2, H, W, C, wv, (__nv_bfloat16*)out);
-    else
-      k_lka_dw21<1, float><<<grid, block, 0, stream>>>(tmp2, H, W, C, wv, (float*)out);
-    return ffsr_check_launch("lka_dw21_v");
-  }
+  if (C == 128) FFSR_DW_CHAIN(128) else if (C == 64) FFSR_DW_CHAIN(64) else FFSR_DW_CHAIN(0)
+#undef FFSR_DW_CHAIN
+  return ffsr_check_launch("lka_depthwise");
 }
 
 // ------------------------------------------------------------------------------------

@@ -481,6 +481,246 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lka_tail128(const __nv_bfloat
   }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(LB_TMEM_COLS));
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_lka_tail128w: the same chain with 512 threads (warp w: TMEM lane group w % 4 = 32 token rows, channel quarter w / 4), the
+// next tile's rows prefetched into registers, and the four hidden quarters written alternately to sH and to the two halves
+// of the (by then dead) x1 planes, so the four ffn2 MMAs are issued back to back with the GELU epilogues instead of being
+// waited for one by one.  ncu of the 256-thread version: 3.3 k instructions per thread and tile at two warps per scheduler,
+// 75 % of the issue cycles without an eligible warp (long-scoreboard on the un-prefetched loads, MMA waits).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int LW_THREADS = 512;
+
+__device__ __forceinline__ float bfl(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bfh(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+template <bool TANH>
+__global__ void __launch_bounds__(LW_THREADS, 1) k_lka_tail128w(const __nv_bfloat16* __restrict__ xin, const __nv_bfloat16* __restrict__ ain,
+                                                                int nimg, int HW, const uint8_t* __restrict__ wblob,
+                                                                const float* __restrict__ pblob, const float* __restrict__ s1p,
+                                                                const float* __restrict__ s2p, __nv_bfloat16* __restrict__ m32) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);          // bar[0]: stage barrier, bar[1]: "ffn2 quarter 0 done" (sH reusable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+  float* par = reinterpret_cast<float*>(smem + LB_S_PAR);
+  uint8_t* sW = smem + LB_S_W;
+  uint8_t* sWM = smem + LB_S_WM;
+  uint8_t* sA = smem + LB_S_A;
+  uint8_t* sH = smem + LB_S_H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane;
+  const int cq = warp >> 2;                          // 32 of the 128 columns
+
+  for (int i = tid; i < (LB_W1 + LB_W0 + LB_W2) / 16; i += LW_THREADS) reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(wblob) + i);
+  for (int i = tid; i < LB_PF; i += LW_THREADS) par[i] = __ldg(pblob + i);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(LB_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float s1 = s1p[0], s2 = s2p[0];
+  const float* b_pw = par;
+  const float* k1 = par + 128;
+  const float* d1 = par + 256;
+  const float* b0 = par + 384;
+  const float* b2 = par + 640;
+  const float* bm = par + 768;
+  const uint32_t w1_32 = smem_u32(sW), w0_32 = w1_32 + LB_W1, w2_32 = w0_32 + LB_W0, wm_32 = smem_u32(sWM), a32 = smem_u32(sA), h32 = smem_u32(sH);
+  const uint32_t hi = desc_hi(128);
+  const uint32_t id128 = idesc_bf16_m128(128), id256 = idesc_bf16_m128(256), id32 = idesc_bf16_m128(32);
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t phase = 0, phase1 = 0;
+  const int tpi = (HW + 127) / 128;
+  const long tiles = (long)nimg * tpi;
+  int cur_e = -1;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+
+  auto row_off = [&](long tile, bool& live) -> long {
+    const int n = (int)(tile / tpi), pr = (int)(tile - (long)n * tpi) * 128 + row;
+    live = pr < HW;
+    return ((long)n * HW + (live ? pr : 0)) * LB_C + cq * 32;
+  };
+  uint4 na[4], nx[4];
+  bool nlive = false;
+  if ((long)blockIdx.x < tiles) {
+    const long o = row_off(blockIdx.x, nlive);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      na[g] = nlive ? __ldg(reinterpret_cast<const uint4*>(ain + o) + g) : zero4;
+      nx[g] = nlive ? __ldg(reinterpret_cast<const uint4*>(xin + o) + g) : zero4;
+    }
+  }
+
+  for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int n = (int)(tile / tpi);
+    const int e = n & 3;
+    const bool live = nlive;
+    bool dummy;
+    const long r32 = (row_off(tile, dummy) - cq * 32) / LB_C * 32;     // this row's offset in m32
+    if (e != cur_e) {                                // (uniform) this expert's modulation weights; the previous tile's MMAs are done
+      for (int i = tid; i < LB_WM / 16; i += LW_THREADS)
+        reinterpret_cast<uint4*>(sWM)[i] = __ldg(reinterpret_cast<const uint4*>(wblob + LB_W1 + LB_W0 + LB_W2 + e * LB_WM) + i);
+      cur_e = e;
+    }
+    float x[32];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      *reinterpret_cast<uint4*>(sA + (cq * 4 + g) * 2048 + row * 16) = na[g];
+      x[8 * g + 0] = bfl(nx[g].x); x[8 * g + 1] = bfh(nx[g].x); x[8 * g + 2] = bfl(nx[g].y); x[8 * g + 3] = bfh(nx[g].y);
+      x[8 * g + 4] = bfl(nx[g].z); x[8 * g + 5] = bfh(nx[g].z); x[8 * g + 6] = bfl(nx[g].w); x[8 * g + 7] = bfh(nx[g].w);
+    }
+    if (tile + gridDim.x < tiles) {                  // next tile's rows: in flight during this tile's compute
+      const long o = row_off(tile + gridDim.x, nlive);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        na[g] = nlive ? __ldg(reinterpret_cast<const uint4*>(ain + o) + g) : zero4;
+        nx[g] = nlive ? __ldg(reinterpret_cast<const uint4*>(xin + o) + g) : zero4;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- stage 1: G = a . Wpw^T (K = 128, N = 128)
+    if (warp == 0) {
+      tc_fence_after();
+      umma_taps_1x4(tmem, desc_lo(a32, 2048u), desc_lo(w1_32, 128u * 16u), id128, 0u, hi, hi, (2u * 2048u) >> 4, 2u * 128u, 0u);
+      umma_taps_1x4(tmem, desc_lo(a32 + 8u * 2048u, 2048u), desc_lo(w1_32 + 8u * 128u * 16u, 128u * 16u), id128, 1u, hi, hi, (2u * 2048u) >> 4, 2u * 128u, 0u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 1: x1 = x + s1 * (x k1 + d1) * sigmoid(G + b) -> registers and planes (the a planes are dead)
+    {
+      uint32_t v0[16], v1[16];
+      tmem_ld16(trow + (uint32_t)(cq * 32), v0);
+      tmem_ld16(trow + (uint32_t)(cq * 32 + 16), v1);
+      tmem_wait_ld(v0);
+      tmem_wait_ld(v1);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int ch = cq * 32 + i;
+        const float g = __uint_as_float(i < 16 ? v0[i & 15] : v1[i & 15]) + b_pw[ch];
+        const float sg = __fdividef(1.0f, 1.0f + __expf(-g));
+        x[i] = fmaf(s1 * fmaf(x[i], k1[ch], d1[ch]), sg, x[i]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(sA + (cq * 4 + g) * 2048 + row * 16) =
+          make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]), pack_bf16(x[g * 8 + 4], x[g * 8 + 5]),
+                     pack_bf16(x[g * 8 + 6], x[g * 8 + 7]));
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- stage 2: Hd = x1 . W0^T (K = 128, N = 256) at TMEM column 128
+    if (warp == 0) {
+      tc_fence_after();
+      umma_taps_1x4(tmem + 128, desc_lo(a32, 2048u), desc_lo(w0_32, 256u * 16u), id256, 0u, hi, hi, (2u * 2048u) >> 4, 2u * 256u, 0u);
+      umma_taps_1x4(tmem + 128, desc_lo(a32 + 8u * 2048u, 2048u), desc_lo(w0_32 + 8u * 256u * 16u, 256u * 16u), id256, 1u, hi, hi, (2u * 2048u) >> 4, 2u * 256u, 0u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- stage 3: hidden quarters of 64 channels: GELU(Hd + b0) -> planes -> acc += . W2^T.  Quarter q goes to
+    //      sH (q = 0, 3), x1 planes low half (q = 1), high half (q = 2): the MMAs are issued without waiting, except that
+    //      quarter 3 reuses sH and waits for quarter 0's MMA (bar[1]), long complete by then.
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)(128 + q * 64 + cq * 16), v);
+      tmem_wait_ld(v);
+      float y[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float z = __uint_as_float(v[i]) + b0[q * 64 + cq * 16 + i];
+        y[i] = TANH ? gelu_tanh_fast(z) : gelu_erf_fast(z);
+      }
+      if (q == 3) {
+        mbar_wait(bar + 1, phase1);
+        phase1 ^= 1;
+      }
+      uint8_t* dst = (q == 0 || q == 3) ? sH : (q == 1 ? sA : sA + 8 * 2048);
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        *reinterpret_cast<uint4*>(dst + (cq * 2 + g) * 2048 + row * 16) =
+            make_uint4(pack_bf16(y[g * 8], y[g * 8 + 1]), pack_bf16(y[g * 8 + 2], y[g * 8 + 3]), pack_bf16(y[g * 8 + 4], y[g * 8 + 5]),
+                       pack_bf16(y[g * 8 + 6], y[g * 8 + 7]));
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        tc_fence_after();
+        const uint32_t src = (q == 0 || q == 3) ? h32 : (q == 1 ? a32 : a32 + 8u * 2048u);
+        umma_taps_1x4(tmem, desc_lo(src, 2048u), desc_lo(w2_32 + (uint32_t)(q * 8) * 128u * 16u, 128u * 16u), id128, q == 0 ? 0u : 1u, hi, hi,
+                      (2u * 2048u) >> 4, 2u * 128u, 0u);
+        if (q == 0) umma_commit(bar + 1);
+        if (q == 3) umma_commit(bar);
+      }
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 3: x2 = x1 + s2 * (acc + b2) -> planes
+    {
+      uint32_t v0[16], v1[16];
+      tmem_ld16(trow + (uint32_t)(cq * 32), v0);
+      tmem_ld16(trow + (uint32_t)(cq * 32 + 16), v1);
+      tmem_wait_ld(v0);
+      tmem_wait_ld(v1);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        x[i] = fmaf(s2, __uint_as_float(i < 16 ? v0[i & 15] : v1[i & 15]) + b2[cq * 32 + i], x[i]);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(sA + (cq * 4 + g) * 2048 + row * 16) =
+          make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]), pack_bf16(x[g * 8 + 4], x[g * 8 + 5]),
+                     pack_bf16(x[g * 8 + 6], x[g * 8 + 7]));
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- stage 4: modulation layer 0 of this expert, m32 = x2 . Wm^T (K = 128, N = 32) at TMEM column 128
+    if (warp == 0) {
+      tc_fence_after();
+      umma_taps_1x4(tmem + 128, desc_lo(a32, 2048u), desc_lo(wm_32, 32u * 16u), id32, 0u, hi, hi, (2u * 2048u) >> 4, 2u * 32u, 0u);
+      umma_taps_1x4(tmem + 128, desc_lo(a32 + 8u * 2048u, 2048u), desc_lo(wm_32 + 8u * 32u * 16u, 32u * 16u), id32, 1u, hi, hi, (2u * 2048u) >> 4, 2u * 32u, 0u);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    if (cq < 2) {
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)(128 + cq * 16), v);
+      tmem_wait_ld(v);
+      if (live) {
+        const float* bb = bm + e * 32 + cq * 16;
+        uint4* op = reinterpret_cast<uint4*>(m32 + r32 + cq * 16);
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          op[g] = make_uint4(pack_bf16(__uint_as_float(v[8 * g]) + bb[8 * g], __uint_as_float(v[8 * g + 1]) + bb[8 * g + 1]),
+                             pack_bf16(__uint_as_float(v[8 * g + 2]) + bb[8 * g + 2], __uint_as_float(v[8 * g + 3]) + bb[8 * g + 3]),
+                             pack_bf16(__uint_as_float(v[8 * g + 4]) + bb[8 * g + 4], __uint_as_float(v[8 * g + 5]) + bb[8 * g + 5]),
+                             pack_bf16(__uint_as_float(v[8 * g + 6]) + bb[8 * g + 6], __uint_as_float(v[8 * g + 7]) + bb[8 * g + 7]));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(LB_TMEM_COLS));
+}
 }  // namespace
 
 extern "C" size_t ffsr_lka_tail_weight_bytes(void) { return (size_t)LT_WBYTES; }
@@ -525,6 +765,22 @@ extern "C" int ffsr_lka_tail128_mod(const void* x, const void* a, int nimg, int 
   }
   const long tiles = (long)nimg * ((HW + 127) / 128);
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  static const bool v1 = getenv("FFSR_LKA_TAIL128_V1") != nullptr;
+  if (!v1) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(k_lka_tail128w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM);
+      cudaFuncSetAttribute(k_lka_tail128w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM);
+      attr = true;
+    }
+    if (erf_forced)
+      k_lka_tail128w<false><<<grid, LW_THREADS, LB_SMEM, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)a, nimg, HW, (const uint8_t*)wblob,
+                                                                    pblob, scale1, scale2, (__nv_bfloat16*)m32);
+    else
+      k_lka_tail128w<true><<<grid, LW_THREADS, LB_SMEM, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)a, nimg, HW, (const uint8_t*)wblob,
+                                                                   pblob, scale1, scale2, (__nv_bfloat16*)m32);
+    return ffsr_check_launch("lka_tail128_mod");
+  }
   if (erf_forced)
     k_lka_tail128<false><<<grid, LT_THREADS, LB_SMEM, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)a, nimg, HW, (const uint8_t*)wblob, pblob,
                                                                 scale1, scale2, (__nv_bfloat16*)m32);
