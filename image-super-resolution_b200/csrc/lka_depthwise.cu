@@ -269,7 +269,7 @@ static int lka_depthwise_impl(const void* x, int x_dtype, int N, int H, int W, i
   const dim3 rv(C / cx, ceil_div((long)W * nsh, ty), N);
 #define FFSR_DW_CHAIN(CT)                                                                                              \
   {                                                                                                                    \
-    if (x_dtype == 1) k_lka_dw5<bf, CT><<<g5, block, 0, stream>>>((const bf*)x, H, W, C, bn_k, bn_d, w5, tmp1);        \
+    if (x_dtype == 1) k_lka_dw5<bf, CT><<<g5, block, 0, stream>>>((const bf*)x, H, W, C, bn_k, bn_d, w5, tmp1); \
     else k_lka_dw5<float, CT><<<g5, block, 0, stream>>>((const float*)x, H, W, C, bn_k, bn_d, w5, tmp1);               \
     if (!roll) {                                                                                                       \
       k_lka_dw21<0, float, CT><<<gh, block, 0, stream>>>(tmp1, H, W, C, wh, tmp2);                                     \

@@ -250,6 +250,181 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lka_tail(const float* __restr
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(LT_TMEM_COLS));
 }
 
+// 512-thread version of k_lka_tail (warp w: TMEM lane group w % 4, channel quarter w / 4 = 16 of the 64 columns): half the
+// instructions per thread at four warps per scheduler, the next tile's rows prefetched into registers, and the second hidden
+// half written to the (dead) x1 planes so the two ffn2 MMA groups are issued without a wait in between.  Same products in the
+// same order as k_lka_tail: bit-identical output.
+__global__ void __launch_bounds__(512, 1) k_lka_tailw(const float* __restrict__ xin, const float* __restrict__ ain, long rows,
+                                                      const uint8_t* __restrict__ wblob, const float* __restrict__ pblob,
+                                                      const float* __restrict__ s1p, const float* __restrict__ s2p,
+                                                      float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8);
+  float* par = reinterpret_cast<float*>(smem + LT_S_PAR);
+  uint8_t* sW = smem + LT_S_W;
+  uint8_t* sA = smem + LT_S_A;
+  uint8_t* sH = smem + LT_S_H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane;
+  const int cq = warp >> 2;
+
+  for (int i = tid; i < LT_WBYTES / 16; i += 512) reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(wblob) + i);
+  for (int i = tid; i < LT_PF; i += 512) par[i] = __ldg(pblob + i);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(LT_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float s1 = s1p[0], s2 = s2p[0];
+  const float* b_pw = par;
+  const float* k1 = par + 64;
+  const float* d1 = par + 128;
+  const float* b0 = par + 192;
+  const float* b2 = par + 320;
+  const uint32_t w1_32 = smem_u32(sW), w0_32 = w1_32 + LT_W1, w2_32 = w0_32 + LT_W0, a32 = smem_u32(sA), h32 = smem_u32(sH);
+  const uint32_t id64 = idesc_bf16_m128(64), id128 = idesc_bf16_m128(128);
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t phase = 0;
+  const long tiles = (rows + 127) / 128;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // 16 values -> their split cells in planes kg = 2 cq, 2 cq + 1 of `dst`
+  auto put_split = [&](uint8_t* dst, const float* v16) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = v16[8 * g + i];
+      uint4 c1, c2, c3;
+      split8(v, c1, c2, c3);
+      uint8_t* cell = dst + (cq * 2 + g) * 2048 + row * 16;
+      *reinterpret_cast<uint4*>(cell) = c1;
+      *reinterpret_cast<uint4*>(cell + 8 * 2048) = c2;
+      *reinterpret_cast<uint4*>(cell + 16 * 2048) = c3;
+    }
+  };
+  float4 na[4], nx[4];
+  bool nlive = false;
+  if ((long)blockIdx.x < tiles) {
+    const long r = (long)blockIdx.x * 128 + row;
+    nlive = r < rows;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      na[g] = nlive ? __ldg(reinterpret_cast<const float4*>(ain + r * LT_C + cq * 16) + g) : z4;
+      nx[g] = nlive ? __ldg(reinterpret_cast<const float4*>(xin + r * LT_C + cq * 16) + g) : z4;
+    }
+  }
+  for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long r = tile * 128 + row;
+    const bool live = nlive;
+    float x[16];
+    {
+      float a16[16];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        a16[4 * g] = na[g].x; a16[4 * g + 1] = na[g].y; a16[4 * g + 2] = na[g].z; a16[4 * g + 3] = na[g].w;
+        x[4 * g] = nx[g].x; x[4 * g + 1] = nx[g].y; x[4 * g + 2] = nx[g].z; x[4 * g + 3] = nx[g].w;
+      }
+      put_split(sA, a16);
+    }
+    if (tile + gridDim.x < tiles) {
+      const long rn = (tile + gridDim.x) * 128 + row;
+      nlive = rn < rows;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        na[g] = nlive ? __ldg(reinterpret_cast<const float4*>(ain + rn * LT_C + cq * 16) + g) : z4;
+        nx[g] = nlive ? __ldg(reinterpret_cast<const float4*>(xin + rn * LT_C + cq * 16) + g) : z4;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      lt_gemm(tmem, a32, w1_32, 64, 8, 0, 4, id64, true);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)(cq * 16), v);
+      tmem_wait_ld(v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int ch = cq * 16 + i;
+        const float xr = x[i];
+        x[i] = xr + s1 * (fmaf(xr, k1[ch], d1[ch]) * sigmoid_acc(__uint_as_float(v[i]) + b_pw[ch]));
+      }
+    }
+    put_split(sA, x);                                // the a planes are dead: their MMAs completed
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      lt_gemm(tmem + 64, a32, w0_32, 128, 8, 0, 4, id128, true);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)(64 + hh * 64 + cq * 16), v);
+      tmem_wait_ld(v);
+      float y[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) y[i] = gelu_erf(__uint_as_float(v[i]) + b0[hh * 64 + cq * 16 + i]);
+      put_split(hh == 0 ? sH : sA, y);               // second half: the x1 planes are dead (stage 2 completed)
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        tc_fence_after();
+        lt_gemm(tmem, hh == 0 ? h32 : a32, w2_32, 64, 16, hh * 8, 4, id64, hh == 0);
+        if (hh == 1) umma_commit(bar);
+      }
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)(cq * 16), v);
+      tmem_wait_ld(v);
+      if (live) {
+        float4* op = reinterpret_cast<float4*>(out + r * LT_C + cq * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = q * 4 + i;
+            o[i] = fmaf(s2, __uint_as_float(v[j]) + b2[cq * 16 + j], x[j]);
+          }
+          op[q] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(LT_TMEM_COLS));
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // bf16 variant for Phase 4 (128-channel tokens, hidden 256, bf16 residual stream): the same tail plus the first modulation
 // layer (128 -> 32 per expert, the 1x1 conv that commutes with the bilinear upsampling), one kernel instead of four
@@ -741,6 +916,16 @@ extern "C" int ffsr_lka_tail64(const float* x, const float* a, long rows, const 
   }
   const long tiles = (rows + 127) / 128;
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  static const bool v1 = getenv("FFSR_LKA_TAIL64_V1") != nullptr;
+  if (!v1) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(k_lka_tailw, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
+      attr = true;
+    }
+    k_lka_tailw<<<grid, 512, LT_SMEM, stream>>>(x, a, rows, (const uint8_t*)wblob, pblob, scale1, scale2, out);
+    return ffsr_check_launch("lka_tail64");
+  }
   k_lka_tail<<<grid, LT_THREADS, LT_SMEM, stream>>>(x, a, rows, (const uint8_t*)wblob, pblob, scale1, scale2, out);
   return ffsr_check_launch("lka_tail64");
 }
