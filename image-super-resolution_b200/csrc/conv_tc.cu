@@ -59,6 +59,7 @@ constexpr int TC_EPI_WARP0 = 1 + TC_MMA_WARPS; // first epilogue warp
 constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS);
 constexpr int TC_TMEM_COLS = 512;             // whole TMEM: ring of 512/slot accumulators (1 CTA per SM)
 constexpr int TC_MAX_ACC = 12;
+constexpr int TC_MAX_ASLOTS = 4;              // geom 2: activation ring depth limit
 
 struct TcArgs {
   int N, H, W, Cin, Cout, taps, ks;
@@ -92,7 +93,9 @@ struct TcArgs {
   void* out2;        // optional bf16 pre-activation copy (same strides as out)
   int halves;        // 1: tile = 8x16 px (M=128); 2: tile = 16x16 px as two M=128 MMAs sharing every weight stage
   int acc_half;      // TMEM columns of one half accumulator (acc_slot = halves * acc_half)
-  int geom;          // 0: 8x16-px tile rows, one haloed A copy per dx;  1: 16x8-px tiles, ONE haloed copy per K chunk
+  int geom;          // 0: 8x16-px tile rows, one haloed A copy per dx;  1: 16x8-px tiles, ONE haloed copy per K chunk;
+                     // 2: streamed weights, 16x16-px tiles as two 16x8 halves: ONE haloed copy {64 ch, 18 px, 18 rows} per K chunk
+                     //    in its own ring + a ring of single-tap weight stages (see the kernel)
   int tile_h;        // output rows per tile (8 * halves, or 16 for geom 1)
   uint32_t a_step16; // geom 1: dy stride inside the haloed copy, in 16-byte units (10 px * 128 B)
   uint32_t a_desc_hi;// geom 1: A descriptor high word (SBO = haloed image-row pitch)
@@ -101,6 +104,8 @@ struct TcArgs {
                      //    tile are spread over the four groups.  See epilogue_loop.
   int lean;          // 1: lean_epilogue (bf16 inference outputs, bias staged in shared memory); see there
   int nmma;          // MMA-issuing warps (1, 2 or 3): warp 1+g issues the MMAs of tiles g, g+nmma, ... of this CTA
+  int a_slot;        // geom 2: bytes of one slot of the activation ring (haloed copy rounded up to 1 KB)
+  int na_slots;      // geom 2: slots of the activation ring (the weight ring has nstages slots of stage_bytes)
 };
 
 // ---------------------------------------------------------------------------- PTX wrappers
@@ -627,11 +632,12 @@ __device__ __forceinline__ void lean_epilogue(const TcArgs& a, uint64_t* tfull, 
     }
     const int n = ti.n;
     const int cb = ti.nb * a.nblk;                      // first output column of this cout block
-    const int x = ti.tx * tw + px;
+    const int x0 = (a.geom == 2 ? ti.tx * 16 : ti.tx * tw) + px;
     mbar_wait(&tfull[as], aph);
     tc_fence_after();
     for (int half = 0; half < halves; ++half) {
-      const int y = ti.ty * a.tile_h + half * TC_TH + py;
+      const int x = a.geom == 2 ? x0 + half * 8 : x0;   // geom 2: the halves are the left / right 8 pixels of 16 rows
+      const int y = ti.ty * a.tile_h + (a.geom == 2 ? 0 : half * TC_TH) + py;
       const bool inside = (y < a.H) && (x < a.W);
       const long long opix = (long long)n * a.out_sN + (long long)y * a.out_sY + (long long)x * a.out_sX + cb;
       long long r1pix = 0, r2pix = 0;
@@ -676,6 +682,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* tempty = bars + 2 * TC_MAX_STAGES + TC_MAX_ACC;    // [TC_MAX_ACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 2 * TC_MAX_ACC);
   uint64_t* bfull = bars + 2 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1;   // resident-weights barrier
+  uint64_t* afull = bfull + 1;                                       // geom 2: activation ring [TC_MAX_ASLOTS]
+  uint64_t* aempty = afull + TC_MAX_ASLOTS;
   float* sbias = reinterpret_cast<float*>(smem + TC_BIAS_OFF);       // lean epilogue: bias of every output column
   uint8_t* bres = smem + TC_SMEM_HDR;                                // resident weights (may be empty)
   uint8_t* stages = bres + a.bres_bytes;
@@ -688,6 +696,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < TC_MAX_ACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], a.epi_own ? 4 : TC_EPI_WARPS); }
     mbar_init(bfull, 1);
+    for (int i = 0; i < TC_MAX_ASLOTS; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
     fence_barrier_init();
   }
   if (a.lean && threadIdx.x >= 32 * TC_EPI_WARP0) {
@@ -715,6 +724,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       int cur_g = -1, cur_nb = -1, last_s = 0;
       uint32_t last_ph = 0;
       bool have_last = false;
+      int as_ = 0;                                   // geom 2: activation ring position
+      uint32_t aph_ = 0;
+      uint8_t* const wring = stages + a.na_slots * a.a_slot;
       TileIter ti;
       for (ti.init(a); ti.valid(a); ti.next(a)) {
         const int tx = ti.tx, ty = ti.ty, n = ti.n, nb = ti.nb;   // cout block varies slowest: resident weights change rarely
@@ -729,7 +741,26 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           cur_g = g;
           cur_nb = nb;
         }
-        if (a.geom) {
+        if (a.geom == 2) {
+          // Streamed weights with a deep pipeline: the 128->128 layers used 86 KB stages (one haloed copy per dx + the
+          // three dy taps of the weights), i.e. a ring of TWO -- every stage load was exposed behind ~1,500 cycles of
+          // MMAs (ncu: tensor pipe 59 % active).  Here the activations of a K chunk are ONE haloed copy
+          // {64 ch, 18 px, 18 rows} (41 KB instead of 3 x 36 KB) in their own ring, and the weights stream through a ring
+          // of single-tap 16 KB stages (8 deep = ~4,000 cycles of MMAs ahead).
+          for (int ch = 0; ch < a.nchunks; ++ch) {
+            mbar_wait(&aempty[as_], aph_ ^ 1);
+            mbar_expect_tx_e(&afull[as_], (uint32_t)a.a_bytes);
+            tma_load_4d(stages + as_ * a.a_slot, &tmA, &afull[as_], ch * 64, tx * 16 - pad, ty * 16 - pad, n);
+            if (++as_ == a.na_slots) { as_ = 0; aph_ ^= 1; }
+            for (int dxi = 0; dxi < 3; ++dxi)
+              for (int dyi = 0; dyi < 3; ++dyi) {
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx_e(&full[s], (uint32_t)a.b_bytes);
+                tma_load_5d(wring + s * a.stage_bytes, &tmB, &full[s], ch * 64, nb * a.nblk, dxi, dyi, g);
+                if (++s == a.nstages) { s = 0; ph ^= 1; }
+              }
+          }
+        } else if (a.geom) {
           // one row-haloed, column-haloed copy {64 ch, 10 px, 18 rows} per K chunk serves all nine taps
           for (int ch = 0; ch < a.nchunks; ++ch) {
             mbar_wait(&empty[s], ph ^ 1);
@@ -776,6 +807,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t b_step = (uint32_t)(a.nblk * 128) >> 4;
     const int last_chunk_it = a.geom ? a.nchunks - 1 : (a.nchunks - 1) * a.ks;   // stages of the last (possibly partial) K chunk
     const int skip = (nmma - 1) * kiters;
+    int g2_as = 0;                                  // geom 2: activation ring position
+    uint32_t g2_aph = 0;
     TileIter ti;
     ti.init(a);                                     // tile coordinates matter only for weight-set changes (nmma == 1)
     for (int q = 0; q < g; ++q) ti.next(a);
@@ -793,6 +826,44 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_wait(&tempty[as], aph ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * a.acc_slot);
+      if (a.geom == 2) {
+        // nmma == 1.  Per K chunk: wait for the haloed copy; per tap: wait for its weight stage, issue the K steps of both
+        // 16x8 halves (left half: pixels 0..7 of each row, right half: 8..15 = the same copy 8 pixels further on),
+        // release the weight stage; after the ninth tap release the copy.
+        const uint32_t wring_u32 = stages_u32 + (uint32_t)(a.na_slots * a.a_slot);
+        for (int ch = 0; ch < a.nchunks; ++ch) {
+          mbar_wait(&afull[g2_as], g2_aph);
+          tc_fence_after();
+          const uint32_t a_addr = stages_u32 + (uint32_t)(g2_as * a.a_slot);
+          const int ksteps = (ch == a.nchunks - 1) ? a.ksteps_last : 4;
+          for (int dxi = 0; dxi < 3; ++dxi)
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              mbar_wait(&full[s], ph);
+              tc_fence_after();
+              const uint32_t bl = desc_lo(wring_u32 + (uint32_t)(s * a.stage_bytes));
+              const uint32_t acc0 = (ch > 0 || dxi > 0 || dyi > 0) ? 1u : 0u;
+              for (int half = 0; half < 2; ++half) {
+                const uint32_t al = desc_lo(a_addr + (uint32_t)dyi * (a.a_step16 << 4) + 128u * (uint32_t)(dxi + 8 * half));
+                const uint32_t td = tmem_d + (uint32_t)(half * a.acc_half);
+                switch (ksteps) {
+                  case 4: umma_tap1c_k4(td, al, bl, idesc, acc0, a.a_desc_hi, TC_DESC_HI); break;
+                  case 3: umma_tap1c_k3(td, al, bl, idesc, acc0, a.a_desc_hi, TC_DESC_HI); break;
+                  case 2: umma_tap1c_k2(td, al, bl, idesc, acc0, a.a_desc_hi, TC_DESC_HI); break;
+                  default: umma_tap1c_k1(td, al, bl, idesc, acc0, a.a_desc_hi, TC_DESC_HI); break;
+                }
+              }
+              umma_commit(&empty[s]);
+              if (++s == a.nstages) { s = 0; ph ^= 1; }
+            }
+          umma_commit(&aempty[g2_as]);
+          if (++g2_as == a.na_slots) { g2_as = 0; g2_aph ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+        as += nmma;
+        if (as >= a.nacc) { as -= a.nacc; aph ^= 1; }
+        ti.next(a);
+        continue;
+      }
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
@@ -965,12 +1036,27 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
     if (p.ksize == 3 && halves == 1 && nch0 * p.ksize * bb + 3 * A1C_STAGE <= avail0 && p.H >= 8 && getenv("FFSR_TC_GEOM0") == nullptr)
       geom = 1;
   }
+  // Streamed-weight 3x3 layers served by the lean epilogue (bf16 inference outputs): dual-ring geometry, see the kernel
+  constexpr int A2_BYTES = 18 * 18 * 128, A2_SLOT = (A2_BYTES + 1023) / 1024 * 1024;
+  if (halves == 2 && geom == 0 && getenv("FFSR_TC_GEOM2_OFF") == nullptr && getenv("FFSR_TC_LEAN0") == nullptr) {
+    const bool mode_ok = p.epi == FFSR_EPI_PLAIN || (p.epi == FFSR_EPI_RESIDUAL && p.act == ACT_NONE);
+    const bool out_ok = p.out_dtype == FFSR_DT_BF16 && p.out2 == nullptr && p.groups == 1 && p.Cout % 8 == 0 && ((uintptr_t)p.out % 16) == 0 &&
+                        p.out_sX % 8 == 0 && p.out_sY % 8 == 0 && p.out_sN % 8 == 0 && cout_pad <= TC_BIAS_MAX && (nblk % 64) == 0;
+    bool res_ok = true;
+    if (p.epi == FFSR_EPI_RESIDUAL) {
+      const int r1q = p.r1_dtype == FFSR_DT_BF16 ? 8 : 4, r2q = p.r2_dtype == FFSR_DT_BF16 ? 8 : 4;
+      res_ok = p.r1 != nullptr && ((uintptr_t)p.r1 % 16) == 0 && p.r1_sX % r1q == 0 && p.r1_sY % r1q == 0 && p.r1_sN % r1q == 0 &&
+               (p.r2 == nullptr || (((uintptr_t)p.r2 % 16) == 0 && p.r2_sX % r2q == 0 && p.r2_sY % r2q == 0 && p.r2_sN % r2q == 0));
+    }
+    if (mode_ok && out_ok && res_ok && p.W >= 18 && p.H >= 18) geom = 2;
+  }
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
     cuuint64_t strides[3] = {(cuuint64_t)p.in_sX * 2, (cuuint64_t)p.in_sY * 2, (cuuint64_t)p.in_sN * 2};
     cuuint32_t box[4] = {64, TC_TW, (cuuint32_t)(TC_TH * halves + 2 * (p.ksize / 2)), 1};
-    if (geom) { box[1] = 10; box[2] = 18; }
+    if (geom == 1) { box[1] = 10; box[2] = 18; }
+    if (geom == 2) { box[1] = 18; box[2] = 18; }
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.in), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -982,7 +1068,7 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
     const cuuint64_t tap_bytes = (cuuint64_t)cin_pad * cout_pad * 2;
     cuuint64_t dims[5] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, (cuuint64_t)p.ksize, (cuuint64_t)p.ksize, (cuuint64_t)p.groups};
     cuuint64_t strides[4] = {(cuuint64_t)cin_pad * 2, tap_bytes, tap_bytes * p.ksize, tap_bytes * taps};
-    cuuint32_t box[5] = {64, (cuuint32_t)nblk, 1, (cuuint32_t)p.ksize, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)nblk, 1, (cuuint32_t)(geom == 2 ? 1 : p.ksize), 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<float*>(p.w), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1015,14 +1101,39 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   }
   a.nstages = (smem_avail - a.bres_bytes) / a.stage_bytes;
   if (a.nstages > TC_MAX_STAGES) a.nstages = TC_MAX_STAGES;
-  const int smem_bytes = 1024 + TC_SMEM_HDR + a.bres_bytes + a.nstages * a.stage_bytes;
+  int smem_bytes = 1024 + TC_SMEM_HDR + a.bres_bytes + a.nstages * a.stage_bytes;
+  a.a_slot = 0;
+  a.na_slots = 0;
+  if (geom == 2) {
+    a.tile_h = 16;
+    a.a_step16 = (18u * 128u) >> 4;
+    a.a_desc_hi = ((18u * 128u) >> 4) | (1u << 14) | (2u << 29);
+    a.a_bytes = A2_BYTES;
+    a.a_slot = A2_SLOT;
+    a.na_slots = 2;
+    a.b_bytes = nblk * 128;                                    // one tap of one K chunk
+    a.b_resident = 0;
+    a.bres_bytes = 0;
+    a.stage_bytes = a.b_bytes;
+    a.nstages = (smem_avail - a.na_slots * a.a_slot) / a.stage_bytes;
+    if (a.nstages > TC_MAX_STAGES) a.nstages = TC_MAX_STAGES;
+    if (const char* e = getenv("FFSR_TC_G2_ASLOTS")) {         // experiment: deeper activation ring, shallower weight ring
+      const int v = atoi(e);
+      if (v >= 1 && v <= TC_MAX_ASLOTS && (smem_avail - v * a.a_slot) / a.stage_bytes >= 2) {
+        a.na_slots = v;
+        a.nstages = (smem_avail - v * a.a_slot) / a.stage_bytes;
+        if (a.nstages > TC_MAX_STAGES) a.nstages = TC_MAX_STAGES;
+      }
+    }
+    smem_bytes = 1024 + TC_SMEM_HDR + a.na_slots * a.a_slot + a.nstages * a.stage_bytes;
+  }
   a.acc_half = nblk <= 32 ? 32 : (nblk <= 64 ? 64 : 128);
   a.acc_slot = a.acc_half * halves;
   a.nacc = TC_TMEM_COLS / a.acc_slot;
   if (a.nacc > TC_MAX_ACC) a.nacc = TC_MAX_ACC;
   a.groups = p.groups;
   a.epi_own = 0;
-  a.tiles_x = ceil_div(p.W, geom ? 8 : TC_TW);
+  a.tiles_x = ceil_div(p.W, geom == 1 ? 8 : TC_TW);
   a.tiles_y = ceil_div(p.H, a.tile_h);
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * p.N * a.n_nblocks;
   a.out = p.out; a.out_sN = p.out_sN; a.out_sY = p.out_sY; a.out_sX = p.out_sX;
@@ -1065,6 +1176,7 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
     if (a.lean) a.epi_own = (!own_off && own_lean) ? 1 : 0;
     if (a.lean && !a.epi_own && !split_lean) a.lean = 0;
   }
+  FFSR_REQUIRE(geom != 2 || a.lean, FFSR_ERR_ARG, "conv2d(tc): internal: dual-ring geometry without the lean epilogue");
   // several MMA-issuing warps for launches whose tiles are a few small MMAs (issue-bound, see the kernel): needs one weight
   // set for the whole launch and an accumulator ring that is a multiple of the warp count (3 warps: ring of 6)
   {
