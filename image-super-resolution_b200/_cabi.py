@@ -98,6 +98,8 @@ PROTOTYPES = {
     "ffsr_token_ffn_param_floats": (_SZ, []),
     "ffsr_token_ffn_chain": (_I, [_P, _L, _P, _P, _P, _P]),
     "ffsr_gate_finalize": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "ffsr_selector_blob_floats": (_SZ, []),
+    "ffsr_selector_fused": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "ffsr_conv2d": (_I, [C.POINTER(ConvParams), _P]),
     "ffsr_conv_params_size": (_SZ, []),
     "ffsr_modulate_hr": (_I, [C.POINTER(_P), _P, _P, _P, _I, _I, _I, _I, _P, _P, _LL, _I, _P]),

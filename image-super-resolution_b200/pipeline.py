@@ -136,6 +136,18 @@ def pack_token_ffn(co):
     return wb, pb
 
 
+def pack_selector(ds):
+    """DynamicExpertSelector difficulty_net / gate_net -> the fp32 blob of ffsr_selector_fused (layout: csrc/selector.cu):
+    [taps][Cin][Cout] weights + bias per layer, the single-channel and 4-channel heads padded to 4 floats of bias."""
+    f = lambda t: t.detach().float().reshape(-1)
+    z3 = torch.zeros(3, device=ds.gate_net[0].weight.device)
+    d, g = ds.difficulty_net, ds.gate_net
+    return torch.cat([_pack_conv(d[0].weight).reshape(-1), f(d[0].bias), _pack_conv(d[2].weight).reshape(-1), f(d[2].bias),
+                      _pack_conv(d[4].weight).reshape(-1), f(d[4].bias), z3,
+                      _pack_conv(g[0].weight).reshape(-1), f(g[0].bias), _pack_conv(g[2].weight).reshape(-1), f(g[2].bias),
+                      _pack_conv(g[4].weight).reshape(-1), f(g[4].bias)]).contiguous()
+
+
 def _pack_linear(w: torch.Tensor) -> torch.Tensor:
     """[out,in] -> [1][in][out]."""
     return w.detach().float().t().contiguous().unsqueeze(0)
@@ -165,6 +177,7 @@ class FusionEngine:
         self.lka_tail_tc = os.environ.get("FFSR_LKA_TAIL_FFMA") is None     # fp32 LKA tail (Phase 3) on tcgen05, 3-term bf16 split
         self.lka_tail128 = os.environ.get("FFSR_LKA_TAIL128_OFF") is None   # bf16 mode: Phase-4 LKA tail + modulation layer 0 fused
         self.token_chain = os.environ.get("FFSR_TOKEN_CHAIN_OFF") is None   # bf16 mode: Phase-4 token pipeline as two tile-resident kernels
+        self.selector_fused = os.environ.get("FFSR_SELECTOR_LAYERS") is None   # Phase 6 as one tile-resident fp32 kernel
         self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ weights
@@ -295,6 +308,10 @@ class FusionEngine:
             for i in (0, 2, 4):
                 conv(f"ds.d{i}", ds.difficulty_net[i])
                 conv(f"ds.g{i}", ds.gate_net[i])
+            shapes = [tuple(l.weight.shape) for l in (ds.difficulty_net[0], ds.difficulty_net[2], ds.difficulty_net[4],
+                                                        ds.gate_net[0], ds.gate_net[2], ds.gate_net[4])]
+            if shapes == [(32, 3, 3, 3), (32, 32, 3, 3), (1, 32, 3, 3), (32, 3, 3, 3), (32, 32, 3, 3), (4, 32, 1, 1)]:
+                w["ds.blob"] = pack_selector(ds)
             self._refine_idx = [i for i, l in enumerate(m.refine) if isinstance(l, torch.nn.Conv2d)]
             for i in self._refine_idx:
                 conv(f"rf.{i}", m.refine[i])
@@ -589,14 +606,18 @@ class FusionEngine:
         graw = self._buf("ds.raw", (B, H, W, 4), dev)
         gates = self._buf("gates", (B, 4, H, W), dev, fresh=fr)
         rv = nchw(routing)
-        self.conv(rv, B, H, W, 3, "ds.d0", 32, 3, nhwc(s_a), act=K.ACT_RELU)
-        self.conv(nhwc(s_a), B, H, W, 32, "ds.d2", 32, 3, nhwc(s_b), act=K.ACT_RELU)
-        self.conv(nhwc(s_b), B, H, W, 32, "ds.d4", 1, 3, nhwc(diff.view(B, H, W, 1)), act=K.ACT_SIGMOID)
-        self.conv(rv, B, H, W, 3, "ds.g0", 32, 3, nhwc(s_a), act=K.ACT_RELU)
-        self.conv(nhwc(s_a), B, H, W, 32, "ds.g2", 32, 3, nhwc(s_b), act=K.ACT_RELU)
-        self.conv(nhwc(s_b), B, H, W, 32, "ds.g4", 4, 1, nhwc(graw))
-        self._call(lib.ffsr_gate_finalize, graw.data_ptr(), diff.data_ptr(), B, H, W, pp("dynamic_selector.temperature"),
-                   gates.data_ptr(), S)
+        if self.selector_fused and "ds.blob" in w:
+            self._call(lib.ffsr_selector_fused, routing.data_ptr(), B, H, W, w["ds.blob"].data_ptr(), pp("dynamic_selector.temperature"),
+                       diff.data_ptr(), graw.data_ptr(), gates.data_ptr(), S)
+        else:
+          self.conv(rv, B, H, W, 3, "ds.d0", 32, 3, nhwc(s_a), act=K.ACT_RELU)
+          self.conv(nhwc(s_a), B, H, W, 32, "ds.d2", 32, 3, nhwc(s_b), act=K.ACT_RELU)
+          self.conv(nhwc(s_b), B, H, W, 32, "ds.d4", 1, 3, nhwc(diff.view(B, H, W, 1)), act=K.ACT_SIGMOID)
+          self.conv(rv, B, H, W, 3, "ds.g0", 32, 3, nhwc(s_a), act=K.ACT_RELU)
+          self.conv(nhwc(s_a), B, H, W, 32, "ds.g2", 32, 3, nhwc(s_b), act=K.ACT_RELU)
+          self.conv(nhwc(s_b), B, H, W, 32, "ds.g4", 4, 1, nhwc(graw))
+          self._call(lib.ffsr_gate_finalize, graw.data_ptr(), diff.data_ptr(), B, H, W, pp("dynamic_selector.temperature"),
+                     gates.data_ptr(), S)
 
         if overlap:
             routing_done = torch.cuda.Event()

@@ -140,6 +140,12 @@ size_t ffsr_token_ffn_param_floats(void);
 int ffsr_token_ffn_chain(const void* x, long rows, const void* wblob, const float* pblob, void* out, cudaStream_t stream);
 
 /* ---- Phase 6 gate normalisation  src/models/enhanced_fusion_v2.py:462-465 ---------------- */
+/* Phase 6 as ONE kernel (csrc/selector.cu): difficulty_net + gate_net + gate normalisation on shared-memory tiles, fp32.
+ * DynamicExpertSelector.forward, src/models/enhanced_fusion_v2.py:450-466.  routing [B][3][H][W] -> diff [B][1][H][W],
+ * graw [B][H][W][4] (gate_net logits), gates [B][4][H][W].  blob: isr_b200.pipeline.pack_selector. */
+size_t ffsr_selector_blob_floats(void);
+int ffsr_selector_fused(const float* routing, int B, int H, int W, const float* blob, const float* temperature, float* diff,
+                        float* graw, float* gates, cudaStream_t stream);
 int ffsr_gate_finalize(const float* raw, const float* diff, int B, int H, int W, const float* temperature,
                        float* gates, cudaStream_t stream);
 

@@ -96,11 +96,13 @@ def test_orchestration_dry_run(with_feats, want_inter, precision):
     # grouped align conv instead of four, each edge refiner (6 convs x 3 levels) as one ffsr_edge_refiner_chain launch and
     # the Phase-4 LKA tail + modulation layer 0 (4 convs) as one ffsr_lka_tail128_mod launch, and the Phase-4 token pipeline
     # (qkv, out, ffn0, ffn2 convs + two LayerNorms + the attention core) as ffsr_token_attn_chain + ffsr_token_ffn_chain
-    expect = (63 if with_feats else 51) - 3
+    # Phase 6 (six selector convs + the gate normalisation) is one ffsr_selector_fused launch in both modes
+    expect = (63 if with_feats else 51) - 3 - 6
     if precision == "bf16":
         expect -= 3 + 18 + 4 + 4
     assert calls.count("ffsr_conv2d") == expect, calls.count("ffsr_conv2d")
     assert calls.count("ffsr_lka_tail64") == 1
+    assert calls.count("ffsr_selector_fused") == 1 and "ffsr_gate_finalize" not in calls
     assert calls.count("ffsr_edge_refiner_chain") == (3 if precision == "bf16" else 0)
     assert calls.count("ffsr_lka_tail128_mod") == (1 if (precision == "bf16" and with_feats) else 0)
     chain = precision == "bf16" and with_feats
