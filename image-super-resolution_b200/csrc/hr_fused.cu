@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(128) k_spatial_gate(const T* __restrict__ x, l
                                                       const float* __restrict__ b1, const float* __restrict__ w2,
                                                       const float* __restrict__ b2, T* __restrict__ y) {
   constexpr int HID = C / 4;
-  __shared__ float sw1[HID][C];
+  __shared__ __align__(16) float sw1[HID][C];
   __shared__ float sb1[HID], sw2[HID];
   for (int i = threadIdx.x; i < HID * C; i += blockDim.x) (&sw1[0][0])[i] = w1[i];
   if (threadIdx.x < HID) { sb1[threadIdx.x] = b1[threadIdx.x]; sw2[threadIdx.x] = w2[threadIdx.x]; }
@@ -439,7 +439,10 @@ __global__ void __launch_bounds__(128) k_spatial_gate(const T* __restrict__ x, l
   for (int h = 0; h < HID; ++h) {
     float a = sb1[h];
 #pragma unroll
-    for (int c = 0; c < C; ++c) a = fmaf(sw1[h][c], v[c], a);
+    for (int c = 0; c < C; c += 4) {                 // broadcast 16-byte weight loads: one shared load per four FMAs
+      const float4 w4 = *reinterpret_cast<const float4*>(&sw1[h][c]);
+      a = fmaf(w4.x, v[c], a); a = fmaf(w4.y, v[c + 1], a); a = fmaf(w4.z, v[c + 2], a); a = fmaf(w4.w, v[c + 3], a);
+    }
     z = fmaf(sw2[h], gelu_sel<!std::is_same<T, float>::value>(a), z);
   }
   const float g = sigmoid_acc(z);
@@ -562,48 +565,58 @@ extern "C" int ffsr_blend_hr(const float* hier, long long hier_sX, const float* 
 // ------------------------------------------------------------------------------------------
 // Laplacian pyramid: down = avg_pool2(gauss5x5(x));  lap = x - bilinear(down)
 // ------------------------------------------------------------------------------------------
+// avg_pool2 o gauss5x5 is ONE 6x6 stride-2 kernel K6 = box2 * gauss5 (the same identity the backward kernel uses): 36 taps x 3
+// channels per output instead of 4 x 25 x 3, and with channels-last rows of >= 4 floats each tap is one 16-byte load
+// (the previous version: 108 predicated scalar loads + 300 FMAs per output, 0.63 TB/s).
+template <bool VEC>
 __global__ void __launch_bounds__(128) k_blur_pool(const float* __restrict__ x, long long x_sX, int H, int W,
                                                    const float* __restrict__ gauss25, float* __restrict__ down,
                                                    long long down_sX, __nv_bfloat16* __restrict__ down_lp,
                                                    long long down_lp_sX) {
-  __shared__ float sg[25];
-  if (threadIdx.x < 25) sg[threadIdx.x] = gauss25[threadIdx.x];
+  __shared__ float k6[6][6];
+  if (threadIdx.x < 36) {
+    const int a = threadIdx.x / 6, b = threadIdx.x % 6;
+    float acc = 0.f;
+    for (int da = 0; da < 2; ++da)
+      for (int db = 0; db < 2; ++db) {
+        const int ky = a - da, kx = b - db;
+        if (ky >= 0 && ky < 5 && kx >= 0 && kx < 5) acc += gauss25[ky * 5 + kx];
+      }
+    k6[a][b] = 0.25f * acc;
+  }
   __syncthreads();
   const int H2 = H / 2, W2 = W / 2;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y, n = blockIdx.z;
   if (j >= W2) return;
   const float* img = x + (long)n * H * W * x_sX;
-  float win[6][6][3];
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll
-  for (int a = 0; a < 6; ++a)
+  for (int a = 0; a < 6; ++a) {
+    const int yy = 2 * i + a - 2;
+    if (yy < 0 || yy >= H) continue;
+    const float* row = img + (long)yy * W * x_sX;
 #pragma unroll
     for (int bb = 0; bb < 6; ++bb) {
-      const int yy = 2 * i + a - 2, xx = 2 * j + bb - 2;
-      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-      const float* p = img + ((long)yy * W + xx) * x_sX;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) win[a][bb][c] = ok ? p[c] : 0.f;
-    }
-  float* o = down + (((long)n * H2 + i) * W2 + j) * down_sX;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float bl[2][2];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int bb = 0; bb < 2; ++bb) {
-        float acc = 0.f;
-#pragma unroll
-        for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 5; ++dx) acc = fmaf(sg[dy * 5 + dx], win[a + dy][bb + dx][c], acc);
-        bl[a][bb] = acc;
+      const int xx = 2 * j + bb - 2;
+      if (xx < 0 || xx >= W) continue;
+      const float kk = k6[a][bb];
+      if (VEC) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + (long)xx * x_sX));
+        o0 = fmaf(kk, v.x, o0); o1 = fmaf(kk, v.y, o1); o2 = fmaf(kk, v.z, o2);
+      } else {
+        const float* p = row + (long)xx * x_sX;
+        o0 = fmaf(kk, p[0], o0); o1 = fmaf(kk, p[1], o1); o2 = fmaf(kk, p[2], o2);
       }
-    o[c] = (((bl[0][0] + bl[0][1]) + bl[1][0]) + bl[1][1]) * 0.25f;
+    }
   }
-  if (down_sX > 3) o[3] = 0.f;
-  if (down_lp) store_vec4<__nv_bfloat16>(down_lp + (((long)n * H2 + i) * W2 + j) * down_lp_sX, o[0], o[1], o[2], 0.f);
+  float* o = down + (((long)n * H2 + i) * W2 + j) * down_sX;
+  if (VEC && down_sX == 4) *reinterpret_cast<float4*>(o) = make_float4(o0, o1, o2, 0.f);
+  else {
+    o[0] = o0; o[1] = o1; o[2] = o2;
+    if (down_sX > 3) o[3] = 0.f;
+  }
+  if (down_lp) store_vec4<__nv_bfloat16>(down_lp + (((long)n * H2 + i) * W2 + j) * down_lp_sX, o0, o1, o2, 0.f);
 }
 
 extern "C" int ffsr_blur_pool(const float* x, long long x_sX, int N, int H, int W, const float* gauss25, float* down,
@@ -613,7 +626,9 @@ extern "C" int ffsr_blur_pool(const float* x, long long x_sX, int N, int H, int 
   dim3 grid(ceil_div(W / 2, 128), H / 2, N);
   FFSR_REQUIRE(!down_lp || (((uintptr_t)down_lp % 8) == 0 && down_lp_sX % 4 == 0 && down_lp_sX >= 4), FFSR_ERR_ALIGN,
                "blur_pool: bf16 copy alignment");
-  k_blur_pool<<<grid, 128, 0, stream>>>(x, x_sX, H, W, gauss25, down, down_sX, (__nv_bfloat16*)down_lp, down_lp_sX);
+  const bool vec = x_sX % 4 == 0 && ((uintptr_t)x % 16) == 0 && (down_sX != 4 || ((uintptr_t)down % 16) == 0);
+  if (vec) k_blur_pool<true><<<grid, 128, 0, stream>>>(x, x_sX, H, W, gauss25, down, down_sX, (__nv_bfloat16*)down_lp, down_lp_sX);
+  else k_blur_pool<false><<<grid, 128, 0, stream>>>(x, x_sX, H, W, gauss25, down, down_sX, (__nv_bfloat16*)down_lp, down_lp_sX);
   return ffsr_check_launch("blur_pool");
 }
 
