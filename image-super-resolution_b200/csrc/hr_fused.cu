@@ -2,6 +2,7 @@
 // per pixel x 4-channel group, coalesced planar reads, channels-last vector writes).
 // Each kernel cites the reference op sequence it replaces in include/ffsr_b200.h.
 #include <type_traits>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/ffsr_b200.h"
 
@@ -391,6 +392,86 @@ __global__ void __launch_bounds__(256) k_resize_nhwc_bf16x8(const __nv_bfloat16*
   *reinterpret_cast<uint4*>(dst + (((long)n * H + Y) * W + X) * dst_sX + 8 * c8) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// ------------------------------------------------------------------------------------------
+// Bilinear upsampling by an INTEGER factor F (2 or 4; align_corners = False), bf16 channels-last, optionally of
+// o * attn (edge refiners) scaled by the softmax level weight.  A thread owns one SOURCE cell and 8 channels: it loads the
+// 3x3 clamped neighbourhood once (9 x 16 bytes) and writes the F x F output pixels of the cell (F = 4: 0.56 loads per output
+// instead of 4, and the taps are compile-time constants).  With scale = 1/F the reference's tap arithmetic
+// src = (dst + 0.5) / F - 0.5 is exact in fp32, so the weights and the association ty.w0*(tx.w0*a + tx.w1*b) + ty.w1*(...)
+// below are those of bilin_tap / k_resize_nhwc_bf16x8 / k_edge_attn_up_bf16x8.
+// ------------------------------------------------------------------------------------------
+template <int F, bool ATTN>
+__global__ void __launch_bounds__(256) k_upsample_int(const __nv_bfloat16* __restrict__ src, const float* __restrict__ attn, int h, int w,
+                                                      int C8, long long src_sX, const float* __restrict__ level_w, int level,
+                                                      __nv_bfloat16* __restrict__ dst, long long dst_sX) {
+  __shared__ float s_lw;
+  if (ATTN) {
+    if (threadIdx.x == 0) {
+      const float l0 = level_w[0], l1 = level_w[1], l2 = level_w[2];
+      const float m = fmaxf(l0, fmaxf(l1, l2));
+      const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
+      s_lw = (level == 0 ? e0 : (level == 1 ? e1 : e2)) / ((e0 + e1) + e2);
+    }
+    __syncthreads();
+  }
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;       // over w * C8
+  const int j = t / C8, c8 = t - j * C8;
+  const int i = blockIdx.y, n = blockIdx.z;
+  if (j >= w) return;
+  const int ys[3] = {max(i - 1, 0), i, min(i + 1, h - 1)};
+  const int xs[3] = {max(j - 1, 0), j, min(j + 1, w - 1)};
+  const __nv_bfloat16* sb = src + (long)n * h * w * src_sX + 8 * c8;
+  float v[3][3][8];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const long q = (long)ys[a] * w + xs[b];
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(sb + q * src_sX));
+      const float am = ATTN ? __ldg(attn + (long)n * h * w + q) : 1.0f;
+      const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float lo = __uint_as_float(wv[k] << 16), hi = __uint_as_float(wv[k] & 0xffff0000u);
+        v[a][b][2 * k] = ATTN ? lo * am : lo;
+        v[a][b][2 * k + 1] = ATTN ? hi * am : hi;
+      }
+    }
+  const float lw = ATTN ? s_lw : 1.0f;
+  const int H = F * h, W = F * w;
+  __nv_bfloat16* db = dst + (((long)n * H + (long)F * i) * W + (long)F * j) * dst_sX + 8 * c8;
+#pragma unroll
+  for (int b = 0; b < F; ++b) {
+    // horizontal taps of output column F j + b: delta = (b + 0.5) / F - 0.5
+    const float dx = ((float)b + 0.5f) / (float)F - 0.5f;
+    const int cA = dx < 0.f ? 0 : 1, cB = cA + 1;
+    float wx1 = dx < 0.f ? 1.0f + dx : dx, wx0 = 1.0f - wx1;
+    if (dx < 0.f && j == 0) { wx0 = 1.0f; wx1 = 0.0f; }   // src clamped to 0: (i0, w1) = (0, 0)
+    float hx[3][8];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hx[a][k] = wx0 * v[a][cA][k] + wx1 * v[a][cB][k];
+#pragma unroll
+    for (int a = 0; a < F; ++a) {
+      const float dy = ((float)a + 0.5f) / (float)F - 0.5f;
+      const int rA = dy < 0.f ? 0 : 1, rB = rA + 1;
+      float wy1 = dy < 0.f ? 1.0f + dy : dy, wy0 = 1.0f - wy1;
+      if (dy < 0.f && i == 0) { wy0 = 1.0f; wy1 = 0.0f; }
+      uint32_t ow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float r0 = wy0 * hx[rA][2 * k] + wy1 * hx[rB][2 * k];
+        float r1 = wy0 * hx[rA][2 * k + 1] + wy1 * hx[rB][2 * k + 1];
+        if (ATTN) { r0 *= lw; r1 *= lw; }
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(r0, r1);
+        ow[k] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+      *reinterpret_cast<uint4*>(db + ((long)a * W + b) * dst_sX) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+}
+
 extern "C" int ffsr_resize_nhwc(const void* src, int N, int h, int w, int C, long long src_sX, void* dst, int H, int W,
                                 long long dst_sX, int dtype, cudaStream_t stream) {
   FFSR_REQUIRE(src && dst, FFSR_ERR_ARG, "resize_nhwc: null pointer");
@@ -398,6 +479,16 @@ extern "C" int ffsr_resize_nhwc(const void* src, int N, int h, int w, int C, lon
   const int esz = dtype == FFSR_DT_BF16 ? 2 : 4;
   FFSR_REQUIRE(((uintptr_t)src % (4 * esz)) == 0 && ((uintptr_t)dst % (4 * esz)) == 0 && src_sX % 4 == 0 && dst_sX % 4 == 0,
                FFSR_ERR_ALIGN, "resize_nhwc: vector alignment");
+  static const bool up_v1 = getenv("FFSR_UPSAMPLE_V1") != nullptr;
+  if (dtype == FFSR_DT_BF16 && C % 8 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0 && src_sX % 8 == 0 &&
+      dst_sX % 8 == 0 && h <= 65535 && N <= 65535 && !up_v1 && ((H == 2 * h && W == 2 * w) || (H == 4 * h && W == 4 * w))) {
+    dim3 grid(ceil_div((long)w * (C / 8), 256), h, N);
+    if (H == 2 * h)
+      k_upsample_int<2, false><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, nullptr, h, w, C / 8, src_sX, nullptr, 0, (__nv_bfloat16*)dst, dst_sX);
+    else
+      k_upsample_int<4, false><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, nullptr, h, w, C / 8, src_sX, nullptr, 0, (__nv_bfloat16*)dst, dst_sX);
+    return ffsr_check_launch("resize_nhwc");
+  }
   if (dtype == FFSR_DT_BF16 && C % 8 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0 && src_sX % 8 == 0 &&
       dst_sX % 8 == 0 && H <= 65535 && N <= 65535) {
     dim3 grid(ceil_div((long)W * (C / 8), 256), H, N);
@@ -450,12 +541,118 @@ __global__ void __launch_bounds__(128) k_spatial_gate(const T* __restrict__ x, l
   for (int c = 0; c < C; c += 4) store_vec4<T>(y + p * C + c, v[c] * g, v[c + 1] * g, v[c + 2] * g, v[c + 3] * g);
 }
 
+// bf16 rows, TPP = C / CH lanes per pixel with CH channels each, the lane's slice of W1 (HID x CH = 64 floats) in REGISTERS
+// for the whole grid-stride loop.  ncu of the one-thread-per-pixel kernel above: 65 % of the issue cycles without an eligible warp,
+// short-scoreboard stalls on the 64 shared-memory weight loads per pixel (weights of all C channels cannot live in one thread's
+// registers).  The HID partial sums are combined by a transposing butterfly: at each of the log2(TPP) steps a lane hands half of
+// its values to its partner, so it ends with HID / TPP complete hidden units (HID - HID / TPP shuffles in total instead of
+// HID log2(TPP)), applies GELU and the second layer to those, and a last xor-reduction sums the gate logit.
+template <int C, int CH>
+__global__ void __launch_bounds__(256) k_spatial_gate_rows(const __nv_bfloat16* __restrict__ x, long pixels, const float* __restrict__ w1,
+                                                           const float* __restrict__ b1, const float* __restrict__ w2,
+                                                           const float* __restrict__ b2, __nv_bfloat16* __restrict__ y) {
+  constexpr int HID = C / 4, TPP = C / CH, OWN = HID / TPP;
+  static_assert(OWN >= 1 && (TPP & (TPP - 1)) == 0, "lanes per pixel must be a power of two not above the hidden width");
+  const int part = threadIdx.x % TPP;
+  float w[HID][CH];
+#pragma unroll
+  for (int h = 0; h < HID; ++h)
+#pragma unroll
+    for (int k = 0; k < CH; ++k) w[h][k] = w1[h * C + part * CH + k];
+  int base = 0;
+  {
+    int half = HID / 2;
+#pragma unroll
+    for (int o = TPP / 2; o >= 1; o >>= 1, half >>= 1) base += (part & o) ? half : 0;
+  }
+  float sb[OWN], sw[OWN];
+#pragma unroll
+  for (int k = 0; k < OWN; ++k) { sb[k] = b1[base + k]; sw[k] = w2[base + k]; }
+  const float bias2 = b2[0];
+  const long stride = (long)gridDim.x * (256 / TPP);
+  const long rounds = (pixels + stride - 1) / stride;
+  long p = (long)blockIdx.x * (256 / TPP) + threadIdx.x / TPP;
+  // the rows of the next TWO rounds are loaded ahead (x is not __restrict__-aliased with y rows of later rounds: a row is read
+  // before any lane writes it, and only its own lanes write it)
+  auto ld = [&](long q) -> uint4 {
+    if (q >= pixels) return make_uint4(0u, 0u, 0u, 0u);
+    if (CH == 8) return *reinterpret_cast<const uint4*>(x + q * C + part * 8);
+    const uint2 t = *reinterpret_cast<const uint2*>(x + q * C + part * 4);
+    return make_uint4(t.x, t.y, 0u, 0u);
+  };
+  uint4 n0 = ld(p), n1 = ld(p + stride);
+  for (long it = 0; it < rounds; ++it, p += stride) {
+    const bool live = p < pixels;
+    const uint4 u = n0;
+    n0 = n1;
+    n1 = ld(p + 2 * stride);
+    float v[CH];
+    {
+      const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < CH / 2; ++k) { v[2 * k] = __uint_as_float(wv[k] << 16); v[2 * k + 1] = __uint_as_float(wv[k] & 0xffff0000u); }
+    }
+    float a[HID];
+#pragma unroll
+    for (int h = 0; h < HID; ++h) {
+      float t = w[h][0] * v[0];
+#pragma unroll
+      for (int k = 1; k < CH; ++k) t = fmaf(w[h][k], v[k], t);
+      a[h] = t;
+    }
+    {
+      int half = HID / 2;
+#pragma unroll
+      for (int o = TPP / 2; o >= 1; o >>= 1, half >>= 1) {
+        const bool up = (part & o) != 0;
+#pragma unroll
+        for (int k = 0; k < HID / 2; ++k)
+          if (k < half) {
+            const float mine = up ? a[half + k] : a[k], other = up ? a[k] : a[half + k];
+            a[k] = mine + __shfl_xor_sync(0xffffffffu, other, o);
+          }
+      }
+    }
+    float z = 0.f;
+#pragma unroll
+    for (int k = 0; k < OWN; ++k) z = fmaf(sw[k], gelu_tanh(a[k] + sb[k]), z);
+#pragma unroll
+    for (int o = TPP / 2; o >= 1; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    const float g = sigmoid_acc(z + bias2);
+    if (live) {
+      uint32_t ow[CH / 2];
+#pragma unroll
+      for (int k = 0; k < CH / 2; ++k) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * k] * g, v[2 * k + 1] * g);
+        ow[k] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+      if (CH == 8) *reinterpret_cast<uint4*>(y + p * C + part * 8) = make_uint4(ow[0], ow[1], ow[CH == 8 ? 2 : 0], ow[CH == 8 ? 3 : 0]);
+      else *reinterpret_cast<uint2*>(y + p * C + part * 4) = make_uint2(ow[0], ow[1]);
+    }
+  }
+}
+
 extern "C" int ffsr_spatial_gate(const void* x, long pixels, int C, const float* w1, const float* b1, const float* w2,
                                  const float* b2, void* y, int dtype, cudaStream_t stream) {
   FFSR_REQUIRE(x && y && w1 && b1 && w2 && b2, FFSR_ERR_ARG, "spatial_gate: null pointer");
   FFSR_REQUIRE(C == 64 || C == 32, FFSR_ERR_ARG, "spatial_gate: C must be 32 or 64");
   FFSR_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0, FFSR_ERR_ALIGN, "spatial_gate: 16B alignment");
   const int grid = ceil_div(pixels, 128);
+  static const bool v1 = getenv("FFSR_SPATIAL_GATE_V1") != nullptr;
+  if (dtype == FFSR_DT_BF16 && !v1) {
+    static int num_sms = 0;
+    if (!num_sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tpp = C == 64 ? 16 : 4;
+    const long need = (pixels * tpp + 255) / 256;
+    const int g2 = (int)(need < 8L * num_sms ? need : 8L * num_sms);
+    if (C == 64) k_spatial_gate_rows<64, 4><<<g2, 256, 0, stream>>>((const __nv_bfloat16*)x, pixels, w1, b1, w2, b2, (__nv_bfloat16*)y);
+    else k_spatial_gate_rows<32, 8><<<g2, 256, 0, stream>>>((const __nv_bfloat16*)x, pixels, w1, b1, w2, b2, (__nv_bfloat16*)y);
+    return ffsr_check_launch("spatial_gate");
+  }
   if (dtype == FFSR_DT_BF16) {
     if (C == 64) k_spatial_gate<__nv_bfloat16, 64><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)x, pixels, w1, b1, w2, b2, (__nv_bfloat16*)y);
     else k_spatial_gate<__nv_bfloat16, 32><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)x, pixels, w1, b1, w2, b2, (__nv_bfloat16*)y);
@@ -831,6 +1028,16 @@ extern "C" int ffsr_edge_attn_upsample(const void* o, int o_dtype, const float* 
                "edge_attn_upsample: alignment");
   const long total = (long)N * H * W * (C / 4);
   FFSR_REQUIRE(o_dtype == FFSR_DT_F32 || dtype == FFSR_DT_BF16, FFSR_ERR_ARG, "edge_attn_upsample: bf16 input needs bf16 output");
+  static const bool up_v1 = getenv("FFSR_UPSAMPLE_V1") != nullptr;
+  if (o_dtype == FFSR_DT_BF16 && C % 8 == 0 && ((uintptr_t)dst % 16) == 0 && dst_sX % 8 == 0 && h <= 65535 && N <= 65535 && !up_v1 &&
+      ((H == 2 * h && W == 2 * w) || (H == 4 * h && W == 4 * w))) {
+    dim3 grid(ceil_div((long)w * (C / 8), 256), h, N);
+    if (H == 2 * h)
+      k_upsample_int<2, true><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)o, attn, h, w, C / 8, C, level_w, level, (__nv_bfloat16*)dst, dst_sX);
+    else
+      k_upsample_int<4, true><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)o, attn, h, w, C / 8, C, level_w, level, (__nv_bfloat16*)dst, dst_sX);
+    return ffsr_check_launch("edge_attn_upsample");
+  }
   if (o_dtype == FFSR_DT_BF16 && C % 8 == 0 && ((uintptr_t)dst % 16) == 0 && dst_sX % 8 == 0 && H <= 65535 && N <= 65535) {
     dim3 grid(ceil_div((long)W * (C / 8), 256), H, N);
     k_edge_attn_up_bf16x8<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)o, attn, h, w, C / 8, level_w, level,
