@@ -91,6 +91,8 @@ PROTOTYPES = {
     "ffsr_layernorm128_bf16": (_I, [_P, _L, _P, _P, _P, _P]),
     "ffsr_lka_depthwise_in": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "ffsr_token_attention": (_I, [_P, _I, _I, _L, _I, _P, _I, _P]),
+    "ffsr_align_tokens_weight_bytes": (_SZ, []),
+    "ffsr_align_tokens": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "ffsr_token_attn_weight_bytes": (_SZ, []),
     "ffsr_token_attn_param_floats": (_SZ, []),
     "ffsr_token_attn_chain": (_I, [_P, _I, _I, _P, _P, _P, _P]),

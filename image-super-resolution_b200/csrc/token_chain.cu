@@ -449,6 +449,136 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_token_ffn(const __nv_bfloat16
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_align_tokens: the four expert feature maps (NCHW fp32 as they come out of the cache, 180 / 180 / 64 / 180 channels) ->
+// aligned bf16 tokens [B][4][HW][128] = align_layers[e](feat_e)  (1x1 conv + bias, large_kernel_attention.py:344-358), in ONE
+// kernel instead of four NCHW -> NHWC bf16 conversions (0.21 ms) + a grouped tcgen05 1x1 conv (0.11 ms).  A tile is 128 pixels
+// of one expert: lanes run along the pixels (coalesced 128-byte reads of a channel row), a thread gathers 8 channels of its
+// pixel and stores them as one 16-byte cell of the K-major operand planes, so the layout change costs no extra pass.  The
+// expert's weights (48 KB, K padded to 192) stay in shared memory; the next tile's values are loaded into registers before
+// the current tile's epilogue, and its MMAs (<= 12 K steps) run under the loads of the tile after.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int AL_KG = 24;                         // 8-channel groups of the padded K = 192
+constexpr int AL_W = AL_KG * 128 * 16;            // 49,152 B of one expert  [kg 24][n 128][8]
+constexpr int AL_S_BIAS = 64;                     // fp32 [4][128]
+constexpr int AL_S_W = 4096;
+constexpr int AL_S_A = AL_S_W + AL_W;
+constexpr int AL_SMEM = AL_S_A + AL_KG * TK_PLANE;   // 102,400 B
+constexpr int AL_THREADS = 256;                   // two CTAs per SM (2 x 100 KB of shared memory, 2 x 128 TMEM columns, 128 registers)
+constexpr int AL_CPT = AL_KG / 2;                 // cells per thread: kg = slot, slot + 2, ...
+
+struct AlignArgs {
+  const float* feat[4];
+  int C[4];
+};
+
+__global__ void __launch_bounds__(AL_THREADS, 2) k_align_tokens(const AlignArgs fa, int B, int HW, const uint8_t* __restrict__ wblob,
+                                                                const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8);
+  float* sb = reinterpret_cast<float*>(smem + AL_S_BIAS);
+  uint8_t* sW = smem + AL_S_W;
+  uint8_t* sA = smem + AL_S_A;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int px = tid & 127, slot = tid >> 7;        // load role: pixel of the tile, first 8-channel group
+  const int row = (warp & 3) * 32 + lane, ch = warp >> 2;   // epilogue role: TMEM lane, 64-column half
+
+  for (int i = tid; i < 512; i += AL_THREADS) sb[i] = __ldg(bias + i);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t w32 = smem_u32(sW), a32 = smem_u32(sA);
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t hi = desc_hi(128), id128 = idesc_bf16_m128(128);
+  const int tpi = (HW + 127) / 128;
+  const long per_e = (long)B * tpi, tiles = 4 * per_e;   // expert-major tile order: a CTA changes weights at most 4 times
+
+  // this thread's 8-channel cells of a tile, packed to bf16 (zero beyond the expert's channels and beyond the image)
+  auto load_cells = [&](long tile, uint4 (&c)[AL_CPT]) {
+    const int e = (int)(tile / per_e);
+    const long r = tile - (long)e * per_e;
+    const int b = (int)(r / tpi), p = (int)(r - (long)b * tpi) * 128 + px;
+    const int Ce = fa.C[e];
+    const float* f = fa.feat[e] + (long)b * Ce * HW + p;
+    const bool in = p < HW;
+#pragma unroll
+    for (int q = 0; q < AL_CPT; ++q) {
+      const int c0 = (slot + 2 * q) * 8;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (in && c0 + k < Ce) ? __ldg(f + (long)(c0 + k) * HW) : 0.f;
+      c[q] = pack8(v);
+    }
+  };
+  uint4 nc[AL_CPT];
+  if ((long)blockIdx.x < tiles) load_cells(blockIdx.x, nc);
+  uint32_t phase = 0;
+  int cur_e = -1;
+  for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int e = (int)(tile / per_e);
+    if (e != cur_e) {                                // the previous tile's MMAs completed (waited for below)
+      for (int i = tid; i < AL_W / 16; i += AL_THREADS) reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(wblob + (long)e * AL_W) + i);
+      cur_e = e;
+    }
+#pragma unroll
+    for (int q = 0; q < AL_CPT; ++q) *reinterpret_cast<uint4*>(sA + (slot + 2 * q) * TK_PLANE + px * 16) = nc[q];
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      const int groups = (fa.C[e] + 63) / 64;        // K steps of 16 in groups of four
+      for (int g = 0; g < groups; ++g)
+        umma_taps_1x4(tmem, desc_lo(a32 + (uint32_t)(g * 8) * TK_PLANE, TK_PLANE), desc_lo(w32 + (uint32_t)(g * 8) * 128u * 16u, 128u * 16u), id128,
+                      g == 0 ? 0u : 1u, hi, hi, (2u * TK_PLANE) >> 4, 2u * 128u, 0u);
+      umma_commit(bar);
+    }
+    if (tile + gridDim.x < tiles) load_cells(tile + gridDim.x, nc);   // in flight during the MMAs and the epilogue
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      const long r = tile - (long)e * per_e;
+      const int b = (int)(r / tpi), p = (int)(r - (long)b * tpi) * 128 + row;
+      uint4* op = reinterpret_cast<uint4*>(out + (((long)b * 4 + e) * HW + (p < HW ? p : 0)) * 128 + ch * 64);
+      const float* bb = sb + e * 128 + ch * 64;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t v0[16], v1[16];
+        tmem_ld16(trow + (uint32_t)(ch * 64 + c2 * 32), v0);
+        tmem_ld16(trow + (uint32_t)(ch * 64 + c2 * 32 + 16), v1);
+        tmem_wait_ld(v0);
+        tmem_wait_ld(v1);
+        if (p < HW) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t* vv = g < 2 ? v0 + 8 * g : v1 + 8 * (g - 2);
+            float o8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o8[k] = __uint_as_float(vv[k]) + bb[c2 * 32 + 8 * g + k];
+            op[c2 * 4 + g] = pack8(o8);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                 // accumulator read, planes free
+    tc_fence_after();
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
 int sm_count() {
   static int n = 0;
   if (!n) {
@@ -500,4 +630,28 @@ extern "C" int ffsr_token_ffn_chain(const void* x, long rows, const void* wblob,
   else
     k_token_ffn<true><<<grid, TK_THREADS, TF_SMEM, stream>>>((const __nv_bfloat16*)x, rows, (const uint8_t*)wblob, pblob, (__nv_bfloat16*)out);
   return ffsr_check_launch("token_ffn_chain");
+}
+
+extern "C" size_t ffsr_align_tokens_weight_bytes(void) { return (size_t)(4 * AL_W); }
+
+// feat[e]: fp32 NCHW [B][C[e]][HW] of expert e (C[e] <= 192); wblob / bias: pipeline.pack_align_tokens; out: bf16 [B][4][HW][128]
+extern "C" int ffsr_align_tokens(const float* const* feat, const int* C, int B, int HW, const void* wblob, const float* bias, void* out,
+                                 cudaStream_t stream) {
+  FFSR_REQUIRE(feat && C && wblob && bias && out && B > 0 && HW > 0, FFSR_ERR_ARG, "align_tokens: bad argument");
+  AlignArgs fa;
+  for (int e = 0; e < 4; ++e) {
+    FFSR_REQUIRE(feat[e] && C[e] > 0 && C[e] <= AL_KG * 8, FFSR_ERR_ARG, "align_tokens: expert %d: null feature map or more than 192 channels", e);
+    fa.feat[e] = feat[e];
+    fa.C[e] = C[e];
+  }
+  FFSR_REQUIRE(((uintptr_t)out % 16) == 0 && ((uintptr_t)wblob % 16) == 0, FFSR_ERR_ALIGN, "align_tokens: 16-byte alignment required");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_align_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
+    attr = true;
+  }
+  const long tiles = 4L * B * ((HW + 127) / 128);
+  const int grid = (int)(tiles < 2L * sm_count() ? tiles : 2L * sm_count());
+  k_align_tokens<<<grid, AL_THREADS, AL_SMEM, stream>>>(fa, B, HW, (const uint8_t*)wblob, bias, (__nv_bfloat16*)out);
+  return ffsr_check_launch("align_tokens");
 }

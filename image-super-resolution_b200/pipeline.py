@@ -108,6 +108,18 @@ def _split3_planes(w2d: torch.Tensor) -> torch.Tensor:
     return torch.stack([w1, w2, w3]).view(3, n, k // 8, 8).permute(0, 2, 1, 3).contiguous()
 
 
+def pack_align_tokens(co):
+    """align_layers -> (bf16 weight blob [4][kg 24][n 128][8] with K zero-padded to 192, fp32 bias [4][128]) of ffsr_align_tokens."""
+    ws, bs = [], []
+    for n in EXPERT_ORDER:
+        l = co.align_layers[n]
+        w2 = torch.zeros(128, 192, device=l.weight.device)
+        w2[:, :l.weight.shape[1]] = l.weight.detach().float().reshape(128, -1)
+        ws.append(_planes_bf16(w2).reshape(-1))
+        bs.append(l.bias.detach().float())
+    return torch.cat(ws).contiguous(), torch.stack(bs).contiguous()
+
+
 def pack_token_attn(co):
     """CollaborativeFeatureLearning norm1 + cross_attn -> (bf16 weight blob, fp32 parameter blob) of ffsr_token_attn_chain
     (layout: csrc/token_chain.cu).  LayerNorm folded into in_proj: g = gamma o W_in, colsum of the bf16-ROUNDED g (what the
@@ -178,6 +190,7 @@ class FusionEngine:
         self.lka_tail128 = os.environ.get("FFSR_LKA_TAIL128_OFF") is None   # bf16 mode: Phase-4 LKA tail + modulation layer 0 fused
         self.token_chain = os.environ.get("FFSR_TOKEN_CHAIN_OFF") is None   # bf16 mode: Phase-4 token pipeline as two tile-resident kernels
         self.selector_fused = os.environ.get("FFSR_SELECTOR_LAYERS") is None   # Phase 6 as one tile-resident fp32 kernel
+        self.align_fused = os.environ.get("FFSR_ALIGN_LAYERS") is None   # bf16 mode: NCHW features -> aligned tokens in one kernel
         self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ weights
@@ -270,6 +283,8 @@ class FusionEngine:
             w["co.f0.b"] = co.ffn[0].bias.detach().float().contiguous()
             w["co.f2"] = _pack_linear(co.ffn[2].weight)
             w["co.f2.b"] = co.ffn[2].bias.detach().float().contiguous()
+            if all(co.align_layers[n].weight.shape[0] == 128 and co.align_layers[n].weight.shape[1] <= 192 for n in EXPERT_ORDER):
+                w["co.align_w"], w["co.align_b"] = pack_align_tokens(co)
             if (co.cross_attn.embed_dim, co.cross_attn.num_heads) == (128, 8) and tuple(co.ffn[0].weight.shape) == (256, 128):
                 w["co.attn_w"], w["co.attn_p"] = pack_token_attn(co)
                 w["co.ffn_w"], w["co.ffn_p"] = pack_token_ffn(co)
@@ -655,7 +670,14 @@ class FusionEngine:
             fast_align = lp and len(have) == 4 and all(feats[n].shape[1] == cin_exp[n] for n in EXPERT_ORDER)
             rdt = torch.bfloat16 if (fast_align and self.p4_bf16_stream) else f32
             tokens = self._buf("co.tok", (B, 4, Hq, Wq, 128), dev, dtype=rdt, zero=True)
-            if fast_align:
+            if fast_align and self.align_fused and rdt == torch.bfloat16 and "co.align_w" in w:
+                # NCHW fp32 features -> aligned bf16 tokens in one tile-resident kernel (csrc/token_chain.cu, k_align_tokens)
+                fl = [feats[n].detach().to(f32).contiguous() for n in EXPERT_ORDER]
+                fptr = (C.c_void_p * 4)(*[t.data_ptr() for t in fl])
+                cnum = (C.c_int * 4)(*[cin_exp[n] for n in EXPERT_ORDER])
+                self._call(lib.ffsr_align_tokens, fptr, cnum, B, Hq * Wq, w["co.align_w"].data_ptr(), w["co.align_b"].data_ptr(),
+                           tokens.data_ptr(), S)
+            elif fast_align:
                 # bf16 mode: NCHW fp32 features -> one bf16 channels-last buffer, then ONE grouped tcgen05 1x1 conv
                 cmax = max(cin_exp.values())
                 cs = (cmax + 7) // 8 * 8

@@ -132,6 +132,12 @@ int ffsr_token_attention(const void* qkv, int B, int T, long HW, int E, void* ct
  *                          (large_kernel_attention.py:389-391); x / out bf16 [B][4][HW][128], out may alias x
  *   ffsr_token_ffn_chain : out = x + ffn2(GELU(ffn0(LN2(x))))  (:392); x / out bf16 [rows][128]
  * Weight / parameter blobs in the kernels' shared-memory layout: isr_b200.pipeline.pack_token_attn / pack_token_ffn. */
+/* The four expert feature maps (fp32 NCHW, channel counts C[e] <= 192) -> aligned bf16 tokens [B][4][HW][128]:
+ * align_layers[e] (1x1 conv + bias, large_kernel_attention.py:344-358) with the NCHW -> channels-last change done on the way
+ * into shared memory.  wblob: per expert [kg 24][n 128][8] bf16 (K zero-padded to 192), bias fp32 [4][128]. */
+size_t ffsr_align_tokens_weight_bytes(void);
+int ffsr_align_tokens(const float* const* feat, const int* C, int B, int HW, const void* wblob, const float* bias, void* out,
+                      cudaStream_t stream);
 size_t ffsr_token_attn_weight_bytes(void);
 size_t ffsr_token_attn_param_floats(void);
 int ffsr_token_attn_chain(const void* x, int B, int HW, const void* wblob, const float* pblob, void* out, cudaStream_t stream);

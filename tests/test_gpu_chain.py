@@ -113,3 +113,30 @@ def test_token_chain_matches_layer_by_layer_forward():
     assert (t2_chain - t2_ref).abs().max().item() <= 0.03 * scale
     assert torch.nn.functional.cosine_similarity(t2_chain.reshape(-1), t2_ref.reshape(-1), dim=0).item() > 0.9995
     assert (sr_chain - sr_ref).abs().max().item() <= 5e-3
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 8, 16), (2, 13, 29), (1, 40, 56)])
+def test_align_tokens_against_torch(B, H, W):
+    """ffsr_align_tokens (csrc/token_chain.cu) against the four nn.Conv2d align layers in fp32 (large_kernel_attention.py:344-358):
+    bf16 operands with fp32 accumulation, bf16 token rows."""
+    import ctypes as C
+    from isr_b200.pipeline import pack_align_tokens, EXPERT_ORDER
+    dev = _cuda()
+    m = _model(dev)
+    co = m.collaborative
+    lib = K.load()
+    g = torch.Generator().manual_seed(B * 100 + H)
+    feats = [torch.randn(B, co.align_layers[n].weight.shape[1], H, W, generator=g).to(dev) for n in EXPERT_ORDER]
+    wb, bb = pack_align_tokens(co)
+    assert wb.numel() * 2 == lib.ffsr_align_tokens_weight_bytes()
+    out = torch.full((B, 4, H * W, 128), float("nan"), device=dev, dtype=torch.bfloat16)
+    fptr = (C.c_void_p * 4)(*[t.data_ptr() for t in feats])
+    cnum = (C.c_int * 4)(*[t.shape[1] for t in feats])
+    K.check(lib.ffsr_align_tokens(fptr, cnum, B, H * W, wb.data_ptr(), bb.data_ptr(), out.data_ptr(), None))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = torch.stack([co.align_layers[n](f).permute(0, 2, 3, 1).reshape(B, H * W, 128) for n, f in zip(EXPERT_ORDER, feats)], 1)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 0.02 * ref.abs().max().item(), err
+    assert torch.nn.functional.cosine_similarity(out.float().reshape(-1), ref.reshape(-1), dim=0).item() > 0.9999

@@ -99,7 +99,7 @@ def test_orchestration_dry_run(with_feats, want_inter, precision):
     # Phase 6 (six selector convs + the gate normalisation) is one ffsr_selector_fused launch in both modes
     expect = (63 if with_feats else 51) - 3 - 6
     if precision == "bf16":
-        expect -= 3 + 18 + 4 + 4
+        expect -= 3 + 18 + 4 + 4 + (1 if with_feats else 0)     # + the grouped align conv, now inside ffsr_align_tokens
     assert calls.count("ffsr_conv2d") == expect, calls.count("ffsr_conv2d")
     assert calls.count("ffsr_lka_tail64") == 1
     assert calls.count("ffsr_selector_fused") == 1 and "ffsr_gate_finalize" not in calls
