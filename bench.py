@@ -1178,8 +1178,12 @@ def forward_breakdown(rows, H, W, hbm_peak, tensor_peak):
             ph = "P2 bands"
         elif lab.startswith("ffsr_crossband") or " cb." in lab:
             ph = "P3 cross-band + LKA"
-        elif " ds." in lab or lab.startswith("ffsr_gate_finalize"):
+        elif " ds." in lab or lab.startswith(("ffsr_gate_finalize", "ffsr_selector_fused")):
             ph = "P6 selector"
+        elif lab.startswith("ffsr_lka_tail64"):
+            ph = "P3 cross-band + LKA"
+        elif lab.startswith(("ffsr_lka_tail128", "ffsr_token_", "ffsr_align_tokens")):
+            ph = "P4 collaborative (LR)"
         elif lab.startswith("ffsr_lka_depthwise"):
             ph = "P3 cross-band + LKA" if lka_seen == 0 else "P4 collaborative (LR)"
             kern["lka_dw_p3" if lka_seen == 0 else "lka_dw_p4"] = ms

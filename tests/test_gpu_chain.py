@@ -140,3 +140,28 @@ def test_align_tokens_against_torch(B, H, W):
     err = (out.float() - ref).abs().max().item()
     assert err <= 0.02 * ref.abs().max().item(), err
     assert torch.nn.functional.cosine_similarity(out.float().reshape(-1), ref.reshape(-1), dim=0).item() > 0.9999
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 16, 16), (2, 13, 29), (1, 40, 56)])
+def test_fused_selector_matches_layer_by_layer(B, H, W):
+    """ffsr_selector_fused (csrc/selector.cu) vs the six fp32 conv launches + ffsr_gate_finalize it replaces
+    (DynamicExpertSelector.forward, enhanced_fusion_v2.py:450-466): same fp32 math in another summation order."""
+    dev = _cuda()
+    m = _model(dev)
+    m.precision = "fp32"
+    lr, imgs, fts, _ = O.synthetic_inputs(B, H, W)
+    lr, imgs, fts = lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()}
+    with torch.no_grad():
+        m.forward_with_precomputed(lr, imgs, fts)
+        eng = m._engine
+        assert eng.selector_fused, "FFSR_SELECTOR_LAYERS is set: nothing to compare"
+        run = lambda: m._run_pipeline(lr, [imgs[k] for k in O.EXPERT_ORDER], fts, 4 * H, 4 * W, {}, True)[1]
+        a = run()
+        a = {k: a[k].clone() for k in ("gates", "difficulty", "gate_logits", "active")}
+        eng.selector_fused = False
+        b = run()
+        eng.selector_fused = True
+    for k in ("gates", "difficulty", "gate_logits"):
+        assert (a[k] - b[k]).abs().max().item() <= 2e-5, k
+    assert a["gates"].argmax(1).eq(b["gates"].argmax(1)).all()
+    assert a["active"].eq(b["active"]).all()
