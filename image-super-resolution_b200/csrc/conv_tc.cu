@@ -633,6 +633,26 @@ __device__ __forceinline__ void lean_epilogue(const TcArgs& a, uint64_t* tfull, 
     const int n = ti.n;
     const int cb = ti.nb * a.nblk;                      // first output column of this cout block
     const int x0 = (a.geom == 2 ? ti.tx * 16 : ti.tx * tw) + px;
+    if (MODE == EM_RESIDUAL) {
+      // the residual rows of this thread's pixels are fetched towards L1 BEFORE the wait for the accumulator: their loads sat
+      // behind the TMEM load in every chunk, and a residual layer cost twice its plain twin (stage3.r2 0.25 vs r0 0.11 ms)
+      for (int half = 0; half < halves; ++half) {
+        const int xx = a.geom == 2 ? x0 + half * 8 : x0;
+        const int yy = ti.ty * a.tile_h + (a.geom == 2 ? 0 : half * TC_TH) + py;
+        if (yy < a.H && xx < a.W) {
+          const long long e1 = (long long)n * a.r1_sN + (long long)yy * a.r1_sY + (long long)xx * a.r1_sX + cb + c_lo * 16;
+          const char* p1 = reinterpret_cast<const char*>(a.r1) + e1 * (a.r1_bf16 ? 2 : 4);
+          const int bytes1 = (c_hi - c_lo) * 16 * (a.r1_bf16 ? 2 : 4);
+          for (int o = 0; o < bytes1; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(p1 + o));
+          if (has_r2) {
+            const long long e2 = (long long)n * a.r2_sN + (long long)yy * a.r2_sY + (long long)xx * a.r2_sX + cb + c_lo * 16;
+            const char* p2 = reinterpret_cast<const char*>(a.r2) + e2 * (a.r2_bf16 ? 2 : 4);
+            const int bytes2 = (c_hi - c_lo) * 16 * (a.r2_bf16 ? 2 : 4);
+            for (int o = 0; o < bytes2; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(p2 + o));
+          }
+        }
+      }
+    }
     mbar_wait(&tfull[as], aph);
     tc_fence_after();
     for (int half = 0; half < halves; ++half) {
