@@ -23,10 +23,10 @@
 namespace {
 using namespace tcx;
 
-constexpr int WT_THREADS = 128;
+constexpr int WT_THREADS = 256;             // two threads per query row: row = tid % 128, score-column half = tid / 128
 constexpr int WT_N = 256;                 // tokens per window (16 x 16)
 constexpr int WT_WS = 16;
-constexpr int WT_HDR = 3072;              // barrier + TMEM slot | pix[256] | rid[256]
+constexpr int WT_HDR = 3072;              // barrier + TMEM slot | pix[256] | rid[256] | xch[256] (row max / row sum exchange)
 constexpr int WT_TMEM_COLS = 256;
 
 __device__ __forceinline__ int wt_region(int p, int n, int shift) { return p < n - WT_WS ? 0 : (p < n - shift ? 1 : 2); }
@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8);
   int* pix = reinterpret_cast<int*>(smem + 64);
   uint8_t* rid = smem + 64 + WT_N * 4;
+  float* xch = reinterpret_cast<float*>(smem + 1408);
   uint8_t* sQ = smem + WT_HDR;
   uint8_t* sK = sQ + 128 * DP * 2;
   uint8_t* sV = sK + WT_N * DP * 2;
@@ -120,8 +121,11 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + u * WT_THREADS;
-        tt[u] = i < total ? i / cpt : 0;
-        gg[u] = i < total ? i - tt[u] * cpt : 0;
+        // eight consecutive items = eight consecutive keys of one 8-channel group: the 2-byte transposing stores of a warp
+        // then fall into 4 distinct 16-byte cells (a 4-way bank conflict) instead of 32 cells one bank row apart (32-way)
+        const int blk = i / (8 * cpt), rem = i - blk * (8 * cpt);
+        tt[u] = i < total ? blk * 8 + (rem & 7) : 0;
+        gg[u] = i < total ? rem >> 3 : 0;
         const __nv_bfloat16* src = qkv + (img + (size_t)pix[tt[u]]) * (size_t)qp + (size_t)(h * DP + gg[u] * 8);
         kc[u] = __ldg(reinterpret_cast<const uint4*>(src + heads * DP));
         vc[u] = __ldg(reinterpret_cast<const uint4*>(src + 2 * heads * DP));
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
   // K planes [kg][key][8] and V^T planes [key group][channel][8 keys].  A warp copies four tokens at a time, lanes across the
   // head's channels (coalesced 2-byte loads), all eight loads of a step issued before the first store: the copy is bound by
   // global-load latency, and the pixel table lives in the same shared memory the stores go to, so the loads are hoisted by hand.
-  for (int t0 = warp * 4; t0 < WT_N; t0 += 16) {
+  for (int t0 = warp * 4; t0 < WT_N; t0 += WT_THREADS / 8) {
     size_t row[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) row[u] = (img + (size_t)pix[t0 + u]) * (size_t)qp + (size_t)(h * dh);
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
     float* red = reinterpret_cast<float*>(sP);
     if (lane == 0) red[warp] = bm;
     __syncthreads();
-    bias_max = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * 1.4426950408889634f;
+    bias_max = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]))) * 1.4426950408889634f;
     __syncthreads();
   }
   const uint32_t hi128 = desc_hi(128);
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
           if (i0 + u * WT_THREADS < total) *reinterpret_cast<uint4*>(sQ + gg[u] * 2048 + rr[u] * 16) = qc[u];
       }
     } else
-    for (int r0 = warp * 8; r0 < 128; r0 += 32) {
+    for (int r0 = warp * 8; r0 < 128; r0 += WT_THREADS / 4) {
       size_t row[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) row[u] = (img + (size_t)pix[mt * 128 + r0 + u]) * (size_t)qp + (size_t)(h * dh);
@@ -227,53 +231,63 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
     phase ^= 1;
     tc_fence_after();
 
+    // ---- this head's relative-position bias table (31 x 31 entries, log2 units) -> the Q planes, dead now that S is complete:
+    //      the softmax below read one global word per score before
+    float* tbl = reinterpret_cast<float*>(sQ);
+    for (int i = tid; i < (2 * WT_WS - 1) * (2 * WT_WS - 1); i += WT_THREADS) tbl[i] = __ldg(table + i * heads + h) * 1.4426950408889634f;
+    __syncthreads();
     // ---- softmax: thread = query row
-    const int q = mt * 128 + tid;
+    const int rowi = tid & 127, half = tid >> 7;                             // this thread's query row of the tile and its 8 of the 16 chunks
+    const int q = mt * 128 + rowi;
     const int qy = q >> 4, qx = q & 15;
     const uint32_t qr = rid[q];
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float L2E = 1.4426950408889634f;
     // Row maximum: of the raw scores only (one pass of tcgen05.ld + max, no bias loads).  softmax is shift invariant, so any
     // m >= max_k s_k is as good as the true maximum for overflow; m = max_k(q k scale) + max(bias table of this head) is such
     // a bound (the mask only lowers scores), and it stays within the bias RANGE of the true maximum, far from underflow.
     float mx = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < 16; ++c) {
+    for (int c = half * 8; c < half * 8 + 8; ++c) {
       uint32_t v[16];
       tmem_ld16(trow + (uint32_t)(c * 16), v);
       tmem_wait_ld(v);
 #pragma unroll
       for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
     }
+    xch[tid] = mx;
+    __syncthreads();
+    mx = fmaxf(xch[rowi], xch[rowi + 128]);
+    __syncthreads();                                                         // both maxima read: xch takes the row sums next
     mx = fmaf(mx, scale2, bias_max);
     float sum = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < 16; ++c) {                                           // 16 columns = key row c of the window
+    for (int c = half * 8; c < half * 8 + 8; ++c) {                          // 16 columns = key row c of the window
       uint32_t v[16];
       tmem_ld16(trow + (uint32_t)(c * 16), v);
       tmem_wait_ld(v);
-      const float* tb = table + ((qy - c + WT_WS - 1) * (2 * WT_WS - 1) + (qx + WT_WS - 1)) * heads + h;   // key column 0; -heads per column
+      const float* tb = tbl + ((qy - c + WT_WS - 1) * (2 * WT_WS - 1) + (qx + WT_WS - 1));   // key column 0; -1 per column
       const uint4 rk = *reinterpret_cast<const uint4*>(rid + c * 16);
       const uint32_t rw[4] = {rk.x, rk.y, rk.z, rk.w};
       float pr[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float a = fmaf(__uint_as_float(v[i]), scale2, fmaf(__ldg(tb - i * heads), L2E, -mx));
+        float a = fmaf(__uint_as_float(v[i]), scale2, tb[-i] - mx);
         if (shift && ((rw[i >> 2] >> ((i & 3) * 8)) & 0xffu) != qr) a -= 100.0f * L2E;
         pr[i] = ex2f(a);
         sum += pr[i];
       }
       // keys 16c .. 16c+7 -> plane 2c, keys 16c+8 .. -> plane 2c+1; row = this query
-      *reinterpret_cast<uint4*>(sP + (2 * c) * 2048 + tid * 16) =
+      *reinterpret_cast<uint4*>(sP + (2 * c) * 2048 + rowi * 16) =
           make_uint4(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]), pack_bf16(pr[4], pr[5]), pack_bf16(pr[6], pr[7]));
-      *reinterpret_cast<uint4*>(sP + (2 * c + 1) * 2048 + tid * 16) =
+      *reinterpret_cast<uint4*>(sP + (2 * c + 1) * 2048 + rowi * 16) =
           make_uint4(pack_bf16(pr[8], pr[9]), pack_bf16(pr[10], pr[11]), pack_bf16(pr[12], pr[13]), pack_bf16(pr[14], pr[15]));
     }
-    mx = 1.0f / sum;
-    const float inv = mx;
+    xch[tid] = sum;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();                                                         // every row of S has been read, P is complete
+    const float inv = 1.0f / (xch[rowi] + xch[rowi + 128]);
     if (tid == 0) {
       tc_fence_after();
       for (int ks = 0; ks < WT_N / 16; ++ks)
@@ -285,21 +299,30 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
     phase ^= 1;
     tc_fence_after();
 
-    // ---- O / rowsum -> global, at the token's original pixel
-    __nv_bfloat16* dst = out + (img + pix[q]) * op + h * dh;
-    for (int c = 0; c < DP / 16; ++c) {
-      uint32_t v[16];
-      tmem_ld16(trow + (uint32_t)(c * 16), v);
-      tmem_wait_ld(v);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int d = c * 16 + i;
-        if (d < dh) dst[d] = __float2bfloat16_rn(__uint_as_float(v[i]) * inv);
+    // ---- O / rowsum -> bf16 rows in the (dead) P buffer -> global at the token's original pixel: a warp writes one row at a
+    //      time, lanes along the channels (the thread-per-row version scattered every 2-byte store of a warp over 32 rows)
+    {
+      __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sP);
+      const int pitch = DP + 8;                                              // elements; 16-byte aligned rows, conflict-free
+      for (int c = half; c < DP / 16; c += 2) {
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)(c * 16), v);
+        tmem_wait_ld(v);
+        uint4* d4 = reinterpret_cast<uint4*>(so + rowi * pitch + c * 16);
+        d4[0] = make_uint4(pack_bf16(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv), pack_bf16(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv),
+                           pack_bf16(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv), pack_bf16(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv));
+        d4[1] = make_uint4(pack_bf16(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv), pack_bf16(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv),
+                           pack_bf16(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv), pack_bf16(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv));
       }
+      tc_fence_before();
+      __syncthreads();                                                       // O read; rows staged
+      for (int r = warp; r < 128; r += WT_THREADS / 32) {
+        __nv_bfloat16* dst = out + (img + pix[mt * 128 + r]) * op + h * dh;
+        for (int d = lane; d < dh; d += 32) dst[d] = so[r * pitch + d];
+      }
+      __syncthreads();                                                       // Q / P free for the next tile
+      tc_fence_after();
     }
-    tc_fence_before();
-    __syncthreads();                                                         // O read, Q / P free for the next tile
-    tc_fence_after();
   }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(WT_TMEM_COLS));
 }
