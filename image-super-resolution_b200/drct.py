@@ -125,6 +125,7 @@ class DRCT(nn.Module):
         # the MLP hidden activations are bf16 rows padded to 8 channels and the Linears run on tcgen05; the residual stream
         # stays fp32.  Both modes are validated on B200 (tests/test_gpu_drct.py).
         self.precision = "fp32"
+        self.tail_tc = os.environ.get("FFSR_DRCT_TAIL_FP32") is None      # bf16 mode: reconstruction tail convs on tcgen05
         self.headpad_qkv = os.environ.get("FFSR_DRCT_QKV_PLAIN") is None   # bf16 mode, 16 x 16 windows: head-padded qkv rows
         self._packed: Optional[Tuple] = None
         self._ws: Dict[Tuple, torch.Tensor] = {}
@@ -274,7 +275,9 @@ class DRCT(nn.Module):
                      n2.data_ptr(), pad(d), K.DT_F32, ADT, S)
                 hd = self._buf("hid", (B, H, W, pad(hid)), dev, adt)
                 conv(nhwc(n2), H, W, d, p + ".mlp.fc1", hid, 1, nhwc(hd), act=K.ACT_GELU)
-                y2 = self._buf("y2", (B, H, W, d), dev) if lp else att
+                # bf16 mode: y2 feeds only the adjust conv, so it is stored as bf16 rows (16-byte pitch) and that conv runs on tcgen05
+                # too (it was an fp32 CUDA-core GEMM: 16 of the 147 ms of a 352x512 forward)
+                y2 = self._buf("y2b", (B, H, W, pad(d)), dev, adt) if (lp and self.tail_tc) else (self._buf("y2", (B, H, W, d), dev) if lp else att)
                 conv(nhwc(hd), H, W, hid, p + ".mlp.fc2", d, 1, nhwc(y2), r1=nhwc(y1))             # + mlp
                 a = f"layers.{i}.adjust{j + 1}"
                 if j < 4:                                      # 32 new channels straight into the growth buffer, LeakyReLU 0.2
@@ -284,6 +287,36 @@ class DRCT(nn.Module):
                 else:                                          # x5 * 0.2 + x, in place on the first `embed_dim` channels
                     conv(nhwc(y2), H, W, d, a, E, 1, prefix(G), r1=prefix(G), sa=0.2)
 
+        if lp and self.tail_tc:
+            # bf16 mode: the reconstruction tail on tcgen05 as well.  Its six 3x3 convs ran as fp32 CUDA-core launches (16.6 of the
+            # 147 ms of a 352x512 forward, the 64 -> 256 conv at 2x resolution alone 7.1 ms at 30 TFLOP/s).  The cached feature
+            # (expert_loader hook) stays an fp32 tensor; x0 + conv_after_body(.) is a second launch of the same conv with the
+            # residual epilogue and a bf16 output (0.1 ms) instead of an add + cast pass.
+            bf, pe = torch.bfloat16, (E + 7) // 8 * 8
+            tb = self._buf("nb", (B, H, W, pe), dev, bf)
+            call(lib.ffsr_layernorm_strided, G.data_ptr(), NP, E, GW, w["norm.w"].data_ptr(), w["norm.b"].data_ptr(), tb.data_ptr(), pe,
+                 K.DT_F32, K.DT_BF16, S)
+            feat = torch.empty(B, H, W, E, device=dev)
+            conv(nhwc(tb), H, W, E, "conv_after_body", E, 3, nhwc(feat))
+            self.last_feature = feat.permute(0, 3, 1, 2)
+            yb = self._buf("yb", (B, H, W, pe), dev, bf)
+            conv(nhwc(tb), H, W, E, "conv_after_body", E, 3, nhwc(yb), r1=nhwc(x0))
+            ub = self._buf("ub", (B, H, W, 64), dev, bf)
+            conv(nhwc(yb), H, W, E, "conv_before_upsample.0", 64, 3, nhwc(ub))
+            call(lib.ffsr_leaky_relu, ub.data_ptr(), NP, 64, 64, 0.01, K.DT_BF16, S)
+            u4 = self._buf("u4b", (B, H, W, 256), dev, bf)
+            conv(nhwc(ub), H, W, 64, "upsample.0", 256, 3, nhwc(u4))
+            s2 = self._buf("s2b", (B, 2 * H, 2 * W, 64), dev, bf)
+            call(lib.ffsr_pixel_shuffle2, u4.data_ptr(), B, H, W, 64, s2.data_ptr(), K.DT_BF16, S)
+            u8 = self._buf("u8b", (B, 2 * H, 2 * W, 256), dev, bf)
+            conv(nhwc(s2), 2 * H, 2 * W, 64, "upsample.2", 256, 3, nhwc(u8))
+            s4 = self._buf("s4b", (B, 4 * H, 4 * W, 64), dev, bf)
+            call(lib.ffsr_pixel_shuffle2, u8.data_ptr(), B, 2 * H, 2 * W, 64, s4.data_ptr(), K.DT_BF16, S)
+            o4 = self._buf("o4", (B, 4 * H, 4 * W, 4), dev)
+            conv(nhwc(s4), 4 * H, 4 * W, 64, "conv_last", 3, 3, nhwc(o4))
+            out = torch.empty(B, 3, 4 * H, 4 * W, device=dev)
+            call(lib.ffsr_rgb_shift_out, o4.data_ptr(), B, 4 * H, 4 * W, 4, mean3, float(self.img_range), out.data_ptr(), K.DT_F32, S)
+            return out
         t = self._buf("n", (B, H, W, E), dev)
         call(lib.ffsr_layernorm_strided, G.data_ptr(), NP, E, GW, w["norm.w"].data_ptr(), w["norm.b"].data_ptr(), t.data_ptr(), E,
              K.DT_F32, K.DT_F32, S)
