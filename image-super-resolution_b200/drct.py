@@ -224,6 +224,18 @@ class DRCT(nn.Module):
             p.sa, p.sb = sa, 1.0
             call(lib.ffsr_conv2d, C.byref(p), S)
 
+        def padded_out(name: str, cout_p: int) -> str:
+            """Weights / bias of Linear `name` with zero output rows appended up to cout_p (packed once)."""
+            key = f"{name}.o{cout_p}"
+            if key not in w:
+                wt = w[name]                                   # [1][in][out]
+                wp = torch.zeros(1, wt.shape[1], cout_p, device=wt.device)
+                wp[:, :, :wt.shape[2]] = wt
+                bp = torch.zeros(cout_p, device=wt.device)
+                bp[:wt.shape[2]] = w[name + ".b"]
+                w[key], w[key + ".b"] = wp.contiguous(), bp
+            return key
+
         def prefix(t: torch.Tensor, c0: int = 0) -> _View:
             """Channel slice starting at c0 of a [B,h,w,Cs] buffer (the conv takes the channel COUNT separately)."""
             return nhwc(t, c0)
@@ -268,17 +280,28 @@ class DRCT(nn.Module):
                 else:
                     call(lib.ffsr_window_attention, qkv.data_ptr(), B, H, W, d, sw.heads, ws, shift,
                          w[p + ".attn.table"].data_ptr(), att.data_ptr(), K.DT_F32, S)
-                y1 = self._buf("y1", (B, H, W, d), dev)
-                conv(nhwc(att), H, W, d, p + ".attn.proj", d, 1, nhwc(y1), r1=prefix(G))          # x + proj(attn)
+                slim = lp and self.tail_tc                     # bf16 mode: the block's inner residual rows y1 / y2 as bf16 too
+                if slim:
+                    # Cout = d is 4 mod 8 for every DRCT-L width, which keeps these Linears off the 16-byte-store epilogue of
+                    # k_conv_tc: their weights get four zero output rows (padded_out), the outputs land in the pad columns of the
+                    # 8-channel-padded bf16 rows (never read: LayerNorm and the next Linear take d channels)
+                    y1 = self._buf("y1b", (B, H, W, pad(d)), dev, adt)
+                    conv(nhwc(att), H, W, d, padded_out(p + ".attn.proj", pad(d)), pad(d), 1, nhwc(y1), r1=prefix(G))
+                else:
+                    y1 = self._buf("y1", (B, H, W, d), dev)
+                    conv(nhwc(att), H, W, d, p + ".attn.proj", d, 1, nhwc(y1), r1=prefix(G))      # x + proj(attn)
                 n2 = n1
-                call(lib.ffsr_layernorm_strided, y1.data_ptr(), NP, d, d, w[p + ".norm2.w"].data_ptr(), w[p + ".norm2.b"].data_ptr(),
-                     n2.data_ptr(), pad(d), K.DT_F32, ADT, S)
+                call(lib.ffsr_layernorm_strided, y1.data_ptr(), NP, d, pad(d) if slim else d, w[p + ".norm2.w"].data_ptr(),
+                     w[p + ".norm2.b"].data_ptr(), n2.data_ptr(), pad(d), ADT if slim else K.DT_F32, ADT, S)
                 hd = self._buf("hid", (B, H, W, pad(hid)), dev, adt)
                 conv(nhwc(n2), H, W, d, p + ".mlp.fc1", hid, 1, nhwc(hd), act=K.ACT_GELU)
                 # bf16 mode: y2 feeds only the adjust conv, so it is stored as bf16 rows (16-byte pitch) and that conv runs on tcgen05
                 # too (it was an fp32 CUDA-core GEMM: 16 of the 147 ms of a 352x512 forward)
                 y2 = self._buf("y2b", (B, H, W, pad(d)), dev, adt) if (lp and self.tail_tc) else (self._buf("y2", (B, H, W, d), dev) if lp else att)
-                conv(nhwc(hd), H, W, hid, p + ".mlp.fc2", d, 1, nhwc(y2), r1=nhwc(y1))             # + mlp
+                if slim:
+                    conv(nhwc(hd), H, W, hid, padded_out(p + ".mlp.fc2", pad(d)), pad(d), 1, nhwc(y2), r1=nhwc(y1))
+                else:
+                    conv(nhwc(hd), H, W, hid, p + ".mlp.fc2", d, 1, nhwc(y2), r1=nhwc(y1))         # + mlp
                 a = f"layers.{i}.adjust{j + 1}"
                 if j < 4:                                      # 32 new channels straight into the growth buffer, LeakyReLU 0.2
                     c0 = E + j * gc
