@@ -49,9 +49,9 @@ constexpr int TC_TH = 8, TC_TW = 16;           // output pixel tile (M = 128)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_ROW_BYTES = TC_TW * 128;      // one image row of the tile: 16 px x 64 bf16
 constexpr int TC_SMEM_MAX = 232448;            // 227 KB opt-in limit per CTA
-constexpr int TC_SMEM_HDR = 3072;              // barriers + TMEM slot (first 1 KB) + staged bias (512 floats)
+constexpr int TC_SMEM_HDR = 5120;              // barriers + TMEM slot (first 1 KB) + staged bias (1024 floats)
 constexpr int TC_BIAS_OFF = 1024;              // byte offset of the staged bias inside the header
-constexpr int TC_BIAS_MAX = 512;               // output columns whose bias is staged (lean epilogue)
+constexpr int TC_BIAS_MAX = 1024;              // output columns whose bias is staged (lean epilogue)
 constexpr int TC_EPI_WARPS = 16;              // 4 per TMEM lane quarter: each owns a 16-column slice
 constexpr int TC_MMA_WARPS = 3;               // warps 1..3 can issue MMAs (TcArgs.nmma of them do; see the MMA issuers).  20 warps = 5
                                               // per SM sub-partition keep the 96-register budget; a 21st would cut it to 80
@@ -104,6 +104,8 @@ struct TcArgs {
                      //    tile are spread over the four groups.  See epilogue_loop.
   int lean;          // 1: lean_epilogue (bf16 inference outputs, bias staged in shared memory); see there
   int nmma;          // MMA-issuing warps (1, 2 or 3): warp 1+g issues the MMAs of tiles g, g+nmma, ... of this CTA
+  int nb_fast;       // 1: the cout block varies FASTEST in the tile walk (multi-block 1x1 layers with streamed weights): the CTAs
+                     //    of a wave then work on the same few pixel tiles, whose activations stay in L2 across the cout blocks
   int a_slot;        // geom 2: bytes of one slot of the activation ring (haloed copy rounded up to 1 KB)
   int na_slots;      // geom 2: slots of the activation ring (the weight ring has nstages slots of stage_bytes)
 };
@@ -353,18 +355,38 @@ struct TileIter {
   long long t;
   __device__ __forceinline__ void init(const TcArgs& a) {
     unsigned r = blockIdx.x;
+    unsigned d = gridDim.x;
+    t = blockIdx.x;
+    if (a.nb_fast) {
+      nb = r % a.n_nblocks; r /= a.n_nblocks;
+      tx = r % a.tiles_x; r /= a.tiles_x;
+      ty = r % a.tiles_y; n = r / a.tiles_y;
+      dnb = d % a.n_nblocks; d /= a.n_nblocks;
+      dtx = d % a.tiles_x; d /= a.tiles_x;
+      dty = d % a.tiles_y; dn = d / a.tiles_y;
+      return;
+    }
     tx = r % a.tiles_x; r /= a.tiles_x;
     ty = r % a.tiles_y; r /= a.tiles_y;
     n = r % a.N; nb = r / a.N;
-    unsigned d = gridDim.x;
     dtx = d % a.tiles_x; d /= a.tiles_x;
     dty = d % a.tiles_y; d /= a.tiles_y;
     dn = d % a.N; dnb = d / a.N;
-    t = blockIdx.x;
   }
   __device__ __forceinline__ bool valid(const TcArgs& a) const { return t < a.total_tiles; }
   __device__ __forceinline__ void next(const TcArgs& a) {
     t += gridDim.x;
+    if (a.nb_fast) {
+      nb += dnb;
+      int c = 0;
+      if (nb >= a.n_nblocks) { nb -= a.n_nblocks; c = 1; }
+      tx += dtx + c; c = 0;
+      if (tx >= a.tiles_x) { tx -= a.tiles_x; c = 1; }
+      ty += dty + c; c = 0;
+      if (ty >= a.tiles_y) { ty -= a.tiles_y; c = 1; }
+      n += dn + c;
+      return;
+    }
     tx += dtx;
     int c = 0;
     if (tx >= a.tiles_x) { tx -= a.tiles_x; c = 1; }
@@ -1034,7 +1056,13 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   // Streamed weights (the whole 3x3 set of a cout block does not fit beside three A stages: 128->128) are re-fetched
   // for every pixel tile and dominate the TMA traffic (2304 of 3264 128-byte rows per tile).  Those layers use
   // 16x16-pixel tiles: two M=128 MMAs per (tap, K-step) share each weight stage, halving the weight rows per pixel.
+  // Multi-block 1x1 layers (the DRCT Linears: N = 360 .. 768 in 128-column blocks).  With the cout block slowest and resident
+  // weights the whole activation tensor was re-read from HBM once per block (6 x 88 MB for a 244 -> 768 Linear: the launch sat on
+  // the HBM roof of that schedule, 150 us for 12 GFLOP).  Here the cout block varies fastest, the weights stream beside the
+  // activations and 16x16-pixel tiles share every weight stage between two M = 128 MMAs.
+  const bool gemm_mode = p.ksize == 1 && cout_pad / nblk > 1 && p.groups == 1 && getenv("FFSR_TC_GEMM_MODE_OFF") == nullptr;
   int halves = 1;
+  if (gemm_mode && p.H >= 16 && nblk * 2 * 2 <= TC_TMEM_COLS) halves = 2;
   {
     const int nch0 = (p.Cin + 63) / 64;
     const int a8 = (TC_TH + 2 * (p.ksize / 2)) * TC_ROW_BYTES;
@@ -1058,7 +1086,7 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   }
   // Streamed-weight 3x3 layers served by the lean epilogue (bf16 inference outputs): dual-ring geometry, see the kernel
   constexpr int A2_BYTES = 18 * 18 * 128, A2_SLOT = (A2_BYTES + 1023) / 1024 * 1024;
-  if (halves == 2 && geom == 0 && getenv("FFSR_TC_GEOM2_OFF") == nullptr && getenv("FFSR_TC_LEAN0") == nullptr) {
+  if (halves == 2 && geom == 0 && p.ksize == 3 && getenv("FFSR_TC_GEOM2_OFF") == nullptr && getenv("FFSR_TC_LEAN0") == nullptr) {
     const bool mode_ok = p.epi == FFSR_EPI_PLAIN || (p.epi == FFSR_EPI_RESIDUAL && p.act == ACT_NONE);
     const bool out_ok = p.out_dtype == FFSR_DT_BF16 && p.out2 == nullptr && p.groups == 1 && p.Cout % 8 == 0 && ((uintptr_t)p.out % 16) == 0 &&
                         p.out_sX % 8 == 0 && p.out_sY % 8 == 0 && p.out_sN % 8 == 0 && cout_pad <= TC_BIAS_MAX && (nblk % 64) == 0;
@@ -1112,7 +1140,8 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   a.b_bytes = p.ksize * nblk * 128;
   const int smem_avail = TC_SMEM_MAX - 1024 - TC_SMEM_HDR;
   const int b_all = a.nchunks * p.ksize * a.b_bytes;          // all taps, all K chunks of one cout block
-  a.b_resident = (b_all + 3 * a.a_bytes <= smem_avail) ? 1 : 0;
+  a.b_resident = (b_all + 3 * a.a_bytes <= smem_avail && !gemm_mode) ? 1 : 0;
+  a.nb_fast = gemm_mode ? 1 : 0;
   a.bres_bytes = a.b_resident ? b_all : 0;
   a.stage_bytes = geom ? A1C_STAGE : a.a_bytes + (a.b_resident ? 0 : a.b_bytes);
   if (geom) {                                                  // decided above with the same residency test
