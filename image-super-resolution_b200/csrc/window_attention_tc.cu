@@ -5,8 +5,8 @@
 // expert forward); this one is bound by the softmax instead of the products.
 //
 //   operands : NO-SWIZZLE K-major planes (tc_ptx.cuh): q tile [128 rows][DP], k [256][DP] and the probabilities p [128][256]
-//              as 8-element planes plane[kg][row] = 16 B; v TRANSPOSED, plane[key group][channel] = 8 keys, so that p v is a
-//              K-major x K-major product over the keys.  DP = head dim padded to a multiple of 16 (30 -> 32, 53 -> 64,
+//              as 8-element planes plane[kg][row] = 16 B; v in the SAME layout as k (planes [channel group][key]): p v takes it as
+//              an MN-major B operand, so nothing is transposed on the way in.  DP = head dim padded to a multiple of 16 (30 -> 32, 53 -> 64,
 //              122 -> 128, 46 -> 48, 77 -> 80) with zero columns.  The window gather (cyclic shift + partition) happens while
 //              the tokens are copied from the channels-last qkv rows into the planes.
 //   per tile : S = Q K^T (DP / 16 MMAs, M = 128, N = 256) -> TMEM columns [0, 256); thread = query row: two passes over
@@ -135,11 +135,7 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
         if (i0 + u * WT_THREADS >= total) continue;
         const int t = tt[u], g8 = gg[u];
         *reinterpret_cast<uint4*>(sK + g8 * (WT_N * 16) + t * 16) = kc[u];
-        const uint32_t w[4] = {vc[u].x, vc[u].y, vc[u].z, vc[u].w};
-        uint8_t* vb = sV + (t >> 3) * (DP * 16) + (g8 * 8) * 16 + (t & 7) * 2;
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          *reinterpret_cast<uint16_t*>(vb + e * 16) = (uint16_t)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+        *reinterpret_cast<uint4*>(sV + g8 * (WT_N * 16) + t * 16) = vc[u];     // V in the K layout: P V reads it as an MN-major B operand
       }
     }
   } else {
@@ -161,7 +157,7 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
       for (int u = 0; u < 4; ++u) {
         const int t = t0 + u;
         *reinterpret_cast<__nv_bfloat16*>(sK + (d >> 3) * (WT_N * 16) + t * 16 + (d & 7) * 2) = kv[u];
-        *reinterpret_cast<__nv_bfloat16*>(sV + (t >> 3) * (DP * 16) + d * 16 + (t & 7) * 2) = vv[u];
+        *reinterpret_cast<__nv_bfloat16*>(sV + (d >> 3) * (WT_N * 16) + t * 16 + (d & 7) * 2) = vv[u];
       }
     }
   }
@@ -183,7 +179,11 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
   }
   const uint32_t hi128 = desc_hi(128);
   const uint32_t q32 = smem_u32(sQ), k32 = smem_u32(sK), v32 = smem_u32(sV), p32 = smem_u32(sP);
-  const uint32_t idesc_s = idesc_bf16_m128(256), idesc_o = idesc_bf16_m128(DP);
+  // P V: B = V[key][channel] with the CHANNELS contiguous (planes [channel group][key] x 16 B, exactly the K layout) = an MN-major
+  // operand (instruction-descriptor bit 16): LBO = 128 B to the next 8 keys, SBO = one plane to the next 8 channels, any 16-byte
+  // aligned start (measured: tools/experiments/umma_mnmajor_b.cu).  No transposition of V on the way into shared memory.
+  const uint32_t idesc_s = idesc_bf16_m128(256), idesc_o = idesc_bf16_m128(DP) | (1u << 16);
+  const uint32_t hi_v = desc_hi(WT_N * 16);
   uint32_t phase = 0;
 
   for (int mt = 0; mt < 2; ++mt) {
@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
     if (tid == 0) {
       tc_fence_after();
       for (int ks = 0; ks < WT_N / 16; ++ks)
-        umma_one(tmem, desc_lo(p32 + (uint32_t)(2 * ks) * 2048u, 2048u), hi128,
-                 desc_lo(v32 + (uint32_t)(2 * ks) * (uint32_t)(DP * 16), (uint32_t)(DP * 16)), hi128, idesc_o, ks > 0 ? 1u : 0u);
+        umma_one(tmem, desc_lo(p32 + (uint32_t)(2 * ks) * 2048u, 2048u), hi128, desc_lo(v32 + (uint32_t)ks * 256u, 128u), hi_v, idesc_o,
+                 ks > 0 ? 1u : 0u);
       umma_commit_one(bar);
     }
     mbar_wait(bar, phase);
