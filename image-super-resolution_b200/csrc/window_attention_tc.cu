@@ -37,6 +37,12 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// 16-byte global -> shared copy that does not pass through registers: every cell of a gather is issued at once
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void umma_one(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
@@ -112,31 +118,15 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
   const int lane = tid & 31;
   const int cpt = DP >> 3;                                                  // 16-byte cells per token and operand
   if (HEADPAD) {
-    // K planes [kg][key][8]: cell = 8 channels of one key, copied whole; V^T planes [key group][channel][8 keys]: the
-    // cell of 8 channels is scattered into 8 transposed cells.  Four independent 16-byte loads in flight per thread.
+    // K and V planes [channel group][key][8]: a cell = 8 channels of one key, copied whole with cp.async, so the loads of the
+    // whole window are in flight together (with four register-staged loads per thread and round the gather was four to eight
+    // dependent round trips to L2 / HBM: 16 % of the kernel's stall samples)
     const int total = WT_N * cpt;
-    for (int i0 = tid; i0 < total; i0 += 4 * WT_THREADS) {
-      uint4 kc[4], vc[4];
-      int tt[4], gg[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * WT_THREADS;
-        // eight consecutive items = eight consecutive keys of one 8-channel group: the 2-byte transposing stores of a warp
-        // then fall into 4 distinct 16-byte cells (a 4-way bank conflict) instead of 32 cells one bank row apart (32-way)
-        const int blk = i / (8 * cpt), rem = i - blk * (8 * cpt);
-        tt[u] = i < total ? blk * 8 + (rem & 7) : 0;
-        gg[u] = i < total ? rem >> 3 : 0;
-        const __nv_bfloat16* src = qkv + (img + (size_t)pix[tt[u]]) * (size_t)qp + (size_t)(h * DP + gg[u] * 8);
-        kc[u] = __ldg(reinterpret_cast<const uint4*>(src + heads * DP));
-        vc[u] = __ldg(reinterpret_cast<const uint4*>(src + 2 * heads * DP));
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (i0 + u * WT_THREADS >= total) continue;
-        const int t = tt[u], g8 = gg[u];
-        *reinterpret_cast<uint4*>(sK + g8 * (WT_N * 16) + t * 16) = kc[u];
-        *reinterpret_cast<uint4*>(sV + g8 * (WT_N * 16) + t * 16) = vc[u];     // V in the K layout: P V reads it as an MN-major B operand
-      }
+    for (int i = tid; i < total; i += WT_THREADS) {
+      const int t = i / cpt, g8 = i - t * cpt;
+      const __nv_bfloat16* src = qkv + (img + (size_t)pix[t]) * (size_t)qp + (size_t)(h * DP + g8 * 8);
+      cp_async16(sK + g8 * (WT_N * 16) + t * 16, src + heads * DP);
+      cp_async16(sV + g8 * (WT_N * 16) + t * 16, src + 2 * heads * DP);
     }
   } else {
   // K planes [kg][key][8] and V^T planes [key group][channel][8 keys].  A warp copies four tokens at a time, lanes across the
@@ -190,20 +180,11 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
     // ---- Q tile planes [kg][row][8]; rows = queries mt*128 .. +127
     if (HEADPAD) {
       const int total = 128 * cpt;
-      for (int i0 = tid; i0 < total; i0 += 4 * WT_THREADS) {
-        uint4 qc[4];
-        int rr[4], gg[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * WT_THREADS;
-          rr[u] = i < total ? i / cpt : 0;
-          gg[u] = i < total ? i - rr[u] * cpt : 0;
-          qc[u] = __ldg(reinterpret_cast<const uint4*>(qkv + (img + (size_t)pix[mt * 128 + rr[u]]) * (size_t)qp + (size_t)(h * DP + gg[u] * 8)));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (i0 + u * WT_THREADS < total) *reinterpret_cast<uint4*>(sQ + gg[u] * 2048 + rr[u] * 16) = qc[u];
+      for (int i = tid; i < total; i += WT_THREADS) {
+        const int rr = i / cpt, gg = i - rr * cpt;
+        cp_async16(sQ + gg * 2048 + rr * 16, qkv + (img + (size_t)pix[mt * 128 + rr]) * (size_t)qp + (size_t)(h * DP + gg * 8));
       }
+      cp_async_wait_all();                           // also the K / V copies issued before the loop (first tile)
     } else
     for (int r0 = warp * 8; r0 < 128; r0 += WT_THREADS / 4) {
       size_t row[8];
@@ -316,9 +297,14 @@ __global__ void __launch_bounds__(WT_THREADS) k_window_attn_tc(const __nv_bfloat
       }
       tc_fence_before();
       __syncthreads();                                                       // O read; rows staged
+      const bool pair_ok = ((dh | (int)(op & 1)) & 1) == 0 && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
       for (int r = warp; r < 128; r += WT_THREADS / 32) {
         __nv_bfloat16* dst = out + (img + pix[mt * 128 + r]) * op + h * dh;
-        for (int d = lane; d < dh; d += 32) dst[d] = so[r * pitch + d];
+        if (pair_ok) {                                                       // even head dim and pitch: 4-byte stores
+          for (int d = 2 * lane; d < dh; d += 64) *reinterpret_cast<uint32_t*>(dst + d) = *reinterpret_cast<const uint32_t*>(so + r * pitch + d);
+        } else {
+          for (int d = lane; d < dh; d += 32) dst[d] = so[r * pitch + d];
+        }
       }
       __syncthreads();                                                       // Q / P free for the next tile
       tc_fence_after();
