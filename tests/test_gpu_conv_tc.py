@@ -70,6 +70,10 @@ def _run(cin, cout, ks, N, H, W, act, epi, out_bf16, cs_in=None, c_off=0, groups
     (3, 128, 3, 19, 37, K.ACT_GELU, K.EPI_PLAIN, True),          # 1 k-step per tap, zero-filled channels
     (128, 3, 3, 19, 37, K.ACT_NONE, K.EPI_RESIDUAL, False),      # N padded to 16, masked scalar stores
     (96, 32, 3, 19, 37, K.ACT_GELU, K.EPI_PLAIN, True),
+    (244, 768, 1, 32, 48, K.ACT_NONE, K.EPI_PLAIN, True),        # multi-block 1x1 (DRCT qkv): activation-resident GEMM walk
+    (180, 360, 1, 19, 37, K.ACT_GELU, K.EPI_PLAIN, True),        # ragged 16x16 tiles, 3 K chunks (last partial), 3 cout blocks
+    (308, 180, 1, 32, 48, K.ACT_NONE, K.EPI_RESIDUAL, False),    # 5 K chunks, fp32 output with residual, 2 cout blocks
+    (244, 768, 1, 8, 16, K.ACT_NONE, K.EPI_PLAIN, True),         # H < 16: streamed weights, cout block fastest
     (16, 3, 3, 9, 11, K.ACT_SIGMOID, K.EPI_PLAIN, False),        # image smaller than the TMA box
     (128, 384, 1, 19, 37, K.ACT_NONE, K.EPI_PLAIN, True),        # 3 cout blocks
     (256, 128, 1, 19, 37, K.ACT_NONE, K.EPI_RESIDUAL, False),    # 4 K chunks
