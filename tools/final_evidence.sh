@@ -19,6 +19,9 @@ cap() {  # name regex skip
   python tools/ncu_raw.py $O/r02_$1.ncu-rep gpu__time_duration.sum dram__bytes_read.sum dram__bytes_write.sum smsp__inst_executed.sum issue_stalled sm__cycles_active.avg pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active sm__warps_active.avg.pct 2>/dev/null | grep -v pcsamp >> $O/r02_$1_ncu_full.txt
   case " ${KEEP_REP:-convtc_refine_c3} " in *" $1 "*) ;; *) rm -f $O/r02_$1.ncu-rep;; esac
 }
+timeout 600 python bench.py --workload n1 --steps 3 --warmup 3 > $O/r02_n1_final.json 2> $O/r02_n1_final.err; echo "n1 rc=$?"
+timeout 600 python bench.py --workload c5 --steps 2 --warmup 3 > $O/r02_c5_final.json 2> $O/r02_c5_final.err; echo "c5 rc=$?"
+if [ "${SKIP_NCU:-0}" = "1" ]; then du -sh $O; exit 0; fi
 cap convtc_refine_c3 k_conv_tc 39
 cap convtc_32x32_c3 k_conv_tc 34
 cap token_attn k_token_attn 1
