@@ -59,7 +59,7 @@ constexpr int TC_EPI_WARP0 = 1 + TC_MMA_WARPS; // first epilogue warp
 constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS);
 constexpr int TC_TMEM_COLS = 512;             // whole TMEM: ring of 512/slot accumulators (1 CTA per SM)
 constexpr int TC_MAX_ACC = 12;
-constexpr int TC_MAX_ASLOTS = 6;              // geom 2 / 3: activation ring depth (geom 3: K chunks of the resident pixel tile)
+constexpr int TC_MAX_ASLOTS = 4;              // geom 2: activation ring depth limit
 
 struct TcArgs {
   int N, H, W, Cin, Cout, taps, ks;
@@ -74,7 +74,6 @@ struct TcArgs {
   int groups;
   int tiles_x, tiles_y;
   long long total_tiles;
-  long long pix_tiles;   // geom 3: pixel tiles (the tile walk visits each with every cout block in turn)
   void* out;
   long long out_sN, out_sY, out_sX;
   int out_bf16;
@@ -96,9 +95,7 @@ struct TcArgs {
   int acc_half;      // TMEM columns of one half accumulator (acc_slot = halves * acc_half)
   int geom;          // 0: 8x16-px tile rows, one haloed A copy per dx;  1: 16x8-px tiles, ONE haloed copy per K chunk;
                      // 2: streamed weights, 16x16-px tiles as two 16x8 halves: ONE haloed copy {64 ch, 18 px, 18 rows} per K chunk
-                     //    in its own ring + a ring of single-tap weight stages (see the kernel);
-                     // 3: multi-block 1x1 layers: the K chunks of a 16x16-pixel tile stay in shared memory while ALL its cout blocks
-                     //    are computed (same CTA, consecutive tiles of the walk); only the weights stream
+                     //    in its own ring + a ring of single-tap weight stages (see the kernel)
   int tile_h;        // output rows per tile (8 * halves, or 16 for geom 1)
   uint32_t a_step16; // geom 1: dy stride inside the haloed copy, in 16-byte units (10 px * 128 B)
   uint32_t a_desc_hi;// geom 1: A descriptor high word (SBO = haloed image-row pitch)
@@ -360,15 +357,6 @@ struct TileIter {
     unsigned r = blockIdx.x;
     unsigned d = gridDim.x;
     t = blockIdx.x;
-    if (a.geom == 3) {                               // t counts PIXEL tiles; nb runs 0 .. n_nblocks-1 inside each
-      tx = r % a.tiles_x; r /= a.tiles_x;
-      ty = r % a.tiles_y; n = r / a.tiles_y;
-      nb = 0;
-      dtx = d % a.tiles_x; d /= a.tiles_x;
-      dty = d % a.tiles_y; dn = d / a.tiles_y;
-      dnb = 0;
-      return;
-    }
     if (a.nb_fast) {
       nb = r % a.n_nblocks; r /= a.n_nblocks;
       tx = r % a.tiles_x; r /= a.tiles_x;
@@ -385,20 +373,8 @@ struct TileIter {
     dty = d % a.tiles_y; d /= a.tiles_y;
     dn = d % a.N; dnb = d / a.N;
   }
-  __device__ __forceinline__ bool valid(const TcArgs& a) const { return t < (a.geom == 3 ? a.pix_tiles : a.total_tiles); }
+  __device__ __forceinline__ bool valid(const TcArgs& a) const { return t < a.total_tiles; }
   __device__ __forceinline__ void next(const TcArgs& a) {
-    if (a.geom == 3) {
-      if (++nb < a.n_nblocks) return;
-      nb = 0;
-      t += gridDim.x;
-      tx += dtx;
-      int c = 0;
-      if (tx >= a.tiles_x) { tx -= a.tiles_x; c = 1; }
-      ty += dty + c; c = 0;
-      if (ty >= a.tiles_y) { ty -= a.tiles_y; c = 1; }
-      n += dn + c;
-      return;
-    }
     t += gridDim.x;
     if (a.nb_fast) {
       nb += dnb;
@@ -463,7 +439,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& a, uint64_t* tfull, 
   const int wq = warp & 3;
   const int cgp = (warp - TC_EPI_WARP0) >> 2;
   const int row = wq * 32 + lane;                       // pixel within the tile (accumulator row)
-  const int tw = (a.geom == 1 || a.geom == 2) ? 8 : TC_TW;   // geom 3 keeps the 16-pixel-wide rows of geom 0
+  const int tw = a.geom ? 8 : TC_TW;
   const int py = row / tw, px = row % tw;
   const int nch = a.nblk >> 4;
   const int Cout = a.Cout, nblk = a.nblk, nacc = a.nacc, acc_slot = a.acc_slot;
@@ -653,7 +629,7 @@ __device__ __forceinline__ void lean_epilogue(const TcArgs& a, uint64_t* tfull, 
   const int wq = warp & 3;
   const int cgp = (warp - TC_EPI_WARP0) >> 2;
   const int row = wq * 32 + lane;
-  const int tw = (a.geom == 1 || a.geom == 2) ? 8 : TC_TW;   // geom 3 keeps the 16-pixel-wide rows of geom 0
+  const int tw = a.geom ? 8 : TC_TW;
   const int py = row / tw, px = row % tw;
   const int nch = a.nblk >> 4;
   const int nv8_total = a.Cout >> 3;                   // Cout % 8 == 0 on this path
@@ -807,24 +783,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           cur_g = g;
           cur_nb = nb;
         }
-        if (a.geom == 3) {
-          // the pixel tile's K chunks once (slot ch of the activation ring, freed by the LAST cout block's MMAs on that chunk),
-          // then this cout block's weights chunk by chunk through the weight ring
-          if (nb == 0) {
-            for (int ch = 0; ch < a.nchunks; ++ch) {
-              mbar_wait(&aempty[ch], aph_ ^ 1);
-              mbar_expect_tx_e(&afull[ch], (uint32_t)a.a_bytes);
-              tma_load_4d(stages + ch * a.a_slot, &tmA, &afull[ch], ch * 64, tx * TC_TW - pad, ty * a.tile_h - pad, n);
-            }
-            aph_ ^= 1;
-          }
-          for (int ch = 0; ch < a.nchunks; ++ch) {
-            mbar_wait(&empty[s], ph ^ 1);
-            mbar_expect_tx_e(&full[s], (uint32_t)a.b_bytes);
-            tma_load_5d(wring + s * a.stage_bytes, &tmB, &full[s], ch * 64, nb * a.nblk, 0, 0, g);
-            if (++s == a.nstages) { s = 0; ph ^= 1; }
-          }
-        } else if (a.geom == 2) {
+        if (a.geom == 2) {
           // Streamed weights with a deep pipeline: the 128->128 layers used 86 KB stages (one haloed copy per dx + the
           // three dy taps of the weights), i.e. a ring of TWO -- every stage load was exposed behind ~1,500 cycles of
           // MMAs (ncu: tensor pipe 59 % active).  Here the activations of a K chunk are ONE haloed copy
@@ -909,42 +868,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_wait(&tempty[as], aph ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * a.acc_slot);
-      if (a.geom == 3) {
-        // nmma == 1.  The K chunks of the pixel tile are waited for at its first cout block only and released at its last.
-        const uint32_t wring_u32 = stages_u32 + (uint32_t)(a.na_slots * a.a_slot);
-        const int nbi = ti.nb;
-        for (int ch = 0; ch < a.nchunks; ++ch) {
-          if (nbi == 0) {
-            mbar_wait(&afull[ch], g2_aph);
-            tc_fence_after();
-          }
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t al0 = desc_lo(stages_u32 + (uint32_t)(ch * a.a_slot));
-          const uint32_t bl = desc_lo(wring_u32 + (uint32_t)(s * a.stage_bytes));
-          const uint32_t acc0 = ch > 0 ? 1u : 0u;
-          const int ksteps = (ch == a.nchunks - 1) ? a.ksteps_last : 4;
-          for (int half = 0; half < a.halves; ++half) {
-            const uint32_t al = al0 + (uint32_t)half * (uint32_t)((TC_TH * TC_ROW_BYTES) >> 4);
-            const uint32_t td = tmem_d + (uint32_t)(half * a.acc_half);
-            switch (ksteps) {
-              case 4: umma_stage_ks1_k4(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
-              case 3: umma_stage_ks1_k3(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
-              case 2: umma_stage_ks1_k2(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
-              default: umma_stage_ks1_k1(td, al, bl, idesc, acc0, TC_DESC_HI, b_step); break;
-            }
-          }
-          umma_commit(&empty[s]);
-          if (nbi == a.n_nblocks - 1) umma_commit(&aempty[ch]);
-          if (++s == a.nstages) { s = 0; ph ^= 1; }
-        }
-        if (nbi == a.n_nblocks - 1) g2_aph ^= 1;
-        umma_commit(&tfull[as]);
-        as += nmma;
-        if (as >= a.nacc) { as -= a.nacc; aph ^= 1; }
-        ti.next(a);
-        continue;
-      }
       if (a.geom == 2) {
         // nmma == 1.  Per K chunk: wait for the haloed copy; per tap: wait for its weight stage, issue the K steps of both
         // 16x8 halves (left half: pixels 0..7 of each row, right half: 8..15 = the same copy 8 pixels further on),
@@ -1230,20 +1153,6 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   int smem_bytes = 1024 + TC_SMEM_HDR + a.bres_bytes + a.nstages * a.stage_bytes;
   a.a_slot = 0;
   a.na_slots = 0;
-  if (gemm_mode && halves == 2 && geom == 0 && a.nchunks <= TC_MAX_ASLOTS && getenv("FFSR_TC_GEOM3_OFF") == nullptr &&
-      (smem_avail - a.nchunks * a.a_bytes) / a.b_bytes >= 2) {
-    // activations of the pixel tile resident across its cout blocks: they were re-fetched from L2 for every block (32 KB of
-    // A beside every 16 KB weight stage); now only the weights stream
-    geom = 3;
-    a.geom = 3;
-    a.nb_fast = 0;
-    a.a_slot = a.a_bytes;                                      // 16 rows x 16 px x 128 B = 32 KB, 1 KB aligned
-    a.na_slots = a.nchunks;
-    a.stage_bytes = a.b_bytes;
-    a.nstages = (smem_avail - a.na_slots * a.a_slot) / a.stage_bytes;
-    if (a.nstages > TC_MAX_STAGES) a.nstages = TC_MAX_STAGES;
-    smem_bytes = 1024 + TC_SMEM_HDR + a.na_slots * a.a_slot + a.nstages * a.stage_bytes;
-  }
   if (geom == 2) {
     a.tile_h = 16;
     a.a_step16 = (18u * 128u) >> 4;
@@ -1276,7 +1185,6 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
   a.tiles_x = ceil_div(p.W, geom == 1 ? 8 : TC_TW);
   a.tiles_y = ceil_div(p.H, a.tile_h);
   a.total_tiles = (long long)a.tiles_x * a.tiles_y * p.N * a.n_nblocks;
-  a.pix_tiles = (long long)a.tiles_x * a.tiles_y * p.N;
   a.out = p.out; a.out_sN = p.out_sN; a.out_sY = p.out_sY; a.out_sX = p.out_sX;
   a.out_bf16 = p.out_dtype == FFSR_DT_BF16;
   a.bias = p.bias; a.act = p.act; a.epi = p.epi;
@@ -1292,8 +1200,7 @@ int ffsr_conv2d_tc(const ffsr_conv_params* pp, cudaStream_t stream) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
   }
-  const long long walk = geom == 3 ? a.pix_tiles : a.total_tiles;
-  const int grid = (int)(walk < num_sms ? walk : num_sms);
+  const int grid = (int)(a.total_tiles < num_sms ? a.total_tiles : num_sms);
   // tile-per-group epilogue: needs >= 8 accumulators in flight (N <= 64, single-half tiles) and enough tiles per CTA
   static const bool own_off = getenv("FFSR_TC_EPI_OWN0") != nullptr;
   static const bool erf_forced = getenv("FFSR_TC_GELU_ERF") != nullptr;
