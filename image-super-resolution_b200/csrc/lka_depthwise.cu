@@ -305,12 +305,20 @@ extern "C" int ffsr_dwconv_stage(const float* in, int N, int H, int W, int C, in
   if (kind == 0) {
     dim3 grid(C / cx, ceil_div((long)ceil_div(H, R5) * ceil_div(W, R5), ty), N);
     k_lka_dw5<float><<<grid, block, 0, stream>>>(in, H, W, C, bn_k, bn_d, w, out);
-  } else if (kind == 1) {
-    dim3 grid(C / cx, ceil_div((long)H * ceil_div(W, R21), ty), N);
-    k_lka_dw21<0, float><<<grid, block, 0, stream>>>(in, H, W, C, w, out);
   } else {
-    dim3 grid(C / cx, ceil_div((long)ceil_div(H, R21) * W, ty), N);
-    k_lka_dw21<1, float><<<grid, block, 0, stream>>>(in, H, W, C, w, out);
+    // the rolling-window passes of the inference chain (bit-identical, see k_lka_dw21_roll); strips of <= 256 outputs
+    const int L = kind == 1 ? W : H, lines = kind == 1 ? H : W;
+    const int ns = ceil_div(L, 256), strip = ceil_div(ceil_div(L, ns), 16) * 16;
+    dim3 grid(C / cx, ceil_div((long)lines * ns, ty), N);
+    if (kind == 1) {
+      if (C == 128) k_lka_dw21_roll<0, float, 128><<<grid, block, 0, stream>>>(in, H, W, C, w, out, strip, ns);
+      else if (C == 64) k_lka_dw21_roll<0, float, 64><<<grid, block, 0, stream>>>(in, H, W, C, w, out, strip, ns);
+      else k_lka_dw21_roll<0, float, 0><<<grid, block, 0, stream>>>(in, H, W, C, w, out, strip, ns);
+    } else {
+      if (C == 128) k_lka_dw21_roll<1, float, 128><<<grid, block, 0, stream>>>(in, H, W, C, w, out, strip, ns);
+      else if (C == 64) k_lka_dw21_roll<1, float, 64><<<grid, block, 0, stream>>>(in, H, W, C, w, out, strip, ns);
+      else k_lka_dw21_roll<1, float, 0><<<grid, block, 0, stream>>>(in, H, W, C, w, out, strip, ns);
+    }
   }
   return ffsr_check_launch("dwconv_stage");
 }
