@@ -142,3 +142,68 @@ def test_device_only_entry_points_refuse_cpu_tensors():
     m = isr_b200.CompleteEnhancedFusionSR(None).eval()
     with pytest.raises(RuntimeError, match="no CPU path"):
         fuse_tiled(m, torch.rand(1, 3, 16, 16), {k: torch.rand(1, 3, 64, 64) for k in ("drct", "grl", "nafnet", "mamba")}, None)
+
+
+def _unplane(planes: torch.Tensor, n: int, k: int) -> torch.Tensor:
+    """Inverse of pipeline._planes_bf16: [k/8][n][8] -> [n][k] (fp32)."""
+    return planes.float().view(k // 8, n, 8).permute(1, 0, 2).reshape(n, k)
+
+
+def test_token_chain_packing_is_layernorm_folded_into_the_linear():
+    """pack_token_attn / pack_token_ffn (csrc/token_chain.cu operands): with g = gamma o W rounded to bf16,
+    rstd * (x g^T - mean * colsum(g)) + (W beta + b) must equal Linear(LayerNorm(x)) up to the bf16 rounding of g, the q rows
+    carry the 1/sqrt(head_dim) = 1/4 of the scores, and the planes decode back to the matrices."""
+    from isr_b200.pipeline import pack_token_attn, pack_token_ffn
+    torch.manual_seed(1)
+    m = isr_b200.CompleteEnhancedFusionSR(None).eval()
+    co = m.collaborative
+    with torch.no_grad():
+        co.norm1.weight.uniform_(0.5, 1.5); co.norm1.bias.normal_(0, 0.2)
+        co.norm2.weight.uniform_(0.5, 1.5); co.norm2.bias.normal_(0, 0.2)
+    wa, pa = pack_token_attn(co)
+    g = _unplane(wa[:384 * 128], 384, 128).double()
+    wo = _unplane(wa[384 * 128:], 128, 128)
+    cs, bq, bo = pa[:384].double(), pa[384:768].double(), pa[768:]
+    assert torch.equal(wo, co.cross_attn.out_proj.weight.detach().to(torch.bfloat16).float())
+    assert torch.equal(bo, co.cross_attn.out_proj.bias.detach())
+    assert torch.allclose(cs, g.sum(1), atol=1e-5)
+    x = torch.randn(64, 128, dtype=torch.float64) * 0.8 + 0.3
+    mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
+    rstd = (var + 1e-5).rsqrt()
+    got = rstd * (x @ g.t() - mean * cs[None, :]) + bq[None, :]
+    ln = torch.nn.functional.layer_norm(x, (128,), co.norm1.weight.double(), co.norm1.bias.double(), 1e-5)
+    want = ln @ co.cross_attn.in_proj_weight.double().t() + co.cross_attn.in_proj_bias.double()
+    want[:, :128] *= 0.25
+    assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()          # bf16 rounding of g only
+    wf, pf = pack_token_ffn(co)
+    g0 = _unplane(wf[:256 * 128], 256, 128).double()
+    w2 = _unplane(wf[256 * 128:], 128, 256)
+    assert torch.equal(w2, co.ffn[2].weight.detach().to(torch.bfloat16).float())
+    got = rstd * (x @ g0.t() - mean * pf[:256].double()[None, :]) + pf[256:512].double()[None, :]
+    ln2 = torch.nn.functional.layer_norm(x, (128,), co.norm2.weight.double(), co.norm2.bias.double(), 1e-5)
+    want = ln2 @ co.ffn[0].weight.double().t() + co.ffn[0].bias.double()
+    assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()
+    assert torch.equal(pf[512:], co.ffn[2].bias.detach())
+
+
+def test_selector_and_align_blobs_follow_the_kernel_layouts():
+    from isr_b200.pipeline import pack_selector, pack_align_tokens, EXPERT_ORDER
+    torch.manual_seed(2)
+    m = isr_b200.CompleteEnhancedFusionSR(None).eval()
+    ds = m.dynamic_selector
+    blob = pack_selector(ds)
+    # csrc/selector.cu: d0w(864) d0b(32) d2w(9216) d2b(32) d4w(288) d4b(1+3) g0w g0b g2w g2b g4w(128) g4b(4)
+    assert blob.numel() == 2 * (864 + 32 + 9216 + 32) + 288 + 4 + 128 + 4
+    o = 864 + 32
+    w2 = blob[o:o + 9216].view(9, 32, 32)                               # [tap][ci][co]
+    assert torch.equal(w2[4], ds.difficulty_net[2].weight.detach()[:, :, 1, 1].t().contiguous())
+    assert torch.equal(blob[o + 9216:o + 9216 + 32], ds.difficulty_net[2].bias.detach())
+    assert torch.equal(blob[-4:], ds.gate_net[4].bias.detach())
+    wb, bb = pack_align_tokens(m.collaborative)
+    assert wb.numel() == 4 * 24 * 128 * 8 and tuple(bb.shape) == (4, 128)
+    for e, n in enumerate(EXPERT_ORDER):
+        l = m.collaborative.align_layers[n]
+        w = _unplane(wb[e * 24 * 128 * 8:(e + 1) * 24 * 128 * 8], 128, 192)
+        cin = l.weight.shape[1]
+        assert torch.equal(w[:, :cin], l.weight.detach().reshape(128, cin).to(torch.bfloat16).float())
+        assert torch.count_nonzero(w[:, cin:]) == 0                      # K zero-padded to 192
