@@ -1205,6 +1205,12 @@ def forward_breakdown(rows, H, W, hbm_peak, tensor_peak):
         else:
             ph = "P7b edge"
         phases[ph] += ms
+        if lab.startswith("ffsr_resize_nhwc"):
+            kern["resize_hr"] = ms                           # last call = the 2x -> HR upsampling into the stage-3 concat
+        if lab.startswith("ffsr_spatial_gate"):
+            kern["spatial_gate_hr"] = ms                     # last call = stage 3 (HR, 32 channels)
+        if lab.startswith("ffsr_blend"):
+            kern["blend_hr"] = ms
         if lab.startswith("ffsr_fft"):
             kern["fft_bands"] = ms
         if lab.startswith("ffsr_crossband_attention"):
@@ -1224,9 +1230,24 @@ def forward_breakdown(rows, H, W, hbm_peak, tensor_peak):
         b = 3 * 4 * 3 * P
         hbm.append({"kernel": "FFT low/high bands (staged shared-memory FFT)", "algorithmic_bytes": b, "ms": kern["fft_bands"],
                     "achieved_gb_s": b / kern["fft_bands"] / 1e6, "frac_of_hbm": b / kern["fft_bands"] / 1e6 / hbm_peak})
+    if "resize_hr" in kern:    # 64 bf16 channels: a quarter of the HR pixels in, every HR pixel out
+        b = 64 * 2 * (4 + 16) * P
+        hbm.append({"kernel": "x2 bilinear upsampling into the stage-3 concat (64 ch bf16)", "algorithmic_bytes": b, "ms": kern["resize_hr"],
+                    "achieved_gb_s": b / kern["resize_hr"] / 1e6, "frac_of_hbm": b / kern["resize_hr"] / 1e6 / hbm_peak})
+    if "spatial_gate_hr" in kern:   # 32 bf16 channels in place
+        b = 32 * 2 * 2 * 16 * P
+        hbm.append({"kernel": "SpatialGate at HR (32 ch bf16, in place)", "algorithmic_bytes": b, "ms": kern["spatial_gate_hr"],
+                    "achieved_gb_s": b / kern["spatial_gate_hr"] / 1e6, "frac_of_hbm": b / kern["spatial_gate_hr"] / 1e6 / hbm_peak})
+    if "blend_hr" in kern:     # 72 B per HR pixel (hier + 12 expert planes in, fused fp32 out) + the 32 B bf16 copy for the refine input
+        b = (72 + 32) * 16 * P
+        hbm.append({"kernel": "P5b / P6 blend at HR", "algorithmic_bytes": b, "ms": kern["blend_hr"],
+                    "achieved_gb_s": b / kern["blend_hr"] / 1e6, "frac_of_hbm": b / kern["blend_hr"] / 1e6 / hbm_peak})
     out["memory_bound_kernels"] = hbm
     if hbm:
         out["worst_memory_bound_frac"] = min(h["frac_of_hbm"] for h in hbm)
+        big = [h["frac_of_hbm"] for h in hbm if h["ms"] >= 0.1]
+        if big:
+            out["worst_memory_bound_frac_of_kernels_over_0.1ms"] = min(big)
     return out
 
 
