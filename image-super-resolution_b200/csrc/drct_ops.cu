@@ -4,6 +4,7 @@
 //
 // STATUS: exercised on a B200 through `isr_b200.drct.DRCT.forward` (parity <= 1e-4 against the reference class's output,
 // tests/test_gpu_drct.py); simple grid-stride kernels, not yet timed against the HBM roof.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/ffsr_b200.h"
 
@@ -46,6 +47,45 @@ __global__ void __launch_bounds__(256) k_layernorm_strided(const TI* __restrict_
     const float rstd = rsqrtf(v / (float)C + 1e-5f);
     TO* yr = y + r * y_pitch;
     for (int c = lane; c < C; c += 32) stf<TO>(yr, c, (ldf<TI>(xr, c) - mean) * rstd * __ldg(w + c) + __ldg(b + c));
+  }
+}
+
+// fp32 rows -> bf16 rows, four channels per lane and step (16-byte loads, 8-byte stores): the DRCT-L LayerNorms in the bf16 mode
+// (C, both pitches and both bases multiples of 4 elements).  Same two-pass statistics as above; the row is read from L1 on
+// the second and third pass.
+__global__ void __launch_bounds__(256) k_layernorm_strided_v4(const float* __restrict__ x, long rows, int C, long x_pitch,
+                                                              const float* __restrict__ w, const float* __restrict__ b,
+                                                              __nv_bfloat16* __restrict__ y, long y_pitch) {
+  const int lane = threadIdx.x & 31;
+  const int C4 = C >> 2;
+  const long warps = (long)gridDim.x * (blockDim.x >> 5);
+  for (long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + r * x_pitch);
+    float s = 0.f;
+    for (int c = lane; c < C4; c += 32) {
+      const float4 v = xr[c];
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+    for (int c = lane; c < C4; c += 32) {
+      const float4 v = xr[c];
+      const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+      q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + 1e-5f);
+    uint2* yr = reinterpret_cast<uint2*>(y + r * y_pitch);
+    for (int c = lane; c < C4; c += 32) {
+      const float4 v = xr[c];
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + c), bv = __ldg(reinterpret_cast<const float4*>(b) + c);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf((v.x - mean) * rstd, wv.x, bv.x), fmaf((v.y - mean) * rstd, wv.y, bv.y));
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf((v.z - mean) * rstd, wv.z, bv.z), fmaf((v.w - mean) * rstd, wv.w, bv.w));
+      yr[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
   }
 }
 
@@ -119,6 +159,9 @@ extern "C" int ffsr_layernorm_strided(const void* x, long rows, int C, long x_pi
   const bool ib = in_dtype == FFSR_DT_BF16, ob = out_dtype == FFSR_DT_BF16;
   if (ib && ob) k_layernorm_strided<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, rows, C, x_pitch, w, b, (__nv_bfloat16*)y, y_pitch);
   else if (ib) k_layernorm_strided<__nv_bfloat16, float><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, rows, C, x_pitch, w, b, (float*)y, y_pitch);
+  else if (ob && (C & 3) == 0 && (x_pitch & 3) == 0 && (y_pitch & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 7) == 0 &&
+           ((uintptr_t)w & 15) == 0 && ((uintptr_t)b & 15) == 0 && getenv("FFSR_LN_SCALAR") == nullptr)
+    k_layernorm_strided_v4<<<grid, 256, 0, stream>>>((const float*)x, rows, C, x_pitch, w, b, (__nv_bfloat16*)y, y_pitch);
   else if (ob) k_layernorm_strided<float, __nv_bfloat16><<<grid, 256, 0, stream>>>((const float*)x, rows, C, x_pitch, w, b, (__nv_bfloat16*)y, y_pitch);
   else k_layernorm_strided<float, float><<<grid, 256, 0, stream>>>((const float*)x, rows, C, x_pitch, w, b, (float*)y, y_pitch);
   return ffsr_check_launch("k_layernorm_strided");
