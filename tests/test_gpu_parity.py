@@ -431,6 +431,29 @@ def test_pipelined_serving_matches_direct_calls():
         assert torch.equal(o, ref.cpu())
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_concurrent_fusion_matches_direct_calls(precision):
+    """serving.ConcurrentFusion (several images in flight on several streams, one engine per stream) returns bit for bit what
+    forward_with_precomputed returns image by image, including images of different sizes in one run."""
+    dev = _cuda()
+    from isr_b200.serving import ConcurrentFusion
+    m = _model(True).to(dev)
+    m.precision = precision
+    items = []
+    for seed, (h, w) in enumerate([(24, 32), (40, 56), (24, 32), (17, 23), (40, 56), (24, 32), (33, 20)]):
+        lr, imgs, fts, _ = O.synthetic_inputs(1, h, w, seed=200 + seed)
+        items.append((lr.to(dev), {k: v.to(dev) for k, v in imgs.items()}, {k: v.to(dev) for k, v in fts.items()}))
+    got = {}
+    conc = ConcurrentFusion(m, ways=3, device=dev)
+    for _ in range(2):                               # second pass: warm workspaces, other way for each image size
+        conc.run(items, sink=lambda i, sr: got.__setitem__(i, sr.clone()))
+        torch.cuda.synchronize()
+        for i, (lr, imgs, fts) in enumerate(items):
+            assert torch.equal(got[i], m.forward_with_precomputed(lr, imgs, fts)), i
+        items = items[1:] + items[:1]
+    m.precision = "fp32"
+
+
 def test_tta_fusion_matches_per_variant_loop():
     """serving.fuse_tta (two batched forwards, reverse + mean on the device) against the reference's loop:
     one forward per variant, reverse_tta, CPU mean, clamp (scripts/generate_fast_submission.py:190-250)."""
